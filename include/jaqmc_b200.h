@@ -1,0 +1,151 @@
+/* jaqmc_b200 -- C ABI of the B200-native JaQMC local-energy + sampling hot path.
+ *
+ * The reference (bytedance/jaqmc) has no native code and no operator ABI: its hot path is Python/JAX
+ * behind three protocols (Wavefunction, SamplerLike, Estimator).  This header is the C boundary a
+ * thin XLA-FFI shim (jax.ffi.ffi_call) or ctypes binds; each entry point names the
+ * reference interface whose per-walker work it replaces.  All citations are relative to the
+ * reference's src/jaqmc/.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer to float32 unless stated; arrays are dense, row-major;
+ *   - the caller (XLA / torch) owns every buffer including the workspace; the library never allocates,
+ *     frees, retains a pointer past return, or synchronises: it only enqueues on `stream`;
+ *   - walkers are independent units: `n_walkers` is the local shard (walker axis = axis 0);
+ *   - parameters keep the reference's Flax layouts (Dense kernel (in,out), DenseGeneral kernel
+ *     (in, ndets, n), envelope pi/sigma (n_orb, n_atoms, ndets));
+ *   - functions return 0 on success, a JAQMC_ERR_* code otherwise; jaqmc_b200_last_error() returns the
+ *     message (thread-local).  Numerical failure (singular determinant) is reported in-band as
+ *     -inf / NaN exactly like jnp.linalg.slogdet, never as an error code;
+ *   - there is no CPU path: the library is built for sm_100a only.
+ */
+#ifndef JAQMC_B200_H
+#define JAQMC_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define JAQMC_OK 0
+#define JAQMC_ERR_INVALID_ARGUMENT 1
+#define JAQMC_ERR_WORKSPACE_TOO_SMALL 2
+#define JAQMC_ERR_CUDA 3
+#define JAQMC_ERR_UNSUPPORTED 4
+
+#define JAQMC_MAX_LAYERS 8
+
+/* Envelope types: wavefunction/output/envelope.py:18-40 (EnvelopeType). */
+#define JAQMC_ENVELOPE_ISOTROPIC 0
+#define JAQMC_ENVELOPE_ABS_ISOTROPIC 1
+#define JAQMC_ENVELOPE_NULL 2
+
+/* Wavefunction kinds (one descriptor type per reference class). */
+#define JAQMC_WF_FERMINET 1 /* app/molecule/wavefunction/ferminet.py:21-96  FermiNetWavefunction */
+#define JAQMC_WF_LAPNET 2   /* app/molecule/wavefunction/lapnet.py          LapNetWavefunction   */
+#define JAQMC_WF_PSIFORMER 3 /* app/molecule/wavefunction/psiformer.py      PsiformerWavefunction */
+#define JAQMC_WF_SOLID_FERMINET 4 /* app/solid/wavefunction.py:91-147       SolidWavefunction    */
+#define JAQMC_WF_HYDROGEN 5 /* app/hydrogen_atom.py:28-35                   HydrogenAtom          */
+
+typedef void* jaqmc_stream_t; /* cudaStream_t */
+
+/* ---- FermiNet ---------------------------------------------------------------------------------
+ * Fields mirror FermiNetWavefunction's dataclass fields (ferminet.py:43-51) plus the system sizes. */
+typedef struct {
+  int32_t n_up, n_dn;     /* nspins */
+  int32_t n_atoms;
+  int32_t ndets;
+  int32_t n_layers;       /* len(hidden_dims_single) */
+  int32_t hidden_single[JAQMC_MAX_LAYERS];
+  int32_t hidden_double[JAQMC_MAX_LAYERS];
+  int32_t envelope_type;  /* JAQMC_ENVELOPE_* */
+  int32_t orbitals_spin_split;
+} jaqmc_ferminet_config;
+
+/* Leaves of the Flax tree `params/…`.  backbone_layer/Dense_{2l} is single layer l,
+ * Dense_{2l+1} double layer l (backbone/ferminet.py:37-43); only n_layers-1 double layers exist. */
+typedef struct {
+  const float* single_kernel[JAQMC_MAX_LAYERS]; /* (fan_in_l, hidden_single[l]) */
+  const float* single_bias[JAQMC_MAX_LAYERS];   /* (hidden_single[l],) */
+  const float* double_kernel[JAQMC_MAX_LAYERS]; /* (d2_{l-1}, hidden_double[l]) */
+  const float* double_bias[JAQMC_MAX_LAYERS];
+  const float* orbital_kernel[2]; /* orbital_layer/SplitChannelDense_0/DenseGeneral_{0,1}/kernel (hidden, ndets, n);
+                                     [1] is NULL when not spin-split (single DenseGeneral_0) */
+  const float* env_pi[2];         /* envelope_layer/{_env_up,_env_down}/pi (n, n_atoms, ndets); [1] NULL -> `_env` */
+  const float* env_sigma[2];
+} jaqmc_ferminet_params;
+
+/* ---- generic wavefunction descriptor ---------------------------------------------------------- */
+typedef struct {
+  int32_t kind;       /* JAQMC_WF_* */
+  const void* config; /* HOST pointer to the kind's config struct */
+  const void* params; /* HOST pointer to the kind's params struct (of device pointers) */
+} jaqmc_wavefunction;
+
+/* System data replicated across walkers: MoleculeData.atoms / charges (app/molecule/data.py:46-53). */
+typedef struct {
+  const float* atoms;   /* (n_atoms, 3) */
+  const float* charges; /* (n_atoms,)  may be NULL where unused */
+  int32_t n_atoms;
+} jaqmc_system;
+
+/* Workspace (bytes) that lets a call process all `n_walkers` walkers in one pass.  A smaller workspace is legal:
+ * the library then tiles the walker axis, as long as one walker fits (else JAQMC_ERR_WORKSPACE_TOO_SMALL).
+ * `track` = 0 for log|psi| only, 1 for value + gradient + Laplacian. */
+size_t jaqmc_b200_workspace_bytes(const jaqmc_wavefunction* wf, int64_t n_walkers, int track);
+
+/* Replaces vmap(wf.logpsi / wf.phase_logpsi) over the walker axis
+ * (sampler/base.py:136-138; app/molecule/wavefunction/ferminet.py:98-124).
+ *   electrons (n_walkers, n, 3) -> logpsi (n_walkers,), sign (n_walkers,) in {-1, 0, +1}. */
+int jaqmc_b200_logpsi(const jaqmc_wavefunction* wf, const jaqmc_system* sys, const float* electrons,
+                      int64_t n_walkers, float* logpsi, float* sign, void* workspace, size_t workspace_bytes,
+                      jaqmc_stream_t stream);
+
+/* Replaces the estimator half of EvaluationWorkStage.compute_step for the energy keys
+ * (workflow/stage/evaluation.py:190-192): EuclideanKinetic in forward_laplacian mode
+ * (estimator/kinetic/euclidean.py:114-135, laplacian/interpreter.py:392-438), the potential
+ * (app/molecule/hamiltonian.py:9-22) and TotalEnergy (estimator/total_energy.py:36-60), vmapped over walkers.
+ * Outputs (any may be NULL except logpsi/sign):
+ *   grad (n_walkers, 3n) = d log|psi| / d r,   lap (n_walkers,) = laplacian of log|psi|,
+ *   e_kin = -1/2 (lap + |grad|^2),  e_pot,  e_loc = e_kin + e_pot,
+ *   sums (3,) += {sum e_loc, sum e_loc^2, count of finite e_loc} over this call's walkers (the per-device partial
+ *   sums that precede the pmean of estimator/base.py:27-53); the caller zeroes it. */
+int jaqmc_b200_local_energy(const jaqmc_wavefunction* wf, const jaqmc_system* sys, const float* electrons,
+                            int64_t n_walkers, float* logpsi, float* sign, float* grad, float* lap, float* e_kin,
+                            float* e_pot, float* e_loc, float* sums, void* workspace, size_t workspace_bytes,
+                            jaqmc_stream_t stream);
+
+/* Replaces potential_energy (app/molecule/hamiltonian.py:9-22) vmapped over walkers. */
+int jaqmc_b200_coulomb(const jaqmc_system* sys, const float* electrons, int64_t n_walkers, int32_t n_electrons,
+                       float* e_pot, jaqmc_stream_t stream);
+
+/* Replaces MCMCSampler.step's fori_loop of _mh_update (sampler/mcmc.py:96-137,167-180) for `n_steps` all-electron
+ * moves with host-supplied noise:
+ *   electrons (n_walkers, n, 3) in/out; logpsi (n_walkers,) in/out (log|psi| of `electrons`; computed on entry
+ *   when `logpsi_valid` == 0); normals (n_steps, n_walkers, n, 3); uniforms (n_steps, n_walkers) in (0,1);
+ *   stddev (1,) device scalar; n_accept (1,) += accepted moves (caller zeroes); accepted (n_steps, n_walkers) u8 or NULL.
+ * accept iff 2*(logpsi' - logpsi) > log(u)  (sampler/base.py:173-178 supplies the factor 2). */
+int jaqmc_b200_mh_step(const jaqmc_wavefunction* wf, const jaqmc_system* sys, float* electrons, float* logpsi,
+                       int32_t logpsi_valid, const float* normals, const float* uniforms, const float* stddev,
+                       int32_t n_steps, int64_t n_walkers, float* n_accept, uint8_t* accepted, void* workspace,
+                       size_t workspace_bytes, jaqmc_stream_t stream);
+
+/* Building blocks of the MH step, exported for samplers that drive their own loop
+ * (sampler/mcmc.py:53-54 gaussian_proposal; :128-137 accept/select). */
+int jaqmc_b200_mh_propose(const float* x1, const float* normals, const float* stddev, float* x2, int64_t count,
+                          jaqmc_stream_t stream);
+int jaqmc_b200_mh_accept(float* x1, const float* x2, float* logprob1, const float* logprob2, const float* uniforms,
+                         int64_t n_walkers, int32_t row, float* n_accept, uint8_t* accepted, jaqmc_stream_t stream);
+
+/* Number of kernels the library has launched on this thread since the last reset (bench.py's gpu_launches). */
+int64_t jaqmc_b200_launch_count(void);
+void jaqmc_b200_reset_launch_count(void);
+
+const char* jaqmc_b200_last_error(void);
+const char* jaqmc_b200_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* JAQMC_B200_H */

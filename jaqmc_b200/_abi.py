@@ -1,0 +1,114 @@
+"""ctypes mirror of ``include/jaqmc_b200.h`` (structures + prototypes).
+
+``bind(cdll)`` attaches argument / result types to a loaded library.  The product loads the CUDA build
+through ``jaqmc_b200._lib``; the CPU test-suite binds the host-emulation build (``tests/emu``) with the same
+prototypes so the two cannot drift apart.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+
+MAX_LAYERS = 8
+
+OK = 0
+ERR_INVALID_ARGUMENT = 1
+ERR_WORKSPACE_TOO_SMALL = 2
+ERR_CUDA = 3
+ERR_UNSUPPORTED = 4
+
+ENVELOPE = {"isotropic": 0, "abs_isotropic": 1, "null": 2}
+
+WF_FERMINET = 1
+WF_LAPNET = 2
+WF_PSIFORMER = 3
+WF_SOLID_FERMINET = 4
+WF_HYDROGEN = 5
+
+FloatP = C.c_void_p  # device (or, for the emulation build, host) pointer to float32
+
+
+class FerminetConfig(C.Structure):
+    _fields_ = [
+        ("n_up", C.c_int32),
+        ("n_dn", C.c_int32),
+        ("n_atoms", C.c_int32),
+        ("ndets", C.c_int32),
+        ("n_layers", C.c_int32),
+        ("hidden_single", C.c_int32 * MAX_LAYERS),
+        ("hidden_double", C.c_int32 * MAX_LAYERS),
+        ("envelope_type", C.c_int32),
+        ("orbitals_spin_split", C.c_int32),
+    ]
+
+
+class FerminetParams(C.Structure):
+    _fields_ = [
+        ("single_kernel", FloatP * MAX_LAYERS),
+        ("single_bias", FloatP * MAX_LAYERS),
+        ("double_kernel", FloatP * MAX_LAYERS),
+        ("double_bias", FloatP * MAX_LAYERS),
+        ("orbital_kernel", FloatP * 2),
+        ("env_pi", FloatP * 2),
+        ("env_sigma", FloatP * 2),
+    ]
+
+
+class Wavefunction(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("config", C.c_void_p), ("params", C.c_void_p)]
+
+
+class System(C.Structure):
+    _fields_ = [("atoms", FloatP), ("charges", FloatP), ("n_atoms", C.c_int32)]
+
+
+PROTOTYPES = {
+    "jaqmc_b200_workspace_bytes": (C.c_size_t, [C.POINTER(Wavefunction), C.c_int64, C.c_int]),
+    "jaqmc_b200_logpsi": (
+        C.c_int,
+        [C.POINTER(Wavefunction), C.POINTER(System), FloatP, C.c_int64, FloatP, FloatP, C.c_void_p, C.c_size_t,
+         C.c_void_p],
+    ),
+    "jaqmc_b200_local_energy": (
+        C.c_int,
+        [C.POINTER(Wavefunction), C.POINTER(System), FloatP, C.c_int64, FloatP, FloatP, FloatP, FloatP, FloatP,
+         FloatP, FloatP, FloatP, C.c_void_p, C.c_size_t, C.c_void_p],
+    ),
+    "jaqmc_b200_coulomb": (C.c_int, [C.POINTER(System), FloatP, C.c_int64, C.c_int32, FloatP, C.c_void_p]),
+    "jaqmc_b200_mh_step": (
+        C.c_int,
+        [C.POINTER(Wavefunction), C.POINTER(System), FloatP, FloatP, C.c_int32, FloatP, FloatP, FloatP, C.c_int32,
+         C.c_int64, FloatP, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p],
+    ),
+    "jaqmc_b200_mh_propose": (C.c_int, [FloatP, FloatP, FloatP, FloatP, C.c_int64, C.c_void_p]),
+    "jaqmc_b200_mh_accept": (
+        C.c_int,
+        [FloatP, FloatP, FloatP, FloatP, FloatP, C.c_int64, C.c_int32, FloatP, C.c_void_p, C.c_void_p],
+    ),
+    "jaqmc_b200_launch_count": (C.c_int64, []),
+    "jaqmc_b200_reset_launch_count": (None, []),
+    "jaqmc_b200_last_error": (C.c_char_p, []),
+    "jaqmc_b200_version": (C.c_char_p, []),
+}
+
+
+def bind(cdll: C.CDLL) -> C.CDLL:
+    """Attach prototypes; raises ``AttributeError`` if the library lacks a declared symbol."""
+    for name, (restype, argtypes) in PROTOTYPES.items():
+        fn = getattr(cdll, name)
+        fn.restype = restype
+        fn.argtypes = argtypes
+    return cdll
+
+
+class JaqmcB200Error(RuntimeError):
+    """A C-ABI call returned a non-zero status."""
+
+    def __init__(self, code: int, message: str):
+        super().__init__(f"jaqmc_b200 error {code}: {message}")
+        self.code = code
+
+
+def check(cdll: C.CDLL, rc: int) -> None:
+    if rc != OK:
+        raise JaqmcB200Error(rc, cdll.jaqmc_b200_last_error().decode())

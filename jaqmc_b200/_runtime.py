@@ -1,0 +1,150 @@
+"""Thin call layer over the C ABI: pointer marshalling, workspace ownership, stream selection.
+
+PyTorch is used for device memory and streams only.  ``Runtime`` is parameterised by the bound library so
+that the CPU test-suite can drive the host-emulation build of the same kernels (tests/emu) through the very
+same marshalling code; the product singleton ``runtime()`` binds the CUDA library and only accepts CUDA tensors.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _abi
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+class Runtime:
+    def __init__(self, cdll, device, workspace_limit_bytes: int | None = None, _emulation: bool = False):
+        self.lib = cdll
+        self.device = torch.device(device)
+        ver = cdll.jaqmc_b200_version()
+        if (b"EMULATION" in ver) != bool(_emulation):
+            raise RuntimeError(f"jaqmc_b200: refusing library {ver!r} (emulation builds are test infrastructure only)")
+        if not _emulation and self.device.type != "cuda":
+            raise RuntimeError("jaqmc_b200: the product path runs on CUDA devices only")
+        self.workspace_limit_bytes = workspace_limit_bytes
+        self._ws = None
+
+    # ---- plumbing -------------------------------------------------------------------------------
+    def _stream(self):
+        if self.device.type == "cuda":
+            return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        return C.c_void_p(0)
+
+    def _check_tensor(self, t, name, dtype=torch.float32):
+        same = t.device.type == self.device.type and (
+            self.device.type != "cuda" or self.device.index is None or t.device.index == self.device.index)
+        if not same:
+            raise ValueError(f"{name}: tensor on {t.device}, runtime on {self.device}")
+        if t.dtype != dtype or not t.is_contiguous():
+            raise ValueError(f"{name}: expected contiguous {dtype}, got {t.dtype} contiguous={t.is_contiguous()}")
+
+    def workspace(self, nbytes: int):
+        if self._ws is None or self._ws.numel() < nbytes:
+            self._ws = None
+            self._ws = torch.empty(int(nbytes), dtype=torch.uint8, device=self.device)
+        return self._ws
+
+    def workspace_bytes(self, wf, n_walkers: int, track: bool) -> int:
+        need = int(self.lib.jaqmc_b200_workspace_bytes(C.byref(wf.struct), int(n_walkers), int(track)))
+        if need == 0 and n_walkers > 0:
+            raise _abi.JaqmcB200Error(_abi.ERR_INVALID_ARGUMENT, self.lib.jaqmc_b200_last_error().decode())
+        return need
+
+    def _ws_for(self, wf, n_walkers, track):
+        need = self.workspace_bytes(wf, n_walkers, track)
+        if self.workspace_limit_bytes is not None:
+            need = min(need, self.workspace_limit_bytes)
+        elif self.device.type == "cuda":
+            free, _ = torch.cuda.mem_get_info(self.device)
+            held = self._ws.numel() if self._ws is not None else 0
+            need = min(need, int(0.8 * (free + held)))
+        return self.workspace(max(need, 1 << 16))
+
+    # ---- entry points ---------------------------------------------------------------------------
+    def logpsi(self, wf, system, electrons):
+        """``electrons`` (W, n, 3) -> (logpsi (W,), sign (W,))."""
+        self._check_tensor(electrons, "electrons")
+        W = electrons.shape[0]
+        logpsi = torch.empty(W, dtype=torch.float32, device=self.device)
+        sign = torch.empty(W, dtype=torch.float32, device=self.device)
+        ws = self._ws_for(wf, W, False)
+        rc = self.lib.jaqmc_b200_logpsi(C.byref(wf.struct), C.byref(system.struct), _ptr(electrons), W, _ptr(logpsi),
+                                        _ptr(sign), _ptr(ws), ws.numel(), self._stream())
+        _abi.check(self.lib, rc)
+        return logpsi, sign
+
+    def local_energy(self, wf, system, electrons, sums=None):
+        """Returns a dict with logpsi, sign, grad (W,3n), lap, e_kin, e_pot, e_loc."""
+        self._check_tensor(electrons, "electrons")
+        W, n = electrons.shape[0], electrons.shape[1]
+        f = lambda *s: torch.empty(*s, dtype=torch.float32, device=self.device)  # noqa: E731
+        out = dict(logpsi=f(W), sign=f(W), grad=f(W, 3 * n), lap=f(W), e_kin=f(W), e_pot=f(W), e_loc=f(W))
+        ws = self._ws_for(wf, W, True)
+        rc = self.lib.jaqmc_b200_local_energy(
+            C.byref(wf.struct), C.byref(system.struct), _ptr(electrons), W, _ptr(out["logpsi"]), _ptr(out["sign"]),
+            _ptr(out["grad"]), _ptr(out["lap"]), _ptr(out["e_kin"]), _ptr(out["e_pot"]), _ptr(out["e_loc"]),
+            _ptr(sums), _ptr(ws), ws.numel(), self._stream())
+        _abi.check(self.lib, rc)
+        return out
+
+    def coulomb(self, system, electrons):
+        self._check_tensor(electrons, "electrons")
+        W, n = electrons.shape[0], electrons.shape[1]
+        e_pot = torch.empty(W, dtype=torch.float32, device=self.device)
+        rc = self.lib.jaqmc_b200_coulomb(C.byref(system.struct), _ptr(electrons), W, n, _ptr(e_pot), self._stream())
+        _abi.check(self.lib, rc)
+        return e_pot
+
+    def mh_step(self, wf, system, electrons, logpsi, normals, uniforms, stddev, logpsi_valid=True,
+                record_accepts=False):
+        """In-place MH sub-steps on ``electrons`` / ``logpsi``; returns (n_accept (1,), accepted u8 (S,W) or None)."""
+        for t, nm in ((electrons, "electrons"), (logpsi, "logpsi"), (normals, "normals"), (uniforms, "uniforms"),
+                      (stddev, "stddev")):
+            self._check_tensor(t, nm)
+        S, W = normals.shape[0], electrons.shape[0]
+        if tuple(normals.shape) != (S, *electrons.shape) or tuple(uniforms.shape) != (S, W):
+            raise ValueError(f"mh_step: normals {tuple(normals.shape)} / uniforms {tuple(uniforms.shape)} do not match "
+                             f"electrons {tuple(electrons.shape)}")
+        n_accept = torch.zeros(1, dtype=torch.float32, device=self.device)
+        accepted = torch.empty(S, W, dtype=torch.uint8, device=self.device) if record_accepts else None
+        ws = self._ws_for(wf, W, False)
+        rc = self.lib.jaqmc_b200_mh_step(
+            C.byref(wf.struct), C.byref(system.struct), _ptr(electrons), _ptr(logpsi), int(bool(logpsi_valid)),
+            _ptr(normals), _ptr(uniforms), _ptr(stddev), S, W, _ptr(n_accept), _ptr(accepted), _ptr(ws), ws.numel(),
+            self._stream())
+        _abi.check(self.lib, rc)
+        return n_accept, accepted
+
+    def launch_count(self) -> int:
+        return int(self.lib.jaqmc_b200_launch_count())
+
+    def reset_launch_count(self) -> None:
+        self.lib.jaqmc_b200_reset_launch_count()
+
+
+_runtimes: dict = {}
+
+
+def runtime(device=None) -> Runtime:
+    """Product runtime for a CUDA device (default: current device).  Raises when the CUDA library is missing."""
+    from ._lib import cuda_library
+
+    if device is None:
+        if not torch.cuda.is_available():
+            raise RuntimeError("jaqmc_b200: no CUDA device available; there is no CPU fallback")
+        device = torch.device("cuda", torch.cuda.current_device())
+    device = torch.device(device)
+    if device.type != "cuda":
+        raise RuntimeError(f"jaqmc_b200: device {device} is not a CUDA device; there is no CPU fallback")
+    if device.index is None:
+        device = torch.device("cuda", torch.cuda.current_device())
+    key = device.index
+    if key not in _runtimes:
+        _runtimes[key] = Runtime(cuda_library(), device)
+    return _runtimes[key]

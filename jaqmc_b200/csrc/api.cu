@@ -1,0 +1,281 @@
+// C-ABI entry points (include/jaqmc_b200.h): argument validation, walker tiling over the caller-owned
+// workspace, and the glue kernels (local-energy finalisation, MH bookkeeping).
+#include <cstdarg>
+
+#include "wf.cuh"
+
+thread_local long long jq_launch_counter = 0;
+static thread_local char jq_err[512] = "";
+
+void jq_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(jq_err, sizeof(jq_err), fmt, ap);
+  va_end(ap);
+}
+
+#ifdef JAQMC_HOST_EMU
+#include <vector>
+thread_local jq_dim3 threadIdx, blockIdx, blockDim, gridDim;
+thread_local unsigned char* jq_emu_dyn_smem = nullptr;
+static thread_local std::vector<unsigned char> jq_emu_smem_store;
+void jq_emu_set_smem(size_t bytes) {
+  if (jq_emu_smem_store.size() < bytes + 64) jq_emu_smem_store.resize(bytes + 64);
+  jq_emu_dyn_smem = jq_emu_smem_store.data();
+}
+#endif
+
+// ------------------------------------------------------------------------------------------------
+// per-kind dispatch
+// ------------------------------------------------------------------------------------------------
+static int wf_n_electrons(const jaqmc_wavefunction* wf) {
+  switch (wf->kind) {
+    case JAQMC_WF_FERMINET: {
+      auto* c = (const jaqmc_ferminet_config*)wf->config;
+      return c->n_up + c->n_dn;
+    }
+    default:
+      return -1;
+  }
+}
+
+static size_t wf_ws_bytes(const jaqmc_wavefunction* wf, long long W, int track) {
+  switch (wf->kind) {
+    case JAQMC_WF_FERMINET:
+      return jq_ferminet_ws_bytes((const jaqmc_ferminet_config*)wf->config, W, track);
+    default:
+      return 0;
+  }
+}
+
+static int wf_forward(const jaqmc_wavefunction* wf, const jaqmc_system* sys, const float* electrons, long long W,
+                      int track, void* ws, size_t ws_bytes, JqWfOut out, cudaStream_t st) {
+  switch (wf->kind) {
+    case JAQMC_WF_FERMINET:
+      return jq_ferminet_forward((const jaqmc_ferminet_config*)wf->config, (const jaqmc_ferminet_params*)wf->params,
+                                 sys, electrons, W, track, ws, ws_bytes, out, st);
+    default:
+      jq_set_error("wavefunction kind %d is not implemented", wf->kind);
+      return JQ_ERR_UNSUPPORTED;
+  }
+}
+
+static int check_wf(const jaqmc_wavefunction* wf) {
+  JQ_REQUIRE(wf && wf->config && wf->params, JQ_ERR_INVALID_ARGUMENT, "null wavefunction descriptor");
+  JQ_REQUIRE(wf_n_electrons(wf) > 0, JQ_ERR_UNSUPPORTED, "wavefunction kind %d is not implemented", wf->kind);
+  return JQ_OK;
+}
+
+// API-level scratch per walker (besides the pipeline's own): grad, lap, e_kin, e_pot, x2, lp2
+static size_t api_scratch_bytes(int n, long long W) {
+  JqArena ar(nullptr, 0);
+  ar.take<float>(W * 3 * n);  // grad
+  ar.take<float>(W);          // lap
+  ar.take<float>(W);          // e_kin
+  ar.take<float>(W);          // e_pot
+  ar.take<float>(W);          // sign
+  return ar.off;
+}
+
+// Largest walker tile whose pipeline workspace fits into `avail` bytes.
+static long long fit_tile(const jaqmc_wavefunction* wf, long long W, int track, size_t avail) {
+  if (wf_ws_bytes(wf, W, track) <= avail) return W;
+  long long lo = 0, hi = W;  // invariant: lo fits (0 = nothing), hi does not
+  while (hi - lo > 1) {
+    long long mid = (lo + hi) / 2;
+    if (wf_ws_bytes(wf, mid, track) <= avail) lo = mid; else hi = mid;
+  }
+  return lo;
+}
+
+extern "C" size_t jaqmc_b200_workspace_bytes(const jaqmc_wavefunction* wf, int64_t n_walkers, int track) {
+  if (check_wf(wf) != JQ_OK || n_walkers < 0) return 0;
+  int n = wf_n_electrons(wf);
+  size_t mh = 0;
+  {
+    JqArena ar(nullptr, 0);
+    ar.take<float>(n_walkers * 3 * n);  // x2
+    ar.take<float>(n_walkers);          // lp2
+    ar.take<float>(n_walkers);          // sign
+    mh = ar.off;
+  }
+  size_t api = api_scratch_bytes(n, n_walkers);
+  return wf_ws_bytes(wf, n_walkers, track) + (api > mh ? api : mh) + 256;
+}
+
+extern "C" int jaqmc_b200_logpsi(const jaqmc_wavefunction* wf, const jaqmc_system* sys, const float* electrons,
+                                 int64_t n_walkers, float* logpsi, float* sign, void* workspace,
+                                 size_t workspace_bytes, jaqmc_stream_t stream) {
+  int rc = check_wf(wf);
+  if (rc) return rc;
+  JQ_REQUIRE(n_walkers >= 0 && (n_walkers == 0 || (electrons && logpsi)), JQ_ERR_INVALID_ARGUMENT, "logpsi: null buffer");
+  if (n_walkers == 0) return JQ_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int n = wf_n_electrons(wf);
+  JqArena ar(workspace, workspace_bytes);
+  float* sign_tmp = sign ? sign : ar.take<float>(n_walkers);
+  JQ_REQUIRE(workspace && ar.off <= workspace_bytes, JQ_ERR_WORKSPACE_TOO_SMALL, "logpsi: workspace too small");
+  size_t avail = workspace_bytes - ar.off;
+  long long tile = fit_tile(wf, n_walkers, 0, avail);
+  JQ_REQUIRE(tile >= 1, JQ_ERR_WORKSPACE_TOO_SMALL, "logpsi: workspace of %zu bytes cannot hold one walker", workspace_bytes);
+  for (long long w0 = 0; w0 < n_walkers; w0 += tile) {
+    long long wc = (n_walkers - w0 < tile) ? n_walkers - w0 : tile;
+    JqWfOut out = {logpsi + w0, sign_tmp + w0, nullptr, nullptr, nullptr};
+    rc = wf_forward(wf, sys, electrons + w0 * 3 * n, wc, 0, ar.base + ar.off, avail, out, st);
+    if (rc) return rc;
+  }
+  return JQ_OK;
+}
+
+// e_loc = e_kin + e_pot and the per-device partial sums {sum, sum of squares, finite count}.
+#ifdef JAQMC_HOST_EMU
+#define JQ_ATOMIC_ADD(p, v) (*(p) += (v))
+#else
+#define JQ_ATOMIC_ADD(p, v) atomicAdd((p), (v))
+#endif
+#define FIN_TILE 256
+__global__ void k_energy_finalize(const float* __restrict__ e_kin, const float* __restrict__ e_pot,
+                                  float* __restrict__ e_loc, float* __restrict__ sums, long long W) {
+  __shared__ float buf[FIN_TILE];
+  const long long w0 = (long long)blockIdx.x * FIN_TILE;
+  const int nw = (int)((W - w0 < FIN_TILE) ? W - w0 : FIN_TILE);
+  for (int t = threadIdx.x; t < nw; t += blockDim.x) {
+    float e = e_kin[w0 + t] + e_pot[w0 + t];
+    if (e_loc) e_loc[w0 + t] = e;
+    buf[t] = e;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0 && sums) {
+    float s = 0.f, s2 = 0.f, c = 0.f;
+    for (int t = 0; t < nw; ++t) {
+      float e = buf[t];
+      if (isfinite(e)) {
+        s += e;
+        s2 = fmaf(e, e, s2);
+        c += 1.f;
+      }
+    }
+    JQ_ATOMIC_ADD(sums + 0, s);
+    JQ_ATOMIC_ADD(sums + 1, s2);
+    JQ_ATOMIC_ADD(sums + 2, c);
+  }
+}
+
+extern "C" int jaqmc_b200_coulomb(const jaqmc_system* sys, const float* electrons, int64_t n_walkers,
+                                  int32_t n_electrons, float* e_pot, jaqmc_stream_t stream) {
+  JQ_REQUIRE(sys && sys->atoms && sys->charges && sys->n_atoms >= 1, JQ_ERR_INVALID_ARGUMENT, "coulomb: null system");
+  JQ_REQUIRE(n_walkers >= 0 && n_electrons >= 1 && (n_walkers == 0 || (electrons && e_pot)), JQ_ERR_INVALID_ARGUMENT,
+             "coulomb: bad arguments");
+  return jq_launch_coulomb(electrons, sys->atoms, sys->charges, (int)n_walkers, n_electrons, sys->n_atoms, e_pot,
+                           (cudaStream_t)stream);
+}
+
+extern "C" int jaqmc_b200_local_energy(const jaqmc_wavefunction* wf, const jaqmc_system* sys, const float* electrons,
+                                       int64_t n_walkers, float* logpsi, float* sign, float* grad, float* lap,
+                                       float* e_kin, float* e_pot, float* e_loc, float* sums, void* workspace,
+                                       size_t workspace_bytes, jaqmc_stream_t stream) {
+  int rc = check_wf(wf);
+  if (rc) return rc;
+  JQ_REQUIRE(n_walkers >= 0 && (n_walkers == 0 || (electrons && logpsi)), JQ_ERR_INVALID_ARGUMENT,
+             "local_energy: null buffer");
+  JQ_REQUIRE(sys && sys->atoms && sys->charges, JQ_ERR_INVALID_ARGUMENT, "local_energy: system needs atoms and charges");
+  if (n_walkers == 0) return JQ_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int n = wf_n_electrons(wf);
+  const long long W = n_walkers;
+  JqArena ar(workspace, workspace_bytes);
+  float* g = grad ? grad : ar.take<float>(W * 3 * n);
+  float* lp = lap ? lap : ar.take<float>(W);
+  float* ek = e_kin ? e_kin : ar.take<float>(W);
+  float* ep = e_pot ? e_pot : ar.take<float>(W);
+  float* sg = sign ? sign : ar.take<float>(W);
+  JQ_REQUIRE(workspace && ar.off <= workspace_bytes, JQ_ERR_WORKSPACE_TOO_SMALL, "local_energy: workspace too small");
+  size_t avail = workspace_bytes - ar.off;
+  long long tile = fit_tile(wf, W, 1, avail);
+  JQ_REQUIRE(tile >= 1, JQ_ERR_WORKSPACE_TOO_SMALL, "local_energy: workspace of %zu bytes cannot hold one walker",
+             workspace_bytes);
+  for (long long w0 = 0; w0 < W; w0 += tile) {
+    long long wc = (W - w0 < tile) ? W - w0 : tile;
+    JqWfOut out = {logpsi + w0, sg + w0, g + w0 * 3 * n, lp + w0, ek + w0};
+    rc = wf_forward(wf, sys, electrons + w0 * 3 * n, wc, 1, ar.base + ar.off, avail, out, st);
+    if (rc) return rc;
+  }
+  rc = jq_launch_coulomb(electrons, sys->atoms, sys->charges, (int)W, n, sys->n_atoms, ep, st);
+  if (rc) return rc;
+  if (e_loc || sums) {
+    JQ_LAUNCH(k_energy_finalize, dim3(jq_cdiv(W, FIN_TILE)), dim3(FIN_TILE), 0, st, ek, ep, e_loc, sums, W);
+    JQ_CHECK_LAUNCH();
+  }
+  return JQ_OK;
+}
+
+extern "C" int jaqmc_b200_mh_propose(const float* x1, const float* normals, const float* stddev, float* x2,
+                                     int64_t count, jaqmc_stream_t stream) {
+  JQ_REQUIRE(count >= 0 && (count == 0 || (x1 && normals && stddev && x2)), JQ_ERR_INVALID_ARGUMENT, "mh_propose: null buffer");
+  return jq_launch_mh_propose(x1, normals, stddev, x2, count, (cudaStream_t)stream);
+}
+
+extern "C" int jaqmc_b200_mh_accept(float* x1, const float* x2, float* logprob1, const float* logprob2,
+                                    const float* uniforms, int64_t n_walkers, int32_t row, float* n_accept,
+                                    uint8_t* accepted, jaqmc_stream_t stream) {
+  JQ_REQUIRE(n_walkers >= 0 && row >= 1 && (n_walkers == 0 || (x1 && x2 && logprob1 && logprob2 && uniforms && n_accept)),
+             JQ_ERR_INVALID_ARGUMENT, "mh_accept: null buffer");
+  return jq_launch_mh_accept(x1, x2, logprob1, logprob2, uniforms, nullptr, nullptr, nullptr, (int)n_walkers, row, 1.0f,
+                             n_accept, accepted, (cudaStream_t)stream);
+}
+
+extern "C" int jaqmc_b200_mh_step(const jaqmc_wavefunction* wf, const jaqmc_system* sys, float* electrons,
+                                  float* logpsi, int32_t logpsi_valid, const float* normals, const float* uniforms,
+                                  const float* stddev, int32_t n_steps, int64_t n_walkers, float* n_accept,
+                                  uint8_t* accepted, void* workspace, size_t workspace_bytes, jaqmc_stream_t stream) {
+  int rc = check_wf(wf);
+  if (rc) return rc;
+  JQ_REQUIRE(n_walkers >= 0 && n_steps >= 0, JQ_ERR_INVALID_ARGUMENT, "mh_step: negative size");
+  if (n_walkers == 0) return JQ_OK;
+  JQ_REQUIRE(electrons && logpsi && stddev && n_accept && (n_steps == 0 || (normals && uniforms)),
+             JQ_ERR_INVALID_ARGUMENT, "mh_step: null buffer");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int n = wf_n_electrons(wf);
+  const long long W = n_walkers;
+  const int row = 3 * n;
+  JqArena ar(workspace, workspace_bytes);
+  float* x2 = ar.take<float>(W * row);
+  float* lp2 = ar.take<float>(W);
+  float* sg = ar.take<float>(W);
+  JQ_REQUIRE(workspace && ar.off <= workspace_bytes, JQ_ERR_WORKSPACE_TOO_SMALL, "mh_step: workspace too small");
+  size_t avail = workspace_bytes - ar.off;
+  long long tile = fit_tile(wf, W, 0, avail);
+  JQ_REQUIRE(tile >= 1, JQ_ERR_WORKSPACE_TOO_SMALL, "mh_step: workspace of %zu bytes cannot hold one walker", workspace_bytes);
+  auto forward_all = [&](const float* x, float* lp) -> int {
+    for (long long w0 = 0; w0 < W; w0 += tile) {
+      long long wc = (W - w0 < tile) ? W - w0 : tile;
+      JqWfOut out = {lp + w0, sg + w0, nullptr, nullptr, nullptr};
+      int r = wf_forward(wf, sys, x + w0 * row, wc, 0, ar.base + ar.off, avail, out, st);
+      if (r) return r;
+    }
+    return JQ_OK;
+  };
+  if (!logpsi_valid && (rc = forward_all(electrons, logpsi))) return rc;
+  if (n_steps == 0) return JQ_OK;
+  if ((rc = jq_launch_mh_propose(electrons, normals, stddev, x2, W * row, st))) return rc;
+  for (int s = 0; s < n_steps; ++s) {
+    if ((rc = forward_all(x2, lp2))) return rc;
+    const float* next = (s + 1 < n_steps) ? normals + (size_t)(s + 1) * W * row : nullptr;
+    // fused: accept test, select, and the next proposal (x2 is rewritten in place)
+    rc = jq_launch_mh_accept(electrons, x2, logpsi, lp2, uniforms + (size_t)s * W, next, stddev, x2, (int)W, row, 2.0f,
+                             n_accept, accepted ? accepted + (size_t)s * W : nullptr, st);
+    if (rc) return rc;
+  }
+  return JQ_OK;
+}
+
+extern "C" int64_t jaqmc_b200_launch_count(void) { return jq_launch_counter; }
+extern "C" void jaqmc_b200_reset_launch_count(void) { jq_launch_counter = 0; }
+extern "C" const char* jaqmc_b200_last_error(void) { return jq_err; }
+extern "C" const char* jaqmc_b200_version(void) {
+#ifdef JAQMC_HOST_EMU
+  return "jaqmc_b200 0.1 (HOST EMULATION BUILD - test infrastructure only)";
+#else
+  return "jaqmc_b200 0.1 (sm_100a)";
+#endif
+}

@@ -1,0 +1,82 @@
+// Augmented ("forward-Laplacian") tensor conventions shared by all kernels.
+//
+// A tracked activation is stored as  T[group][C][F]  (row-major, F contiguous) where
+//   group  = (walker, electron)  for single-electron streams,   [W][n]
+//          = (walker, i, j)      for pair streams,              [W][n*n], pair p = i*n + j
+//   C      = number of components carried per group:
+//              C == 1        value only (sampling / psi-ratio path),
+//              C == ncoord+2 value, ncoord Jacobian columns, Laplacian      (c = 0, 1..ncoord, ncoord+1)
+//            with ncoord = 3 for "Local1" tensors (each row depends on its own electron only,
+//            reference laplacian/sparse.py Local1Jacobian), 6 for "Local2" pair tensors (columns
+//            0-2 w.r.t. electron i, 3-5 w.r.t. electron j, Local2Jacobian) and 3n for dense tensors.
+// One GEMM over the rows {x, J_1..J_K, L} is the forward-Laplacian rule of an affine map (reference
+// laplacian/primitives/dot_general.py:377-407); the elementwise rule f'(x)J, f'(x)L + f''(x) sum J^2
+// (primitives/elementwise.py:42-72) needs all C rows of one group, which is why groups are contiguous.
+#pragma once
+#include "common.cuh"
+
+#define JQ_MAX_LAYERS 8
+#define JQ_MAX_ATOMS 64
+
+// Non-empty spin channels (reference utils/array.py:24-45 split_nonempty_channels).
+struct JqSpins {
+  int n_up, n_dn;
+  __host__ __device__ int n() const { return n_up + n_dn; }
+  __host__ __device__ int nch() const { return (n_up > 0 && n_dn > 0) ? 2 : 1; }
+  // channel s covers electrons [lo, hi)
+  __host__ __device__ int lo(int s) const { return (nch() == 2 && s == 1) ? n_up : 0; }
+  __host__ __device__ int hi(int s) const { return (nch() == 2 && s == 0) ? n_up : n_up + n_dn; }
+  __host__ __device__ int chan_of(int e) const { return (nch() == 2 && e >= n_up) ? 1 : 0; }
+};
+
+// ---- kernels implemented in features.cu ---------------------------------------------------------
+int jq_launch_mol_features(const float* electrons, const float* atoms, int W, JqSpins sp, int A, int rescale,
+                           int track, float* ae, float* ee, cudaStream_t st);
+int jq_launch_coulomb(const float* electrons, const float* atoms, const float* charges, int W, int n, int A,
+                      float* e_pot, cudaStream_t st);
+
+// ---- kernels implemented in dense.cu ------------------------------------------------------------
+struct JqDenseArgs {
+  const float* src0;  // [groups_total][C][k0]
+  int k0;
+  const float* src1;  // optional second source concatenated along the contraction axis, [..][C][k1]
+  int k1;
+  const float* w0;    // [k0][N]  rows of the flax kernel that multiply src0
+  const float* w1;    // [k1][N]
+  const float* bias;  // [N] or null; added to the value row only
+  const float* cadd;  // [W][C][N] or null; per-walker addend broadcast over the walker's groups
+  float* out;         // [groups_total][C][N]
+  int N, C;
+  // group mapping: launch covers G = W*n_sub groups; sub-group g' -> group (g'/n_sub)*n_tot + j0 + g'%n_sub
+  int n_sub, n_tot, j0;
+  long long G;
+};
+int jq_launch_dense(const JqDenseArgs& a, cudaStream_t st);
+// out = act(y) or (res + act(y))/sqrt(2); act = tanh with the forward-Laplacian rule.  In-place allowed.
+int jq_launch_tanh_fl(const float* y, const float* res, float* out, long long G, int C, int F, int residual_mode,
+                      cudaStream_t st);
+int jq_launch_pair_mean(const float* h2, float* g2, int W, JqSpins sp, int d2, int track, cudaStream_t st);
+int jq_launch_concat_layer1(const float* ae, const float* g2, float* out, int W, JqSpins sp, int f1, int fg,
+                            int track, cudaStream_t st);
+int jq_launch_spin_mean(const float* h, float* m, int W, JqSpins sp, int C, int F, cudaStream_t st);
+
+// ---- kernels implemented in logdet.cu -----------------------------------------------------------
+struct JqEnvelopeArgs {
+  const float* pi[2];     // per spin channel: [n_orb][A][D]   (reference output/envelope.py:131-135)
+  const float* sigma[2];
+  int type;               // 0 isotropic, 1 abs_isotropic, 2 null
+};
+int jq_launch_orb_envelope(float* orb, const float* electrons, const float* atoms, const JqEnvelopeArgs& env,
+                           int W, JqSpins sp, int A, int D, int track, cudaStream_t st);
+int jq_launch_logdet(const float* orb, int W, int n, int D, int track, float* det_sign, float* det_logabs,
+                     float* det_grad, float* det_lap, cudaStream_t st);
+int jq_launch_logdet_combine(const float* det_sign, const float* det_logabs, const float* det_grad,
+                             const float* det_lap, int W, int n, int D, int track, const float* extra_logpsi,
+                             float* logpsi, float* sign, float* grad, float* lap, float* e_kin, cudaStream_t st);
+
+// ---- kernels implemented in mcmc.cu ---------------------------------------------------------------
+int jq_launch_mh_propose(const float* x1, const float* normals, const float* stddev, float* x2, long long count,
+                         cudaStream_t st);
+int jq_launch_mh_accept(float* x1, const float* x2, float* lp1, const float* lp2, const float* log_u,
+                        const float* next_normals, const float* stddev, float* x2_next, int W, int row,
+                        float scale, float* n_accept, unsigned char* accepted, cudaStream_t st);

@@ -1,0 +1,354 @@
+// Augmented-row dense layers (CUDA-core path), tanh forward-Laplacian epilogue, and the FermiNet
+// aggregation kernels.
+//
+// Reference semantics:
+//   * nn.Dense under forward_laplacian = one GEMM over the rows {x, J_1..J_K, L}; bias on the value row
+//     only (laplacian/primitives/dot_general.py:377-407)
+//   * tanh rule y_J = (1-y^2) J, y_L = (1-y^2) L - 2y(1-y^2) sum_k J_k^2 (primitives/elementwise.py:42-72)
+//   * FermiNet aggregate_features / residual (wavefunction/backbone/ferminet.py:51-90)
+//
+// The CUDA-core GEMM below serves the narrow layers (contraction width < 64: input layers, the
+// two-electron stream) and is the numerical cross-check of the tcgen05 kernel in dense_tc.cu, which takes
+// the wide (>= 64-deep) layers on device builds.
+#include "aug.cuh"
+
+// ------------------------------------------------------------------------------------------------
+// GEMM: out[row][col] = sum_k [src0|src1][row][k] * [w0;w1][k][col] (+cadd) (+bias on value rows)
+// ------------------------------------------------------------------------------------------------
+#define GM_BM 128
+#define GM_BN 64
+#define GM_BK 16
+
+__device__ __forceinline__ long long jq_group_of(long long gsub, int n_sub, int n_tot, int j0) {
+  return (gsub / n_sub) * (long long)n_tot + j0 + (gsub % n_sub);
+}
+
+#ifndef JAQMC_HOST_EMU
+__global__ void __launch_bounds__(256) k_dense_simt(JqDenseArgs a) {
+  __shared__ float As[GM_BK][GM_BM + 4];
+  __shared__ float Bs[GM_BK][GM_BN];
+  const long long R = a.G * a.C;
+  const long long row0 = (long long)blockIdx.x * GM_BM;
+  const int col0 = blockIdx.y * GM_BN;
+  const int tid = threadIdx.x;
+  const int ty = tid / 16, tx = tid % 16;
+  const int kt = a.k0 + a.k1;
+  float acc[8][4];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  // each thread loads 8 A elements: element q -> (row = (tid + q*256)/16, k = (tid + q*256)%16)
+  long long arow[8];
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    long long r = row0 + (tid + q * 256) / GM_BK;
+    if (r < R) {
+      long long gs = r / a.C;
+      int c = (int)(r % a.C);
+      arow[q] = jq_group_of(gs, a.n_sub, a.n_tot, a.j0) * a.C + c;
+    } else {
+      arow[q] = -1;
+    }
+  }
+  for (int kb = 0; kb < kt; kb += GM_BK) {
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      int idx = tid + q * 256;
+      int rl = idx / GM_BK, kl = idx % GM_BK;
+      int kk = kb + kl;
+      float v = 0.f;
+      if (arow[q] >= 0 && kk < kt)
+        v = (kk < a.k0) ? a.src0[arow[q] * a.k0 + kk] : a.src1[arow[q] * a.k1 + (kk - a.k0)];
+      As[kl][rl] = v;
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      int idx = tid + q * 256;
+      int kl = idx / GM_BN, cl = idx % GM_BN;
+      int kk = kb + kl, col = col0 + cl;
+      float v = 0.f;
+      if (kk < kt && col < a.N) v = (kk < a.k0) ? a.w0[(long long)kk * a.N + col] : a.w1[(long long)(kk - a.k0) * a.N + col];
+      Bs[kl][cl] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < GM_BK; ++k) {
+      float av[8], bv[4];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) av[i] = As[k][ty * 8 + i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) bv[j] = Bs[k][tx * 4 + j];
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    long long r = row0 + ty * 8 + i;
+    if (r >= R) continue;
+    long long gs = r / a.C;
+    int c = (int)(r % a.C);
+    long long g = jq_group_of(gs, a.n_sub, a.n_tot, a.j0);
+    long long orow = g * a.C + c;
+    long long w = g / a.n_tot;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      int col = col0 + tx * 4 + j;
+      if (col >= a.N) continue;
+      float v = acc[i][j];
+      if (a.cadd) v += a.cadd[(w * a.C + c) * a.N + col];
+      if (a.bias && c == 0) v += a.bias[col];
+      a.out[orow * a.N + col] = v;
+    }
+  }
+}
+#else
+__global__ void k_dense_simt(JqDenseArgs a) {
+  const long long R = a.G * a.C;
+  for (long long r = (long long)blockIdx.x * GM_BM; r < R && r < (long long)(blockIdx.x + 1) * GM_BM; ++r) {
+    long long gs = r / a.C;
+    int c = (int)(r % a.C);
+    long long g = jq_group_of(gs, a.n_sub, a.n_tot, a.j0);
+    long long row = g * a.C + c;
+    long long w = g / a.n_tot;
+    for (int col = blockIdx.y * GM_BN; col < a.N && col < (int)(blockIdx.y + 1) * GM_BN; ++col) {
+      float v = 0.f;
+      for (int k = 0; k < a.k0; ++k) v = fmaf(a.src0[row * a.k0 + k], a.w0[(long long)k * a.N + col], v);
+      for (int k = 0; k < a.k1; ++k) v = fmaf(a.src1[row * a.k1 + k], a.w1[(long long)k * a.N + col], v);
+      if (a.cadd) v += a.cadd[(w * a.C + c) * a.N + col];
+      if (a.bias && c == 0) v += a.bias[col];
+      a.out[row * a.N + col] = v;
+    }
+  }
+}
+#endif
+
+#ifndef JAQMC_HOST_EMU
+int jq_launch_dense_tc(const JqDenseArgs& a, cudaStream_t st, bool* handled);  // dense_tc.cu
+#endif
+
+int jq_launch_dense(const JqDenseArgs& a, cudaStream_t st) {
+  if (a.G <= 0 || a.N <= 0) return JQ_OK;
+  JQ_REQUIRE(a.k0 > 0 && a.src0 && a.w0 && a.out, JQ_ERR_INVALID_ARGUMENT, "dense: null operand");
+  JQ_REQUIRE(a.k1 == 0 || (a.src1 && a.w1), JQ_ERR_INVALID_ARGUMENT, "dense: null second operand");
+#ifndef JAQMC_HOST_EMU
+  bool handled = false;
+  int rc = jq_launch_dense_tc(a, st, &handled);
+  if (rc != JQ_OK) return rc;
+  if (handled) return JQ_OK;
+#endif
+  long long R = a.G * a.C;
+  dim3 grid(jq_cdiv(R, GM_BM), jq_cdiv(a.N, GM_BN));
+  JQ_LAUNCH(k_dense_simt, grid, dim3(256), 0, st, a);
+  JQ_CHECK_LAUNCH();
+  return JQ_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// tanh with the forward-Laplacian rule (+ FermiNet residual).  One item per (group, feature).
+//   residual_mode 0: out = tanh(y)     1: out = (res + tanh(y)) / sqrt(2)     2: out = res + tanh(y)
+// ------------------------------------------------------------------------------------------------
+__global__ void k_tanh_fl(const float* __restrict__ y, const float* __restrict__ res, float* __restrict__ out,
+                          long long items, int C, int F, int mode) {
+  const float inv_sqrt2 = 0.70710678118654752440f;
+  for (long long it = (long long)blockIdx.x * blockDim.x + threadIdx.x; it < items;
+       it += (long long)gridDim.x * blockDim.x) {
+    long long g = it / F;
+    int f = (int)(it % F);
+    const float* yp = y + g * C * F + f;
+    const float* rp = res ? res + g * C * F + f : nullptr;
+    float* op = out + g * C * F + f;
+    float t = tanhf(yp[0]);
+    float d1 = 1.0f - t * t;
+    float v = t;
+    if (mode == 1) v = (rp[0] + t) * inv_sqrt2;
+    else if (mode == 2) v = rp[0] + t;
+    if (C > 1) {
+      float s2 = 0.f;
+      for (int c = 1; c < C - 1; ++c) {
+        float j = yp[(long long)c * F];
+        s2 = fmaf(j, j, s2);
+        float o = d1 * j;
+        if (mode == 1) o = (rp[(long long)c * F] + o) * inv_sqrt2;
+        else if (mode == 2) o = rp[(long long)c * F] + o;
+        op[(long long)c * F] = o;
+      }
+      float l = d1 * yp[(long long)(C - 1) * F] - 2.0f * t * d1 * s2;
+      if (mode == 1) l = (rp[(long long)(C - 1) * F] + l) * inv_sqrt2;
+      else if (mode == 2) l = rp[(long long)(C - 1) * F] + l;
+      op[(long long)(C - 1) * F] = l;
+    }
+    op[0] = v;
+  }
+}
+
+int jq_launch_tanh_fl(const float* y, const float* res, float* out, long long G, int C, int F, int residual_mode,
+                      cudaStream_t st) {
+  long long items = G * F;
+  if (items <= 0) return JQ_OK;
+  JQ_REQUIRE(residual_mode == 0 || res != nullptr, JQ_ERR_INVALID_ARGUMENT, "tanh_fl: residual without source");
+  int grid = jq_cdiv(items, 256);
+  if (grid > 148 * 32) grid = 148 * 32;
+  JQ_LAUNCH(k_tanh_fl, dim3(grid), dim3(256), 0, st, y, res, out, items, C, F, residual_mode);
+  JQ_CHECK_LAUNCH();
+  return JQ_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// FermiNet pair-stream spin means: h2 [W][n*n][C2][d2] (Local2, pair p = i*n + j) -> g2 [W][n][C][nch*d2]
+// g2[j][s] = mean_{i in s} h2[i][j]  (mean over the FIRST electron axis, ferminet.py:86-89).  This is the
+// Local2 -> dense transition of the reference (laplacian/primitives/reductions.py:52-61).
+// One item per (walker, j, s, feature).
+// ------------------------------------------------------------------------------------------------
+__global__ void k_pair_mean(const float* __restrict__ h2, float* __restrict__ g2, long long items, JqSpins sp,
+                            int d2, int track) {
+  const int n = sp.n(), nch = sp.nch();
+  const int C2 = track ? 8 : 1, C = track ? 3 * n + 2 : 1, FO = nch * d2;
+  for (long long it = (long long)blockIdx.x * blockDim.x + threadIdx.x; it < items;
+       it += (long long)gridDim.x * blockDim.x) {
+    int f = (int)(it % d2);
+    long long t = it / d2;
+    int s = (int)(t % nch);
+    t /= nch;
+    int j = (int)(t % n);
+    long long w = t / n;
+    const int lo = sp.lo(s), hi = sp.hi(s);
+    const float inv = 1.0f / (float)(hi - lo);
+    const float* base = h2 + (w * n * n) * (long long)C2 * d2 + f;  // pair p comp c at base + (p*C2 + c)*d2
+    float* o = g2 + ((w * n + j) * (long long)C) * FO + s * d2 + f;  // comp c at o + c*FO
+    float sx = 0.f, sl = 0.f, sj[3] = {0.f, 0.f, 0.f};
+    for (int i = lo; i < hi; ++i) {
+      const float* p = base + ((long long)(i * n + j) * C2) * d2;
+      sx += p[0];
+      if (track) {
+        sl += p[7 * d2];
+        sj[0] += p[4 * d2];
+        sj[1] += p[5 * d2];
+        sj[2] += p[6 * d2];
+      }
+    }
+    o[0] = sx * inv;
+    if (track) {
+      o[(long long)(C - 1) * FO] = sl * inv;
+      for (int e = 0; e < n; ++e) {
+        bool in_s = (e >= lo && e < hi);
+        const float* p = base + ((long long)(e * n + j) * C2) * d2;
+        for (int a = 0; a < 3; ++a) {
+          float v = in_s ? p[(1 + a) * d2] : 0.f;
+          if (e == j) v += sj[a];
+          o[(long long)(1 + 3 * e + a) * FO] = v * inv;
+        }
+      }
+    }
+  }
+}
+
+int jq_launch_pair_mean(const float* h2, float* g2, int W, JqSpins sp, int d2, int track, cudaStream_t st) {
+  long long items = (long long)W * sp.n() * sp.nch() * d2;
+  if (items <= 0) return JQ_OK;
+  int grid = jq_cdiv(items, 256);
+  if (grid > 148 * 32) grid = 148 * 32;
+  JQ_LAUNCH(k_pair_mean, dim3(grid), dim3(256), 0, st, h2, g2, items, sp, d2, track);
+  JQ_CHECK_LAUNCH();
+  return JQ_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// First single-stream layer input: concat [ae_j | mean_s ae | g2_j]  (ferminet.py:65-90) as a dense
+// augmented tensor [W][n][C][f1*(1+nch) + fg];  ae is Local1 [W][n][C1][f1], g2 dense [W][n][C][fg].
+// One item per (walker, j, output column).
+// ------------------------------------------------------------------------------------------------
+__global__ void k_concat_layer1(const float* __restrict__ ae, const float* __restrict__ g2, float* __restrict__ out,
+                                long long items, JqSpins sp, int f1, int fg, int track) {
+  const int n = sp.n(), nch = sp.nch();
+  const int C1 = track ? 5 : 1, C = track ? 3 * n + 2 : 1;
+  const int FO = f1 * (1 + nch) + fg;
+  for (long long it = (long long)blockIdx.x * blockDim.x + threadIdx.x; it < items;
+       it += (long long)gridDim.x * blockDim.x) {
+    int col = (int)(it % FO);
+    long long t = it / FO;
+    int j = (int)(t % n);
+    long long w = t / n;
+    float* o = out + ((w * n + j) * (long long)C) * FO + col;
+    if (col < f1) {
+      const float* p = ae + ((w * n + j) * (long long)C1) * f1 + col;
+      o[0] = p[0];
+      if (track) {
+        for (int c = 1; c < C - 1; ++c) o[(long long)c * FO] = 0.f;
+        for (int a = 0; a < 3; ++a) o[(long long)(1 + 3 * j + a) * FO] = p[(1 + a) * f1];
+        o[(long long)(C - 1) * FO] = p[4 * f1];
+      }
+    } else if (col < f1 * (1 + nch)) {
+      int s = (col - f1) / f1, f = (col - f1) % f1;
+      int lo = sp.lo(s), hi = sp.hi(s);
+      float inv = 1.0f / (float)(hi - lo);
+      float sx = 0.f, sl = 0.f;
+      if (track)
+        for (int c = 1; c < C - 1; ++c) o[(long long)c * FO] = 0.f;
+      for (int e = lo; e < hi; ++e) {
+        const float* p = ae + ((w * n + e) * (long long)C1) * f1 + f;
+        sx += p[0];
+        if (track) {
+          sl += p[4 * f1];
+          for (int a = 0; a < 3; ++a) o[(long long)(1 + 3 * e + a) * FO] = p[(1 + a) * f1] * inv;
+        }
+      }
+      o[0] = sx * inv;
+      if (track) o[(long long)(C - 1) * FO] = sl * inv;
+    } else {
+      int f = col - f1 * (1 + nch);
+      const float* p = g2 + ((w * n + j) * (long long)C) * fg + f;
+      for (int c = 0; c < C; ++c) o[(long long)c * FO] = p[(long long)c * fg];
+    }
+  }
+}
+
+int jq_launch_concat_layer1(const float* ae, const float* g2, float* out, int W, JqSpins sp, int f1, int fg,
+                            int track, cudaStream_t st) {
+  int FO = f1 * (1 + sp.nch()) + fg;
+  long long items = (long long)W * sp.n() * FO;
+  if (items <= 0) return JQ_OK;
+  int grid = jq_cdiv(items, 256);
+  if (grid > 148 * 32) grid = 148 * 32;
+  JQ_LAUNCH(k_concat_layer1, dim3(grid), dim3(256), 0, st, ae, g2, out, items, sp, f1, fg, track);
+  JQ_CHECK_LAUNCH();
+  return JQ_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Spin means of a dense single stream: h [W][n][C][F] -> m [W][C][nch*F], m[w][c][s*F+f] = mean_{e in s} h
+// (the walker-wide part of aggregate_features; it is the same for every electron of the walker, so its
+// Dense contribution is computed once per walker and broadcast, instead of once per electron).
+// ------------------------------------------------------------------------------------------------
+__global__ void k_spin_mean(const float* __restrict__ h, float* __restrict__ m, long long items, JqSpins sp, int C,
+                            int F) {
+  const int n = sp.n(), nch = sp.nch();
+  for (long long it = (long long)blockIdx.x * blockDim.x + threadIdx.x; it < items;
+       it += (long long)gridDim.x * blockDim.x) {
+    int f = (int)(it % F);
+    long long t = it / F;
+    int s = (int)(t % nch);
+    t /= nch;
+    int c = (int)(t % C);
+    long long w = t / C;
+    int lo = sp.lo(s), hi = sp.hi(s);
+    float acc = 0.f;
+    for (int e = lo; e < hi; ++e) acc += h[(((w * n + e) * (long long)C) + c) * F + f];
+    m[((w * C + c) * (long long)nch + s) * F + f] = acc / (float)(hi - lo);
+  }
+}
+
+int jq_launch_spin_mean(const float* h, float* m, int W, JqSpins sp, int C, int F, cudaStream_t st) {
+  long long items = (long long)W * C * sp.nch() * F;
+  if (items <= 0) return JQ_OK;
+  int grid = jq_cdiv(items, 256);
+  if (grid > 148 * 32) grid = 148 * 32;
+  JQ_LAUNCH(k_spin_mean, dim3(grid), dim3(256), 0, st, h, m, items, sp, C, F);
+  JQ_CHECK_LAUNCH();
+  return JQ_OK;
+}

@@ -1,0 +1,228 @@
+// FermiNet forward / forward-Laplacian pipeline (molecule).
+//
+// Composition follows app/molecule/wavefunction/ferminet.py:76-96 (features -> FermiLayers -> orbitals x
+// envelope -> LogDet) with the layer structure of wavefunction/backbone/ferminet.py:29-63.
+//
+// Restructuring relative to the reference's traced graph (same function, fewer FLOPs):
+//   the aggregated input [h_j | mean_up h | mean_dn h | g2_j] is never materialised for layers >= 2.  The Dense
+//   kernel is split by rows; the spin-mean part is identical for every electron of a walker, so it is contracted
+//   once per walker (rows W*C) and broadcast-added inside the main GEMM's epilogue, and the main GEMM contracts
+//   only [h_j | g2_j]  (256+64 wide instead of 832 wide for the default network).
+#include "wf.cuh"
+
+struct FermiDims {
+  JqSpins sp;
+  int n, A, D, L, nch, C, C1, C2, f1;
+  int d1[JQ_MAX_LAYERS], d2[JQ_MAX_LAYERS];  // widths after layer l
+  int d1max, d2max, in1;
+};
+
+static int fermi_dims(const jaqmc_ferminet_config* c, int track, FermiDims* o) {
+  JQ_REQUIRE(c->n_layers >= 1 && c->n_layers <= JQ_MAX_LAYERS, JQ_ERR_INVALID_ARGUMENT, "ferminet: n_layers=%d",
+             c->n_layers);
+  JQ_REQUIRE(c->n_up >= 0 && c->n_dn >= 0 && c->n_up + c->n_dn >= 1, JQ_ERR_INVALID_ARGUMENT, "ferminet: nspins");
+  JQ_REQUIRE(c->n_atoms >= 1 && c->n_atoms <= JQ_MAX_ATOMS, JQ_ERR_INVALID_ARGUMENT, "ferminet: n_atoms=%d",
+             c->n_atoms);
+  JQ_REQUIRE(c->ndets >= 1, JQ_ERR_INVALID_ARGUMENT, "ferminet: ndets=%d", c->ndets);
+  o->sp.n_up = c->n_up;
+  o->sp.n_dn = c->n_dn;
+  o->n = c->n_up + c->n_dn;
+  o->A = c->n_atoms;
+  o->D = c->ndets;
+  o->L = c->n_layers;
+  o->nch = o->sp.nch();
+  o->C = track ? 3 * o->n + 2 : 1;
+  o->C1 = track ? 5 : 1;
+  o->C2 = track ? 8 : 1;
+  o->f1 = 4 * o->A;
+  o->d1max = 0;
+  o->d2max = 4;
+  for (int l = 0; l < o->L; ++l) {
+    o->d1[l] = c->hidden_single[l];
+    o->d2[l] = c->hidden_double[l];
+    JQ_REQUIRE(o->d1[l] >= 1 && (l == o->L - 1 || o->d2[l] >= 1), JQ_ERR_INVALID_ARGUMENT, "ferminet: hidden dims");
+    if (o->d1[l] > o->d1max) o->d1max = o->d1[l];
+    if (l < o->L - 1 && o->d2[l] > o->d2max) o->d2max = o->d2[l];
+  }
+  o->in1 = o->f1 * (1 + o->nch) + 4 * o->nch;
+  JQ_REQUIRE(o->f1 != o->d1[0], JQ_ERR_UNSUPPORTED,
+             "ferminet: 4*n_atoms == hidden_dims_single[0] (input-layer residual) is not supported");
+  return JQ_OK;
+}
+
+struct FermiBufs {
+  float *ae, *h2a, *h2b, *y2, *g2, *x1, *ha, *hb, *y, *m, *cadd, *orb;
+  float *det_sign, *det_logabs, *det_grad, *det_lap;
+};
+
+static void fermi_carve(const FermiDims& d, long long W, JqArena& ar, FermiBufs* b) {
+  long long n = d.n, nn = (long long)d.n * d.n;
+  bool pairs = d.L > 1;
+  b->ae = ar.take<float>(W * n * d.C1 * d.f1);
+  b->h2a = ar.take<float>(W * nn * d.C2 * d.d2max);
+  b->h2b = pairs ? ar.take<float>(W * nn * d.C2 * d.d2max) : nullptr;
+  b->y2 = pairs ? ar.take<float>(W * nn * d.C2 * d.d2max) : nullptr;
+  b->g2 = ar.take<float>(W * n * d.C * d.nch * d.d2max);
+  b->x1 = ar.take<float>(W * n * d.C * d.in1);
+  b->ha = ar.take<float>(W * n * d.C * d.d1max);
+  b->hb = ar.take<float>(W * n * d.C * d.d1max);
+  b->y = ar.take<float>(W * n * d.C * d.d1max);
+  b->m = ar.take<float>(W * d.C * d.nch * d.d1max);
+  b->cadd = ar.take<float>(W * d.C * d.d1max);
+  b->orb = ar.take<float>(W * n * d.C * d.D * n);
+  b->det_sign = ar.take<float>(W * d.D);
+  b->det_logabs = ar.take<float>(W * d.D);
+  b->det_grad = ar.take<float>(W * d.D * (d.C > 1 ? 3 * n : 1));
+  b->det_lap = ar.take<float>(W * d.D);
+}
+
+size_t jq_ferminet_ws_bytes(const jaqmc_ferminet_config* c, long long W, int track) {
+  FermiDims d;
+  if (fermi_dims(c, track, &d) != JQ_OK) return 0;
+  JqArena ar(nullptr, 0);
+  FermiBufs b;
+  fermi_carve(d, W, ar, &b);
+  return ar.off;
+}
+
+int jq_ferminet_forward(const jaqmc_ferminet_config* c, const jaqmc_ferminet_params* p, const jaqmc_system* sys,
+                        const float* electrons, long long W, int track, void* ws, size_t ws_bytes, JqWfOut out,
+                        cudaStream_t st) {
+  FermiDims d;
+  int rc = fermi_dims(c, track, &d);
+  if (rc != JQ_OK) return rc;
+  JQ_REQUIRE(sys && sys->atoms && sys->n_atoms == d.A, JQ_ERR_INVALID_ARGUMENT, "ferminet: system/atoms mismatch");
+  JqArena ar(ws, ws_bytes);
+  FermiBufs b;
+  fermi_carve(d, W, ar, &b);
+  JQ_REQUIRE(ar.ok(), JQ_ERR_WORKSPACE_TOO_SMALL, "ferminet: workspace %zu < %zu bytes", ws_bytes, ar.off);
+  const int n = d.n, C = d.C;
+  const bool split = c->orbitals_spin_split && d.nch == 2;
+  for (int l = 0; l < d.L; ++l)
+    JQ_REQUIRE(p->single_kernel[l] && p->single_bias[l] && (l == d.L - 1 || (p->double_kernel[l] && p->double_bias[l])),
+               JQ_ERR_INVALID_ARGUMENT, "ferminet: null parameter in layer %d", l);
+  JQ_REQUIRE(p->orbital_kernel[0] && (!split || p->orbital_kernel[1]), JQ_ERR_INVALID_ARGUMENT,
+             "ferminet: null orbital kernel");
+  JQ_REQUIRE(c->envelope_type == JAQMC_ENVELOPE_NULL || (p->env_pi[0] && p->env_sigma[0] && (!split || (p->env_pi[1] && p->env_sigma[1]))),
+             JQ_ERR_INVALID_ARGUMENT, "ferminet: null envelope parameter");
+
+  // features: ae Local1 [W][n][C1][4A], ee Local2 [W][n*n][C2][4] (into h2a)
+  if ((rc = jq_launch_mol_features(electrons, sys->atoms, (int)W, d.sp, d.A, /*rescale=*/0, track, b.ae, b.h2a, st)))
+    return rc;
+
+  float* h2 = b.h2a;
+  float* h2n = b.h2b;
+  float* h = b.ha;
+  float* hn = b.hb;
+  int d2prev = 4, d1prev = d.f1;
+  for (int l = 0; l < d.L; ++l) {
+    const int fg = d.nch * d2prev;
+    if ((rc = jq_launch_pair_mean(h2, b.g2, (int)W, d.sp, d2prev, track, st))) return rc;
+    JqDenseArgs a;
+    memset(&a, 0, sizeof(a));
+    a.N = d.d1[l];
+    a.C = C;
+    a.n_sub = n;
+    a.n_tot = n;
+    a.j0 = 0;
+    a.G = W * n;
+    a.bias = p->single_bias[l];
+    a.out = b.y;
+    if (l == 0) {
+      if ((rc = jq_launch_concat_layer1(b.ae, b.g2, b.x1, (int)W, d.sp, d.f1, fg, track, st))) return rc;
+      a.src0 = b.x1;
+      a.k0 = d.in1;
+      a.w0 = p->single_kernel[0];
+      if ((rc = jq_launch_dense(a, st))) return rc;
+      if ((rc = jq_launch_tanh_fl(b.y, nullptr, h, W * n, C, d.d1[0], 0, st))) return rc;
+    } else {
+      // walker-wide part: cadd[w][c] = [mean_up h | mean_dn h] . K[d1prev : d1prev*(1+nch)]
+      if ((rc = jq_launch_spin_mean(h, b.m, (int)W, d.sp, C, d1prev, st))) return rc;
+      JqDenseArgs am;
+      memset(&am, 0, sizeof(am));
+      am.src0 = b.m;
+      am.k0 = d.nch * d1prev;
+      am.w0 = p->single_kernel[l] + (size_t)d1prev * d.d1[l];
+      am.out = b.cadd;
+      am.N = d.d1[l];
+      am.C = C;
+      am.n_sub = 1;
+      am.n_tot = 1;
+      am.G = W;
+      if ((rc = jq_launch_dense(am, st))) return rc;
+      a.src0 = h;
+      a.k0 = d1prev;
+      a.w0 = p->single_kernel[l];
+      a.src1 = b.g2;
+      a.k1 = fg;
+      a.w1 = p->single_kernel[l] + (size_t)d1prev * (1 + d.nch) * d.d1[l];
+      a.cadd = b.cadd;
+      if ((rc = jq_launch_dense(a, st))) return rc;
+      bool res = (d1prev == d.d1[l]);
+      if ((rc = jq_launch_tanh_fl(b.y, res ? h : nullptr, hn, W * n, C, d.d1[l], res ? 1 : 0, st))) return rc;
+      float* t = h;
+      h = hn;
+      hn = t;
+    }
+    d1prev = d.d1[l];
+    if (l < d.L - 1) {
+      JqDenseArgs a2;
+      memset(&a2, 0, sizeof(a2));
+      a2.src0 = h2;
+      a2.k0 = d2prev;
+      a2.w0 = p->double_kernel[l];
+      a2.bias = p->double_bias[l];
+      a2.out = b.y2;
+      a2.N = d.d2[l];
+      a2.C = d.C2;
+      a2.n_sub = n * n;
+      a2.n_tot = n * n;
+      a2.G = W * n * n;
+      if ((rc = jq_launch_dense(a2, st))) return rc;
+      bool res = (d2prev == d.d2[l]);
+      if ((rc = jq_launch_tanh_fl(b.y2, res ? h2 : nullptr, h2n, W * n * n, d.C2, d.d2[l], res ? 1 : 0, st))) return rc;
+      float* t = h2;
+      h2 = h2n;
+      h2n = t;
+      d2prev = d.d2[l];
+    }
+  }
+
+  // orbitals: per spin channel DenseGeneral (hidden -> ndets*n), no bias (output/orbital.py:59-78)
+  {
+    int nchan = split ? 2 : 1;
+    for (int s = 0; s < nchan; ++s) {
+      JqDenseArgs a;
+      memset(&a, 0, sizeof(a));
+      a.src0 = h;
+      a.k0 = d1prev;
+      a.w0 = p->orbital_kernel[s];
+      a.out = b.orb;
+      a.N = d.D * n;
+      a.C = C;
+      a.n_tot = n;
+      if (split) {
+        a.j0 = d.sp.lo(s);
+        a.n_sub = d.sp.hi(s) - d.sp.lo(s);
+      } else {
+        a.j0 = 0;
+        a.n_sub = n;
+      }
+      a.G = W * a.n_sub;
+      if ((rc = jq_launch_dense(a, st))) return rc;
+    }
+  }
+  JqEnvelopeArgs env;
+  env.type = c->envelope_type;
+  env.pi[0] = p->env_pi[0];
+  env.sigma[0] = p->env_sigma[0];
+  env.pi[1] = split ? p->env_pi[1] : nullptr;
+  env.sigma[1] = split ? p->env_sigma[1] : nullptr;
+  if ((rc = jq_launch_orb_envelope(b.orb, electrons, sys->atoms, env, (int)W, d.sp, d.A, d.D, track, st))) return rc;
+  if ((rc = jq_launch_logdet(b.orb, (int)W, n, d.D, track, b.det_sign, b.det_logabs, b.det_grad, b.det_lap, st)))
+    return rc;
+  if ((rc = jq_launch_logdet_combine(b.det_sign, b.det_logabs, b.det_grad, b.det_lap, (int)W, n, d.D, track, nullptr,
+                                     out.logpsi, out.sign, out.grad, out.lap, out.e_kin, st)))
+    return rc;
+  return JQ_OK;
+}

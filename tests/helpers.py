@@ -1,0 +1,104 @@
+"""Shared test utilities: float32 parameter trees from the oracle's initialisers, synthetic walkers, oracle
+evaluation of a walker batch, and the two runtimes (host emulation for CPU tests, CUDA for -m gpu tests)."""
+
+from __future__ import annotations
+
+import ctypes
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from jaqmc_b200 import _abi  # noqa: E402
+from jaqmc_b200._runtime import Runtime  # noqa: E402
+from oracle import estimators as OE  # noqa: E402
+from oracle import networks as ON  # noqa: E402
+
+F64 = torch.float64
+_emu_rt = None
+
+
+def emu_runtime() -> Runtime:
+    """Host-emulation build of the kernels (tests/emu) behind the product's own marshalling layer."""
+    global _emu_rt
+    if _emu_rt is None:
+        sys.path.insert(0, os.path.join(ROOT, "tests", "emu"))
+        import build_emu
+
+        lib = _abi.bind(ctypes.CDLL(build_emu.build()))
+        _emu_rt = Runtime(lib, "cpu", _emulation=True)
+    return _emu_rt
+
+
+def to_f32(tree, device="cpu"):
+    return ON.tree_map(lambda t: t.to(torch.float32).contiguous().to(device), tree)
+
+
+def round_f32(tree):
+    """float64 tree holding exactly the float32-representable values (so oracle and kernels see identical numbers)."""
+    return ON.tree_map(lambda t: t.to(torch.float32).to(F64), tree)
+
+
+def molecule(name):
+    """(atoms (A,3) float64, charges (A,), nspins)."""
+    if name == "Li":
+        return torch.zeros(1, 3, dtype=F64), torch.tensor([3.0], dtype=F64), (2, 1)
+    if name == "H":
+        return torch.zeros(1, 3, dtype=F64), torch.tensor([1.0], dtype=F64), (1, 0)
+    if name == "He":
+        return torch.zeros(1, 3, dtype=F64), torch.tensor([2.0], dtype=F64), (1, 1)
+    if name == "LiH":
+        return (torch.tensor([[0.0, 0.0, 0.0], [0.0, 0.0, 3.015]], dtype=F64), torch.tensor([3.0, 1.0], dtype=F64), (2, 2))
+    if name == "N2":
+        return (torch.tensor([[0.0, 0.0, -1.034], [0.0, 0.0, 1.034]], dtype=F64), torch.tensor([7.0, 7.0], dtype=F64), (7, 7))
+    raise KeyError(name)
+
+
+def synthetic_walkers(atoms, charges, nspins, W, seed=0):
+    """Electrons ~ N(atom, 1) assigned to atoms in proportion to nuclear charge (app/molecule/data.py:36-44 style)."""
+    g = torch.Generator().manual_seed(seed)
+    n = sum(nspins)
+    A = atoms.shape[0]
+    owners = []
+    z = charges.clone()
+    for _ in range(n):
+        i = int(torch.argmax(z))
+        owners.append(i)
+        z[i] -= 1.0
+    centers = atoms[torch.tensor(owners)]
+    el = centers[None] + torch.randn(W, n, 3, generator=g, dtype=F64)
+    return el.to(torch.float32).to(F64)  # exactly float32-representable
+
+
+def oracle_batch(logpsi_fn, electrons, atoms=None, charges=None, track=True):
+    """Evaluate the float64 oracle walker by walker.  ``logpsi_fn(e)`` -> (sign, logpsi)."""
+    W = electrons.shape[0]
+    out = dict(logpsi=[], sign=[], grad=[], lap=[], e_kin=[], e_pot=[])
+    for w in range(W):
+        e = electrons[w]
+        if track:
+            sign_holder = {}
+
+            def f(x):
+                s, lp = logpsi_fn(x)
+                sign_holder["s"] = s
+                return lp
+
+            v, g, lap = OE.forward_laplacian(f, e)
+            out["logpsi"].append(float(v))
+            out["sign"].append(float(sign_holder["s"]))
+            out["grad"].append(g.numpy())
+            out["lap"].append(float(lap))
+            out["e_kin"].append(float(-0.5 * lap - 0.5 * (g * g).sum()))
+        else:
+            s, lp = logpsi_fn(e)
+            out["logpsi"].append(float(lp))
+            out["sign"].append(float(s))
+        if charges is not None:
+            out["e_pot"].append(float(OE.potential_energy(e, atoms, charges)))
+    return {k: np.asarray(v) for k, v in out.items() if len(v)}
