@@ -1,0 +1,351 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path: local-energy evaluations per second (BASELINE.json's metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload n2|li|...]
+
+A *step* is one local-energy evaluation (forward-Laplacian kinetic + Coulomb potential + total) of the whole walker
+batch of the named system -- the estimator half of the reference's ``EvaluationWorkStage.compute_step``
+(workflow/stage/evaluation.py:190-192).  The walker batch is global (4096, the reference's ``workflow.batch_size``)
+and sharded over the ranks: strong scaling, as ``docs/guide/multi-device.md:25-29`` defines it.
+
+``value``   walkers * K / device time, inputs resident in HBM (max over ranks, CUDA events on the launch stream).
+``e2e``     the same metric through the public API (``FermiNetWavefunction.local_energy``) with the step's electrons
+            copied from pinned host memory and the per-walker local energies read back, inside the timed region.
+``roofline``the dominant kernel's achieved algorithmic throughput against the measured peak (MEASURED_PEAKS.json).
+``cpu_baseline`` / ``--impl reference``: the float32 ``torch.func.vmap`` port of the reference's CPU path
+            (oracle/, vmapped forward-Laplacian + potential) on the host cores, on a bounded sample of the workload.
+"""
+
+from __future__ import annotations
+
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+WORKLOADS = {
+    # name: (molecule, ndets, hidden_single, hidden_double, description)
+    "n2": ("N2", 16, (256,) * 4, (32,) * 4, "FermiNet-N2 (14 electrons, 16 dets, 256x4/32x4)"),
+    "li": ("Li", 16, (256,) * 4, (32,) * 4, "FermiNet-Li (3 electrons, 16 dets, 256x4/32x4)"),
+    "lih": ("LiH", 16, (256,) * 4, (32,) * 4, "FermiNet-LiH (4 electrons, 16 dets, 256x4/32x4)"),
+}
+METRIC = "local_energy_evals_per_sec"
+UNIT = "evals/s"
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return d, "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+# ---------------------------------------------------------------------------------------------
+# CPU arm: vmapped float32 port of the reference path (oracle/), bounded sample
+# ---------------------------------------------------------------------------------------------
+def cpu_rate(workload: str, budget_s: float, chunk: int = 64):
+    import helpers as H
+    from oracle import estimators as OE
+    from oracle import lap as L
+    from oracle import networks as ON
+
+    mol, ndets, hs, hd, _ = WORKLOADS[workload]
+    atoms, charges, nspins = H.molecule(mol)
+    p = ON.tree_map(lambda t: t.float(), ON.init_ferminet_params(nspins, atoms.shape[0], ndets, hs, hd, seed=1))
+    at, ch = atoms.float(), charges.float()
+
+    def one(e):
+        out = ON.ferminet_logpsi(p, L.seed(e), at, nspins)[1]
+        g = out.jac.reshape(-1)
+        return -0.5 * out.lap - 0.5 * (g * g).sum() + OE.potential_energy(e, at, ch)
+
+    f = torch.func.vmap(one)
+    el = H.synthetic_walkers(atoms, charges, nspins, chunk, seed=0).float()
+    f(el)  # warm-up
+    done, t0 = 0, time.perf_counter()
+    while True:
+        f(el)
+        done += chunk
+        dt = time.perf_counter() - t0
+        if dt >= budget_s:
+            break
+    return done / dt, done, torch.get_num_threads()
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    # K steps, each a bounded sample sized so the whole run ends within a few minutes
+    per_step = max(2.0, min(20.0, 120.0 / max(1, args.steps + args.warmup)))
+    rates, total = [], 0
+    for i in range(args.warmup + args.steps):
+        r, done, threads = cpu_rate(args.workload, per_step)
+        if i >= args.warmup:
+            rates.append(r)
+            total += done
+    value = float(np.mean(rates))
+    mol, ndets, hs, hd, desc = WORKLOADS[args.workload]
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * args.walkers / value, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{desc}, {args.walkers} walkers, forward-Laplacian local energy"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": f"{total} walkers in chunks of 64 (torch.func.vmap float32 port of the reference "
+                                   f"graph; jax/jaxlib are not installable offline), scaled per walker"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------
+# clocks sampler
+# ---------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.rows.append(ln.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            parts = [x.strip() for x in r.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx = float(parts[1])
+            except ValueError:
+                continue
+            for nm, v in zip(names, parts[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------------
+def parse_profile(rt):
+    buf = ctypes.create_string_buffer(1 << 16)
+    n = rt.lib.jaqmc_b200_profile_fetch(buf, len(buf))
+    out = {}
+    for ln in buf.raw[:n].decode().splitlines():
+        name, cnt, ms, fl, by = ln.split()
+        out[name] = {"launches": int(cnt), "ms": float(ms), "flops": float(fl), "bytes": float(by)}
+    return out
+
+
+def run_ours(args):
+    import helpers as H
+    from jaqmc_b200.data import MoleculeData
+    from jaqmc_b200.sampler import MCMCSampler, SamplePlan
+    from jaqmc_b200.wavefunction import FermiNetWavefunction
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = world > 1
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    if dist:
+        torch.distributed.init_process_group("nccl", device_id=dev)
+    if args.gpus != world and rank == 0:
+        print(f"warning: --gpus {args.gpus} but WORLD_SIZE={world}", file=sys.stderr)
+
+    mol, ndets, hs, hd, desc = WORKLOADS[args.workload]
+    atoms64, charges64, nspins = H.molecule(mol)
+    n = sum(nspins)
+    W = args.walkers
+    if W % world:
+        raise SystemExit(f"--walkers {W} not divisible by {world} ranks")
+    Wl = W // world
+    wf = FermiNetWavefunction(nspins=nspins, ndets=ndets, hidden_dims_single=list(hs), hidden_dims_double=list(hd))
+    atoms, charges = atoms64.float().to(dev), charges64.float().to(dev)
+    el_all = H.synthetic_walkers(atoms64, charges64, nspins, W, seed=0).float()
+    el_host = el_all[rank * Wl:(rank + 1) * Wl].contiguous().pin_memory()
+    data = MoleculeData(electrons=el_host.to(dev), atoms=atoms, charges=charges)
+    params = wf.init_params(data, 42)
+    # equilibrate a little so that no walker sits at a pathological random position
+    plan = SamplePlan(wf, MCMCSampler(steps=10))
+    st = plan.init(data)
+    gen = torch.Generator(device=dev).manual_seed(1234 + rank)
+    for _ in range(2):
+        data, _, st = plan.step(params, data, st, gen)
+    el_host.copy_(data.electrons.cpu())
+    from jaqmc_b200._runtime import runtime
+    rt = runtime(dev)
+    sums = torch.zeros(3, device=dev)
+
+    def step_resident():
+        sums.zero_()
+        out = wf.local_energy(params, data, sums=sums)
+        if dist:
+            torch.distributed.all_reduce(sums)  # the only cross-GPU traffic: energy statistics (3 floats)
+        return out
+
+    e_host = torch.empty(Wl, dtype=torch.float32).pin_memory()
+    el_dev = torch.empty_like(data.electrons)
+
+    def step_e2e():
+        el_dev.copy_(el_host, non_blocking=True)
+        sums.zero_()
+        out = wf.local_energy(params, MoleculeData(el_dev, atoms, charges), sums=sums)
+        if dist:
+            torch.distributed.all_reduce(sums)
+        e_host.copy_(out["e_loc"], non_blocking=True)
+        return out
+
+    def barrier():
+        if dist:
+            torch.distributed.barrier()
+        torch.cuda.synchronize(dev)
+
+    def timed(fn, k):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(k):
+            fn()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if dist:
+            t = torch.tensor([ms], device=dev)
+            torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+            ms = float(t)
+        return ms
+
+    for _ in range(max(3, args.warmup)):
+        step_resident()
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    rt.reset_launch_count()
+    ms = timed(step_resident, args.steps)
+    launches = rt.launch_count()
+    clk = clocks.stop() if rank == 0 else None
+    value = W * args.steps / (ms * 1e-3)
+
+    for _ in range(2):
+        step_e2e()
+    ms_e2e = timed(step_e2e, args.steps)
+    e2e_value = W * args.steps / (ms_e2e * 1e-3)
+    finite = bool(torch.isfinite(e_host).all())
+
+    # roofline leg: per-kernel CUDA events on the launch stream over the same steps (rank 0 only)
+    roof, kernels = None, None
+    if rank == 0:
+        rt.lib.jaqmc_b200_profile_enable(1)
+        for _ in range(min(args.steps, 3)):
+            wf.local_energy(params, data, sums=sums)
+        torch.cuda.synchronize(dev)
+        rt.lib.jaqmc_b200_profile_enable(0)
+        prof = parse_profile(rt)
+        tot_ms = sum(v["ms"] for v in prof.values()) or 1.0
+        kernels = {k: {"launches": v["launches"], "share": round(v["ms"] / tot_ms, 4),
+                       "ms_per_launch": round(v["ms"] / v["launches"], 4)} for k, v in prof.items()}
+        top = max(prof.items(), key=lambda kv: kv[1]["ms"])
+        peaks, src = load_peaks()
+        name, v = top
+        if v["flops"] > 0:
+            # split-TF32 (3 tensor-core passes per product) against one third of the measured dense bf16 ... TF32 runs at
+            # half the bf16 rate, so the split-precision peak is bf16/2/3.
+            peak = peaks["bf16_tflops_sustained"] / 2.0 / 3.0 if "tc" in name else None
+            ach = v["flops"] / (v["ms"] * 1e-3) / 1e12
+            if peak is None:
+                peak = peaks["bf16_tflops_sustained"] / 2.0 / 3.0
+            roof = {"kernel": name, "bound": "tensor", "achieved": round(ach, 3), "peak": round(peak, 1),
+                    "unit": "TFLOP/s", "frac": round(ach / peak, 4), "traffic": None,
+                    "peak_source": f"{src}: bf16_tflops_sustained/2 (tf32) /3 (split)", "share_of_step": kernels[name]["share"]}
+        else:
+            ach = v["bytes"] / (v["ms"] * 1e-3) / 1e9
+            roof = {"kernel": name, "bound": "hbm", "achieved": round(ach, 1), "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                    "frac": round(ach / peaks["hbm_gbs"], 4), "traffic": None, "peak_source": src,
+                    "share_of_step": kernels[name]["share"]}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        r, done, threads = cpu_rate(args.workload, args.cpu_seconds)
+        cpu = {"value": round(r, 2), "unit": UNIT, "cores": threads, "kind": "port",
+               "sample": f"{done} walkers of the same workload in chunks of 64 (float32 torch.func.vmap port of the "
+                         f"reference graph), scaled per walker"}
+
+    if rank == 0:
+        ws_gb = rt.workspace_bytes(wf._handle(params, atoms.shape[0]), Wl, True) / 1e9
+        line = {
+            "metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(3, args.warmup), "ms_per_step": round(ms / args.steps, 4), "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{desc}, {W} walkers global ({Wl}/GPU), forward-Laplacian local energy",
+                       "l2": f"no flush: each step streams a {ws_gb:.1f} GB working set (>> 126 MB L2) per GPU",
+                       "parallelism": f"walkers sharded over {world} GPU(s); all-reduce of 3 floats per step"},
+            "e2e": {"value": round(e2e_value, 1), "unit": UNIT, "h2d_bytes_per_step": int(Wl * n * 3 * 4) * world,
+                    "d2h_bytes_per_step": int(Wl * 4) * world, "finite": finite},
+            "gpu_launches": int(launches), "clocks": clk, "roofline": roof, "kernels": kernels,
+        }
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line), flush=True)
+    if dist:
+        torch.distributed.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="n2", choices=sorted(WORKLOADS))
+    ap.add_argument("--walkers", type=int, default=4096, help="global walker batch (reference workflow.batch_size)")
+    ap.add_argument("--cpu-seconds", type=float, default=15.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

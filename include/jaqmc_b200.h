@@ -142,6 +142,12 @@ int jaqmc_b200_mh_accept(float* x1, const float* x2, float* logprob1, const floa
 int64_t jaqmc_b200_launch_count(void);
 void jaqmc_b200_reset_launch_count(void);
 
+/* Per-kernel device timing for the roofline report (bench.py).  While enabled, every kernel launch on the calling
+ * thread is bracketed by CUDA events on its stream.  `fetch` waits for them and writes one text line per kernel,
+ * "name launches total_ms algorithmic_flops algorithmic_bytes", returning the bytes written. */
+void jaqmc_b200_profile_enable(int on);
+size_t jaqmc_b200_profile_fetch(char* buf, size_t cap);
+
 const char* jaqmc_b200_last_error(void);
 const char* jaqmc_b200_version(void);
 

@@ -87,6 +87,8 @@ PROTOTYPES = {
     ),
     "jaqmc_b200_launch_count": (C.c_int64, []),
     "jaqmc_b200_reset_launch_count": (None, []),
+    "jaqmc_b200_profile_enable": (None, [C.c_int]),
+    "jaqmc_b200_profile_fetch": (C.c_size_t, [C.c_char_p, C.c_size_t]),
     "jaqmc_b200_last_error": (C.c_char_p, []),
     "jaqmc_b200_version": (C.c_char_p, []),
 }

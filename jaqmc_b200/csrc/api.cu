@@ -14,8 +14,75 @@ void jq_set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
-#ifdef JAQMC_HOST_EMU
+// ------------------------------------------------------------------------------------------------
+// per-kernel profiler (device build only)
+// ------------------------------------------------------------------------------------------------
+#include <map>
+#include <string>
 #include <vector>
+thread_local int jq_prof_enabled = 0;
+static thread_local double jq_prof_next_flops = 0.0, jq_prof_next_bytes = 0.0;
+void jq_prof_work(double flops, double bytes) {
+  jq_prof_next_flops = flops;
+  jq_prof_next_bytes = bytes;
+}
+#ifndef JAQMC_HOST_EMU
+struct JqProfRec {
+  const char* name;
+  cudaEvent_t e0, e1;
+  double flops, bytes;
+};
+static thread_local std::vector<JqProfRec> jq_prof_recs;
+void jq_prof_before(const char* name, cudaStream_t st) {
+  JqProfRec r;
+  r.name = name;
+  r.flops = jq_prof_next_flops;
+  r.bytes = jq_prof_next_bytes;
+  jq_prof_next_flops = jq_prof_next_bytes = 0.0;
+  cudaEventCreate(&r.e0);
+  cudaEventCreate(&r.e1);
+  cudaEventRecord(r.e0, st);
+  jq_prof_recs.push_back(r);
+}
+void jq_prof_after(cudaStream_t st) { cudaEventRecord(jq_prof_recs.back().e1, st); }
+#endif
+
+extern "C" void jaqmc_b200_profile_enable(int on) { jq_prof_enabled = on; }
+
+// Synchronises the recorded events and writes one line per kernel: "name launches total_ms flops bytes\n".
+// Returns the number of bytes written (0 when nothing was recorded); clears the records.
+extern "C" size_t jaqmc_b200_profile_fetch(char* buf, size_t cap) {
+  size_t off = 0;
+#ifndef JAQMC_HOST_EMU
+  struct Agg { long long n = 0; double ms = 0, flops = 0, bytes = 0; };
+  std::map<std::string, Agg> agg;
+  for (auto& r : jq_prof_recs) {
+    cudaEventSynchronize(r.e1);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, r.e0, r.e1);
+    Agg& a = agg[r.name];
+    a.n += 1;
+    a.ms += ms;
+    a.flops += r.flops;
+    a.bytes += r.bytes;
+    cudaEventDestroy(r.e0);
+    cudaEventDestroy(r.e1);
+  }
+  jq_prof_recs.clear();
+  for (auto& kv : agg) {
+    int w = snprintf(buf + off, off < cap ? cap - off : 0, "%s %lld %.6f %.6e %.6e\n", kv.first.c_str(), kv.second.n,
+                     kv.second.ms, kv.second.flops, kv.second.bytes);
+    if (w < 0 || off + (size_t)w >= cap) break;
+    off += (size_t)w;
+  }
+#else
+  (void)buf;
+  (void)cap;
+#endif
+  return off;
+}
+
+#ifdef JAQMC_HOST_EMU
 thread_local jq_dim3 threadIdx, blockIdx, blockDim, gridDim;
 thread_local unsigned char* jq_emu_dyn_smem = nullptr;
 static thread_local std::vector<unsigned char> jq_emu_smem_store;

@@ -78,12 +78,21 @@ static __device__ __forceinline__ void sincosf_(float x, float* s, float* c) { s
 static inline cudaError_t cudaMemcpyAsyncD2D(void* d, const void* s, size_t n, cudaStream_t st) {
   return cudaMemcpyAsync(d, s, n, cudaMemcpyDeviceToDevice, st);
 }
+// Optional per-kernel device timing (bench.py's roofline leg): when enabled, every launch is bracketed by
+// two cudaEvents on the launching stream and tagged with the work the launcher declared via jq_prof_work().
+void jq_prof_before(const char* name, cudaStream_t st);
+void jq_prof_after(cudaStream_t st);
+extern thread_local int jq_prof_enabled;
 #define JQ_LAUNCH(kernel, grid, block, smem, stream, ...)                       \
   do {                                                                          \
     ++jq_launch_counter;                                                        \
+    if (jq_prof_enabled) jq_prof_before(#kernel, (stream));                     \
     kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);                 \
+    if (jq_prof_enabled) jq_prof_after((stream));                               \
   } while (0)
 #endif
+// Declares the algorithmic work (flops, bytes) of the NEXT launch for the profiler; no-op when disabled.
+void jq_prof_work(double flops, double bytes);
 
 // ------------------------------------------------------------------------------------------------
 // status codes returned through the C ABI (0 == ok); see include/jaqmc_b200.h

@@ -144,6 +144,7 @@ int jq_launch_dense(const JqDenseArgs& a, cudaStream_t st) {
 #endif
   long long R = a.G * a.C;
   dim3 grid(jq_cdiv(R, GM_BM), jq_cdiv(a.N, GM_BN));
+  jq_prof_work(2.0 * (double)R * (a.k0 + a.k1) * a.N, 4.0 * (double)R * (a.k0 + a.k1 + a.N));
   JQ_LAUNCH(k_dense_simt, grid, dim3(256), 0, st, a);
   JQ_CHECK_LAUNCH();
   return JQ_OK;
@@ -194,6 +195,7 @@ int jq_launch_tanh_fl(const float* y, const float* res, float* out, long long G,
   JQ_REQUIRE(residual_mode == 0 || res != nullptr, JQ_ERR_INVALID_ARGUMENT, "tanh_fl: residual without source");
   int grid = jq_cdiv(items, 256);
   if (grid > 148 * 32) grid = 148 * 32;
+  jq_prof_work(0.0, 4.0 * (double)G * C * F * (res ? 3 : 2));
   JQ_LAUNCH(k_tanh_fl, dim3(grid), dim3(256), 0, st, y, res, out, items, C, F, residual_mode);
   JQ_CHECK_LAUNCH();
   return JQ_OK;

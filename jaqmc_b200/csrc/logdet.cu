@@ -71,6 +71,7 @@ int jq_launch_orb_envelope(float* orb, const float* electrons, const float* atom
   if (items <= 0) return JQ_OK;
   int grid = jq_cdiv(items, 256);
   if (grid > 148 * 32) grid = 148 * 32;
+  jq_prof_work(0.0, 8.0 * (double)items * (track ? 3 * sp.n() + 2 : 1));
   JQ_LAUNCH(k_orb_envelope, dim3(grid), dim3(256), 0, st, orb, electrons, atoms, env, items, sp, A, D, track);
   JQ_CHECK_LAUNCH();
   return JQ_OK;
@@ -258,6 +259,7 @@ int jq_launch_logdet(const float* orb, int W, int n, int D, int track, float* de
   }
 #endif
   int threads = track ? 256 : 64;
+  jq_prof_work((double)blocks * (2.0 * n * n * n * (track ? (C - 1) * 2 + 1 : 0.34)), 4.0 * (double)blocks * C * n * n);
   JQ_LAUNCH(k_logdet, dim3((unsigned)blocks), dim3(threads), smem, st, orb, n, D, C, KC, det_sign, det_logabs,
             det_grad, det_lap);
   JQ_CHECK_LAUNCH();

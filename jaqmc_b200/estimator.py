@@ -1,0 +1,101 @@
+"""Energy estimators: host-side mirror of ``estimator/base.py`` (``PerWalkerEstimator``, ``mean_reduce``,
+``EstimatorPipeline``), ``estimator/kinetic/euclidean.py`` (``EuclideanKinetic``, forward-Laplacian mode),
+``app/molecule/hamiltonian.py`` (``potential_energy``) and ``estimator/total_energy.py`` (``TotalEnergy``).
+
+Batched like the wavefunction classes: ``evaluate_batch_walkers`` is the unit of work (the reference reaches it by
+``chunked_vmap`` of ``evaluate_single_walker``, estimator/base.py:251-270).
+"""
+
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+import torch
+
+from . import _marshal
+from ._runtime import runtime
+from .data import MoleculeData
+
+
+def mean_reduce(walker_stats: dict, include_variance: bool = True) -> dict:
+    """``pmean(nanmean(x))`` and variance ``E[x^2] - E[x]^2`` (estimator/base.py:27-53).  The cross-device mean is a
+    NCCL all-reduce of scalars when ``torch.distributed`` is initialised."""
+    dist = torch.distributed.is_available() and torch.distributed.is_initialized()
+    out = {}
+    for k, v in walker_stats.items():
+        m = torch.nanmean(v, dim=0)
+        m2 = torch.nanmean(v * v, dim=0) if include_variance else None
+        if dist:
+            ws = torch.distributed.get_world_size()
+            buf = torch.stack([m, m2]) if include_variance else m.reshape(1)
+            torch.distributed.all_reduce(buf)
+            buf = buf / ws
+            m = buf[0]
+            m2 = buf[1] if include_variance else None
+        out[k] = m
+        if include_variance:
+            out[f"{k}_var"] = m2 - m * m
+    return out
+
+
+def potential_energy(params, data: MoleculeData, prev_walker_stats=None, state=None, rngs=None):
+    """Coulomb potential per walker (app/molecule/hamiltonian.py:9-22) -> ``({"energy:potential": (W,)}, state)``."""
+    el = data.electrons.contiguous()
+    rt = runtime(el.device)
+    sysh = _marshal.system_handle(data.atoms, data.charges)
+    return {"energy:potential": rt.coulomb(sysh, el)}, state
+
+
+@dataclass
+class EuclideanKinetic:
+    """``E_kin = -1/2 (lap log|psi| + |grad log|psi||^2)`` by the forward Laplacian
+    (estimator/kinetic/euclidean.py:114-135).  ``f_log_psi`` is the wavefunction object."""
+
+    f_log_psi: object = None
+    mode: str = "forward_laplacian"
+    data_field: str = "electrons"
+
+    def __post_init__(self):
+        if self.mode != "forward_laplacian":
+            raise NotImplementedError("only LaplacianMode.forward_laplacian is implemented by the CUDA pipeline")
+
+    def evaluate_batch_walkers(self, params, data: MoleculeData, prev_walker_stats=None, state=None, rngs=None):
+        out = self.f_log_psi.local_energy(params, data)
+        stats = {"energy:kinetic": out["e_kin"]}
+        if prev_walker_stats is not None:
+            prev_walker_stats.setdefault("_fused", out)
+        return stats, state
+
+
+@dataclass
+class TotalEnergy:
+    """Sum of every ``energy:*`` key per walker (estimator/total_energy.py:36-60)."""
+
+    def evaluate_batch_walkers(self, params, data, prev_walker_stats, state=None, rngs=None):
+        keys = [k for k in prev_walker_stats if k.startswith("energy:")]
+        if not keys:
+            raise ValueError("TotalEnergy needs at least one 'energy:*' key from earlier estimators")
+        total = None
+        for k in keys:
+            v = prev_walker_stats[k]
+            if v.dim() != 1:
+                raise ValueError(f"Energy term {k!r} must be a scalar per walker, got shape {tuple(v.shape[1:])}")
+            total = v if total is None else total + v
+        return {"total_energy": total}, state
+
+
+class EstimatorPipeline:
+    """Runs estimators in insertion order, threading the accumulated per-walker stats
+    (estimator/base.py:331-362), then reduces them with :func:`mean_reduce`."""
+
+    def __init__(self, estimators: dict):
+        self.estimators = dict(estimators)
+
+    def evaluate(self, params, data: MoleculeData, state=None, rngs=None):
+        walker_stats: dict = {}
+        for name, est in self.estimators.items():
+            fn = est.evaluate_batch_walkers if hasattr(est, "evaluate_batch_walkers") else est
+            stats, _ = fn(params, data, walker_stats, state, rngs)
+            walker_stats.update(stats)
+        walker_stats.pop("_fused", None)
+        return mean_reduce(walker_stats), walker_stats

@@ -1,0 +1,16 @@
+#!/bin/bash
+# One gpurun call: GPU tests, smoke, bench, ncu launch list (+ optional full capture of one kernel).
+# usage: scripts/gpu_round.sh <tag> [ncu-kernel-regex]
+TAG=${1:-r1}
+KREGEX=${2:-}
+OUT=gpurun_out/$TAG
+mkdir -p $OUT
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw,memory.total --format=csv > $OUT/gpu.txt 2>&1
+echo "== pytest -m gpu" ; timeout 900 python -m pytest tests -m gpu -x -q -s > $OUT/pytest_gpu.log 2>&1 ; echo "pytest exit $?" ; tail -25 $OUT/pytest_gpu.log
+echo "== smoke" ; timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > $OUT/smoke.log 2>&1 ; echo "smoke exit $?" ; tail -5 $OUT/smoke.log
+echo "== bench" ; timeout 900 python bench.py --steps ${STEPS:-5} --warmup 3 > $OUT/bench.json 2> $OUT/bench.err ; echo "bench exit $?" ; tail -3 $OUT/bench.err ; cat $OUT/bench.json
+echo "== ncu launch list" ; timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/launches.csv python bench.py --steps 1 --warmup 1 --no-cpu-baseline > $OUT/ncu_bench.log 2>&1 ; echo "ncu exit $?"
+if [ -n "$KREGEX" ]; then
+  echo "== ncu full $KREGEX" ; timeout 900 ncu --set full --clock-control none --import-source on -k regex:$KREGEX -s 4 -c 2 -o $OUT/prof python bench.py --steps 1 --warmup 1 --no-cpu-baseline --walkers ${NCU_WALKERS:-1024} > $OUT/ncu_full.log 2>&1 ; echo "ncu full exit $?"; tail -3 $OUT/ncu_full.log
+fi
+ls -la $OUT
