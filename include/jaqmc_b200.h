@@ -131,6 +131,22 @@ int jaqmc_b200_mh_step(const jaqmc_wavefunction* wf, const jaqmc_system* sys, fl
                        int32_t n_steps, int64_t n_walkers, float* n_accept, uint8_t* accepted, void* workspace,
                        size_t workspace_bytes, jaqmc_stream_t stream);
 
+/* One dense layer under the forward Laplacian: replaces nn.Dense traced by forward_laplacian
+ * (laplacian/primitives/dot_general.py:377-407: one GEMM over the rows {x, J_1..J_K, L}, bias on the value row) fused
+ * with the tanh rule (laplacian/primitives/elementwise.py:42-72) and FermiNet's residual (backbone/ferminet.py:59-63).
+ *   x (n_groups, n_components, k0) [, x2 (.., k1) concatenated along the contraction axis with kernel2 (k1, n_out)],
+ *   kernel (k0, n_out), bias (n_out,) or NULL, addend (n_groups/groups_per_walker, n_components, n_out) or NULL
+ *   (broadcast over a walker's groups), residual / out (n_groups, n_components, n_out).
+ *   n_components = 1 (value only) or K+2 (value, K Jacobian columns, Laplacian).
+ *   activation 0 none | 1 tanh;  residual_mode 0 none | 1 (res + y)/sqrt(2) | 2 res + y.
+ *   use_tensor_cores != 0 routes eligible shapes (k0, k1 multiples of 32, 64 <= n_out <= 256) to the tcgen05 3xTF32
+ *   kernel and needs workspace >= 2*(k0+k1)*n_out floats; 0 forces the CUDA-core FP32 kernel. */
+int jaqmc_b200_dense_fl(const float* x, const float* x2, const float* kernel, const float* kernel2, const float* bias,
+                        const float* addend, const float* residual, float* out, int64_t n_groups, int32_t n_components,
+                        int32_t k0, int32_t k1, int32_t n_out, int32_t groups_per_walker, int32_t activation,
+                        int32_t residual_mode, int32_t use_tensor_cores, void* workspace, size_t workspace_bytes,
+                        jaqmc_stream_t stream);
+
 /* Building blocks of the MH step, exported for samplers that drive their own loop
  * (sampler/mcmc.py:53-54 gaussian_proposal; :128-137 accept/select). */
 int jaqmc_b200_mh_propose(const float* x1, const float* normals, const float* stddev, float* x2, int64_t count,

@@ -80,6 +80,11 @@ PROTOTYPES = {
         [C.POINTER(Wavefunction), C.POINTER(System), FloatP, FloatP, C.c_int32, FloatP, FloatP, FloatP, C.c_int32,
          C.c_int64, FloatP, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p],
     ),
+    "jaqmc_b200_dense_fl": (
+        C.c_int,
+        [FloatP, FloatP, FloatP, FloatP, FloatP, FloatP, FloatP, FloatP, C.c_int64, C.c_int32, C.c_int32, C.c_int32,
+         C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_size_t, C.c_void_p],
+    ),
     "jaqmc_b200_mh_propose": (C.c_int, [FloatP, FloatP, FloatP, FloatP, C.c_int64, C.c_void_p]),
     "jaqmc_b200_mh_accept": (
         C.c_int,

@@ -276,6 +276,42 @@ extern "C" int jaqmc_b200_local_energy(const jaqmc_wavefunction* wf, const jaqmc
   return JQ_OK;
 }
 
+extern "C" int jaqmc_b200_dense_fl(const float* x, const float* x2, const float* kernel, const float* kernel2,
+                                   const float* bias, const float* addend, const float* residual, float* out,
+                                   int64_t n_groups, int32_t n_components, int32_t k0, int32_t k1, int32_t n_out,
+                                   int32_t groups_per_walker, int32_t activation, int32_t residual_mode,
+                                   int32_t use_tensor_cores, void* workspace, size_t workspace_bytes,
+                                   jaqmc_stream_t stream) {
+  JQ_REQUIRE(n_groups >= 0 && n_components >= 1 && k0 >= 1 && k1 >= 0 && n_out >= 1 && groups_per_walker >= 1,
+             JQ_ERR_INVALID_ARGUMENT, "dense_fl: bad sizes");
+  JQ_REQUIRE(n_groups % groups_per_walker == 0, JQ_ERR_INVALID_ARGUMENT, "dense_fl: n_groups %% groups_per_walker != 0");
+  JqDenseArgs a;
+  memset(&a, 0, sizeof(a));
+  a.src0 = x;
+  a.k0 = k0;
+  a.src1 = x2;
+  a.k1 = k1;
+  a.w0 = kernel;
+  a.w1 = kernel2;
+  a.bias = bias;
+  a.cadd = addend;
+  a.res = residual;
+  a.out = out;
+  a.N = n_out;
+  a.C = n_components;
+  a.n_sub = a.n_tot = groups_per_walker;
+  a.G = n_groups;
+  a.act = activation;
+  a.res_mode = residual_mode;
+  if (use_tensor_cores) {
+    size_t need = jq_dense_tc_scratch_floats(k0 + k1, n_out) * sizeof(float);
+    JQ_REQUIRE(workspace && workspace_bytes >= need, JQ_ERR_WORKSPACE_TOO_SMALL, "dense_fl: workspace %zu < %zu bytes",
+               workspace_bytes, need);
+    a.wscratch = (float*)workspace;
+  }
+  return jq_launch_dense(a, (cudaStream_t)stream);
+}
+
 extern "C" int jaqmc_b200_mh_propose(const float* x1, const float* normals, const float* stddev, float* x2,
                                      int64_t count, jaqmc_stream_t stream) {
   JQ_REQUIRE(count >= 0 && (count == 0 || (x1 && normals && stddev && x2)), JQ_ERR_INVALID_ARGUMENT, "mh_propose: null buffer");

@@ -50,8 +50,16 @@ struct JqDenseArgs {
   // group mapping: launch covers G = W*n_sub groups; sub-group g' -> group (g'/n_sub)*n_tot + j0 + g'%n_sub
   int n_sub, n_tot, j0;
   long long G;
+  // fused epilogue: act 0 = none, 1 = tanh with the forward-Laplacian rule; then the optional residual
+  // res_mode 0 none, 1 (res + y)/sqrt(2) (FermiNet), 2 res + y; res has the layout of out
+  int act, res_mode;
+  const float* res;
+  // scratch for the tensor-core path's transposed hi/lo weight split: jq_dense_tc_scratch_floats(k0+k1, N) floats,
+  // or null to force the CUDA-core kernel
+  float* wscratch;
 };
 int jq_launch_dense(const JqDenseArgs& a, cudaStream_t st);
+size_t jq_dense_tc_scratch_floats(int k_total, int n_out);
 // out = act(y) or (res + act(y))/sqrt(2); act = tanh with the forward-Laplacian rule.  In-place allowed.
 int jq_launch_tanh_fl(const float* y, const float* res, float* out, long long G, int C, int F, int residual_mode,
                       cudaStream_t st);

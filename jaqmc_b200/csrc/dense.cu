@@ -132,8 +132,16 @@ __global__ void k_dense_simt(JqDenseArgs a) {
 int jq_launch_dense_tc(const JqDenseArgs& a, cudaStream_t st, bool* handled);  // dense_tc.cu
 #endif
 
+int jq_launch_tanh_fl_mapped(const JqDenseArgs& a, cudaStream_t st);
+#ifdef JAQMC_HOST_EMU
+size_t jq_dense_tc_scratch_floats(int k_total, int n_out) { return (size_t)2 * k_total * n_out; }
+#endif
+
 int jq_launch_dense(const JqDenseArgs& a, cudaStream_t st) {
   if (a.G <= 0 || a.N <= 0) return JQ_OK;
+  JQ_REQUIRE(a.act == 0 || a.act == 1, JQ_ERR_INVALID_ARGUMENT, "dense: unknown activation %d", a.act);
+  JQ_REQUIRE(a.res_mode == 0 || a.res != nullptr, JQ_ERR_INVALID_ARGUMENT, "dense: residual without source");
+  JQ_REQUIRE(a.act != 0 || a.res_mode == 0, JQ_ERR_INVALID_ARGUMENT, "dense: residual needs an activation");
   JQ_REQUIRE(a.k0 > 0 && a.src0 && a.w0 && a.out, JQ_ERR_INVALID_ARGUMENT, "dense: null operand");
   JQ_REQUIRE(a.k1 == 0 || (a.src1 && a.w1), JQ_ERR_INVALID_ARGUMENT, "dense: null second operand");
 #ifndef JAQMC_HOST_EMU
@@ -147,6 +155,7 @@ int jq_launch_dense(const JqDenseArgs& a, cudaStream_t st) {
   jq_prof_work(2.0 * (double)R * (a.k0 + a.k1) * a.N, 4.0 * (double)R * (a.k0 + a.k1 + a.N));
   JQ_LAUNCH(k_dense_simt, grid, dim3(256), 0, st, a);
   JQ_CHECK_LAUNCH();
+  if (a.act == 1) return jq_launch_tanh_fl_mapped(a, st);  // unfused epilogue, in place on `out`
   return JQ_OK;
 }
 
@@ -154,12 +163,12 @@ int jq_launch_dense(const JqDenseArgs& a, cudaStream_t st) {
 // tanh with the forward-Laplacian rule (+ FermiNet residual).  One item per (group, feature).
 //   residual_mode 0: out = tanh(y)     1: out = (res + tanh(y)) / sqrt(2)     2: out = res + tanh(y)
 // ------------------------------------------------------------------------------------------------
-__global__ void k_tanh_fl(const float* __restrict__ y, const float* __restrict__ res, float* __restrict__ out,
-                          long long items, int C, int F, int mode) {
+__global__ void k_tanh_fl(const float* y, const float* res, float* out, long long items, int C, int F, int mode,
+                          int n_sub, int n_tot, int j0) {
   const float inv_sqrt2 = 0.70710678118654752440f;
   for (long long it = (long long)blockIdx.x * blockDim.x + threadIdx.x; it < items;
        it += (long long)gridDim.x * blockDim.x) {
-    long long g = it / F;
+    long long g = jq_group_of(it / F, n_sub, n_tot, j0);
     int f = (int)(it % F);
     const float* yp = y + g * C * F + f;
     const float* rp = res ? res + g * C * F + f : nullptr;
@@ -196,7 +205,19 @@ int jq_launch_tanh_fl(const float* y, const float* res, float* out, long long G,
   int grid = jq_cdiv(items, 256);
   if (grid > 148 * 32) grid = 148 * 32;
   jq_prof_work(0.0, 4.0 * (double)G * C * F * (res ? 3 : 2));
-  JQ_LAUNCH(k_tanh_fl, dim3(grid), dim3(256), 0, st, y, res, out, items, C, F, residual_mode);
+  JQ_LAUNCH(k_tanh_fl, dim3(grid), dim3(256), 0, st, y, res, out, items, C, F, residual_mode, 1, 1, 0);
+  JQ_CHECK_LAUNCH();
+  return JQ_OK;
+}
+
+// epilogue of an unfused dense launch: in place on a.out, honouring the launch's group mapping
+int jq_launch_tanh_fl_mapped(const JqDenseArgs& a, cudaStream_t st) {
+  long long items = a.G * a.N;
+  int grid = jq_cdiv(items, 256);
+  if (grid > 148 * 32) grid = 148 * 32;
+  jq_prof_work(0.0, 4.0 * (double)a.G * a.C * a.N * (a.res ? 3 : 2));
+  JQ_LAUNCH(k_tanh_fl, dim3(grid), dim3(256), 0, st, a.out, a.res, a.out, items, a.C, a.N, a.res_mode, a.n_sub, a.n_tot,
+            a.j0);
   JQ_CHECK_LAUNCH();
   return JQ_OK;
 }

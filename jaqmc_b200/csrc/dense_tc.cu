@@ -1,10 +1,538 @@
-// tcgen05 / TMEM / TMA split-TF32 augmented-row GEMM (sm_100a).  Placeholder until the kernel lands:
-// reports "not handled" so jq_launch_dense uses the CUDA-core kernel.
+// Augmented-row dense layer on the 5th-generation tensor cores (sm_100a): tcgen05.mma kind::tf32 with the
+// accumulator in TMEM, operands staged in shared memory by TMA, FP32-faithful 3xTF32 split arithmetic, and the
+// bias / per-walker addend / tanh forward-Laplacian / residual epilogue fused.
+//
+// Orientation ("swap AB"): the MMA's M dimension is the layer's OUTPUT FEATURES and its N dimension is the
+// tile's ROWS {x, J_1..J_K, L} of a few whole (walker, electron) groups:
+//     D[f, r] = sum_k Wt[f, k] * X[r, k]          A = Wt (out x in, K-major), B = X (rows x in, K-major)
+// so a TMEM lane holds one output feature and its columns are the rows of the groups.  The epilogue thread that
+// owns lane f reads x, every J_k and L of a group from its own lane: the tanh rule's sum_k J_k^2 is a private
+// serial reduction (no shuffles), and for a fixed row the 32 lanes of a warp write 32 consecutive floats.
+//
+// 3xTF32: X = Xh + Xl, W = Wh + Wl with every part exactly representable in TF32 (cvt.rna), and
+//     D = Wh.Xh + Wl.Xh + Wh.Xl      (Wl.Xl ~ 2^-22 relative, dropped)
+// accumulated in FP32 in TMEM.  Wh/Wl are produced once per call by a small transpose+split kernel; Xh/Xl are
+// produced in shared memory by a converter warpgroup from the raw FP32 tile that TMA landed, so activations cross
+// L2->SMEM once.
+//
+// Warp roles (512 threads, 1 CTA/SM, persistent over tiles):
+//   warp 0      TMA producer            warp 1      MMA issuer (+ TMEM alloc/dealloc)
+//   warps 4-7   converter (hi/lo split) warps 8-15  epilogue (warps 8-11: features 0-127, 12-15: 128-255)
+// Pipelines: smem ring  full[s] (TMA->converter) -> ready[s] (converter->MMA) -> empty[s] (MMA commit->TMA);
+//            accumulator acc_full (MMA commit->epilogue) / acc_empty (epilogue->MMA).
+#include <cuda.h>
+
 #include "aug.cuh"
 
+namespace {
+
+constexpr int TC_BK = 32;          // K chunk: 32 floats = 128 B = one SWIZZLE_128B row
+constexpr int TC_NMAX = 176;       // max MMA N (rows per tile)
+constexpr int TC_STAGES = 2;
+constexpr int TC_MBLK = 128;       // features per MMA
+constexpr int TC_X_BYTES = TC_NMAX * 128;        // 22528 (multiple of 1024)
+constexpr int TC_W_BYTES = 2 * TC_MBLK * 128;    // 32768: both 128-feature blocks
+constexpr int TC_STAGE_BYTES = 2 * TC_X_BYTES + 2 * TC_W_BYTES;  // Xh, Xl, Wh, Wl
+constexpr int TC_SMEM_BYTES = TC_STAGES * TC_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int TC_THREADS = 512;
+constexpr int TC_TMEM_COLS = 512;
+
+struct TcParams {
+  // problem
+  int n_rows_tile;   // G_t * C
+  int n_mma;         // roundup16(n_rows_tile)
+  int G_t, C, N_out, mblocks;
+  int kchunks0, kchunks1;
+  long long tiles, tiles_per_w;
+  int n_sub, n_tot, j0;    // TMA-side grouping (flat launches use n_sub = n_tot = all groups, one "walker")
+  int n_tot_true;          // electrons per walker (for the per-walker addend)
+  long long G_sub_total;   // total sub-groups covered (W * n_sub)
+  const float* bias;
+  const float* cadd;
+  const float* res;
+  float* out;
+  int act;       // 0 raw, 1 tanh forward-Laplacian
+  int res_mode;  // 0 none, 1 (res + y)/sqrt2, 2 res + y
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "DONE:\n\t"
+      "}" ::"r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+// D[tmem] (+)= A[smem desc] * B[smem desc], kind::tf32, M=128
+__device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// K-major, SWIZZLE_128B operand descriptor: 8-row atoms of 1024 B (SBO), rows of 128 B.
+__device__ __forceinline__ uint64_t tc_smem_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)1 << 16;                    // LBO (ignored for swizzled K-major), 16 B
+  d |= (uint64_t)(1024 >> 4) << 32;          // SBO = 1024 B between 8-row atoms
+  d |= (uint64_t)1 << 46;                    // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;                    // SWIZZLE_128B
+  return d;
+}
+__device__ __forceinline__ uint32_t tc_idesc(int M, int N) {
+  // c_format F32 (1) @4, a_format TF32 (2) @7, b_format TF32 (2) @10, K-major A and B, N>>3 @17, M>>4 @24
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
+  uint32_t r[8];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ float tmem_ld1(uint32_t taddr) {
+  uint32_t r;
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r) : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+  return __uint_as_float(r);
+}
+__device__ __forceinline__ float tf32_rna(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+
+struct PipeState {
+  int stage = 0;
+  uint32_t phase = 0;
+  __device__ __forceinline__ void advance() {
+    if (++stage == TC_STAGES) {
+      stage = 0;
+      phase ^= 1;
+    }
+  }
+};
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+k_dense_tc(const __grid_constant__ CUtensorMap mapX0, const __grid_constant__ CUtensorMap mapX1,
+           const __grid_constant__ CUtensorMap mapWh, const __grid_constant__ CUtensorMap mapWl, TcParams p) {
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + TC_STAGES * TC_STAGE_BYTES);
+  uint64_t* full = bars;                   // [TC_STAGES]  TMA -> converter
+  uint64_t* ready = bars + TC_STAGES;      // [TC_STAGES]  converter -> MMA
+  uint64_t* empty = bars + 2 * TC_STAGES;  // [TC_STAGES]  MMA -> TMA
+  uint64_t* acc_full = bars + 3 * TC_STAGES;
+  uint64_t* acc_empty = acc_full + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int kchunks = p.kchunks0 + p.kchunks1;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < TC_STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&ready[s], 4);   // one arrive per converter warp
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(acc_full, 1);
+    mbar_init(acc_empty, 8);     // one arrive per epilogue warp
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"(TC_TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      PipeState ps;
+      const uint32_t stage_tx = (uint32_t)(p.n_mma * 128 + 2 * p.mblocks * TC_MBLK * 128);
+      for (long long t = blockIdx.x; t < p.tiles; t += gridDim.x) {
+        long long w = t / p.tiles_per_w;
+        int gsub0 = (int)(t % p.tiles_per_w) * p.G_t;
+        int row0 = (p.j0 + gsub0) * p.C;
+        for (int kc = 0; kc < kchunks; ++kc) {
+          mbar_wait(&empty[ps.stage], ps.phase ^ 1);
+          unsigned char* st = smem + ps.stage * TC_STAGE_BYTES;
+          mbar_expect_tx(&full[ps.stage], stage_tx);
+          if (kc < p.kchunks0)
+            tma_load_3d(st, &mapX0, &full[ps.stage], kc * TC_BK, row0, (int)w);
+          else
+            tma_load_3d(st, &mapX1, &full[ps.stage], (kc - p.kchunks0) * TC_BK, row0, (int)w);
+          for (int mb = 0; mb < p.mblocks; ++mb) {
+            tma_load_2d(st + 2 * TC_X_BYTES + mb * TC_MBLK * 128, &mapWh, &full[ps.stage], kc * TC_BK, mb * TC_MBLK);
+            tma_load_2d(st + 2 * TC_X_BYTES + TC_W_BYTES + mb * TC_MBLK * 128, &mapWl, &full[ps.stage], kc * TC_BK,
+                        mb * TC_MBLK);
+          }
+          ps.advance();
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      PipeState ps;
+      uint32_t acc_phase = 0;
+      const uint32_t idesc = tc_idesc(TC_MBLK, p.n_mma);
+      for (long long t = blockIdx.x; t < p.tiles; t += gridDim.x) {
+        mbar_wait(acc_empty, acc_phase ^ 1);   // epilogue has drained the accumulators of the previous tile
+        tc_fence_after();
+        for (int kc = 0; kc < kchunks; ++kc) {
+          mbar_wait(&ready[ps.stage], ps.phase);
+          tc_fence_after();
+          const uint32_t sbase = smem_u32(smem + ps.stage * TC_STAGE_BYTES);
+          const uint32_t xh = sbase, xl = sbase + TC_X_BYTES;
+          const uint32_t wh = sbase + 2 * TC_X_BYTES, wl = wh + TC_W_BYTES;
+          for (int mb = 0; mb < p.mblocks; ++mb) {
+            const uint32_t d = tmem_base + mb * 256;
+            const uint32_t wh_mb = wh + mb * TC_MBLK * 128, wl_mb = wl + mb * TC_MBLK * 128;
+#pragma unroll
+            for (int kk = 0; kk < TC_BK / 8; ++kk) {
+              const uint32_t ko = kk * 32;  // 8 tf32 = 32 bytes along K inside the 128 B swizzle row
+              tc_mma_tf32(d, tc_smem_desc(wh_mb + ko), tc_smem_desc(xh + ko), idesc, (kc | kk) ? 1u : 0u);
+              tc_mma_tf32(d, tc_smem_desc(wl_mb + ko), tc_smem_desc(xh + ko), idesc, 1u);
+              tc_mma_tf32(d, tc_smem_desc(wh_mb + ko), tc_smem_desc(xl + ko), idesc, 1u);
+            }
+          }
+          tc_commit(&empty[ps.stage]);   // stage reusable once these MMAs have read it
+          ps.advance();
+        }
+        tc_commit(acc_full);
+        acc_phase ^= 1;
+      }
+    }
+  } else if (warp >= 4 && warp < 8) {
+    // ===================== converter: raw FP32 -> TF32 hi (in place) and lo =====================
+    PipeState ps;
+    const int ct = threadIdx.x - 128;  // 0..127
+    const int nvec = p.n_mma * 8;      // float4 per X chunk (128 B rows)
+    for (long long t = blockIdx.x; t < p.tiles; t += gridDim.x) {
+      for (int kc = 0; kc < kchunks; ++kc) {
+        mbar_wait(&full[ps.stage], ps.phase);
+        float4* xh = reinterpret_cast<float4*>(smem + ps.stage * TC_STAGE_BYTES);
+        float4* xl = reinterpret_cast<float4*>(smem + ps.stage * TC_STAGE_BYTES + TC_X_BYTES);
+        for (int i = ct; i < nvec; i += 128) {
+          float4 v = xh[i];
+          float4 h, l;
+          h.x = tf32_rna(v.x); l.x = tf32_rna(v.x - h.x);
+          h.y = tf32_rna(v.y); l.y = tf32_rna(v.y - h.y);
+          h.z = tf32_rna(v.z); l.z = tf32_rna(v.z - h.z);
+          h.w = tf32_rna(v.w); l.w = tf32_rna(v.w - h.w);
+          xh[i] = h;
+          xl[i] = l;
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the MMA
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&ready[ps.stage]);
+        ps.advance();
+      }
+    }
+  } else if (warp >= 8) {
+    // ===================== epilogue =====================
+    const int q = warp & 3;            // TMEM lane quarter this warp may access
+    const int mb = (warp - 8) >> 2;    // feature block
+    const int f = mb * TC_MBLK + q * 32 + lane;
+    const bool f_ok = (mb < p.mblocks) && (f < p.N_out);
+    const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16) + mb * 256;
+    const float inv_sqrt2 = 0.70710678118654752440f;
+    const float bias_f = (p.bias && f_ok) ? p.bias[f] : 0.f;
+    uint32_t acc_phase = 0;
+    const int C = p.C;
+    for (long long t = blockIdx.x; t < p.tiles; t += gridDim.x) {
+      long long w_tma = t / p.tiles_per_w;
+      int gsub0 = (int)(t % p.tiles_per_w) * p.G_t;
+      mbar_wait(acc_full, acc_phase);
+      tc_fence_after();
+      if (mb < p.mblocks) {
+        for (int gi = 0; gi < p.G_t; ++gi) {
+          int gsub = gsub0 + gi;
+          if (gsub >= p.n_sub) break;  // warp-uniform
+          long long g = w_tma * p.n_tot + p.j0 + gsub;       // actual group index
+          long long orow = g * C;                              // first output row of the group
+          const float* cadd = p.cadd ? p.cadd + ((g / p.n_tot_true) * C) * (long long)p.N_out + f : nullptr;
+          const float* res = p.res ? p.res + orow * p.N_out + f : nullptr;
+          float* out = p.out + orow * p.N_out + f;
+          const uint32_t tcol = tlane + gi * C;
+          if (p.act == 0) {
+            for (int c0 = 0; c0 < C; c0 += 8) {
+              float v[8];
+              if (c0 + 8 <= C) {
+                tmem_ld8(tcol + c0, v);
+              } else {
+                for (int i = 0; i < C - c0; ++i) v[i] = tmem_ld1(tcol + c0 + i);
+              }
+              int nc = (C - c0 < 8) ? C - c0 : 8;
+              if (f_ok)
+                for (int i = 0; i < nc; ++i) {
+                  int c = c0 + i;
+                  float y = v[i];
+                  if (cadd) y += cadd[(long long)c * p.N_out];
+                  if (c == 0) y += bias_f;
+                  out[(long long)c * p.N_out] = y;
+                }
+            }
+          } else {
+            float x = tmem_ld1(tcol);
+            if (cadd && f_ok) x += cadd[0];
+            x += bias_f;
+            float th = tanhf(x);
+            float d1 = 1.0f - th * th;
+            float s2 = 0.f;
+            const int nj = C - 2;
+            for (int c0 = 0; c0 < nj; c0 += 8) {
+              float v[8];
+              int nc = (nj - c0 < 8) ? nj - c0 : 8;
+              if (nc == 8) {
+                tmem_ld8(tcol + 1 + c0, v);
+              } else {
+                for (int i = 0; i < nc; ++i) v[i] = tmem_ld1(tcol + 1 + c0 + i);
+              }
+              if (f_ok)
+                for (int i = 0; i < nc; ++i) {
+                  long long c = 1 + c0 + i;
+                  float y = v[i];
+                  if (cadd) y += cadd[c * p.N_out];
+                  s2 = fmaf(y, y, s2);
+                  float o = d1 * y;
+                  if (p.res_mode == 1) o = (res[c * p.N_out] + o) * inv_sqrt2;
+                  else if (p.res_mode == 2) o = res[c * p.N_out] + o;
+                  out[c * p.N_out] = o;
+                }
+            }
+            if (C > 1) {
+              float yl = tmem_ld1(tcol + C - 1);
+              if (f_ok) {
+                long long c = C - 1;
+                if (cadd) yl += cadd[c * p.N_out];
+                float l = d1 * yl - 2.0f * th * d1 * s2;
+                if (p.res_mode == 1) l = (res[c * p.N_out] + l) * inv_sqrt2;
+                else if (p.res_mode == 2) l = res[c * p.N_out] + l;
+                out[c * p.N_out] = l;
+              }
+            }
+            if (f_ok) {
+              float o = th;
+              if (p.res_mode == 1) o = (res[0] + th) * inv_sqrt2;
+              else if (p.res_mode == 2) o = res[0] + th;
+              out[0] = o;
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(acc_empty);
+      acc_phase ^= 1;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TC_TMEM_COLS) : "memory");
+  }
+}
+
+// Wt_hi / Wt_lo [N_out][Kt] (K-major) from the flax kernel rows w0 [k0][N], w1 [k1][N].
+__global__ void k_weight_split_t(const float* __restrict__ w0, int k0, const float* __restrict__ w1, int k1, int N,
+                                 float* __restrict__ wh, float* __restrict__ wl) {
+  const int kt = k0 + k1;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < (long long)N * kt;
+       i += (long long)gridDim.x * blockDim.x) {
+    int k = (int)(i % kt);
+    int f = (int)(i / kt);
+    float v = (k < k0) ? w0[(long long)k * N + f] : w1[(long long)(k - k0) * N + f];
+    float h = tf32_rna(v);
+    wh[i] = h;
+    wl[i] = tf32_rna(v - h);
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// dims are innermost-first; strides (bytes) for dims 1..rank-1
+int make_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides,
+             const cuuint32_t* box) {
+  EncodeTiledFn enc = get_encode();
+  JQ_REQUIRE(enc != nullptr, JQ_ERR_CUDA, "dense_tc: cuTensorMapEncodeTiled is unavailable");
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void*>(base), dims, strides, box,
+                   estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  JQ_REQUIRE(r == CUDA_SUCCESS, JQ_ERR_CUDA, "dense_tc: cuTensorMapEncodeTiled failed with %d", (int)r);
+  return JQ_OK;
+}
+
+int pick_groups_per_tile(int C) {
+  int g = TC_NMAX / C;
+  return g < 1 ? 0 : g;
+}
+
+}  // namespace
+
+size_t jq_dense_tc_scratch_floats(int k_total, int n_out) { return (size_t)2 * k_total * n_out; }
+
+bool jq_dense_tc_eligible(const JqDenseArgs& a) {
+  if (a.C > TC_NMAX) return false;
+  if (a.k0 % TC_BK || a.k1 % TC_BK) return false;
+  if (a.k0 + a.k1 < 64) return false;
+  if (a.N < 64 || a.N > 2 * TC_MBLK) return false;
+  if (!a.wscratch) return false;
+  if ((reinterpret_cast<uintptr_t>(a.src0) & 15) || (a.src1 && (reinterpret_cast<uintptr_t>(a.src1) & 15))) return false;
+  return true;
+}
+
 int jq_launch_dense_tc(const JqDenseArgs& a, cudaStream_t st, bool* handled) {
-  (void)a;
-  (void)st;
   *handled = false;
+  if (!jq_dense_tc_eligible(a)) return JQ_OK;
+  static int sm_count = 0;
+  static bool attr_set = false;
+  if (!attr_set) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
+    cudaError_t e = cudaFuncSetAttribute(k_dense_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
+    JQ_REQUIRE(e == cudaSuccess, JQ_ERR_CUDA, "dense_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    attr_set = true;
+  }
+  const int kt = a.k0 + a.k1;
+  float* wh = a.wscratch;
+  float* wl = a.wscratch + (size_t)kt * a.N;
+  {
+    long long items = (long long)kt * a.N;
+    int grid = jq_cdiv(items, 256);
+    if (grid > 148 * 4) grid = 148 * 4;
+    JQ_LAUNCH(k_weight_split_t, dim3(grid), dim3(256), 0, st, a.w0, a.k0, a.w1, a.k1, a.N, wh, wl);
+    JQ_CHECK_LAUNCH();
+  }
+  TcParams p;
+  memset(&p, 0, sizeof(p));
+  p.C = a.C;
+  p.G_t = pick_groups_per_tile(a.C);
+  p.N_out = a.N;
+  p.mblocks = jq_cdiv(a.N, TC_MBLK);
+  p.kchunks0 = a.k0 / TC_BK;
+  p.kchunks1 = a.k1 / TC_BK;
+  p.n_tot_true = a.n_tot;
+  long long Wn;  // number of TMA "walkers" (outer dimension)
+  if (a.n_sub == a.n_tot) {
+    // flat: all groups are contiguous
+    p.n_sub = p.n_tot = 0;  // set below (may exceed int for huge problems: guarded)
+    JQ_REQUIRE(a.G <= 0x7fffffffLL / a.C, JQ_ERR_UNSUPPORTED, "dense_tc: too many rows");
+    p.n_sub = p.n_tot = (int)a.G;
+    p.j0 = 0;
+    Wn = 1;
+  } else {
+    p.n_sub = a.n_sub;
+    p.n_tot = a.n_tot;
+    p.j0 = a.j0;
+    Wn = a.G / a.n_sub;
+  }
+  if (p.G_t > p.n_sub) p.G_t = p.n_sub;
+  p.n_rows_tile = p.G_t * a.C;
+  p.n_mma = (p.n_rows_tile + 15) / 16 * 16;
+  p.tiles_per_w = jq_cdiv(p.n_sub, p.G_t);
+  p.tiles = p.tiles_per_w * Wn;
+  p.G_sub_total = a.G;
+  p.bias = a.bias;
+  p.cadd = a.cadd;
+  p.res = a.res;
+  p.out = a.out;
+  p.act = a.act;
+  p.res_mode = a.res_mode;
+
+  CUtensorMap mX0, mX1, mWh, mWl;
+  {
+    cuuint64_t dims[3] = {(cuuint64_t)a.k0, (cuuint64_t)p.n_tot * a.C, (cuuint64_t)Wn};
+    cuuint64_t str[2] = {(cuuint64_t)a.k0 * 4, (cuuint64_t)p.n_tot * a.C * a.k0 * 4};
+    cuuint32_t box[3] = {TC_BK, (cuuint32_t)p.n_mma, 1};
+    int rc = make_map(&mX0, a.src0, 3, dims, str, box);
+    if (rc) return rc;
+    if (a.k1 > 0) {
+      cuuint64_t dims1[3] = {(cuuint64_t)a.k1, (cuuint64_t)p.n_tot * a.C, (cuuint64_t)Wn};
+      cuuint64_t str1[2] = {(cuuint64_t)a.k1 * 4, (cuuint64_t)p.n_tot * a.C * a.k1 * 4};
+      rc = make_map(&mX1, a.src1, 3, dims1, str1, box);
+      if (rc) return rc;
+    } else {
+      mX1 = mX0;
+    }
+    cuuint64_t wd[2] = {(cuuint64_t)kt, (cuuint64_t)a.N};
+    cuuint64_t ws[1] = {(cuuint64_t)kt * 4};
+    cuuint32_t wbox[2] = {TC_BK, TC_MBLK};
+    rc = make_map(&mWh, wh, 2, wd, ws, wbox);
+    if (rc) return rc;
+    rc = make_map(&mWl, wl, 2, wd, ws, wbox);
+    if (rc) return rc;
+  }
+  long long grid = p.tiles < sm_count ? p.tiles : sm_count;
+  double R = (double)a.G * a.C;
+  jq_prof_work(2.0 * R * kt * a.N, 4.0 * R * (kt + a.N * (a.res ? 2 : 1)));
+  JQ_LAUNCH(k_dense_tc, dim3((unsigned)grid), dim3(TC_THREADS), TC_SMEM_BYTES, st, mX0, mX1, mWh, mWl, p);
+  JQ_CHECK_LAUNCH();
+  *handled = true;
   return JQ_OK;
 }

@@ -51,7 +51,7 @@ static int fermi_dims(const jaqmc_ferminet_config* c, int track, FermiDims* o) {
 }
 
 struct FermiBufs {
-  float *ae, *h2a, *h2b, *y2, *g2, *x1, *ha, *hb, *y, *m, *cadd, *orb;
+  float *ae, *h2a, *h2b, *g2, *x1, *ha, *hb, *m, *cadd, *orb, *wscr;
   float *det_sign, *det_logabs, *det_grad, *det_lap;
 };
 
@@ -61,15 +61,19 @@ static void fermi_carve(const FermiDims& d, long long W, JqArena& ar, FermiBufs*
   b->ae = ar.take<float>(W * n * d.C1 * d.f1);
   b->h2a = ar.take<float>(W * nn * d.C2 * d.d2max);
   b->h2b = pairs ? ar.take<float>(W * nn * d.C2 * d.d2max) : nullptr;
-  b->y2 = pairs ? ar.take<float>(W * nn * d.C2 * d.d2max) : nullptr;
   b->g2 = ar.take<float>(W * n * d.C * d.nch * d.d2max);
   b->x1 = ar.take<float>(W * n * d.C * d.in1);
   b->ha = ar.take<float>(W * n * d.C * d.d1max);
   b->hb = ar.take<float>(W * n * d.C * d.d1max);
-  b->y = ar.take<float>(W * n * d.C * d.d1max);
   b->m = ar.take<float>(W * d.C * d.nch * d.d1max);
   b->cadd = ar.take<float>(W * d.C * d.d1max);
   b->orb = ar.take<float>(W * n * d.C * d.D * n);
+  {
+    int kmax = d.d1max * (1 + d.nch) + d.nch * d.d2max;
+    if (d.in1 > kmax) kmax = d.in1;
+    int nmax = d.d1max > d.D * d.n ? d.d1max : d.D * d.n;
+    b->wscr = ar.take<float>(jq_dense_tc_scratch_floats(kmax, nmax));
+  }
   b->det_sign = ar.take<float>(W * d.D);
   b->det_logabs = ar.take<float>(W * d.D);
   b->det_grad = ar.take<float>(W * d.D * (d.C > 1 ? 3 * n : 1));
@@ -127,14 +131,15 @@ int jq_ferminet_forward(const jaqmc_ferminet_config* c, const jaqmc_ferminet_par
     a.j0 = 0;
     a.G = W * n;
     a.bias = p->single_bias[l];
-    a.out = b.y;
+    a.act = 1;
+    a.wscratch = b.wscr;
     if (l == 0) {
       if ((rc = jq_launch_concat_layer1(b.ae, b.g2, b.x1, (int)W, d.sp, d.f1, fg, track, st))) return rc;
       a.src0 = b.x1;
       a.k0 = d.in1;
       a.w0 = p->single_kernel[0];
+      a.out = h;
       if ((rc = jq_launch_dense(a, st))) return rc;
-      if ((rc = jq_launch_tanh_fl(b.y, nullptr, h, W * n, C, d.d1[0], 0, st))) return rc;
     } else {
       // walker-wide part: cadd[w][c] = [mean_up h | mean_dn h] . K[d1prev : d1prev*(1+nch)]
       if ((rc = jq_launch_spin_mean(h, b.m, (int)W, d.sp, C, d1prev, st))) return rc;
@@ -149,6 +154,7 @@ int jq_ferminet_forward(const jaqmc_ferminet_config* c, const jaqmc_ferminet_par
       am.n_sub = 1;
       am.n_tot = 1;
       am.G = W;
+      am.wscratch = b.wscr;
       if ((rc = jq_launch_dense(am, st))) return rc;
       a.src0 = h;
       a.k0 = d1prev;
@@ -157,9 +163,12 @@ int jq_ferminet_forward(const jaqmc_ferminet_config* c, const jaqmc_ferminet_par
       a.k1 = fg;
       a.w1 = p->single_kernel[l] + (size_t)d1prev * (1 + d.nch) * d.d1[l];
       a.cadd = b.cadd;
+      a.out = hn;
+      if (d1prev == d.d1[l]) {
+        a.res = h;
+        a.res_mode = 1;
+      }
       if ((rc = jq_launch_dense(a, st))) return rc;
-      bool res = (d1prev == d.d1[l]);
-      if ((rc = jq_launch_tanh_fl(b.y, res ? h : nullptr, hn, W * n, C, d.d1[l], res ? 1 : 0, st))) return rc;
       float* t = h;
       h = hn;
       hn = t;
@@ -172,15 +181,19 @@ int jq_ferminet_forward(const jaqmc_ferminet_config* c, const jaqmc_ferminet_par
       a2.k0 = d2prev;
       a2.w0 = p->double_kernel[l];
       a2.bias = p->double_bias[l];
-      a2.out = b.y2;
+      a2.out = h2n;
+      a2.act = 1;
+      a2.wscratch = b.wscr;
+      if (d2prev == d.d2[l]) {
+        a2.res = h2;
+        a2.res_mode = 1;
+      }
       a2.N = d.d2[l];
       a2.C = d.C2;
       a2.n_sub = n * n;
       a2.n_tot = n * n;
       a2.G = W * n * n;
       if ((rc = jq_launch_dense(a2, st))) return rc;
-      bool res = (d2prev == d.d2[l]);
-      if ((rc = jq_launch_tanh_fl(b.y2, res ? h2 : nullptr, h2n, W * n * n, d.C2, d.d2[l], res ? 1 : 0, st))) return rc;
       float* t = h2;
       h2 = h2n;
       h2n = t;
@@ -198,6 +211,7 @@ int jq_ferminet_forward(const jaqmc_ferminet_config* c, const jaqmc_ferminet_par
       a.k0 = d1prev;
       a.w0 = p->orbital_kernel[s];
       a.out = b.orb;
+      a.wscratch = b.wscr;
       a.N = d.D * n;
       a.C = C;
       a.n_tot = n;
