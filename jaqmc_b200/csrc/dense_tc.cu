@@ -22,6 +22,8 @@
 //            accumulator acc_full (MMA commit->epilogue) / acc_empty (epilogue->MMA).
 #include <cuda.h>
 
+#include <cstdlib>
+
 #include "aug.cuh"
 
 namespace {
@@ -437,6 +439,9 @@ int pick_groups_per_tile(int C) {
 size_t jq_dense_tc_scratch_floats(int k_total, int n_out) { return (size_t)2 * k_total * n_out; }
 
 bool jq_dense_tc_eligible(const JqDenseArgs& a) {
+  // debugging switch (bisecting a numerical difference between the two dense kernels); both are sm_100a CUDA
+  static const bool disabled = getenv("JAQMC_B200_DISABLE_TC") != nullptr;
+  if (disabled) return false;
   if (a.C > TC_NMAX) return false;
   if (a.k0 % TC_BK || a.k1 % TC_BK) return false;
   if (a.k0 + a.k1 < 64) return false;

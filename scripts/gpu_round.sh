@@ -7,8 +7,12 @@ OUT=gpurun_out/$TAG
 mkdir -p $OUT
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw,memory.total --format=csv > $OUT/gpu.txt 2>&1
 echo "== dense canary" ; timeout -s KILL 180 python tests/gpu_dense_check.py > $OUT/dense_check.log 2>&1 ; RC=$? ; tail -12 $OUT/dense_check.log
-if [ $RC -ge 124 ]; then echo "dense canary hung/killed: aborting round"; exit 1; fi
-echo "== pytest -m gpu" ; timeout 900 python -m pytest tests -m gpu -x -q -s > $OUT/pytest_gpu.log 2>&1 ; echo "pytest exit $?" ; tail -25 $OUT/pytest_gpu.log
+if [ $RC -ne 0 ]; then
+  echo "dense canary rc=$RC: continuing with the tcgen05 kernel disabled"
+  export JAQMC_B200_DISABLE_TC=1
+  nvidia-smi > $OUT/after_canary_smi.txt 2>&1 || { echo "GPU unresponsive after canary"; exit 1; }
+fi
+echo "== pytest -m gpu" ; timeout 1200 python -m pytest tests -m gpu -q -s > $OUT/pytest_gpu.log 2>&1 ; echo "pytest exit $?" ; tail -40 $OUT/pytest_gpu.log
 echo "== smoke" ; timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > $OUT/smoke.log 2>&1 ; echo "smoke exit $?" ; tail -5 $OUT/smoke.log
 echo "== bench" ; timeout 900 python bench.py --steps ${STEPS:-5} --warmup 3 > $OUT/bench.json 2> $OUT/bench.err ; echo "bench exit $?" ; tail -3 $OUT/bench.err ; cat $OUT/bench.json
 echo "== ncu launch list" ; timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/launches.csv python bench.py --steps 1 --warmup 1 --no-cpu-baseline > $OUT/ncu_bench.log 2>&1 ; echo "ncu exit $?"
