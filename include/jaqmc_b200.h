@@ -76,6 +76,90 @@ typedef struct {
   const float* env_sigma[2];
 } jaqmc_ferminet_params;
 
+/* ---- shared output head: orbitals x envelope -> LogDet (+ Jastrow) ----------------------------
+ * OrbitalProjection (wavefunction/output/orbital.py:59-78), Envelope (output/envelope.py:98-140),
+ * SimpleEEJastrow (wavefunction/jastrow.py:47-122). */
+typedef struct {
+  const float* orbital_kernel[2]; /* orbital_layer/SplitChannelDense_0/DenseGeneral_{0,1}/kernel (hidden, ndets, n) */
+  const float* orbital_bias[2];   /* .../bias (ndets, n) or NULL (use_bias=False, the default) */
+  const float* env_pi[2];         /* envelope_layer/{_env_up,_env_down}/pi (n, n_atoms, ndets); [1] NULL -> `_env` */
+  const float* env_sigma[2];
+  const float* jastrow_alpha_par;  /* jastrow_layer/alpha_par (1,) or NULL (jastrow = none) */
+  const float* jastrow_alpha_anti; /* jastrow_layer/alpha_anti (1,) */
+} jaqmc_head_params;
+
+/* ---- LapNet ------------------------------------------------------------------------------------
+ * Fields mirror LapNetWavefunction (app/molecule/wavefunction/lapnet.py:63-78). */
+typedef struct {
+  int32_t n_up, n_dn;
+  int32_t n_atoms;
+  int32_t ndets;
+  int32_t num_layers, num_heads, heads_dim;
+  int32_t num_local_updates; /* per layer except the last (backbone/lapnet/_backbone.py:184-186) */
+  int32_t envelope_type;
+  int32_t rescale;           /* log-scaled input features (wavefunction/input/atomic.py:59-67) */
+} jaqmc_lapnet_config;
+
+/* backbone_layer/input_projection and backbone_layer/layers_{l}/... (_backbone.py:40-64,169-189).
+ * Every bias may be NULL (use_input_bias / use_backbone_bias = False). use_layernorm=True is not supported. */
+typedef struct {
+  const float* input_kernel; /* (4*n_atoms+1, hidden) */
+  const float* input_bias;
+  const float* qk_kernel[JAQMC_MAX_LAYERS];     /* qk_projection (hidden, 2*hidden) */
+  const float* qk_bias[JAQMC_MAX_LAYERS];
+  const float* value_kernel[JAQMC_MAX_LAYERS];  /* value_projection (hidden, hidden) */
+  const float* value_bias[JAQMC_MAX_LAYERS];
+  const float* output_kernel[JAQMC_MAX_LAYERS]; /* output_projection */
+  const float* output_bias[JAQMC_MAX_LAYERS];
+  const float* update_kernel[JAQMC_MAX_LAYERS]; /* value_update */
+  const float* update_bias[JAQMC_MAX_LAYERS];
+  const float* qk_update_kernel[JAQMC_MAX_LAYERS][4]; /* qk_update_layers_{j}, j < num_local_updates <= 4 */
+  const float* qk_update_bias[JAQMC_MAX_LAYERS][4];
+  jaqmc_head_params head;
+} jaqmc_lapnet_params;
+
+/* ---- Psiformer ---------------------------------------------------------------------------------
+ * Fields mirror PsiformerWavefunction (app/molecule/wavefunction/psiformer.py:77-94). */
+#define JAQMC_LAYERNORM_PRE 0
+#define JAQMC_LAYERNORM_POST 1
+#define JAQMC_LAYERNORM_NULL 2
+#define JAQMC_MAX_MLP 4
+typedef struct {
+  int32_t n_up, n_dn;
+  int32_t n_atoms;
+  int32_t ndets;
+  int32_t num_layers, num_heads, heads_dim;
+  int32_t n_mlp_hidden;                 /* len(mlp_hidden_dims) <= JAQMC_MAX_MLP - 1 */
+  int32_t mlp_hidden[JAQMC_MAX_MLP];
+  int32_t layer_norm_mode;              /* JAQMC_LAYERNORM_* (backbone/psiformer.py:57,72-98) */
+  int32_t envelope_type;
+  int32_t orbitals_spin_split;
+  int32_t rescale;
+} jaqmc_psiformer_config;
+
+/* backbone_layer/Dense_0 and backbone_layer/PsiformerLayer_{l}/... (backbone/psiformer.py:60-99,175-185);
+ * flax MultiHeadDotProductAttention kernels: query/key/value (hidden, heads, head_dim) == row-major (hidden, hidden),
+ * out (heads, head_dim, hidden) == (hidden, hidden). LayerNorm epsilon is 1e-5. */
+typedef struct {
+  const float* input_kernel; /* (4*n_atoms+1, hidden) */
+  const float* input_bias;   /* or NULL */
+  const float* ln0_scale[JAQMC_MAX_LAYERS];
+  const float* ln0_bias[JAQMC_MAX_LAYERS];
+  const float* q_kernel[JAQMC_MAX_LAYERS];
+  const float* q_bias[JAQMC_MAX_LAYERS];
+  const float* k_kernel[JAQMC_MAX_LAYERS];
+  const float* k_bias[JAQMC_MAX_LAYERS];
+  const float* v_kernel[JAQMC_MAX_LAYERS];
+  const float* v_bias[JAQMC_MAX_LAYERS];
+  const float* out_kernel[JAQMC_MAX_LAYERS];
+  const float* out_bias[JAQMC_MAX_LAYERS];
+  const float* ln1_scale[JAQMC_MAX_LAYERS];
+  const float* ln1_bias[JAQMC_MAX_LAYERS];
+  const float* mlp_kernel[JAQMC_MAX_LAYERS][JAQMC_MAX_MLP]; /* Dense_{j}: j < n_mlp_hidden hidden layers, then Dense_{n_mlp_hidden} -> hidden */
+  const float* mlp_bias[JAQMC_MAX_LAYERS][JAQMC_MAX_MLP];
+  jaqmc_head_params head;
+} jaqmc_psiformer_params;
+
 /* ---- generic wavefunction descriptor ---------------------------------------------------------- */
 typedef struct {
   int32_t kind;       /* JAQMC_WF_* */

@@ -51,11 +51,24 @@ static int fermi_dims(const jaqmc_ferminet_config* c, int track, FermiDims* o) {
 }
 
 struct FermiBufs {
-  float *ae, *h2a, *h2b, *g2, *x1, *ha, *hb, *m, *cadd, *orb, *wscr;
-  float *det_sign, *det_logabs, *det_grad, *det_lap;
+  float *ae, *h2a, *h2b, *g2, *x1, *ha, *hb, *m, *cadd, *wscr;
+  JqHeadBufs head;
 };
 
-static void fermi_carve(const FermiDims& d, long long W, JqArena& ar, FermiBufs* b) {
+static JqHeadDims fermi_head_dims(const FermiDims& d, const jaqmc_ferminet_config* c) {
+  JqHeadDims hd;
+  hd.sp = d.sp;
+  hd.A = d.A;
+  hd.D = d.D;
+  hd.C = d.C;
+  hd.hidden = d.d1[d.L - 1];
+  hd.envelope_type = c->envelope_type;
+  hd.split = c->orbitals_spin_split;
+  hd.jastrow = 0;
+  return hd;
+}
+
+static void fermi_carve(const FermiDims& d, const jaqmc_ferminet_config* c, long long W, JqArena& ar, FermiBufs* b) {
   long long n = d.n, nn = (long long)d.n * d.n;
   bool pairs = d.L > 1;
   b->ae = ar.take<float>(W * n * d.C1 * d.f1);
@@ -67,17 +80,13 @@ static void fermi_carve(const FermiDims& d, long long W, JqArena& ar, FermiBufs*
   b->hb = ar.take<float>(W * n * d.C * d.d1max);
   b->m = ar.take<float>(W * d.C * d.nch * d.d1max);
   b->cadd = ar.take<float>(W * d.C * d.d1max);
-  b->orb = ar.take<float>(W * n * d.C * d.D * n);
   {
     int kmax = d.d1max * (1 + d.nch) + d.nch * d.d2max;
     if (d.in1 > kmax) kmax = d.in1;
     int nmax = d.d1max > d.D * d.n ? d.d1max : d.D * d.n;
     b->wscr = ar.take<float>(jq_dense_tc_scratch_floats(kmax, nmax));
   }
-  b->det_sign = ar.take<float>(W * d.D);
-  b->det_logabs = ar.take<float>(W * d.D);
-  b->det_grad = ar.take<float>(W * d.D * (d.C > 1 ? 3 * n : 1));
-  b->det_lap = ar.take<float>(W * d.D);
+  jq_head_carve(fermi_head_dims(d, c), W, ar, &b->head);
 }
 
 size_t jq_ferminet_ws_bytes(const jaqmc_ferminet_config* c, long long W, int track) {
@@ -85,7 +94,7 @@ size_t jq_ferminet_ws_bytes(const jaqmc_ferminet_config* c, long long W, int tra
   if (fermi_dims(c, track, &d) != JQ_OK) return 0;
   JqArena ar(nullptr, 0);
   FermiBufs b;
-  fermi_carve(d, W, ar, &b);
+  fermi_carve(d, c, W, ar, &b);
   return ar.off;
 }
 
@@ -98,18 +107,12 @@ int jq_ferminet_forward(const jaqmc_ferminet_config* c, const jaqmc_ferminet_par
   JQ_REQUIRE(sys && sys->atoms && sys->n_atoms == d.A, JQ_ERR_INVALID_ARGUMENT, "ferminet: system/atoms mismatch");
   JqArena ar(ws, ws_bytes);
   FermiBufs b;
-  fermi_carve(d, W, ar, &b);
+  fermi_carve(d, c, W, ar, &b);
   JQ_REQUIRE(ar.ok(), JQ_ERR_WORKSPACE_TOO_SMALL, "ferminet: workspace %zu < %zu bytes", ws_bytes, ar.off);
   const int n = d.n, C = d.C;
-  const bool split = c->orbitals_spin_split && d.nch == 2;
   for (int l = 0; l < d.L; ++l)
     JQ_REQUIRE(p->single_kernel[l] && p->single_bias[l] && (l == d.L - 1 || (p->double_kernel[l] && p->double_bias[l])),
                JQ_ERR_INVALID_ARGUMENT, "ferminet: null parameter in layer %d", l);
-  JQ_REQUIRE(p->orbital_kernel[0] && (!split || p->orbital_kernel[1]), JQ_ERR_INVALID_ARGUMENT,
-             "ferminet: null orbital kernel");
-  JQ_REQUIRE(c->envelope_type == JAQMC_ENVELOPE_NULL || (p->env_pi[0] && p->env_sigma[0] && (!split || (p->env_pi[1] && p->env_sigma[1]))),
-             JQ_ERR_INVALID_ARGUMENT, "ferminet: null envelope parameter");
-
   // features: ae Local1 [W][n][C1][4A], ee Local2 [W][n*n][C2][4] (into h2a)
   if ((rc = jq_launch_mol_features(electrons, sys->atoms, (int)W, d.sp, d.A, /*rescale=*/0, track, b.ae, b.h2a, st)))
     return rc;
@@ -201,42 +204,12 @@ int jq_ferminet_forward(const jaqmc_ferminet_config* c, const jaqmc_ferminet_par
     }
   }
 
-  // orbitals: per spin channel DenseGeneral (hidden -> ndets*n), no bias (output/orbital.py:59-78)
-  {
-    int nchan = split ? 2 : 1;
-    for (int s = 0; s < nchan; ++s) {
-      JqDenseArgs a;
-      memset(&a, 0, sizeof(a));
-      a.src0 = h;
-      a.k0 = d1prev;
-      a.w0 = p->orbital_kernel[s];
-      a.out = b.orb;
-      a.wscratch = b.wscr;
-      a.N = d.D * n;
-      a.C = C;
-      a.n_tot = n;
-      if (split) {
-        a.j0 = d.sp.lo(s);
-        a.n_sub = d.sp.hi(s) - d.sp.lo(s);
-      } else {
-        a.j0 = 0;
-        a.n_sub = n;
-      }
-      a.G = W * a.n_sub;
-      if ((rc = jq_launch_dense(a, st))) return rc;
-    }
+  jaqmc_head_params hp;
+  memset(&hp, 0, sizeof(hp));
+  for (int s = 0; s < 2; ++s) {
+    hp.orbital_kernel[s] = p->orbital_kernel[s];
+    hp.env_pi[s] = p->env_pi[s];
+    hp.env_sigma[s] = p->env_sigma[s];
   }
-  JqEnvelopeArgs env;
-  env.type = c->envelope_type;
-  env.pi[0] = p->env_pi[0];
-  env.sigma[0] = p->env_sigma[0];
-  env.pi[1] = split ? p->env_pi[1] : nullptr;
-  env.sigma[1] = split ? p->env_sigma[1] : nullptr;
-  if ((rc = jq_launch_orb_envelope(b.orb, electrons, sys->atoms, env, (int)W, d.sp, d.A, d.D, track, st))) return rc;
-  if ((rc = jq_launch_logdet(b.orb, (int)W, n, d.D, track, b.det_sign, b.det_logabs, b.det_grad, b.det_lap, st)))
-    return rc;
-  if ((rc = jq_launch_logdet_combine(b.det_sign, b.det_logabs, b.det_grad, b.det_lap, (int)W, n, d.D, track, nullptr,
-                                     out.logpsi, out.sign, out.grad, out.lap, out.e_kin, st)))
-    return rc;
-  return JQ_OK;
+  return jq_head_forward(fermi_head_dims(d, c), &hp, h, electrons, sys->atoms, W, b.head, b.wscr, out, st);
 }

@@ -15,3 +15,20 @@ size_t jq_ferminet_ws_bytes(const jaqmc_ferminet_config* c, long long W, int tra
 int jq_ferminet_forward(const jaqmc_ferminet_config* c, const jaqmc_ferminet_params* p, const jaqmc_system* sys,
                         const float* electrons, long long W, int track, void* ws, size_t ws_bytes, JqWfOut out,
                         cudaStream_t st);
+
+// ---- shared output head (head.cu) ---------------------------------------------------------------
+struct JqHeadDims {
+  JqSpins sp;
+  int A, D, C, hidden;
+  int envelope_type, split, jastrow;
+};
+struct JqHeadBufs {
+  float *orb, *det_sign, *det_logabs, *det_grad, *det_lap, *extra;
+};
+void jq_head_carve(const JqHeadDims& d, long long W, JqArena& ar, JqHeadBufs* b);
+// h [W][n][C][hidden] -> logpsi, sign (+ grad, lap, e_kin when C > 1)
+int jq_head_forward(const JqHeadDims& d, const jaqmc_head_params* p, const float* h, const float* electrons,
+                    const float* atoms, long long W, const JqHeadBufs& b, float* wscratch, JqWfOut out,
+                    cudaStream_t st);
+int jq_launch_jastrow(const float* electrons, const float* alpha_par, const float* alpha_anti, int W, JqSpins sp,
+                      int track, float* extra, cudaStream_t st);

@@ -102,3 +102,38 @@ def oracle_batch(logpsi_fn, electrons, atoms=None, charges=None, track=True):
         if charges is not None:
             out["e_pot"].append(float(OE.potential_energy(e, atoms, charges)))
     return {k: np.asarray(v) for k, v in out.items() if len(v)}
+
+
+def fp32_scales(ref, electrons):
+    """Magnitudes the float32 tolerances are relative to (see tests/test_gpu_ferminet.py docstring)."""
+    g2 = (ref["grad"] ** 2).sum(1)
+    e_scale = 0.5 * np.abs(ref["lap"]) + 0.5 * g2 + np.abs(ref["e_pot"])
+    r = np.linalg.norm(np.asarray(electrons, dtype=np.float64).reshape(len(g2), -1), axis=1)
+    l_scale = np.abs(ref["logpsi"]) + np.sqrt(g2) * r
+    return e_scale, l_scale
+
+
+def fp32_errors(out, ref, electrons):
+    e_scale, l_scale = fp32_scales(ref, electrons)
+    e_out = out["e_loc"] if "e_loc" in out else out["e_kin"] + out["e_pot"]
+    e_err = np.abs(e_out - (ref["e_kin"] + ref["e_pot"])) / e_scale
+    l_err = np.abs(out["logpsi"] - ref["logpsi"]) / l_scale
+    return e_err, l_err
+
+
+def assert_fp32_parity(out, ref, electrons, e_tol=1e-5, l_tol=1e-6):
+    """E_L within ``e_tol`` and log|psi| within ``l_tol`` of the float64 oracle, relative to the magnitude of the terms
+    summed; median (typical-walker) unscaled errors within 10x of the same tolerances."""
+    e_err, l_err = fp32_errors(out, ref, electrons)
+    assert e_err.max() < e_tol, ("E_L", e_err)
+    assert l_err.max() < l_tol, ("logpsi", l_err)
+    e_ref = ref["e_kin"] + ref["e_pot"]
+    e_out = out["e_loc"] if "e_loc" in out else out["e_kin"] + out["e_pot"]
+    plain_e = np.abs(e_out - e_ref) / (np.abs(ref["e_kin"]) + np.abs(ref["e_pot"]))
+    plain_l = np.abs(out["logpsi"] - ref["logpsi"]) / np.maximum(1.0, np.abs(ref["logpsi"]))
+    assert np.median(plain_e) < 10 * e_tol, ("E_L median", plain_e)
+    assert np.median(plain_l) < 10 * l_tol, ("logpsi median", plain_l)
+    if "grad" in out:
+        gs = np.abs(ref["grad"]).max(axis=1, keepdims=True) + 1.0
+        assert np.max(np.abs(out["grad"] - ref["grad"]) / gs) < 1e-4
+    return e_err, l_err
