@@ -54,6 +54,94 @@ class FerminetParams(C.Structure):
     ]
 
 
+class HeadParams(C.Structure):
+    _fields_ = [
+        ("orbital_kernel", FloatP * 2),
+        ("orbital_bias", FloatP * 2),
+        ("env_pi", FloatP * 2),
+        ("env_sigma", FloatP * 2),
+        ("jastrow_alpha_par", FloatP),
+        ("jastrow_alpha_anti", FloatP),
+    ]
+
+
+class LapnetConfig(C.Structure):
+    _fields_ = [
+        ("n_up", C.c_int32),
+        ("n_dn", C.c_int32),
+        ("n_atoms", C.c_int32),
+        ("ndets", C.c_int32),
+        ("num_layers", C.c_int32),
+        ("num_heads", C.c_int32),
+        ("heads_dim", C.c_int32),
+        ("num_local_updates", C.c_int32),
+        ("envelope_type", C.c_int32),
+        ("rescale", C.c_int32),
+    ]
+
+
+class LapnetParams(C.Structure):
+    _fields_ = [
+        ("input_kernel", FloatP),
+        ("input_bias", FloatP),
+        ("qk_kernel", FloatP * MAX_LAYERS),
+        ("qk_bias", FloatP * MAX_LAYERS),
+        ("value_kernel", FloatP * MAX_LAYERS),
+        ("value_bias", FloatP * MAX_LAYERS),
+        ("output_kernel", FloatP * MAX_LAYERS),
+        ("output_bias", FloatP * MAX_LAYERS),
+        ("update_kernel", FloatP * MAX_LAYERS),
+        ("update_bias", FloatP * MAX_LAYERS),
+        ("qk_update_kernel", (FloatP * 4) * MAX_LAYERS),
+        ("qk_update_bias", (FloatP * 4) * MAX_LAYERS),
+        ("head", HeadParams),
+    ]
+
+
+LAYERNORM = {"pre": 0, "post": 1, "null": 2}
+MAX_MLP = 4
+
+
+class PsiformerConfig(C.Structure):
+    _fields_ = [
+        ("n_up", C.c_int32),
+        ("n_dn", C.c_int32),
+        ("n_atoms", C.c_int32),
+        ("ndets", C.c_int32),
+        ("num_layers", C.c_int32),
+        ("num_heads", C.c_int32),
+        ("heads_dim", C.c_int32),
+        ("n_mlp_hidden", C.c_int32),
+        ("mlp_hidden", C.c_int32 * MAX_MLP),
+        ("layer_norm_mode", C.c_int32),
+        ("envelope_type", C.c_int32),
+        ("orbitals_spin_split", C.c_int32),
+        ("rescale", C.c_int32),
+    ]
+
+
+class PsiformerParams(C.Structure):
+    _fields_ = [
+        ("input_kernel", FloatP),
+        ("input_bias", FloatP),
+        ("ln0_scale", FloatP * MAX_LAYERS),
+        ("ln0_bias", FloatP * MAX_LAYERS),
+        ("q_kernel", FloatP * MAX_LAYERS),
+        ("q_bias", FloatP * MAX_LAYERS),
+        ("k_kernel", FloatP * MAX_LAYERS),
+        ("k_bias", FloatP * MAX_LAYERS),
+        ("v_kernel", FloatP * MAX_LAYERS),
+        ("v_bias", FloatP * MAX_LAYERS),
+        ("out_kernel", FloatP * MAX_LAYERS),
+        ("out_bias", FloatP * MAX_LAYERS),
+        ("ln1_scale", FloatP * MAX_LAYERS),
+        ("ln1_bias", FloatP * MAX_LAYERS),
+        ("mlp_kernel", (FloatP * MAX_MLP) * MAX_LAYERS),
+        ("mlp_bias", (FloatP * MAX_MLP) * MAX_LAYERS),
+        ("head", HeadParams),
+    ]
+
+
 class Wavefunction(C.Structure):
     _fields_ = [("kind", C.c_int32), ("config", C.c_void_p), ("params", C.c_void_p)]
 

@@ -115,3 +115,143 @@ def ferminet_handle(params, nspins, n_atoms, ndets, hidden_dims_single, hidden_d
     wf.config = C.cast(C.pointer(cfg), C.c_void_p)
     wf.params = C.cast(C.pointer(ps), C.c_void_p)
     return Handle(wf, keep)
+
+
+class _Binder:
+    """Collects leaves (keeping them alive) while filling pointer fields."""
+
+    def __init__(self):
+        self.keep = []
+
+    def leaf(self, tree, path, shape=None, optional=False):
+        node = tree
+        for key in path.split("/"):
+            if not isinstance(node, dict) or key not in node:
+                if optional:
+                    return None
+                raise KeyError(f"parameter tree has no leaf {path!r}")
+            node = node[key]
+        t = _leaf(node, path, shape)
+        self.keep.append(t)
+        return t.data_ptr()
+
+
+def _fill_head(b: _Binder, head: "_abi.HeadParams", p, n, n_atoms, ndets, hidden, split, envelope, jastrow):
+    ol = p["orbital_layer"]
+    if split:
+        for s in range(2):
+            base = f"SplitChannelDense_0/DenseGeneral_{s}"
+            head.orbital_kernel[s] = b.leaf(ol, f"{base}/kernel", (hidden, ndets, n))
+            head.orbital_bias[s] = b.leaf(ol, f"{base}/bias", (ndets, n), optional=True)
+    else:
+        head.orbital_kernel[0] = b.leaf(ol, "DenseGeneral_0/kernel", (hidden, ndets, n))
+        head.orbital_bias[0] = b.leaf(ol, "DenseGeneral_0/bias", (ndets, n), optional=True)
+    if envelope != "null":
+        el = p["envelope_layer"]
+        for s, nm in enumerate(["_env_up", "_env_down"] if split else ["_env"]):
+            head.env_pi[s] = b.leaf(el, f"{nm}/pi", (n, n_atoms, ndets))
+            head.env_sigma[s] = b.leaf(el, f"{nm}/sigma", (n, n_atoms, ndets))
+    if jastrow:
+        head.jastrow_alpha_par = b.leaf(p["jastrow_layer"], "alpha_par", (1,))
+        head.jastrow_alpha_anti = b.leaf(p["jastrow_layer"], "alpha_anti", (1,))
+
+
+def _wf_handle(kind, cfg, ps, keep):
+    wf = _abi.Wavefunction()
+    wf.kind = kind
+    wf.config = C.cast(C.pointer(cfg), C.c_void_p)
+    wf.params = C.cast(C.pointer(ps), C.c_void_p)
+    return Handle(wf, [cfg, ps, *keep])
+
+
+def lapnet_handle(params, nspins, n_atoms, ndets=16, num_layers=4, num_heads=4, heads_dim=64, num_local_updates=2,
+                  envelope="abs_isotropic", rescale=True, jastrow=True) -> Handle:
+    """Descriptor for ``LapNetWavefunction`` (reference app/molecule/wavefunction/lapnet.py:63-115)."""
+    n_up, n_dn = int(nspins[0]), int(nspins[1])
+    n = n_up + n_dn
+    if not 1 <= num_layers <= _abi.MAX_LAYERS:
+        raise ValueError(f"num_layers must be in [1, {_abi.MAX_LAYERS}]")
+    if not 0 <= num_local_updates <= 4:
+        raise ValueError("num_local_updates must be in [0, 4]")
+    if envelope not in _abi.ENVELOPE:
+        raise ValueError(f"Unknown envelope: {envelope!r}")
+    p = params["params"] if "params" in params else params
+    hid = num_heads * heads_dim
+    cfg = _abi.LapnetConfig(n_up, n_dn, int(n_atoms), int(ndets), int(num_layers), int(num_heads), int(heads_dim),
+                            int(num_local_updates), _abi.ENVELOPE[envelope], int(bool(rescale)))
+    ps = _abi.LapnetParams()
+    b = _Binder()
+    bb = p["backbone_layer"]
+    ps.input_kernel = b.leaf(bb, "input_projection/kernel", (4 * n_atoms + 1, hid))
+    ps.input_bias = b.leaf(bb, "input_projection/bias", (hid,), optional=True)
+    for l in range(num_layers):
+        lp = bb[f"layers_{l}"]
+        if "qk_layernorm" in lp or "value_layernorm" in lp:
+            raise NotImplementedError("LapNet use_layernorm=True is not supported by the CUDA pipeline")
+        ps.qk_kernel[l] = b.leaf(lp, "qk_projection/kernel", (hid, 2 * hid))
+        ps.qk_bias[l] = b.leaf(lp, "qk_projection/bias", (2 * hid,), optional=True)
+        for nm, fld in (("value_projection", "value"), ("output_projection", "output"), ("value_update", "update")):
+            getattr(ps, fld + "_kernel")[l] = b.leaf(lp, f"{nm}/kernel", (hid, hid))
+            getattr(ps, fld + "_bias")[l] = b.leaf(lp, f"{nm}/bias", (hid,), optional=True)
+        if l < num_layers - 1:
+            for j in range(num_local_updates):
+                ps.qk_update_kernel[l][j] = b.leaf(lp, f"qk_update_layers_{j}/kernel", (hid, hid))
+                ps.qk_update_bias[l][j] = b.leaf(lp, f"qk_update_layers_{j}/bias", (hid,), optional=True)
+    split = n_up > 0 and n_dn > 0
+    _fill_head(b, ps.head, p, n, n_atoms, ndets, hid, split, envelope, jastrow)
+    return _wf_handle(_abi.WF_LAPNET, cfg, ps, b.keep)
+
+
+def psiformer_handle(params, nspins, n_atoms, ndets=16, num_layers=4, num_heads=4, heads_dim=64, mlp_hidden_dims=(256,),
+                     layer_norm_mode="pre", envelope="abs_isotropic", orbitals_spin_split=True, rescale=True,
+                     jastrow=True) -> Handle:
+    """Descriptor for ``PsiformerWavefunction`` (reference app/molecule/wavefunction/psiformer.py:77-135)."""
+    n_up, n_dn = int(nspins[0]), int(nspins[1])
+    n = n_up + n_dn
+    if not 1 <= num_layers <= _abi.MAX_LAYERS:
+        raise ValueError(f"num_layers must be in [1, {_abi.MAX_LAYERS}]")
+    if len(mlp_hidden_dims) > _abi.MAX_MLP - 1:
+        raise ValueError(f"at most {_abi.MAX_MLP - 1} hidden MLP layers are supported")
+    if layer_norm_mode not in _abi.LAYERNORM:
+        raise ValueError(f"Unknown layer_norm_mode: {layer_norm_mode!r}")
+    if envelope not in _abi.ENVELOPE:
+        raise ValueError(f"Unknown envelope: {envelope!r}")
+    p = params["params"] if "params" in params else params
+    hid = num_heads * heads_dim
+    cfg = _abi.PsiformerConfig()
+    cfg.n_up, cfg.n_dn, cfg.n_atoms, cfg.ndets = n_up, n_dn, int(n_atoms), int(ndets)
+    cfg.num_layers, cfg.num_heads, cfg.heads_dim = int(num_layers), int(num_heads), int(heads_dim)
+    cfg.n_mlp_hidden = len(mlp_hidden_dims)
+    for j, h in enumerate(mlp_hidden_dims):
+        cfg.mlp_hidden[j] = int(h)
+    cfg.layer_norm_mode = _abi.LAYERNORM[layer_norm_mode]
+    cfg.envelope_type = _abi.ENVELOPE[envelope]
+    split = bool(orbitals_spin_split) and n_up > 0 and n_dn > 0
+    cfg.orbitals_spin_split = int(split)
+    cfg.rescale = int(bool(rescale))
+    ps = _abi.PsiformerParams()
+    b = _Binder()
+    bb = p["backbone_layer"]
+    ps.input_kernel = b.leaf(bb, "Dense_0/kernel", (4 * n_atoms + 1, hid))
+    ps.input_bias = b.leaf(bb, "Dense_0/bias", (hid,), optional=True)
+    for l in range(num_layers):
+        lp = bb[f"PsiformerLayer_{l}"]
+        mha = lp["MultiHeadDotProductAttention_0"]
+        if layer_norm_mode != "null":
+            ps.ln0_scale[l] = b.leaf(lp, "LayerNorm_0/scale", (hid,))
+            ps.ln0_bias[l] = b.leaf(lp, "LayerNorm_0/bias", (hid,))
+            ps.ln1_scale[l] = b.leaf(lp, "LayerNorm_1/scale", (hid,))
+            ps.ln1_bias[l] = b.leaf(lp, "LayerNorm_1/bias", (hid,))
+        for nm, fld in (("query", "q"), ("key", "k"), ("value", "v")):
+            getattr(ps, fld + "_kernel")[l] = b.leaf(mha, f"{nm}/kernel", (hid, num_heads, heads_dim))
+            getattr(ps, fld + "_bias")[l] = b.leaf(mha, f"{nm}/bias", (num_heads, heads_dim), optional=True)
+        ps.out_kernel[l] = b.leaf(mha, "out/kernel", (num_heads, heads_dim, hid))
+        ps.out_bias[l] = b.leaf(mha, "out/bias", (hid,), optional=True)
+        fan = hid
+        dims = [int(h) for h in mlp_hidden_dims] + [hid]
+        for j, h in enumerate(dims):
+            ps.mlp_kernel[l][j] = b.leaf(lp, f"Dense_{j}/kernel", (fan, h))
+            ps.mlp_bias[l][j] = b.leaf(lp, f"Dense_{j}/bias", (h,), optional=True)
+            fan = h
+    _fill_head(b, ps.head, p, n, n_atoms, ndets, hid, split, envelope, jastrow)
+    return _wf_handle(_abi.WF_PSIFORMER, cfg, ps, b.keep)

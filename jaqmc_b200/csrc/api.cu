@@ -101,6 +101,14 @@ static int wf_n_electrons(const jaqmc_wavefunction* wf) {
       auto* c = (const jaqmc_ferminet_config*)wf->config;
       return c->n_up + c->n_dn;
     }
+    case JAQMC_WF_LAPNET: {
+      auto* c = (const jaqmc_lapnet_config*)wf->config;
+      return c->n_up + c->n_dn;
+    }
+    case JAQMC_WF_PSIFORMER: {
+      auto* c = (const jaqmc_psiformer_config*)wf->config;
+      return c->n_up + c->n_dn;
+    }
     default:
       return -1;
   }
@@ -110,6 +118,10 @@ static size_t wf_ws_bytes(const jaqmc_wavefunction* wf, long long W, int track) 
   switch (wf->kind) {
     case JAQMC_WF_FERMINET:
       return jq_ferminet_ws_bytes((const jaqmc_ferminet_config*)wf->config, W, track);
+    case JAQMC_WF_LAPNET:
+      return jq_lapnet_ws_bytes((const jaqmc_lapnet_config*)wf->config, W, track);
+    case JAQMC_WF_PSIFORMER:
+      return jq_psiformer_ws_bytes((const jaqmc_psiformer_config*)wf->config, W, track);
     default:
       return 0;
   }
@@ -121,6 +133,12 @@ static int wf_forward(const jaqmc_wavefunction* wf, const jaqmc_system* sys, con
     case JAQMC_WF_FERMINET:
       return jq_ferminet_forward((const jaqmc_ferminet_config*)wf->config, (const jaqmc_ferminet_params*)wf->params,
                                  sys, electrons, W, track, ws, ws_bytes, out, st);
+    case JAQMC_WF_LAPNET:
+      return jq_lapnet_forward((const jaqmc_lapnet_config*)wf->config, (const jaqmc_lapnet_params*)wf->params, sys,
+                               electrons, W, track, ws, ws_bytes, out, st);
+    case JAQMC_WF_PSIFORMER:
+      return jq_psiformer_forward((const jaqmc_psiformer_config*)wf->config, (const jaqmc_psiformer_params*)wf->params,
+                                  sys, electrons, W, track, ws, ws_bytes, out, st);
     default:
       jq_set_error("wavefunction kind %d is not implemented", wf->kind);
       return JQ_ERR_UNSUPPORTED;

@@ -1,0 +1,402 @@
+// Attention-network building blocks under the forward Laplacian: Local1 -> dense expansion, LayerNorm, and
+// softmax attention (LapNet cross-stream attention and Psiformer self-attention share one kernel).
+//
+// Reference semantics:
+//   * flax nn.LayerNorm(epsilon) as used by backbone/psiformer.py:74,86,88,98: mean / fast variance over the last
+//     axis, y = (x - mu) rsqrt(var + eps) scale + bias; traced by the interpreter through the mean / square / rsqrt /
+//     product rules (laplacian/primitives/{reductions,elementwise,arithmetic}.py)
+//   * attention  softmax(q k^T / sqrt(d)) v  with operands (n, heads, d): backbone/lapnet/_attention.py:20-34 and
+//     its hand rule :113-196 (q, k Local1, v dense); flax MultiHeadDotProductAttention for Psiformer
+//     (backbone/psiformer.py:76-82), traced through dot_general (laplacian/primitives/dot_general.py:410-449) and softmax
+// Both are evaluated here in closed form (Appendix A of SURVEY.md): same function, same derivatives.
+#include "aug.cuh"
+
+// ------------------------------------------------------------------------------------------------
+// Local1 [W][n][5][F] -> dense [W][n][3n+2][F]: electron i owns Jacobian columns 3i..3i+2
+// (laplacian/sparse.py Local1Jacobian.to_dense).  One item per output element.
+// ------------------------------------------------------------------------------------------------
+__global__ void k_densify_local1(const float* __restrict__ in, float* __restrict__ out, long long items, int n, int F) {
+  const int C = 3 * n + 2;
+  for (long long it = (long long)blockIdx.x * blockDim.x + threadIdx.x; it < items;
+       it += (long long)gridDim.x * blockDim.x) {
+    int f = (int)(it % F);
+    long long t = it / F;
+    int c = (int)(t % C);
+    long long g = t / C;
+    int i = (int)(g % n);
+    float v = 0.f;
+    const float* p = in + g * 5 * F + f;
+    if (c == 0) v = p[0];
+    else if (c == C - 1) v = p[4 * F];
+    else if ((c - 1) / 3 == i) v = p[(1 + (c - 1) % 3) * F];
+    out[it] = v;
+  }
+}
+
+int jq_launch_densify_local1(const float* in, float* out, long long W, int n, int F, cudaStream_t st) {
+  long long items = W * n * (3 * n + 2) * F;
+  if (items <= 0) return JQ_OK;
+  int grid = jq_cdiv(items, 256);
+  if (grid > 148 * 32) grid = 148 * 32;
+  jq_prof_work(0.0, 4.0 * (double)items);
+  JQ_LAUNCH(k_densify_local1, dim3(grid), dim3(256), 0, st, in, out, items, n, F);
+  JQ_CHECK_LAUNCH();
+  return JQ_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// LayerNorm with the forward-Laplacian rule.  One block per group (walker, electron); x, out [G][C][F].
+//   mu = mean x, var = max(0, mean x^2 - mu^2), s = rsqrt(var + eps), xc = x - mu, y = xc s scale + bias
+//   J rows:  muJ = mean J, xcJ = J - muJ, varJ = 2 mean(xc xcJ), sJ = -1/2 s^3 varJ,  yJ = (xcJ s + xc sJ) scale
+//   L row:   varL = 2 mean(xc xcL) + 2 sum_k mean(xcJ_k^2),  sL = -1/2 s^3 varL + 3/4 s^5 sum_k varJ_k^2,
+//            yL = (xcL s + xc sL + 2 sum_k xcJ_k sJ_k) scale
+// Shared: mu[C] | dot[C] | sq[C] | sj[C] | part[C*LN_T] | scal[8]
+// ------------------------------------------------------------------------------------------------
+#define LN_T 32
+__global__ void k_layernorm_fl(const float* __restrict__ x, const float* __restrict__ scale,
+                               const float* __restrict__ bias, float* __restrict__ out, int C, int F, float eps) {
+  JQ_DYN_SMEM(float, sm);
+  float* mu = sm;
+  float* dot = mu + C;
+  float* sq = dot + C;
+  float* sj = sq + C;
+  float* part = sj + C;
+  float* part2 = part + C * LN_T;
+  float* scal = part2 + C * LN_T;
+  const long long g = blockIdx.x;
+  const float* xg = x + g * (long long)C * F;
+  float* og = out + g * (long long)C * F;
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const float invF = 1.0f / (float)F;
+  const int K = C - 2;  // Jacobian rows (C == 1: value only)
+
+  // pass 1: row sums (+ sum of squares of the value row)
+  for (int q = tid; q < C * LN_T; q += nt) {
+    int c = q / LN_T, t = q % LN_T;
+    const float* r = xg + (long long)c * F;
+    float s = 0.f, s2 = 0.f;
+    for (int f = t; f < F; f += LN_T) {
+      float v = r[f];
+      s += v;
+      if (c == 0) s2 = fmaf(v, v, s2);
+    }
+    part[q] = s;
+    if (c == 0) part2[t] = s2;
+  }
+  __syncthreads();
+  for (int c = tid; c < C; c += nt) {
+    float s = 0.f;
+    for (int t = 0; t < LN_T; ++t) s += part[c * LN_T + t];
+    mu[c] = s * invF;
+  }
+  if (tid == 0) {
+    float s2 = 0.f;
+    for (int t = 0; t < LN_T; ++t) s2 += part2[t];
+    scal[7] = s2 * invF;  // mean x^2
+  }
+  __syncthreads();
+  if (tid == 0) {
+    float var = scal[7] - mu[0] * mu[0];
+    if (var < 0.f) var = 0.f;
+    scal[0] = rsqrtf(var + eps);
+  }
+  // pass 2: dot[c] = sum xc (row_c - mu_c), sq[c] = sum (row_c - mu_c)^2 for derivative rows
+  if (C > 1) {
+    const float mu0 = mu[0];
+    for (int q = tid; q < (C - 1) * LN_T; q += nt) {
+      int c = 1 + q / LN_T, t = q % LN_T;
+      const float* r = xg + (long long)c * F;
+      const float m = mu[c];
+      float d = 0.f, s2 = 0.f;
+      for (int f = t; f < F; f += LN_T) {
+        float v = r[f] - m;
+        d = fmaf(xg[f] - mu0, v, d);
+        s2 = fmaf(v, v, s2);
+      }
+      part[c * LN_T + t] = d;
+      part2[c * LN_T + t] = s2;
+    }
+  }
+  __syncthreads();
+  const float s = scal[0];
+  if (C > 1) {
+    for (int c = 1 + tid; c < C; c += nt) {
+      float d = 0.f, s2 = 0.f;
+      for (int t = 0; t < LN_T; ++t) {
+        d += part[c * LN_T + t];
+        s2 += part2[c * LN_T + t];
+      }
+      dot[c] = d;
+      sq[c] = s2;
+      sj[c] = -0.5f * s * s * s * (2.0f * d * invF);  // sJ (for c == C-1 this is the first part of sL)
+    }
+    __syncthreads();
+    if (tid == 0) {
+      float sumq = 0.f, sumv2 = 0.f;
+      for (int k = 1; k <= K; ++k) {
+        sumq += sq[k];
+        float vj = 2.0f * dot[k] * invF;
+        sumv2 = fmaf(vj, vj, sumv2);
+      }
+      float s3 = s * s * s;
+      float varL = 2.0f * dot[C - 1] * invF + 2.0f * sumq * invF;
+      scal[1] = -0.5f * s3 * varL + 0.75f * s3 * s * s * sumv2;  // sL
+    }
+    __syncthreads();
+  }
+  // pass 3: outputs
+  const float mu0 = mu[0];
+  for (int q = tid; q < (C > 1 ? C - 1 : 1) * F; q += nt) {
+    int c = q / F, f = q % F;
+    float xc = xg[f] - mu0;
+    float sc = scale ? scale[f] : 1.0f;
+    if (c == 0) {
+      float y = xc * s * sc;
+      if (bias) y += bias[f];
+      og[f] = y;
+    } else {
+      float v = xg[(long long)c * F + f] - mu[c];
+      og[(long long)c * F + f] = (v * s + xc * sj[c]) * sc;
+    }
+  }
+  if (C > 1) {
+    const float sL = scal[1];
+    for (int f = tid; f < F; f += nt) {
+      float xc = xg[f] - mu0;
+      float acc = 0.f;
+      for (int k = 1; k <= K; ++k) acc = fmaf(xg[(long long)k * F + f] - mu[k], sj[k], acc);
+      float v = xg[(long long)(C - 1) * F + f] - mu[C - 1];
+      float sc = scale ? scale[f] : 1.0f;
+      og[(long long)(C - 1) * F + f] = (v * s + xc * sL + 2.0f * acc) * sc;
+    }
+  }
+}
+
+int jq_launch_layernorm_fl(const float* x, const float* scale, const float* bias, float* out, long long G, int C, int F,
+                           float eps, cudaStream_t st) {
+  if (G <= 0) return JQ_OK;
+  JQ_REQUIRE(x != out, JQ_ERR_INVALID_ARGUMENT, "layernorm: in-place is not supported");
+  size_t smem = sizeof(float) * ((size_t)4 * C + (size_t)2 * C * LN_T + 8);
+  JQ_REQUIRE(smem <= 200 * 1024, JQ_ERR_UNSUPPORTED, "layernorm: %d components need %zu bytes of shared memory", C, smem);
+#ifndef JAQMC_HOST_EMU
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(k_layernorm_fl, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    JQ_REQUIRE(e == cudaSuccess, JQ_ERR_CUDA, "layernorm: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+  }
+#endif
+  jq_prof_work(0.0, 8.0 * (double)G * C * F);
+  JQ_LAUNCH(k_layernorm_fl, dim3((unsigned)G), dim3(256), smem, st, x, scale, bias, out, C, F, eps);
+  JQ_CHECK_LAUNCH();
+  return JQ_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// softmax attention with the forward-Laplacian rule.  One block per (walker, head).
+//   a_ij = q_i . k_j / sqrt(d),  w = softmax_j(a),  o_i = sum_j w_ij v_j
+//   per coordinate k:  aJ = (qJ.k + q.kJ)/sqrt(d),  abar_i = sum_m w_im aJ_im,  wJ_ij = w_ij (aJ_ij - abar_i),
+//                      oJ_i = sum_j (wJ_ij v_j + w_ij vJ_j)
+//   Laplacian:  aL = (qL.k + q.kL + 2 sum_k qJ_k.kJ_k)/sqrt(d),
+//               wL_ij = sum_k wJ_ij (aJ_ij - abar_i) + w_ij (aL_ij - sum_m w_im aL_im - sum_k sum_m wJ_im aJ_im),
+//               oL_i = sum_j (wL_ij v_j + w_ij vL_j) + 2 sum_k sum_j wJ_ij vJ_kj
+// Operand layouts: t[W][n][Ct][ld] with Ct = 3n+2 (dense) or 5 (Local1: electron i carries only its own 3
+// Jacobian columns); head h occupies columns [off + h*dh, off + (h+1)*dh).
+// Shared (floats, rows padded to dh+1): q0 k0 v0 qJ kJ vJ oL [n][dh+1] | w aJ aL t1 wJ [n][n] | abar t2 [n]
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float attn_fetch(const JqAttnOperand& t, long long w, int n, int i, int comp_dense, int col,
+                                            int Cd) {
+  // comp_dense in [0, Cd): 0 value, 1..3n Jacobian column k = comp-1, Cd-1 Laplacian
+  const float* base = t.p + ((w * n + i) * (long long)t.C) * t.ld + col;
+  if (t.C == Cd) return base[(long long)comp_dense * t.ld];
+  if (comp_dense == 0) return base[0];
+  if (comp_dense == Cd - 1) return base[(long long)4 * t.ld];
+  int k = comp_dense - 1;
+  if (k / 3 != i) return 0.f;
+  return base[(long long)(1 + k % 3) * t.ld];
+}
+
+__global__ void k_attention_fl(JqAttnOperand q, JqAttnOperand k, JqAttnOperand v, float* __restrict__ out, int ldo,
+                               int n, int H, int dh, int track) {
+  JQ_DYN_SMEM(float, sm);
+  const int ldh = dh + 1;
+  const int nd = n * ldh, nn = n * n;
+  float* q0 = sm;
+  float* k0 = q0 + nd;
+  float* v0 = k0 + nd;
+  float* qJ = v0 + nd;
+  float* kJ = qJ + nd;
+  float* vJ = kJ + nd;
+  float* oL = vJ + nd;
+  float* wgt = oL + nd;
+  float* aJ = wgt + nn;
+  float* aL = aJ + nn;
+  float* t1 = aL + nn;
+  float* wJ = t1 + nn;
+  float* abar = wJ + nn;
+  float* t2 = abar + n;
+  const long long w = blockIdx.x / H;
+  const int h = blockIdx.x % H;
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const int Cd = track ? 3 * n + 2 : 1;
+  const int K = track ? 3 * n : 0;
+  const float scale = rsqrtf((float)dh);
+  const int ndh = n * dh;
+
+  for (int x = tid; x < ndh; x += nt) {
+    int i = x / dh, d = x % dh;
+    q0[i * ldh + d] = attn_fetch(q, w, n, i, 0, q.off + h * dh + d, Cd);
+    k0[i * ldh + d] = attn_fetch(k, w, n, i, 0, k.off + h * dh + d, Cd);
+    v0[i * ldh + d] = attn_fetch(v, w, n, i, 0, v.off + h * dh + d, Cd);
+    oL[i * ldh + d] = 0.f;
+  }
+  __syncthreads();
+  for (int x = tid; x < nn; x += nt) {
+    int i = x / n, j = x % n;
+    float acc = 0.f;
+    for (int d = 0; d < dh; ++d) acc = fmaf(q0[i * ldh + d], k0[j * ldh + d], acc);
+    wgt[x] = acc * scale;
+    aL[x] = 0.f;
+    t1[x] = 0.f;
+  }
+  __syncthreads();
+  for (int i = tid; i < n; i += nt) {
+    float m = wgt[i * n];
+    for (int j = 1; j < n; ++j) m = fmaxf(m, wgt[i * n + j]);
+    float z = 0.f;
+    for (int j = 0; j < n; ++j) {
+      float e = expf(wgt[i * n + j] - m);
+      wgt[i * n + j] = e;
+      z += e;
+    }
+    float zi = 1.0f / z;
+    for (int j = 0; j < n; ++j) wgt[i * n + j] *= zi;
+    t2[i] = 0.f;
+  }
+  __syncthreads();
+  // value row
+  for (int x = tid; x < ndh; x += nt) {
+    int i = x / dh, d = x % dh;
+    float acc = 0.f;
+    for (int j = 0; j < n; ++j) acc = fmaf(wgt[i * n + j], v0[j * ldh + d], acc);
+    out[((w * n + i) * (long long)Cd) * ldo + h * dh + d] = acc;
+  }
+  if (!track) return;
+
+  for (int kk = 0; kk < K; ++kk) {
+    const int comp = 1 + kk;
+    __syncthreads();
+    for (int x = tid; x < ndh; x += nt) {
+      int i = x / dh, d = x % dh;
+      qJ[i * ldh + d] = attn_fetch(q, w, n, i, comp, q.off + h * dh + d, Cd);
+      kJ[i * ldh + d] = attn_fetch(k, w, n, i, comp, k.off + h * dh + d, Cd);
+      vJ[i * ldh + d] = attn_fetch(v, w, n, i, comp, v.off + h * dh + d, Cd);
+    }
+    __syncthreads();
+    for (int x = tid; x < nn; x += nt) {
+      int i = x / n, j = x % n;
+      float a1 = 0.f, a2 = 0.f;
+      for (int d = 0; d < dh; ++d) {
+        float qj = qJ[i * ldh + d], kj = kJ[j * ldh + d];
+        a1 = fmaf(qj, k0[j * ldh + d], a1);
+        a1 = fmaf(q0[i * ldh + d], kj, a1);
+        a2 = fmaf(qj, kj, a2);
+      }
+      aJ[x] = a1 * scale;
+      aL[x] = fmaf(2.0f * scale, a2, aL[x]);
+    }
+    __syncthreads();
+    for (int i = tid; i < n; i += nt) {
+      float ab = 0.f;
+      for (int m = 0; m < n; ++m) ab = fmaf(wgt[i * n + m], aJ[i * n + m], ab);
+      abar[i] = ab;
+    }
+    __syncthreads();
+    for (int x = tid; x < nn; x += nt) {
+      int i = x / n;
+      float c = aJ[x] - abar[i];
+      float wj = wgt[x] * c;
+      t1[x] = fmaf(wj, c, t1[x]);
+      wJ[x] = wj;
+    }
+    __syncthreads();
+    for (int i = tid; i < n; i += nt) {
+      float acc = 0.f;
+      for (int m = 0; m < n; ++m) acc = fmaf(wJ[i * n + m], aJ[i * n + m], acc);
+      t2[i] += acc;
+    }
+    for (int x = tid; x < ndh; x += nt) {
+      int i = x / dh, d = x % dh;
+      float acc = 0.f, acc2 = 0.f;
+      for (int j = 0; j < n; ++j) {
+        float wj = wJ[i * n + j];
+        float vj = vJ[j * ldh + d];
+        acc = fmaf(wj, v0[j * ldh + d], acc);
+        acc = fmaf(wgt[i * n + j], vj, acc);
+        acc2 = fmaf(wj, vj, acc2);
+      }
+      out[((w * n + i) * (long long)Cd + comp) * ldo + h * dh + d] = acc;
+      oL[i * ldh + d] = fmaf(2.0f, acc2, oL[i * ldh + d]);
+    }
+  }
+  // Laplacian row
+  __syncthreads();
+  const int cl = Cd - 1;
+  for (int x = tid; x < ndh; x += nt) {
+    int i = x / dh, d = x % dh;
+    qJ[i * ldh + d] = attn_fetch(q, w, n, i, cl, q.off + h * dh + d, Cd);
+    kJ[i * ldh + d] = attn_fetch(k, w, n, i, cl, k.off + h * dh + d, Cd);
+    vJ[i * ldh + d] = attn_fetch(v, w, n, i, cl, v.off + h * dh + d, Cd);
+  }
+  __syncthreads();
+  for (int x = tid; x < nn; x += nt) {
+    int i = x / n, j = x % n;
+    float a1 = 0.f;
+    for (int d = 0; d < dh; ++d) {
+      a1 = fmaf(qJ[i * ldh + d], k0[j * ldh + d], a1);
+      a1 = fmaf(q0[i * ldh + d], kJ[j * ldh + d], a1);
+    }
+    aL[x] = fmaf(a1, scale, aL[x]);
+  }
+  __syncthreads();
+  for (int i = tid; i < n; i += nt) {
+    float ab = 0.f;
+    for (int m = 0; m < n; ++m) ab = fmaf(wgt[i * n + m], aL[i * n + m], ab);
+    abar[i] = ab;
+  }
+  __syncthreads();
+  for (int x = tid; x < nn; x += nt) {
+    int i = x / n;
+    aJ[x] = t1[x] + wgt[x] * (aL[x] - abar[i] - t2[i]);  // wL
+  }
+  __syncthreads();
+  for (int x = tid; x < ndh; x += nt) {
+    int i = x / dh, d = x % dh;
+    float acc = oL[i * ldh + d];
+    for (int j = 0; j < n; ++j) {
+      acc = fmaf(aJ[i * n + j], v0[j * ldh + d], acc);
+      acc = fmaf(wgt[i * n + j], vJ[j * ldh + d], acc);
+    }
+    out[((w * n + i) * (long long)Cd + cl) * ldo + h * dh + d] = acc;
+  }
+}
+
+int jq_launch_attention_fl(const JqAttnOperand& q, const JqAttnOperand& k, const JqAttnOperand& v, float* out, int ldo,
+                           long long W, int n, int H, int dh, int track, cudaStream_t st) {
+  if (W <= 0) return JQ_OK;
+  const int Cd = track ? 3 * n + 2 : 1;
+  JQ_REQUIRE(v.C == Cd && (q.C == Cd || (track && q.C == 5)) && (k.C == Cd || (track && k.C == 5)),
+             JQ_ERR_INVALID_ARGUMENT, "attention: operand components %d/%d/%d do not match %d", q.C, k.C, v.C, Cd);
+  size_t smem = sizeof(float) * ((size_t)7 * n * (dh + 1) + (size_t)5 * n * n + 2 * n);
+  JQ_REQUIRE(smem <= 220 * 1024, JQ_ERR_UNSUPPORTED, "attention: n=%d head_dim=%d need %zu bytes of shared memory", n, dh,
+             smem);
+#ifndef JAQMC_HOST_EMU
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(k_attention_fl, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    JQ_REQUIRE(e == cudaSuccess, JQ_ERR_CUDA, "attention: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+  }
+#endif
+  double K = track ? 3.0 * n + 1.0 : 0.0;
+  jq_prof_work((double)W * H * (4.0 * n * n * dh * (1.0 + 2.0 * K)), 4.0 * (double)W * n * Cd * H * dh * 4);
+  JQ_LAUNCH(k_attention_fl, dim3((unsigned)(W * H)), dim3(256), smem, st, q, k, v, out, ldo, n, H, dh, track);
+  JQ_CHECK_LAUNCH();
+  return JQ_OK;
+}

@@ -30,8 +30,9 @@ struct JqSpins {
 };
 
 // ---- kernels implemented in features.cu ---------------------------------------------------------
+// ae [W][n][C1][4A (+1 with spin_column)] Local1, ee [W][n*n][C2][4] Local2 (skipped when ee == nullptr)
 int jq_launch_mol_features(const float* electrons, const float* atoms, int W, JqSpins sp, int A, int rescale,
-                           int track, float* ae, float* ee, cudaStream_t st);
+                           int track, int spin_column, float* ae, float* ee, cudaStream_t st);
 int jq_launch_coulomb(const float* electrons, const float* atoms, const float* charges, int W, int n, int A,
                       float* e_pot, cudaStream_t st);
 
@@ -41,8 +42,9 @@ struct JqDenseArgs {
   int k0;
   const float* src1;  // optional second source concatenated along the contraction axis, [..][C][k1]
   int k1;
-  const float* w0;    // [k0][N]  rows of the flax kernel that multiply src0
-  const float* w1;    // [k1][N]
+  const float* w0;    // [k0][ldw]  rows of the flax kernel that multiply src0 (columns [0, N) of each row)
+  const float* w1;    // [k1][ldw]
+  int ldw;            // row stride of w0 / w1 (0 -> N); lets a launch take a column block of a wider kernel
   const float* bias;  // [N] or null; added to the value row only
   const float* cadd;  // [W][C][N] or null; per-walker addend broadcast over the walker's groups
   float* out;         // [groups_total][C][N]
@@ -88,3 +90,16 @@ int jq_launch_mh_propose(const float* x1, const float* normals, const float* std
 int jq_launch_mh_accept(float* x1, const float* x2, float* lp1, const float* lp2, const float* log_u,
                         const float* next_normals, const float* stddev, float* x2_next, int W, int row,
                         float scale, float* n_accept, unsigned char* accepted, cudaStream_t st);
+
+// ---- kernels implemented in attention.cu ----------------------------------------------------------
+struct JqAttnOperand {
+  const float* p;
+  int C;    // components stored: 3n+2 (dense), 5 (Local1) or 1 (value only)
+  int ld;   // row length
+  int off;  // first column of head 0
+};
+int jq_launch_densify_local1(const float* in, float* out, long long W, int n, int F, cudaStream_t st);
+int jq_launch_layernorm_fl(const float* x, const float* scale, const float* bias, float* out, long long G, int C, int F,
+                           float eps, cudaStream_t st);
+int jq_launch_attention_fl(const JqAttnOperand& q, const JqAttnOperand& k, const JqAttnOperand& v, float* out, int ldo,
+                           long long W, int n, int H, int dh, int track, cudaStream_t st);

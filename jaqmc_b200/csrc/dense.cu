@@ -33,6 +33,7 @@ __global__ void __launch_bounds__(256) k_dense_simt(JqDenseArgs a) {
   const int tid = threadIdx.x;
   const int ty = tid / 16, tx = tid % 16;
   const int kt = a.k0 + a.k1;
+  const int ldw = a.ldw ? a.ldw : a.N;
   float acc[8][4];
 #pragma unroll
   for (int i = 0; i < 8; ++i)
@@ -69,7 +70,7 @@ __global__ void __launch_bounds__(256) k_dense_simt(JqDenseArgs a) {
       int kl = idx / GM_BN, cl = idx % GM_BN;
       int kk = kb + kl, col = col0 + cl;
       float v = 0.f;
-      if (kk < kt && col < a.N) v = (kk < a.k0) ? a.w0[(long long)kk * a.N + col] : a.w1[(long long)(kk - a.k0) * a.N + col];
+      if (kk < kt && col < a.N) v = (kk < a.k0) ? a.w0[(long long)kk * ldw + col] : a.w1[(long long)(kk - a.k0) * ldw + col];
       Bs[kl][cl] = v;
     }
     __syncthreads();
@@ -103,6 +104,10 @@ __global__ void __launch_bounds__(256) k_dense_simt(JqDenseArgs a) {
       float v = acc[i][j];
       if (a.cadd) v += a.cadd[(w * a.C + c) * a.N + col];
       if (a.bias && c == 0) v += a.bias[col];
+      if (a.act == 0 && a.res_mode) {  // linear layer with a residual connection (no activation)
+        float r = a.res[orow * a.N + col];
+        v = (a.res_mode == 1) ? (r + v) * 0.70710678118654752440f : r + v;
+      }
       a.out[orow * a.N + col] = v;
     }
   }
@@ -110,6 +115,7 @@ __global__ void __launch_bounds__(256) k_dense_simt(JqDenseArgs a) {
 #else
 __global__ void k_dense_simt(JqDenseArgs a) {
   const long long R = a.G * a.C;
+  const int ldw = a.ldw ? a.ldw : a.N;
   for (long long r = (long long)blockIdx.x * GM_BM; r < R && r < (long long)(blockIdx.x + 1) * GM_BM; ++r) {
     long long gs = r / a.C;
     int c = (int)(r % a.C);
@@ -118,10 +124,14 @@ __global__ void k_dense_simt(JqDenseArgs a) {
     long long w = g / a.n_tot;
     for (int col = blockIdx.y * GM_BN; col < a.N && col < (int)(blockIdx.y + 1) * GM_BN; ++col) {
       float v = 0.f;
-      for (int k = 0; k < a.k0; ++k) v = fmaf(a.src0[row * a.k0 + k], a.w0[(long long)k * a.N + col], v);
-      for (int k = 0; k < a.k1; ++k) v = fmaf(a.src1[row * a.k1 + k], a.w1[(long long)k * a.N + col], v);
+      for (int k = 0; k < a.k0; ++k) v = fmaf(a.src0[row * a.k0 + k], a.w0[(long long)k * ldw + col], v);
+      for (int k = 0; k < a.k1; ++k) v = fmaf(a.src1[row * a.k1 + k], a.w1[(long long)k * ldw + col], v);
       if (a.cadd) v += a.cadd[(w * a.C + c) * a.N + col];
       if (a.bias && c == 0) v += a.bias[col];
+      if (a.act == 0 && a.res_mode) {
+        float r = a.res[row * a.N + col];
+        v = (a.res_mode == 1) ? (r + v) * 0.70710678118654752440f : r + v;
+      }
       a.out[row * a.N + col] = v;
     }
   }
@@ -141,7 +151,6 @@ int jq_launch_dense(const JqDenseArgs& a, cudaStream_t st) {
   if (a.G <= 0 || a.N <= 0) return JQ_OK;
   JQ_REQUIRE(a.act == 0 || a.act == 1, JQ_ERR_INVALID_ARGUMENT, "dense: unknown activation %d", a.act);
   JQ_REQUIRE(a.res_mode == 0 || a.res != nullptr, JQ_ERR_INVALID_ARGUMENT, "dense: residual without source");
-  JQ_REQUIRE(a.act != 0 || a.res_mode == 0, JQ_ERR_INVALID_ARGUMENT, "dense: residual needs an activation");
   JQ_REQUIRE(a.k0 > 0 && a.src0 && a.w0 && a.out, JQ_ERR_INVALID_ARGUMENT, "dense: null operand");
   JQ_REQUIRE(a.k1 == 0 || (a.src1 && a.w1), JQ_ERR_INVALID_ARGUMENT, "dense: null second operand");
 #ifndef JAQMC_HOST_EMU

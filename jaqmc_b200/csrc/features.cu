@@ -7,9 +7,11 @@
 #include "aug.cuh"
 
 // one item per (walker, electron j, atom I)
+// spin_up >= 0 appends the spin-encoding column (+1 for the first spin_up electrons, -1 after; untracked constant):
+// backbone/psiformer.py:166-170, backbone/lapnet/_backbone.py:259-261.
 __global__ void k_mol_ae_features(const float* __restrict__ el, const float* __restrict__ atoms, long long items,
-                                  int n, int A, int rescale, int C, float* __restrict__ ae) {
-  const int F = 4 * A;
+                                  int n, int A, int rescale, int C, int spin_up, float* __restrict__ ae) {
+  const int F = 4 * A + (spin_up >= 0 ? 1 : 0);
   for (long long it = (long long)blockIdx.x * blockDim.x + threadIdx.x; it < items;
        it += (long long)gridDim.x * blockDim.x) {
     int I = (int)(it % A);
@@ -20,6 +22,11 @@ __global__ void k_mol_ae_features(const float* __restrict__ el, const float* __r
     float r = sqrtf(r2);
     float rinv = 1.0f / r;
     float* o = ae + g * C * F + 4 * I;  // component c lives at o + c*F
+    if (spin_up >= 0 && I == 0) {
+      float* sc = ae + g * C * F + 4 * A;
+      sc[0] = ((int)(g % n) < spin_up) ? 1.f : -1.f;
+      for (int c = 1; c < C; ++c) sc[c * F] = 0.f;
+    }
     if (!rescale) {
       // features (r, dx, dy, dz)
       o[0] = r;
@@ -110,14 +117,14 @@ __global__ void k_mol_ee_features(const float* __restrict__ el, long long items,
 }
 
 int jq_launch_mol_features(const float* electrons, const float* atoms, int W, JqSpins sp, int A, int rescale,
-                           int track, float* ae, float* ee, cudaStream_t st) {
+                           int track, int spin_column, float* ae, float* ee, cudaStream_t st) {
   int n = sp.n();
   long long items = (long long)W * n * A;
   if (items > 0) {
     int grid = jq_cdiv(items, 256);
     if (grid > 148 * 16) grid = 148 * 16;
     JQ_LAUNCH(k_mol_ae_features, dim3(grid), dim3(256), 0, st, electrons, atoms, items, n, A, rescale,
-              track ? 5 : 1, ae);
+              track ? 5 : 1, spin_column ? sp.n_up : -1, ae);
     JQ_CHECK_LAUNCH();
   }
   if (ee != nullptr) {

@@ -114,7 +114,7 @@ int jq_ferminet_forward(const jaqmc_ferminet_config* c, const jaqmc_ferminet_par
     JQ_REQUIRE(p->single_kernel[l] && p->single_bias[l] && (l == d.L - 1 || (p->double_kernel[l] && p->double_bias[l])),
                JQ_ERR_INVALID_ARGUMENT, "ferminet: null parameter in layer %d", l);
   // features: ae Local1 [W][n][C1][4A], ee Local2 [W][n*n][C2][4] (into h2a)
-  if ((rc = jq_launch_mol_features(electrons, sys->atoms, (int)W, d.sp, d.A, /*rescale=*/0, track, b.ae, b.h2a, st)))
+  if ((rc = jq_launch_mol_features(electrons, sys->atoms, (int)W, d.sp, d.A, /*rescale=*/0, track, /*spin_column=*/0, b.ae, b.h2a, st)))
     return rc;
 
   float* h2 = b.h2a;

@@ -32,3 +32,13 @@ int jq_head_forward(const JqHeadDims& d, const jaqmc_head_params* p, const float
                     cudaStream_t st);
 int jq_launch_jastrow(const float* electrons, const float* alpha_par, const float* alpha_anti, int W, JqSpins sp,
                       int track, float* extra, cudaStream_t st);
+
+// ---- LapNet / Psiformer pipelines (attnnets.cu) ---------------------------------------------------
+size_t jq_lapnet_ws_bytes(const jaqmc_lapnet_config* c, long long W, int track);
+int jq_lapnet_forward(const jaqmc_lapnet_config* c, const jaqmc_lapnet_params* p, const jaqmc_system* sys,
+                      const float* electrons, long long W, int track, void* ws, size_t ws_bytes, JqWfOut out,
+                      cudaStream_t st);
+size_t jq_psiformer_ws_bytes(const jaqmc_psiformer_config* c, long long W, int track);
+int jq_psiformer_forward(const jaqmc_psiformer_config* c, const jaqmc_psiformer_params* p, const jaqmc_system* sys,
+                         const float* electrons, long long W, int track, void* ws, size_t ws_bytes, JqWfOut out,
+                         cudaStream_t st);

@@ -142,3 +142,172 @@ class FermiNetWavefunction(Wavefunction):
         # rebuilt per call (a few dozen pointer reads): parameter leaves may have been replaced by the optimizer
         return _marshal.ferminet_handle(params, self.nspins, n_atoms, self.ndets, self.hidden_dims_single,
                                         self.hidden_dims_double, self.envelope, self.orbitals_spin_split)
+
+
+def _lecun(g, dev, *shape, fan_in=None):
+    fan_in = shape[0] if fan_in is None else fan_in
+    return (torch.randn(*shape, generator=g, dtype=torch.float32) / math.sqrt(fan_in)).to(dev)
+
+
+def _head_params(g, dev, nspins, n_atoms, ndets, hidden, split, envelope, bias_orbitals, jastrow, alpha_init):
+    """orbital_layer / envelope_layer / jastrow_layer sub-trees with the reference's initialisers
+    (output/orbital.py:59-78, output/envelope.py:131-135, jastrow.py:61-63)."""
+    n = sum(nspins)
+
+    def dg():
+        d = {"kernel": _lecun(g, dev, hidden, ndets, n)}
+        if bias_orbitals:
+            d["bias"] = torch.zeros(ndets, n, device=dev)
+        return d
+
+    orb = {"SplitChannelDense_0": {"DenseGeneral_0": dg(), "DenseGeneral_1": dg()}} if split else {"DenseGeneral_0": dg()}
+    ones = lambda: torch.ones(n, n_atoms, ndets, device=dev)  # noqa: E731
+    names = ["_env_up", "_env_down"] if split else ["_env"]
+    env = {nm: {"pi": ones(), "sigma": ones()} for nm in names} if envelope != "null" else {}
+    out = {"orbital_layer": orb, "envelope_layer": env}
+    if jastrow:
+        out["jastrow_layer"] = {"alpha_par": torch.full((1,), float(alpha_init), device=dev),
+                                "alpha_anti": torch.full((1,), float(alpha_init), device=dev)}
+    return out
+
+
+@dataclass
+class LapNetWavefunction(Wavefunction):
+    """LapNet ansatz (reference app/molecule/wavefunction/lapnet.py:39-135); same fields and defaults."""
+
+    nspins: tuple = (1, 1)
+    ndets: int = 16
+    num_layers: int = 4
+    num_heads: int = 4
+    heads_dim: int = 64
+    use_layernorm: bool = False
+    jastrow: str = "simple_ee"
+    use_input_bias: bool = True
+    use_backbone_bias: bool = True
+    num_local_updates: int = 2
+    envelope: str = "abs_isotropic"
+    use_orbital_bias: bool = False
+    rescale: bool = True
+    jastrow_alpha_init: float = 1.0
+    full_det: bool = True
+
+    def __post_init__(self):
+        if not self.full_det:
+            raise ValueError("LapNet requires full_det=True.")
+        if self.num_layers <= 0:
+            raise ValueError("LapNet requires at least one layer.")
+        if self.jastrow not in ("none", "simple_ee"):
+            raise ValueError(f"Invalid jastrow: {self.jastrow!r}. Must be one of: ['none', 'simple_ee']")
+        if self.use_layernorm:
+            raise NotImplementedError("use_layernorm=True is not supported by the CUDA pipeline")
+
+    def init_params(self, data: MoleculeData, rngs) -> dict:
+        """Flax-layout tree (backbone/lapnet/_backbone.py:40-64,169-189): LeCun-normal kernels, N(0,1) biases."""
+        dev = data.electrons.device
+        g = rngs if isinstance(rngs, torch.Generator) else torch.Generator(device="cpu").manual_seed(int(rngs))
+        A = data.atoms.shape[0]
+        hid = self.num_heads * self.heads_dim
+
+        def dense(fi, fo, use_bias):
+            d = {"kernel": _lecun(g, dev, fi, fo)}
+            if use_bias:
+                d["bias"] = torch.randn(fo, generator=g, dtype=torch.float32).to(dev)
+            return d
+
+        bb = {"input_projection": dense(4 * A + 1, hid, self.use_input_bias)}
+        for l in range(self.num_layers):
+            lp = {"qk_projection": dense(hid, 2 * hid, self.use_backbone_bias),
+                  "value_projection": dense(hid, hid, self.use_backbone_bias),
+                  "output_projection": dense(hid, hid, self.use_backbone_bias),
+                  "value_update": dense(hid, hid, self.use_backbone_bias)}
+            if l < self.num_layers - 1:
+                for j in range(self.num_local_updates):
+                    lp[f"qk_update_layers_{j}"] = dense(hid, hid, self.use_backbone_bias)
+            bb[f"layers_{l}"] = lp
+        split = self.nspins[0] > 0 and self.nspins[1] > 0
+        tree = {"backbone_layer": bb}
+        tree.update(_head_params(g, dev, self.nspins, A, self.ndets, hid, split, self.envelope, self.use_orbital_bias,
+                                 self.jastrow == "simple_ee", self.jastrow_alpha_init))
+        return {"params": tree}
+
+    def _handle(self, params, n_atoms: int):
+        return _marshal.lapnet_handle(params, self.nspins, n_atoms, self.ndets, self.num_layers, self.num_heads,
+                                      self.heads_dim, self.num_local_updates, self.envelope, self.rescale,
+                                      self.jastrow == "simple_ee")
+
+
+@dataclass
+class PsiformerWavefunction(Wavefunction):
+    """Psiformer ansatz (reference app/molecule/wavefunction/psiformer.py:39-167); same fields and defaults."""
+
+    nspins: tuple = (1, 1)
+    ndets: int = 16
+    num_layers: int = 4
+    num_heads: int = 4
+    heads_dim: int = 64
+    mlp_hidden_dims: list = field(default_factory=lambda: [256])
+    layer_norm_mode: str = "pre"
+    jastrow: str = "simple_ee"
+    with_bias: bool = True
+    input_bias: bool = True
+    envelope: str = "abs_isotropic"
+    orbitals_spin_split: bool = True
+    bias_orbitals: bool = False
+    rescale: bool = True
+    jastrow_alpha_init: float = 1.0
+    full_det: bool = True
+
+    def __post_init__(self):
+        if not self.full_det:
+            raise ValueError("Psiformer requires full_det=True.")
+        if self.jastrow not in ("none", "simple_ee"):
+            raise ValueError(f"Invalid jastrow: {self.jastrow!r}. Must be one of: ['none', 'simple_ee']")
+        if self.layer_norm_mode not in ("pre", "post", "null"):
+            raise ValueError(f"Invalid layer_norm_mode: {self.layer_norm_mode!r}")
+
+    def init_params(self, data: MoleculeData, rngs) -> dict:
+        """Flax-layout tree (backbone/psiformer.py:60-99,175-185): LeCun-normal kernels, zero biases, LayerNorm
+        scale 1 / bias 0."""
+        dev = data.electrons.device
+        g = rngs if isinstance(rngs, torch.Generator) else torch.Generator(device="cpu").manual_seed(int(rngs))
+        A = data.atoms.shape[0]
+        H, dh = self.num_heads, self.heads_dim
+        hid = H * dh
+
+        def dense(fi, fo, use_bias=True):
+            d = {"kernel": _lecun(g, dev, fi, fo)}
+            if use_bias:
+                d["bias"] = torch.zeros(fo, device=dev)
+            return d
+
+        def proj():
+            d = {"kernel": _lecun(g, dev, hid, H, dh)}
+            if self.with_bias:
+                d["bias"] = torch.zeros(H, dh, device=dev)
+            return d
+
+        bb = {"Dense_0": dense(4 * A + 1, hid, self.input_bias)}
+        for l in range(self.num_layers):
+            out = {"kernel": _lecun(g, dev, H, dh, hid, fan_in=hid)}
+            if self.with_bias:
+                out["bias"] = torch.zeros(hid, device=dev)
+            lp = {"MultiHeadDotProductAttention_0": {"query": proj(), "key": proj(), "value": proj(), "out": out}}
+            if self.layer_norm_mode != "null":
+                for nm in ("LayerNorm_0", "LayerNorm_1"):
+                    lp[nm] = {"scale": torch.ones(hid, device=dev), "bias": torch.zeros(hid, device=dev)}
+            fan = hid
+            for j, h in enumerate(list(self.mlp_hidden_dims) + [hid]):
+                lp[f"Dense_{j}"] = dense(fan, h)
+                fan = h
+            bb[f"PsiformerLayer_{l}"] = lp
+        split = self.orbitals_spin_split and self.nspins[0] > 0 and self.nspins[1] > 0
+        tree = {"backbone_layer": bb}
+        tree.update(_head_params(g, dev, self.nspins, A, self.ndets, hid, split, self.envelope, self.bias_orbitals,
+                                 self.jastrow == "simple_ee", self.jastrow_alpha_init))
+        return {"params": tree}
+
+    def _handle(self, params, n_atoms: int):
+        return _marshal.psiformer_handle(params, self.nspins, n_atoms, self.ndets, self.num_layers, self.num_heads,
+                                         self.heads_dim, tuple(self.mlp_hidden_dims), self.layer_norm_mode,
+                                         self.envelope, self.orbitals_spin_split, self.rescale,
+                                         self.jastrow == "simple_ee")

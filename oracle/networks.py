@@ -291,8 +291,8 @@ def lapnet_logpsi(params, electrons, atoms, nspins, heads=4):
 # ---------------------------------------------------------------------------------------
 # Psiformer
 # ---------------------------------------------------------------------------------------
-def psiformer_backbone(p, ae_features, nspins):
-    """``backbone/psiformer.py:143-187`` with pre-LN layers ``:60-99``."""
+def psiformer_backbone(p, ae_features, nspins, layer_norm_mode="pre"):
+    """``backbone/psiformer.py:143-187``; layers ``:60-99`` in the three LayerNorm modes (pre is the default)."""
     n_up, n_dn = nspins
     n = n_up + n_dn
     spins = torch.cat([torch.ones(n_up, dtype=F64), -torch.ones(n_dn, dtype=F64)])
@@ -302,7 +302,7 @@ def psiformer_backbone(p, ae_features, nspins):
     while f"PsiformerLayer_{li}" in p:
         lp = p[f"PsiformerLayer_{li}"]
         mha = lp["MultiHeadDotProductAttention_0"]
-        x_in = layer_norm(lp["LayerNorm_0"], x, 1e-5)
+        x_in = layer_norm(lp["LayerNorm_0"], x, 1e-5) if layer_norm_mode == "pre" else x
         q = L.dense(x_in, mha["query"]["kernel"], mha["query"].get("bias"))
         k = L.dense(x_in, mha["key"]["kernel"], mha["key"].get("bias"))
         v = L.dense(x_in, mha["value"]["kernel"], mha["value"].get("bias"))
@@ -313,21 +313,28 @@ def psiformer_backbone(p, ae_features, nspins):
         if "bias" in mha["out"]:
             out = out + mha["out"]["bias"]
         x = x + out
-        m = layer_norm(lp["LayerNorm_1"], x, 1e-5)
+        if layer_norm_mode == "pre":
+            m = layer_norm(lp["LayerNorm_1"], x, 1e-5)
+        elif layer_norm_mode == "post":
+            m = x = layer_norm(lp["LayerNorm_0"], x, 1e-5)
+        else:
+            m = x
         j = 0
         while f"Dense_{j}" in lp:
             m = L.tanh(L.dense(m, lp[f"Dense_{j}"]["kernel"], lp[f"Dense_{j}"].get("bias")))
             j += 1
         x = x + m
+        if layer_norm_mode == "post":
+            x = layer_norm(lp["LayerNorm_1"], x, 1e-5)
         li += 1
     return x
 
 
-def psiformer_logpsi(params, electrons, atoms, nspins):
+def psiformer_logpsi(params, electrons, atoms, nspins, layer_norm_mode="pre"):
     """``app/molecule/wavefunction/psiformer.py:137-167``."""
     p = params["params"]
     emb = molecule_features(electrons, atoms, rescale=True)
-    h = psiformer_backbone(p["backbone_layer"], emb["ae_features"], nspins)
+    h = psiformer_backbone(p["backbone_layer"], emb["ae_features"], nspins, layer_norm_mode)
     orb = orbital_projection(p["orbital_layer"], h, nspins) * envelope(p["envelope_layer"], emb["r_ae"], nspins)
     sign, lp = logdet_sum(orb)
     if "jastrow_layer" in p:
