@@ -35,11 +35,30 @@ import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
 WORKLOADS = {
-    # name: (molecule, ndets, hidden_single, hidden_double, description)
+    # name: (molecule, ndets, hidden_single, hidden_double, description[, network kind])
     "n2": ("N2", 16, (256,) * 4, (32,) * 4, "FermiNet-N2 (14 electrons, 16 dets, 256x4/32x4)"),
     "li": ("Li", 16, (256,) * 4, (32,) * 4, "FermiNet-Li (3 electrons, 16 dets, 256x4/32x4)"),
     "lih": ("LiH", 16, (256,) * 4, (32,) * 4, "FermiNet-LiH (4 electrons, 16 dets, 256x4/32x4)"),
+    "n2-lapnet": ("N2", 16, None, None, "LapNet-N2 (14 electrons, 16 dets, 4 layers x 4 heads x 64)", "lapnet"),
+    "n2-psiformer": ("N2", 16, None, None, "Psiformer-N2 (14 electrons, 16 dets, 4 x 4 x 64, MLP 256)", "psiformer"),
 }
+
+
+def workload_kind(name):
+    w = WORKLOADS[name]
+    return w[5] if len(w) > 5 else "ferminet"
+
+
+def make_wavefunction(name, nspins):
+    from jaqmc_b200.wavefunction import FermiNetWavefunction, LapNetWavefunction, PsiformerWavefunction
+
+    mol, ndets, hs, hd, desc = WORKLOADS[name][:5]
+    kind = workload_kind(name)
+    if kind == "lapnet":
+        return LapNetWavefunction(nspins=nspins, ndets=ndets)
+    if kind == "psiformer":
+        return PsiformerWavefunction(nspins=nspins, ndets=ndets)
+    return FermiNetWavefunction(nspins=nspins, ndets=ndets, hidden_dims_single=list(hs), hidden_dims_double=list(hd))
 METRIC = "local_energy_evals_per_sec"
 UNIT = "evals/s"
 
@@ -62,13 +81,22 @@ def cpu_rate(workload: str, budget_s: float, chunk: int = 64):
     from oracle import lap as L
     from oracle import networks as ON
 
-    mol, ndets, hs, hd, _ = WORKLOADS[workload]
+    mol, ndets, hs, hd = WORKLOADS[workload][:4]
+    kind = workload_kind(workload)
     atoms, charges, nspins = H.molecule(mol)
-    p = ON.tree_map(lambda t: t.float(), ON.init_ferminet_params(nspins, atoms.shape[0], ndets, hs, hd, seed=1))
     at, ch = atoms.float(), charges.float()
+    if kind == "lapnet":
+        p = ON.tree_map(lambda t: t.float(), ON.init_lapnet_params(nspins, atoms.shape[0], ndets, seed=1))
+        net = lambda x: ON.lapnet_logpsi(p, x, at, nspins)  # noqa: E731
+    elif kind == "psiformer":
+        p = ON.tree_map(lambda t: t.float(), ON.init_psiformer_params(nspins, atoms.shape[0], ndets, seed=1))
+        net = lambda x: ON.psiformer_logpsi(p, x, at, nspins)  # noqa: E731
+    else:
+        p = ON.tree_map(lambda t: t.float(), ON.init_ferminet_params(nspins, atoms.shape[0], ndets, hs, hd, seed=1))
+        net = lambda x: ON.ferminet_logpsi(p, x, at, nspins)  # noqa: E731
 
     def one(e):
-        out = ON.ferminet_logpsi(p, L.seed(e), at, nspins)[1]
+        out = net(L.seed(e))[1]
         g = out.jac.reshape(-1)
         return -0.5 * out.lap - 0.5 * (g * g).sum() + OE.potential_energy(e, at, ch)
 
@@ -98,7 +126,7 @@ def run_reference(args):
             rates.append(r)
             total += done
     value = float(np.mean(rates))
-    mol, ndets, hs, hd, desc = WORKLOADS[args.workload]
+    mol, ndets, hs, hd, desc = WORKLOADS[args.workload][:5]
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * args.walkers / value, "higher_is_better": True, "scaling": "strong",
@@ -179,8 +207,6 @@ def run_ours(args):
     import helpers as H
     from jaqmc_b200.data import MoleculeData
     from jaqmc_b200.sampler import MCMCSampler, SamplePlan
-    from jaqmc_b200.wavefunction import FermiNetWavefunction
-
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -192,14 +218,14 @@ def run_ours(args):
     if args.gpus != world and rank == 0:
         print(f"warning: --gpus {args.gpus} but WORLD_SIZE={world}", file=sys.stderr)
 
-    mol, ndets, hs, hd, desc = WORKLOADS[args.workload]
+    mol, ndets, hs, hd, desc = WORKLOADS[args.workload][:5]
     atoms64, charges64, nspins = H.molecule(mol)
     n = sum(nspins)
     W = args.walkers
     if W % world:
         raise SystemExit(f"--walkers {W} not divisible by {world} ranks")
     Wl = W // world
-    wf = FermiNetWavefunction(nspins=nspins, ndets=ndets, hidden_dims_single=list(hs), hidden_dims_double=list(hd))
+    wf = make_wavefunction(args.workload, nspins)
     atoms, charges = atoms64.float().to(dev), charges64.float().to(dev)
     el_all = H.synthetic_walkers(atoms64, charges64, nspins, W, seed=0).float()
     el_host = el_all[rank * Wl:(rank + 1) * Wl].contiguous().pin_memory()
@@ -209,7 +235,7 @@ def run_ours(args):
     plan = SamplePlan(wf, MCMCSampler(steps=10))
     st = plan.init(data)
     gen = torch.Generator(device=dev).manual_seed(1234 + rank)
-    for _ in range(2):
+    for _ in range(0 if args.no_equilibrate else 2):
         data, _, st = plan.step(params, data, st, gen)
     el_host.copy_(data.electrons.cpu())
     from jaqmc_b200._runtime import runtime
@@ -340,6 +366,7 @@ def main():
     ap.add_argument("--walkers", type=int, default=4096, help="global walker batch (reference workflow.batch_size)")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-equilibrate", action="store_true", help="skip the MH sweeps before timing (profiling runs)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -1,0 +1,105 @@
+"""GPU parity tests of the LapNet and Psiformer hot paths: CUDA kernels (through the C ABI) vs the float64 oracle.
+Tolerances as in test_gpu_ferminet.py (float32, relative to the magnitude of the terms summed)."""
+
+import numpy as np
+import pytest
+import torch
+
+import helpers as H
+from jaqmc_b200 import _marshal as M
+from oracle import networks as ON
+
+pytestmark = pytest.mark.gpu
+
+
+def _rt():
+    from jaqmc_b200._runtime import runtime
+
+    return runtime(torch.device("cuda", 0))
+
+
+def _lapnet(mol, ndets, layers, heads, dh, W, seed=0, jastrow=True):
+    dev = torch.device("cuda", 0)
+    atoms, charges, nspins = H.molecule(mol)
+    p64 = H.round_f32(ON.init_lapnet_params(nspins, atoms.shape[0], ndets, layers, heads, dh, 2, seed=seed + 3,
+                                            jastrow=jastrow))
+    el = H.synthetic_walkers(atoms, charges, nspins, W, seed=seed)
+    wf = M.lapnet_handle(H.to_f32(p64, dev), nspins, atoms.shape[0], ndets, layers, heads, dh, 2, jastrow=jastrow)
+    sysh = M.system_handle(atoms.float().to(dev), charges.float().to(dev))
+    return wf, sysh, el, atoms, charges, nspins, (lambda e: ON.lapnet_logpsi(p64, e, atoms, nspins, heads))
+
+
+def _psiformer(mol, ndets, layers, heads, dh, mlp, W, seed=0, lnm="pre"):
+    dev = torch.device("cuda", 0)
+    atoms, charges, nspins = H.molecule(mol)
+    p64 = H.round_f32(ON.init_psiformer_params(nspins, atoms.shape[0], ndets, layers, heads, dh, mlp, seed=seed + 5))
+    el = H.synthetic_walkers(atoms, charges, nspins, W, seed=seed)
+    wf = M.psiformer_handle(H.to_f32(p64, dev), nspins, atoms.shape[0], ndets, layers, heads, dh, mlp, lnm)
+    sysh = M.system_handle(atoms.float().to(dev), charges.float().to(dev))
+    return wf, sysh, el, atoms, charges, nspins, (lambda e: ON.psiformer_logpsi(p64, e, atoms, nspins, lnm))
+
+
+def _check(setup, e_tol=2e-5, l_tol=2e-6):
+    rt = _rt()
+    wf, sysh, el, atoms, charges, nspins, fn = setup
+    e32 = el.float().contiguous().cuda()
+    out = {k: v.cpu().numpy() for k, v in rt.local_energy(wf, sysh, e32).items()}
+    ref = H.oracle_batch(fn, el, atoms, charges)
+    assert np.array_equal(out["sign"], ref["sign"])
+    e_err, l_err = H.assert_fp32_parity(out, ref, el, e_tol=e_tol, l_tol=l_tol)
+    print("scaled errors: E_L max %.2e, logpsi max %.2e" % (e_err.max(), l_err.max()))
+    lp, sg = rt.logpsi(wf, sysh, e32)
+    assert torch.equal(sg.cpu(), torch.from_numpy(out["sign"]))
+    np.testing.assert_allclose(lp.cpu().numpy(), out["logpsi"], rtol=2e-6, atol=2e-5)
+
+
+@pytest.mark.parametrize("mol,ndets,layers,heads,dh", [
+    ("Li", 3, 2, 2, 8),
+    ("LiH", 16, 4, 4, 64),   # default LapNet network on a 4-electron system
+    ("H", 2, 2, 2, 16),
+])
+def test_lapnet_parity_small(mol, ndets, layers, heads, dh):
+    _check(_lapnet(mol, ndets, layers, heads, dh, 6))
+
+
+def test_lapnet_parity_n2_full_network():
+    """BASELINE config 3: N2, LapNet 4 layers x 4 heads x 64, 16 determinants."""
+    _check(_lapnet("N2", 16, 4, 4, 64, 6))
+
+
+@pytest.mark.parametrize("mol,ndets,layers,heads,dh,mlp,lnm", [
+    ("Li", 3, 2, 2, 8, (16,), "pre"),
+    ("LiH", 16, 4, 4, 64, (256,), "pre"),   # default Psiformer network on a 4-electron system
+    ("LiH", 4, 2, 2, 32, (64,), "post"),
+    ("He", 2, 2, 2, 16, (32, 64), "null"),
+])
+def test_psiformer_parity_small(mol, ndets, layers, heads, dh, mlp, lnm):
+    _check(_psiformer(mol, ndets, layers, heads, dh, mlp, 6, lnm=lnm))
+
+
+def test_psiformer_parity_n2_full_network():
+    """Default Psiformer network (4 x 4 x 64, MLP 256) on N2 (14 electrons)."""
+    _check(_psiformer("N2", 16, 4, 4, 64, (256,), 4))
+
+
+def test_attention_nets_full_batch_properties():
+    """Size-independent properties at 4096 walkers: finite energies, antisymmetry, walker-permutation equivariance."""
+    rt = _rt()
+    W = 4096
+    for setup in (_lapnet("Li", 16, 4, 4, 64, W, seed=9), _psiformer("Li", 16, 4, 4, 64, (256,), W, seed=9)):
+        wf, sysh, el, atoms, charges, nspins, fn = setup
+        e32 = el.float().contiguous().cuda()
+        out = rt.local_energy(wf, sysh, e32)
+        assert torch.isfinite(out["e_loc"]).all()
+        sw = e32.clone()
+        sw[:, [0, 1]] = sw[:, [1, 0]]
+        out_sw = rt.local_energy(wf, sysh, sw.contiguous())
+        assert torch.equal(out_sw["sign"], -out["sign"])
+        lscale = out["logpsi"].abs() + out["grad"].norm(dim=1) * e32.reshape(W, -1).norm(dim=1)
+        assert ((out_sw["logpsi"] - out["logpsi"]).abs() / lscale).max() < 4e-6
+        scale = 0.5 * out["lap"].abs() + 0.5 * (out["grad"] ** 2).sum(1) + out["e_pot"].abs()
+        assert ((out_sw["e_loc"] - out["e_loc"]).abs() / scale).max() < 4e-5
+        perm = torch.randperm(W, device=e32.device)
+        out_p = rt.local_energy(wf, sysh, e32[perm].contiguous())
+        for k in ("logpsi", "sign", "e_loc"):
+            assert torch.equal(out_p[k], out[k][perm]), k
