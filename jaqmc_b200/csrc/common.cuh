@@ -27,6 +27,9 @@ struct jq_dim3 {
   jq_dim3(unsigned a = 1, unsigned b = 1, unsigned c = 1) : x(a), y(b), z(c) {}
 };
 typedef jq_dim3 dim3;
+struct float4 {
+  float x, y, z, w;
+};
 typedef void* cudaStream_t;
 typedef int cudaError_t;
 #define cudaSuccess 0

@@ -138,6 +138,80 @@ __global__ void k_dense_simt(JqDenseArgs a) {
 }
 #endif
 
+// ------------------------------------------------------------------------------------------------
+// Narrow layers with few components per group (FermiNet's two-electron stream: Local2, C = 8, 4/32 -> 32 features;
+// Local1 layers, C = 5): one fused kernel per layer.  A block stages a tile of SM_GT groups [C][k0] in shared memory
+// with coalesced loads; each item owns one (group, output feature) with all C components in registers, so the bias,
+// the tanh forward-Laplacian rule and the residual are private to the item, and the tile doubles as the residual
+// source when the layer is square.  HBM traffic = read x once + write out once.
+// ------------------------------------------------------------------------------------------------
+#define SM_GT 32
+#define SM_CMAX 8
+__global__ void k_dense_small(JqDenseArgs a) {
+  JQ_DYN_SMEM(float, sm);
+  const int C = a.C, K = a.k0, N = a.N;
+  const int ldw = a.ldw ? a.ldw : N;
+  float* Ws = sm;                 // [K][N]
+  float* Xs = Ws + K * N;         // [SM_GT][C][K]
+  const long long g0 = (long long)blockIdx.x * SM_GT;
+  const int ng = (int)((a.G - g0 < SM_GT) ? a.G - g0 : SM_GT);
+  const int tid = threadIdx.x, nt = blockDim.x;
+  for (int q = tid; q < K * N; q += nt) Ws[q] = a.w0[(long long)(q / N) * ldw + (q % N)];
+  const float* xg = a.src0 + g0 * C * K;
+  for (int q = tid; q < ng * C * K; q += nt) Xs[q] = xg[q];
+  __syncthreads();
+  const float inv_sqrt2 = 0.70710678118654752440f;
+  const bool res_from_tile = (a.res == a.src0) && (K == N);
+  for (int q = tid; q < ng * N; q += nt) {
+    const int gl = q / N, f = q % N;
+    const float* xr = Xs + gl * C * K;
+    float acc[SM_CMAX];
+#pragma unroll
+    for (int c = 0; c < SM_CMAX; ++c) acc[c] = 0.f;
+    for (int k = 0; k < K; ++k) {
+      const float w = Ws[k * N + f];
+#pragma unroll
+      for (int c = 0; c < SM_CMAX; ++c)
+        if (c < C) acc[c] = fmaf(xr[c * K + k], w, acc[c]);
+    }
+    if (a.bias) acc[0] += a.bias[f];
+    if (a.act == 1) {
+      const float t = tanhf(acc[0]);
+      const float d1 = 1.0f - t * t;
+      float s2 = 0.f;
+#pragma unroll
+      for (int c = 1; c < SM_CMAX - 1; ++c)
+        if (c < C - 1) {
+          s2 = fmaf(acc[c], acc[c], s2);
+          acc[c] *= d1;
+        }
+      if (C > 1) {
+#pragma unroll
+        for (int c = 1; c < SM_CMAX; ++c)
+          if (c == C - 1) acc[c] = d1 * acc[c] - 2.0f * t * d1 * s2;
+      }
+      acc[0] = t;
+    }
+    float* o = a.out + ((g0 + gl) * C) * N + f;
+    const float* rg = a.res ? a.res + ((g0 + gl) * C) * N + f : nullptr;
+#pragma unroll
+    for (int c = 0; c < SM_CMAX; ++c)
+      if (c < C) {
+        float v = acc[c];
+        if (a.res_mode) {
+          const float r = res_from_tile ? xr[c * K + f] : rg[(long long)c * N];
+          v = (a.res_mode == 1) ? (r + v) * inv_sqrt2 : r + v;
+        }
+        o[(long long)c * N] = v;
+      }
+  }
+}
+
+static bool dense_small_eligible(const JqDenseArgs& a) {
+  return a.C <= SM_CMAX && a.k1 == 0 && a.cadd == nullptr && a.n_sub == a.n_tot && a.k0 <= 64 && a.N <= 64 &&
+         a.out != a.src0;
+}
+
 #ifndef JAQMC_HOST_EMU
 int jq_launch_dense_tc(const JqDenseArgs& a, cudaStream_t st, bool* handled);  // dense_tc.cu
 #endif
@@ -159,6 +233,20 @@ int jq_launch_dense(const JqDenseArgs& a, cudaStream_t st) {
   if (rc != JQ_OK) return rc;
   if (handled) return JQ_OK;
 #endif
+  if (dense_small_eligible(a)) {
+    size_t smem = sizeof(float) * ((size_t)a.k0 * a.N + (size_t)SM_GT * a.C * a.k0);
+    jq_prof_work(2.0 * (double)a.G * a.C * a.k0 * a.N, 4.0 * (double)a.G * a.C * (a.k0 + a.N));
+#ifndef JAQMC_HOST_EMU
+    static bool attr_set = false;
+    if (!attr_set) {
+      cudaFuncSetAttribute(k_dense_small, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+      attr_set = true;
+    }
+#endif
+    JQ_LAUNCH(k_dense_small, dim3((unsigned)jq_cdiv(a.G, SM_GT)), dim3(256), smem, st, a);
+    JQ_CHECK_LAUNCH();
+    return JQ_OK;
+  }
   long long R = a.G * a.C;
   dim3 grid(jq_cdiv(R, GM_BM), jq_cdiv(a.N, GM_BN));
   jq_prof_work(2.0 * (double)R * (a.k0 + a.k1) * a.N, 4.0 * (double)R * (a.k0 + a.k1 + a.N));
@@ -358,29 +446,53 @@ int jq_launch_concat_layer1(const float* ae, const float* g2, float* out, int W,
 // Dense contribution is computed once per walker and broadcast, instead of once per electron).
 // ------------------------------------------------------------------------------------------------
 __global__ void k_spin_mean(const float* __restrict__ h, float* __restrict__ m, long long items, JqSpins sp, int C,
-                            int F) {
+                            int F, int vec) {
+  // one item per (walker, component, channel, `vec` consecutive features); vec = 4 when F % 4 == 0, else 1
   const int n = sp.n(), nch = sp.nch();
+  const int FV = F / vec;
   for (long long it = (long long)blockIdx.x * blockDim.x + threadIdx.x; it < items;
        it += (long long)gridDim.x * blockDim.x) {
-    int f = (int)(it % F);
-    long long t = it / F;
+    int fv = (int)(it % FV);
+    long long t = it / FV;
     int s = (int)(t % nch);
     t /= nch;
     int c = (int)(t % C);
     long long w = t / C;
     int lo = sp.lo(s), hi = sp.hi(s);
-    float acc = 0.f;
-    for (int e = lo; e < hi; ++e) acc += h[(((w * n + e) * (long long)C) + c) * F + f];
-    m[((w * C + c) * (long long)nch + s) * F + f] = acc / (float)(hi - lo);
+    const float* base = h + (((w * n + lo) * (long long)C) + c) * F + vec * fv;
+    const long long stride = (long long)C * F;
+    const float inv = 1.0f / (float)(hi - lo);
+    float* o = m + ((w * C + c) * (long long)nch + s) * F + vec * fv;
+    if (vec == 4) {
+      float4 a = {0.f, 0.f, 0.f, 0.f};
+      for (int e = lo; e < hi; ++e) {
+        float4 v = *reinterpret_cast<const float4*>(base + (e - lo) * stride);
+        a.x += v.x;
+        a.y += v.y;
+        a.z += v.z;
+        a.w += v.w;
+      }
+      a.x *= inv;
+      a.y *= inv;
+      a.z *= inv;
+      a.w *= inv;
+      *reinterpret_cast<float4*>(o) = a;
+    } else {
+      float a = 0.f;
+      for (int e = lo; e < hi; ++e) a += base[(e - lo) * stride];
+      o[0] = a * inv;
+    }
   }
 }
 
 int jq_launch_spin_mean(const float* h, float* m, int W, JqSpins sp, int C, int F, cudaStream_t st) {
-  long long items = (long long)W * C * sp.nch() * F;
+  const int vec = (F % 4 == 0) ? 4 : 1;
+  long long items = (long long)W * C * sp.nch() * (F / vec);
   if (items <= 0) return JQ_OK;
   int grid = jq_cdiv(items, 256);
   if (grid > 148 * 32) grid = 148 * 32;
-  JQ_LAUNCH(k_spin_mean, dim3(grid), dim3(256), 0, st, h, m, items, sp, C, F);
+  jq_prof_work(0.0, 4.0 * (double)W * C * F * (sp.n() + sp.nch()));
+  JQ_LAUNCH(k_spin_mean, dim3(grid), dim3(256), 0, st, h, m, items, sp, C, F, vec);
   JQ_CHECK_LAUNCH();
   return JQ_OK;
 }

@@ -29,10 +29,10 @@
 namespace {
 
 constexpr int TC_BK = 32;          // K chunk: 32 floats = 128 B = one SWIZZLE_128B row
-constexpr int TC_NMAX = 176;       // max MMA N (rows per tile)
+constexpr int TC_NMAX = 128;       // max MMA N (rows per tile); two accumulator buffers x two feature blocks = 512 TMEM columns
 constexpr int TC_STAGES = 2;
 constexpr int TC_MBLK = 128;       // features per MMA
-constexpr int TC_X_BYTES = TC_NMAX * 128;        // 22528 (multiple of 1024)
+constexpr int TC_X_BYTES = TC_NMAX * 128;        // 16384 (multiple of 1024)
 constexpr int TC_W_BYTES = 2 * TC_MBLK * 128;    // 32768: both 128-feature blocks
 constexpr int TC_STAGE_BYTES = 2 * TC_X_BYTES + 2 * TC_W_BYTES;  // Xh, Xl, Wh, Wl
 constexpr int TC_SMEM_BYTES = TC_STAGES * TC_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
@@ -132,6 +132,17 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
 #pragma unroll
   for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
 }
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, float* v) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ float tmem_ld1(uint32_t taddr) {
   uint32_t r;
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r) : "r"(taddr));
@@ -164,9 +175,9 @@ k_dense_tc(const __grid_constant__ CUtensorMap mapX0, const __grid_constant__ CU
   uint64_t* full = bars;                   // [TC_STAGES]  TMA -> converter
   uint64_t* ready = bars + TC_STAGES;      // [TC_STAGES]  converter -> MMA
   uint64_t* empty = bars + 2 * TC_STAGES;  // [TC_STAGES]  MMA -> TMA
-  uint64_t* acc_full = bars + 3 * TC_STAGES;
-  uint64_t* acc_empty = acc_full + 1;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 1);
+  uint64_t* acc_full = bars + 3 * TC_STAGES;   // [2]  MMA commit -> epilogue, per accumulator buffer
+  uint64_t* acc_empty = acc_full + 2;          // [2]  epilogue -> MMA
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -178,8 +189,10 @@ k_dense_tc(const __grid_constant__ CUtensorMap mapX0, const __grid_constant__ CU
       mbar_init(&ready[s], 4);   // one arrive per converter warp
       mbar_init(&empty[s], 1);
     }
-    mbar_init(acc_full, 1);
-    mbar_init(acc_empty, 8);     // one arrive per epilogue warp
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&acc_full[b], 1);
+      mbar_init(&acc_empty[b], 8);  // one arrive per epilogue warp
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -223,10 +236,11 @@ k_dense_tc(const __grid_constant__ CUtensorMap mapX0, const __grid_constant__ CU
     // ===================== MMA issuer =====================
     if (lane == 0) {
       PipeState ps;
-      uint32_t acc_phase = 0;
+      uint32_t it = 0;
       const uint32_t idesc = tc_idesc(TC_MBLK, p.n_mma);
-      for (long long t = blockIdx.x; t < p.tiles; t += gridDim.x) {
-        mbar_wait(acc_empty, acc_phase ^ 1);   // epilogue has drained the accumulators of the previous tile
+      for (long long t = blockIdx.x; t < p.tiles; t += gridDim.x, ++it) {
+        const uint32_t buf = it & 1, acc_phase = (it >> 1) & 1;
+        mbar_wait(&acc_empty[buf], acc_phase ^ 1);   // epilogue has drained this buffer (two tiles ago)
         tc_fence_after();
         for (int kc = 0; kc < kchunks; ++kc) {
           mbar_wait(&ready[ps.stage], ps.phase);
@@ -235,7 +249,7 @@ k_dense_tc(const __grid_constant__ CUtensorMap mapX0, const __grid_constant__ CU
           const uint32_t xh = sbase, xl = sbase + TC_X_BYTES;
           const uint32_t wh = sbase + 2 * TC_X_BYTES, wl = wh + TC_W_BYTES;
           for (int mb = 0; mb < p.mblocks; ++mb) {
-            const uint32_t d = tmem_base + mb * 256;
+            const uint32_t d = tmem_base + (buf * 2 + mb) * TC_NMAX;
             const uint32_t wh_mb = wh + mb * TC_MBLK * 128, wl_mb = wl + mb * TC_MBLK * 128;
 #pragma unroll
             for (int kk = 0; kk < TC_BK / 8; ++kk) {
@@ -248,8 +262,7 @@ k_dense_tc(const __grid_constant__ CUtensorMap mapX0, const __grid_constant__ CU
           tc_commit(&empty[ps.stage]);   // stage reusable once these MMAs have read it
           ps.advance();
         }
-        tc_commit(acc_full);
-        acc_phase ^= 1;
+        tc_commit(&acc_full[buf]);
       }
     }
   } else if (warp >= 4 && warp < 8) {
@@ -280,19 +293,26 @@ k_dense_tc(const __grid_constant__ CUtensorMap mapX0, const __grid_constant__ CU
     }
   } else if (warp >= 8) {
     // ===================== epilogue =====================
+    // A thread owns output feature f (TMEM lane) and walks the tile's groups; a group's C columns are fetched in
+    // chunks of 16 (tcgen05.ld x16), the matching addend / residual rows are loaded as 16 independent coalesced
+    // requests before any store is issued, and the tanh rule takes two passes over the (cheap to re-read) columns:
+    // pass 1 accumulates sum_k y_k^2, pass 2 emits the rows.
     const int q = warp & 3;            // TMEM lane quarter this warp may access
     const int mb = (warp - 8) >> 2;    // feature block
     const int f = mb * TC_MBLK + q * 32 + lane;
     const bool f_ok = (mb < p.mblocks) && (f < p.N_out);
-    const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16) + mb * 256;
     const float inv_sqrt2 = 0.70710678118654752440f;
     const float bias_f = (p.bias && f_ok) ? p.bias[f] : 0.f;
-    uint32_t acc_phase = 0;
     const int C = p.C;
-    for (long long t = blockIdx.x; t < p.tiles; t += gridDim.x) {
+    const long long N = p.N_out;
+    const int res_mode = p.res_mode;
+    uint32_t it = 0;
+    for (long long t = blockIdx.x; t < p.tiles; t += gridDim.x, ++it) {
+      const uint32_t buf = it & 1, acc_phase = (it >> 1) & 1;
+      const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16) + (buf * 2 + mb) * TC_NMAX;
       long long w_tma = t / p.tiles_per_w;
       int gsub0 = (int)(t % p.tiles_per_w) * p.G_t;
-      mbar_wait(acc_full, acc_phase);
+      mbar_wait(&acc_full[buf], acc_phase);
       tc_fence_after();
       if (mb < p.mblocks) {
         for (int gi = 0; gi < p.G_t; ++gi) {
@@ -300,73 +320,105 @@ k_dense_tc(const __grid_constant__ CUtensorMap mapX0, const __grid_constant__ CU
           if (gsub >= p.n_sub) break;  // warp-uniform
           long long g = w_tma * p.n_tot + p.j0 + gsub;       // actual group index
           long long orow = g * C;                              // first output row of the group
-          const float* cadd = p.cadd ? p.cadd + ((g / p.n_tot_true) * C) * (long long)p.N_out + f : nullptr;
-          const float* res = p.res ? p.res + orow * p.N_out + f : nullptr;
-          float* out = p.out + orow * p.N_out + f;
+          const float* __restrict__ cadd = (p.cadd && f_ok) ? p.cadd + ((g / p.n_tot_true) * C) * N + f : nullptr;
+          const float* __restrict__ res = (p.res && f_ok) ? p.res + orow * N + f : nullptr;
+          float* __restrict__ out = p.out + orow * N + f;
           const uint32_t tcol = tlane + gi * C;
-          if (p.act == 0) {
-            for (int c0 = 0; c0 < C; c0 += 8) {
-              float v[8];
-              if (c0 + 8 <= C) {
-                tmem_ld8(tcol + c0, v);
-              } else {
-                for (int i = 0; i < C - c0; ++i) v[i] = tmem_ld1(tcol + c0 + i);
-              }
-              int nc = (C - c0 < 8) ? C - c0 : 8;
-              if (f_ok)
-                for (int i = 0; i < nc; ++i) {
-                  int c = c0 + i;
-                  float y = v[i];
-                  if (cadd) y += cadd[(long long)c * p.N_out];
-                  if (c == 0) y += bias_f;
-                  if (p.res_mode == 1) y = (res[(long long)c * p.N_out] + y) * inv_sqrt2;
-                  else if (p.res_mode == 2) y = res[(long long)c * p.N_out] + y;
-                  out[(long long)c * p.N_out] = y;
+          // rows [r0, r1) of the group in chunks of 16 columns; the last chunk is shifted back to stay inside the
+          // group's columns (needs r1 - r0 >= 16; shorter ranges go column by column)
+          float th = 0.f, d1 = 1.f, s2 = 0.f;
+          int r0 = 0, r1 = C;
+          if (p.act == 1) {
+            float x = tmem_ld1(tcol);
+            if (cadd) x += cadd[0];
+            x += bias_f;
+            th = tanhf(x);
+            d1 = 1.0f - th * th;
+            r0 = 1;
+            r1 = C - 1;  // Jacobian rows
+            // ---- pass 1: s2 = sum_k y_k^2
+            if (r1 - r0 >= 16) {
+              for (int c0 = r0; c0 < r1; c0 += 16) {
+                int cs = c0, skip = 0;
+                if (c0 + 16 > r1) {
+                  cs = r1 - 16;
+                  skip = c0 - cs;
                 }
+                float v[16], ca[16];
+                tmem_ld16_nowait(tcol + cs, v);
+#pragma unroll
+                for (int i = 0; i < 16; ++i) ca[i] = cadd ? cadd[(long long)(cs + i) * N] : 0.f;
+                tmem_wait_ld();
+#pragma unroll
+                for (int i = 0; i < 16; ++i)
+                  if (i >= skip) {
+                    float y = v[i] + ca[i];
+                    s2 = fmaf(y, y, s2);
+                  }
+              }
+            } else {
+              for (int c = r0; c < r1; ++c) {
+                float y = tmem_ld1(tcol + c);
+                if (cadd) y += cadd[(long long)c * N];
+                s2 = fmaf(y, y, s2);
+              }
+            }
+          }
+          // ---- pass 2 (or the only pass of a linear layer): emit rows [r0, r1)
+          if (r1 - r0 >= 16) {
+            for (int c0 = r0; c0 < r1; c0 += 16) {
+              int cs = c0, skip = 0;
+              if (c0 + 16 > r1) {
+                cs = r1 - 16;
+                skip = c0 - cs;
+              }
+              float v[16], ca[16], rr[16];
+              tmem_ld16_nowait(tcol + cs, v);
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                ca[i] = cadd ? cadd[(long long)(cs + i) * N] : 0.f;
+                rr[i] = (res && res_mode) ? res[(long long)(cs + i) * N] : 0.f;
+              }
+              tmem_wait_ld();
+              if (f_ok) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i)
+                  if (i >= skip) {
+                    float y = (v[i] + ca[i]) * d1;
+                    if (p.act == 0 && cs + i == 0) y += bias_f;
+                    if (res_mode == 1) y = (rr[i] + y) * inv_sqrt2;
+                    else if (res_mode == 2) y = rr[i] + y;
+                    out[(long long)(cs + i) * N] = y;
+                  }
+              }
             }
           } else {
-            float x = tmem_ld1(tcol);
-            if (cadd && f_ok) x += cadd[0];
-            x += bias_f;
-            float th = tanhf(x);
-            float d1 = 1.0f - th * th;
-            float s2 = 0.f;
-            const int nj = C - 2;
-            for (int c0 = 0; c0 < nj; c0 += 8) {
-              float v[8];
-              int nc = (nj - c0 < 8) ? nj - c0 : 8;
-              if (nc == 8) {
-                tmem_ld8(tcol + 1 + c0, v);
-              } else {
-                for (int i = 0; i < nc; ++i) v[i] = tmem_ld1(tcol + 1 + c0 + i);
-              }
-              if (f_ok)
-                for (int i = 0; i < nc; ++i) {
-                  long long c = 1 + c0 + i;
-                  float y = v[i];
-                  if (cadd) y += cadd[c * p.N_out];
-                  s2 = fmaf(y, y, s2);
-                  float o = d1 * y;
-                  if (p.res_mode == 1) o = (res[c * p.N_out] + o) * inv_sqrt2;
-                  else if (p.res_mode == 2) o = res[c * p.N_out] + o;
-                  out[c * p.N_out] = o;
-                }
-            }
-            if (C > 1) {
-              float yl = tmem_ld1(tcol + C - 1);
+            for (int c = r0; c < r1; ++c) {
+              float y = tmem_ld1(tcol + c);
               if (f_ok) {
-                long long c = C - 1;
-                if (cadd) yl += cadd[c * p.N_out];
-                float l = d1 * yl - 2.0f * th * d1 * s2;
-                if (p.res_mode == 1) l = (res[c * p.N_out] + l) * inv_sqrt2;
-                else if (p.res_mode == 2) l = res[c * p.N_out] + l;
-                out[c * p.N_out] = l;
+                if (cadd) y += cadd[(long long)c * N];
+                y *= d1;
+                if (p.act == 0 && c == 0) y += bias_f;
+                if (res_mode == 1) y = (res[(long long)c * N] + y) * inv_sqrt2;
+                else if (res_mode == 2) y = res[(long long)c * N] + y;
+                out[(long long)c * N] = y;
               }
             }
+          }
+          if (p.act == 1) {
+            float yl = (C > 1) ? tmem_ld1(tcol + C - 1) : 0.f;
             if (f_ok) {
+              if (C > 1) {
+                long long c = C - 1;
+                if (cadd) yl += cadd[c * N];
+                float l = d1 * yl - 2.0f * th * d1 * s2;
+                if (res_mode == 1) l = (res[c * N] + l) * inv_sqrt2;
+                else if (res_mode == 2) l = res[c * N] + l;
+                out[c * N] = l;
+              }
               float o = th;
-              if (p.res_mode == 1) o = (res[0] + th) * inv_sqrt2;
-              else if (p.res_mode == 2) o = res[0] + th;
+              if (res_mode == 1) o = (res[0] + th) * inv_sqrt2;
+              else if (res_mode == 2) o = res[0] + th;
               out[0] = o;
             }
           }
@@ -374,8 +426,7 @@ k_dense_tc(const __grid_constant__ CUtensorMap mapX0, const __grid_constant__ CU
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(acc_empty);
-      acc_phase ^= 1;
+      if (lane == 0) mbar_arrive(&acc_empty[buf]);
     }
   }
 
@@ -446,7 +497,7 @@ bool jq_dense_tc_eligible(const JqDenseArgs& a) {
   if (disabled) return false;
   if (a.C > TC_NMAX) return false;
   if (a.k0 % TC_BK || a.k1 % TC_BK) return false;
-  if (a.k0 + a.k1 < 64) return false;
+  if (a.k0 + a.k1 < 32) return false;
   if (a.N < 64 || a.N > 2 * TC_MBLK) return false;
   if (!a.wscratch) return false;
   if ((reinterpret_cast<uintptr_t>(a.src0) & 15) || (a.src1 && (reinterpret_cast<uintptr_t>(a.src1) & 15))) return false;

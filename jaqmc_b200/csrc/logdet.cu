@@ -78,179 +78,224 @@ int jq_launch_orb_envelope(float* orb, const float* electrons, const float* atom
 }
 
 // ------------------------------------------------------------------------------------------------
-// slogdet + forward-Laplacian rule.  One block per (walker, determinant).
-// Shared memory: inv[n*n] | colp[n] | piv[n] | scal[8] | t2[KT] | Jc[KC*n*n] | Mc[KC*n*n] | p1[KC*n] | p2[KC*n]
+// slogdet + forward-Laplacian rule.  One block per (walker, group of DB determinants): a walker's orbital slab
+// [n][C][D*n] is read in rows of DB*n contiguous floats, and all DB matrices go through every phase together.
 // In-place Gauss-Jordan with partial (row) pivoting; sign = prod sign(pivot) * (-1)^swaps,
-// log|det| = sum log|pivot| (accumulated in double by the single pivot-search item).
+// log|det| = sum log|pivot| accumulated in double.  Then, KC derivative slabs at a time,
+//   M = A^-1 dA_c,  ld_J[c] = tr M,  and  ld_L = tr(A^-1 A_L) - sum_k tr(M_k^2)      (primitives/slogdet.py:46-72).
+// Shared: inv[DB][nn] | colp[DB][n] | piv[DB][n] | pivinv[DB] sgn[DB] trL[DB] t2[DB] | logabs[DB] (double) |
+//         Jc[KC][DB][nn] | Mc[KC][DB][nn] | p1[KC][DB][n] | p2[KC][DB][n]
 // ------------------------------------------------------------------------------------------------
-__global__ void k_logdet(const float* __restrict__ orb, int n, int D, int C, int KC, float* __restrict__ det_sign,
-                         float* __restrict__ det_logabs, float* __restrict__ det_grad, float* __restrict__ det_lap) {
+__global__ void k_logdet(const float* __restrict__ orb, int n, int D, int C, int DB, int KC,
+                         float* __restrict__ det_sign, float* __restrict__ det_logabs, float* __restrict__ det_grad,
+                         float* __restrict__ det_lap) {
   JQ_DYN_SMEM(float, sm);
   const int nn = n * n;
-  const int K = C - 2;           // Jacobian columns (C == 1: value only)
+  const int K = C - 2;                 // Jacobian columns (C == 1: value only)
   const int KT = (C > 1) ? C - 1 : 0;  // J columns + the Laplacian row
-  float* inv = sm;
-  float* colp = inv + nn;
-  int* piv = reinterpret_cast<int*>(colp + n);
-  float* scal = reinterpret_cast<float*>(piv + n);  // [0] pivinv, [1] sign, [2] logabs, [3] trL
-  float* t2 = scal + 8;
-  float* Jc = t2 + (KT > 0 ? KT : 1);
-  float* Mc = Jc + (long long)KC * nn;
-  float* p1 = Mc + (long long)KC * nn;
-  float* p2 = p1 + KC * n;
-  const long long b = blockIdx.x;
-  const long long w = b / D;
-  const int d = (int)(b % D);
+  double* logabs = reinterpret_cast<double*>(sm);  // first, for 8-byte alignment
+  float* inv = reinterpret_cast<float*>(logabs + DB);
+  float* colp = inv + (size_t)DB * nn;
+  int* piv = reinterpret_cast<int*>(colp + DB * n);
+  float* pivinv = reinterpret_cast<float*>(piv + DB * n);
+  float* sgn = pivinv + DB;
+  float* trL = sgn + DB;
+  float* t2 = trL + DB;
+  float* Jc = t2 + DB;
+  float* Mc = Jc + (size_t)KC * DB * nn;
+  float* p1 = Mc + (size_t)KC * DB * nn;
+  float* p2 = p1 + KC * DB * n;
+  const int ngrp = (D + DB - 1) / DB;
+  const long long w = blockIdx.x / ngrp;
+  const int d0 = (int)(blockIdx.x % ngrp) * DB;
+  const int db = (D - d0 < DB) ? D - d0 : DB;  // determinants in this block
   const int DN = D * n;
   const int tid = threadIdx.x, nt = blockDim.x;
   const bool need_inv = (C > 1);
+  const float* ow = orb + (w * n) * (long long)C * DN + d0 * n;  // (j, c, d, i) at ow[(j*C + c)*DN + d*n + i]
 
-  // load A[j][i] (value rows)
-  for (int q = tid; q < nn; q += nt) {
-    int j = q / n, i = q % n;
-    inv[q] = orb[((w * n + j) * (long long)C) * DN + d * n + i];
+  // value slab: inv[d][j][i] = A_d[j][i]; consecutive items read db*n contiguous floats
+  for (int q = tid; q < n * db * n; q += nt) {
+    int j = q / (db * n), r = q % (db * n);
+    int d = r / n, i = r % n;
+    inv[d * nn + j * n + i] = ow[(long long)j * C * DN + r];
+  }
+  for (int d = tid; d < db; d += nt) {
+    logabs[d] = 0.0;
+    sgn[d] = 1.0f;
+    t2[d] = 0.f;
+    trL[d] = 0.f;
   }
   __syncthreads();
-  double logabs = 0.0;  // only meaningful in the item that runs the pivot search (tid 0)
-  float sgn = 1.0f;
   for (int p = 0; p < n; ++p) {
-    if (tid == 0) {
+    for (int d = tid; d < db; d += nt) {
+      const float* a = inv + d * nn;
       int r = p;
-      float best = fabsf(inv[p * n + p]);
+      float best = fabsf(a[p * n + p]);
       for (int q = p + 1; q < n; ++q) {
-        float v = fabsf(inv[q * n + p]);
+        float v = fabsf(a[q * n + p]);
         if (v > best) { best = v; r = q; }
       }
-      piv[p] = r;
-      float pv = inv[r * n + p];
-      if (r != p) sgn = -sgn;
-      if (pv < 0.f) sgn = -sgn;
-      if (pv == 0.f) sgn = 0.f;
-      logabs += log((double)fabsf(pv));
-      scal[0] = 1.0f / pv;
+      piv[d * n + p] = r;
+      float pv = a[r * n + p];
+      float s = sgn[d];
+      if (r != p) s = -s;
+      if (pv < 0.f) s = -s;
+      if (pv == 0.f) s = 0.f;
+      sgn[d] = s;
+      logabs[d] += log((double)fabsf(pv));
+      pivinv[d] = 1.0f / pv;
     }
     __syncthreads();
-    {
-      int r = piv[p];
-      if (r != p)
-        for (int c = tid; c < n; c += nt) {
-          float t = inv[p * n + c];
-          inv[p * n + c] = inv[r * n + c];
-          inv[r * n + c] = t;
-        }
+    for (int q = tid; q < db * n; q += nt) {
+      int d = q / n, c = q % n;
+      int r = piv[d * n + p];
+      float* a = inv + d * nn;
+      if (r != p) {
+        float t = a[p * n + c];
+        a[p * n + c] = a[r * n + c];
+        a[r * n + c] = t;
+      }
     }
     __syncthreads();
-    float pivinv = scal[0];
     if (need_inv) {
-      for (int q = tid; q < n; q += nt) colp[q] = inv[q * n + p];  // column p before it is overwritten
+      for (int q = tid; q < db * n; q += nt) {
+        int d = q / n, i = q % n;
+        colp[q] = inv[d * nn + i * n + p];  // column p before it is overwritten
+      }
       __syncthreads();
-      for (int c = tid; c < n; c += nt) inv[p * n + c] = ((c == p) ? 1.0f : inv[p * n + c]) * pivinv;
+      for (int q = tid; q < db * n; q += nt) {
+        int d = q / n, c = q % n;
+        float* a = inv + d * nn;
+        a[p * n + c] = ((c == p) ? 1.0f : a[p * n + c]) * pivinv[d];
+      }
       __syncthreads();
-      for (int q = tid; q < nn; q += nt) {
-        int i = q / n, c = q % n;
+      for (int q = tid; q < db * nn; q += nt) {
+        int d = q / nn, rem = q % nn;
+        int i = rem / n, c = rem % n;
         if (i == p) continue;
-        float base = (c == p) ? 0.f : inv[q];
-        inv[q] = fmaf(-colp[i], inv[p * n + c], base);
+        float* a = inv + d * nn;
+        float base = (c == p) ? 0.f : a[rem];
+        a[rem] = fmaf(-colp[d * n + i], a[p * n + c], base);
       }
       __syncthreads();
     } else {
       // value only: eliminate below the pivot (LU), no inverse needed
-      for (int q = tid; q < n; q += nt) colp[q] = inv[q * n + p] * pivinv;
+      for (int q = tid; q < db * n; q += nt) {
+        int d = q / n, i = q % n;
+        colp[q] = inv[d * nn + i * n + p] * pivinv[d];
+      }
       __syncthreads();
-      for (int q = tid; q < nn; q += nt) {
-        int i = q / n, c = q % n;
+      for (int q = tid; q < db * nn; q += nt) {
+        int d = q / nn, rem = q % nn;
+        int i = rem / n, c = rem % n;
         if (i <= p || c <= p) continue;
-        inv[q] = fmaf(-colp[i], inv[p * n + c], inv[q]);
+        float* a = inv + d * nn;
+        a[rem] = fmaf(-colp[d * n + i], a[p * n + c], a[rem]);
       }
       __syncthreads();
     }
   }
-  if (tid == 0) {
-    det_sign[b] = sgn;
-    det_logabs[b] = (float)logabs;
+  for (int d = tid; d < db; d += nt) {
+    det_sign[w * D + d0 + d] = sgn[d];
+    det_logabs[w * D + d0 + d] = (float)logabs[d];
   }
   if (!need_inv) return;
   // undo the row swaps as column swaps, in reverse order
   for (int p = n - 1; p >= 0; --p) {
-    int r = piv[p];
-    if (r != p) {
-      for (int q = tid; q < n; q += nt) {
-        float t = inv[q * n + p];
-        inv[q * n + p] = inv[q * n + r];
-        inv[q * n + r] = t;
+    for (int q = tid; q < db * n; q += nt) {
+      int d = q / n, i = q % n;
+      int r = piv[d * n + p];
+      if (r != p) {
+        float* a = inv + d * nn;
+        float t = a[i * n + p];
+        a[i * n + p] = a[i * n + r];
+        a[i * n + r] = t;
       }
     }
     __syncthreads();
   }
-  // traces, KC derivative slabs at a time.  slab kk <-> component c = 1 + kk (kk == K is the Laplacian row)
+  // traces, KC derivative slabs at a time.  slab kk <-> component c = 1 + k0 + kk (k0 + kk == K is the Laplacian row)
   for (int k0 = 0; k0 < KT; k0 += KC) {
-    int kc = (KT - k0 < KC) ? KT - k0 : KC;
-    for (int q = tid; q < kc * nn; q += nt) {
-      int kk = q / nn, rem = q % nn;
-      int j = rem / n, i = rem % n;
-      Jc[q] = orb[((w * n + j) * (long long)C + (1 + k0 + kk)) * DN + d * n + i];
+    const int kc = (KT - k0 < KC) ? KT - k0 : KC;
+    for (int q = tid; q < kc * n * db * n; q += nt) {
+      int r = q % (db * n);
+      int t = q / (db * n);
+      int j = t % n, kk = t / n;
+      int d = r / n, i = r % n;
+      Jc[(kk * DB + d) * nn + j * n + i] = ow[((long long)j * C + (1 + k0 + kk)) * DN + r];
     }
     __syncthreads();
-    for (int q = tid; q < kc * nn; q += nt) {
-      int kk = q / nn, rem = q % nn;
+    for (int q = tid; q < kc * db * nn; q += nt) {
+      int rem = q % nn;
+      int t = q / nn;
+      int d = t % db, kk = t / db;
       int i = rem / n, i2 = rem % n;
-      const float* jp = Jc + kk * nn + i2;
-      const float* ip = inv + i * n;
+      const float* jp = Jc + (kk * DB + d) * nn + i2;
+      const float* ip = inv + d * nn + i * n;
       float acc = 0.f;
       for (int j = 0; j < n; ++j) acc = fmaf(ip[j], jp[j * n], acc);
-      Mc[q] = acc;
+      Mc[(kk * DB + d) * nn + rem] = acc;
     }
     __syncthreads();
-    for (int q = tid; q < kc * n; q += nt) {
-      int kk = q / n, i = q % n;
-      const float* m = Mc + kk * nn;
+    for (int q = tid; q < kc * db * n; q += nt) {
+      int i = q % n;
+      int t = q / n;
+      int d = t % db, kk = t / db;
+      const float* m = Mc + (kk * DB + d) * nn;
       float acc = 0.f;
       for (int i2 = 0; i2 < n; ++i2) acc = fmaf(m[i * n + i2], m[i2 * n + i], acc);
-      p1[q] = m[i * n + i];
-      p2[q] = acc;
+      p1[(kk * DB + d) * n + i] = m[i * n + i];
+      p2[(kk * DB + d) * n + i] = acc;
     }
     __syncthreads();
-    for (int kk = tid; kk < kc; kk += nt) {
+    for (int q = tid; q < kc * db; q += nt) {
+      int d = q % db, kk = q / db;
       float s1 = 0.f, s2 = 0.f;
       for (int i = 0; i < n; ++i) {
-        s1 += p1[kk * n + i];
-        s2 += p2[kk * n + i];
+        s1 += p1[(kk * DB + d) * n + i];
+        s2 += p2[(kk * DB + d) * n + i];
       }
       int k = k0 + kk;
       if (k < K) {
-        det_grad[b * K + k] = s1;
-        t2[k] = s2;
+        det_grad[(w * D + d0 + d) * K + k] = s1;
+        p2[(kk * DB + d) * n] = s2;  // parked for the serial accumulation below
       } else {
-        scal[3] = s1;
+        trL[d] = s1;
       }
     }
     __syncthreads();
+    for (int d = tid; d < db; d += nt) {
+      float acc = t2[d];
+      for (int kk = 0; kk < kc; ++kk)
+        if (k0 + kk < K) acc += p2[(kk * DB + d) * n];
+      t2[d] = acc;
+    }
+    __syncthreads();
   }
-  if (tid == 0) {
-    float s = 0.f;
-    for (int k = 0; k < K; ++k) s += t2[k];
-    det_lap[b] = scal[3] - s;
-  }
-}
-
-static int logdet_kc(int n, int C) {
-  int KT = C > 1 ? C - 1 : 0;
-  if (KT == 0) return 1;
-  int kc = (64 * 1024 / 4 / 2) / (n * n);
-  if (kc < 1) kc = 1;
-  if (kc > KT) kc = KT;
-  return kc;
+  for (int d = tid; d < db; d += nt) det_lap[w * D + d0 + d] = trL[d] - t2[d];
 }
 
 int jq_launch_logdet(const float* orb, int W, int n, int D, int track, float* det_sign, float* det_logabs,
                      float* det_grad, float* det_lap, cudaStream_t st) {
-  long long blocks = (long long)W * D;
-  if (blocks <= 0) return JQ_OK;
-  int C = track ? 3 * n + 2 : 1;
-  int KC = logdet_kc(n, C);
-  int KT = C > 1 ? C - 1 : 0;
-  size_t smem = sizeof(float) * ((size_t)n * n + n + n + 8 + (KT > 0 ? KT : 1) +
-                                 (track ? (size_t)KC * n * n * 2 + (size_t)KC * n * 2 : 0));
+  if ((long long)W * D <= 0) return JQ_OK;
+  const int C = track ? 3 * n + 2 : 1;
+  const int KT = C > 1 ? C - 1 : 0;
+  const size_t nn = (size_t)n * n;
+  // DB matrices per block: about 16 KB of inverses; KC slabs so that the block stays under ~100 KB
+  int DB = (int)(16384 / (nn * 4));
+  if (DB < 1) DB = 1;
+  if (DB > D) DB = D;
+  int KC = 1;
+  auto smem_for = [&](int db, int kc) {
+    return (size_t)8 * db + sizeof(float) * ((size_t)db * nn + 2 * (size_t)db * n + 4 * (size_t)db +
+                                            (track ? (size_t)kc * db * nn * 2 + (size_t)kc * db * n * 2 : 0)) + 16;
+  };
+  if (track) {
+    while (KC < KT && smem_for(DB, KC + 1) <= 100 * 1024) ++KC;
+    while (DB > 1 && smem_for(DB, KC) > 200 * 1024) --DB;
+  }
+  size_t smem = smem_for(DB, KC);
   JQ_REQUIRE(smem <= 200 * 1024, JQ_ERR_UNSUPPORTED, "logdet: %d electrons need %zu bytes of shared memory", n, smem);
 #ifndef JAQMC_HOST_EMU
   if (smem > 48 * 1024) {
@@ -258,9 +303,9 @@ int jq_launch_logdet(const float* orb, int W, int n, int D, int track, float* de
     JQ_REQUIRE(e == cudaSuccess, JQ_ERR_CUDA, "logdet: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
   }
 #endif
-  int threads = track ? 256 : 64;
-  jq_prof_work((double)blocks * (2.0 * n * n * n * (track ? (C - 1) * 2 + 1 : 0.34)), 4.0 * (double)blocks * C * n * n);
-  JQ_LAUNCH(k_logdet, dim3((unsigned)blocks), dim3(threads), smem, st, orb, n, D, C, KC, det_sign, det_logabs,
+  const long long blocks = (long long)W * ((D + DB - 1) / DB);
+  jq_prof_work((double)W * D * (2.0 * n * n * n * (track ? (C - 1) * 2 + 1 : 0.34)), 4.0 * (double)W * D * C * n * n);
+  JQ_LAUNCH(k_logdet, dim3((unsigned)blocks), dim3(256), smem, st, orb, n, D, C, DB, KC, det_sign, det_logabs,
             det_grad, det_lap);
   JQ_CHECK_LAUNCH();
   return JQ_OK;

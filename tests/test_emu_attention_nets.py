@@ -57,7 +57,7 @@ def _check(rt, wf, sysh, el, atoms, charges, fn):
     out = {k: v.numpy() for k, v in rt.local_energy(wf, sysh, e32).items()}
     ref = H.oracle_batch(fn, el, atoms, charges, track=True)
     assert np.array_equal(out["sign"], ref["sign"])
-    H.assert_fp32_parity(out, ref, el, e_tol=2e-5, l_tol=2e-6)
+    H.assert_fp32_parity(out, ref, el)
     np.testing.assert_allclose(out["e_kin"], -0.5 * (out["lap"] + (out["grad"] ** 2).sum(-1)), rtol=1e-5, atol=1e-5)
     lp, sg = rt.logpsi(wf, sysh, e32)  # value-only path (the MCMC forward)
     assert np.array_equal(sg.numpy(), ref["sign"])
