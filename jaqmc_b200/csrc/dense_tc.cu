@@ -166,6 +166,147 @@ struct PipeState {
   }
 };
 
+// Epilogue of one CTA (all its tiles), specialised on the fused operations.  A thread owns output feature f (its
+// TMEM lane) and walks the tile's groups; a group's C columns are fetched in chunks of 16 (tcgen05.ld x16).  All
+// global addresses are a warp-uniform 64-bit base plus one 32-bit per-thread offset (row * N + f) shared by the
+// addend, the residual and the output, so a row costs one integer add.  The tanh rule takes two passes over the
+// (cheap to re-read) TMEM columns: pass 1 accumulates sum_k y_k^2, pass 2 emits the rows.
+template <int ACT, int RES, bool CADD>
+__device__ __forceinline__ void epilogue_loop(const TcParams& p, uint32_t tlane0, int f, bool f_ok, bool mb_ok,
+                                              uint64_t* acc_full, uint64_t* acc_empty, int lane) {
+  const float inv_sqrt2 = 0.70710678118654752440f;
+  const float bias_f = (p.bias && f_ok) ? p.bias[f] : 0.f;
+  const int C = p.C;
+  const uint32_t N = (uint32_t)p.N_out;
+  uint32_t it = 0;
+  for (long long t = blockIdx.x; t < p.tiles; t += gridDim.x, ++it) {
+    const uint32_t buf = it & 1, acc_phase = (it >> 1) & 1;
+    const uint32_t tbuf = tlane0 + buf * 2 * TC_NMAX;
+    const long long w_tma = t / p.tiles_per_w;
+    const int gsub0 = (int)(t % p.tiles_per_w) * p.G_t;
+    mbar_wait(&acc_full[buf], acc_phase);
+    tc_fence_after();
+    if (mb_ok) {
+      for (int gi = 0; gi < p.G_t; ++gi) {
+        const int gsub = gsub0 + gi;
+        if (gsub >= p.n_sub) break;  // warp-uniform
+        const long long g = w_tma * p.n_tot + p.j0 + gsub;   // actual group index
+        // warp-uniform bases; per-thread offset o = row * N + f
+        const float* __restrict__ cadd_b = CADD ? p.cadd + ((g / p.n_tot_true) * C) * (long long)N : nullptr;
+        const float* __restrict__ res_b = RES ? p.res + g * C * (long long)N : nullptr;
+        float* __restrict__ out_b = p.out + g * C * (long long)N;
+        const uint32_t tcol = tbuf + gi * C;
+        const uint32_t fo = f_ok ? (uint32_t)f : 0u;  // lanes beyond N_out read a valid column and never store
+        float th = 0.f, d1 = 1.f, s2 = 0.f;
+        int r0 = 0, r1 = C;
+        if (ACT == 1) {
+          float x = tmem_ld1(tcol);
+          if (CADD) x += cadd_b[fo];
+          x += bias_f;
+          th = tanhf(x);
+          d1 = 1.0f - th * th;
+          r0 = 1;
+          r1 = C - 1;  // Jacobian rows
+          if (r1 - r0 >= 16) {
+            for (int c0 = r0; c0 < r1; c0 += 16) {
+              int cs = c0, skip = 0;
+              if (c0 + 16 > r1) {  // last chunk: shifted back to stay inside the group's columns
+                cs = r1 - 16;
+                skip = c0 - cs;
+              }
+              float v[16], ca[16];
+              tmem_ld16_nowait(tcol + cs, v);
+              if (CADD) {
+                uint32_t o = (uint32_t)cs * N + fo;
+#pragma unroll
+                for (int i = 0; i < 16; ++i, o += N) ca[i] = cadd_b[o];
+              }
+              tmem_wait_ld();
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                float y = CADD ? v[i] + ca[i] : v[i];
+                if (i >= skip) s2 = fmaf(y, y, s2);
+              }
+            }
+          } else {
+            for (int c = r0; c < r1; ++c) {
+              float y = tmem_ld1(tcol + c);
+              if (CADD) y += cadd_b[(uint32_t)c * N + fo];
+              s2 = fmaf(y, y, s2);
+            }
+          }
+        }
+        // pass 2 (or the only pass of a linear layer): emit rows [r0, r1)
+        if (r1 - r0 >= 16) {
+          for (int c0 = r0; c0 < r1; c0 += 16) {
+            int cs = c0, skip = 0;
+            if (c0 + 16 > r1) {
+              cs = r1 - 16;
+              skip = c0 - cs;
+            }
+            float v[16], ca[16], rr[16];
+            tmem_ld16_nowait(tcol + cs, v);
+            {
+              uint32_t o = (uint32_t)cs * N + fo;
+#pragma unroll
+              for (int i = 0; i < 16; ++i, o += N) {
+                if (CADD) ca[i] = cadd_b[o];
+                if (RES) rr[i] = res_b[o];
+              }
+            }
+            tmem_wait_ld();
+            if (f_ok) {
+              uint32_t o = (uint32_t)cs * N + fo;
+#pragma unroll
+              for (int i = 0; i < 16; ++i, o += N) {
+                float y = CADD ? v[i] + ca[i] : v[i];
+                if (ACT == 1) y *= d1;
+                if (ACT == 0 && cs + i == 0) y += bias_f;
+                if (RES == 1) y = (rr[i] + y) * inv_sqrt2;
+                if (RES == 2) y = rr[i] + y;
+                if (i >= skip) out_b[o] = y;
+              }
+            }
+          }
+        } else {
+          for (int c = r0; c < r1; ++c) {
+            float y = tmem_ld1(tcol + c);
+            const uint32_t o = (uint32_t)c * N + fo;
+            if (f_ok) {
+              if (CADD) y += cadd_b[o];
+              if (ACT == 1) y *= d1;
+              if (ACT == 0 && c == 0) y += bias_f;
+              if (RES == 1) y = (res_b[o] + y) * inv_sqrt2;
+              if (RES == 2) y = res_b[o] + y;
+              out_b[o] = y;
+            }
+          }
+        }
+        if (ACT == 1) {
+          float yl = (C > 1) ? tmem_ld1(tcol + C - 1) : 0.f;
+          if (f_ok) {
+            if (C > 1) {
+              const uint32_t o = (uint32_t)(C - 1) * N + fo;
+              if (CADD) yl += cadd_b[o];
+              float l = d1 * yl - 2.0f * th * d1 * s2;
+              if (RES == 1) l = (res_b[o] + l) * inv_sqrt2;
+              if (RES == 2) l = res_b[o] + l;
+              out_b[o] = l;
+            }
+            float o0 = th;
+            if (RES == 1) o0 = (res_b[fo] + th) * inv_sqrt2;
+            if (RES == 2) o0 = res_b[fo] + th;
+            out_b[fo] = o0;
+          }
+        }
+      }
+    }
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&acc_empty[buf]);
+  }
+}
+
 __global__ void __launch_bounds__(TC_THREADS, 1)
 k_dense_tc(const __grid_constant__ CUtensorMap mapX0, const __grid_constant__ CUtensorMap mapX1,
            const __grid_constant__ CUtensorMap mapWh, const __grid_constant__ CUtensorMap mapWl, TcParams p) {
@@ -293,141 +434,29 @@ k_dense_tc(const __grid_constant__ CUtensorMap mapX0, const __grid_constant__ CU
     }
   } else if (warp >= 8) {
     // ===================== epilogue =====================
-    // A thread owns output feature f (TMEM lane) and walks the tile's groups; a group's C columns are fetched in
-    // chunks of 16 (tcgen05.ld x16), the matching addend / residual rows are loaded as 16 independent coalesced
-    // requests before any store is issued, and the tanh rule takes two passes over the (cheap to re-read) columns:
-    // pass 1 accumulates sum_k y_k^2, pass 2 emits the rows.
     const int q = warp & 3;            // TMEM lane quarter this warp may access
     const int mb = (warp - 8) >> 2;    // feature block
+    const uint32_t tlane0 = tmem_base + ((uint32_t)(q * 32) << 16) + mb * TC_NMAX;
     const int f = mb * TC_MBLK + q * 32 + lane;
     const bool f_ok = (mb < p.mblocks) && (f < p.N_out);
-    const float inv_sqrt2 = 0.70710678118654752440f;
-    const float bias_f = (p.bias && f_ok) ? p.bias[f] : 0.f;
-    const int C = p.C;
-    const long long N = p.N_out;
-    const int res_mode = p.res_mode;
-    uint32_t it = 0;
-    for (long long t = blockIdx.x; t < p.tiles; t += gridDim.x, ++it) {
-      const uint32_t buf = it & 1, acc_phase = (it >> 1) & 1;
-      const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16) + (buf * 2 + mb) * TC_NMAX;
-      long long w_tma = t / p.tiles_per_w;
-      int gsub0 = (int)(t % p.tiles_per_w) * p.G_t;
-      mbar_wait(&acc_full[buf], acc_phase);
-      tc_fence_after();
-      if (mb < p.mblocks) {
-        for (int gi = 0; gi < p.G_t; ++gi) {
-          int gsub = gsub0 + gi;
-          if (gsub >= p.n_sub) break;  // warp-uniform
-          long long g = w_tma * p.n_tot + p.j0 + gsub;       // actual group index
-          long long orow = g * C;                              // first output row of the group
-          const float* __restrict__ cadd = (p.cadd && f_ok) ? p.cadd + ((g / p.n_tot_true) * C) * N + f : nullptr;
-          const float* __restrict__ res = (p.res && f_ok) ? p.res + orow * N + f : nullptr;
-          float* __restrict__ out = p.out + orow * N + f;
-          const uint32_t tcol = tlane + gi * C;
-          // rows [r0, r1) of the group in chunks of 16 columns; the last chunk is shifted back to stay inside the
-          // group's columns (needs r1 - r0 >= 16; shorter ranges go column by column)
-          float th = 0.f, d1 = 1.f, s2 = 0.f;
-          int r0 = 0, r1 = C;
-          if (p.act == 1) {
-            float x = tmem_ld1(tcol);
-            if (cadd) x += cadd[0];
-            x += bias_f;
-            th = tanhf(x);
-            d1 = 1.0f - th * th;
-            r0 = 1;
-            r1 = C - 1;  // Jacobian rows
-            // ---- pass 1: s2 = sum_k y_k^2
-            if (r1 - r0 >= 16) {
-              for (int c0 = r0; c0 < r1; c0 += 16) {
-                int cs = c0, skip = 0;
-                if (c0 + 16 > r1) {
-                  cs = r1 - 16;
-                  skip = c0 - cs;
-                }
-                float v[16], ca[16];
-                tmem_ld16_nowait(tcol + cs, v);
-#pragma unroll
-                for (int i = 0; i < 16; ++i) ca[i] = cadd ? cadd[(long long)(cs + i) * N] : 0.f;
-                tmem_wait_ld();
-#pragma unroll
-                for (int i = 0; i < 16; ++i)
-                  if (i >= skip) {
-                    float y = v[i] + ca[i];
-                    s2 = fmaf(y, y, s2);
-                  }
-              }
-            } else {
-              for (int c = r0; c < r1; ++c) {
-                float y = tmem_ld1(tcol + c);
-                if (cadd) y += cadd[(long long)c * N];
-                s2 = fmaf(y, y, s2);
-              }
-            }
-          }
-          // ---- pass 2 (or the only pass of a linear layer): emit rows [r0, r1)
-          if (r1 - r0 >= 16) {
-            for (int c0 = r0; c0 < r1; c0 += 16) {
-              int cs = c0, skip = 0;
-              if (c0 + 16 > r1) {
-                cs = r1 - 16;
-                skip = c0 - cs;
-              }
-              float v[16], ca[16], rr[16];
-              tmem_ld16_nowait(tcol + cs, v);
-#pragma unroll
-              for (int i = 0; i < 16; ++i) {
-                ca[i] = cadd ? cadd[(long long)(cs + i) * N] : 0.f;
-                rr[i] = (res && res_mode) ? res[(long long)(cs + i) * N] : 0.f;
-              }
-              tmem_wait_ld();
-              if (f_ok) {
-#pragma unroll
-                for (int i = 0; i < 16; ++i)
-                  if (i >= skip) {
-                    float y = (v[i] + ca[i]) * d1;
-                    if (p.act == 0 && cs + i == 0) y += bias_f;
-                    if (res_mode == 1) y = (rr[i] + y) * inv_sqrt2;
-                    else if (res_mode == 2) y = rr[i] + y;
-                    out[(long long)(cs + i) * N] = y;
-                  }
-              }
-            }
-          } else {
-            for (int c = r0; c < r1; ++c) {
-              float y = tmem_ld1(tcol + c);
-              if (f_ok) {
-                if (cadd) y += cadd[(long long)c * N];
-                y *= d1;
-                if (p.act == 0 && c == 0) y += bias_f;
-                if (res_mode == 1) y = (res[(long long)c * N] + y) * inv_sqrt2;
-                else if (res_mode == 2) y = res[(long long)c * N] + y;
-                out[(long long)c * N] = y;
-              }
-            }
-          }
-          if (p.act == 1) {
-            float yl = (C > 1) ? tmem_ld1(tcol + C - 1) : 0.f;
-            if (f_ok) {
-              if (C > 1) {
-                long long c = C - 1;
-                if (cadd) yl += cadd[c * N];
-                float l = d1 * yl - 2.0f * th * d1 * s2;
-                if (res_mode == 1) l = (res[c * N] + l) * inv_sqrt2;
-                else if (res_mode == 2) l = res[c * N] + l;
-                out[c * N] = l;
-              }
-              float o = th;
-              if (res_mode == 1) o = (res[0] + th) * inv_sqrt2;
-              else if (res_mode == 2) o = res[0] + th;
-              out[0] = o;
-            }
-          }
-        }
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&acc_empty[buf]);
+    // one instantiation per (activation, residual mode, addend) combination: no per-element predicates
+#define TC_EPI(ACT, RES, CADD) epilogue_loop<ACT, RES, CADD>(p, tlane0, f, f_ok, mb < p.mblocks, acc_full, acc_empty, lane)
+    const int key = (p.act ? 8 : 0) | (p.res_mode << 1) | (p.cadd ? 1 : 0);
+    switch (key) {
+      case 0: TC_EPI(0, 0, false); break;
+      case 1: TC_EPI(0, 0, true); break;
+      case 2: TC_EPI(0, 1, false); break;
+      case 3: TC_EPI(0, 1, true); break;
+      case 4: TC_EPI(0, 2, false); break;
+      case 5: TC_EPI(0, 2, true); break;
+      case 8: TC_EPI(1, 0, false); break;
+      case 9: TC_EPI(1, 0, true); break;
+      case 10: TC_EPI(1, 1, false); break;
+      case 11: TC_EPI(1, 1, true); break;
+      case 12: TC_EPI(1, 2, false); break;
+      default: TC_EPI(1, 2, true); break;
     }
+#undef TC_EPI
   }
 
   tc_fence_before();

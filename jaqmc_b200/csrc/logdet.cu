@@ -11,6 +11,22 @@
 //   * E_kin = -1/2 (lap + |grad|^2)                                estimator/kinetic/_common.py:61-73
 #include "aug.cuh"
 
+// q / d and q % d for block-uniform runtime d without the ~20-instruction integer division sequence
+// (inv = 1.0f / d; exact after the one-step correction for q < 2^23).
+__device__ __forceinline__ void jq_divmod(int q, int d, float inv, int* quo, int* rem) {
+  int a = (int)((float)q * inv);
+  int r = q - a * d;
+  if (r >= d) {
+    r -= d;
+    ++a;
+  } else if (r < 0) {
+    r += d;
+    --a;
+  }
+  *quo = a;
+  *rem = r;
+}
+
 // ------------------------------------------------------------------------------------------------
 // orb[w][j][c][d*n+i] *= envelope(j, i, d)   (in place, product rule).  One item per (w, j, d, i).
 // ------------------------------------------------------------------------------------------------
@@ -112,12 +128,17 @@ __global__ void k_logdet(const float* __restrict__ orb, int n, int D, int C, int
   const int DN = D * n;
   const int tid = threadIdx.x, nt = blockDim.x;
   const bool need_inv = (C > 1);
+  const int TX = (nt >= 64) ? 8 : 1, TY = nt / TX;
+  const int tx = tid % TX, ty = tid / TX;
+  const float inv_n = 1.0f / (float)n, inv_nn = 1.0f / (float)nn, inv_db = 1.0f / (float)db,
+              inv_dbn = 1.0f / (float)(db * n);
   const float* ow = orb + (w * n) * (long long)C * DN + d0 * n;  // (j, c, d, i) at ow[(j*C + c)*DN + d*n + i]
 
   // value slab: inv[d][j][i] = A_d[j][i]; consecutive items read db*n contiguous floats
   for (int q = tid; q < n * db * n; q += nt) {
-    int j = q / (db * n), r = q % (db * n);
-    int d = r / n, i = r % n;
+    int j, r, d, i;
+    jq_divmod(q, db * n, inv_dbn, &j, &r);
+    jq_divmod(r, n, inv_n, &d, &i);
     inv[d * nn + j * n + i] = ow[(long long)j * C * DN + r];
   }
   for (int d = tid; d < db; d += nt) {
@@ -171,8 +192,9 @@ __global__ void k_logdet(const float* __restrict__ orb, int n, int D, int C, int
       }
       __syncthreads();
       for (int q = tid; q < db * nn; q += nt) {
-        int d = q / nn, rem = q % nn;
-        int i = rem / n, c = rem % n;
+        int d, rem, i, c;
+        jq_divmod(q, nn, inv_nn, &d, &rem);
+        jq_divmod(rem, n, inv_n, &i, &c);
         if (i == p) continue;
         float* a = inv + d * nn;
         float base = (c == p) ? 0.f : a[rem];
@@ -187,8 +209,9 @@ __global__ void k_logdet(const float* __restrict__ orb, int n, int D, int C, int
       }
       __syncthreads();
       for (int q = tid; q < db * nn; q += nt) {
-        int d = q / nn, rem = q % nn;
-        int i = rem / n, c = rem % n;
+        int d, rem, i, c;
+        jq_divmod(q, nn, inv_nn, &d, &rem);
+        jq_divmod(rem, n, inv_n, &i, &c);
         if (i <= p || c <= p) continue;
         float* a = inv + d * nn;
         a[rem] = fmaf(-colp[d * n + i], a[p * n + c], a[rem]);
@@ -219,29 +242,40 @@ __global__ void k_logdet(const float* __restrict__ orb, int n, int D, int C, int
   for (int k0 = 0; k0 < KT; k0 += KC) {
     const int kc = (KT - k0 < KC) ? KT - k0 : KC;
     for (int q = tid; q < kc * n * db * n; q += nt) {
-      int r = q % (db * n);
-      int t = q / (db * n);
-      int j = t % n, kk = t / n;
-      int d = r / n, i = r % n;
+      int t, r, kk, j, d, i;
+      jq_divmod(q, db * n, inv_dbn, &t, &r);
+      jq_divmod(t, n, inv_n, &kk, &j);
+      jq_divmod(r, n, inv_n, &d, &i);
       Jc[(kk * DB + d) * nn + j * n + i] = ow[((long long)j * C + (1 + k0 + kk)) * DN + r];
     }
     __syncthreads();
-    for (int q = tid; q < kc * db * nn; q += nt) {
-      int rem = q % nn;
-      int t = q / nn;
-      int d = t % db, kk = t / db;
-      int i = rem / n, i2 = rem % n;
-      const float* jp = Jc + (kk * DB + d) * nn + i2;
+    // M = inv . J: thread (ty, tx) walks rows r = (kk, d, i) by TY and columns i2 by TX; a 1 x 2 register tile per step
+    for (int r = ty; r < kc * db * n; r += TY) {
+      int t, i, kk, d;
+      jq_divmod(r, n, inv_n, &t, &i);
+      jq_divmod(t, db, inv_db, &kk, &d);
       const float* ip = inv + d * nn + i * n;
-      float acc = 0.f;
-      for (int j = 0; j < n; ++j) acc = fmaf(ip[j], jp[j * n], acc);
-      Mc[(kk * DB + d) * nn + rem] = acc;
+      const float* jb = Jc + (kk * DB + d) * nn;
+      float* mrow = Mc + (kk * DB + d) * nn + i * n;
+      for (int i2 = tx; i2 < n; i2 += 2 * TX) {
+        const int i3 = i2 + TX;
+        const bool two = i3 < n;
+        const float* jp = jb + i2;
+        float a0 = 0.f, a1 = 0.f;
+        for (int j = 0; j < n; ++j) {
+          const float iv = ip[j];
+          a0 = fmaf(iv, jp[j * n], a0);
+          if (two) a1 = fmaf(iv, jp[j * n + TX], a1);
+        }
+        mrow[i2] = a0;
+        if (two) mrow[i3] = a1;
+      }
     }
     __syncthreads();
     for (int q = tid; q < kc * db * n; q += nt) {
-      int i = q % n;
-      int t = q / n;
-      int d = t % db, kk = t / db;
+      int t, i, kk, d;
+      jq_divmod(q, n, inv_n, &t, &i);
+      jq_divmod(t, db, inv_db, &kk, &d);
       const float* m = Mc + (kk * DB + d) * nn;
       float acc = 0.f;
       for (int i2 = 0; i2 < n; ++i2) acc = fmaf(m[i * n + i2], m[i2 * n + i], acc);

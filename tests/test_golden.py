@@ -60,4 +60,5 @@ def test_cuda_matches_golden(name):
     el = torch.from_numpy(z["electrons"]).to(dev)
     out = {k: v.cpu().numpy() for k, v in rt.local_energy(wf, sysh, el).items()}
     assert np.array_equal(out["sign"], ref["sign"])
-    H.assert_fp32_parity(out, ref, z["electrons"])
+    wide = kind != "ferminet" and kw["heads"] * kw["heads_dim"] >= 64  # tensor-core path, see test_gpu_attention_nets
+    H.assert_fp32_parity(out, ref, z["electrons"], l_tol=4e-6 if wide else 1e-6)
