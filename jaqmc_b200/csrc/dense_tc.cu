@@ -15,11 +15,23 @@
 // produced in shared memory by a converter warpgroup from the raw FP32 tile that TMA landed, so activations cross
 // L2->SMEM once.
 //
-// Warp roles (512 threads, 1 CTA/SM, persistent over tiles):
+// Work decomposition: a work item is (row tile, block of 128 output features); a persistent CTA (one per SM) walks
+// items blockIdx.x, blockIdx.x + gridDim.x, ...  The two feature blocks of a 256-wide layer are adjacent items, so
+// the second read of the activation tile hits L2.  One 128-feature block per CTA keeps a pipeline stage at 64 KB
+// (Xh, Xl, Wh, Wl: 16 KB each -> 3 stages) and leaves TMEM room for two accumulator buffers (the epilogue of item i
+// overlaps the MMAs of item i+1), each split in two:
+//     main  += Wh.Xh          (one truncating TMEM accumulation per 8-deep K step)
+//     cross += Wl.Xh + Wh.Xl  (2^-11 smaller: its truncation error is negligible)
+// The tensor core adds into TMEM with round-toward-zero, a coherent bias that grows with the number of accumulation
+// steps; keeping the small products out of the large accumulator cuts those steps by three (DESIGN.md "Numerics").
+//
+// Warp roles (512 threads, 1 CTA/SM):
 //   warp 0      TMA producer            warp 1      MMA issuer (+ TMEM alloc/dealloc)
-//   warps 4-7   converter (hi/lo split) warps 8-15  epilogue (warps 8-11: features 0-127, 12-15: 128-255)
+//   warps 4-7   converter (hi/lo split) warps 8-15  epilogue: lane quarter = warp % 4; the two warps of a quarter
+//                                                   take alternate groups of the tile (alternate column chunks when
+//                                                   the tile holds a single group)
 // Pipelines: smem ring  full[s] (TMA->converter) -> ready[s] (converter->MMA) -> empty[s] (MMA commit->TMA);
-//            accumulator acc_full (MMA commit->epilogue) / acc_empty (epilogue->MMA).
+//            accumulators acc_full[b] (MMA commit->epilogue) / acc_empty[b] (epilogue->MMA), b = item parity.
 #include <cuda.h>
 
 #include <cstdlib>
@@ -29,15 +41,16 @@
 namespace {
 
 constexpr int TC_BK = 32;          // K chunk: 32 floats = 128 B = one SWIZZLE_128B row
-constexpr int TC_NMAX = 128;       // max MMA N (rows per tile); two accumulator buffers x two feature blocks = 512 TMEM columns
-constexpr int TC_STAGES = 2;
-constexpr int TC_MBLK = 128;       // features per MMA
-constexpr int TC_X_BYTES = TC_NMAX * 128;        // 16384 (multiple of 1024)
-constexpr int TC_W_BYTES = 2 * TC_MBLK * 128;    // 32768: both 128-feature blocks
+constexpr int TC_NMAX = 128;       // max MMA N (rows per tile)
+constexpr int TC_STAGES = 3;
+constexpr int TC_MBLK = 128;       // features per work item (MMA M)
+constexpr int TC_X_BYTES = TC_NMAX * 128;   // 16384 (multiple of 1024)
+constexpr int TC_W_BYTES = TC_MBLK * 128;   // 16384
 constexpr int TC_STAGE_BYTES = 2 * TC_X_BYTES + 2 * TC_W_BYTES;  // Xh, Xl, Wh, Wl
 constexpr int TC_SMEM_BYTES = TC_STAGES * TC_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 constexpr int TC_THREADS = 512;
-constexpr int TC_TMEM_COLS = 512;
+constexpr int TC_TMEM_COLS = 512;  // 2 buffers x {main, cross} x 128 columns
+constexpr int TC_CH = 8;           // epilogue column chunk
 
 struct TcParams {
   // problem
@@ -45,7 +58,7 @@ struct TcParams {
   int n_mma;         // roundup16(n_rows_tile)
   int G_t, C, N_out, mblocks;
   int kchunks0, kchunks1;
-  long long tiles, tiles_per_w;
+  long long tiles, tiles_per_w, items;  // items = tiles * mblocks
   int n_sub, n_tot, j0;    // TMA-side grouping (flat launches use n_sub = n_tot = all groups, one "walker")
   int n_tot_true;          // electrons per walker (for the per-walker addend)
   long long G_sub_total;   // total sub-groups covered (W * n_sub)
@@ -142,6 +155,14 @@ __device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, float* v) {
 #pragma unroll
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
+__device__ __forceinline__ void tmem_ld8_nowait(uint32_t taddr, float* v) {
+  uint32_t r[8];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr));
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ float tmem_ld1(uint32_t taddr) {
   uint32_t r;
@@ -166,138 +187,149 @@ struct PipeState {
   }
 };
 
-// Epilogue of one CTA (all its tiles), specialised on the fused operations.  A thread owns output feature f (its
-// TMEM lane) and walks the tile's groups; a group's C columns are fetched in chunks of 16 (tcgen05.ld x16).  All
-// global addresses are a warp-uniform 64-bit base plus one 32-bit per-thread offset (row * N + f) shared by the
-// addend, the residual and the output, so a row costs one integer add.  The tanh rule takes two passes over the
-// (cheap to re-read) TMEM columns: pass 1 accumulates sum_k y_k^2, pass 2 emits the rows.
+// Epilogue of one CTA (all its items), specialised on the fused operations.  A thread owns one output feature (its
+// TMEM lane) and walks the tile's groups; a group's C columns are fetched in chunks of TC_CH from both accumulators
+// (tcgen05.ld x8) and summed.  All global addresses are a warp-uniform 64-bit base plus one 32-bit per-thread offset
+// (row * N + f) shared by the addend, the residual and the output, so a row costs one integer add.  The tanh rule
+// takes two passes over the (cheap to re-read) TMEM columns: pass 1 accumulates sum_k y_k^2, pass 2 emits the rows.
+__device__ __forceinline__ float tmem_sum1(uint32_t tcol) { return tmem_ld1(tcol) + tmem_ld1(tcol + TC_NMAX); }
+
 template <int ACT, int RES, bool CADD>
-__device__ __forceinline__ void epilogue_loop(const TcParams& p, uint32_t tlane0, int f, bool f_ok, bool mb_ok,
-                                              uint64_t* acc_full, uint64_t* acc_empty, int lane) {
+__device__ __forceinline__ void epilogue_loop(const TcParams& p, uint32_t tlane0, int q, int sub, uint64_t* acc_full,
+                                              uint64_t* acc_empty, int lane) {
   const float inv_sqrt2 = 0.70710678118654752440f;
-  const float bias_f = (p.bias && f_ok) ? p.bias[f] : 0.f;
   const int C = p.C;
   const uint32_t N = (uint32_t)p.N_out;
+  const bool by_chunk = (p.G_t == 1);  // a single group per tile: the quarter's two warps split its chunks
   uint32_t it = 0;
-  for (long long t = blockIdx.x; t < p.tiles; t += gridDim.x, ++it) {
+  for (long long item = blockIdx.x; item < p.items; item += gridDim.x, ++it) {
+    const long long t = item / p.mblocks;
+    const int hf = (int)(item % p.mblocks);
+    const int f = hf * TC_MBLK + q * 32 + lane;
+    const bool f_ok = f < p.N_out;
+    const uint32_t fo = f_ok ? (uint32_t)f : 0u;  // lanes beyond N_out read a valid column and never store
+    const float bias_f = (p.bias && f_ok) ? p.bias[f] : 0.f;
     const uint32_t buf = it & 1, acc_phase = (it >> 1) & 1;
     const uint32_t tbuf = tlane0 + buf * 2 * TC_NMAX;
     const long long w_tma = t / p.tiles_per_w;
     const int gsub0 = (int)(t % p.tiles_per_w) * p.G_t;
     mbar_wait(&acc_full[buf], acc_phase);
     tc_fence_after();
-    if (mb_ok) {
-      for (int gi = 0; gi < p.G_t; ++gi) {
-        const int gsub = gsub0 + gi;
-        if (gsub >= p.n_sub) break;  // warp-uniform
-        const long long g = w_tma * p.n_tot + p.j0 + gsub;   // actual group index
-        // warp-uniform bases; per-thread offset o = row * N + f
-        const float* __restrict__ cadd_b = CADD ? p.cadd + ((g / p.n_tot_true) * C) * (long long)N : nullptr;
-        const float* __restrict__ res_b = RES ? p.res + g * C * (long long)N : nullptr;
-        float* __restrict__ out_b = p.out + g * C * (long long)N;
-        const uint32_t tcol = tbuf + gi * C;
-        const uint32_t fo = f_ok ? (uint32_t)f : 0u;  // lanes beyond N_out read a valid column and never store
-        float th = 0.f, d1 = 1.f, s2 = 0.f;
-        int r0 = 0, r1 = C;
-        if (ACT == 1) {
-          float x = tmem_ld1(tcol);
-          if (CADD) x += cadd_b[fo];
-          x += bias_f;
-          th = tanhf(x);
-          d1 = 1.0f - th * th;
-          r0 = 1;
-          r1 = C - 1;  // Jacobian rows
-          if (r1 - r0 >= 16) {
-            for (int c0 = r0; c0 < r1; c0 += 16) {
-              int cs = c0, skip = 0;
-              if (c0 + 16 > r1) {  // last chunk: shifted back to stay inside the group's columns
-                cs = r1 - 16;
-                skip = c0 - cs;
-              }
-              float v[16], ca[16];
-              tmem_ld16_nowait(tcol + cs, v);
-              if (CADD) {
-                uint32_t o = (uint32_t)cs * N + fo;
-#pragma unroll
-                for (int i = 0; i < 16; ++i, o += N) ca[i] = cadd_b[o];
-              }
-              tmem_wait_ld();
-#pragma unroll
-              for (int i = 0; i < 16; ++i) {
-                float y = CADD ? v[i] + ca[i] : v[i];
-                if (i >= skip) s2 = fmaf(y, y, s2);
-              }
-            }
-          } else {
-            for (int c = r0; c < r1; ++c) {
-              float y = tmem_ld1(tcol + c);
-              if (CADD) y += cadd_b[(uint32_t)c * N + fo];
-              s2 = fmaf(y, y, s2);
-            }
-          }
-        }
-        // pass 2 (or the only pass of a linear layer): emit rows [r0, r1)
-        if (r1 - r0 >= 16) {
-          for (int c0 = r0; c0 < r1; c0 += 16) {
+    for (int gi = by_chunk ? 0 : sub; gi < p.G_t; gi += by_chunk ? 1 : 2) {
+      const int gsub = gsub0 + gi;
+      if (gsub >= p.n_sub) break;  // warp-uniform
+      const long long g = w_tma * p.n_tot + p.j0 + gsub;   // actual group index
+      const float* __restrict__ cadd_b = CADD ? p.cadd + ((g / p.n_tot_true) * C) * (long long)N : nullptr;
+      const float* __restrict__ res_b = RES ? p.res + g * C * (long long)N : nullptr;
+      float* __restrict__ out_b = p.out + g * C * (long long)N;
+      const uint32_t tcol = tbuf + gi * C;
+      const bool lead = !by_chunk || sub == 0;  // emits the value / Laplacian rows
+      float th = 0.f, d1 = 1.f, s2 = 0.f;
+      int r0 = 0, r1 = C;
+      if (ACT == 1) {
+        float x = tmem_sum1(tcol);
+        if (CADD) x += cadd_b[fo];
+        x += bias_f;
+        th = tanhf(x);
+        d1 = 1.0f - th * th;
+        r0 = 1;
+        r1 = C - 1;  // Jacobian rows
+        if (r1 - r0 >= TC_CH) {
+          for (int c0 = r0; c0 < r1; c0 += TC_CH) {
             int cs = c0, skip = 0;
-            if (c0 + 16 > r1) {
-              cs = r1 - 16;
+            if (c0 + TC_CH > r1) {  // last chunk: shifted back to stay inside the group's columns
+              cs = r1 - TC_CH;
               skip = c0 - cs;
             }
-            float v[16], ca[16], rr[16];
-            tmem_ld16_nowait(tcol + cs, v);
-            {
+            float v[TC_CH], v2[TC_CH], ca[TC_CH];
+            tmem_ld8_nowait(tcol + cs, v);
+            tmem_ld8_nowait(tcol + TC_NMAX + cs, v2);
+            if (CADD) {
               uint32_t o = (uint32_t)cs * N + fo;
 #pragma unroll
-              for (int i = 0; i < 16; ++i, o += N) {
-                if (CADD) ca[i] = cadd_b[o];
-                if (RES) rr[i] = res_b[o];
-              }
+              for (int i = 0; i < TC_CH; ++i, o += N) ca[i] = cadd_b[o];
             }
             tmem_wait_ld();
-            if (f_ok) {
-              uint32_t o = (uint32_t)cs * N + fo;
 #pragma unroll
-              for (int i = 0; i < 16; ++i, o += N) {
-                float y = CADD ? v[i] + ca[i] : v[i];
-                if (ACT == 1) y *= d1;
-                if (ACT == 0 && cs + i == 0) y += bias_f;
-                if (RES == 1) y = (rr[i] + y) * inv_sqrt2;
-                if (RES == 2) y = rr[i] + y;
-                if (i >= skip) out_b[o] = y;
-              }
+            for (int i = 0; i < TC_CH; ++i) {
+              float y = v[i] + v2[i];
+              if (CADD) y += ca[i];
+              if (i >= skip) s2 = fmaf(y, y, s2);
             }
           }
         } else {
           for (int c = r0; c < r1; ++c) {
-            float y = tmem_ld1(tcol + c);
-            const uint32_t o = (uint32_t)c * N + fo;
-            if (f_ok) {
-              if (CADD) y += cadd_b[o];
+            float y = tmem_sum1(tcol + c);
+            if (CADD) y += cadd_b[(uint32_t)c * N + fo];
+            s2 = fmaf(y, y, s2);
+          }
+        }
+      }
+      // pass 2 (or the only pass of a linear layer): emit rows [r0, r1)
+      if (r1 - r0 >= TC_CH) {
+        int ci = 0;
+        for (int c0 = r0; c0 < r1; c0 += TC_CH, ++ci) {
+          if (by_chunk && (ci & 1) != sub) continue;
+          int cs = c0, skip = 0;
+          if (c0 + TC_CH > r1) {
+            cs = r1 - TC_CH;
+            skip = c0 - cs;
+          }
+          float v[TC_CH], v2[TC_CH], ca[TC_CH], rr[TC_CH];
+          tmem_ld8_nowait(tcol + cs, v);
+          tmem_ld8_nowait(tcol + TC_NMAX + cs, v2);
+          {
+            uint32_t o = (uint32_t)cs * N + fo;
+#pragma unroll
+            for (int i = 0; i < TC_CH; ++i, o += N) {
+              if (CADD) ca[i] = cadd_b[o];
+              if (RES) rr[i] = res_b[o];
+            }
+          }
+          tmem_wait_ld();
+          if (f_ok) {
+            uint32_t o = (uint32_t)cs * N + fo;
+#pragma unroll
+            for (int i = 0; i < TC_CH; ++i, o += N) {
+              float y = v[i] + v2[i];
+              if (CADD) y += ca[i];
               if (ACT == 1) y *= d1;
-              if (ACT == 0 && c == 0) y += bias_f;
-              if (RES == 1) y = (res_b[o] + y) * inv_sqrt2;
-              if (RES == 2) y = res_b[o] + y;
-              out_b[o] = y;
+              if (ACT == 0 && cs + i == 0) y += bias_f;
+              if (RES == 1) y = (rr[i] + y) * inv_sqrt2;
+              if (RES == 2) y = rr[i] + y;
+              if (i >= skip) out_b[o] = y;
             }
           }
         }
-        if (ACT == 1) {
-          float yl = (C > 1) ? tmem_ld1(tcol + C - 1) : 0.f;
+      } else if (lead) {
+        for (int c = r0; c < r1; ++c) {
+          float y = tmem_sum1(tcol + c);
+          const uint32_t o = (uint32_t)c * N + fo;
           if (f_ok) {
-            if (C > 1) {
-              const uint32_t o = (uint32_t)(C - 1) * N + fo;
-              if (CADD) yl += cadd_b[o];
-              float l = d1 * yl - 2.0f * th * d1 * s2;
-              if (RES == 1) l = (res_b[o] + l) * inv_sqrt2;
-              if (RES == 2) l = res_b[o] + l;
-              out_b[o] = l;
-            }
-            float o0 = th;
-            if (RES == 1) o0 = (res_b[fo] + th) * inv_sqrt2;
-            if (RES == 2) o0 = res_b[fo] + th;
-            out_b[fo] = o0;
+            if (CADD) y += cadd_b[o];
+            if (ACT == 1) y *= d1;
+            if (ACT == 0 && c == 0) y += bias_f;
+            if (RES == 1) y = (res_b[o] + y) * inv_sqrt2;
+            if (RES == 2) y = res_b[o] + y;
+            out_b[o] = y;
           }
+        }
+      }
+      if (ACT == 1 && lead) {
+        float yl = (C > 1) ? tmem_sum1(tcol + C - 1) : 0.f;
+        if (f_ok) {
+          if (C > 1) {
+            const uint32_t o = (uint32_t)(C - 1) * N + fo;
+            if (CADD) yl += cadd_b[o];
+            float l = d1 * yl - 2.0f * th * d1 * s2;
+            if (RES == 1) l = (res_b[o] + l) * inv_sqrt2;
+            if (RES == 2) l = res_b[o] + l;
+            out_b[o] = l;
+          }
+          float o0 = th;
+          if (RES == 1) o0 = (res_b[fo] + th) * inv_sqrt2;
+          if (RES == 2) o0 = res_b[fo] + th;
+          out_b[fo] = o0;
         }
       }
     }
@@ -351,8 +383,10 @@ k_dense_tc(const __grid_constant__ CUtensorMap mapX0, const __grid_constant__ CU
     // ===================== TMA producer =====================
     if (lane == 0) {
       PipeState ps;
-      const uint32_t stage_tx = (uint32_t)(p.n_mma * 128 + 2 * p.mblocks * TC_MBLK * 128);
-      for (long long t = blockIdx.x; t < p.tiles; t += gridDim.x) {
+      const uint32_t stage_tx = (uint32_t)(p.n_mma * 128 + 2 * TC_W_BYTES);
+      for (long long item = blockIdx.x; item < p.items; item += gridDim.x) {
+        const long long t = item / p.mblocks;
+        const int hf = (int)(item % p.mblocks);
         long long w = t / p.tiles_per_w;
         int gsub0 = (int)(t % p.tiles_per_w) * p.G_t;
         int row0 = (p.j0 + gsub0) * p.C;
@@ -364,11 +398,8 @@ k_dense_tc(const __grid_constant__ CUtensorMap mapX0, const __grid_constant__ CU
             tma_load_3d(st, &mapX0, &full[ps.stage], kc * TC_BK, row0, (int)w);
           else
             tma_load_3d(st, &mapX1, &full[ps.stage], (kc - p.kchunks0) * TC_BK, row0, (int)w);
-          for (int mb = 0; mb < p.mblocks; ++mb) {
-            tma_load_2d(st + 2 * TC_X_BYTES + mb * TC_MBLK * 128, &mapWh, &full[ps.stage], kc * TC_BK, mb * TC_MBLK);
-            tma_load_2d(st + 2 * TC_X_BYTES + TC_W_BYTES + mb * TC_MBLK * 128, &mapWl, &full[ps.stage], kc * TC_BK,
-                        mb * TC_MBLK);
-          }
+          tma_load_2d(st + 2 * TC_X_BYTES, &mapWh, &full[ps.stage], kc * TC_BK, hf * TC_MBLK);
+          tma_load_2d(st + 2 * TC_X_BYTES + TC_W_BYTES, &mapWl, &full[ps.stage], kc * TC_BK, hf * TC_MBLK);
           ps.advance();
         }
       }
@@ -379,26 +410,24 @@ k_dense_tc(const __grid_constant__ CUtensorMap mapX0, const __grid_constant__ CU
       PipeState ps;
       uint32_t it = 0;
       const uint32_t idesc = tc_idesc(TC_MBLK, p.n_mma);
-      for (long long t = blockIdx.x; t < p.tiles; t += gridDim.x, ++it) {
+      for (long long item = blockIdx.x; item < p.items; item += gridDim.x, ++it) {
         const uint32_t buf = it & 1, acc_phase = (it >> 1) & 1;
-        mbar_wait(&acc_empty[buf], acc_phase ^ 1);   // epilogue has drained this buffer (two tiles ago)
+        mbar_wait(&acc_empty[buf], acc_phase ^ 1);   // epilogue has drained this buffer (two items ago)
         tc_fence_after();
+        const uint32_t d_main = tmem_base + buf * 2 * TC_NMAX, d_cross = d_main + TC_NMAX;
         for (int kc = 0; kc < kchunks; ++kc) {
           mbar_wait(&ready[ps.stage], ps.phase);
           tc_fence_after();
           const uint32_t sbase = smem_u32(smem + ps.stage * TC_STAGE_BYTES);
           const uint32_t xh = sbase, xl = sbase + TC_X_BYTES;
           const uint32_t wh = sbase + 2 * TC_X_BYTES, wl = wh + TC_W_BYTES;
-          for (int mb = 0; mb < p.mblocks; ++mb) {
-            const uint32_t d = tmem_base + (buf * 2 + mb) * TC_NMAX;
-            const uint32_t wh_mb = wh + mb * TC_MBLK * 128, wl_mb = wl + mb * TC_MBLK * 128;
 #pragma unroll
-            for (int kk = 0; kk < TC_BK / 8; ++kk) {
-              const uint32_t ko = kk * 32;  // 8 tf32 = 32 bytes along K inside the 128 B swizzle row
-              tc_mma_tf32(d, tc_smem_desc(wh_mb + ko), tc_smem_desc(xh + ko), idesc, (kc | kk) ? 1u : 0u);
-              tc_mma_tf32(d, tc_smem_desc(wl_mb + ko), tc_smem_desc(xh + ko), idesc, 1u);
-              tc_mma_tf32(d, tc_smem_desc(wh_mb + ko), tc_smem_desc(xl + ko), idesc, 1u);
-            }
+          for (int kk = 0; kk < TC_BK / 8; ++kk) {
+            const uint32_t ko = kk * 32;  // 8 tf32 = 32 bytes along K inside the 128 B swizzle row
+            const uint32_t first = (kc | kk) ? 1u : 0u;
+            tc_mma_tf32(d_main, tc_smem_desc(wh + ko), tc_smem_desc(xh + ko), idesc, first);
+            tc_mma_tf32(d_cross, tc_smem_desc(wl + ko), tc_smem_desc(xh + ko), idesc, first);
+            tc_mma_tf32(d_cross, tc_smem_desc(wh + ko), tc_smem_desc(xl + ko), idesc, 1u);
           }
           tc_commit(&empty[ps.stage]);   // stage reusable once these MMAs have read it
           ps.advance();
@@ -411,7 +440,7 @@ k_dense_tc(const __grid_constant__ CUtensorMap mapX0, const __grid_constant__ CU
     PipeState ps;
     const int ct = threadIdx.x - 128;  // 0..127
     const int nvec = p.n_mma * 8;      // float4 per X chunk (128 B rows)
-    for (long long t = blockIdx.x; t < p.tiles; t += gridDim.x) {
+    for (long long item = blockIdx.x; item < p.items; item += gridDim.x) {
       for (int kc = 0; kc < kchunks; ++kc) {
         mbar_wait(&full[ps.stage], ps.phase);
         float4* xh = reinterpret_cast<float4*>(smem + ps.stage * TC_STAGE_BYTES);
@@ -435,12 +464,10 @@ k_dense_tc(const __grid_constant__ CUtensorMap mapX0, const __grid_constant__ CU
   } else if (warp >= 8) {
     // ===================== epilogue =====================
     const int q = warp & 3;            // TMEM lane quarter this warp may access
-    const int mb = (warp - 8) >> 2;    // feature block
-    const uint32_t tlane0 = tmem_base + ((uint32_t)(q * 32) << 16) + mb * TC_NMAX;
-    const int f = mb * TC_MBLK + q * 32 + lane;
-    const bool f_ok = (mb < p.mblocks) && (f < p.N_out);
+    const int sub = (warp - 8) >> 2;   // which of the quarter's two warps
+    const uint32_t tlane0 = tmem_base + ((uint32_t)(q * 32) << 16);
     // one instantiation per (activation, residual mode, addend) combination: no per-element predicates
-#define TC_EPI(ACT, RES, CADD) epilogue_loop<ACT, RES, CADD>(p, tlane0, f, f_ok, mb < p.mblocks, acc_full, acc_empty, lane)
+#define TC_EPI(ACT, RES, CADD) epilogue_loop<ACT, RES, CADD>(p, tlane0, q, sub, acc_full, acc_empty, lane)
     const int key = (p.act ? 8 : 0) | (p.res_mode << 1) | (p.cadd ? 1 : 0);
     switch (key) {
       case 0: TC_EPI(0, 0, false); break;
@@ -584,6 +611,7 @@ int jq_launch_dense_tc(const JqDenseArgs& a, cudaStream_t st, bool* handled) {
   p.n_mma = (p.n_rows_tile + 15) / 16 * 16;
   p.tiles_per_w = jq_cdiv(p.n_sub, p.G_t);
   p.tiles = p.tiles_per_w * Wn;
+  p.items = p.tiles * p.mblocks;
   p.G_sub_total = a.G;
   p.bias = a.bias;
   p.cadd = a.cadd;
@@ -615,7 +643,7 @@ int jq_launch_dense_tc(const JqDenseArgs& a, cudaStream_t st, bool* handled) {
     rc = make_map(&mWl, wl, 2, wd, ws, wbox);
     if (rc) return rc;
   }
-  long long grid = p.tiles < sm_count ? p.tiles : sm_count;
+  long long grid = p.items < sm_count ? p.items : sm_count;
   double R = (double)a.G * a.C;
   jq_prof_work(2.0 * R * kt * a.N, 4.0 * R * (kt + a.N * (a.res ? 2 : 1)));
   JQ_LAUNCH(k_dense_tc, dim3((unsigned)grid), dim3(TC_THREADS), TC_SMEM_BYTES, st, mX0, mX1, mWh, mWl, p);

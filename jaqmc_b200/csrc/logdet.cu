@@ -102,6 +102,7 @@ int jq_launch_orb_envelope(float* orb, const float* electrons, const float* atom
 // Shared: inv[DB][nn] | colp[DB][n] | piv[DB][n] | pivinv[DB] sgn[DB] trL[DB] t2[DB] | logabs[DB] (double) |
 //         Jc[KC][DB][nn] | Mc[KC][DB][nn] | p1[KC][DB][n] | p2[KC][DB][n]
 // ------------------------------------------------------------------------------------------------
+#define LD_NP 16
 __global__ void k_logdet(const float* __restrict__ orb, int n, int D, int C, int DB, int KC,
                          float* __restrict__ det_sign, float* __restrict__ det_logabs, float* __restrict__ det_grad,
                          float* __restrict__ det_lap) {
@@ -238,6 +239,71 @@ __global__ void k_logdet(const float* __restrict__ orb, int n, int D, int C, int
     }
     __syncthreads();
   }
+  if (n <= LD_NP) {
+    // ---- small matrices (n <= 16): one item per (determinant, column i2) and derivative slab.  The item holds
+    // column i2 of dA_c in registers and forms column i2 of M = A^-1 dA_c with the inverse read as float4 broadcasts
+    // from a row-padded copy: ~1.3 instructions per multiply-add instead of 3-4 for the shared-memory tiled product.
+    float* invp = Jc;                       // [DB][n][LD_NP]  (reuses the slab area)
+    float* Ms = invp + (size_t)DB * n * LD_NP;  // [DB][n][n]
+    for (int q = tid; q < db * n * LD_NP; q += nt) {
+      int d = q / (n * LD_NP), r = q % (n * LD_NP);
+      int i = r / LD_NP, j = r % LD_NP;
+      invp[q] = (j < n) ? inv[d * nn + i * n + j] : 0.f;
+    }
+    __syncthreads();
+    for (int kk = 0; kk < KT; ++kk) {
+      const float* oc = ow + (long long)(1 + kk) * DN;  // slab: (j, d, i) at oc[j*C*DN + d*n + i]
+      for (int q = tid; q < db * n; q += nt) {
+        int d, i2;
+        jq_divmod(q, n, inv_n, &d, &i2);
+        float col[LD_NP];
+#pragma unroll
+        for (int j = 0; j < LD_NP; ++j) col[j] = (j < n) ? oc[(long long)j * C * DN + q] : 0.f;
+        const float* ib = invp + (size_t)d * n * LD_NP;
+        float* mo = Ms + d * nn + i2;
+        for (int i = 0; i < n; ++i) {
+          const float4* r4 = reinterpret_cast<const float4*>(ib + i * LD_NP);
+          float acc = 0.f;
+#pragma unroll
+          for (int j4 = 0; j4 < LD_NP / 4; ++j4) {
+            float4 v = r4[j4];
+            acc = fmaf(v.x, col[4 * j4 + 0], acc);
+            acc = fmaf(v.y, col[4 * j4 + 1], acc);
+            acc = fmaf(v.z, col[4 * j4 + 2], acc);
+            acc = fmaf(v.w, col[4 * j4 + 3], acc);
+          }
+          mo[i * n] = acc;
+        }
+      }
+      __syncthreads();
+      for (int q = tid; q < db * n; q += nt) {
+        int d, i2;
+        jq_divmod(q, n, inv_n, &d, &i2);
+        const float* m = Ms + d * nn;
+        float acc = 0.f;
+        for (int i = 0; i < n; ++i) acc = fmaf(m[i * n + i2], m[i2 * n + i], acc);
+        p1[q] = m[i2 * n + i2];
+        p2[q] = acc;
+      }
+      __syncthreads();
+      for (int d = tid; d < db; d += nt) {
+        float s1 = 0.f, s2 = 0.f;
+        for (int i = 0; i < n; ++i) {
+          s1 += p1[d * n + i];
+          s2 += p2[d * n + i];
+        }
+        if (kk < K) {
+          det_grad[(w * D + d0 + d) * K + kk] = s1;
+          t2[d] += s2;
+        } else {
+          trL[d] = s1;
+        }
+      }
+    }
+    __syncthreads();
+    for (int d = tid; d < db; d += nt) det_lap[w * D + d0 + d] = trL[d] - t2[d];
+    return;
+  }
   // traces, KC derivative slabs at a time.  slab kk <-> component c = 1 + k0 + kk (k0 + kk == K is the Laplacian row)
   for (int k0 = 0; k0 < KT; k0 += KC) {
     const int kc = (KT - k0 < KC) ? KT - k0 : KC;
@@ -325,7 +391,14 @@ int jq_launch_logdet(const float* orb, int W, int n, int D, int track, float* de
     return (size_t)8 * db + sizeof(float) * ((size_t)db * nn + 2 * (size_t)db * n + 4 * (size_t)db +
                                             (track ? (size_t)kc * db * nn * 2 + (size_t)kc * db * n * 2 : 0)) + 16;
   };
-  if (track) {
+  if (track && n <= LD_NP) {
+    // small-matrix path: all determinants of a walker in one block when they fit; the slab area [2*KC][DB][nn] must
+    // hold the row-padded inverses [DB][n][16] and one product slab [DB][nn]
+    DB = D;
+    KC = 1;
+    while ((size_t)2 * KC * nn < (size_t)n * LD_NP + nn) ++KC;
+    while (DB > 1 && smem_for(DB, KC) > 64 * 1024) --DB;
+  } else if (track) {
     while (KC < KT && smem_for(DB, KC + 1) <= 100 * 1024) ++KC;
     while (DB > 1 && smem_for(DB, KC) > 200 * 1024) --DB;
   }

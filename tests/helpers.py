@@ -54,6 +54,8 @@ def molecule(name):
         return torch.zeros(1, 3, dtype=F64), torch.tensor([2.0], dtype=F64), (1, 1)
     if name == "LiH":
         return (torch.tensor([[0.0, 0.0, 0.0], [0.0, 0.0, 3.015]], dtype=F64), torch.tensor([3.0, 1.0], dtype=F64), (2, 2))
+    if name == "Ar":  # 18 electrons: exercises the n > 16 code paths (generic LogDet kernel)
+        return torch.zeros(1, 3, dtype=F64), torch.tensor([18.0], dtype=F64), (9, 9)
     if name == "N2":
         return (torch.tensor([[0.0, 0.0, -1.034], [0.0, 0.0, 1.034]], dtype=F64), torch.tensor([7.0, 7.0], dtype=F64), (7, 7))
     raise KeyError(name)
