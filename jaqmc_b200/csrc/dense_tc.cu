@@ -42,12 +42,12 @@ namespace {
 
 constexpr int TC_BK = 32;          // K chunk: 32 floats = 128 B = one SWIZZLE_128B row
 constexpr int TC_NMAX = 128;       // max MMA N (rows per tile)
-constexpr int TC_STAGES = 3;
+constexpr int TC_MAX_STAGES = 4;   // ring depth is chosen per launch from the tile's row count
 constexpr int TC_MBLK = 128;       // features per work item (MMA M)
 constexpr int TC_X_BYTES = TC_NMAX * 128;   // 16384 (multiple of 1024)
 constexpr int TC_W_BYTES = TC_MBLK * 128;   // 16384
-constexpr int TC_STAGE_BYTES = 2 * TC_X_BYTES + 2 * TC_W_BYTES;  // Xh, Xl, Wh, Wl
-constexpr int TC_SMEM_BYTES = TC_STAGES * TC_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int TC_SMEM_LIMIT = 227 * 1024;
+constexpr int TC_SMEM_EXTRA = 1024 /*align*/ + 256 /*barriers*/;
 constexpr int TC_THREADS = 512;
 constexpr int TC_TMEM_COLS = 512;  // 2 buffers x {main, cross} x 128 columns
 constexpr int TC_CH = 8;           // epilogue column chunk
@@ -58,6 +58,7 @@ struct TcParams {
   int n_mma;         // roundup16(n_rows_tile)
   int G_t, C, N_out, mblocks;
   int kchunks0, kchunks1;
+  int stages, x_bytes, stage_bytes;  // smem ring: per stage X (raw fp32 = tf32 hi by truncation) | Xl | Wh | Wl
   long long tiles, tiles_per_w, items;  // items = tiles * mblocks
   int n_sub, n_tot, j0;    // TMA-side grouping (flat launches use n_sub = n_tot = all groups, one "walker")
   int n_tot_true;          // electrons per walker (for the per-walker addend)
@@ -179,8 +180,8 @@ __device__ __forceinline__ float tf32_rna(float x) {
 struct PipeState {
   int stage = 0;
   uint32_t phase = 0;
-  __device__ __forceinline__ void advance() {
-    if (++stage == TC_STAGES) {
+  __device__ __forceinline__ void advance(int n_stages) {
+    if (++stage == n_stages) {
       stage = 0;
       phase ^= 1;
     }
@@ -344,11 +345,11 @@ k_dense_tc(const __grid_constant__ CUtensorMap mapX0, const __grid_constant__ CU
            const __grid_constant__ CUtensorMap mapWh, const __grid_constant__ CUtensorMap mapWl, TcParams p) {
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + TC_STAGES * TC_STAGE_BYTES);
-  uint64_t* full = bars;                   // [TC_STAGES]  TMA -> converter
-  uint64_t* ready = bars + TC_STAGES;      // [TC_STAGES]  converter -> MMA
-  uint64_t* empty = bars + 2 * TC_STAGES;  // [TC_STAGES]  MMA -> TMA
-  uint64_t* acc_full = bars + 3 * TC_STAGES;   // [2]  MMA commit -> epilogue, per accumulator buffer
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + p.stages * p.stage_bytes);
+  uint64_t* full = bars;                       // [stages]  TMA -> converter and MMA (raw X, W)
+  uint64_t* ready = bars + TC_MAX_STAGES;      // [stages]  converter -> MMA (Xl)
+  uint64_t* empty = bars + 2 * TC_MAX_STAGES;  // [stages]  MMA -> TMA
+  uint64_t* acc_full = bars + 3 * TC_MAX_STAGES;   // [2]  MMA commit -> epilogue, per accumulator buffer
   uint64_t* acc_empty = acc_full + 2;          // [2]  epilogue -> MMA
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
@@ -357,7 +358,7 @@ k_dense_tc(const __grid_constant__ CUtensorMap mapX0, const __grid_constant__ CU
   const int kchunks = p.kchunks0 + p.kchunks1;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < TC_STAGES; ++s) {
+    for (int s = 0; s < p.stages; ++s) {
       mbar_init(&full[s], 1);
       mbar_init(&ready[s], 4);   // one arrive per converter warp
       mbar_init(&empty[s], 1);
@@ -392,15 +393,15 @@ k_dense_tc(const __grid_constant__ CUtensorMap mapX0, const __grid_constant__ CU
         int row0 = (p.j0 + gsub0) * p.C;
         for (int kc = 0; kc < kchunks; ++kc) {
           mbar_wait(&empty[ps.stage], ps.phase ^ 1);
-          unsigned char* st = smem + ps.stage * TC_STAGE_BYTES;
+          unsigned char* st = smem + ps.stage * p.stage_bytes;
           mbar_expect_tx(&full[ps.stage], stage_tx);
           if (kc < p.kchunks0)
             tma_load_3d(st, &mapX0, &full[ps.stage], kc * TC_BK, row0, (int)w);
           else
             tma_load_3d(st, &mapX1, &full[ps.stage], (kc - p.kchunks0) * TC_BK, row0, (int)w);
-          tma_load_2d(st + 2 * TC_X_BYTES, &mapWh, &full[ps.stage], kc * TC_BK, hf * TC_MBLK);
-          tma_load_2d(st + 2 * TC_X_BYTES + TC_W_BYTES, &mapWl, &full[ps.stage], kc * TC_BK, hf * TC_MBLK);
-          ps.advance();
+          tma_load_2d(st + 2 * p.x_bytes, &mapWh, &full[ps.stage], kc * TC_BK, hf * TC_MBLK);
+          tma_load_2d(st + 2 * p.x_bytes + TC_W_BYTES, &mapWl, &full[ps.stage], kc * TC_BK, hf * TC_MBLK);
+          ps.advance(p.stages);
         }
       }
     }
@@ -416,49 +417,56 @@ k_dense_tc(const __grid_constant__ CUtensorMap mapX0, const __grid_constant__ CU
         tc_fence_after();
         const uint32_t d_main = tmem_base + buf * 2 * TC_NMAX, d_cross = d_main + TC_NMAX;
         for (int kc = 0; kc < kchunks; ++kc) {
-          mbar_wait(&ready[ps.stage], ps.phase);
+          // the raw FP32 tile is consumed as TF32 directly (the tensor core ignores the low 13 mantissa bits: hi =
+          // trunc(x)), so two of the three products start as soon as TMA lands; only Wh.Xl waits for the converter
+          mbar_wait(&full[ps.stage], ps.phase);
           tc_fence_after();
-          const uint32_t sbase = smem_u32(smem + ps.stage * TC_STAGE_BYTES);
-          const uint32_t xh = sbase, xl = sbase + TC_X_BYTES;
-          const uint32_t wh = sbase + 2 * TC_X_BYTES, wl = wh + TC_W_BYTES;
+          const uint32_t sbase = smem_u32(smem + ps.stage * p.stage_bytes);
+          const uint32_t xh = sbase, xl = sbase + p.x_bytes;
+          const uint32_t wh = sbase + 2 * p.x_bytes, wl = wh + TC_W_BYTES;
 #pragma unroll
           for (int kk = 0; kk < TC_BK / 8; ++kk) {
             const uint32_t ko = kk * 32;  // 8 tf32 = 32 bytes along K inside the 128 B swizzle row
             const uint32_t first = (kc | kk) ? 1u : 0u;
             tc_mma_tf32(d_main, tc_smem_desc(wh + ko), tc_smem_desc(xh + ko), idesc, first);
             tc_mma_tf32(d_cross, tc_smem_desc(wl + ko), tc_smem_desc(xh + ko), idesc, first);
+          }
+          mbar_wait(&ready[ps.stage], ps.phase);
+          tc_fence_after();
+#pragma unroll
+          for (int kk = 0; kk < TC_BK / 8; ++kk) {
+            const uint32_t ko = kk * 32;
             tc_mma_tf32(d_cross, tc_smem_desc(wh + ko), tc_smem_desc(xl + ko), idesc, 1u);
           }
           tc_commit(&empty[ps.stage]);   // stage reusable once these MMAs have read it
-          ps.advance();
+          ps.advance(p.stages);
         }
         tc_commit(&acc_full[buf]);
       }
     }
   } else if (warp >= 4 && warp < 8) {
-    // ===================== converter: raw FP32 -> TF32 hi (in place) and lo =====================
+    // ===================== converter: Xl = x - trunc_tf32(x) =====================
     PipeState ps;
     const int ct = threadIdx.x - 128;  // 0..127
     const int nvec = p.n_mma * 8;      // float4 per X chunk (128 B rows)
     for (long long item = blockIdx.x; item < p.items; item += gridDim.x) {
       for (int kc = 0; kc < kchunks; ++kc) {
         mbar_wait(&full[ps.stage], ps.phase);
-        float4* xh = reinterpret_cast<float4*>(smem + ps.stage * TC_STAGE_BYTES);
-        float4* xl = reinterpret_cast<float4*>(smem + ps.stage * TC_STAGE_BYTES + TC_X_BYTES);
+        const float4* xh = reinterpret_cast<const float4*>(smem + ps.stage * p.stage_bytes);
+        float4* xl = reinterpret_cast<float4*>(smem + ps.stage * p.stage_bytes + p.x_bytes);
         for (int i = ct; i < nvec; i += 128) {
           float4 v = xh[i];
-          float4 h, l;
-          h.x = tf32_rna(v.x); l.x = tf32_rna(v.x - h.x);
-          h.y = tf32_rna(v.y); l.y = tf32_rna(v.y - h.y);
-          h.z = tf32_rna(v.z); l.z = tf32_rna(v.z - h.z);
-          h.w = tf32_rna(v.w); l.w = tf32_rna(v.w - h.w);
-          xh[i] = h;
+          float4 l;  // lo = x - trunc_tf32(x): exact, at most 13 significant bits
+          l.x = v.x - __uint_as_float(__float_as_uint(v.x) & 0xffffe000u);
+          l.y = v.y - __uint_as_float(__float_as_uint(v.y) & 0xffffe000u);
+          l.z = v.z - __uint_as_float(__float_as_uint(v.z) & 0xffffe000u);
+          l.w = v.w - __uint_as_float(__float_as_uint(v.w) & 0xffffe000u);
           xl[i] = l;
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the MMA
         __syncwarp();
         if (lane == 0) mbar_arrive(&ready[ps.stage]);
-        ps.advance();
+        ps.advance(p.stages);
       }
     }
   } else if (warp >= 8) {
@@ -569,7 +577,7 @@ int jq_launch_dense_tc(const JqDenseArgs& a, cudaStream_t st, bool* handled) {
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
-    cudaError_t e = cudaFuncSetAttribute(k_dense_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(k_dense_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT);
     JQ_REQUIRE(e == cudaSuccess, JQ_ERR_CUDA, "dense_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     attr_set = true;
   }
@@ -612,6 +620,11 @@ int jq_launch_dense_tc(const JqDenseArgs& a, cudaStream_t st, bool* handled) {
   p.tiles_per_w = jq_cdiv(p.n_sub, p.G_t);
   p.tiles = p.tiles_per_w * Wn;
   p.items = p.tiles * p.mblocks;
+  p.x_bytes = p.n_mma * 128;  // multiple of 2048: keeps every operand 1024-byte aligned
+  p.stage_bytes = 2 * p.x_bytes + 2 * TC_W_BYTES;
+  p.stages = (TC_SMEM_LIMIT - TC_SMEM_EXTRA) / p.stage_bytes;
+  if (p.stages > TC_MAX_STAGES) p.stages = TC_MAX_STAGES;
+  const int smem_bytes = p.stages * p.stage_bytes + TC_SMEM_EXTRA;
   p.G_sub_total = a.G;
   p.bias = a.bias;
   p.cadd = a.cadd;
@@ -646,7 +659,7 @@ int jq_launch_dense_tc(const JqDenseArgs& a, cudaStream_t st, bool* handled) {
   long long grid = p.items < sm_count ? p.items : sm_count;
   double R = (double)a.G * a.C;
   jq_prof_work(2.0 * R * kt * a.N, 4.0 * R * (kt + a.N * (a.res ? 2 : 1)));
-  JQ_LAUNCH(k_dense_tc, dim3((unsigned)grid), dim3(TC_THREADS), TC_SMEM_BYTES, st, mX0, mX1, mWh, mWl, p);
+  JQ_LAUNCH(k_dense_tc, dim3((unsigned)grid), dim3(TC_THREADS), smem_bytes, st, mX0, mX1, mWh, mWl, p);
   JQ_CHECK_LAUNCH();
   *handled = true;
   return JQ_OK;

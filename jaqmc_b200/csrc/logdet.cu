@@ -118,7 +118,7 @@ __global__ void k_logdet(const float* __restrict__ orb, int n, int D, int C, int
   float* sgn = pivinv + DB;
   float* trL = sgn + DB;
   float* t2 = trL + DB;
-  float* Jc = t2 + DB;
+  float* Jc = sm + (((t2 + DB) - sm + 3) & ~3);  // 16-byte aligned (float4 reads of the padded inverses)
   float* Mc = Jc + (size_t)KC * DB * nn;
   float* p1 = Mc + (size_t)KC * DB * nn;
   float* p2 = p1 + KC * DB * n;
@@ -243,8 +243,10 @@ __global__ void k_logdet(const float* __restrict__ orb, int n, int D, int C, int
     // ---- small matrices (n <= 16): one item per (determinant, column i2) and derivative slab.  The item holds
     // column i2 of dA_c in registers and forms column i2 of M = A^-1 dA_c with the inverse read as float4 broadcasts
     // from a row-padded copy: ~1.3 instructions per multiply-add instead of 3-4 for the shared-memory tiled product.
-    float* invp = Jc;                       // [DB][n][LD_NP]  (reuses the slab area)
+    float* invp = Jc;                       // [DB][n][LD_NP]  (the slab area is carved differently on this path)
     float* Ms = invp + (size_t)DB * n * LD_NP;  // [DB][n][n]
+    p1 = Ms + (size_t)DB * nn;
+    p2 = p1 + DB * n;
     for (int q = tid; q < db * n * LD_NP; q += nt) {
       int d = q / (n * LD_NP), r = q % (n * LD_NP);
       int i = r / LD_NP, j = r % LD_NP;
@@ -388,21 +390,24 @@ int jq_launch_logdet(const float* orb, int W, int n, int D, int track, float* de
   if (DB > D) DB = D;
   int KC = 1;
   auto smem_for = [&](int db, int kc) {
+    if (track && kc == 0)  // small path: inv | colp piv scalars | padded inverses | one product slab | p1 p2
+      return (size_t)8 * db + sizeof(float) * ((size_t)db * nn + 2 * (size_t)db * n + 4 * (size_t)db +
+                                              (size_t)db * n * LD_NP + (size_t)db * nn + 2 * (size_t)db * n) + 32;
     return (size_t)8 * db + sizeof(float) * ((size_t)db * nn + 2 * (size_t)db * n + 4 * (size_t)db +
-                                            (track ? (size_t)kc * db * nn * 2 + (size_t)kc * db * n * 2 : 0)) + 16;
+                                            (track ? (size_t)kc * db * nn * 2 + (size_t)kc * db * n * 2 : 0)) + 32;
   };
   if (track && n <= LD_NP) {
     // small-matrix path: all determinants of a walker in one block when they fit; the slab area [2*KC][DB][nn] must
     // hold the row-padded inverses [DB][n][16] and one product slab [DB][nn]
     DB = D;
-    KC = 1;
-    while ((size_t)2 * KC * nn < (size_t)n * LD_NP + nn) ++KC;
-    while (DB > 1 && smem_for(DB, KC) > 64 * 1024) --DB;
+    KC = 0;  // marks the small path for the size computation below
+    while (DB > 1 && smem_for(DB, 0) > 64 * 1024) DB = (DB + 1) / 2;
   } else if (track) {
     while (KC < KT && smem_for(DB, KC + 1) <= 100 * 1024) ++KC;
     while (DB > 1 && smem_for(DB, KC) > 200 * 1024) --DB;
   }
   size_t smem = smem_for(DB, KC);
+  if (KC == 0) KC = 1;
   JQ_REQUIRE(smem <= 200 * 1024, JQ_ERR_UNSUPPORTED, "logdet: %d electrons need %zu bytes of shared memory", n, smem);
 #ifndef JAQMC_HOST_EMU
   if (smem > 48 * 1024) {
