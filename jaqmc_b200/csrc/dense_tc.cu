@@ -120,8 +120,7 @@ __device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t a_desc, ui
       ".reg .pred p;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
-      "}" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
-      : "memory");
+      "}" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate));
 }
 // K-major, SWIZZLE_128B operand descriptor: 8-row atoms of 1024 B (SBO), rows of 128 B.
 __device__ __forceinline__ uint64_t tc_smem_desc(uint32_t saddr) {
@@ -175,6 +174,19 @@ __device__ __forceinline__ float tf32_rna(float x) {
   uint32_t r;
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
   return __uint_as_float(r);
+}
+
+// One elected lane of a converged warp (warp-uniform control flow keeps descriptors in uniform registers).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P;\n\t"
+      "elect.sync _|P, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t"
+      "}"
+      : "=r"(pred));
+  return pred != 0;
 }
 
 struct PipeState {
@@ -406,11 +418,19 @@ k_dense_tc(const __grid_constant__ CUtensorMap mapX0, const __grid_constant__ CU
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // ===================== MMA issuer (whole warp runs the loop; one elected lane issues) =====================
+    {
       PipeState ps;
       uint32_t it = 0;
       const uint32_t idesc = tc_idesc(TC_MBLK, p.n_mma);
+      // Operand descriptors differ between stages and K steps only in the 14-bit start-address field (bytes >> 4):
+      // build them once and advance with integer adds -- the issuing thread is the pipeline's critical resource.
+      const uint32_t smem0 = smem_u32(smem);
+      const uint64_t dx_h0 = tc_smem_desc(smem0);
+      const uint64_t dx_l0 = tc_smem_desc(smem0 + p.x_bytes);
+      const uint64_t dw_h0 = tc_smem_desc(smem0 + 2 * p.x_bytes);
+      const uint64_t dw_l0 = tc_smem_desc(smem0 + 2 * p.x_bytes + TC_W_BYTES);
+      const uint64_t stage_step = (uint64_t)(p.stage_bytes >> 4);
       for (long long item = blockIdx.x; item < p.items; item += gridDim.x, ++it) {
         const uint32_t buf = it & 1, acc_phase = (it >> 1) & 1;
         mbar_wait(&acc_empty[buf], acc_phase ^ 1);   // epilogue has drained this buffer (two items ago)
@@ -419,29 +439,36 @@ k_dense_tc(const __grid_constant__ CUtensorMap mapX0, const __grid_constant__ CU
         for (int kc = 0; kc < kchunks; ++kc) {
           // the raw FP32 tile is consumed as TF32 directly (the tensor core ignores the low 13 mantissa bits: hi =
           // trunc(x)), so two of the three products start as soon as TMA lands; only Wh.Xl waits for the converter
+          const uint64_t so = stage_step * (uint64_t)ps.stage;
+          const uint64_t xh = dx_h0 + so, xl = dx_l0 + so, wh = dw_h0 + so, wl = dw_l0 + so;
+          const uint32_t acc0 = kc ? 1u : 0u;
           mbar_wait(&full[ps.stage], ps.phase);
           tc_fence_after();
-          const uint32_t sbase = smem_u32(smem + ps.stage * p.stage_bytes);
-          const uint32_t xh = sbase, xl = sbase + p.x_bytes;
-          const uint32_t wh = sbase + 2 * p.x_bytes, wl = wh + TC_W_BYTES;
-#pragma unroll
-          for (int kk = 0; kk < TC_BK / 8; ++kk) {
-            const uint32_t ko = kk * 32;  // 8 tf32 = 32 bytes along K inside the 128 B swizzle row
-            const uint32_t first = (kc | kk) ? 1u : 0u;
-            tc_mma_tf32(d_main, tc_smem_desc(wh + ko), tc_smem_desc(xh + ko), idesc, first);
-            tc_mma_tf32(d_cross, tc_smem_desc(wl + ko), tc_smem_desc(xh + ko), idesc, first);
+          // 8 tf32 = 32 bytes along K inside the 128 B swizzle row: +2 in the address field per K step
+          if (elect_one()) {
+          tc_mma_tf32(d_main, wh, xh, idesc, acc0);
+          tc_mma_tf32(d_cross, wl, xh, idesc, acc0);
+          tc_mma_tf32(d_main, wh + 2, xh + 2, idesc, 1u);
+          tc_mma_tf32(d_cross, wl + 2, xh + 2, idesc, 1u);
+          tc_mma_tf32(d_main, wh + 4, xh + 4, idesc, 1u);
+          tc_mma_tf32(d_cross, wl + 4, xh + 4, idesc, 1u);
+          tc_mma_tf32(d_main, wh + 6, xh + 6, idesc, 1u);
+          tc_mma_tf32(d_cross, wl + 6, xh + 6, idesc, 1u);
           }
+          __syncwarp();
           mbar_wait(&ready[ps.stage], ps.phase);
           tc_fence_after();
-#pragma unroll
-          for (int kk = 0; kk < TC_BK / 8; ++kk) {
-            const uint32_t ko = kk * 32;
-            tc_mma_tf32(d_cross, tc_smem_desc(wh + ko), tc_smem_desc(xl + ko), idesc, 1u);
-          }
+          if (elect_one()) {
+          tc_mma_tf32(d_cross, wh, xl, idesc, 1u);
+          tc_mma_tf32(d_cross, wh + 2, xl + 2, idesc, 1u);
+          tc_mma_tf32(d_cross, wh + 4, xl + 4, idesc, 1u);
+          tc_mma_tf32(d_cross, wh + 6, xl + 6, idesc, 1u);
           tc_commit(&empty[ps.stage]);   // stage reusable once these MMAs have read it
+          if (kc == kchunks - 1) tc_commit(&acc_full[buf]);
+          }
+          __syncwarp();
           ps.advance(p.stages);
         }
-        tc_commit(&acc_full[buf]);
       }
     }
   } else if (warp >= 4 && warp < 8) {
