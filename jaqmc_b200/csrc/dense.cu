@@ -162,48 +162,87 @@ __global__ void k_dense_small(JqDenseArgs a) {
   __syncthreads();
   const float inv_sqrt2 = 0.70710678118654752440f;
   const bool res_from_tile = (a.res == a.src0) && (K == N);
-  for (int q = tid; q < ng * N; q += nt) {
-    const int gl = q / N, f = q % N;
+  // an item owns NF output features of one group: f and f + N/2 when N is even (the tile reads are shared by both)
+  const int NF = (N % 2 == 0) ? 2 : 1;
+  const int NH = N / NF;
+  const bool vec4 = (K % 4 == 0);
+  for (int q = tid; q < ng * NH; q += nt) {
+    const int gl = q / NH, f0 = q % NH;
     const float* xr = Xs + gl * C * K;
-    float acc[SM_CMAX];
+    float acc[2][SM_CMAX];
 #pragma unroll
-    for (int c = 0; c < SM_CMAX; ++c) acc[c] = 0.f;
-    for (int k = 0; k < K; ++k) {
-      const float w = Ws[k * N + f];
+    for (int c = 0; c < SM_CMAX; ++c) acc[0][c] = acc[1][c] = 0.f;
+    if (vec4) {
+      for (int k = 0; k < K; k += 4) {
+        float w0[4], w1[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          w0[u] = Ws[(k + u) * N + f0];
+          w1[u] = (NF == 2) ? Ws[(k + u) * N + f0 + NH] : 0.f;
+        }
+#pragma unroll
+        for (int c = 0; c < SM_CMAX; ++c)
+          if (c < C) {
+            const float4 x4 = *reinterpret_cast<const float4*>(xr + c * K + k);
+            acc[0][c] = fmaf(x4.x, w0[0], acc[0][c]);
+            acc[0][c] = fmaf(x4.y, w0[1], acc[0][c]);
+            acc[0][c] = fmaf(x4.z, w0[2], acc[0][c]);
+            acc[0][c] = fmaf(x4.w, w0[3], acc[0][c]);
+            acc[1][c] = fmaf(x4.x, w1[0], acc[1][c]);
+            acc[1][c] = fmaf(x4.y, w1[1], acc[1][c]);
+            acc[1][c] = fmaf(x4.z, w1[2], acc[1][c]);
+            acc[1][c] = fmaf(x4.w, w1[3], acc[1][c]);
+          }
+      }
+    } else {
+      for (int k = 0; k < K; ++k) {
+        const float w0 = Ws[k * N + f0];
+        const float w1 = (NF == 2) ? Ws[k * N + f0 + NH] : 0.f;
+#pragma unroll
+        for (int c = 0; c < SM_CMAX; ++c)
+          if (c < C) {
+            const float x = xr[c * K + k];
+            acc[0][c] = fmaf(x, w0, acc[0][c]);
+            acc[1][c] = fmaf(x, w1, acc[1][c]);
+          }
+      }
+    }
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      if (h >= NF) continue;
+      const int f = f0 + h * NH;
+      float(&ac)[SM_CMAX] = acc[h];
+      if (a.bias) ac[0] += a.bias[f];
+      if (a.act == 1) {
+        const float t = tanhf(ac[0]);
+        const float d1 = 1.0f - t * t;
+        float s2 = 0.f;
+#pragma unroll
+        for (int c = 1; c < SM_CMAX - 1; ++c)
+          if (c < C - 1) {
+            s2 = fmaf(ac[c], ac[c], s2);
+            ac[c] *= d1;
+          }
+        if (C > 1) {
+#pragma unroll
+          for (int c = 1; c < SM_CMAX; ++c)
+            if (c == C - 1) ac[c] = d1 * ac[c] - 2.0f * t * d1 * s2;
+        }
+        ac[0] = t;
+      }
+      float* o = a.out + ((g0 + gl) * C) * N + f;
+      const float* rg = a.res ? a.res + ((g0 + gl) * C) * N + f : nullptr;
 #pragma unroll
       for (int c = 0; c < SM_CMAX; ++c)
-        if (c < C) acc[c] = fmaf(xr[c * K + k], w, acc[c]);
-    }
-    if (a.bias) acc[0] += a.bias[f];
-    if (a.act == 1) {
-      const float t = tanhf(acc[0]);
-      const float d1 = 1.0f - t * t;
-      float s2 = 0.f;
-#pragma unroll
-      for (int c = 1; c < SM_CMAX - 1; ++c)
-        if (c < C - 1) {
-          s2 = fmaf(acc[c], acc[c], s2);
-          acc[c] *= d1;
+        if (c < C) {
+          float v = ac[c];
+          if (a.res_mode) {
+            const float r = res_from_tile ? xr[c * K + f] : rg[(long long)c * N];
+            v = (a.res_mode == 1) ? (r + v) * inv_sqrt2 : r + v;
+          }
+          o[(long long)c * N] = v;
         }
-      if (C > 1) {
-#pragma unroll
-        for (int c = 1; c < SM_CMAX; ++c)
-          if (c == C - 1) acc[c] = d1 * acc[c] - 2.0f * t * d1 * s2;
-      }
-      acc[0] = t;
     }
-    float* o = a.out + ((g0 + gl) * C) * N + f;
-    const float* rg = a.res ? a.res + ((g0 + gl) * C) * N + f : nullptr;
-#pragma unroll
-    for (int c = 0; c < SM_CMAX; ++c)
-      if (c < C) {
-        float v = acc[c];
-        if (a.res_mode) {
-          const float r = res_from_tile ? xr[c * K + f] : rg[(long long)c * N];
-          v = (a.res_mode == 1) ? (r + v) * inv_sqrt2 : r + v;
-        }
-        o[(long long)c * N] = v;
-      }
   }
 }
 

@@ -27,9 +27,8 @@
 //
 // Warp roles (512 threads, 1 CTA/SM):
 //   warp 0      TMA producer            warp 1      MMA issuer (+ TMEM alloc/dealloc)
-//   warps 4-7   converter (hi/lo split) warps 8-15  epilogue: lane quarter = warp % 4; the two warps of a quarter
-//                                                   take alternate groups of the tile (alternate column chunks when
-//                                                   the tile holds a single group)
+//   warps 4-7   converter (lo part)     warps 8-15  epilogue: lane quarter = warp % 4; the two warps of a quarter
+//                                                   take alternate groups of the tile
 // Pipelines: smem ring  full[s] (TMA->converter) -> ready[s] (converter->MMA) -> empty[s] (MMA commit->TMA);
 //            accumulators acc_full[b] (MMA commit->epilogue) / acc_empty[b] (epilogue->MMA), b = item parity.
 #include <cuda.h>
@@ -203,8 +202,7 @@ struct PipeState {
 // Epilogue of one CTA (all its items), specialised on the fused operations.  A thread owns one output feature (its
 // TMEM lane) and walks the tile's groups; a group's C columns are fetched in chunks of TC_CH from both accumulators
 // (tcgen05.ld x8) and summed.  All global addresses are a warp-uniform 64-bit base plus one 32-bit per-thread offset
-// (row * N + f) shared by the addend, the residual and the output, so a row costs one integer add.  The tanh rule
-// takes two passes over the (cheap to re-read) TMEM columns: pass 1 accumulates sum_k y_k^2, pass 2 emits the rows.
+// (row * N + f) shared by the addend, the residual and the output, so a row costs one integer add.
 __device__ __forceinline__ float tmem_sum1(uint32_t tcol) { return tmem_ld1(tcol) + tmem_ld1(tcol + TC_NMAX); }
 
 template <int ACT, int RES, bool CADD>
@@ -213,7 +211,6 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& p, uint32_t tlane0
   const float inv_sqrt2 = 0.70710678118654752440f;
   const int C = p.C;
   const uint32_t N = (uint32_t)p.N_out;
-  const bool by_chunk = (p.G_t == 1);  // a single group per tile: the quarter's two warps split its chunks
   uint32_t it = 0;
   for (long long item = blockIdx.x; item < p.items; item += gridDim.x, ++it) {
     const long long t = item / p.mblocks;
@@ -228,7 +225,7 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& p, uint32_t tlane0
     const int gsub0 = (int)(t % p.tiles_per_w) * p.G_t;
     mbar_wait(&acc_full[buf], acc_phase);
     tc_fence_after();
-    for (int gi = by_chunk ? 0 : sub; gi < p.G_t; gi += by_chunk ? 1 : 2) {
+    for (int gi = sub; gi < p.G_t; gi += 2) {
       const int gsub = gsub0 + gi;
       if (gsub >= p.n_sub) break;  // warp-uniform
       const long long g = w_tma * p.n_tot + p.j0 + gsub;   // actual group index
@@ -236,7 +233,8 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& p, uint32_t tlane0
       const float* __restrict__ res_b = RES ? p.res + g * C * (long long)N : nullptr;
       float* __restrict__ out_b = p.out + g * C * (long long)N;
       const uint32_t tcol = tbuf + gi * C;
-      const bool lead = !by_chunk || sub == 0;  // emits the value / Laplacian rows
+      // Single pass: the Jacobian rows of tanh only need d1 = 1 - tanh(x)^2 (value column, read first); sum_k y_k^2
+      // is accumulated on the way and enters the Laplacian row, which is emitted last.
       float th = 0.f, d1 = 1.f, s2 = 0.f;
       int r0 = 0, r1 = C;
       if (ACT == 1) {
@@ -247,44 +245,11 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& p, uint32_t tlane0
         d1 = 1.0f - th * th;
         r0 = 1;
         r1 = C - 1;  // Jacobian rows
-        if (r1 - r0 >= TC_CH) {
-          for (int c0 = r0; c0 < r1; c0 += TC_CH) {
-            int cs = c0, skip = 0;
-            if (c0 + TC_CH > r1) {  // last chunk: shifted back to stay inside the group's columns
-              cs = r1 - TC_CH;
-              skip = c0 - cs;
-            }
-            float v[TC_CH], v2[TC_CH], ca[TC_CH];
-            tmem_ld8_nowait(tcol + cs, v);
-            tmem_ld8_nowait(tcol + TC_NMAX + cs, v2);
-            if (CADD) {
-              uint32_t o = (uint32_t)cs * N + fo;
-#pragma unroll
-              for (int i = 0; i < TC_CH; ++i, o += N) ca[i] = cadd_b[o];
-            }
-            tmem_wait_ld();
-#pragma unroll
-            for (int i = 0; i < TC_CH; ++i) {
-              float y = v[i] + v2[i];
-              if (CADD) y += ca[i];
-              if (i >= skip) s2 = fmaf(y, y, s2);
-            }
-          }
-        } else {
-          for (int c = r0; c < r1; ++c) {
-            float y = tmem_sum1(tcol + c);
-            if (CADD) y += cadd_b[(uint32_t)c * N + fo];
-            s2 = fmaf(y, y, s2);
-          }
-        }
       }
-      // pass 2 (or the only pass of a linear layer): emit rows [r0, r1)
       if (r1 - r0 >= TC_CH) {
-        int ci = 0;
-        for (int c0 = r0; c0 < r1; c0 += TC_CH, ++ci) {
-          if (by_chunk && (ci & 1) != sub) continue;
+        for (int c0 = r0; c0 < r1; c0 += TC_CH) {
           int cs = c0, skip = 0;
-          if (c0 + TC_CH > r1) {
+          if (c0 + TC_CH > r1) {  // last chunk: shifted back to stay inside the group's columns
             cs = r1 - TC_CH;
             skip = c0 - cs;
           }
@@ -300,35 +265,37 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& p, uint32_t tlane0
             }
           }
           tmem_wait_ld();
-          if (f_ok) {
-            uint32_t o = (uint32_t)cs * N + fo;
+          uint32_t o = (uint32_t)cs * N + fo;
 #pragma unroll
-            for (int i = 0; i < TC_CH; ++i, o += N) {
-              float y = v[i] + v2[i];
-              if (CADD) y += ca[i];
-              if (ACT == 1) y *= d1;
-              if (ACT == 0 && cs + i == 0) y += bias_f;
-              if (RES == 1) y = (rr[i] + y) * inv_sqrt2;
-              if (RES == 2) y = rr[i] + y;
-              if (i >= skip) out_b[o] = y;
+          for (int i = 0; i < TC_CH; ++i, o += N) {
+            float y = v[i] + v2[i];
+            if (CADD) y += ca[i];
+            if (ACT == 1) {
+              if (i >= skip) s2 = fmaf(y, y, s2);
+              y *= d1;
             }
+            if (ACT == 0 && cs + i == 0) y += bias_f;
+            if (RES == 1) y = (rr[i] + y) * inv_sqrt2;
+            if (RES == 2) y = rr[i] + y;
+            if (f_ok && i >= skip) out_b[o] = y;
           }
         }
-      } else if (lead) {
+      } else {
         for (int c = r0; c < r1; ++c) {
           float y = tmem_sum1(tcol + c);
           const uint32_t o = (uint32_t)c * N + fo;
-          if (f_ok) {
-            if (CADD) y += cadd_b[o];
-            if (ACT == 1) y *= d1;
-            if (ACT == 0 && c == 0) y += bias_f;
-            if (RES == 1) y = (res_b[o] + y) * inv_sqrt2;
-            if (RES == 2) y = res_b[o] + y;
-            out_b[o] = y;
+          if (CADD) y += cadd_b[o];
+          if (ACT == 1) {
+            s2 = fmaf(y, y, s2);
+            y *= d1;
           }
+          if (ACT == 0 && c == 0) y += bias_f;
+          if (RES == 1) y = (res_b[o] + y) * inv_sqrt2;
+          if (RES == 2) y = res_b[o] + y;
+          if (f_ok) out_b[o] = y;
         }
       }
-      if (ACT == 1 && lead) {
+      if (ACT == 1) {
         float yl = (C > 1) ? tmem_sum1(tcol + C - 1) : 0.f;
         if (f_ok) {
           if (C > 1) {
