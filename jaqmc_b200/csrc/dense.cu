@@ -147,6 +147,43 @@ __global__ void k_dense_simt(JqDenseArgs a) {
 // ------------------------------------------------------------------------------------------------
 #define SM_GT 32
 #define SM_CMAX 8
+// bias + tanh forward-Laplacian rule + residual for one (group, feature) item of k_dense_small
+__device__ __forceinline__ void small_epilogue(const JqDenseArgs& a, float (&ac)[8], int f, long long g, const float* xr,
+                                               bool res_from_tile) {
+  const float inv_sqrt2 = 0.70710678118654752440f;
+  const int C = a.C, K = a.k0, N = a.N;
+  if (a.bias) ac[0] += a.bias[f];
+  if (a.act == 1) {
+    const float t = tanhf(ac[0]);
+    const float d1 = 1.0f - t * t;
+    float s2 = 0.f;
+#pragma unroll
+    for (int c = 1; c < 7; ++c)
+      if (c < C - 1) {
+        s2 = fmaf(ac[c], ac[c], s2);
+        ac[c] *= d1;
+      }
+    if (C > 1) {
+#pragma unroll
+      for (int c = 1; c < 8; ++c)
+        if (c == C - 1) ac[c] = d1 * ac[c] - 2.0f * t * d1 * s2;
+    }
+    ac[0] = t;
+  }
+  float* o = a.out + (g * C) * N + f;
+  const float* rg = a.res ? a.res + (g * C) * N + f : nullptr;
+#pragma unroll
+  for (int c = 0; c < 8; ++c)
+    if (c < C) {
+      float v = ac[c];
+      if (a.res_mode) {
+        const float r = res_from_tile ? xr[c * K + f] : rg[(long long)c * N];
+        v = (a.res_mode == 1) ? (r + v) * inv_sqrt2 : r + v;
+      }
+      o[(long long)c * N] = v;
+    }
+}
+
 __global__ void k_dense_small(JqDenseArgs a) {
   JQ_DYN_SMEM(float, sm);
   const int C = a.C, K = a.k0, N = a.N;
@@ -169,9 +206,9 @@ __global__ void k_dense_small(JqDenseArgs a) {
   for (int q = tid; q < ng * NH; q += nt) {
     const int gl = q / NH, f0 = q % NH;
     const float* xr = Xs + gl * C * K;
-    float acc[2][SM_CMAX];
+    float acc0[SM_CMAX], acc1[SM_CMAX];
 #pragma unroll
-    for (int c = 0; c < SM_CMAX; ++c) acc[0][c] = acc[1][c] = 0.f;
+    for (int c = 0; c < SM_CMAX; ++c) acc0[c] = acc1[c] = 0.f;
     if (vec4) {
       for (int k = 0; k < K; k += 4) {
         float w0[4], w1[4];
@@ -184,14 +221,14 @@ __global__ void k_dense_small(JqDenseArgs a) {
         for (int c = 0; c < SM_CMAX; ++c)
           if (c < C) {
             const float4 x4 = *reinterpret_cast<const float4*>(xr + c * K + k);
-            acc[0][c] = fmaf(x4.x, w0[0], acc[0][c]);
-            acc[0][c] = fmaf(x4.y, w0[1], acc[0][c]);
-            acc[0][c] = fmaf(x4.z, w0[2], acc[0][c]);
-            acc[0][c] = fmaf(x4.w, w0[3], acc[0][c]);
-            acc[1][c] = fmaf(x4.x, w1[0], acc[1][c]);
-            acc[1][c] = fmaf(x4.y, w1[1], acc[1][c]);
-            acc[1][c] = fmaf(x4.z, w1[2], acc[1][c]);
-            acc[1][c] = fmaf(x4.w, w1[3], acc[1][c]);
+            acc0[c] = fmaf(x4.x, w0[0], acc0[c]);
+            acc0[c] = fmaf(x4.y, w0[1], acc0[c]);
+            acc0[c] = fmaf(x4.z, w0[2], acc0[c]);
+            acc0[c] = fmaf(x4.w, w0[3], acc0[c]);
+            acc1[c] = fmaf(x4.x, w1[0], acc1[c]);
+            acc1[c] = fmaf(x4.y, w1[1], acc1[c]);
+            acc1[c] = fmaf(x4.z, w1[2], acc1[c]);
+            acc1[c] = fmaf(x4.w, w1[3], acc1[c]);
           }
       }
     } else {
@@ -202,47 +239,13 @@ __global__ void k_dense_small(JqDenseArgs a) {
         for (int c = 0; c < SM_CMAX; ++c)
           if (c < C) {
             const float x = xr[c * K + k];
-            acc[0][c] = fmaf(x, w0, acc[0][c]);
-            acc[1][c] = fmaf(x, w1, acc[1][c]);
+            acc0[c] = fmaf(x, w0, acc0[c]);
+            acc1[c] = fmaf(x, w1, acc1[c]);
           }
       }
     }
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      if (h >= NF) continue;
-      const int f = f0 + h * NH;
-      float(&ac)[SM_CMAX] = acc[h];
-      if (a.bias) ac[0] += a.bias[f];
-      if (a.act == 1) {
-        const float t = tanhf(ac[0]);
-        const float d1 = 1.0f - t * t;
-        float s2 = 0.f;
-#pragma unroll
-        for (int c = 1; c < SM_CMAX - 1; ++c)
-          if (c < C - 1) {
-            s2 = fmaf(ac[c], ac[c], s2);
-            ac[c] *= d1;
-          }
-        if (C > 1) {
-#pragma unroll
-          for (int c = 1; c < SM_CMAX; ++c)
-            if (c == C - 1) ac[c] = d1 * ac[c] - 2.0f * t * d1 * s2;
-        }
-        ac[0] = t;
-      }
-      float* o = a.out + ((g0 + gl) * C) * N + f;
-      const float* rg = a.res ? a.res + ((g0 + gl) * C) * N + f : nullptr;
-#pragma unroll
-      for (int c = 0; c < SM_CMAX; ++c)
-        if (c < C) {
-          float v = ac[c];
-          if (a.res_mode) {
-            const float r = res_from_tile ? xr[c * K + f] : rg[(long long)c * N];
-            v = (a.res_mode == 1) ? (r + v) * inv_sqrt2 : r + v;
-          }
-          o[(long long)c * N] = v;
-        }
-    }
+    small_epilogue(a, acc0, f0, g0 + gl, xr, res_from_tile);
+    if (NF == 2) small_epilogue(a, acc1, f0 + NH, g0 + gl, xr, res_from_tile);
   }
 }
 

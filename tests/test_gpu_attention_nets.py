@@ -54,7 +54,9 @@ def _check(setup, e_tol=1e-5, l_tol=1e-6):
     print("scaled errors: E_L max %.2e, logpsi max %.2e" % (e_err.max(), l_err.max()))
     lp, sg = rt.logpsi(wf, sysh, e32)
     assert torch.equal(sg.cpu(), torch.from_numpy(out["sign"]))
-    np.testing.assert_allclose(lp.cpu().numpy(), out["logpsi"], rtol=2e-6, atol=2e-5)
+    _, l_scale = H.fp32_scales(ref, el)  # value-only (sampling) path against the oracle, same scaled tolerance
+    l_val = np.abs(lp.cpu().numpy() - ref["logpsi"]) / l_scale
+    assert np.median(l_val) < l_tol and l_val.max() < 10 * l_tol, l_val
 
 
 @pytest.mark.parametrize("mol,ndets,layers,heads,dh", [
