@@ -204,6 +204,27 @@ int jaqmc_b200_local_energy(const jaqmc_wavefunction* wf, const jaqmc_system* sy
 int jaqmc_b200_coulomb(const jaqmc_system* sys, const float* electrons, int64_t n_walkers, int32_t n_electrons,
                        float* e_pot, jaqmc_stream_t stream);
 
+/* ---- Ewald sum (solid-state potential) ---------------------------------------------------------
+ * Precomputed by the host exactly as EwaldSum.__init__ does (estimator/ewald.py:50-110): all pointers are DEVICE
+ * arrays of float32. */
+typedef struct {
+  const float* lattice;     /* (3,3) supercell lattice vectors, rows */
+  const float* inv_lattice; /* (3,3) inverse (orthogonal-cell minimum image), or NULL */
+  const float* mic_shifts;  /* (27,3) neighbouring-image shifts in the reference's meshgrid order (general cell), or NULL */
+  const float* images;      /* (n_images,3) lattice_displacements of the real-space sum */
+  const float* gpoints;     /* (n_g,3) selected reciprocal vectors (half space) */
+  const float* gweight;     /* (n_g,) 4 pi exp(-G^2/4 alpha^2) / (V G^2) */
+  int32_t n_images, center_image, n_g;
+  int32_t mic_kind;         /* 0 diagonal, 1 orthogonal, 2 general (geometry/pbc.py:114-184) */
+  float alpha, self_const_factor, ijconst;
+} jaqmc_ewald;
+
+/* Replaces PotentialEnergy.evaluate_single_walker (app/solid/hamiltonian.py:28-56) / EwaldSum.energy
+ * (estimator/ewald.py:112-173) vmapped over walkers: electrons (n_walkers, n_electrons, 3) with charge -1 and the
+ * supercell ions atoms (n_atoms,3) / charges (n_atoms,) -> e_pot (n_walkers,). */
+int jaqmc_b200_ewald(const jaqmc_ewald* ewald, const float* electrons, int64_t n_walkers, int32_t n_electrons,
+                     const float* atoms, const float* charges, int32_t n_atoms, float* e_pot, jaqmc_stream_t stream);
+
 /* Replaces MCMCSampler.step's fori_loop of _mh_update (sampler/mcmc.py:96-137,167-180) for `n_steps` all-electron
  * moves with host-supplied noise:
  *   electrons (n_walkers, n, 3) in/out; logpsi (n_walkers,) in/out (log|psi| of `electrons`; computed on entry

@@ -150,7 +150,29 @@ class System(C.Structure):
     _fields_ = [("atoms", FloatP), ("charges", FloatP), ("n_atoms", C.c_int32)]
 
 
+class Ewald(C.Structure):
+    _fields_ = [
+        ("lattice", FloatP),
+        ("inv_lattice", FloatP),
+        ("mic_shifts", FloatP),
+        ("images", FloatP),
+        ("gpoints", FloatP),
+        ("gweight", FloatP),
+        ("n_images", C.c_int32),
+        ("center_image", C.c_int32),
+        ("n_g", C.c_int32),
+        ("mic_kind", C.c_int32),
+        ("alpha", C.c_float),
+        ("self_const_factor", C.c_float),
+        ("ijconst", C.c_float),
+    ]
+
+
 PROTOTYPES = {
+    "jaqmc_b200_ewald": (
+        C.c_int,
+        [C.POINTER(Ewald), FloatP, C.c_int64, C.c_int32, FloatP, FloatP, C.c_int32, FloatP, C.c_void_p],
+    ),
     "jaqmc_b200_workspace_bytes": (C.c_size_t, [C.POINTER(Wavefunction), C.c_int64, C.c_int]),
     "jaqmc_b200_logpsi": (
         C.c_int,

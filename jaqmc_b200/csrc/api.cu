@@ -60,7 +60,10 @@ extern "C" size_t jaqmc_b200_profile_fetch(char* buf, size_t cap) {
     cudaEventSynchronize(r.e1);
     float ms = 0.f;
     cudaEventElapsedTime(&ms, r.e0, r.e1);
-    Agg& a = agg[r.name];
+    // launches of one kernel with different declared work are different shapes: keep them apart
+    char key[160];
+    snprintf(key, sizeof(key), "%s@%.4g", r.name, r.flops > 0 ? r.flops : r.bytes);
+    Agg& a = agg[key];
     a.n += 1;
     a.ms += ms;
     a.flops += r.flops;
@@ -253,6 +256,16 @@ extern "C" int jaqmc_b200_coulomb(const jaqmc_system* sys, const float* electron
              "coulomb: bad arguments");
   return jq_launch_coulomb(electrons, sys->atoms, sys->charges, (int)n_walkers, n_electrons, sys->n_atoms, e_pot,
                            (cudaStream_t)stream);
+}
+
+extern "C" int jaqmc_b200_ewald(const jaqmc_ewald* ewald, const float* electrons, int64_t n_walkers, int32_t n_electrons,
+                                const float* atoms, const float* charges, int32_t n_atoms, float* e_pot,
+                                jaqmc_stream_t stream) {
+  JQ_REQUIRE(ewald != nullptr, JQ_ERR_INVALID_ARGUMENT, "ewald: null descriptor");
+  JQ_REQUIRE(n_walkers >= 0 && n_electrons >= 0 && n_atoms >= 0 && n_electrons + n_atoms >= 1 &&
+                 (n_walkers == 0 || ((electrons || n_electrons == 0) && e_pot && (n_atoms == 0 || (atoms && charges)))),
+             JQ_ERR_INVALID_ARGUMENT, "ewald: bad arguments");
+  return jq_launch_ewald(ewald, electrons, n_walkers, n_electrons, atoms, charges, n_atoms, e_pot, (cudaStream_t)stream);
 }
 
 extern "C" int jaqmc_b200_local_energy(const jaqmc_wavefunction* wf, const jaqmc_system* sys, const float* electrons,

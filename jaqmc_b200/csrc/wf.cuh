@@ -42,3 +42,7 @@ size_t jq_psiformer_ws_bytes(const jaqmc_psiformer_config* c, long long W, int t
 int jq_psiformer_forward(const jaqmc_psiformer_config* c, const jaqmc_psiformer_params* p, const jaqmc_system* sys,
                          const float* electrons, long long W, int track, void* ws, size_t ws_bytes, JqWfOut out,
                          cudaStream_t st);
+
+// ---- Ewald (ewald.cu) ---------------------------------------------------------------------------
+int jq_launch_ewald(const jaqmc_ewald* ew, const float* electrons, long long W, int n_el, const float* atoms,
+                    const float* charges, int n_at, float* e_pot, cudaStream_t st);

@@ -187,3 +187,27 @@ def test_coulomb_matches_oracle():
     v = rt.coulomb(sysh, el.float().contiguous().cuda()).cpu().numpy()
     ref = np.array([float(OE.potential_energy(el[w], atoms, charges)) for w in range(64)])
     np.testing.assert_allclose(v, ref, rtol=2e-6)
+
+
+def test_ewald_matches_oracle_on_lih_supercell():
+    """LiH rock-salt 2x2x2 supercell (BASELINE config 5 geometry): 32 electrons + 16 ions, general (FCC) cell."""
+    from jaqmc_b200.ewald import EwaldSum
+
+    a = 4.0 / 0.529177  # 4.0 Angstrom in bohr
+    prim = a / 2 * np.array([[0.0, 1.0, 1.0], [1.0, 0.0, 1.0], [1.0, 1.0, 0.0]])
+    lat = 2 * prim
+    frac = np.array([[i, j, k] for i in range(2) for j in range(2) for k in range(2)], dtype=np.float64)
+    li = frac @ prim
+    h = li + np.array([a / 2, a / 2, a / 2])
+    atoms = np.concatenate([li, h]).astype(np.float32)
+    charges = np.concatenate([3 * np.ones(8), np.ones(8)]).astype(np.float32)
+    g = np.random.default_rng(0)
+    W = 64
+    el = (atoms[g.integers(0, 16, (W, 32))] + g.normal(size=(W, 32, 3))).astype(np.float32)
+    ew = EwaldSum(lat, device="cuda")
+    got = ew.energy(torch.from_numpy(el).cuda(), torch.from_numpy(atoms).cuda(), torch.from_numpy(charges).cuda()).cpu().numpy()
+    ref_ew = OE.EwaldSum(lat)
+    ref = np.array([OE.solid_potential_energy(ref_ew, el[w].astype(np.float64), atoms.astype(np.float64), charges)
+                    for w in range(8)])
+    np.testing.assert_allclose(got[:8], ref, rtol=2e-6, atol=2e-5)
+    assert np.isfinite(got).all()
