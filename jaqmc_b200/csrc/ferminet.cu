@@ -10,14 +10,7 @@
 //   only [h_j | g2_j]  (256+64 wide instead of 832 wide for the default network).
 #include "wf.cuh"
 
-struct FermiDims {
-  JqSpins sp;
-  int n, A, D, L, nch, C, C1, C2, f1;
-  int d1[JQ_MAX_LAYERS], d2[JQ_MAX_LAYERS];  // widths after layer l
-  int d1max, d2max, in1;
-};
-
-static int fermi_dims(const jaqmc_ferminet_config* c, int track, FermiDims* o) {
+int jq_fermi_dims(const jaqmc_ferminet_config* c, int track, int fat, int fee, FermiDims* o) {
   JQ_REQUIRE(c->n_layers >= 1 && c->n_layers <= JQ_MAX_LAYERS, JQ_ERR_INVALID_ARGUMENT, "ferminet: n_layers=%d",
              c->n_layers);
   JQ_REQUIRE(c->n_up >= 0 && c->n_dn >= 0 && c->n_up + c->n_dn >= 1, JQ_ERR_INVALID_ARGUMENT, "ferminet: nspins");
@@ -34,9 +27,10 @@ static int fermi_dims(const jaqmc_ferminet_config* c, int track, FermiDims* o) {
   o->C = track ? 3 * o->n + 2 : 1;
   o->C1 = track ? 5 : 1;
   o->C2 = track ? 8 : 1;
-  o->f1 = 4 * o->A;
+  o->fee = fee;
+  o->f1 = fat * o->A;
   o->d1max = 0;
-  o->d2max = 4;
+  o->d2max = fee;
   for (int l = 0; l < o->L; ++l) {
     o->d1[l] = c->hidden_single[l];
     o->d2[l] = c->hidden_double[l];
@@ -44,16 +38,11 @@ static int fermi_dims(const jaqmc_ferminet_config* c, int track, FermiDims* o) {
     if (o->d1[l] > o->d1max) o->d1max = o->d1[l];
     if (l < o->L - 1 && o->d2[l] > o->d2max) o->d2max = o->d2[l];
   }
-  o->in1 = o->f1 * (1 + o->nch) + 4 * o->nch;
+  o->in1 = o->f1 * (1 + o->nch) + fee * o->nch;
   JQ_REQUIRE(o->f1 != o->d1[0], JQ_ERR_UNSUPPORTED,
-             "ferminet: 4*n_atoms == hidden_dims_single[0] (input-layer residual) is not supported");
+             "ferminet: input feature width == hidden_dims_single[0] (input-layer residual) is not supported");
   return JQ_OK;
 }
-
-struct FermiBufs {
-  float *ae, *h2a, *h2b, *g2, *x1, *ha, *hb, *m, *cadd, *wscr;
-  JqHeadBufs head;
-};
 
 static JqHeadDims fermi_head_dims(const FermiDims& d, const jaqmc_ferminet_config* c) {
   JqHeadDims hd;
@@ -68,7 +57,7 @@ static JqHeadDims fermi_head_dims(const FermiDims& d, const jaqmc_ferminet_confi
   return hd;
 }
 
-static void fermi_carve(const FermiDims& d, const jaqmc_ferminet_config* c, long long W, JqArena& ar, FermiBufs* b) {
+void jq_fermi_carve_backbone(const FermiDims& d, long long W, JqArena& ar, FermiBufs* b) {
   long long n = d.n, nn = (long long)d.n * d.n;
   bool pairs = d.L > 1;
   b->ae = ar.take<float>(W * n * d.C1 * d.f1);
@@ -86,42 +75,27 @@ static void fermi_carve(const FermiDims& d, const jaqmc_ferminet_config* c, long
     int nmax = d.d1max > d.D * d.n ? d.d1max : d.D * d.n;
     b->wscr = ar.take<float>(jq_dense_tc_scratch_floats(kmax, nmax));
   }
+}
+
+static void fermi_carve(const FermiDims& d, const jaqmc_ferminet_config* c, long long W, JqArena& ar, FermiBufs* b) {
+  jq_fermi_carve_backbone(d, W, ar, b);
   jq_head_carve(fermi_head_dims(d, c), W, ar, &b->head);
 }
 
-size_t jq_ferminet_ws_bytes(const jaqmc_ferminet_config* c, long long W, int track) {
-  FermiDims d;
-  if (fermi_dims(c, track, &d) != JQ_OK) return 0;
-  JqArena ar(nullptr, 0);
-  FermiBufs b;
-  fermi_carve(d, c, W, ar, &b);
-  return ar.off;
-}
-
-int jq_ferminet_forward(const jaqmc_ferminet_config* c, const jaqmc_ferminet_params* p, const jaqmc_system* sys,
-                        const float* electrons, long long W, int track, void* ws, size_t ws_bytes, JqWfOut out,
-                        cudaStream_t st) {
-  FermiDims d;
-  int rc = fermi_dims(c, track, &d);
-  if (rc != JQ_OK) return rc;
-  JQ_REQUIRE(sys && sys->atoms && sys->n_atoms == d.A, JQ_ERR_INVALID_ARGUMENT, "ferminet: system/atoms mismatch");
-  JqArena ar(ws, ws_bytes);
-  FermiBufs b;
-  fermi_carve(d, c, W, ar, &b);
-  JQ_REQUIRE(ar.ok(), JQ_ERR_WORKSPACE_TOO_SMALL, "ferminet: workspace %zu < %zu bytes", ws_bytes, ar.off);
+// FermiLayers on precomputed features: b.ae [W][n][C1][f1] (Local1), b.h2a [W][n*n][C2][fee] (Local2) -> *h_out
+// [W][n][C][hidden_single[-1]].  Shared by the molecular and the periodic FermiNet.
+int jq_fermi_backbone(const FermiDims& d, const jaqmc_ferminet_params* p, long long W, int track, const FermiBufs& b,
+                      cudaStream_t st, float** h_out) {
+  int rc;
   const int n = d.n, C = d.C;
   for (int l = 0; l < d.L; ++l)
     JQ_REQUIRE(p->single_kernel[l] && p->single_bias[l] && (l == d.L - 1 || (p->double_kernel[l] && p->double_bias[l])),
                JQ_ERR_INVALID_ARGUMENT, "ferminet: null parameter in layer %d", l);
-  // features: ae Local1 [W][n][C1][4A], ee Local2 [W][n*n][C2][4] (into h2a)
-  if ((rc = jq_launch_mol_features(electrons, sys->atoms, (int)W, d.sp, d.A, /*rescale=*/0, track, /*spin_column=*/0, b.ae, b.h2a, st)))
-    return rc;
-
   float* h2 = b.h2a;
   float* h2n = b.h2b;
   float* h = b.ha;
   float* hn = b.hb;
-  int d2prev = 4, d1prev = d.f1;
+  int d2prev = d.fee, d1prev = d.f1;
   for (int l = 0; l < d.L; ++l) {
     const int fg = d.nch * d2prev;
     if ((rc = jq_launch_pair_mean(h2, b.g2, (int)W, d.sp, d2prev, track, st))) return rc;
@@ -204,6 +178,36 @@ int jq_ferminet_forward(const jaqmc_ferminet_config* c, const jaqmc_ferminet_par
     }
   }
 
+  *h_out = h;
+  return JQ_OK;
+}
+
+size_t jq_ferminet_ws_bytes(const jaqmc_ferminet_config* c, long long W, int track) {
+  FermiDims d;
+  if (jq_fermi_dims(c, track, 4, 4, &d) != JQ_OK) return 0;
+  JqArena ar(nullptr, 0);
+  FermiBufs b;
+  fermi_carve(d, c, W, ar, &b);
+  return ar.off;
+}
+
+int jq_ferminet_forward(const jaqmc_ferminet_config* c, const jaqmc_ferminet_params* p, const jaqmc_system* sys,
+                        const float* electrons, long long W, int track, void* ws, size_t ws_bytes, JqWfOut out,
+                        cudaStream_t st) {
+  FermiDims d;
+  int rc = jq_fermi_dims(c, track, 4, 4, &d);
+  if (rc != JQ_OK) return rc;
+  JQ_REQUIRE(sys && sys->atoms && sys->n_atoms == d.A, JQ_ERR_INVALID_ARGUMENT, "ferminet: system/atoms mismatch");
+  JqArena ar(ws, ws_bytes);
+  FermiBufs b;
+  fermi_carve(d, c, W, ar, &b);
+  JQ_REQUIRE(ar.ok(), JQ_ERR_WORKSPACE_TOO_SMALL, "ferminet: workspace %zu < %zu bytes", ws_bytes, ar.off);
+  // features: ae Local1 [W][n][C1][4A], ee Local2 [W][n*n][C2][4] (into h2a)
+  if ((rc = jq_launch_mol_features(electrons, sys->atoms, (int)W, d.sp, d.A, /*rescale=*/0, track, /*spin_column=*/0, b.ae, b.h2a, st)))
+    return rc;
+
+  float* h = nullptr;
+  if ((rc = jq_fermi_backbone(d, p, W, track, b, st, &h))) return rc;
   jaqmc_head_params hp;
   memset(&hp, 0, sizeof(hp));
   for (int s = 0; s < 2; ++s) {

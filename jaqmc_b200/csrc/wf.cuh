@@ -46,3 +46,24 @@ int jq_psiformer_forward(const jaqmc_psiformer_config* c, const jaqmc_psiformer_
 // ---- Ewald (ewald.cu) ---------------------------------------------------------------------------
 int jq_launch_ewald(const jaqmc_ewald* ew, const float* electrons, long long W, int n_el, const float* atoms,
                     const float* charges, int n_at, float* e_pot, cudaStream_t st);
+
+// ---- FermiNet backbone shared by the molecular and periodic networks (ferminet.cu) -----------------
+struct FermiDims {
+  JqSpins sp;
+  int n, A, D, L, nch, C, C1, C2, f1, fee;  // f1 = input features per electron, fee = per pair
+  int d1[JQ_MAX_LAYERS], d2[JQ_MAX_LAYERS];  // widths after layer l
+  int d1max, d2max, in1;
+};
+
+struct FermiBufs {
+  float *ae, *h2a, *h2b, *g2, *x1, *ha, *hb, *m, *cadd, *wscr;
+  JqHeadBufs head;
+};
+
+int jq_fermi_dims(const jaqmc_ferminet_config* c, int track, int fat, int fee, FermiDims* o);
+void jq_fermi_carve_backbone(const FermiDims& d, long long W, JqArena& ar, FermiBufs* b);
+int jq_fermi_backbone(const FermiDims& d, const jaqmc_ferminet_params* p, long long W, int track, const FermiBufs& b,
+                      cudaStream_t st, float** h_out);
+int jq_launch_solid_features(const float* electrons, const float* prim_atoms, const float* sim_lattice,
+                             const float* prim_lattice, int W, int n, int A, int track, float* ae, float* r_ae, float* ee,
+                             cudaStream_t st);
