@@ -160,6 +160,23 @@ typedef struct {
   jaqmc_head_params head;
 } jaqmc_psiformer_params;
 
+/* ---- periodic FermiNet (solid) ------------------------------------------------------------------
+ * SolidWavefunction (app/solid/wavefunction.py:40-147): `tri` distance features with minimal symmetry (7 per primitive
+ * atom / per pair), FermiLayers, real + imaginary orbital projections, envelope on the periodic distance, Bloch
+ * phases exp(i k.r).  log psi is complex. */
+typedef struct {
+  jaqmc_ferminet_config net;      /* n_atoms = atoms of the PRIMITIVE cell (SolidData.primitive_atoms) */
+  float simulation_lattice[9];    /* rows are lattice vectors (host values) */
+  float primitive_lattice[9];
+} jaqmc_solid_config;
+
+typedef struct {
+  jaqmc_ferminet_params net;             /* backbone_layer/Dense_*, envelope_layer; net.orbital_kernel is unused */
+  const float* real_orbital_kernel[2];   /* real_orbital_layer/.../kernel (hidden, ndets, n) per spin channel */
+  const float* imag_orbital_kernel[2];   /* imag_orbital_layer/.../kernel */
+  const float* klist;                    /* (n, 3) k-point of every orbital (module attribute `klist`) */
+} jaqmc_solid_params;
+
 /* ---- generic wavefunction descriptor ---------------------------------------------------------- */
 typedef struct {
   int32_t kind;       /* JAQMC_WF_* */
@@ -173,36 +190,6 @@ typedef struct {
   const float* charges; /* (n_atoms,)  may be NULL where unused */
   int32_t n_atoms;
 } jaqmc_system;
-
-/* Workspace (bytes) that lets a call process all `n_walkers` walkers in one pass.  A smaller workspace is legal:
- * the library then tiles the walker axis, as long as one walker fits (else JAQMC_ERR_WORKSPACE_TOO_SMALL).
- * `track` = 0 for log|psi| only, 1 for value + gradient + Laplacian. */
-size_t jaqmc_b200_workspace_bytes(const jaqmc_wavefunction* wf, int64_t n_walkers, int track);
-
-/* Replaces vmap(wf.logpsi / wf.phase_logpsi) over the walker axis
- * (sampler/base.py:136-138; app/molecule/wavefunction/ferminet.py:98-124).
- *   electrons (n_walkers, n, 3) -> logpsi (n_walkers,), sign (n_walkers,) in {-1, 0, +1}. */
-int jaqmc_b200_logpsi(const jaqmc_wavefunction* wf, const jaqmc_system* sys, const float* electrons,
-                      int64_t n_walkers, float* logpsi, float* sign, void* workspace, size_t workspace_bytes,
-                      jaqmc_stream_t stream);
-
-/* Replaces the estimator half of EvaluationWorkStage.compute_step for the energy keys
- * (workflow/stage/evaluation.py:190-192): EuclideanKinetic in forward_laplacian mode
- * (estimator/kinetic/euclidean.py:114-135, laplacian/interpreter.py:392-438), the potential
- * (app/molecule/hamiltonian.py:9-22) and TotalEnergy (estimator/total_energy.py:36-60), vmapped over walkers.
- * Outputs (any may be NULL except logpsi/sign):
- *   grad (n_walkers, 3n) = d log|psi| / d r,   lap (n_walkers,) = laplacian of log|psi|,
- *   e_kin = -1/2 (lap + |grad|^2),  e_pot,  e_loc = e_kin + e_pot,
- *   sums (3,) += {sum e_loc, sum e_loc^2, count of finite e_loc} over this call's walkers (the per-device partial
- *   sums that precede the pmean of estimator/base.py:27-53); the caller zeroes it. */
-int jaqmc_b200_local_energy(const jaqmc_wavefunction* wf, const jaqmc_system* sys, const float* electrons,
-                            int64_t n_walkers, float* logpsi, float* sign, float* grad, float* lap, float* e_kin,
-                            float* e_pot, float* e_loc, float* sums, void* workspace, size_t workspace_bytes,
-                            jaqmc_stream_t stream);
-
-/* Replaces potential_energy (app/molecule/hamiltonian.py:9-22) vmapped over walkers. */
-int jaqmc_b200_coulomb(const jaqmc_system* sys, const float* electrons, int64_t n_walkers, int32_t n_electrons,
-                       float* e_pot, jaqmc_stream_t stream);
 
 /* ---- Ewald sum (solid-state potential) ---------------------------------------------------------
  * Precomputed by the host exactly as EwaldSum.__init__ does (estimator/ewald.py:50-110): all pointers are DEVICE
@@ -224,6 +211,52 @@ typedef struct {
  * supercell ions atoms (n_atoms,3) / charges (n_atoms,) -> e_pot (n_walkers,). */
 int jaqmc_b200_ewald(const jaqmc_ewald* ewald, const float* electrons, int64_t n_walkers, int32_t n_electrons,
                      const float* atoms, const float* charges, int32_t n_atoms, float* e_pot, jaqmc_stream_t stream);
+
+
+/* Workspace (bytes) that lets a call process all `n_walkers` walkers in one pass.  A smaller workspace is legal:
+ * the library then tiles the walker axis, as long as one walker fits (else JAQMC_ERR_WORKSPACE_TOO_SMALL).
+ * `track` = 0 for log|psi| only, 1 for value + gradient + Laplacian. */
+size_t jaqmc_b200_workspace_bytes(const jaqmc_wavefunction* wf, int64_t n_walkers, int track);
+
+/* Replaces vmap(wf.logpsi / wf.phase_logpsi) over the walker axis
+ * (sampler/base.py:136-138; app/molecule/wavefunction/ferminet.py:98-124).
+ *   electrons (n_walkers, n, 3) -> logpsi (n_walkers,), sign (n_walkers,) in {-1, 0, +1}.
+ * For JAQMC_WF_SOLID_FERMINET log psi is complex: logpsi receives its real part (what the sampler uses,
+ * sampler/mcmc.py:127) and `sign` the phase angle Im log psi in (-pi, pi]. */
+int jaqmc_b200_logpsi(const jaqmc_wavefunction* wf, const jaqmc_system* sys, const float* electrons,
+                      int64_t n_walkers, float* logpsi, float* sign, void* workspace, size_t workspace_bytes,
+                      jaqmc_stream_t stream);
+
+/* Replaces the estimator half of EvaluationWorkStage.compute_step for the energy keys
+ * (workflow/stage/evaluation.py:190-192): EuclideanKinetic in forward_laplacian mode
+ * (estimator/kinetic/euclidean.py:114-135, laplacian/interpreter.py:392-438), the potential
+ * (app/molecule/hamiltonian.py:9-22) and TotalEnergy (estimator/total_energy.py:36-60), vmapped over walkers.
+ * Outputs (any may be NULL except logpsi/sign):
+ *   grad (n_walkers, 3n) = d log|psi| / d r,   lap (n_walkers,) = laplacian of log|psi|,
+ *   e_kin = -1/2 (lap + |grad|^2),  e_pot,  e_loc = e_kin + e_pot,
+ *   sums (3,) += {sum e_loc, sum e_loc^2, count of finite e_loc} over this call's walkers (the per-device partial
+ *   sums that precede the pmean of estimator/base.py:27-53); the caller zeroes it. */
+int jaqmc_b200_local_energy(const jaqmc_wavefunction* wf, const jaqmc_system* sys, const float* electrons,
+                            int64_t n_walkers, float* logpsi, float* sign, float* grad, float* lap, float* e_kin,
+                            float* e_pot, float* e_loc, float* sums, void* workspace, size_t workspace_bytes,
+                            jaqmc_stream_t stream);
+
+/* Complex-valued counterpart of jaqmc_b200_local_energy for JAQMC_WF_SOLID_FERMINET: EuclideanKinetic on the complex
+ * log psi (estimator/kinetic/euclidean.py:114-135 with the complex square of kinetic/_common.py:61-73), the Ewald
+ * potential (app/solid/hamiltonian.py:18-56) and TotalEnergy.  `sys` holds the primitive-cell atoms the network sees;
+ * `ewald` / `cell_atoms` (n_cell_atoms,3) / `cell_charges` describe the simulation cell for the potential (ewald NULL:
+ * e_pot is not computed).  Complex outputs are interleaved (re, im):
+ *   logpsi (W,2), grad (W,3n,2), lap (W,2), e_kin (W,2), e_pot (W,), e_loc (W,2) = e_kin + e_pot,
+ *   sums (3,) += {sum Re e_loc, sum (Re e_loc)^2, finite count}.  Any output except logpsi may be NULL. */
+int jaqmc_b200_local_energy_complex(const jaqmc_wavefunction* wf, const jaqmc_system* sys, const jaqmc_ewald* ewald,
+                                    const float* cell_atoms, const float* cell_charges, int32_t n_cell_atoms,
+                                    const float* electrons, int64_t n_walkers, float* logpsi, float* grad, float* lap,
+                                    float* e_kin, float* e_pot, float* e_loc, float* sums, void* workspace,
+                                    size_t workspace_bytes, jaqmc_stream_t stream);
+
+/* Replaces potential_energy (app/molecule/hamiltonian.py:9-22) vmapped over walkers. */
+int jaqmc_b200_coulomb(const jaqmc_system* sys, const float* electrons, int64_t n_walkers, int32_t n_electrons,
+                       float* e_pot, jaqmc_stream_t stream);
 
 /* Replaces MCMCSampler.step's fori_loop of _mh_update (sampler/mcmc.py:96-137,167-180) for `n_steps` all-electron
  * moves with host-supplied noise:

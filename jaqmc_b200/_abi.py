@@ -142,6 +142,19 @@ class PsiformerParams(C.Structure):
     ]
 
 
+class SolidConfig(C.Structure):
+    _fields_ = [("net", FerminetConfig), ("simulation_lattice", C.c_float * 9), ("primitive_lattice", C.c_float * 9)]
+
+
+class SolidParams(C.Structure):
+    _fields_ = [
+        ("net", FerminetParams),
+        ("real_orbital_kernel", FloatP * 2),
+        ("imag_orbital_kernel", FloatP * 2),
+        ("klist", FloatP),
+    ]
+
+
 class Wavefunction(C.Structure):
     _fields_ = [("kind", C.c_int32), ("config", C.c_void_p), ("params", C.c_void_p)]
 
@@ -169,6 +182,11 @@ class Ewald(C.Structure):
 
 
 PROTOTYPES = {
+    "jaqmc_b200_local_energy_complex": (
+        C.c_int,
+        [C.POINTER(Wavefunction), C.POINTER(System), C.c_void_p, FloatP, FloatP, C.c_int32, FloatP, C.c_int64, FloatP,
+         FloatP, FloatP, FloatP, FloatP, FloatP, FloatP, C.c_void_p, C.c_size_t, C.c_void_p],
+    ),
     "jaqmc_b200_ewald": (
         C.c_int,
         [C.POINTER(Ewald), FloatP, C.c_int64, C.c_int32, FloatP, FloatP, C.c_int32, FloatP, C.c_void_p],

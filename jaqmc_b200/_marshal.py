@@ -255,3 +255,66 @@ def psiformer_handle(params, nspins, n_atoms, ndets=16, num_layers=4, num_heads=
             fan = h
     _fill_head(b, ps.head, p, n, n_atoms, ndets, hid, split, envelope, jastrow)
     return _wf_handle(_abi.WF_PSIFORMER, cfg, ps, b.keep)
+
+
+def solid_handle(params, nspins, n_prim_atoms, simulation_lattice, primitive_lattice, klist, ndets=16,
+                 hidden_dims_single=(256,) * 4, hidden_dims_double=(32,) * 4, envelope="abs_isotropic",
+                 orbitals_spin_split=True) -> Handle:
+    """Descriptor for ``SolidWavefunction`` (reference app/solid/wavefunction.py:40-147); ``klist`` (n, 3) on device."""
+    n_up, n_dn = int(nspins[0]), int(nspins[1])
+    n = n_up + n_dn
+    L = len(hidden_dims_single)
+    if L < 1 or L > _abi.MAX_LAYERS or len(hidden_dims_double) != L:
+        raise ValueError(f"hidden_dims_single/double must have the same length in [1, {_abi.MAX_LAYERS}]")
+    if envelope not in _abi.ENVELOPE:
+        raise ValueError(f"Unknown envelope: {envelope!r}")
+    nch = 2 if (n_up > 0 and n_dn > 0) else 1
+    split = bool(orbitals_spin_split) and nch == 2
+    p = params["params"] if "params" in params else params
+    cfg = _abi.SolidConfig()
+    net = cfg.net
+    net.n_up, net.n_dn, net.n_atoms, net.ndets, net.n_layers = n_up, n_dn, int(n_prim_atoms), int(ndets), L
+    for i in range(L):
+        net.hidden_single[i] = int(hidden_dims_single[i])
+        net.hidden_double[i] = int(hidden_dims_double[i])
+    net.envelope_type = _abi.ENVELOPE[envelope]
+    net.orbitals_spin_split = int(split)
+    for name, lat in (("simulation_lattice", simulation_lattice), ("primitive_lattice", primitive_lattice)):
+        vals = [float(v) for v in torch.as_tensor(lat).reshape(-1).tolist()]
+        if len(vals) != 9:
+            raise ValueError(f"{name}: expected a (3, 3) lattice")
+        for i, v in enumerate(vals):
+            getattr(cfg, name)[i] = v
+    ps = _abi.SolidParams()
+    b = _Binder()
+    bb = p["backbone_layer"]
+    d1, d2 = 7 * n_prim_atoms, 7
+    idx = 0
+    for layer in range(L):
+        h1 = int(hidden_dims_single[layer])
+        ps.net.single_kernel[layer] = b.leaf(bb, f"Dense_{idx}/kernel", (d1 * (1 + nch) + d2 * nch, h1))
+        ps.net.single_bias[layer] = b.leaf(bb, f"Dense_{idx}/bias", (h1,))
+        idx += 1
+        if layer < L - 1:
+            h2 = int(hidden_dims_double[layer])
+            ps.net.double_kernel[layer] = b.leaf(bb, f"Dense_{idx}/kernel", (d2, h2))
+            ps.net.double_bias[layer] = b.leaf(bb, f"Dense_{idx}/bias", (h2,))
+            idx += 1
+            d2 = h2
+        d1 = h1
+    for part, fld in (("real_orbital_layer", ps.real_orbital_kernel), ("imag_orbital_layer", ps.imag_orbital_kernel)):
+        ol = p[part]
+        if split:
+            for s_ in range(2):
+                fld[s_] = b.leaf(ol, f"SplitChannelDense_0/DenseGeneral_{s_}/kernel", (d1, ndets, n))
+        else:
+            fld[0] = b.leaf(ol, "DenseGeneral_0/kernel", (d1, ndets, n))
+    if envelope != "null":
+        el = p["envelope_layer"]
+        for s_, nm in enumerate(["_env_up", "_env_down"] if split else ["_env"]):
+            ps.net.env_pi[s_] = b.leaf(el, f"{nm}/pi", (n, n_prim_atoms, ndets))
+            ps.net.env_sigma[s_] = b.leaf(el, f"{nm}/sigma", (n, n_prim_atoms, ndets))
+    kl = _leaf(klist, "klist", (n, 3))
+    b.keep.append(kl)
+    ps.klist = kl.data_ptr()
+    return _wf_handle(_abi.WF_SOLID_FERMINET, cfg, ps, b.keep)

@@ -93,6 +93,29 @@ class Runtime:
         _abi.check(self.lib, rc)
         return out
 
+    def local_energy_complex(self, wf, system, electrons, ewald=None, cell_atoms=None, cell_charges=None, sums=None):
+        """Periodic (complex log psi) local energy: dict with complex64 logpsi / grad (W,3n) / lap / e_kin / e_loc and
+        float32 e_pot (present when ``ewald`` -- a ``jaqmc_b200.ewald.EwaldSum`` -- is given)."""
+        self._check_tensor(electrons, "electrons")
+        W, n = electrons.shape[0], electrons.shape[1]
+        f = lambda *s: torch.empty(*s, dtype=torch.float32, device=self.device)  # noqa: E731
+        raw = dict(logpsi=f(W, 2), grad=f(W, 3 * n, 2), lap=f(W, 2), e_kin=f(W, 2), e_loc=f(W, 2))
+        e_pot = f(W) if ewald is not None else None
+        if ewald is not None:
+            self._check_tensor(cell_atoms, "cell_atoms")
+            self._check_tensor(cell_charges, "cell_charges")
+        ws = self._ws_for(wf, W, True)
+        rc = self.lib.jaqmc_b200_local_energy_complex(
+            C.byref(wf.struct), C.byref(system.struct), C.byref(ewald._struct) if ewald is not None else None,
+            _ptr(cell_atoms), _ptr(cell_charges), 0 if cell_atoms is None else cell_atoms.shape[0], _ptr(electrons), W,
+            _ptr(raw["logpsi"]), _ptr(raw["grad"]), _ptr(raw["lap"]), _ptr(raw["e_kin"]), _ptr(e_pot), _ptr(raw["e_loc"]),
+            _ptr(sums), _ptr(ws), ws.numel(), self._stream())
+        _abi.check(self.lib, rc)
+        out = {k: torch.view_as_complex(v) for k, v in raw.items()}
+        if e_pot is not None:
+            out["e_pot"] = e_pot
+        return out
+
     def coulomb(self, system, electrons):
         self._check_tensor(electrons, "electrons")
         W, n = electrons.shape[0], electrons.shape[1]

@@ -112,6 +112,10 @@ static int wf_n_electrons(const jaqmc_wavefunction* wf) {
       auto* c = (const jaqmc_psiformer_config*)wf->config;
       return c->n_up + c->n_dn;
     }
+    case JAQMC_WF_SOLID_FERMINET: {
+      auto* c = (const jaqmc_solid_config*)wf->config;
+      return c->net.n_up + c->net.n_dn;
+    }
     default:
       return -1;
   }
@@ -125,6 +129,8 @@ static size_t wf_ws_bytes(const jaqmc_wavefunction* wf, long long W, int track) 
       return jq_lapnet_ws_bytes((const jaqmc_lapnet_config*)wf->config, W, track);
     case JAQMC_WF_PSIFORMER:
       return jq_psiformer_ws_bytes((const jaqmc_psiformer_config*)wf->config, W, track);
+    case JAQMC_WF_SOLID_FERMINET:
+      return jq_solid_ws_bytes((const jaqmc_solid_config*)wf->config, W, track);
     default:
       return 0;
   }
@@ -142,6 +148,13 @@ static int wf_forward(const jaqmc_wavefunction* wf, const jaqmc_system* sys, con
     case JAQMC_WF_PSIFORMER:
       return jq_psiformer_forward((const jaqmc_psiformer_config*)wf->config, (const jaqmc_psiformer_params*)wf->params,
                                   sys, electrons, W, track, ws, ws_bytes, out, st);
+    case JAQMC_WF_SOLID_FERMINET: {
+      // value path only (sampling): real part -> logpsi, phase angle -> sign
+      JQ_REQUIRE(track == 0, JQ_ERR_UNSUPPORTED, "solid: use jaqmc_b200_local_energy_complex for the tracked path");
+      JqWfOutC oc = {out.logpsi, out.sign, nullptr, nullptr, nullptr};
+      return jq_solid_forward((const jaqmc_solid_config*)wf->config, (const jaqmc_solid_params*)wf->params, sys,
+                              electrons, W, 0, ws, ws_bytes, oc, st);
+    }
     default:
       jq_set_error("wavefunction kind %d is not implemented", wf->kind);
       return JQ_ERR_UNSUPPORTED;
@@ -188,6 +201,7 @@ extern "C" size_t jaqmc_b200_workspace_bytes(const jaqmc_wavefunction* wf, int64
     mh = ar.off;
   }
   size_t api = api_scratch_bytes(n, n_walkers);
+  if (wf->kind == JAQMC_WF_SOLID_FERMINET) api = 2 * api + 4 * 256 + (size_t)n_walkers * 16;  // complex grad / lap / e_kin, logpsi planes
   return wf_ws_bytes(wf, n_walkers, track) + (api > mh ? api : mh) + 256;
 }
 
@@ -302,6 +316,95 @@ extern "C" int jaqmc_b200_local_energy(const jaqmc_wavefunction* wf, const jaqmc
   if (rc) return rc;
   if (e_loc || sums) {
     JQ_LAUNCH(k_energy_finalize, dim3(jq_cdiv(W, FIN_TILE)), dim3(FIN_TILE), 0, st, ek, ep, e_loc, sums, W);
+    JQ_CHECK_LAUNCH();
+  }
+  return JQ_OK;
+}
+
+// e_loc = e_kin (complex) + e_pot and the partial sums of its real part
+__global__ void k_energy_finalize_c(const float* __restrict__ e_kin, const float* __restrict__ e_pot,
+                                    float* __restrict__ e_loc, float* __restrict__ sums, long long W) {
+  __shared__ float buf[FIN_TILE];
+  const long long w0 = (long long)blockIdx.x * FIN_TILE;
+  const int nw = (int)((W - w0 < FIN_TILE) ? W - w0 : FIN_TILE);
+  for (int t = threadIdx.x; t < nw; t += blockDim.x) {
+    const float er = e_kin[2 * (w0 + t)] + (e_pot ? e_pot[w0 + t] : 0.f);
+    if (e_loc) {
+      e_loc[2 * (w0 + t)] = er;
+      e_loc[2 * (w0 + t) + 1] = e_kin[2 * (w0 + t) + 1];
+    }
+    buf[t] = er;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0 && sums) {
+    float s = 0.f, s2 = 0.f, c = 0.f;
+    for (int t = 0; t < nw; ++t) {
+      float e = buf[t];
+      if (isfinite(e)) {
+        s += e;
+        s2 = fmaf(e, e, s2);
+        c += 1.f;
+      }
+    }
+    JQ_ATOMIC_ADD(sums + 0, s);
+    JQ_ATOMIC_ADD(sums + 1, s2);
+    JQ_ATOMIC_ADD(sums + 2, c);
+  }
+}
+
+// interleave two planes into (re, im) pairs
+__global__ void k_interleave2(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ o, long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    o[2 * i] = a[i];
+    o[2 * i + 1] = b[i];
+  }
+}
+
+extern "C" int jaqmc_b200_local_energy_complex(const jaqmc_wavefunction* wf, const jaqmc_system* sys,
+                                               const jaqmc_ewald* ewald, const float* cell_atoms,
+                                               const float* cell_charges, int32_t n_cell_atoms, const float* electrons,
+                                               int64_t n_walkers, float* logpsi, float* grad, float* lap, float* e_kin,
+                                               float* e_pot, float* e_loc, float* sums, void* workspace,
+                                               size_t workspace_bytes, jaqmc_stream_t stream) {
+  JQ_REQUIRE(wf && wf->config && wf->params, JQ_ERR_INVALID_ARGUMENT, "null wavefunction descriptor");
+  JQ_REQUIRE(wf->kind == JAQMC_WF_SOLID_FERMINET, JQ_ERR_UNSUPPORTED,
+             "local_energy_complex: wavefunction kind %d has a real log psi; use jaqmc_b200_local_energy", wf->kind);
+  JQ_REQUIRE(n_walkers >= 0 && (n_walkers == 0 || (electrons && logpsi)), JQ_ERR_INVALID_ARGUMENT,
+             "local_energy_complex: null buffer");
+  JQ_REQUIRE(!ewald || (cell_atoms && cell_charges && n_cell_atoms >= 1), JQ_ERR_INVALID_ARGUMENT,
+             "local_energy_complex: the Ewald potential needs the simulation-cell atoms and charges");
+  JQ_REQUIRE(!e_pot || ewald, JQ_ERR_INVALID_ARGUMENT, "local_energy_complex: e_pot requested without an Ewald descriptor");
+  if (n_walkers == 0) return JQ_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int n = wf_n_electrons(wf);
+  const long long W = n_walkers;
+  JqArena ar(workspace, workspace_bytes);
+  float* lp_re = ar.take<float>(W);
+  float* lp_im = ar.take<float>(W);
+  float* g = grad ? grad : ar.take<float>(W * 3 * n * 2);
+  float* lpc = lap ? lap : ar.take<float>(W * 2);
+  float* ek = e_kin ? e_kin : ar.take<float>(W * 2);
+  float* ep = e_pot ? e_pot : (ewald ? ar.take<float>(W) : nullptr);
+  JQ_REQUIRE(workspace && ar.off <= workspace_bytes, JQ_ERR_WORKSPACE_TOO_SMALL, "local_energy_complex: workspace too small");
+  size_t avail = workspace_bytes - ar.off;
+  long long tile = fit_tile(wf, W, 1, avail);
+  JQ_REQUIRE(tile >= 1, JQ_ERR_WORKSPACE_TOO_SMALL,
+             "local_energy_complex: workspace of %zu bytes cannot hold one walker", workspace_bytes);
+  for (long long w0 = 0; w0 < W; w0 += tile) {
+    long long wc = (W - w0 < tile) ? W - w0 : tile;
+    JqWfOutC out = {lp_re + w0, lp_im + w0, g + w0 * 3 * n * 2, lpc + w0 * 2, ek + w0 * 2};
+    int rc = jq_solid_forward((const jaqmc_solid_config*)wf->config, (const jaqmc_solid_params*)wf->params, sys,
+                              electrons + w0 * 3 * n, wc, 1, ar.base + ar.off, avail, out, st);
+    if (rc) return rc;
+  }
+  JQ_LAUNCH(k_interleave2, dim3(jq_cdiv(W, 256)), dim3(256), 0, st, lp_re, lp_im, logpsi, W);
+  JQ_CHECK_LAUNCH();
+  if (ewald) {
+    int rc = jq_launch_ewald(ewald, electrons, W, n, cell_atoms, cell_charges, n_cell_atoms, ep, st);
+    if (rc) return rc;
+  }
+  if (e_loc || sums) {
+    JQ_LAUNCH(k_energy_finalize_c, dim3(jq_cdiv(W, FIN_TILE)), dim3(FIN_TILE), 0, st, ek, ep, e_loc, sums, W);
     JQ_CHECK_LAUNCH();
   }
   return JQ_OK;

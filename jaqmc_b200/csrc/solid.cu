@@ -1,0 +1,520 @@
+// Periodic (solid-state) FermiNet: complex orbitals, Bloch phases, complex multi-determinant LogDet with its
+// forward-Laplacian rule, and the pipeline that composes them.
+//
+// Reference semantics: app/solid/wavefunction.py:91-147 (SolidWavefunction: features -> FermiLayers -> real + i imag
+// orbital projections -> x envelope(r_ae) -> x exp(i k.r) -> LogDet), output/logdet.py:53-79 (complex branch: max over
+// the real parts, complex log-sum-exp), laplacian/primitives/slogdet.py:46-72 (complex rule: ld = log|det| + i arg det,
+// ld_J = tr(A^-1 dA), ld_L = tr(A^-1 A_L) - sum_k tr((A^-1 dA_k)^2), all complex), estimator/kinetic/_common.py:61-73
+// (E_kin = -1/2 (lap + sum_k J_k^2) with the complex square).
+// Complex tensors are stored as two float planes (re, im) with the layouts of their real counterparts.
+#include "wf.cuh"
+
+// ------------------------------------------------------------------------------------------------
+// (orb_r + i orb_i)[w][j][c][d*n+i] *= envelope(j, i, d) * exp(i k_i . r_j)     in place, product rule.
+// envelope E = sum_I pi exp(-|sigma| sd_I) on the periodic distance sd = r_ae (Local1, rows {x, 3 J, L} per electron).
+// F = E P,  dF_a = (dE_a + i k_a E) P,  lap F = (lap E - |k|^2 E + 2 i k . dE) P.      One item per (w, j, d, i).
+// ------------------------------------------------------------------------------------------------
+__global__ void k_solid_orb_factor(float* __restrict__ orb_r, float* __restrict__ orb_i, const float* __restrict__ el,
+                                   const float* __restrict__ r_ae, const float* __restrict__ klist, JqEnvelopeArgs env,
+                                   long long items, JqSpins sp, int A, int D, int track) {
+  const int n = sp.n();
+  const int DN = D * n;
+  const int C = track ? 3 * n + 2 : 1, C1 = track ? 5 : 1;
+  for (long long it = (long long)blockIdx.x * blockDim.x + threadIdx.x; it < items;
+       it += (long long)gridDim.x * blockDim.x) {
+    const int col = (int)(it % DN);
+    const long long g = it / DN;  // (w, j)
+    const int j = (int)(g % n);
+    const int d = col / n, i = col % n;
+    const int ch = (env.pi[1] != nullptr) ? sp.chan_of(j) : 0;
+    const float* pi = env.pi[ch];
+    const float* sg = env.sigma[ch];
+    const float* ra = r_ae + g * C1 * A;  // component c of atom I at ra[c*A + I]
+    float E = (env.type == 2) ? 1.f : 0.f, dE[3] = {0.f, 0.f, 0.f}, lE = 0.f;
+    if (env.type != 2)
+      for (int I = 0; I < A; ++I) {
+        float s = sg[(i * A + I) * D + d];
+        if (env.type == 1) s = fabsf(s);
+        const float t = pi[(i * A + I) * D + d] * expf(-s * ra[I]);
+        E += t;
+        if (track) {
+          float g2 = 0.f;
+          for (int a = 0; a < 3; ++a) {
+            const float da = ra[(1 + a) * A + I];
+            dE[a] = fmaf(-s * t, da, dE[a]);
+            g2 = fmaf(da, da, g2);
+          }
+          lE += t * (s * s * g2 - s * ra[4 * A + I]);
+        }
+      }
+    const float* e = el + g * 3;
+    const float k0 = klist[3 * i], k1 = klist[3 * i + 1], k2 = klist[3 * i + 2];
+    float ps, pc;
+    sincosf_(k0 * e[0] + k1 * e[1] + k2 * e[2], &ps, &pc);
+    // F = (fr, fi);  dF_a = (gr[a], gi[a]);  lap F = (lr, li)
+    const float fr = E * pc, fi = E * ps;
+    const float kk[3] = {k0, k1, k2};
+    float gr[3], gi[3], lr = 0.f, li = 0.f;
+    if (track) {
+      float kdE = 0.f;
+      for (int a = 0; a < 3; ++a) {
+        // (dE + i k E)(pc + i ps)
+        gr[a] = dE[a] * pc - kk[a] * E * ps;
+        gi[a] = dE[a] * ps + kk[a] * E * pc;
+        kdE = fmaf(kk[a], dE[a], kdE);
+      }
+      const float ar = lE - (k0 * k0 + k1 * k1 + k2 * k2) * E, ai = 2.f * kdE;
+      lr = ar * pc - ai * ps;
+      li = ar * ps + ai * pc;
+    }
+    float* pr = orb_r + g * (long long)C * DN + col;
+    float* pq = orb_i + g * (long long)C * DN + col;
+    const float o0r = pr[0], o0i = pq[0];
+    if (track) {
+      float cr = 0.f, ci = 0.f;  // sum_a O_{own a} dF_a
+      for (int a = 0; a < 3; ++a) {
+        const float ur = pr[(long long)(1 + 3 * j + a) * DN], ui = pq[(long long)(1 + 3 * j + a) * DN];
+        cr += ur * gr[a] - ui * gi[a];
+        ci += ur * gi[a] + ui * gr[a];
+      }
+      const float olr = pr[(long long)(C - 1) * DN], oli = pq[(long long)(C - 1) * DN];
+      pr[(long long)(C - 1) * DN] = olr * fr - oli * fi + o0r * lr - o0i * li + 2.f * cr;
+      pq[(long long)(C - 1) * DN] = olr * fi + oli * fr + o0r * li + o0i * lr + 2.f * ci;
+      for (int c = 1; c < C - 1; ++c) {
+        const float ur = pr[(long long)c * DN], ui = pq[(long long)c * DN];
+        float vr = ur * fr - ui * fi, vi = ur * fi + ui * fr;
+        const int k = c - 1;
+        if (k / 3 == j) {
+          vr += o0r * gr[k % 3] - o0i * gi[k % 3];
+          vi += o0r * gi[k % 3] + o0i * gr[k % 3];
+        }
+        pr[(long long)c * DN] = vr;
+        pq[(long long)c * DN] = vi;
+      }
+    }
+    pr[0] = o0r * fr - o0i * fi;
+    pq[0] = o0r * fi + o0i * fr;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// complex slogdet + forward-Laplacian rule.  One block per (walker, group of DB determinants); same scheme as the
+// real kernel (logdet.cu) in complex arithmetic: Gauss-Jordan with partial pivoting on |z|,
+//   log det = sum log|p| + i (sum arg p + pi * swaps),  M = A^-1 dA_c,  ld_J[c] = tr M,  ld_L = tr(A^-1 A_L) - sum_k tr(M_k^2).
+// Shared (floats): logabs[DB] arg[DB] (double) | inv_r inv_i [DB][nn] | colp_r colp_i [DB][n] | piv[DB][n] |
+//                  pv_r pv_i [DB] | trL_r trL_i t2_r t2_i [DB] | J_r J_i M_r M_i [DB][nn] | p1r p1i p2r p2i [DB][n]
+// ------------------------------------------------------------------------------------------------
+__global__ void k_logdet_c(const float* __restrict__ orb_r, const float* __restrict__ orb_i, int n, int D, int C, int DB,
+                           float* __restrict__ det_ld, float* __restrict__ det_grad, float* __restrict__ det_lap) {
+  JQ_DYN_SMEM(float, sm);
+  const int nn = n * n;
+  const int K = C - 2;
+  const int KT = (C > 1) ? C - 1 : 0;
+  double* logabs = reinterpret_cast<double*>(sm);
+  double* argsum = logabs + DB;
+  float* inv_r = reinterpret_cast<float*>(argsum + DB);
+  float* inv_i = inv_r + (size_t)DB * nn;
+  float* colp_r = inv_i + (size_t)DB * nn;
+  float* colp_i = colp_r + DB * n;
+  int* piv = reinterpret_cast<int*>(colp_i + DB * n);
+  float* pv_r = reinterpret_cast<float*>(piv + DB * n);
+  float* pv_i = pv_r + DB;
+  float* trL_r = pv_i + DB;
+  float* trL_i = trL_r + DB;
+  float* t2_r = trL_i + DB;
+  float* t2_i = t2_r + DB;
+  float* J_r = t2_i + DB;
+  float* J_i = J_r + (size_t)DB * nn;
+  float* M_r = J_i + (size_t)DB * nn;
+  float* M_i = M_r + (size_t)DB * nn;
+  float* p1r = M_i + (size_t)DB * nn;
+  float* p1i = p1r + DB * n;
+  float* p2r = p1i + DB * n;
+  float* p2i = p2r + DB * n;
+  const int ngrp = (D + DB - 1) / DB;
+  const long long w = blockIdx.x / ngrp;
+  const int d0 = (int)(blockIdx.x % ngrp) * DB;
+  const int db = (D - d0 < DB) ? D - d0 : DB;
+  const int DN = D * n;
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const bool need_inv = (C > 1);
+  const long long base = (w * n) * (long long)C * DN + d0 * n;  // (j, c, d, i) at base + (j*C + c)*DN + d*n + i
+
+  for (int q = tid; q < n * db * n; q += nt) {
+    const int j = q / (db * n), r = q % (db * n);
+    const int d = r / n, i = r % n;
+    inv_r[d * nn + j * n + i] = orb_r[base + (long long)j * C * DN + r];
+    inv_i[d * nn + j * n + i] = orb_i[base + (long long)j * C * DN + r];
+  }
+  for (int d = tid; d < db; d += nt) {
+    logabs[d] = 0.0;
+    argsum[d] = 0.0;
+    t2_r[d] = t2_i[d] = trL_r[d] = trL_i[d] = 0.f;
+  }
+  __syncthreads();
+  for (int p = 0; p < n; ++p) {
+    for (int d = tid; d < db; d += nt) {
+      const float* ar = inv_r + d * nn;
+      const float* ai = inv_i + d * nn;
+      int r = p;
+      float best = ar[p * n + p] * ar[p * n + p] + ai[p * n + p] * ai[p * n + p];
+      for (int q = p + 1; q < n; ++q) {
+        float v = ar[q * n + p] * ar[q * n + p] + ai[q * n + p] * ai[q * n + p];
+        if (v > best) { best = v; r = q; }
+      }
+      piv[d * n + p] = r;
+      const float zr = ar[r * n + p], zi = ai[r * n + p];
+      logabs[d] += 0.5 * log((double)best);
+      argsum[d] += atan2((double)zi, (double)zr) + ((r != p) ? 3.14159265358979323846 : 0.0);
+      const float inv2 = 1.0f / best;  // 1/z = conj(z)/|z|^2
+      pv_r[d] = zr * inv2;
+      pv_i[d] = -zi * inv2;
+    }
+    __syncthreads();
+    for (int q = tid; q < db * n; q += nt) {
+      const int d = q / n, c = q % n;
+      const int r = piv[d * n + p];
+      if (r != p) {
+        float* ar = inv_r + d * nn;
+        float* ai = inv_i + d * nn;
+        float t = ar[p * n + c];
+        ar[p * n + c] = ar[r * n + c];
+        ar[r * n + c] = t;
+        t = ai[p * n + c];
+        ai[p * n + c] = ai[r * n + c];
+        ai[r * n + c] = t;
+      }
+    }
+    __syncthreads();
+    if (need_inv) {
+      for (int q = tid; q < db * n; q += nt) {
+        const int d = q / n, i = q % n;
+        colp_r[q] = inv_r[d * nn + i * n + p];
+        colp_i[q] = inv_i[d * nn + i * n + p];
+      }
+      __syncthreads();
+      for (int q = tid; q < db * n; q += nt) {
+        const int d = q / n, c = q % n;
+        float* ar = inv_r + d * nn + p * n + c;
+        float* ai = inv_i + d * nn + p * n + c;
+        const float xr = (c == p) ? 1.0f : *ar, xi = (c == p) ? 0.0f : *ai;
+        *ar = xr * pv_r[d] - xi * pv_i[d];
+        *ai = xr * pv_i[d] + xi * pv_r[d];
+      }
+      __syncthreads();
+      for (int q = tid; q < db * nn; q += nt) {
+        const int d = q / nn, rem = q % nn;
+        const int i = rem / n, c = rem % n;
+        if (i == p) continue;
+        float* ar = inv_r + d * nn;
+        float* ai = inv_i + d * nn;
+        const float br = (c == p) ? 0.f : ar[rem], bi = (c == p) ? 0.f : ai[rem];
+        const float cr = colp_r[d * n + i], ci = colp_i[d * n + i];
+        const float rr = ar[p * n + c], ri = ai[p * n + c];
+        ar[rem] = br - (cr * rr - ci * ri);
+        ai[rem] = bi - (cr * ri + ci * rr);
+      }
+      __syncthreads();
+    } else {
+      for (int q = tid; q < db * n; q += nt) {
+        const int d = q / n, i = q % n;
+        const float xr = inv_r[d * nn + i * n + p], xi = inv_i[d * nn + i * n + p];
+        colp_r[q] = xr * pv_r[d] - xi * pv_i[d];
+        colp_i[q] = xr * pv_i[d] + xi * pv_r[d];
+      }
+      __syncthreads();
+      for (int q = tid; q < db * nn; q += nt) {
+        const int d = q / nn, rem = q % nn;
+        const int i = rem / n, c = rem % n;
+        if (i <= p || c <= p) continue;
+        float* ar = inv_r + d * nn;
+        float* ai = inv_i + d * nn;
+        const float cr = colp_r[d * n + i], ci = colp_i[d * n + i];
+        const float rr = ar[p * n + c], ri = ai[p * n + c];
+        ar[rem] -= cr * rr - ci * ri;
+        ai[rem] -= cr * ri + ci * rr;
+      }
+      __syncthreads();
+    }
+  }
+  for (int d = tid; d < db; d += nt) {
+    det_ld[(w * D + d0 + d) * 2] = (float)logabs[d];
+    double a = fmod(argsum[d], 6.283185307179586476925286766559);
+    if (a > 3.14159265358979323846) a -= 6.283185307179586476925286766559;
+    if (a <= -3.14159265358979323846) a += 6.283185307179586476925286766559;
+    det_ld[(w * D + d0 + d) * 2 + 1] = (float)a;
+  }
+  if (!need_inv) return;
+  for (int p = n - 1; p >= 0; --p) {
+    for (int q = tid; q < db * n; q += nt) {
+      const int d = q / n, i = q % n;
+      const int r = piv[d * n + p];
+      if (r != p) {
+        float* ar = inv_r + d * nn;
+        float* ai = inv_i + d * nn;
+        float t = ar[i * n + p];
+        ar[i * n + p] = ar[i * n + r];
+        ar[i * n + r] = t;
+        t = ai[i * n + p];
+        ai[i * n + p] = ai[i * n + r];
+        ai[i * n + r] = t;
+      }
+    }
+    __syncthreads();
+  }
+  for (int kk = 0; kk < KT; ++kk) {
+    for (int q = tid; q < n * db * n; q += nt) {
+      const int j = q / (db * n), r = q % (db * n);
+      const int d = r / n, i = r % n;
+      const long long src = base + ((long long)j * C + (1 + kk)) * DN + r;
+      J_r[d * nn + j * n + i] = orb_r[src];
+      J_i[d * nn + j * n + i] = orb_i[src];
+    }
+    __syncthreads();
+    for (int q = tid; q < db * nn; q += nt) {
+      const int d = q / nn, rem = q % nn;
+      const int i = rem / n, i2 = rem % n;
+      const float* ir = inv_r + d * nn + i * n;
+      const float* ii = inv_i + d * nn + i * n;
+      const float* jr = J_r + d * nn + i2;
+      const float* ji = J_i + d * nn + i2;
+      float ar = 0.f, ai = 0.f;
+      for (int j = 0; j < n; ++j) {
+        const float xr = ir[j], xi = ii[j], yr = jr[j * n], yi = ji[j * n];
+        ar += xr * yr - xi * yi;
+        ai += xr * yi + xi * yr;
+      }
+      M_r[q] = ar;
+      M_i[q] = ai;
+    }
+    __syncthreads();
+    for (int q = tid; q < db * n; q += nt) {
+      const int d = q / n, i = q % n;
+      const float* mr = M_r + d * nn;
+      const float* mi = M_i + d * nn;
+      float ar = 0.f, ai = 0.f;
+      for (int i2 = 0; i2 < n; ++i2) {
+        const float xr = mr[i * n + i2], xi = mi[i * n + i2], yr = mr[i2 * n + i], yi = mi[i2 * n + i];
+        ar += xr * yr - xi * yi;
+        ai += xr * yi + xi * yr;
+      }
+      p1r[q] = mr[i * n + i];
+      p1i[q] = mi[i * n + i];
+      p2r[q] = ar;
+      p2i[q] = ai;
+    }
+    __syncthreads();
+    for (int d = tid; d < db; d += nt) {
+      float s1r = 0.f, s1i = 0.f, s2r = 0.f, s2i = 0.f;
+      for (int i = 0; i < n; ++i) {
+        s1r += p1r[d * n + i];
+        s1i += p1i[d * n + i];
+        s2r += p2r[d * n + i];
+        s2i += p2i[d * n + i];
+      }
+      if (kk < K) {
+        det_grad[((w * D + d0 + d) * K + kk) * 2] = s1r;
+        det_grad[((w * D + d0 + d) * K + kk) * 2 + 1] = s1i;
+        t2_r[d] += s2r;
+        t2_i[d] += s2i;
+      } else {
+        trL_r[d] = s1r;
+        trL_i[d] = s1i;
+      }
+    }
+    __syncthreads();
+  }
+  for (int d = tid; d < db; d += nt) {
+    det_lap[(w * D + d0 + d) * 2] = trL_r[d] - t2_r[d];
+    det_lap[(w * D + d0 + d) * 2 + 1] = trL_i[d] - t2_i[d];
+  }
+}
+
+// complex log-sum-exp over determinants -> log psi (re, im), grad (3n complex), lap (complex), E_kin (complex)
+__global__ void k_logdet_combine_c(const float* __restrict__ det_ld, const float* __restrict__ det_grad,
+                                   const float* __restrict__ det_lap, int W, int n, int D, int track,
+                                   float* __restrict__ logpsi_re, float* __restrict__ logpsi_im, float* __restrict__ grad,
+                                   float* __restrict__ lap, float* __restrict__ e_kin) {
+  const int K = 3 * n;
+  for (long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x; w < W;
+       w += (long long)gridDim.x * blockDim.x) {
+    const float* ld = det_ld + w * D * 2;
+    float lmax = ld[0];
+    for (int d = 1; d < D; ++d) lmax = fmaxf(lmax, ld[2 * d]);
+    float sr = 0.f, si = 0.f;
+    for (int d = 0; d < D; ++d) {
+      const float m = expf(ld[2 * d] - lmax);
+      float sn, cs;
+      sincosf_(ld[2 * d + 1], &sn, &cs);
+      sr = fmaf(m, cs, sr);
+      si = fmaf(m, sn, si);
+    }
+    const float s2 = sr * sr + si * si;
+    logpsi_re[w] = 0.5f * logf(s2) + lmax;
+    logpsi_im[w] = atan2f(si, sr);
+    if (!track) continue;
+    const float* g = det_grad + w * D * K * 2;
+    const float inv2 = 1.0f / s2;
+    float alr = 0.f, ali = 0.f;  // sum_d w_d (lap_d + sum_k g_dk^2)
+    for (int d = 0; d < D; ++d) {
+      const float m = expf(ld[2 * d] - lmax);
+      float sn, cs;
+      sincosf_(ld[2 * d + 1], &sn, &cs);
+      const float er = m * cs, ei = m * sn;  // exp(ld_d - lmax)
+      const float wr = (er * sr + ei * si) * inv2, wi = (ei * sr - er * si) * inv2;  // / s
+      float qr = det_lap[(w * D + d) * 2], qi = det_lap[(w * D + d) * 2 + 1];
+      for (int k = 0; k < K; ++k) {
+        const float xr = g[(d * K + k) * 2], xi = g[(d * K + k) * 2 + 1];
+        qr += xr * xr - xi * xi;
+        qi += 2.f * xr * xi;
+      }
+      alr += wr * qr - wi * qi;
+      ali += wr * qi + wi * qr;
+    }
+    float ggr = 0.f, ggi = 0.f;
+    for (int k = 0; k < K; ++k) {
+      float gr = 0.f, gi = 0.f;
+      for (int d = 0; d < D; ++d) {
+        const float m = expf(ld[2 * d] - lmax);
+        float sn, cs;
+        sincosf_(ld[2 * d + 1], &sn, &cs);
+        const float er = m * cs, ei = m * sn;
+        const float wr = (er * sr + ei * si) * inv2, wi = (ei * sr - er * si) * inv2;
+        const float xr = g[(d * K + k) * 2], xi = g[(d * K + k) * 2 + 1];
+        gr += wr * xr - wi * xi;
+        gi += wr * xi + wi * xr;
+      }
+      grad[(w * K + k) * 2] = gr;
+      grad[(w * K + k) * 2 + 1] = gi;
+      ggr += gr * gr - gi * gi;
+      ggi += 2.f * gr * gi;
+    }
+    const float lr = alr - ggr, li = ali - ggi;
+    lap[2 * w] = lr;
+    lap[2 * w + 1] = li;
+    e_kin[2 * w] = -0.5f * (lr + ggr);
+    e_kin[2 * w + 1] = -0.5f * (li + ggi);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// pipeline
+// ------------------------------------------------------------------------------------------------
+namespace {
+struct SolidBufs {
+  FermiBufs f;
+  float *r_ae, *orb_r, *orb_i, *det_ld, *det_grad, *det_lap;
+};
+
+void solid_carve(const FermiDims& d, long long W, JqArena& ar, SolidBufs* b) {
+  const long long n = d.n;
+  jq_fermi_carve_backbone(d, W, ar, &b->f);
+  b->r_ae = ar.take<float>(W * n * d.C1 * d.A);
+  b->orb_r = ar.take<float>(W * n * d.C * d.D * n);
+  b->orb_i = ar.take<float>(W * n * d.C * d.D * n);
+  b->det_ld = ar.take<float>(W * d.D * 2);
+  b->det_grad = ar.take<float>(W * d.D * (d.C > 1 ? 3 * n : 1) * 2);
+  b->det_lap = ar.take<float>(W * d.D * 2);
+}
+
+int solid_dims(const jaqmc_solid_config* c, int track, FermiDims* d) {
+  return jq_fermi_dims(&c->net, track, 7, 7, d);
+}
+
+size_t logdet_c_smem(int db, int n) {
+  const size_t nn = (size_t)n * n;
+  return 16 * (size_t)db + sizeof(float) * (6 * db * nn + 7 * (size_t)db * n + 6 * (size_t)db) + 32;
+}
+}  // namespace
+
+size_t jq_solid_ws_bytes(const jaqmc_solid_config* c, long long W, int track) {
+  FermiDims d;
+  if (solid_dims(c, track, &d) != JQ_OK) return 0;
+  JqArena ar(nullptr, 0);
+  SolidBufs b;
+  solid_carve(d, W, ar, &b);
+  return ar.off;
+}
+
+int jq_solid_forward(const jaqmc_solid_config* c, const jaqmc_solid_params* p, const jaqmc_system* sys,
+                     const float* electrons, long long W, int track, void* ws, size_t ws_bytes, JqWfOutC out,
+                     cudaStream_t st) {
+  FermiDims d;
+  int rc = solid_dims(c, track, &d);
+  if (rc) return rc;
+  JQ_REQUIRE(sys && sys->atoms && sys->n_atoms == d.A, JQ_ERR_INVALID_ARGUMENT,
+             "solid: system must hold the %d primitive-cell atoms", d.A);
+  JQ_REQUIRE(p->klist, JQ_ERR_INVALID_ARGUMENT, "solid: null klist");
+  const bool split = c->net.orbitals_spin_split && d.nch == 2;
+  JQ_REQUIRE(p->real_orbital_kernel[0] && p->imag_orbital_kernel[0] &&
+                 (!split || (p->real_orbital_kernel[1] && p->imag_orbital_kernel[1])),
+             JQ_ERR_INVALID_ARGUMENT, "solid: null orbital kernel");
+  JQ_REQUIRE(c->net.envelope_type == JAQMC_ENVELOPE_NULL ||
+                 (p->net.env_pi[0] && p->net.env_sigma[0] && (!split || (p->net.env_pi[1] && p->net.env_sigma[1]))),
+             JQ_ERR_INVALID_ARGUMENT, "solid: null envelope parameter");
+  JqArena ar(ws, ws_bytes);
+  SolidBufs b;
+  solid_carve(d, W, ar, &b);
+  JQ_REQUIRE(ar.ok(), JQ_ERR_WORKSPACE_TOO_SMALL, "solid: workspace %zu < %zu bytes", ws_bytes, ar.off);
+  const int n = d.n;
+  if ((rc = jq_launch_solid_features(electrons, sys->atoms, c->simulation_lattice, c->primitive_lattice, (int)W, n, d.A,
+                                     track, b.f.ae, b.r_ae, b.f.h2a, st)))
+    return rc;
+  float* h = nullptr;
+  if ((rc = jq_fermi_backbone(d, &p->net, W, track, b.f, st, &h))) return rc;
+  // real and imaginary orbital projections (per spin channel DenseGeneral, no bias)
+  const int nchan = split ? 2 : 1;
+  for (int part = 0; part < 2; ++part)
+    for (int s = 0; s < nchan; ++s) {
+      JqDenseArgs a;
+      memset(&a, 0, sizeof(a));
+      a.src0 = h;
+      a.k0 = d.d1[d.L - 1];
+      a.w0 = part ? p->imag_orbital_kernel[s] : p->real_orbital_kernel[s];
+      a.out = part ? b.orb_i : b.orb_r;
+      a.wscratch = b.f.wscr;
+      a.N = d.D * n;
+      a.C = d.C;
+      a.n_tot = n;
+      a.j0 = split ? d.sp.lo(s) : 0;
+      a.n_sub = split ? d.sp.hi(s) - d.sp.lo(s) : n;
+      a.G = W * a.n_sub;
+      if ((rc = jq_launch_dense(a, st))) return rc;
+    }
+  JqEnvelopeArgs env;
+  env.type = c->net.envelope_type;
+  env.pi[0] = p->net.env_pi[0];
+  env.sigma[0] = p->net.env_sigma[0];
+  env.pi[1] = split ? p->net.env_pi[1] : nullptr;
+  env.sigma[1] = split ? p->net.env_sigma[1] : nullptr;
+  {
+    long long items = W * n * d.D * n;
+    int grid = jq_cdiv(items, 256);
+    if (grid > 148 * 32) grid = 148 * 32;
+    jq_prof_work(0.0, 16.0 * (double)items * d.C);
+    JQ_LAUNCH(k_solid_orb_factor, dim3(grid), dim3(256), 0, st, b.orb_r, b.orb_i, electrons, b.r_ae, p->klist, env, items,
+              d.sp, d.A, d.D, track);
+    JQ_CHECK_LAUNCH();
+  }
+  {
+    int DB = d.D;
+    while (DB > 1 && logdet_c_smem(DB, n) > 96 * 1024) DB = (DB + 1) / 2;
+    size_t smem = logdet_c_smem(DB, n);
+    JQ_REQUIRE(smem <= 200 * 1024, JQ_ERR_UNSUPPORTED, "solid: %d electrons need %zu bytes of shared memory", n, smem);
+#ifndef JAQMC_HOST_EMU
+    if (smem > 48 * 1024) {
+      cudaError_t e = cudaFuncSetAttribute(k_logdet_c, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      JQ_REQUIRE(e == cudaSuccess, JQ_ERR_CUDA, "solid: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    }
+#endif
+    const long long blocks = W * ((d.D + DB - 1) / DB);
+    jq_prof_work((double)W * d.D * 8.0 * n * n * n * (track ? 2 * (d.C - 1) + 1 : 0.34), 8.0 * (double)W * d.D * d.C * n * n);
+    JQ_LAUNCH(k_logdet_c, dim3((unsigned)blocks), dim3(256), smem, st, b.orb_r, b.orb_i, n, d.D, d.C, DB, b.det_ld,
+              b.det_grad, b.det_lap);
+    JQ_CHECK_LAUNCH();
+  }
+  JQ_LAUNCH(k_logdet_combine_c, dim3(jq_cdiv(W, 64)), dim3(64), 0, st, b.det_ld, b.det_grad, b.det_lap, (int)W, n, d.D,
+            track, out.logpsi_re, out.logpsi_im, out.grad, out.lap, out.e_kin);
+  JQ_CHECK_LAUNCH();
+  return JQ_OK;
+}

@@ -67,3 +67,16 @@ int jq_fermi_backbone(const FermiDims& d, const jaqmc_ferminet_params* p, long l
 int jq_launch_solid_features(const float* electrons, const float* prim_atoms, const float* sim_lattice,
                              const float* prim_lattice, int W, int n, int A, int track, float* ae, float* r_ae, float* ee,
                              cudaStream_t st);
+
+// ---- periodic FermiNet (solid.cu) ------------------------------------------------------------------
+struct JqWfOutC {
+  float* logpsi_re;  // [W]
+  float* logpsi_im;  // [W]
+  float* grad;       // [W][3n][2]  (track only)
+  float* lap;        // [W][2]
+  float* e_kin;      // [W][2]
+};
+size_t jq_solid_ws_bytes(const jaqmc_solid_config* c, long long W, int track);
+int jq_solid_forward(const jaqmc_solid_config* c, const jaqmc_solid_params* p, const jaqmc_system* sys,
+                     const float* electrons, long long W, int track, void* ws, size_t ws_bytes, JqWfOutC out,
+                     cudaStream_t st);

@@ -47,3 +47,17 @@ class BatchedData:
             per = t.shape[0] // world_size
             upd[name] = t[rank * per:(rank + 1) * per].contiguous()
         return BatchedData(self.data.merge(upd), list(self.fields_with_batch))
+
+
+@dataclass
+class SolidData:
+    """``electrons`` (W, n, 3), ``atoms`` (A_cell, 3) / ``charges`` (A_cell,) of the simulation cell,
+    ``primitive_atoms`` (A_prim, 3) -- reference app/solid/data.py:52-79."""
+
+    electrons: torch.Tensor
+    atoms: torch.Tensor
+    charges: torch.Tensor
+    primitive_atoms: torch.Tensor
+
+    def merge(self, updates: dict) -> "SolidData":
+        return dataclasses.replace(self, **updates)

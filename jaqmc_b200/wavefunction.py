@@ -311,3 +311,94 @@ class PsiformerWavefunction(Wavefunction):
                                          self.heads_dim, tuple(self.mlp_hidden_dims), self.layer_norm_mode,
                                          self.envelope, self.orbitals_spin_split, self.rescale,
                                          self.jastrow == "simple_ee")
+
+
+@dataclass
+class SolidWavefunction:
+    """Periodic FermiNet with complex orbitals (reference app/solid/wavefunction.py:40-147); same fields and defaults.
+    ``klist`` (n, 3) is the k-point of every orbital (set by the workflow after SCF in the reference)."""
+
+    nspins: tuple = (1, 1)
+    simulation_lattice: object = None
+    primitive_lattice: object = None
+    klist: object = None
+    ndets: int = 16
+    hidden_dims_single: list = field(default_factory=lambda: [256] * 4)
+    hidden_dims_double: list = field(default_factory=lambda: [32] * 4)
+    distance_type: str = "tri"
+    sym_type: str = "minimal"
+    envelope_type: str = "abs_isotropic"
+    orbitals_spin_split: bool = True
+    full_det: bool = True
+
+    def __post_init__(self):
+        if self.distance_type != "tri" or self.sym_type != "minimal":
+            raise NotImplementedError("only distance_type='tri' with sym_type='minimal' is implemented by the CUDA pipeline")
+        if len(self.hidden_dims_single) != len(self.hidden_dims_double):
+            raise ValueError("hidden_dims_single and hidden_dims_double must have the same length")
+        if self.simulation_lattice is None or self.primitive_lattice is None or self.klist is None:
+            raise ValueError("SolidWavefunction needs simulation_lattice, primitive_lattice and klist")
+
+    def init_params(self, data, rngs) -> dict:
+        """Flax-layout tree: backbone_layer/Dense_*, real_orbital_layer, imag_orbital_layer, envelope_layer."""
+        dev = data.electrons.device
+        g = rngs if isinstance(rngs, torch.Generator) else torch.Generator(device="cpu").manual_seed(int(rngs))
+        n_up, n_dn = self.nspins
+        n = n_up + n_dn
+        A = data.primitive_atoms.shape[0]
+        nch = 2 if (n_up > 0 and n_dn > 0) else 1
+        bb = {}
+        d1, d2 = 7 * A, 7
+        idx = 0
+        L = len(self.hidden_dims_single)
+        for layer in range(L):
+            h1 = self.hidden_dims_single[layer]
+            bb[f"Dense_{idx}"] = {"kernel": _lecun(g, dev, d1 * (1 + nch) + d2 * nch, h1), "bias": torch.zeros(h1, device=dev)}
+            idx += 1
+            if layer < L - 1:
+                h2 = self.hidden_dims_double[layer]
+                bb[f"Dense_{idx}"] = {"kernel": _lecun(g, dev, d2, h2), "bias": torch.zeros(h2, device=dev)}
+                idx += 1
+                d2 = h2
+            d1 = h1
+        split = self.orbitals_spin_split and nch == 2
+        head_r = _head_params(g, dev, self.nspins, A, self.ndets, d1, split, self.envelope_type, False, False, 1.0)
+        head_i = _head_params(g, dev, self.nspins, A, self.ndets, d1, split, "null", False, False, 1.0)
+        return {"params": {"backbone_layer": bb, "real_orbital_layer": head_r["orbital_layer"],
+                           "imag_orbital_layer": head_i["orbital_layer"], "envelope_layer": head_r["envelope_layer"]}}
+
+    def _handle(self, params, n_prim_atoms: int, device):
+        kl = torch.as_tensor(self.klist, dtype=torch.float32).to(device).contiguous()
+        return _marshal.solid_handle(params, self.nspins, n_prim_atoms, self.simulation_lattice, self.primitive_lattice,
+                                     kl, self.ndets, self.hidden_dims_single, self.hidden_dims_double,
+                                     self.envelope_type, self.orbitals_spin_split)
+
+    def evaluate(self, params, data) -> dict:
+        """``{"logpsi"}``: complex log psi per walker (reference LogDet complex output)."""
+        el, squeeze = _batched(data.electrons)
+        rt = runtime(el.device)
+        wf = self._handle(params, data.primitive_atoms.shape[0], el.device)
+        sysh = _marshal.system_handle(data.primitive_atoms, None)
+        re, im = rt.logpsi(wf, sysh, el)
+        lp = torch.complex(re, im)
+        return {"logpsi": lp[0] if squeeze else lp}
+
+    def logpsi(self, params, data):
+        return self.evaluate(params, data)["logpsi"]
+
+    def phase_logpsi(self, params, data):
+        lp = self.logpsi(params, data)
+        return torch.exp(1j * lp.imag), lp.real
+
+    def __call__(self, params, data):
+        return self.evaluate(params, data)
+
+    def local_energy(self, params, data, ewald=None, sums=None) -> dict:
+        """Complex value / gradient / Laplacian / kinetic energy per walker, plus the Ewald potential when an
+        :class:`jaqmc_b200.ewald.EwaldSum` of the simulation cell is given."""
+        el, _ = _batched(data.electrons)
+        rt = runtime(el.device)
+        wf = self._handle(params, data.primitive_atoms.shape[0], el.device)
+        sysh = _marshal.system_handle(data.primitive_atoms, None)
+        return rt.local_energy_complex(wf, sysh, el, ewald, data.atoms if ewald is not None else None,
+                                       data.charges if ewald is not None else None, sums=sums)
