@@ -177,6 +177,14 @@ typedef struct {
   const float* klist;                    /* (n, 3) k-point of every orbital (module attribute `klist`) */
 } jaqmc_solid_params;
 
+/* ---- HydrogenAtom demo wavefunction (app/hydrogen_atom.py:28-35): log psi = alpha * |electrons| ------------------ */
+typedef struct {
+  int32_t n_electrons; /* 1 in the reference app */
+} jaqmc_hydrogen_config;
+typedef struct {
+  const float* alpha;  /* params/alpha, scalar */
+} jaqmc_hydrogen_params;
+
 /* ---- generic wavefunction descriptor ---------------------------------------------------------- */
 typedef struct {
   int32_t kind;       /* JAQMC_WF_* */
@@ -268,6 +276,13 @@ int jaqmc_b200_mh_step(const jaqmc_wavefunction* wf, const jaqmc_system* sys, fl
                        int32_t logpsi_valid, const float* normals, const float* uniforms, const float* stddev,
                        int32_t n_steps, int64_t n_walkers, float* n_accept, uint8_t* accepted, void* workspace,
                        size_t workspace_bytes, jaqmc_stream_t stream);
+
+/* Same with proposals wrapped into the periodic cell (geometry/pbc.py:187-201 make_pbc_gaussian_proposal, used by
+ * `jaqmc solid train`): x2 = wrap_positions(x1 + normal * stddev, lattice); `lattice` is a HOST pointer to 9 floats. */
+int jaqmc_b200_mh_step_pbc(const jaqmc_wavefunction* wf, const jaqmc_system* sys, float* electrons, float* logpsi,
+                           int32_t logpsi_valid, const float* normals, const float* uniforms, const float* stddev,
+                           int32_t n_steps, int64_t n_walkers, float* n_accept, uint8_t* accepted, const float* lattice,
+                           void* workspace, size_t workspace_bytes, jaqmc_stream_t stream);
 
 /* One dense layer under the forward Laplacian: replaces nn.Dense traced by forward_laplacian
  * (laplacian/primitives/dot_general.py:377-407: one GEMM over the rows {x, J_1..J_K, L}, bias on the value row) fused

@@ -155,6 +155,14 @@ class SolidParams(C.Structure):
     ]
 
 
+class HydrogenConfig(C.Structure):
+    _fields_ = [("n_electrons", C.c_int32)]
+
+
+class HydrogenParams(C.Structure):
+    _fields_ = [("alpha", FloatP)]
+
+
 class Wavefunction(C.Structure):
     _fields_ = [("kind", C.c_int32), ("config", C.c_void_p), ("params", C.c_void_p)]
 
@@ -207,6 +215,11 @@ PROTOTYPES = {
         C.c_int,
         [C.POINTER(Wavefunction), C.POINTER(System), FloatP, FloatP, C.c_int32, FloatP, FloatP, FloatP, C.c_int32,
          C.c_int64, FloatP, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p],
+    ),
+    "jaqmc_b200_mh_step_pbc": (
+        C.c_int,
+        [C.POINTER(Wavefunction), C.POINTER(System), FloatP, FloatP, C.c_int32, FloatP, FloatP, FloatP, C.c_int32,
+         C.c_int64, FloatP, C.c_void_p, C.POINTER(C.c_float), C.c_void_p, C.c_size_t, C.c_void_p],
     ),
     "jaqmc_b200_dense_fl": (
         C.c_int,

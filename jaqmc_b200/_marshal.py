@@ -318,3 +318,13 @@ def solid_handle(params, nspins, n_prim_atoms, simulation_lattice, primitive_lat
     b.keep.append(kl)
     ps.klist = kl.data_ptr()
     return _wf_handle(_abi.WF_SOLID_FERMINET, cfg, ps, b.keep)
+
+
+def hydrogen_handle(params, n_electrons: int = 1) -> Handle:
+    """Descriptor for the ``HydrogenAtom`` demo wavefunction (reference app/hydrogen_atom.py:28-35)."""
+    p = params["params"] if "params" in params else params
+    alpha = _leaf(p["alpha"].reshape(1) if p["alpha"].dim() == 0 else p["alpha"], "alpha", (1,))
+    cfg = _abi.HydrogenConfig(int(n_electrons))
+    ps = _abi.HydrogenParams()
+    ps.alpha = alpha.data_ptr()
+    return _wf_handle(_abi.WF_HYDROGEN, cfg, ps, [alpha])

@@ -125,7 +125,7 @@ class Runtime:
         return e_pot
 
     def mh_step(self, wf, system, electrons, logpsi, normals, uniforms, stddev, logpsi_valid=True,
-                record_accepts=False):
+                record_accepts=False, wrap_lattice=None):
         """In-place MH sub-steps on ``electrons`` / ``logpsi``; returns (n_accept (1,), accepted u8 (S,W) or None)."""
         for t, nm in ((electrons, "electrons"), (logpsi, "logpsi"), (normals, "normals"), (uniforms, "uniforms"),
                       (stddev, "stddev")):
@@ -137,6 +137,14 @@ class Runtime:
         n_accept = torch.zeros(1, dtype=torch.float32, device=self.device)
         accepted = torch.empty(S, W, dtype=torch.uint8, device=self.device) if record_accepts else None
         ws = self._ws_for(wf, W, False)
+        if wrap_lattice is not None:  # periodic proposal (solid): wrap into the simulation cell
+            lat = (C.c_float * 9)(*[float(v) for v in torch.as_tensor(wrap_lattice).reshape(-1).tolist()])
+            rc = self.lib.jaqmc_b200_mh_step_pbc(
+                C.byref(wf.struct), C.byref(system.struct), _ptr(electrons), _ptr(logpsi), int(bool(logpsi_valid)),
+                _ptr(normals), _ptr(uniforms), _ptr(stddev), S, W, _ptr(n_accept), _ptr(accepted), lat, _ptr(ws),
+                ws.numel(), self._stream())
+            _abi.check(self.lib, rc)
+            return n_accept, accepted
         rc = self.lib.jaqmc_b200_mh_step(
             C.byref(wf.struct), C.byref(system.struct), _ptr(electrons), _ptr(logpsi), int(bool(logpsi_valid)),
             _ptr(normals), _ptr(uniforms), _ptr(stddev), S, W, _ptr(n_accept), _ptr(accepted), _ptr(ws), ws.numel(),

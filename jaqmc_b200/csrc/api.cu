@@ -14,6 +14,30 @@ void jq_set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
+static JqWrap make_wrap(const float* lattice) {
+  JqWrap wr;
+  memset(&wr, 0, sizeof(wr));
+  if (!lattice) return wr;
+  wr.on = 1;
+  double L[9], inv[9];
+  for (int i = 0; i < 9; ++i) L[i] = lattice[i];
+  const double det = L[0] * (L[4] * L[8] - L[5] * L[7]) - L[1] * (L[3] * L[8] - L[5] * L[6]) + L[2] * (L[3] * L[7] - L[4] * L[6]);
+  inv[0] = (L[4] * L[8] - L[5] * L[7]) / det;
+  inv[1] = (L[2] * L[7] - L[1] * L[8]) / det;
+  inv[2] = (L[1] * L[5] - L[2] * L[4]) / det;
+  inv[3] = (L[5] * L[6] - L[3] * L[8]) / det;
+  inv[4] = (L[0] * L[8] - L[2] * L[6]) / det;
+  inv[5] = (L[2] * L[3] - L[0] * L[5]) / det;
+  inv[6] = (L[3] * L[7] - L[4] * L[6]) / det;
+  inv[7] = (L[1] * L[6] - L[0] * L[7]) / det;
+  inv[8] = (L[0] * L[4] - L[1] * L[3]) / det;
+  for (int i = 0; i < 9; ++i) {
+    wr.lat[i] = (float)L[i];
+    wr.inv[i] = (float)inv[i];
+  }
+  return wr;
+}
+
 // ------------------------------------------------------------------------------------------------
 // per-kernel profiler (device build only)
 // ------------------------------------------------------------------------------------------------
@@ -116,6 +140,8 @@ static int wf_n_electrons(const jaqmc_wavefunction* wf) {
       auto* c = (const jaqmc_solid_config*)wf->config;
       return c->net.n_up + c->net.n_dn;
     }
+    case JAQMC_WF_HYDROGEN:
+      return ((const jaqmc_hydrogen_config*)wf->config)->n_electrons;
     default:
       return -1;
   }
@@ -131,6 +157,8 @@ static size_t wf_ws_bytes(const jaqmc_wavefunction* wf, long long W, int track) 
       return jq_psiformer_ws_bytes((const jaqmc_psiformer_config*)wf->config, W, track);
     case JAQMC_WF_SOLID_FERMINET:
       return jq_solid_ws_bytes((const jaqmc_solid_config*)wf->config, W, track);
+    case JAQMC_WF_HYDROGEN:
+      return 256;
     default:
       return 0;
   }
@@ -148,6 +176,9 @@ static int wf_forward(const jaqmc_wavefunction* wf, const jaqmc_system* sys, con
     case JAQMC_WF_PSIFORMER:
       return jq_psiformer_forward((const jaqmc_psiformer_config*)wf->config, (const jaqmc_psiformer_params*)wf->params,
                                   sys, electrons, W, track, ws, ws_bytes, out, st);
+    case JAQMC_WF_HYDROGEN:
+      return jq_hydrogen_forward((const jaqmc_hydrogen_config*)wf->config, (const jaqmc_hydrogen_params*)wf->params,
+                                 electrons, W, track, out, st);
     case JAQMC_WF_SOLID_FERMINET: {
       // value path only (sampling): real part -> logpsi, phase angle -> sign
       JQ_REQUIRE(track == 0, JQ_ERR_UNSUPPORTED, "solid: use jaqmc_b200_local_energy_complex for the tracked path");
@@ -449,7 +480,7 @@ extern "C" int jaqmc_b200_dense_fl(const float* x, const float* x2, const float*
 extern "C" int jaqmc_b200_mh_propose(const float* x1, const float* normals, const float* stddev, float* x2,
                                      int64_t count, jaqmc_stream_t stream) {
   JQ_REQUIRE(count >= 0 && (count == 0 || (x1 && normals && stddev && x2)), JQ_ERR_INVALID_ARGUMENT, "mh_propose: null buffer");
-  return jq_launch_mh_propose(x1, normals, stddev, x2, count, (cudaStream_t)stream);
+  return jq_launch_mh_propose(x1, normals, stddev, x2, count, make_wrap(nullptr), (cudaStream_t)stream);
 }
 
 extern "C" int jaqmc_b200_mh_accept(float* x1, const float* x2, float* logprob1, const float* logprob2,
@@ -458,13 +489,36 @@ extern "C" int jaqmc_b200_mh_accept(float* x1, const float* x2, float* logprob1,
   JQ_REQUIRE(n_walkers >= 0 && row >= 1 && (n_walkers == 0 || (x1 && x2 && logprob1 && logprob2 && uniforms && n_accept)),
              JQ_ERR_INVALID_ARGUMENT, "mh_accept: null buffer");
   return jq_launch_mh_accept(x1, x2, logprob1, logprob2, uniforms, nullptr, nullptr, nullptr, (int)n_walkers, row, 1.0f,
-                             n_accept, accepted, (cudaStream_t)stream);
+                             n_accept, accepted, make_wrap(nullptr), (cudaStream_t)stream);
 }
+
+static int mh_step_impl(const jaqmc_wavefunction* wf, const jaqmc_system* sys, float* electrons, float* logpsi,
+                        int32_t logpsi_valid, const float* normals, const float* uniforms, const float* stddev,
+                        int32_t n_steps, int64_t n_walkers, float* n_accept, uint8_t* accepted, const JqWrap& wrap,
+                        void* workspace, size_t workspace_bytes, jaqmc_stream_t stream);
 
 extern "C" int jaqmc_b200_mh_step(const jaqmc_wavefunction* wf, const jaqmc_system* sys, float* electrons,
                                   float* logpsi, int32_t logpsi_valid, const float* normals, const float* uniforms,
                                   const float* stddev, int32_t n_steps, int64_t n_walkers, float* n_accept,
                                   uint8_t* accepted, void* workspace, size_t workspace_bytes, jaqmc_stream_t stream) {
+  return mh_step_impl(wf, sys, electrons, logpsi, logpsi_valid, normals, uniforms, stddev, n_steps, n_walkers, n_accept,
+                      accepted, make_wrap(nullptr), workspace, workspace_bytes, stream);
+}
+
+extern "C" int jaqmc_b200_mh_step_pbc(const jaqmc_wavefunction* wf, const jaqmc_system* sys, float* electrons,
+                                      float* logpsi, int32_t logpsi_valid, const float* normals, const float* uniforms,
+                                      const float* stddev, int32_t n_steps, int64_t n_walkers, float* n_accept,
+                                      uint8_t* accepted, const float* lattice, void* workspace, size_t workspace_bytes,
+                                      jaqmc_stream_t stream) {
+  JQ_REQUIRE(lattice != nullptr, JQ_ERR_INVALID_ARGUMENT, "mh_step_pbc: null lattice");
+  return mh_step_impl(wf, sys, electrons, logpsi, logpsi_valid, normals, uniforms, stddev, n_steps, n_walkers, n_accept,
+                      accepted, make_wrap(lattice), workspace, workspace_bytes, stream);
+}
+
+static int mh_step_impl(const jaqmc_wavefunction* wf, const jaqmc_system* sys, float* electrons, float* logpsi,
+                        int32_t logpsi_valid, const float* normals, const float* uniforms, const float* stddev,
+                        int32_t n_steps, int64_t n_walkers, float* n_accept, uint8_t* accepted, const JqWrap& wrap,
+                        void* workspace, size_t workspace_bytes, jaqmc_stream_t stream) {
   int rc = check_wf(wf);
   if (rc) return rc;
   JQ_REQUIRE(n_walkers >= 0 && n_steps >= 0, JQ_ERR_INVALID_ARGUMENT, "mh_step: negative size");
@@ -494,13 +548,13 @@ extern "C" int jaqmc_b200_mh_step(const jaqmc_wavefunction* wf, const jaqmc_syst
   };
   if (!logpsi_valid && (rc = forward_all(electrons, logpsi))) return rc;
   if (n_steps == 0) return JQ_OK;
-  if ((rc = jq_launch_mh_propose(electrons, normals, stddev, x2, W * row, st))) return rc;
+  if ((rc = jq_launch_mh_propose(electrons, normals, stddev, x2, W * row, wrap, st))) return rc;
   for (int s = 0; s < n_steps; ++s) {
     if ((rc = forward_all(x2, lp2))) return rc;
     const float* next = (s + 1 < n_steps) ? normals + (size_t)(s + 1) * W * row : nullptr;
     // fused: accept test, select, and the next proposal (x2 is rewritten in place)
     rc = jq_launch_mh_accept(electrons, x2, logpsi, lp2, uniforms + (size_t)s * W, next, stddev, x2, (int)W, row, 2.0f,
-                             n_accept, accepted ? accepted + (size_t)s * W : nullptr, st);
+                             n_accept, accepted ? accepted + (size_t)s * W : nullptr, wrap, st);
     if (rc) return rc;
   }
   return JQ_OK;

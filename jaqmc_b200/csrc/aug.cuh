@@ -85,11 +85,15 @@ int jq_launch_logdet_combine(const float* det_sign, const float* det_logabs, con
                              float* logpsi, float* sign, float* grad, float* lap, float* e_kin, cudaStream_t st);
 
 // ---- kernels implemented in mcmc.cu ---------------------------------------------------------------
+struct JqWrap {   // periodic wrap of proposals into a cell: lattice rows and inverse (on == 0: open boundaries)
+  int on;
+  float lat[9], inv[9];
+};
 int jq_launch_mh_propose(const float* x1, const float* normals, const float* stddev, float* x2, long long count,
-                         cudaStream_t st);
+                         const JqWrap& wr, cudaStream_t st);
 int jq_launch_mh_accept(float* x1, const float* x2, float* lp1, const float* lp2, const float* log_u,
                         const float* next_normals, const float* stddev, float* x2_next, int W, int row,
-                        float scale, float* n_accept, unsigned char* accepted, cudaStream_t st);
+                        float scale, float* n_accept, unsigned char* accepted, const JqWrap& wr, cudaStream_t st);
 
 // ---- kernels implemented in attention.cu ----------------------------------------------------------
 struct JqAttnOperand {

@@ -146,3 +146,40 @@ int jq_head_forward(const JqHeadDims& d, const jaqmc_head_params* p, const float
   return jq_launch_logdet_combine(b.det_sign, b.det_logabs, b.det_grad, b.det_lap, (int)W, n, d.D, track,
                                   d.jastrow ? b.extra : nullptr, out.logpsi, out.sign, out.grad, out.lap, out.e_kin, st);
 }
+
+// ------------------------------------------------------------------------------------------------
+// HydrogenAtom demo wavefunction (app/hydrogen_atom.py:28-35): log psi = alpha * ||electrons|| (norm of the whole
+// (n, 3) array; the app uses n = 1).  grad = alpha x / r, lap = alpha (3n - 1) / r.  One item per walker.
+// ------------------------------------------------------------------------------------------------
+__global__ void k_hydrogen(const float* __restrict__ el, const float* __restrict__ alpha, int W, int n, int track,
+                           float* __restrict__ logpsi, float* __restrict__ sign, float* __restrict__ grad,
+                           float* __restrict__ lap, float* __restrict__ e_kin) {
+  const int K = 3 * n;
+  const float a = alpha[0];
+  for (long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x; w < W;
+       w += (long long)gridDim.x * blockDim.x) {
+    const float* e = el + w * K;
+    float r2 = 0.f;
+    for (int k = 0; k < K; ++k) r2 = fmaf(e[k], e[k], r2);
+    const float r = sqrtf(r2);
+    logpsi[w] = a * r;
+    if (sign) sign[w] = 1.0f;
+    if (!track) continue;
+    const float rinv = 1.0f / r;
+    for (int k = 0; k < K; ++k) grad[w * K + k] = a * e[k] * rinv;
+    const float l = a * (float)(K - 1) * rinv;
+    lap[w] = l;
+    e_kin[w] = -0.5f * (l + a * a);
+  }
+}
+
+int jq_hydrogen_forward(const jaqmc_hydrogen_config* c, const jaqmc_hydrogen_params* p, const float* electrons,
+                        long long W, int track, JqWfOut out, cudaStream_t st) {
+  JQ_REQUIRE(c->n_electrons >= 1, JQ_ERR_INVALID_ARGUMENT, "hydrogen: n_electrons=%d", c->n_electrons);
+  JQ_REQUIRE(p->alpha, JQ_ERR_INVALID_ARGUMENT, "hydrogen: null alpha");
+  if (W <= 0) return JQ_OK;
+  JQ_LAUNCH(k_hydrogen, dim3(jq_cdiv(W, 128)), dim3(128), 0, st, electrons, p->alpha, (int)W, c->n_electrons, track,
+            out.logpsi, out.sign, out.grad, out.lap, out.e_kin);
+  JQ_CHECK_LAUNCH();
+  return JQ_OK;
+}

@@ -80,3 +80,6 @@ size_t jq_solid_ws_bytes(const jaqmc_solid_config* c, long long W, int track);
 int jq_solid_forward(const jaqmc_solid_config* c, const jaqmc_solid_params* p, const jaqmc_system* sys,
                      const float* electrons, long long W, int track, void* ws, size_t ws_bytes, JqWfOutC out,
                      cudaStream_t st);
+
+int jq_hydrogen_forward(const jaqmc_hydrogen_config* c, const jaqmc_hydrogen_params* p, const float* electrons,
+                        long long W, int track, JqWfOut out, cudaStream_t st);

@@ -402,3 +402,19 @@ class SolidWavefunction:
         sysh = _marshal.system_handle(data.primitive_atoms, None)
         return rt.local_energy_complex(wf, sysh, el, ewald, data.atoms if ewald is not None else None,
                                        data.charges if ewald is not None else None, sums=sums)
+
+
+@dataclass
+class HydrogenAtom(Wavefunction):
+    """One-parameter demo wavefunction ``log psi = alpha |r|`` of ``jaqmc hydrogen-atom train``
+    (reference app/hydrogen_atom.py:28-35); ``initial_alpha = -0.8``.  The potential ``-1/|r|`` (``:36-39``) is the
+    Coulomb kernel with a unit charge at the origin."""
+
+    initial_alpha: float = -0.8
+    nspins: tuple = (1, 0)
+
+    def init_params(self, data, rngs=None) -> dict:
+        return {"params": {"alpha": torch.full((1,), float(self.initial_alpha), device=data.electrons.device)}}
+
+    def _handle(self, params, n_atoms: int):
+        return _marshal.hydrogen_handle(params, sum(self.nspins))

@@ -114,3 +114,22 @@ def test_partial_sums():
     assert np.isclose(float(sums[0]), float(e.sum()), rtol=1e-5)
     assert np.isclose(float(sums[1]), float((e * e).sum()), rtol=1e-5)
     assert float(sums[2]) == 9.0
+
+
+def test_hydrogen_atom_closed_form():
+    """``log psi = alpha |r|``: E_L = -alpha^2/2 - (alpha + 1)/|r| (hydrogen closed form; exact ground state -0.5 at
+    alpha = -1, reference tests/hydrogen/atom_test.py:47-52)."""
+    from oracle import estimators as OE
+
+    rt = H.emu_runtime()
+    g = torch.Generator().manual_seed(0)
+    el = torch.randn(16, 1, 3, generator=g)
+    sysh = M.system_handle(torch.zeros(1, 3), torch.ones(1))
+    for alpha in (-0.8, -1.0):
+        wf = M.hydrogen_handle({"params": {"alpha": torch.tensor([alpha])}})
+        out = rt.local_energy(wf, sysh, el.contiguous())
+        ref = OE.hydrogen_local_energy(alpha, el.double())
+        np.testing.assert_allclose(out["e_loc"].numpy(), ref.numpy(), rtol=2e-6, atol=2e-6)
+        np.testing.assert_allclose(out["logpsi"].numpy(), alpha * el.norm(dim=-1).squeeze(-1).numpy(), rtol=1e-6)
+        assert (out["sign"] == 1).all()
+    assert np.allclose(out["e_loc"].numpy(), -0.5, atol=1e-5)
