@@ -76,6 +76,11 @@ def load_peaks():
 # CPU arm: vmapped float32 port of the reference path (oracle/), bounded sample
 # ---------------------------------------------------------------------------------------------
 def cpu_rate(workload: str, budget_s: float, chunk: int = 64):
+    # all the host threads this process may use (torchrun exports OMP_NUM_THREADS=1, which would time one core)
+    try:
+        torch.set_num_threads(max(1, len(os.sched_getaffinity(0))))
+    except (AttributeError, OSError):
+        torch.set_num_threads(max(1, os.cpu_count() or 1))
     import helpers as H
     from oracle import estimators as OE
     from oracle import lap as L

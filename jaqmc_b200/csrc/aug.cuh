@@ -37,6 +37,13 @@ int jq_launch_coulomb(const float* electrons, const float* atoms, const float* c
                       float* e_pot, cudaStream_t st);
 
 // ---- kernels implemented in dense.cu ------------------------------------------------------------
+struct JqEnvFuse {
+  const float* electrons;  // [W][n][3]
+  const float* atoms;      // [A][3]
+  const float* pi;         // [n_orb][A][D] of the launch's spin channel
+  const float* sigma;
+  int A, D, n, type;       // type 0 isotropic, 1 abs_isotropic
+};
 struct JqDenseArgs {
   const float* src0;  // [groups_total][C][k0]
   int k0;
@@ -56,11 +63,15 @@ struct JqDenseArgs {
   // res_mode 0 none, 1 (res + y)/sqrt(2) (FermiNet), 2 res + y; res has the layout of out
   int act, res_mode;
   const float* res;
+  // act 2 (tensor-core path only): the output is multiplied by the orbital envelope with the product rule
+  // (wavefunction/output/envelope.py:98-140): features are (determinant, orbital) pairs, groups are electrons
+  const struct JqEnvFuse* env;
   // scratch for the tensor-core path's transposed hi/lo weight split: jq_dense_tc_scratch_floats(k0+k1, N) floats,
   // or null to force the CUDA-core kernel
   float* wscratch;
 };
 int jq_launch_dense(const JqDenseArgs& a, cudaStream_t st);
+bool jq_dense_tc_eligible(const JqDenseArgs& a);  // device build: will this launch take the tcgen05 kernel?
 size_t jq_dense_tc_scratch_floats(int k_total, int n_out);
 // out = act(y) or (res + act(y))/sqrt(2); act = tanh with the forward-Laplacian rule.  In-place allowed.
 int jq_launch_tanh_fl(const float* y, const float* res, float* out, long long G, int C, int F, int residual_mode,

@@ -261,11 +261,17 @@ int jq_launch_dense_tc(const JqDenseArgs& a, cudaStream_t st, bool* handled);  /
 int jq_launch_tanh_fl_mapped(const JqDenseArgs& a, cudaStream_t st);
 #ifdef JAQMC_HOST_EMU
 size_t jq_dense_tc_scratch_floats(int k_total, int n_out) { return (size_t)2 * k_total * n_out; }
+bool jq_dense_tc_eligible(const JqDenseArgs&) { return false; }
 #endif
 
 int jq_launch_dense(const JqDenseArgs& a, cudaStream_t st) {
   if (a.G <= 0 || a.N <= 0) return JQ_OK;
+#ifdef JAQMC_HOST_EMU
   JQ_REQUIRE(a.act == 0 || a.act == 1, JQ_ERR_INVALID_ARGUMENT, "dense: unknown activation %d", a.act);
+#else
+  JQ_REQUIRE(a.act == 0 || a.act == 1 || (a.act == 2 && a.env && jq_dense_tc_eligible(a)), JQ_ERR_INVALID_ARGUMENT,
+             "dense: unknown activation %d", a.act);
+#endif
   JQ_REQUIRE(a.res_mode == 0 || a.res != nullptr, JQ_ERR_INVALID_ARGUMENT, "dense: residual without source");
   JQ_REQUIRE(a.k0 > 0 && a.src0 && a.w0 && a.out, JQ_ERR_INVALID_ARGUMENT, "dense: null operand");
   JQ_REQUIRE(a.k1 == 0 || (a.src1 && a.w1), JQ_ERR_INVALID_ARGUMENT, "dense: null second operand");

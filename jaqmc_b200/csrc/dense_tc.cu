@@ -66,8 +66,9 @@ struct TcParams {
   const float* cadd;
   const float* res;
   float* out;
-  int act;       // 0 raw, 1 tanh forward-Laplacian
+  int act;       // 0 raw, 1 tanh forward-Laplacian, 2 envelope product
   int res_mode;  // 0 none, 1 (res + y)/sqrt2, 2 res + y
+  JqEnvFuse env; // act == 2
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -237,6 +238,38 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& p, uint32_t tlane0
       // is accumulated on the way and enters the Laplacian row, which is emitted last.
       float th = 0.f, d1 = 1.f, s2 = 0.f;
       int r0 = 0, r1 = C;
+      // ACT == 2: orbital x envelope.  E = sum_I pi exp(-s r_I) for (electron j, orbital i, determinant d) with
+      // dE_a = sum_I -s t (r_j - R_I)_a / r_I and lap E = sum_I t (s^2 - 2 s / r_I); product rule per row:
+      //   out_0 = y_0 E,  out_c = y_c E (+ y_0 dE_a on the electron's own three rows),
+      //   out_L = y_L E + y_0 lap E + 2 sum_a y_{own a} dE_a
+      float y0 = 0.f, ev = 1.f, e_d[3] = {0.f, 0.f, 0.f}, e_l = 0.f;
+      int own0 = -8;
+      if (ACT == 2) {
+        const int nel = p.env.n;
+        const int j = (int)(g % nel);
+        own0 = 1 + 3 * j;
+        const int dd = (int)fo / nel, io = (int)fo % nel;
+        const float* e = p.env.electrons + g * 3;
+        ev = 0.f;
+        for (int I = 0; I < p.env.A; ++I) {
+          const float dx = e[0] - p.env.atoms[3 * I], dy = e[1] - p.env.atoms[3 * I + 1], dz = e[2] - p.env.atoms[3 * I + 2];
+          const float r = sqrtf(dx * dx + dy * dy + dz * dz);
+          float sg = p.env.sigma[(io * p.env.A + I) * p.env.D + dd];
+          if (p.env.type == 1) sg = fabsf(sg);
+          const float t = p.env.pi[(io * p.env.A + I) * p.env.D + dd] * expf(-sg * r);
+          const float rinv = 1.0f / r;
+          const float c1 = -sg * t * rinv;
+          ev += t;
+          e_d[0] += c1 * dx;
+          e_d[1] += c1 * dy;
+          e_d[2] += c1 * dz;
+          e_l += t * (sg * sg - 2.0f * sg * rinv);
+        }
+        y0 = tmem_sum1(tcol) + bias_f;
+        if (f_ok) out_b[fo] = y0 * ev;
+        r0 = 1;
+        r1 = (C > 1) ? C - 1 : 1;
+      }
       if (ACT == 1) {
         float x = tmem_sum1(tcol);
         if (CADD) x += cadd_b[fo];
@@ -274,6 +307,16 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& p, uint32_t tlane0
               if (i >= skip) s2 = fmaf(y, y, s2);
               y *= d1;
             }
+            if (ACT == 2) {
+              const int a = cs + i - own0;
+              float o2 = y * ev;
+              if (a >= 0 && a < 3) {
+                const float da = (a == 0) ? e_d[0] : ((a == 1) ? e_d[1] : e_d[2]);
+                if (i >= skip) s2 = fmaf(y, da, s2);  // cross term for the Laplacian row
+                o2 = fmaf(y0, da, o2);
+              }
+              y = o2;
+            }
             if (ACT == 0 && cs + i == 0) y += bias_f;
             if (RES == 1) y = (rr[i] + y) * inv_sqrt2;
             if (RES == 2) y = rr[i] + y;
@@ -289,11 +332,25 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& p, uint32_t tlane0
             s2 = fmaf(y, y, s2);
             y *= d1;
           }
+          if (ACT == 2) {
+            const int a = c - own0;
+            float o2 = y * ev;
+            if (a >= 0 && a < 3) {
+              const float da = (a == 0) ? e_d[0] : ((a == 1) ? e_d[1] : e_d[2]);
+              s2 = fmaf(y, da, s2);
+              o2 = fmaf(y0, da, o2);
+            }
+            y = o2;
+          }
           if (ACT == 0 && c == 0) y += bias_f;
           if (RES == 1) y = (res_b[o] + y) * inv_sqrt2;
           if (RES == 2) y = res_b[o] + y;
           if (f_ok) out_b[o] = y;
         }
+      }
+      if (ACT == 2 && C > 1) {
+        const float yl = tmem_sum1(tcol + C - 1);
+        if (f_ok) out_b[(uint32_t)(C - 1) * N + fo] = yl * ev + y0 * e_l + 2.0f * s2;
       }
       if (ACT == 1) {
         float yl = (C > 1) ? tmem_sum1(tcol + C - 1) : 0.f;
@@ -470,8 +527,9 @@ k_dense_tc(const __grid_constant__ CUtensorMap mapX0, const __grid_constant__ CU
     const uint32_t tlane0 = tmem_base + ((uint32_t)(q * 32) << 16);
     // one instantiation per (activation, residual mode, addend) combination: no per-element predicates
 #define TC_EPI(ACT, RES, CADD) epilogue_loop<ACT, RES, CADD>(p, tlane0, q, sub, acc_full, acc_empty, lane)
-    const int key = (p.act ? 8 : 0) | (p.res_mode << 1) | (p.cadd ? 1 : 0);
+    const int key = (p.act == 2) ? 16 : ((p.act ? 8 : 0) | (p.res_mode << 1) | (p.cadd ? 1 : 0));
     switch (key) {
+      case 16: TC_EPI(2, 0, false); break;
       case 0: TC_EPI(0, 0, false); break;
       case 1: TC_EPI(0, 0, true); break;
       case 2: TC_EPI(0, 1, false); break;
@@ -626,6 +684,11 @@ int jq_launch_dense_tc(const JqDenseArgs& a, cudaStream_t st, bool* handled) {
   p.out = a.out;
   p.act = a.act;
   p.res_mode = a.res_mode;
+  if (a.act == 2) {
+    JQ_REQUIRE(a.env && !a.cadd && !a.res && a.env->n == a.n_tot && a.N == a.env->D * a.env->n, JQ_ERR_INVALID_ARGUMENT,
+               "dense_tc: envelope epilogue needs (determinant, orbital) features and no addend / residual");
+    p.env = *a.env;
+  }
 
   CUtensorMap mX0, mX1, mWh, mWl;
   {

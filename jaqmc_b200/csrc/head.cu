@@ -109,6 +109,8 @@ int jq_head_forward(const JqHeadDims& d, const jaqmc_head_params* p, const float
              "head: null jastrow parameter");
   int rc;
   const int nchan = split ? 2 : 1;
+  bool env_fused = true;  // the tcgen05 kernel applies the envelope in its epilogue; otherwise a separate pass does
+  JqEnvFuse ef[2];
   for (int s = 0; s < nchan; ++s) {
     JqDenseArgs a;
     memset(&a, 0, sizeof(a));
@@ -129,6 +131,20 @@ int jq_head_forward(const JqHeadDims& d, const jaqmc_head_params* p, const float
       a.n_sub = n;
     }
     a.G = W * a.n_sub;
+    if (d.envelope_type != JAQMC_ENVELOPE_NULL && env_fused && jq_dense_tc_eligible(a)) {
+      ef[s].electrons = electrons;
+      ef[s].atoms = atoms;
+      ef[s].pi = p->env_pi[s];
+      ef[s].sigma = p->env_sigma[s];
+      ef[s].A = d.A;
+      ef[s].D = d.D;
+      ef[s].n = n;
+      ef[s].type = d.envelope_type;
+      a.env = &ef[s];
+      a.act = 2;
+    } else {
+      env_fused = false;
+    }
     if ((rc = jq_launch_dense(a, st))) return rc;
   }
   JqEnvelopeArgs env;
@@ -137,7 +153,8 @@ int jq_head_forward(const JqHeadDims& d, const jaqmc_head_params* p, const float
   env.sigma[0] = p->env_sigma[0];
   env.pi[1] = split ? p->env_pi[1] : nullptr;
   env.sigma[1] = split ? p->env_sigma[1] : nullptr;
-  if ((rc = jq_launch_orb_envelope(b.orb, electrons, atoms, env, (int)W, d.sp, d.A, d.D, track, st))) return rc;
+  if (!env_fused && (rc = jq_launch_orb_envelope(b.orb, electrons, atoms, env, (int)W, d.sp, d.A, d.D, track, st)))
+    return rc;
   if ((rc = jq_launch_logdet(b.orb, (int)W, n, d.D, track, b.det_sign, b.det_logabs, b.det_grad, b.det_lap, st)))
     return rc;
   if (d.jastrow &&

@@ -103,7 +103,7 @@ int jq_launch_orb_envelope(float* orb, const float* electrons, const float* atom
 //         Jc[KC][DB][nn] | Mc[KC][DB][nn] | p1[KC][DB][n] | p2[KC][DB][n]
 // ------------------------------------------------------------------------------------------------
 #define LD_NP 16
-__global__ void k_logdet(const float* __restrict__ orb, int n, int D, int C, int DB, int KC,
+__global__ void __launch_bounds__(256, 3) k_logdet(const float* __restrict__ orb, int n, int D, int C, int DB, int KC,
                          float* __restrict__ det_sign, float* __restrict__ det_logabs, float* __restrict__ det_grad,
                          float* __restrict__ det_lap) {
   JQ_DYN_SMEM(float, sm);
@@ -253,14 +253,31 @@ __global__ void k_logdet(const float* __restrict__ orb, int n, int D, int C, int
       invp[q] = (j < n) ? inv[d * nn + i * n + j] : 0.f;
     }
     __syncthreads();
+    // When every item has its own thread (db * n <= blockDim, the common case) the next slab's column is fetched
+    // into registers before the current one is consumed, so the global-load latency overlaps the products.
+    const bool one_item = (db * n <= nt);
+    float nxt[LD_NP];
+    if (one_item && tid < db * n) {
+#pragma unroll
+      for (int j = 0; j < LD_NP; ++j) nxt[j] = (j < n) ? ow[(long long)DN + (long long)j * C * DN + tid] : 0.f;
+    }
     for (int kk = 0; kk < KT; ++kk) {
       const float* oc = ow + (long long)(1 + kk) * DN;  // slab: (j, d, i) at oc[j*C*DN + d*n + i]
       for (int q = tid; q < db * n; q += nt) {
         int d, i2;
         jq_divmod(q, n, inv_n, &d, &i2);
         float col[LD_NP];
+        if (one_item) {
 #pragma unroll
-        for (int j = 0; j < LD_NP; ++j) col[j] = (j < n) ? oc[(long long)j * C * DN + q] : 0.f;
+          for (int j = 0; j < LD_NP; ++j) col[j] = nxt[j];
+          if (kk + 1 < KT) {
+#pragma unroll
+            for (int j = 0; j < LD_NP; ++j) nxt[j] = (j < n) ? oc[(long long)DN + (long long)j * C * DN + q] : 0.f;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < LD_NP; ++j) col[j] = (j < n) ? oc[(long long)j * C * DN + q] : 0.f;
+        }
         const float* ib = invp + (size_t)d * n * LD_NP;
         float* mo = Ms + d * nn + i2;
         for (int i = 0; i < n; ++i) {
