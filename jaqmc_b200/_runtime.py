@@ -116,6 +116,25 @@ class Runtime:
             out["e_pot"] = e_pot
         return out
 
+    def capture_local_energy(self, wf, system, electrons, sums=None):
+        """CUDA-graph version of :meth:`local_energy` for a fixed walker-batch shape: the ~60 kernel launches of one
+        evaluation are captured once and replayed with a single launch.  Returns ``(replay, out)``: ``replay()``
+        re-evaluates on the current contents of ``electrons`` (same tensor) and refreshes the tensors in ``out``.
+        The library only enqueues on the stream and never allocates, so the whole call is capturable."""
+        self.local_energy(wf, system, electrons, sums=sums)  # warm-up: one-off attribute / descriptor setup
+        torch.cuda.synchronize(self.device)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            out = self.local_energy(wf, system, electrons, sums=sums)
+        keep = (wf, system, electrons, sums, self._ws)
+
+        def replay():
+            graph.replay()
+            return out
+
+        replay._keep = keep
+        return replay, out
+
     def coulomb(self, system, electrons):
         self._check_tensor(electrons, "electrons")
         W, n = electrons.shape[0], electrons.shape[1]

@@ -78,6 +78,19 @@ class Wavefunction:
         return rt.local_energy(wf, sysh, el, sums=sums)
 
 
+def capture_local_energy(wf: "Wavefunction", params, data: MoleculeData, sums: torch.Tensor | None = None):
+    """``(replay, out)`` -- CUDA-graph replay of ``wf.local_energy(params, data)`` for fixed shapes; ``data.electrons``
+    and the parameter leaves are read in place at every replay."""
+    wf._check(data)
+    el, _ = _batched(data.electrons)
+    if el.data_ptr() != data.electrons.data_ptr():
+        raise ValueError("capture_local_energy needs a contiguous (W, n, 3) electrons tensor")
+    rt = runtime(el.device)
+    handle = wf._handle(params, data.atoms.shape[0])
+    sysh = _marshal.system_handle(data.atoms, data.charges)
+    return rt.capture_local_energy(handle, sysh, el, sums=sums)
+
+
 @dataclass
 class FermiNetWavefunction(Wavefunction):
     """FermiNet ansatz (reference app/molecule/wavefunction/ferminet.py:21-74); same fields and defaults."""
