@@ -184,9 +184,12 @@ __device__ __forceinline__ void small_epilogue(const JqDenseArgs& a, float (&ac)
     }
 }
 
+// TC / TK / TN fix the components, contraction depth and width at compile time (0 = runtime value): with constants
+// the address arithmetic folds into immediate offsets and the loops unroll, which is what bounds this kernel.
+template <int TC, int TK, int TN>
 __global__ void k_dense_small(JqDenseArgs a) {
   JQ_DYN_SMEM(float, sm);
-  const int C = a.C, K = a.k0, N = a.N;
+  const int C = TC ? TC : a.C, K = TK ? TK : a.k0, N = TN ? TN : a.N;
   const int ldw = a.ldw ? a.ldw : N;
   float* Ws = sm;                 // [K][N]
   float* Xs = Ws + K * N;         // [SM_GT][C][K]
@@ -210,6 +213,7 @@ __global__ void k_dense_small(JqDenseArgs a) {
 #pragma unroll
     for (int c = 0; c < SM_CMAX; ++c) acc0[c] = acc1[c] = 0.f;
     if (vec4) {
+#pragma unroll
       for (int k = 0; k < K; k += 4) {
         float w0[4], w1[4];
 #pragma unroll
@@ -287,11 +291,18 @@ int jq_launch_dense(const JqDenseArgs& a, cudaStream_t st) {
 #ifndef JAQMC_HOST_EMU
     static bool attr_set = false;
     if (!attr_set) {
-      cudaFuncSetAttribute(k_dense_small, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+      cudaFuncSetAttribute(k_dense_small<0, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
       attr_set = true;
     }
 #endif
-    JQ_LAUNCH(k_dense_small, dim3((unsigned)jq_cdiv(a.G, SM_GT)), dim3(256), smem, st, a);
+    const dim3 grid((unsigned)jq_cdiv(a.G, SM_GT));
+    // the FermiNet two-electron stream (Local2: 8 components; value path: 1) and Local1 layers at the default widths
+    if (a.C == 8 && a.k0 == 32 && a.N == 32) JQ_LAUNCH((k_dense_small<8, 32, 32>), grid, dim3(256), smem, st, a);
+    else if (a.C == 8 && a.k0 == 4 && a.N == 32) JQ_LAUNCH((k_dense_small<8, 4, 32>), grid, dim3(256), smem, st, a);
+    else if (a.C == 1 && a.k0 == 32 && a.N == 32) JQ_LAUNCH((k_dense_small<1, 32, 32>), grid, dim3(256), smem, st, a);
+    else if (a.C == 1 && a.k0 == 4 && a.N == 32) JQ_LAUNCH((k_dense_small<1, 4, 32>), grid, dim3(256), smem, st, a);
+    else if (a.C == 8 && a.k0 == 7 && a.N == 32) JQ_LAUNCH((k_dense_small<8, 7, 32>), grid, dim3(256), smem, st, a);
+    else JQ_LAUNCH((k_dense_small<0, 0, 0>), grid, dim3(256), smem, st, a);
     JQ_CHECK_LAUNCH();
     return JQ_OK;
   }

@@ -243,14 +243,18 @@ __global__ void __launch_bounds__(256, 3) k_logdet(const float* __restrict__ orb
     // ---- small matrices (n <= 16): one item per (determinant, column i2) and derivative slab.  The item holds
     // column i2 of dA_c in registers and forms column i2 of M = A^-1 dA_c with the inverse read as float4 broadcasts
     // from a row-padded copy: ~1.3 instructions per multiply-add instead of 3-4 for the shared-memory tiled product.
-    float* invp = Jc;                       // [DB][n][LD_NP]  (the slab area is carved differently on this path)
-    float* Ms = invp + (size_t)DB * n * LD_NP;  // [DB][n][n]
-    p1 = Ms + (size_t)DB * nn;
+    // per-determinant strides padded so that the 2-3 determinants a warp touches fall into different banks:
+    // IS = n*16 + 4 (float4 rows shifted by one 16-byte bank group), MS = nn rounded up to n modulo 32
+    const int IS = n * LD_NP + 4;
+    const int MS = nn + ((n - nn) % 32 + 32) % 32;
+    float* invp = Jc;                       // [DB][IS]  (the slab area is carved differently on this path)
+    float* Ms = invp + (size_t)DB * IS;     // [DB][MS]
+    p1 = Ms + (size_t)DB * MS;
     p2 = p1 + DB * n;
     for (int q = tid; q < db * n * LD_NP; q += nt) {
       int d = q / (n * LD_NP), r = q % (n * LD_NP);
       int i = r / LD_NP, j = r % LD_NP;
-      invp[q] = (j < n) ? inv[d * nn + i * n + j] : 0.f;
+      invp[d * IS + r] = (j < n) ? inv[d * nn + i * n + j] : 0.f;
     }
     __syncthreads();
     // When every item has its own thread (db * n <= blockDim, the common case) the next slab's column is fetched
@@ -278,8 +282,8 @@ __global__ void __launch_bounds__(256, 3) k_logdet(const float* __restrict__ orb
 #pragma unroll
           for (int j = 0; j < LD_NP; ++j) col[j] = (j < n) ? oc[(long long)j * C * DN + q] : 0.f;
         }
-        const float* ib = invp + (size_t)d * n * LD_NP;
-        float* mo = Ms + d * nn + i2;
+        const float* ib = invp + (size_t)d * IS;
+        float* mo = Ms + d * MS + i2;
         for (int i = 0; i < n; ++i) {
           const float4* r4 = reinterpret_cast<const float4*>(ib + i * LD_NP);
           float acc = 0.f;
@@ -298,7 +302,7 @@ __global__ void __launch_bounds__(256, 3) k_logdet(const float* __restrict__ orb
       for (int q = tid; q < db * n; q += nt) {
         int d, i2;
         jq_divmod(q, n, inv_n, &d, &i2);
-        const float* m = Ms + d * nn;
+        const float* m = Ms + d * MS;
         float acc = 0.f;
         for (int i = 0; i < n; ++i) acc = fmaf(m[i * n + i2], m[i2 * n + i], acc);
         p1[q] = m[i2 * n + i2];
@@ -409,7 +413,7 @@ int jq_launch_logdet(const float* orb, int W, int n, int D, int track, float* de
   auto smem_for = [&](int db, int kc) {
     if (track && kc == 0)  // small path: inv | colp piv scalars | padded inverses | one product slab | p1 p2
       return (size_t)8 * db + sizeof(float) * ((size_t)db * nn + 2 * (size_t)db * n + 4 * (size_t)db +
-                                              (size_t)db * n * LD_NP + (size_t)db * nn + 2 * (size_t)db * n) + 32;
+                                              (size_t)db * (n * LD_NP + 4) + (size_t)db * (nn + 32) + 2 * (size_t)db * n) + 32;
     return (size_t)8 * db + sizeof(float) * ((size_t)db * nn + 2 * (size_t)db * n + 4 * (size_t)db +
                                             (track ? (size_t)kc * db * nn * 2 + (size_t)kc * db * n * 2 : 0)) + 32;
   };
