@@ -203,7 +203,8 @@ def parse_profile(rt):
     n = rt.lib.jaqmc_b200_profile_fetch(buf, len(buf))
     out = {}
     for ln in buf.raw[:n].decode().splitlines():
-        name, cnt, ms, fl, by = ln.split()
+        name, cnt, ms, fl, by = ln.rsplit(None, 4)   # template kernels carry spaces in their name
+        name = name.replace(" ", "").replace("(", "").replace(")", "")
         out[name] = {"launches": int(cnt), "ms": float(ms), "flops": float(fl), "bytes": float(by)}
     return out
 
