@@ -265,9 +265,14 @@ def run_ours(args):
     el_dev = torch.empty_like(data.electrons)
 
     def step_e2e():
-        el_dev.copy_(el_host, non_blocking=True)
+        # public API with host buffers: pinned H2D of the walkers into the captured input, graph replay, D2H of E_L
         sums.zero_()
-        out = wf.local_energy(params, MoleculeData(el_dev, atoms, charges), sums=sums)
+        if use_graph:
+            data.electrons.copy_(el_host, non_blocking=True)
+            out = replay()
+        else:
+            el_dev.copy_(el_host, non_blocking=True)
+            out = wf.local_energy(params, MoleculeData(el_dev, atoms, charges), sums=sums)
         if dist:
             torch.distributed.all_reduce(sums)
         e_host.copy_(out["e_loc"], non_blocking=True)
