@@ -237,7 +237,23 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& p, uint32_t tlane0
       // Single pass: the Jacobian rows of tanh only need d1 = 1 - tanh(x)^2 (value column, read first); sum_k y_k^2
       // is accumulated on the way and enters the Laplacian row, which is emitted last.
       float th = 0.f, d1 = 1.f, s2 = 0.f;
-      int r0 = 0, r1 = C;
+      const int r0 = (ACT == 0) ? 0 : 1;
+      const int r1 = (ACT == 0) ? C : ((ACT == 1) ? C - 1 : ((C > 1) ? C - 1 : 1));
+      // Rows r0..r1 are walked in chunks of TC_CH, software-pipelined: the addend / residual loads of chunk j+1 are
+      // in flight while chunk j is read from TMEM, transformed and stored (the epilogue is latency-bound on those
+      // loads); chunk 0 is requested before the value column is handled.
+      const bool chunked = r1 - r0 >= TC_CH;
+      float caA[TC_CH], rrA[TC_CH], caB[TC_CH], rrB[TC_CH];
+#define TC_CHUNK_START(j) ((r0 + (j) * TC_CH + TC_CH > r1) ? (r1 - TC_CH) : (r0 + (j) * TC_CH))
+#define TC_CHUNK_LOAD(j, ca, rr)                                  \
+  {                                                               \
+    uint32_t o_ = (uint32_t)TC_CHUNK_START(j) * N + fo;           \
+    _Pragma("unroll") for (int i = 0; i < TC_CH; ++i, o_ += N) { \
+      if (CADD) ca[i] = cadd_b[o_];                               \
+      if (RES) rr[i] = res_b[o_];                                 \
+    }                                                             \
+  }
+      if ((CADD || RES) && chunked) TC_CHUNK_LOAD(0, caA, rrA)
       // ACT == 2: orbital x envelope.  E = sum_I pi exp(-s r_I) for (electron j, orbital i, determinant d) with
       // dE_a = sum_I -s t (r_j - R_I)_a / r_I and lap E = sum_I t (s^2 - 2 s / r_I); product rule per row:
       //   out_0 = y_0 E,  out_c = y_c E (+ y_0 dE_a on the electron's own three rows),
@@ -267,8 +283,6 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& p, uint32_t tlane0
         }
         y0 = tmem_sum1(tcol) + bias_f;
         if (f_ok) out_b[fo] = y0 * ev;
-        r0 = 1;
-        r1 = (C > 1) ? C - 1 : 1;
       }
       if (ACT == 1) {
         float x = tmem_sum1(tcol);
@@ -276,27 +290,15 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& p, uint32_t tlane0
         x += bias_f;
         th = tanhf(x);
         d1 = 1.0f - th * th;
-        r0 = 1;
-        r1 = C - 1;  // Jacobian rows
       }
-      if (r1 - r0 >= TC_CH) {
-        for (int c0 = r0; c0 < r1; c0 += TC_CH) {
-          int cs = c0, skip = 0;
-          if (c0 + TC_CH > r1) {  // last chunk: shifted back to stay inside the group's columns
-            cs = r1 - TC_CH;
-            skip = c0 - cs;
-          }
-          float v[TC_CH], v2[TC_CH], ca[TC_CH], rr[TC_CH];
+      if (chunked) {
+        const int nch = (r1 - r0 + TC_CH - 1) / TC_CH;
+        auto process = [&](int j, const float* ca, const float* rr) {
+          const int cs = TC_CHUNK_START(j);
+          const int skip = r0 + j * TC_CH - cs;  // last chunk: shifted back to stay inside the group's columns
+          float v[TC_CH], v2[TC_CH];
           tmem_ld8_nowait(tcol + cs, v);
           tmem_ld8_nowait(tcol + TC_NMAX + cs, v2);
-          {
-            uint32_t o = (uint32_t)cs * N + fo;
-#pragma unroll
-            for (int i = 0; i < TC_CH; ++i, o += N) {
-              if (CADD) ca[i] = cadd_b[o];
-              if (RES) rr[i] = res_b[o];
-            }
-          }
           tmem_wait_ld();
           uint32_t o = (uint32_t)cs * N + fo;
 #pragma unroll
@@ -322,7 +324,17 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& p, uint32_t tlane0
             if (RES == 2) y = rr[i] + y;
             if (f_ok && i >= skip) out_b[o] = y;
           }
+        };
+        for (int j = 0; j < nch; j += 2) {
+          if ((CADD || RES) && j + 1 < nch) TC_CHUNK_LOAD(j + 1, caB, rrB)
+          process(j, caA, rrA);
+          if (j + 1 < nch) {
+            if ((CADD || RES) && j + 2 < nch) TC_CHUNK_LOAD(j + 2, caA, rrA)
+            process(j + 1, caB, rrB);
+          }
         }
+#undef TC_CHUNK_LOAD
+#undef TC_CHUNK_START
       } else {
         for (int c = r0; c < r1; ++c) {
           float y = tmem_sum1(tcol + c);
