@@ -293,7 +293,8 @@ int jaqmc_b200_mh_step_pbc(const jaqmc_wavefunction* wf, const jaqmc_system* sys
  *   n_components = 1 (value only) or K+2 (value, K Jacobian columns, Laplacian).
  *   activation 0 none | 1 tanh;  residual_mode 0 none | 1 (res + y)/sqrt(2) | 2 res + y.
  *   use_tensor_cores != 0 routes eligible shapes (k0, k1 multiples of 32, 64 <= n_out <= 256) to the tcgen05 3xTF32
- *   kernel and needs workspace >= 2*(k0+k1)*n_out floats; 0 forces the CUDA-core FP32 kernel. */
+ *   kernel and needs workspace >= 2*(k0+k1)*n_out floats; 0 forces the CUDA-core FP32 kernel; 2 forces the
+ *   weight-streaming single-CTA variant of the tcgen05 kernel (1 prefers the CTA-pair variant with resident weights). */
 int jaqmc_b200_dense_fl(const float* x, const float* x2, const float* kernel, const float* kernel2, const float* bias,
                         const float* addend, const float* residual, float* out, int64_t n_groups, int32_t n_components,
                         int32_t k0, int32_t k1, int32_t n_out, int32_t groups_per_walker, int32_t activation,

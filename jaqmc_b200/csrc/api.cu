@@ -473,6 +473,7 @@ extern "C" int jaqmc_b200_dense_fl(const float* x, const float* x2, const float*
     JQ_REQUIRE(workspace && workspace_bytes >= need, JQ_ERR_WORKSPACE_TOO_SMALL, "dense_fl: workspace %zu < %zu bytes",
                workspace_bytes, need);
     a.wscratch = (float*)workspace;
+    a.tc_mode = (use_tensor_cores == 2) ? 1 : 0;
   }
   return jq_launch_dense(a, (cudaStream_t)stream);
 }

@@ -69,6 +69,7 @@ struct JqDenseArgs {
   // scratch for the tensor-core path's transposed hi/lo weight split: jq_dense_tc_scratch_floats(k0+k1, N) floats,
   // or null to force the CUDA-core kernel
   float* wscratch;
+  int tc_mode;  // 0: CTA-pair kernel (weights resident) when the shape allows, else the streaming one; 1: streaming only
 };
 int jq_launch_dense(const JqDenseArgs& a, cudaStream_t st);
 bool jq_dense_tc_eligible(const JqDenseArgs& a);  // device build: will this launch take the tcgen05 kernel?

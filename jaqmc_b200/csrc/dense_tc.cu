@@ -69,6 +69,9 @@ struct TcParams {
   int act;       // 0 raw, 1 tanh forward-Laplacian, 2 envelope product
   int res_mode;  // 0 none, 1 (res + y)/sqrt2, 2 res + y
   JqEnvFuse env; // act == 2
+  // CTA-pair kernel (k_dense_tc_pair): G_t = 2 * G_h groups per tile, each CTA stages the Hp = roundup8(G_h * C)
+  // rows of its half; pairs_per_block pairs walk the tiles of one 128-feature block
+  int G_h, Hp, pairs_per_block, smem_request;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -189,6 +192,75 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
+// ---- thread-block-cluster helpers (CTA-pair kernel) ----
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// Arrive on the mbarrier at the same shared-memory offset in CTA `cta` of the cluster.  Default (CTA-scope release)
+// semantics, as for every consumer -> producer signal of a 2-SM tcgen05 pipeline: what the signal orders is shared
+// memory handed to the async proxy (fence.proxy.async before it) and TMEM reads (tcgen05.fence before it), not global
+// memory -- a cluster-scope release costs a MEMBAR.GPU per arrive and a cluster-scope acquire a CCTL.IVALL per poll.
+__device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t cta) {
+  uint32_t remote;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(bar)), "r"(cta));
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+}
+// completion of all prior tcgen05.mma of the pair -> one arrival on the barrier at this offset in both CTAs
+__device__ __forceinline__ void tc_commit_pair(uint64_t* bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+          smem_u32(bar)),
+      "h"((uint16_t)3)
+      : "memory");
+}
+// D[tmem] (+)= A * B over the CTA pair: M = 128 (64 rows of A from each CTA), N rows of B split half / half
+__device__ __forceinline__ void tc_mma_tf32_pair(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                                 uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate));
+}
+
+// Register reallocation between warpgroups (all four warps of a warpgroup execute the same one).
+template <int R>
+__device__ __forceinline__ void setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(R)); }
+template <int R>
+__device__ __forceinline__ void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(R)); }
+__device__ __forceinline__ float4 lds128(uint32_t a) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t a, float4 v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+// Converter body: lo = x - trunc_tf32(x) (exact, at most 13 significant bits) for `nvec` float4 (<= 1024) of a raw
+// tile, 128 threads; every thread's loads are issued before its first store.
+__device__ __forceinline__ void convert_lo(uint32_t raw, uint32_t lo, int nvec, int ct) {
+  float4 v[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k)
+    if (ct + k * 128 < nvec) v[k] = lds128(raw + (uint32_t)(ct + k * 128) * 16u);
+#pragma unroll
+  for (int k = 0; k < 8; ++k)
+    if (ct + k * 128 < nvec) {
+      float4 l;
+      l.x = v[k].x - __uint_as_float(__float_as_uint(v[k].x) & 0xffffe000u);
+      l.y = v[k].y - __uint_as_float(__float_as_uint(v[k].y) & 0xffffe000u);
+      l.z = v[k].z - __uint_as_float(__float_as_uint(v[k].z) & 0xffffe000u);
+      l.w = v[k].w - __uint_as_float(__float_as_uint(v[k].w) & 0xffffe000u);
+      sts128(lo + (uint32_t)(ct + k * 128) * 16u, l);
+    }
+}
+
 struct PipeState {
   int stage = 0;
   uint32_t phase = 0;
@@ -201,59 +273,155 @@ struct PipeState {
 };
 
 // Epilogue of one CTA (all its items), specialised on the fused operations.  A thread owns one output feature (its
-// TMEM lane) and walks the tile's groups; a group's C columns are fetched in chunks of TC_CH from both accumulators
-// (tcgen05.ld x8) and summed.  All global addresses are a warp-uniform 64-bit base plus one 32-bit per-thread offset
-// (row * N + f) shared by the addend, the residual and the output, so a row costs one integer add.
+// TMEM lane) and walks the tile's groups; a group's C rows {value, Jacobian rows, Laplacian} are fetched in chunks of
+// TC_CH columns from both accumulators (tcgen05.ld x8) and summed.  All global addresses are a warp-uniform 64-bit
+// base plus one 32-bit per-thread offset (row * N + f) shared by the addend, the residual and the output.
+//
+// The epilogue is bound by the latency of the addend / residual loads, so those run one whole group ahead in
+// registers: the work of a warp is a sequence of units (item, group); while unit u is read from TMEM, transformed and
+// stored, the operands of unit u+1 are requested chunk by chunk into the register slots unit u frees (TC_RING slots
+// of TC_CH rows; a group of more than TC_RING chunks streams through them as a ring).  The loads of an item's first
+// unit are thus in flight before the warp waits for that item's accumulator.  This needs ~100 registers of operand
+// buffers: the kernels move registers from the producer warpgroups to the epilogue warpgroups with setmaxnreg.
+//
+// PAIR (k_dense_tc_pair, tcgen05 cta_group::2 with M = 128): this CTA's TMEM holds its 64 features of the block;
+// lanes 0-63 carry the tile's first half of the rows (staged by CTA 0) and lanes 64-127 the second half (CTA 1), both at
+// columns [0, Hp).  A lane quarter is then (feature half q & 1, row half q >> 1).
 __device__ __forceinline__ float tmem_sum1(uint32_t tcol) { return tmem_ld1(tcol) + tmem_ld1(tcol + TC_NMAX); }
 
-template <int ACT, int RES, bool CADD>
+constexpr int TC_RING = 6;       // operand chunks held in registers (6 x 8 rows covers a 44-row FermiNet-N2 group)
+constexpr int TC_REGS_EPI = 192; // setmaxnreg: epilogue warpgroups (2 x 128 threads)
+constexpr int TC_REGS_PROD = 64; //             TMA / MMA / converter warpgroups; 256 * (192 + 64) = 64 K registers
+
+struct EpiUnit {
+  long long item;   // item (non-pair) or tile (pair) index; >= limit: no more units
+  int gi;           // group of the tile, within this lane quarter's range
+  uint32_t it;      // ordinal of the item in this CTA's sequence (accumulator buffer / phase)
+  uint32_t fo;      // feature, clamped to a valid column
+  bool f_ok;
+  float bias_f;
+  long long g;      // group index in the activation tensors
+  const float* cadd_b;
+  const float* res_b;
+  float* out_b;
+};
+
+template <int ACT, int RES, bool CADD, bool PAIR>
 __device__ __forceinline__ void epilogue_loop(const TcParams& p, uint32_t tlane0, int q, int sub, uint64_t* acc_full,
                                               uint64_t* acc_empty, int lane) {
   const float inv_sqrt2 = 0.70710678118654752440f;
+  constexpr bool LD = CADD || RES;
   const int C = p.C;
   const uint32_t N = (uint32_t)p.N_out;
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
+  const int pair_id = (int)(blockIdx.x >> 1);
+  const int pair_hf = PAIR ? pair_id / p.pairs_per_block : 0;
+  const long long first = PAIR ? (long long)(pair_id % p.pairs_per_block) : (long long)blockIdx.x;
+  const long long limit = PAIR ? (pair_hf < p.mblocks ? p.tiles : 0) : p.items;
+  const long long stride = PAIR ? (long long)p.pairs_per_block : (long long)gridDim.x;
+  const int g_first = PAIR ? (q >> 1) * p.G_h : 0;   // first group of the tile this lane quarter sees
+  const int g_count = PAIR ? p.G_h : p.G_t;
+  const int f_lane = PAIR ? (int)rank * 64 + (q & 1) * 32 + lane : q * 32 + lane;
+
+  // (item, gi) -> unit; valid iff the group exists
+  auto unit_ok = [&](long long item, int gi) -> bool {
+    if (item >= limit || gi >= g_count) return false;
+    const long long t = PAIR ? item : item / p.mblocks;
+    return (int)(t % p.tiles_per_w) * p.G_t + g_first + gi < p.n_sub;
+  };
+  auto make_unit = [&](long long item, int gi, uint32_t it) -> EpiUnit {
+    EpiUnit u;
+    u.item = item;
+    u.gi = gi;
+    u.it = it;
+    const long long t = PAIR ? item : item / p.mblocks;
+    const int hf = PAIR ? pair_hf : (int)(item % p.mblocks);
+    const int f = hf * TC_MBLK + f_lane;
+    u.f_ok = f < p.N_out;
+    u.fo = u.f_ok ? (uint32_t)f : 0u;  // lanes beyond N_out read a valid column and never store
+    u.bias_f = (p.bias && u.f_ok) ? p.bias[f] : 0.f;
+    const int gsub = (int)(t % p.tiles_per_w) * p.G_t + g_first + gi;
+    u.g = (t / p.tiles_per_w) * p.n_tot + p.j0 + gsub;
+    u.cadd_b = CADD ? p.cadd + ((u.g / p.n_tot_true) * C) * (long long)N : nullptr;
+    u.res_b = RES ? p.res + u.g * C * (long long)N : nullptr;
+    u.out_b = p.out + u.g * C * (long long)N;
+    return u;
+  };
+  // first unit at or after (item, gi) in this warp's walk: groups gi, gi+2, ... of an item, then the next items
+  auto find_unit = [&](long long item, int gi, uint32_t it) -> EpiUnit {
+    while (item < limit) {
+      if (unit_ok(item, gi)) return make_unit(item, gi, it);
+      item += stride;
+      ++it;
+      gi = sub;
+    }
+    EpiUnit u;
+    u.item = limit;
+    u.gi = 0;
+    u.it = it;
+    u.fo = 0;
+    u.f_ok = false;
+    u.bias_f = 0.f;
+    u.g = 0;
+    u.cadd_b = nullptr;
+    u.res_b = nullptr;
+    u.out_b = nullptr;
+    return u;
+  };
+
+  // Rows r0..r1 are the chunked ones: all of them without activation, the Jacobian rows otherwise (the value row
+  // comes first -- tanh needs d1 = 1 - tanh(x)^2 before the Jacobian rows -- and the Laplacian row last, after
+  // sum_k y_k^2 has been accumulated; their two operands travel in scalar registers, one unit ahead as well).
+  const int r0 = (ACT == 0) ? 0 : 1;
+  const int r1 = (ACT == 0) ? C : ((ACT == 1) ? C - 1 : ((C > 1) ? C - 1 : 1));
+  const bool chunked = r1 - r0 >= TC_CH;
+  const int nch = chunked ? (r1 - r0 + TC_CH - 1) / TC_CH : 0;
+  const uint32_t o_last = (uint32_t)(C - 1) * N;
+  float ca[TC_RING][TC_CH], rr[TC_RING][TC_CH];
+  float ca0 = 0.f, rr0 = 0.f, caL = 0.f, rrL = 0.f;   // value / Laplacian row operands of the current unit
+#define TC_CHUNK_START(j) ((r0 + (j) * TC_CH + TC_CH > r1) ? (r1 - TC_CH) : (r0 + (j) * TC_CH))
+#define TC_CHUNK_LOAD(u, j, slot)                                    \
+  {                                                                  \
+    uint32_t o_ = (uint32_t)TC_CHUNK_START(j) * N + (u).fo;          \
+    _Pragma("unroll") for (int i_ = 0; i_ < TC_CH; ++i_, o_ += N) { \
+      if (CADD) ca[slot][i_] = (u).cadd_b[o_];                       \
+      if (RES) rr[slot][i_] = (u).res_b[o_];                         \
+    }                                                                \
+  }
+#define TC_EDGE_LOAD(u, c0_, r0_, cl_, rl_)                          \
+  {                                                                  \
+    if (CADD) c0_ = (u).cadd_b[(u).fo];                              \
+    if (RES) r0_ = (u).res_b[(u).fo];                                \
+    if (C > 1) {                                                     \
+      if (CADD) cl_ = (u).cadd_b[o_last + (u).fo];                   \
+      if (RES) rl_ = (u).res_b[o_last + (u).fo];                     \
+    }                                                                \
+  }
+
+  EpiUnit cur = find_unit(first, sub, 0);
+  if (LD && cur.item < limit) {
+    if (ACT != 0 && chunked) TC_EDGE_LOAD(cur, ca0, rr0, caL, rrL)
+    if (chunked) {
+#pragma unroll
+      for (int s = 0; s < TC_RING; ++s)
+        if (s < nch) TC_CHUNK_LOAD(cur, s, s)
+    }
+  }
   uint32_t it = 0;
-  for (long long item = blockIdx.x; item < p.items; item += gridDim.x, ++it) {
-    const long long t = item / p.mblocks;
-    const int hf = (int)(item % p.mblocks);
-    const int f = hf * TC_MBLK + q * 32 + lane;
-    const bool f_ok = f < p.N_out;
-    const uint32_t fo = f_ok ? (uint32_t)f : 0u;  // lanes beyond N_out read a valid column and never store
-    const float bias_f = (p.bias && f_ok) ? p.bias[f] : 0.f;
+  for (long long item = first; item < limit; item += stride, ++it) {
     const uint32_t buf = it & 1, acc_phase = (it >> 1) & 1;
     const uint32_t tbuf = tlane0 + buf * 2 * TC_NMAX;
-    const long long w_tma = t / p.tiles_per_w;
-    const int gsub0 = (int)(t % p.tiles_per_w) * p.G_t;
     mbar_wait(&acc_full[buf], acc_phase);
     tc_fence_after();
-    for (int gi = sub; gi < p.G_t; gi += 2) {
-      const int gsub = gsub0 + gi;
-      if (gsub >= p.n_sub) break;  // warp-uniform
-      const long long g = w_tma * p.n_tot + p.j0 + gsub;   // actual group index
-      const float* __restrict__ cadd_b = CADD ? p.cadd + ((g / p.n_tot_true) * C) * (long long)N : nullptr;
-      const float* __restrict__ res_b = RES ? p.res + g * C * (long long)N : nullptr;
-      float* __restrict__ out_b = p.out + g * C * (long long)N;
-      const uint32_t tcol = tbuf + gi * C;
-      // Single pass: the Jacobian rows of tanh only need d1 = 1 - tanh(x)^2 (value column, read first); sum_k y_k^2
-      // is accumulated on the way and enters the Laplacian row, which is emitted last.
+    while (cur.item == item) {
+      const EpiUnit nxt = find_unit(cur.item, cur.gi + 2, cur.it);
+      const uint32_t fo = cur.fo;
+      const bool f_ok = cur.f_ok;
+      const float bias_f = cur.bias_f;
+      const long long g = cur.g;
+      float* __restrict__ out_b = cur.out_b;
+      const uint32_t tcol = tbuf + cur.gi * C;
       float th = 0.f, d1 = 1.f, s2 = 0.f;
-      const int r0 = (ACT == 0) ? 0 : 1;
-      const int r1 = (ACT == 0) ? C : ((ACT == 1) ? C - 1 : ((C > 1) ? C - 1 : 1));
-      // Rows r0..r1 are walked in chunks of TC_CH, software-pipelined: the addend / residual loads of chunk j+1 are
-      // in flight while chunk j is read from TMEM, transformed and stored (the epilogue is latency-bound on those
-      // loads); chunk 0 is requested before the value column is handled.
-      const bool chunked = r1 - r0 >= TC_CH;
-      float caA[TC_CH], rrA[TC_CH], caB[TC_CH], rrB[TC_CH];
-#define TC_CHUNK_START(j) ((r0 + (j) * TC_CH + TC_CH > r1) ? (r1 - TC_CH) : (r0 + (j) * TC_CH))
-#define TC_CHUNK_LOAD(j, ca, rr)                                  \
-  {                                                               \
-    uint32_t o_ = (uint32_t)TC_CHUNK_START(j) * N + fo;           \
-    _Pragma("unroll") for (int i = 0; i < TC_CH; ++i, o_ += N) { \
-      if (CADD) ca[i] = cadd_b[o_];                               \
-      if (RES) rr[i] = res_b[o_];                                 \
-    }                                                             \
-  }
-      if ((CADD || RES) && chunked) TC_CHUNK_LOAD(0, caA, rrA)
       // ACT == 2: orbital x envelope.  E = sum_I pi exp(-s r_I) for (electron j, orbital i, determinant d) with
       // dE_a = sum_I -s t (r_j - R_I)_a / r_I and lap E = sum_I t (s^2 - 2 s / r_I); product rule per row:
       //   out_0 = y_0 E,  out_c = y_c E (+ y_0 dE_a on the electron's own three rows),
@@ -281,111 +449,136 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& p, uint32_t tlane0
           e_d[2] += c1 * dz;
           e_l += t * (sg * sg - 2.0f * sg * rinv);
         }
-        y0 = tmem_sum1(tcol) + bias_f;
-        if (f_ok) out_b[fo] = y0 * ev;
-      }
-      if (ACT == 1) {
-        float x = tmem_sum1(tcol);
-        if (CADD) x += cadd_b[fo];
-        x += bias_f;
-        th = tanhf(x);
-        d1 = 1.0f - th * th;
       }
       if (chunked) {
-        const int nch = (r1 - r0 + TC_CH - 1) / TC_CH;
-        auto process = [&](int j, const float* ca, const float* rr) {
-          const int cs = TC_CHUNK_START(j);
-          const int skip = r0 + j * TC_CH - cs;  // last chunk: shifted back to stay inside the group's columns
-          float v[TC_CH], v2[TC_CH];
-          tmem_ld8_nowait(tcol + cs, v);
-          tmem_ld8_nowait(tcol + TC_NMAX + cs, v2);
-          tmem_wait_ld();
-          uint32_t o = (uint32_t)cs * N + fo;
+        // next unit's value / Laplacian row operands
+        float n_ca0 = 0.f, n_rr0 = 0.f, n_caL = 0.f, n_rrL = 0.f;
+        if (LD && ACT != 0 && nxt.item < limit) TC_EDGE_LOAD(nxt, n_ca0, n_rr0, n_caL, n_rrL)
+        if (ACT != 0) {   // value row
+          float x = tmem_sum1(tcol);
+          if (CADD) x += ca0;
+          x += bias_f;
+          float o0;
+          if (ACT == 1) {
+            th = tanhf(x);
+            d1 = 1.0f - th * th;
+            o0 = th;
+          } else {
+            y0 = x;
+            o0 = y0 * ev;
+          }
+          if (RES == 1) o0 = (rr0 + o0) * inv_sqrt2;
+          if (RES == 2) o0 = rr0 + o0;
+          if (f_ok) out_b[fo] = o0;
+        }
+        for (int j0 = 0; j0 < nch; j0 += TC_RING) {
 #pragma unroll
-          for (int i = 0; i < TC_CH; ++i, o += N) {
-            float y = v[i] + v2[i];
-            if (CADD) y += ca[i];
-            if (ACT == 1) {
-              if (i >= skip) s2 = fmaf(y, y, s2);
+          for (int s = 0; s < TC_RING; ++s) {
+            const int j = j0 + s;
+            if (j < nch) {
+              const int cs = TC_CHUNK_START(j);
+              const int skip = r0 + j * TC_CH - cs;  // last chunk: shifted back to stay inside the group's columns
+              float v[TC_CH], v2[TC_CH];
+              tmem_ld8_nowait(tcol + cs, v);
+              tmem_ld8_nowait(tcol + TC_NMAX + cs, v2);
+              tmem_wait_ld();
+              uint32_t o = (uint32_t)cs * N + fo;
+#pragma unroll
+              for (int i = 0; i < TC_CH; ++i, o += N) {
+                float y = v[i] + v2[i];
+                if (CADD) y += ca[s][i];
+                if (ACT == 1) {
+                  if (i >= skip) s2 = fmaf(y, y, s2);
+                  y *= d1;
+                }
+                if (ACT == 2) {
+                  const int a = cs + i - own0;
+                  float o2 = y * ev;
+                  if (a >= 0 && a < 3) {
+                    const float da = (a == 0) ? e_d[0] : ((a == 1) ? e_d[1] : e_d[2]);
+                    if (i >= skip) s2 = fmaf(y, da, s2);  // cross term for the Laplacian row
+                    o2 = fmaf(y0, da, o2);
+                  }
+                  y = o2;
+                }
+                if (ACT == 0 && cs + i == 0) y += bias_f;
+                if (RES == 1) y = (rr[s][i] + y) * inv_sqrt2;
+                if (RES == 2) y = rr[s][i] + y;
+                if (f_ok && i >= skip) out_b[o] = y;
+              }
+              // the slot is free: request this group's chunk j + TC_RING, or the next unit's chunk s
+              if (LD) {
+                if (j + TC_RING < nch) TC_CHUNK_LOAD(cur, j + TC_RING, s)
+                else if (nxt.item < limit) TC_CHUNK_LOAD(nxt, s, s)
+              }
+            }
+          }
+        }
+        if (ACT != 0 && C > 1) {   // Laplacian row
+          float yl = tmem_sum1(tcol + C - 1);
+          if (CADD) yl += caL;
+          float l = (ACT == 1) ? d1 * yl - 2.0f * th * d1 * s2 : yl * ev + y0 * e_l + 2.0f * s2;
+          if (RES == 1) l = (rrL + l) * inv_sqrt2;
+          if (RES == 2) l = rrL + l;
+          if (f_ok) out_b[o_last + fo] = l;
+        }
+        ca0 = n_ca0;
+        rr0 = n_rr0;
+        caL = n_caL;
+        rrL = n_rrL;
+      } else {
+        // short groups (value-only sampling path, Local1 inputs): row by row, operands loaded on demand
+        for (int c = 0; c < C; ++c) {
+          float y = tmem_sum1(tcol + c);
+          const uint32_t o = (uint32_t)c * N + fo;
+          if (CADD) y += cur.cadd_b[o];
+          if (ACT == 1) {
+            if (c == 0) {
+              th = tanhf(y + bias_f);
+              d1 = 1.0f - th * th;
+              y = th;
+            } else if (c == C - 1) {
+              y = d1 * y - 2.0f * th * d1 * s2;
+            } else {
+              s2 = fmaf(y, y, s2);
               y *= d1;
             }
-            if (ACT == 2) {
-              const int a = cs + i - own0;
+          } else if (ACT == 2) {
+            if (c == 0) {
+              y0 = y + bias_f;
+              y = y0 * ev;
+            } else if (c == C - 1) {
+              y = y * ev + y0 * e_l + 2.0f * s2;
+            } else {
+              const int a = c - own0;
               float o2 = y * ev;
               if (a >= 0 && a < 3) {
                 const float da = (a == 0) ? e_d[0] : ((a == 1) ? e_d[1] : e_d[2]);
-                if (i >= skip) s2 = fmaf(y, da, s2);  // cross term for the Laplacian row
+                s2 = fmaf(y, da, s2);
                 o2 = fmaf(y0, da, o2);
               }
               y = o2;
             }
-            if (ACT == 0 && cs + i == 0) y += bias_f;
-            if (RES == 1) y = (rr[i] + y) * inv_sqrt2;
-            if (RES == 2) y = rr[i] + y;
-            if (f_ok && i >= skip) out_b[o] = y;
+          } else if (c == 0) {
+            y += bias_f;
           }
-        };
-        for (int j = 0; j < nch; j += 2) {
-          if ((CADD || RES) && j + 1 < nch) TC_CHUNK_LOAD(j + 1, caB, rrB)
-          process(j, caA, rrA);
-          if (j + 1 < nch) {
-            if ((CADD || RES) && j + 2 < nch) TC_CHUNK_LOAD(j + 2, caA, rrA)
-            process(j + 1, caB, rrB);
-          }
-        }
-#undef TC_CHUNK_LOAD
-#undef TC_CHUNK_START
-      } else {
-        for (int c = r0; c < r1; ++c) {
-          float y = tmem_sum1(tcol + c);
-          const uint32_t o = (uint32_t)c * N + fo;
-          if (CADD) y += cadd_b[o];
-          if (ACT == 1) {
-            s2 = fmaf(y, y, s2);
-            y *= d1;
-          }
-          if (ACT == 2) {
-            const int a = c - own0;
-            float o2 = y * ev;
-            if (a >= 0 && a < 3) {
-              const float da = (a == 0) ? e_d[0] : ((a == 1) ? e_d[1] : e_d[2]);
-              s2 = fmaf(y, da, s2);
-              o2 = fmaf(y0, da, o2);
-            }
-            y = o2;
-          }
-          if (ACT == 0 && c == 0) y += bias_f;
-          if (RES == 1) y = (res_b[o] + y) * inv_sqrt2;
-          if (RES == 2) y = res_b[o] + y;
+          if (RES == 1) y = (cur.res_b[o] + y) * inv_sqrt2;
+          if (RES == 2) y = cur.res_b[o] + y;
           if (f_ok) out_b[o] = y;
         }
       }
-      if (ACT == 2 && C > 1) {
-        const float yl = tmem_sum1(tcol + C - 1);
-        if (f_ok) out_b[(uint32_t)(C - 1) * N + fo] = yl * ev + y0 * e_l + 2.0f * s2;
-      }
-      if (ACT == 1) {
-        float yl = (C > 1) ? tmem_sum1(tcol + C - 1) : 0.f;
-        if (f_ok) {
-          if (C > 1) {
-            const uint32_t o = (uint32_t)(C - 1) * N + fo;
-            if (CADD) yl += cadd_b[o];
-            float l = d1 * yl - 2.0f * th * d1 * s2;
-            if (RES == 1) l = (res_b[o] + l) * inv_sqrt2;
-            if (RES == 2) l = res_b[o] + l;
-            out_b[o] = l;
-          }
-          float o0 = th;
-          if (RES == 1) o0 = (res_b[fo] + th) * inv_sqrt2;
-          if (RES == 2) o0 = res_b[fo] + th;
-          out_b[fo] = o0;
-        }
-      }
+      cur = nxt;
     }
     tc_fence_before();
     __syncwarp();
-    if (lane == 0) mbar_arrive(&acc_empty[buf]);
+    if (lane == 0) {
+      if (PAIR) mbar_arrive_cluster(&acc_empty[buf], 0);  // the leader CTA issues the pair's MMAs
+      else mbar_arrive(&acc_empty[buf]);
+    }
   }
+#undef TC_EDGE_LOAD
+#undef TC_CHUNK_LOAD
+#undef TC_CHUNK_START
 }
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
@@ -428,6 +621,8 @@ k_dense_tc(const __grid_constant__ CUtensorMap mapX0, const __grid_constant__ CU
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  if (warp < 8) {
+  setmaxnreg_dec<TC_REGS_PROD>();
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
@@ -515,30 +710,23 @@ k_dense_tc(const __grid_constant__ CUtensorMap mapX0, const __grid_constant__ CU
     for (long long item = blockIdx.x; item < p.items; item += gridDim.x) {
       for (int kc = 0; kc < kchunks; ++kc) {
         mbar_wait(&full[ps.stage], ps.phase);
-        const float4* xh = reinterpret_cast<const float4*>(smem + ps.stage * p.stage_bytes);
-        float4* xl = reinterpret_cast<float4*>(smem + ps.stage * p.stage_bytes + p.x_bytes);
-        for (int i = ct; i < nvec; i += 128) {
-          float4 v = xh[i];
-          float4 l;  // lo = x - trunc_tf32(x): exact, at most 13 significant bits
-          l.x = v.x - __uint_as_float(__float_as_uint(v.x) & 0xffffe000u);
-          l.y = v.y - __uint_as_float(__float_as_uint(v.y) & 0xffffe000u);
-          l.z = v.z - __uint_as_float(__float_as_uint(v.z) & 0xffffe000u);
-          l.w = v.w - __uint_as_float(__float_as_uint(v.w) & 0xffffe000u);
-          xl[i] = l;
-        }
+        const uint32_t raw = smem_u32(smem + ps.stage * p.stage_bytes);
+        convert_lo(raw, raw + (uint32_t)p.x_bytes, nvec, ct);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the MMA
         __syncwarp();
         if (lane == 0) mbar_arrive(&ready[ps.stage]);
         ps.advance(p.stages);
       }
     }
-  } else if (warp >= 8) {
+  }
+  } else {
     // ===================== epilogue =====================
+    setmaxnreg_inc<TC_REGS_EPI>();
     const int q = warp & 3;            // TMEM lane quarter this warp may access
     const int sub = (warp - 8) >> 2;   // which of the quarter's two warps
     const uint32_t tlane0 = tmem_base + ((uint32_t)(q * 32) << 16);
     // one instantiation per (activation, residual mode, addend) combination: no per-element predicates
-#define TC_EPI(ACT, RES, CADD) epilogue_loop<ACT, RES, CADD>(p, tlane0, q, sub, acc_full, acc_empty, lane)
+#define TC_EPI(ACT, RES, CADD) epilogue_loop<ACT, RES, CADD, false>(p, tlane0, q, sub, acc_full, acc_empty, lane)
     const int key = (p.act == 2) ? 16 : ((p.act ? 8 : 0) | (p.res_mode << 1) | (p.cadd ? 1 : 0));
     switch (key) {
       case 16: TC_EPI(2, 0, false); break;
@@ -563,6 +751,202 @@ k_dense_tc(const __grid_constant__ CUtensorMap mapX0, const __grid_constant__ CU
   if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TC_TMEM_COLS) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// CTA-pair variant: weights resident in shared memory.
+//
+// k_dense_tc re-streams the 128-feature hi/lo weight block (32 KB per 32-deep K chunk) for every 88-row tile, which
+// makes the L2 -> SM operand stream (28 GB per FermiNet-N2 layer), not the tensor pipe, its bound.  Here two CTAs of a
+// cluster issue tcgen05.mma.cta_group::2 with M = 128: each CTA contributes 64 features of A and half of the rows of
+// B, so its share of the weights (64 x K x {hi, lo}, 160 KB for K = 320) stays in shared memory for the whole kernel
+// and only activations stream.  The pair's accumulator for N rows occupies N/2 TMEM columns per CTA (lanes 0-63: first
+// half of the rows, lanes 64-127: second half), so a tile is 4 groups of 44 rows instead of 2 with the same
+// main / cross, double-buffered accumulator set.
+//
+//   warp 0 (both CTAs)   TMA: weights once, then the CTA's half of every activation chunk -> local full[s]
+//   warps 4-7 (both)     converter: lo part in place next to the raw tile -> arrive on the LEADER's ready[s]
+//   warp 1 (leader)      MMA issue for the pair; tcgen05.commit multicasts empty[s] / acc_full[b] to both CTAs
+//   warps 8-15 (both)    epilogue of the CTA's 64 features (all rows of the tile) -> arrive on the leader's acc_empty[b]
+// ------------------------------------------------------------------------------------------------
+constexpr int TCP_W_CHUNK = 64 * 128;  // one K chunk of one weight part for 64 features: 8 KB
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
+k_dense_tc_pair(const __grid_constant__ CUtensorMap mapX0, const __grid_constant__ CUtensorMap mapX1,
+                const __grid_constant__ CUtensorMap mapWh, const __grid_constant__ CUtensorMap mapWl, TcParams p) {
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int kchunks = p.kchunks0 + p.kchunks1;
+  const int w_bytes = kchunks * 2 * TCP_W_CHUNK;
+  unsigned char* xring = smem + w_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(xring + p.stages * p.stage_bytes);
+  uint64_t* full = bars;                       // [stages]  local: TMA -> converter
+  uint64_t* ready = bars + TC_MAX_STAGES;      // [stages]  leader's: converters of both CTAs -> MMA
+  uint64_t* empty = bars + 2 * TC_MAX_STAGES;  // [stages]  both (multicast commit): MMA -> TMA
+  uint64_t* acc_full = bars + 3 * TC_MAX_STAGES;   // [2]  both (multicast commit): MMA -> epilogue
+  uint64_t* acc_empty = acc_full + 2;          // [2]  leader's: epilogue warps of both CTAs -> MMA
+  uint64_t* wfull = acc_empty + 2;             // local: weights landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wfull + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int pair_id = (int)(blockIdx.x >> 1);
+  const int hf = pair_id / p.pairs_per_block;
+  const long long t_first = pair_id % p.pairs_per_block;
+  const long long t_limit = hf < p.mblocks ? p.tiles : 0;   // surplus pairs idle
+
+  if (threadIdx.x == 0) {
+    // the carve-up assumes the 1024-byte alignment pad is not needed (the launcher sized the request without it)
+    if (reinterpret_cast<unsigned char*>(tmem_slot + 1) > smem_raw + p.smem_request) __trap();
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&ready[s], 8);   // one arrive per converter warp of either CTA
+      mbar_init(&empty[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&acc_full[b], 1);
+      mbar_init(&acc_empty[b], 16);  // one arrive per epilogue warp of either CTA
+    }
+    mbar_init(wfull, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  cluster_sync_all();   // barriers of both CTAs exist before anyone arrives remotely
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"(TC_TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  cluster_sync_all();   // both CTAs hold their TMEM before the leader's first MMA
+
+  if (warp < 8) {
+  setmaxnreg_dec<TC_REGS_PROD>();
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0 && t_limit > 0) {
+      mbar_expect_tx(wfull, (uint32_t)w_bytes);
+      const int frow = hf * TC_MBLK + (int)rank * 64;
+      for (int kc = 0; kc < kchunks; ++kc) {
+        tma_load_2d(smem + kc * 2 * TCP_W_CHUNK, &mapWh, wfull, kc * TC_BK, frow);
+        tma_load_2d(smem + kc * 2 * TCP_W_CHUNK + TCP_W_CHUNK, &mapWl, wfull, kc * TC_BK, frow);
+      }
+      PipeState ps;
+      const uint32_t stage_tx = (uint32_t)(p.Hp * 128);
+      for (long long t = t_first; t < t_limit; t += p.pairs_per_block) {
+        const long long w = t / p.tiles_per_w;
+        const int gsub0 = (int)(t % p.tiles_per_w) * p.G_t + (int)rank * p.G_h;
+        const int row0 = (p.j0 + gsub0) * p.C;
+        for (int kc = 0; kc < kchunks; ++kc) {
+          mbar_wait(&empty[ps.stage], ps.phase ^ 1);
+          unsigned char* st = xring + ps.stage * p.stage_bytes;
+          mbar_expect_tx(&full[ps.stage], stage_tx);
+          if (kc < p.kchunks0)
+            tma_load_3d(st, &mapX0, &full[ps.stage], kc * TC_BK, row0, (int)w);
+          else
+            tma_load_3d(st, &mapX1, &full[ps.stage], (kc - p.kchunks0) * TC_BK, row0, (int)w);
+          ps.advance(p.stages);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA only) =====================
+    if (rank == 0) {
+      PipeState ps;
+      uint32_t it = 0;
+      const uint32_t idesc = tc_idesc(TC_MBLK, 2 * p.Hp);
+      const uint64_t dw0 = tc_smem_desc(smem_u32(smem));
+      const uint64_t dx0 = tc_smem_desc(smem_u32(xring));
+      const uint64_t w_part = (uint64_t)(TCP_W_CHUNK >> 4), w_chunk = (uint64_t)((2 * TCP_W_CHUNK) >> 4);
+      const uint64_t x_lo = (uint64_t)((p.Hp * 128) >> 4), stage_step = (uint64_t)(p.stage_bytes >> 4);
+      for (long long t = t_first; t < t_limit; t += p.pairs_per_block, ++it) {
+        const uint32_t buf = it & 1, acc_phase = (it >> 1) & 1;
+        mbar_wait(&acc_empty[buf], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_main = tmem_base + buf * 2 * TC_NMAX, d_cross = d_main + TC_NMAX;
+        for (int kc = 0; kc < kchunks; ++kc) {
+          const uint64_t wh = dw0 + w_chunk * (uint64_t)kc, wl = wh + w_part;
+          const uint64_t xh = dx0 + stage_step * (uint64_t)ps.stage, xl = xh + x_lo;
+          const uint32_t acc0 = kc ? 1u : 0u;
+          mbar_wait(&ready[ps.stage], ps.phase);   // raw tile landed and lo part written, in both CTAs
+          tc_fence_after();
+          if (elect_one()) {
+            tc_mma_tf32_pair(d_main, wh, xh, idesc, acc0);
+            tc_mma_tf32_pair(d_cross, wl, xh, idesc, acc0);
+            tc_mma_tf32_pair(d_main, wh + 2, xh + 2, idesc, 1u);
+            tc_mma_tf32_pair(d_cross, wl + 2, xh + 2, idesc, 1u);
+            tc_mma_tf32_pair(d_main, wh + 4, xh + 4, idesc, 1u);
+            tc_mma_tf32_pair(d_cross, wl + 4, xh + 4, idesc, 1u);
+            tc_mma_tf32_pair(d_main, wh + 6, xh + 6, idesc, 1u);
+            tc_mma_tf32_pair(d_cross, wl + 6, xh + 6, idesc, 1u);
+            tc_mma_tf32_pair(d_cross, wh, xl, idesc, 1u);
+            tc_mma_tf32_pair(d_cross, wh + 2, xl + 2, idesc, 1u);
+            tc_mma_tf32_pair(d_cross, wh + 4, xl + 4, idesc, 1u);
+            tc_mma_tf32_pair(d_cross, wh + 6, xl + 6, idesc, 1u);
+            tc_commit_pair(&empty[ps.stage]);
+            if (kc == kchunks - 1) tc_commit_pair(&acc_full[buf]);
+          }
+          __syncwarp();
+          ps.advance(p.stages);
+        }
+      }
+    }
+  } else if (warp >= 4 && warp < 8) {
+    // ===================== converter: Xl = x - trunc_tf32(x) for this CTA's half of the rows =====================
+    if (t_limit > 0) {
+      PipeState ps;
+      const int ct = threadIdx.x - 128;  // 0..127
+      const int nvec = p.Hp * 8;         // float4 per chunk
+      mbar_wait(wfull, 0);               // this CTA's weights are in place before its first `ready` arrival
+      for (long long t = t_first; t < t_limit; t += p.pairs_per_block) {
+        for (int kc = 0; kc < kchunks; ++kc) {
+          mbar_wait(&full[ps.stage], ps.phase);
+          const uint32_t raw = smem_u32(xring + ps.stage * p.stage_bytes);
+          convert_lo(raw, raw + (uint32_t)(p.Hp * 128), nvec, ct);
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(&ready[ps.stage], 0);
+          ps.advance(p.stages);
+        }
+      }
+    }
+  }
+  } else {
+    // ===================== epilogue =====================
+    setmaxnreg_inc<TC_REGS_EPI>();
+    const int q = warp & 3;
+    const int sub = (warp - 8) >> 2;
+    const uint32_t tlane0 = tmem_base + ((uint32_t)(q * 32) << 16);
+#define TC_EPI(ACT, RES, CADD) epilogue_loop<ACT, RES, CADD, true>(p, tlane0, q, sub, acc_full, acc_empty, lane)
+    const int key = (p.act == 2) ? 16 : ((p.act ? 8 : 0) | (p.res_mode << 1) | (p.cadd ? 1 : 0));
+    switch (key) {
+      case 16: TC_EPI(2, 0, false); break;
+      case 0: TC_EPI(0, 0, false); break;
+      case 1: TC_EPI(0, 0, true); break;
+      case 2: TC_EPI(0, 1, false); break;
+      case 3: TC_EPI(0, 1, true); break;
+      case 4: TC_EPI(0, 2, false); break;
+      case 5: TC_EPI(0, 2, true); break;
+      case 8: TC_EPI(1, 0, false); break;
+      case 9: TC_EPI(1, 0, true); break;
+      case 10: TC_EPI(1, 1, false); break;
+      case 11: TC_EPI(1, 1, true); break;
+      case 12: TC_EPI(1, 2, false); break;
+      default: TC_EPI(1, 2, true); break;
+    }
+#undef TC_EPI
+  }
+
+  tc_fence_before();
+  cluster_sync_all();   // the peer's shared memory and TMEM stay alive until both CTAs are done
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TC_TMEM_COLS) : "memory");
   }
 }
 
@@ -632,6 +1016,39 @@ bool jq_dense_tc_eligible(const JqDenseArgs& a) {
   return true;
 }
 
+// Shape of the CTA-pair launch, or false when the weights of one CTA (64 features x K x {hi, lo}) plus a two-stage
+// activation ring do not fit in shared memory (K > 320 for 44-row groups) -> k_dense_tc streams them instead.
+static bool pair_plan(const JqDenseArgs& a, int sm_count, TcParams* p, int* smem_bytes) {
+  static const bool disabled = getenv("JAQMC_B200_DISABLE_TC_PAIR") != nullptr;
+  if (disabled || a.tc_mode == 1) return false;
+  const int kt = a.k0 + a.k1;
+  const int mblocks = jq_cdiv(a.N, TC_MBLK);
+  const int n_pairs = sm_count / 2;
+  if (a.N < 96 || n_pairs < mblocks) return false;
+  int G_h = TC_NMAX / a.C;
+  if (G_h < 1) return false;
+  const long long n_sub = (a.n_sub == a.n_tot) ? a.G : a.n_sub;
+  if ((long long)2 * G_h > n_sub) G_h = (int)((n_sub + 1) / 2);
+  const int Hp = (G_h * a.C + 7) / 8 * 8;
+  const int w_bytes = (kt / TC_BK) * 2 * TCP_W_CHUNK;
+  const int stage_bytes = 2 * Hp * 128;
+  int stages = (TC_SMEM_LIMIT - 256 - w_bytes) / stage_bytes;
+  if (stages < 2) return false;
+  if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
+  p->G_h = G_h;
+  p->G_t = 2 * G_h;
+  p->Hp = Hp;
+  p->stages = stages;
+  p->stage_bytes = stage_bytes;
+  p->pairs_per_block = n_pairs / mblocks;
+  *smem_bytes = w_bytes + stages * stage_bytes + 256;
+  // the dynamic shared-memory window starts 1024-byte aligned on sm_100 (the kernel traps otherwise); keep the pad
+  // whenever it is free
+  if (*smem_bytes + 1024 <= TC_SMEM_LIMIT) *smem_bytes += 1024;
+  p->smem_request = *smem_bytes;
+  return true;
+}
+
 int jq_launch_dense_tc(const JqDenseArgs& a, cudaStream_t st, bool* handled) {
   *handled = false;
   if (!jq_dense_tc_eligible(a)) return JQ_OK;
@@ -643,6 +1060,8 @@ int jq_launch_dense_tc(const JqDenseArgs& a, cudaStream_t st, bool* handled) {
     cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
     cudaError_t e = cudaFuncSetAttribute(k_dense_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT);
     JQ_REQUIRE(e == cudaSuccess, JQ_ERR_CUDA, "dense_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    e = cudaFuncSetAttribute(k_dense_tc_pair, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT);
+    JQ_REQUIRE(e == cudaSuccess, JQ_ERR_CUDA, "dense_tc: cudaFuncSetAttribute (pair): %s", cudaGetErrorString(e));
     attr_set = true;
   }
   const int kt = a.k0 + a.k1;
@@ -678,17 +1097,21 @@ int jq_launch_dense_tc(const JqDenseArgs& a, cudaStream_t st, bool* handled) {
     p.j0 = a.j0;
     Wn = a.G / a.n_sub;
   }
-  if (p.G_t > p.n_sub) p.G_t = p.n_sub;
-  p.n_rows_tile = p.G_t * a.C;
-  p.n_mma = (p.n_rows_tile + 15) / 16 * 16;
+  int smem_bytes = 0;
+  const bool pair = pair_plan(a, sm_count, &p, &smem_bytes);
+  if (!pair) {
+    if (p.G_t > p.n_sub) p.G_t = p.n_sub;
+    p.n_rows_tile = p.G_t * a.C;
+    p.n_mma = (p.n_rows_tile + 15) / 16 * 16;
+    p.x_bytes = p.n_mma * 128;  // multiple of 2048: keeps every operand 1024-byte aligned
+    p.stage_bytes = 2 * p.x_bytes + 2 * TC_W_BYTES;
+    p.stages = (TC_SMEM_LIMIT - TC_SMEM_EXTRA) / p.stage_bytes;
+    if (p.stages > TC_MAX_STAGES) p.stages = TC_MAX_STAGES;
+    smem_bytes = p.stages * p.stage_bytes + TC_SMEM_EXTRA;
+  }
   p.tiles_per_w = jq_cdiv(p.n_sub, p.G_t);
   p.tiles = p.tiles_per_w * Wn;
   p.items = p.tiles * p.mblocks;
-  p.x_bytes = p.n_mma * 128;  // multiple of 2048: keeps every operand 1024-byte aligned
-  p.stage_bytes = 2 * p.x_bytes + 2 * TC_W_BYTES;
-  p.stages = (TC_SMEM_LIMIT - TC_SMEM_EXTRA) / p.stage_bytes;
-  if (p.stages > TC_MAX_STAGES) p.stages = TC_MAX_STAGES;
-  const int smem_bytes = p.stages * p.stage_bytes + TC_SMEM_EXTRA;
   p.G_sub_total = a.G;
   p.bias = a.bias;
   p.cadd = a.cadd;
@@ -706,7 +1129,7 @@ int jq_launch_dense_tc(const JqDenseArgs& a, cudaStream_t st, bool* handled) {
   {
     cuuint64_t dims[3] = {(cuuint64_t)a.k0, (cuuint64_t)p.n_tot * a.C, (cuuint64_t)Wn};
     cuuint64_t str[2] = {(cuuint64_t)a.k0 * 4, (cuuint64_t)p.n_tot * a.C * a.k0 * 4};
-    cuuint32_t box[3] = {TC_BK, (cuuint32_t)p.n_mma, 1};
+    cuuint32_t box[3] = {TC_BK, (cuuint32_t)(pair ? p.Hp : p.n_mma), 1};
     int rc = make_map(&mX0, a.src0, 3, dims, str, box);
     if (rc) return rc;
     if (a.k1 > 0) {
@@ -719,7 +1142,7 @@ int jq_launch_dense_tc(const JqDenseArgs& a, cudaStream_t st, bool* handled) {
     }
     cuuint64_t wd[2] = {(cuuint64_t)kt, (cuuint64_t)a.N};
     cuuint64_t ws[1] = {(cuuint64_t)kt * 4};
-    cuuint32_t wbox[2] = {TC_BK, TC_MBLK};
+    cuuint32_t wbox[2] = {TC_BK, (cuuint32_t)(pair ? 64 : TC_MBLK)};
     rc = make_map(&mWh, wh, 2, wd, ws, wbox);
     if (rc) return rc;
     rc = make_map(&mWl, wl, 2, wd, ws, wbox);
@@ -728,7 +1151,11 @@ int jq_launch_dense_tc(const JqDenseArgs& a, cudaStream_t st, bool* handled) {
   long long grid = p.items < sm_count ? p.items : sm_count;
   double R = (double)a.G * a.C;
   jq_prof_work(2.0 * R * kt * a.N, 4.0 * R * (kt + a.N * (a.res ? 2 : 1)));
-  JQ_LAUNCH(k_dense_tc, dim3((unsigned)grid), dim3(TC_THREADS), smem_bytes, st, mX0, mX1, mWh, mWl, p);
+  if (pair) {
+    JQ_LAUNCH(k_dense_tc_pair, dim3((unsigned)(sm_count / 2 * 2)), dim3(TC_THREADS), smem_bytes, st, mX0, mX1, mWh, mWl, p);
+  } else {
+    JQ_LAUNCH(k_dense_tc, dim3((unsigned)grid), dim3(TC_THREADS), smem_bytes, st, mX0, mX1, mWh, mWl, p);
+  }
   JQ_CHECK_LAUNCH();
   *handled = true;
   return JQ_OK;

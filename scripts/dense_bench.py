@@ -46,25 +46,26 @@ def main():
         p = lambda t: C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)  # noqa: E731
         st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
-        def call():
-            rc = lib.jaqmc_b200_dense_fl(p(x), p(x2), p(k), p(k2), p(bias), p(addend), p(res), p(out), G, Cc, k0, k1, N,
-                                         gpw, act, res_mode, 1, p(ws), ws.numel(), st)
-            _abi.check(lib, rc)
+        for mode, label in ((1, "pair"), (2, "stream")):
+            def call():
+                rc = lib.jaqmc_b200_dense_fl(p(x), p(x2), p(k), p(k2), p(bias), p(addend), p(res), p(out), G, Cc, k0, k1,
+                                             N, gpw, act, res_mode, mode, p(ws), ws.numel(), st)
+                _abi.check(lib, rc)
 
-        for _ in range(3):
-            call()
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        reps = 10
-        e0.record()
-        for _ in range(reps):
-            call()
-        e1.record()
-        torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1) / reps
-        flops = 2.0 * G * Cc * (k0 + k1) * N
-        print(f"{name:10s} rows {G * Cc:9d} K {k0 + k1:4d} N {N:4d}: {ms:7.3f} ms  {flops / ms / 1e9:7.1f} TFLOP/s (x3 products)",
-              flush=True)
+            for _ in range(3):
+                call()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            reps = 10
+            e0.record()
+            for _ in range(reps):
+                call()
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / reps
+            flops = 2.0 * G * Cc * (k0 + k1) * N
+            print(f"{name:10s} {label:6s} rows {G * Cc:9d} K {k0 + k1:4d} N {N:4d}: {ms:7.3f} ms  "
+                  f"{flops / ms / 1e9:7.1f} TFLOP/s (x3 products)", flush=True)
 
 
 if __name__ == "__main__":
