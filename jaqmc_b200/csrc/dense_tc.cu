@@ -109,6 +109,12 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, u
       ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
 }
+// L2 prefetch of a tensor-map box (no shared-memory destination, no barrier)
+__device__ __forceinline__ void tma_prefetch_3d(const CUtensorMap* map, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global [%0, {%1, %2, %3}];" ::"l"(reinterpret_cast<uint64_t>(map)),
+               "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint64_t* bar) {
@@ -294,13 +300,12 @@ constexpr int TC_REGS_EPI = 192; // setmaxnreg: epilogue warpgroups (2 x 128 thr
 constexpr int TC_REGS_PROD = 64; //             TMA / MMA / converter warpgroups; 256 * (192 + 64) = 64 K registers
 
 struct EpiUnit {
-  long long item;   // item (non-pair) or tile (pair) index; >= limit: no more units
+  int item;         // item (non-pair) or tile (pair) index; >= limit: no more units
   int gi;           // group of the tile, within this lane quarter's range
-  uint32_t it;      // ordinal of the item in this CTA's sequence (accumulator buffer / phase)
   uint32_t fo;      // feature, clamped to a valid column
   bool f_ok;
   float bias_f;
-  long long g;      // group index in the activation tensors
+  int g;            // group index in the activation tensors
   const float* cadd_b;
   const float* res_b;
   float* out_b;
@@ -316,49 +321,44 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& p, uint32_t tlane0
   const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
   const int pair_id = (int)(blockIdx.x >> 1);
   const int pair_hf = PAIR ? pair_id / p.pairs_per_block : 0;
-  const long long first = PAIR ? (long long)(pair_id % p.pairs_per_block) : (long long)blockIdx.x;
-  const long long limit = PAIR ? (pair_hf < p.mblocks ? p.tiles : 0) : p.items;
-  const long long stride = PAIR ? (long long)p.pairs_per_block : (long long)gridDim.x;
+  // item / tile / group indices fit in 32 bits (checked by the launcher): all the index arithmetic of the walk,
+  // divisions included, is 32-bit
+  const int first = PAIR ? pair_id % p.pairs_per_block : (int)blockIdx.x;
+  const int limit = PAIR ? (pair_hf < p.mblocks ? (int)p.tiles : 0) : (int)p.items;
+  const int stride = PAIR ? p.pairs_per_block : (int)gridDim.x;
   const int g_first = PAIR ? (q >> 1) * p.G_h : 0;   // first group of the tile this lane quarter sees
   const int g_count = PAIR ? p.G_h : p.G_t;
   const int f_lane = PAIR ? (int)rank * 64 + (q & 1) * 32 + lane : q * 32 + lane;
+  const uint32_t tiles_per_w = (uint32_t)p.tiles_per_w, mblocks = (uint32_t)p.mblocks;
 
-  // (item, gi) -> unit; valid iff the group exists
-  auto unit_ok = [&](long long item, int gi) -> bool {
-    if (item >= limit || gi >= g_count) return false;
-    const long long t = PAIR ? item : item / p.mblocks;
-    return (int)(t % p.tiles_per_w) * p.G_t + g_first + gi < p.n_sub;
-  };
-  auto make_unit = [&](long long item, int gi, uint32_t it) -> EpiUnit {
-    EpiUnit u;
-    u.item = item;
-    u.gi = gi;
-    u.it = it;
-    const long long t = PAIR ? item : item / p.mblocks;
-    const int hf = PAIR ? pair_hf : (int)(item % p.mblocks);
-    const int f = hf * TC_MBLK + f_lane;
-    u.f_ok = f < p.N_out;
-    u.fo = u.f_ok ? (uint32_t)f : 0u;  // lanes beyond N_out read a valid column and never store
-    u.bias_f = (p.bias && u.f_ok) ? p.bias[f] : 0.f;
-    const int gsub = (int)(t % p.tiles_per_w) * p.G_t + g_first + gi;
-    u.g = (t / p.tiles_per_w) * p.n_tot + p.j0 + gsub;
-    u.cadd_b = CADD ? p.cadd + ((u.g / p.n_tot_true) * C) * (long long)N : nullptr;
-    u.res_b = RES ? p.res + u.g * C * (long long)N : nullptr;
-    u.out_b = p.out + u.g * C * (long long)N;
-    return u;
-  };
   // first unit at or after (item, gi) in this warp's walk: groups gi, gi+2, ... of an item, then the next items
-  auto find_unit = [&](long long item, int gi, uint32_t it) -> EpiUnit {
+  auto find_unit = [&](int item, int gi) -> EpiUnit {
+    EpiUnit u;
     while (item < limit) {
-      if (unit_ok(item, gi)) return make_unit(item, gi, it);
+      const uint32_t t = PAIR ? (uint32_t)item : (uint32_t)item / mblocks;
+      const uint32_t w = t / tiles_per_w;
+      const int gsub = (int)(t - w * tiles_per_w) * p.G_t + g_first + gi;
+      const int hf = PAIR ? pair_hf : (int)((uint32_t)item - t * mblocks);
+      const int f = hf * TC_MBLK + f_lane;
+      // N_out is a multiple of 32 (launcher): a warp's 32 features are all inside or all outside the layer
+      if (gi < g_count && gsub < p.n_sub && f - lane < p.N_out) {
+        u.item = item;
+        u.gi = gi;
+        u.f_ok = true;
+        u.fo = (uint32_t)f;
+        u.bias_f = p.bias ? p.bias[f] : 0.f;
+        u.g = (int)w * p.n_tot + p.j0 + gsub;
+        const size_t go = (size_t)u.g * (size_t)C * N;
+        u.cadd_b = CADD ? p.cadd + (size_t)((uint32_t)u.g / (uint32_t)p.n_tot_true) * (size_t)C * N : nullptr;
+        u.res_b = RES ? p.res + go : nullptr;
+        u.out_b = p.out + go;
+        return u;
+      }
       item += stride;
-      ++it;
       gi = sub;
     }
-    EpiUnit u;
     u.item = limit;
     u.gi = 0;
-    u.it = it;
     u.fo = 0;
     u.f_ok = false;
     u.bias_f = 0.f;
@@ -369,23 +369,35 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& p, uint32_t tlane0
     return u;
   };
 
-  // Rows r0..r1 are the chunked ones: all of them without activation, the Jacobian rows otherwise (the value row
+  // Rows [r0, r1) are walked in chunks: all rows without activation, the Jacobian rows otherwise (the value row
   // comes first -- tanh needs d1 = 1 - tanh(x)^2 before the Jacobian rows -- and the Laplacian row last, after
   // sum_k y_k^2 has been accumulated; their two operands travel in scalar registers, one unit ahead as well).
+  // nfull chunks of TC_CH rows go through the register ring, the remaining `tail` (< TC_CH) rows through one more slot.
   const int r0 = (ACT == 0) ? 0 : 1;
   const int r1 = (ACT == 0) ? C : ((ACT == 1) ? C - 1 : ((C > 1) ? C - 1 : 1));
-  const bool chunked = r1 - r0 >= TC_CH;
-  const int nch = chunked ? (r1 - r0 + TC_CH - 1) / TC_CH : 0;
+  const int nfull = (r1 - r0) / TC_CH;
+  const int tail = (r1 - r0) - nfull * TC_CH;
+  const bool chunked = nfull >= 1;
   const uint32_t o_last = (uint32_t)(C - 1) * N;
-  float ca[TC_RING][TC_CH], rr[TC_RING][TC_CH];
+  const uint32_t o_tail = (uint32_t)(r0 + nfull * TC_CH) * N;
+  float ca[TC_RING][TC_CH], rr[TC_RING][TC_CH], caT[TC_CH], rrT[TC_CH];
   float ca0 = 0.f, rr0 = 0.f, caL = 0.f, rrL = 0.f;   // value / Laplacian row operands of the current unit
-#define TC_CHUNK_START(j) ((r0 + (j) * TC_CH + TC_CH > r1) ? (r1 - TC_CH) : (r0 + (j) * TC_CH))
 #define TC_CHUNK_LOAD(u, j, slot)                                    \
   {                                                                  \
-    uint32_t o_ = (uint32_t)TC_CHUNK_START(j) * N + (u).fo;          \
+    uint32_t o_ = (uint32_t)(r0 + (j) * TC_CH) * N + (u).fo;         \
     _Pragma("unroll") for (int i_ = 0; i_ < TC_CH; ++i_, o_ += N) { \
       if (CADD) ca[slot][i_] = (u).cadd_b[o_];                       \
       if (RES) rr[slot][i_] = (u).res_b[o_];                         \
+    }                                                                \
+  }
+#define TC_TAIL_LOAD(u)                                              \
+  {                                                                  \
+    uint32_t o_ = o_tail + (u).fo;                                   \
+    _Pragma("unroll") for (int i_ = 0; i_ < TC_CH - 1; ++i_, o_ += N) { \
+      if (i_ < tail) {                                               \
+        if (CADD) caT[i_] = (u).cadd_b[o_];                          \
+        if (RES) rrT[i_] = (u).res_b[o_];                            \
+      }                                                              \
     }                                                                \
   }
 #define TC_EDGE_LOAD(u, c0_, r0_, cl_, rl_)                          \
@@ -397,28 +409,51 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& p, uint32_t tlane0
       if (RES) rl_ = (u).res_b[o_last + (u).fo];                     \
     }                                                                \
   }
+  // one chunk row: accumulator sum (+ addend) -> activation rule -> residual; `c` is the row's component index
+#define TC_ROW(c, yv, cav, rrv, o)                                     \
+  {                                                                    \
+    float y_ = (yv);                                                   \
+    if (CADD) y_ += (cav);                                             \
+    if (ACT == 1) {                                                    \
+      s2 = fmaf(y_, y_, s2);                                           \
+      y_ *= d1;                                                        \
+    }                                                                  \
+    if (ACT == 2) {                                                    \
+      const int a_ = (c) - own0;                                       \
+      float o2_ = y_ * ev;                                             \
+      if (a_ >= 0 && a_ < 3) {                                         \
+        const float da_ = (a_ == 0) ? e_d[0] : ((a_ == 1) ? e_d[1] : e_d[2]); \
+        s2 = fmaf(y_, da_, s2); /* cross term for the Laplacian row */ \
+        o2_ = fmaf(y0, da_, o2_);                                      \
+      }                                                                \
+      y_ = o2_;                                                        \
+    }                                                                  \
+    if (ACT == 0 && (c) == 0) y_ += bias_f;                            \
+    if (RES == 1) y_ = ((rrv) + y_) * inv_sqrt2;                       \
+    if (RES == 2) y_ = (rrv) + y_;                                     \
+    out_b[o] = y_;                                                     \
+  }
 
-  EpiUnit cur = find_unit(first, sub, 0);
-  if (LD && cur.item < limit) {
-    if (ACT != 0 && chunked) TC_EDGE_LOAD(cur, ca0, rr0, caL, rrL)
-    if (chunked) {
+  EpiUnit cur = find_unit(first, sub);
+  if (LD && chunked && cur.item < limit) {
+    if (ACT != 0) TC_EDGE_LOAD(cur, ca0, rr0, caL, rrL)
 #pragma unroll
-      for (int s = 0; s < TC_RING; ++s)
-        if (s < nch) TC_CHUNK_LOAD(cur, s, s)
-    }
+    for (int s = 0; s < TC_RING; ++s)
+      if (s < nfull) TC_CHUNK_LOAD(cur, s, s)
+    if (tail) TC_TAIL_LOAD(cur)
   }
   uint32_t it = 0;
-  for (long long item = first; item < limit; item += stride, ++it) {
+  for (int item = first; item < limit; item += stride, ++it) {
     const uint32_t buf = it & 1, acc_phase = (it >> 1) & 1;
     const uint32_t tbuf = tlane0 + buf * 2 * TC_NMAX;
     mbar_wait(&acc_full[buf], acc_phase);
     tc_fence_after();
     while (cur.item == item) {
-      const EpiUnit nxt = find_unit(cur.item, cur.gi + 2, cur.it);
+      const EpiUnit nxt = find_unit(cur.item, cur.gi + 2);
+      const bool have_nxt = nxt.item < limit;
       const uint32_t fo = cur.fo;
-      const bool f_ok = cur.f_ok;
       const float bias_f = cur.bias_f;
-      const long long g = cur.g;
+      const int g = cur.g;
       float* __restrict__ out_b = cur.out_b;
       const uint32_t tcol = tbuf + cur.gi * C;
       float th = 0.f, d1 = 1.f, s2 = 0.f;
@@ -430,10 +465,10 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& p, uint32_t tlane0
       int own0 = -8;
       if (ACT == 2) {
         const int nel = p.env.n;
-        const int j = (int)(g % nel);
+        const int j = (int)((uint32_t)g % (uint32_t)nel);
         own0 = 1 + 3 * j;
         const int dd = (int)fo / nel, io = (int)fo % nel;
-        const float* e = p.env.electrons + g * 3;
+        const float* e = p.env.electrons + (size_t)g * 3;
         ev = 0.f;
         for (int I = 0; I < p.env.A; ++I) {
           const float dx = e[0] - p.env.atoms[3 * I], dy = e[1] - p.env.atoms[3 * I + 1], dz = e[2] - p.env.atoms[3 * I + 2];
@@ -453,7 +488,7 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& p, uint32_t tlane0
       if (chunked) {
         // next unit's value / Laplacian row operands
         float n_ca0 = 0.f, n_rr0 = 0.f, n_caL = 0.f, n_rrL = 0.f;
-        if (LD && ACT != 0 && nxt.item < limit) TC_EDGE_LOAD(nxt, n_ca0, n_rr0, n_caL, n_rrL)
+        if (LD && ACT != 0 && have_nxt) TC_EDGE_LOAD(nxt, n_ca0, n_rr0, n_caL, n_rrL)
         if (ACT != 0) {   // value row
           float x = tmem_sum1(tcol);
           if (CADD) x += ca0;
@@ -469,50 +504,40 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& p, uint32_t tlane0
           }
           if (RES == 1) o0 = (rr0 + o0) * inv_sqrt2;
           if (RES == 2) o0 = rr0 + o0;
-          if (f_ok) out_b[fo] = o0;
+          out_b[fo] = o0;
         }
-        for (int j0 = 0; j0 < nch; j0 += TC_RING) {
+        for (int j0 = 0; j0 < nfull; j0 += TC_RING) {
 #pragma unroll
           for (int s = 0; s < TC_RING; ++s) {
             const int j = j0 + s;
-            if (j < nch) {
-              const int cs = TC_CHUNK_START(j);
-              const int skip = r0 + j * TC_CH - cs;  // last chunk: shifted back to stay inside the group's columns
+            if (j < nfull) {
+              const int cs = r0 + j * TC_CH;
               float v[TC_CH], v2[TC_CH];
               tmem_ld8_nowait(tcol + cs, v);
               tmem_ld8_nowait(tcol + TC_NMAX + cs, v2);
               tmem_wait_ld();
               uint32_t o = (uint32_t)cs * N + fo;
 #pragma unroll
-              for (int i = 0; i < TC_CH; ++i, o += N) {
-                float y = v[i] + v2[i];
-                if (CADD) y += ca[s][i];
-                if (ACT == 1) {
-                  if (i >= skip) s2 = fmaf(y, y, s2);
-                  y *= d1;
-                }
-                if (ACT == 2) {
-                  const int a = cs + i - own0;
-                  float o2 = y * ev;
-                  if (a >= 0 && a < 3) {
-                    const float da = (a == 0) ? e_d[0] : ((a == 1) ? e_d[1] : e_d[2]);
-                    if (i >= skip) s2 = fmaf(y, da, s2);  // cross term for the Laplacian row
-                    o2 = fmaf(y0, da, o2);
-                  }
-                  y = o2;
-                }
-                if (ACT == 0 && cs + i == 0) y += bias_f;
-                if (RES == 1) y = (rr[s][i] + y) * inv_sqrt2;
-                if (RES == 2) y = rr[s][i] + y;
-                if (f_ok && i >= skip) out_b[o] = y;
-              }
+              for (int i = 0; i < TC_CH; ++i, o += N) TC_ROW(cs + i, v[i] + v2[i], ca[s][i], rr[s][i], o)
               // the slot is free: request this group's chunk j + TC_RING, or the next unit's chunk s
               if (LD) {
-                if (j + TC_RING < nch) TC_CHUNK_LOAD(cur, j + TC_RING, s)
-                else if (nxt.item < limit) TC_CHUNK_LOAD(nxt, s, s)
+                if (j + TC_RING < nfull) TC_CHUNK_LOAD(cur, j + TC_RING, s)
+                else if (have_nxt) TC_CHUNK_LOAD(nxt, s, s)
               }
             }
           }
+        }
+        if (tail) {
+          const int cs = r0 + nfull * TC_CH;
+          float v[TC_CH], v2[TC_CH];
+          tmem_ld8_nowait(tcol + cs, v);   // columns past the group belong to the next group or are unused: ignored
+          tmem_ld8_nowait(tcol + TC_NMAX + cs, v2);
+          tmem_wait_ld();
+          uint32_t o = o_tail + fo;
+#pragma unroll
+          for (int i = 0; i < TC_CH - 1; ++i, o += N)
+            if (i < tail) TC_ROW(cs + i, v[i] + v2[i], caT[i], rrT[i], o)
+          if (LD && have_nxt) TC_TAIL_LOAD(nxt)
         }
         if (ACT != 0 && C > 1) {   // Laplacian row
           float yl = tmem_sum1(tcol + C - 1);
@@ -520,7 +545,7 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& p, uint32_t tlane0
           float l = (ACT == 1) ? d1 * yl - 2.0f * th * d1 * s2 : yl * ev + y0 * e_l + 2.0f * s2;
           if (RES == 1) l = (rrL + l) * inv_sqrt2;
           if (RES == 2) l = rrL + l;
-          if (f_ok) out_b[o_last + fo] = l;
+          out_b[o_last + fo] = l;
         }
         ca0 = n_ca0;
         rr0 = n_rr0;
@@ -564,7 +589,7 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& p, uint32_t tlane0
           }
           if (RES == 1) y = (cur.res_b[o] + y) * inv_sqrt2;
           if (RES == 2) y = cur.res_b[o] + y;
-          if (f_ok) out_b[o] = y;
+          out_b[o] = y;
         }
       }
       cur = nxt;
@@ -576,9 +601,10 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& p, uint32_t tlane0
       else mbar_arrive(&acc_empty[buf]);
     }
   }
+#undef TC_ROW
+#undef TC_TAIL_LOAD
 #undef TC_EDGE_LOAD
 #undef TC_CHUNK_LOAD
-#undef TC_CHUNK_START
 }
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
@@ -594,7 +620,7 @@ k_dense_tc(const __grid_constant__ CUtensorMap mapX0, const __grid_constant__ CU
   uint64_t* acc_empty = acc_full + 2;          // [2]  epilogue -> MMA
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);  // warp-uniform for the compiler (uniform registers / branches)
   const int lane = threadIdx.x & 31;
   const int kchunks = p.kchunks0 + p.kchunks1;
 
@@ -771,6 +797,7 @@ k_dense_tc(const __grid_constant__ CUtensorMap mapX0, const __grid_constant__ CU
 //   warps 8-15 (both)    epilogue of the CTA's 64 features (all rows of the tile) -> arrive on the leader's acc_empty[b]
 // ------------------------------------------------------------------------------------------------
 constexpr int TCP_W_CHUNK = 64 * 128;  // one K chunk of one weight part for 64 features: 8 KB
+constexpr int TCP_PREFETCH = 0;       // activation tiles requested into L2 ahead of the shared-memory ring
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
 k_dense_tc_pair(const __grid_constant__ CUtensorMap mapX0, const __grid_constant__ CUtensorMap mapX1,
@@ -789,7 +816,7 @@ k_dense_tc_pair(const __grid_constant__ CUtensorMap mapX0, const __grid_constant
   uint64_t* wfull = acc_empty + 2;             // local: weights landed
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wfull + 1);
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);  // warp-uniform for the compiler (uniform registers / branches)
   const int lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
   const int pair_id = (int)(blockIdx.x >> 1);
@@ -838,10 +865,23 @@ k_dense_tc_pair(const __grid_constant__ CUtensorMap mapX0, const __grid_constant
       }
       PipeState ps;
       const uint32_t stage_tx = (uint32_t)(p.Hp * 128);
+      // The ring holds three chunks per CTA, about one DRAM latency of MMA time: the activation tile of the item
+      // TCP_PREFETCH steps ahead is pulled into L2 while this one streams, so the ring's loads are L2 hits.
+      auto prefetch_tile = [&](long long t) {
+        if (t >= t_limit) return;
+        const long long w = t / p.tiles_per_w;
+        const int row0 = (p.j0 + (int)(t % p.tiles_per_w) * p.G_t + (int)rank * p.G_h) * p.C;
+        for (int kc = 0; kc < kchunks; ++kc) {
+          if (kc < p.kchunks0) tma_prefetch_3d(&mapX0, kc * TC_BK, row0, (int)w);
+          else tma_prefetch_3d(&mapX1, (kc - p.kchunks0) * TC_BK, row0, (int)w);
+        }
+      };
+      for (int a = 0; a < TCP_PREFETCH; ++a) prefetch_tile(t_first + (long long)a * p.pairs_per_block);
       for (long long t = t_first; t < t_limit; t += p.pairs_per_block) {
         const long long w = t / p.tiles_per_w;
         const int gsub0 = (int)(t % p.tiles_per_w) * p.G_t + (int)rank * p.G_h;
         const int row0 = (p.j0 + gsub0) * p.C;
+        prefetch_tile(t + (long long)TCP_PREFETCH * p.pairs_per_block);
         for (int kc = 0; kc < kchunks; ++kc) {
           mbar_wait(&empty[ps.stage], ps.phase ^ 1);
           unsigned char* st = xring + ps.stage * p.stage_bytes;
@@ -1010,7 +1050,7 @@ bool jq_dense_tc_eligible(const JqDenseArgs& a) {
   if (a.C > TC_NMAX) return false;
   if (a.k0 % TC_BK || a.k1 % TC_BK) return false;
   if (a.k0 + a.k1 < 32) return false;
-  if (a.N < 64 || a.N > 2 * TC_MBLK) return false;
+  if (a.N < 64 || a.N > 2 * TC_MBLK || a.N % 32) return false;   // a warp's 32 features are all valid or all not
   if (!a.wscratch) return false;
   if ((reinterpret_cast<uintptr_t>(a.src0) & 15) || (a.src1 && (reinterpret_cast<uintptr_t>(a.src1) & 15))) return false;
   return true;
@@ -1112,6 +1152,7 @@ int jq_launch_dense_tc(const JqDenseArgs& a, cudaStream_t st, bool* handled) {
   p.tiles_per_w = jq_cdiv(p.n_sub, p.G_t);
   p.tiles = p.tiles_per_w * Wn;
   p.items = p.tiles * p.mblocks;
+  JQ_REQUIRE(p.items < 0x7fffffffLL && a.G < 0x7fffffffLL, JQ_ERR_UNSUPPORTED, "dense_tc: too many tiles");
   p.G_sub_total = a.G;
   p.bias = a.bias;
   p.cadd = a.cadd;
