@@ -781,23 +781,57 @@ k_dense_tc(const __grid_constant__ CUtensorMap mapX0, const __grid_constant__ CU
 }
 
 // ------------------------------------------------------------------------------------------------
-// CTA-pair variant: weights resident in shared memory.
+// CTA-pair variant: weights resident in shared memory, activation ring of raw tiles converted in place.
 //
-// k_dense_tc re-streams the 128-feature hi/lo weight block (32 KB per 32-deep K chunk) for every 88-row tile, which
-// makes the L2 -> SM operand stream (28 GB per FermiNet-N2 layer), not the tensor pipe, its bound.  Here two CTAs of a
-// cluster issue tcgen05.mma.cta_group::2 with M = 128: each CTA contributes 64 features of A and half of the rows of
-// B, so its share of the weights (64 x K x {hi, lo}, 160 KB for K = 320) stays in shared memory for the whole kernel
-// and only activations stream.  The pair's accumulator for N rows occupies N/2 TMEM columns per CTA (lanes 0-63: first
-// half of the rows, lanes 64-127: second half), so a tile is 4 groups of 44 rows instead of 2 with the same
-// main / cross, double-buffered accumulator set.
+// k_dense_tc re-streams the 128-feature hi/lo weight block (32 KB per 32-deep K chunk) for every 88-row tile and has
+// room for a 4-deep ring only.  Here two CTAs of a cluster issue tcgen05.mma.cta_group::2 with M = 128: each CTA
+// contributes 64 features of A and half of the rows of B, so its share of the weights (64 x K x {hi, lo}, 160 KB for
+// K = 320) stays in shared memory for the whole kernel and only activations stream.  The pair's accumulator for N rows
+// occupies N/2 TMEM columns per CTA (lanes 0-63: first half of the rows, lanes 64-127: second half), so a tile is 4
+// groups of 44 rows instead of 2 with the same main / cross, double-buffered accumulator set.
 //
-//   warp 0 (both CTAs)   TMA: weights once, then the CTA's half of every activation chunk -> local full[s]
-//   warps 4-7 (both)     converter: lo part in place next to the raw tile -> arrive on the LEADER's ready[s]
-//   warp 1 (leader)      MMA issue for the pair; tcgen05.commit multicasts empty[s] / acc_full[b] to both CTAs
+// What remains of shared memory (66 KB) is the activation ring.  A slot holds ONE 11 KB tile: the two products that
+// read the raw tile (Wh.Xraw, Wl.Xraw; the tensor core truncates raw FP32 to the TF32 hi part) are issued when TMA
+// lands, the converter then overwrites the tile with its lo part, and the third product (Wh.Xlo) follows TCP_LAG chunks
+// behind in the issue order.  Six slots instead of three, i.e. about one DRAM latency of MMA time in flight.
+//
+// Bound (measured r1m by switching stages off: loads + MMAs alone 1.50 ms, + conversion 1.84, + epilogue arithmetic
+// 1.94, + epilogue loads / stores 2.41 ms for the FermiNet-N2 layer): SHARED-MEMORY BANDWIDTH, not the tensor pipe.
+// A TF32 MMA of the pair (M 128 x N 176 x K 8, 44 cycles) reads 2 KB of A and 2.8 KB of B from each CTA's shared
+// memory, 110 B/cycle of the SM's 128; with the TMA writes, the converter's read + write and the epilogue's
+// global loads / stores (same SRAM data path) a 176-row item moves ~1.05 MB per SM, 8.2 k cycles against 5.3 k of
+// tensor time.  3xTF32 at these tile shapes (M = 64 per CTA because the weights must fit, N bounded by TMEM) cannot
+// reach the tensor roofline; the streaming kernel (M 128 x N 96: 146 B/cycle of operands) is further away still.
+//
+//   warp 0 (both CTAs)   TMA: weights once -> leader's wfull; the CTA's half of every activation chunk -> leader's full[s]
+//   warp 1 (leader)      MMA issue for the pair; tcgen05.commit multicasts raw_done[s] / empty[s] / acc_full[b]
+//   warps 4-7 (both)     converter: raw_done[s] -> lo in place -> arrive on the leader's ready[s]
 //   warps 8-15 (both)    epilogue of the CTA's 64 features (all rows of the tile) -> arrive on the leader's acc_empty[b]
 // ------------------------------------------------------------------------------------------------
 constexpr int TCP_W_CHUNK = 64 * 128;  // one K chunk of one weight part for 64 features: 8 KB
-constexpr int TCP_PREFETCH = 0;       // activation tiles requested into L2 ahead of the shared-memory ring
+constexpr int TCP_MAX_STAGES = 8;
+constexpr int TCP_LAG = 2;             // chunks between the raw products and the lo product in the MMA issue order
+constexpr int TCP_BAR_BYTES = 512;
+
+// TMA load of this CTA's box whose completion bytes are counted on the LEADER CTA's mbarrier (same offset, rank 0)
+__device__ __forceinline__ void tma_load_3d_pair(void* dst, const CUtensorMap* map, uint32_t leader_bar, int c0, int c1,
+                                                 int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(leader_bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_pair(void* dst, const CUtensorMap* map, uint32_t leader_bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(leader_bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ uint32_t mapa_u32(const void* p, uint32_t cta) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_u32(p)), "r"(cta));
+  return r;
+}
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
 k_dense_tc_pair(const __grid_constant__ CUtensorMap mapX0, const __grid_constant__ CUtensorMap mapX1,
@@ -806,30 +840,34 @@ k_dense_tc_pair(const __grid_constant__ CUtensorMap mapX0, const __grid_constant
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int kchunks = p.kchunks0 + p.kchunks1;
   const int w_bytes = kchunks * 2 * TCP_W_CHUNK;
+  const int S = p.stages;
   unsigned char* xring = smem + w_bytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(xring + p.stages * p.stage_bytes);
-  uint64_t* full = bars;                       // [stages]  local: TMA -> converter
-  uint64_t* ready = bars + TC_MAX_STAGES;      // [stages]  leader's: converters of both CTAs -> MMA
-  uint64_t* empty = bars + 2 * TC_MAX_STAGES;  // [stages]  both (multicast commit): MMA -> TMA
-  uint64_t* acc_full = bars + 3 * TC_MAX_STAGES;   // [2]  both (multicast commit): MMA -> epilogue
-  uint64_t* acc_empty = acc_full + 2;          // [2]  leader's: epilogue warps of both CTAs -> MMA
-  uint64_t* wfull = acc_empty + 2;             // local: weights landed
+  uint64_t* bars = reinterpret_cast<uint64_t*>(xring + S * p.stage_bytes);
+  uint64_t* full = bars;                            // [S] leader's: TMA bytes of both CTAs -> MMA (raw products)
+  uint64_t* raw_done = bars + TCP_MAX_STAGES;       // [S] both (multicast commit): raw products done -> converter
+  uint64_t* ready = bars + 2 * TCP_MAX_STAGES;      // [S] leader's: converters of both CTAs -> MMA (lo product)
+  uint64_t* empty = bars + 3 * TCP_MAX_STAGES;      // [S] both (multicast commit): lo product done -> TMA
+  uint64_t* acc_full = bars + 4 * TCP_MAX_STAGES;   // [2] both (multicast commit): MMA -> epilogue
+  uint64_t* acc_empty = acc_full + 2;               // [2] leader's: epilogue warps of both CTAs -> MMA
+  uint64_t* wfull = acc_empty + 2;                  // leader's: weights of both CTAs landed
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wfull + 1);
 
-  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);  // warp-uniform for the compiler (uniform registers / branches)
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);  // warp-uniform for the compiler
   const int lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
   const int pair_id = (int)(blockIdx.x >> 1);
   const int hf = pair_id / p.pairs_per_block;
-  const long long t_first = pair_id % p.pairs_per_block;
-  const long long t_limit = hf < p.mblocks ? p.tiles : 0;   // surplus pairs idle
+  const int t_first = pair_id % p.pairs_per_block;
+  const int t_limit = hf < p.mblocks ? (int)p.tiles : 0;   // surplus pairs idle
+  const int t_stride = p.pairs_per_block;
 
   if (threadIdx.x == 0) {
     // the carve-up assumes the 1024-byte alignment pad is not needed (the launcher sized the request without it)
     if (reinterpret_cast<unsigned char*>(tmem_slot + 1) > smem_raw + p.smem_request) __trap();
-    for (int s = 0; s < p.stages; ++s) {
-      mbar_init(&full[s], 1);
-      mbar_init(&ready[s], 8);   // one arrive per converter warp of either CTA
+    for (int s = 0; s < S; ++s) {
+      mbar_init(&full[s], 1);      // the leader's producer arrives (expect_tx of both halves)
+      mbar_init(&raw_done[s], 1);
+      mbar_init(&ready[s], 8);     // one arrive per converter warp of either CTA
       mbar_init(&empty[s], 1);
     }
     for (int b = 0; b < 2; ++b) {
@@ -857,102 +895,122 @@ k_dense_tc_pair(const __grid_constant__ CUtensorMap mapX0, const __grid_constant
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0 && t_limit > 0) {
-      mbar_expect_tx(wfull, (uint32_t)w_bytes);
+      const uint32_t stage_tx = (uint32_t)(p.Hp * 128);
+      if (rank == 0) mbar_expect_tx(wfull, 2u * (uint32_t)w_bytes);
+      const uint32_t wfull_l = mapa_u32(wfull, 0);
       const int frow = hf * TC_MBLK + (int)rank * 64;
       for (int kc = 0; kc < kchunks; ++kc) {
-        tma_load_2d(smem + kc * 2 * TCP_W_CHUNK, &mapWh, wfull, kc * TC_BK, frow);
-        tma_load_2d(smem + kc * 2 * TCP_W_CHUNK + TCP_W_CHUNK, &mapWl, wfull, kc * TC_BK, frow);
+        tma_load_2d_pair(smem + kc * 2 * TCP_W_CHUNK, &mapWh, wfull_l, kc * TC_BK, frow);
+        tma_load_2d_pair(smem + kc * 2 * TCP_W_CHUNK + TCP_W_CHUNK, &mapWl, wfull_l, kc * TC_BK, frow);
       }
       PipeState ps;
-      const uint32_t stage_tx = (uint32_t)(p.Hp * 128);
-      // The ring holds three chunks per CTA, about one DRAM latency of MMA time: the activation tile of the item
-      // TCP_PREFETCH steps ahead is pulled into L2 while this one streams, so the ring's loads are L2 hits.
-      auto prefetch_tile = [&](long long t) {
-        if (t >= t_limit) return;
-        const long long w = t / p.tiles_per_w;
-        const int row0 = (p.j0 + (int)(t % p.tiles_per_w) * p.G_t + (int)rank * p.G_h) * p.C;
-        for (int kc = 0; kc < kchunks; ++kc) {
-          if (kc < p.kchunks0) tma_prefetch_3d(&mapX0, kc * TC_BK, row0, (int)w);
-          else tma_prefetch_3d(&mapX1, (kc - p.kchunks0) * TC_BK, row0, (int)w);
-        }
-      };
-      for (int a = 0; a < TCP_PREFETCH; ++a) prefetch_tile(t_first + (long long)a * p.pairs_per_block);
-      for (long long t = t_first; t < t_limit; t += p.pairs_per_block) {
-        const long long w = t / p.tiles_per_w;
-        const int gsub0 = (int)(t % p.tiles_per_w) * p.G_t + (int)rank * p.G_h;
+      const uint32_t full_l0 = mapa_u32(&full[0], 0);
+      for (int t = t_first; t < t_limit; t += t_stride) {
+        const int w = (int)((uint32_t)t / (uint32_t)p.tiles_per_w);
+        const int gsub0 = (t - w * (int)p.tiles_per_w) * p.G_t + (int)rank * p.G_h;
         const int row0 = (p.j0 + gsub0) * p.C;
-        prefetch_tile(t + (long long)TCP_PREFETCH * p.pairs_per_block);
         for (int kc = 0; kc < kchunks; ++kc) {
           mbar_wait(&empty[ps.stage], ps.phase ^ 1);
           unsigned char* st = xring + ps.stage * p.stage_bytes;
-          mbar_expect_tx(&full[ps.stage], stage_tx);
+          if (rank == 0) mbar_expect_tx(&full[ps.stage], 2u * stage_tx);
+          const uint32_t fb = full_l0 + 8u * (uint32_t)ps.stage;
           if (kc < p.kchunks0)
-            tma_load_3d(st, &mapX0, &full[ps.stage], kc * TC_BK, row0, (int)w);
+            tma_load_3d_pair(st, &mapX0, fb, kc * TC_BK, row0, w);
           else
-            tma_load_3d(st, &mapX1, &full[ps.stage], (kc - p.kchunks0) * TC_BK, row0, (int)w);
-          ps.advance(p.stages);
+            tma_load_3d_pair(st, &mapX1, fb, (kc - p.kchunks0) * TC_BK, row0, w);
+          ps.advance(S);
         }
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (leader CTA only) =====================
-    if (rank == 0) {
-      PipeState ps;
-      uint32_t it = 0;
+    if (rank == 0 && t_limit > 0) {
       const uint32_t idesc = tc_idesc(TC_MBLK, 2 * p.Hp);
       const uint64_t dw0 = tc_smem_desc(smem_u32(smem));
       const uint64_t dx0 = tc_smem_desc(smem_u32(xring));
       const uint64_t w_part = (uint64_t)(TCP_W_CHUNK >> 4), w_chunk = (uint64_t)((2 * TCP_W_CHUNK) >> 4);
-      const uint64_t x_lo = (uint64_t)((p.Hp * 128) >> 4), stage_step = (uint64_t)(p.stage_bytes >> 4);
-      for (long long t = t_first; t < t_limit; t += p.pairs_per_block, ++it) {
-        const uint32_t buf = it & 1, acc_phase = (it >> 1) & 1;
-        mbar_wait(&acc_empty[buf], acc_phase ^ 1);
-        tc_fence_after();
-        const uint32_t d_main = tmem_base + buf * 2 * TC_NMAX, d_cross = d_main + TC_NMAX;
-        for (int kc = 0; kc < kchunks; ++kc) {
-          const uint64_t wh = dw0 + w_chunk * (uint64_t)kc, wl = wh + w_part;
-          const uint64_t xh = dx0 + stage_step * (uint64_t)ps.stage, xl = xh + x_lo;
-          const uint32_t acc0 = kc ? 1u : 0u;
-          mbar_wait(&ready[ps.stage], ps.phase);   // raw tile landed and lo part written, in both CTAs
+      const uint64_t stage_step = (uint64_t)(p.stage_bytes >> 4);
+      const int n_items = (t_limit - t_first + t_stride - 1) / t_stride;
+      const int total = n_items * kchunks;
+      // head: raw products of chunk c; tail: lo product of chunk c - TCP_LAG
+      PipeState hs, ts;
+      int h_kc = 0, t_kc = 0;
+      uint32_t h_it = 0, t_it = 0;
+      mbar_wait(wfull, 0);
+      tc_fence_after();
+      for (int c = 0; c < total + TCP_LAG; ++c) {
+        // the lo product first: the raw products of a new item may wait for an accumulator that this one completes
+        if (c >= TCP_LAG) {
+          const uint32_t buf = t_it & 1;
+          const uint32_t d_cross = tmem_base + buf * 2 * TC_NMAX + TC_NMAX;
+          const uint64_t wh = dw0 + w_chunk * (uint64_t)t_kc;
+          const uint64_t x = dx0 + stage_step * (uint64_t)ts.stage;
+          mbar_wait(&ready[ts.stage], ts.phase);   // lo parts written, in both CTAs
           tc_fence_after();
           if (elect_one()) {
-            tc_mma_tf32_pair(d_main, wh, xh, idesc, acc0);
-            tc_mma_tf32_pair(d_cross, wl, xh, idesc, acc0);
-            tc_mma_tf32_pair(d_main, wh + 2, xh + 2, idesc, 1u);
-            tc_mma_tf32_pair(d_cross, wl + 2, xh + 2, idesc, 1u);
-            tc_mma_tf32_pair(d_main, wh + 4, xh + 4, idesc, 1u);
-            tc_mma_tf32_pair(d_cross, wl + 4, xh + 4, idesc, 1u);
-            tc_mma_tf32_pair(d_main, wh + 6, xh + 6, idesc, 1u);
-            tc_mma_tf32_pair(d_cross, wl + 6, xh + 6, idesc, 1u);
-            tc_mma_tf32_pair(d_cross, wh, xl, idesc, 1u);
-            tc_mma_tf32_pair(d_cross, wh + 2, xl + 2, idesc, 1u);
-            tc_mma_tf32_pair(d_cross, wh + 4, xl + 4, idesc, 1u);
-            tc_mma_tf32_pair(d_cross, wh + 6, xl + 6, idesc, 1u);
-            tc_commit_pair(&empty[ps.stage]);
-            if (kc == kchunks - 1) tc_commit_pair(&acc_full[buf]);
+            tc_mma_tf32_pair(d_cross, wh, x, idesc, 1u);
+            tc_mma_tf32_pair(d_cross, wh + 2, x + 2, idesc, 1u);
+            tc_mma_tf32_pair(d_cross, wh + 4, x + 4, idesc, 1u);
+            tc_mma_tf32_pair(d_cross, wh + 6, x + 6, idesc, 1u);
+            tc_commit_pair(&empty[ts.stage]);
+            if (t_kc == kchunks - 1) tc_commit_pair(&acc_full[buf]);
           }
           __syncwarp();
-          ps.advance(p.stages);
+          ts.advance(S);
+          if (++t_kc == kchunks) {
+            t_kc = 0;
+            ++t_it;
+          }
+        }
+        if (c < total) {
+          const uint32_t buf = h_it & 1;
+          if (h_kc == 0) {
+            mbar_wait(&acc_empty[buf], ((h_it >> 1) & 1) ^ 1);   // epilogue has drained this buffer (two items ago)
+            tc_fence_after();
+          }
+          const uint32_t d_main = tmem_base + buf * 2 * TC_NMAX, d_cross = d_main + TC_NMAX;
+          const uint64_t wh = dw0 + w_chunk * (uint64_t)h_kc, wl = wh + w_part;
+          const uint64_t x = dx0 + stage_step * (uint64_t)hs.stage;
+          const uint32_t acc0 = h_kc ? 1u : 0u;
+          mbar_wait(&full[hs.stage], hs.phase);   // raw tiles of both CTAs landed
+          tc_fence_after();
+          if (elect_one()) {
+            // 8 tf32 = 32 bytes along K inside the 128 B swizzle row: +2 in the address field per K step
+            tc_mma_tf32_pair(d_main, wh, x, idesc, acc0);
+            tc_mma_tf32_pair(d_cross, wl, x, idesc, acc0);
+            tc_mma_tf32_pair(d_main, wh + 2, x + 2, idesc, 1u);
+            tc_mma_tf32_pair(d_cross, wl + 2, x + 2, idesc, 1u);
+            tc_mma_tf32_pair(d_main, wh + 4, x + 4, idesc, 1u);
+            tc_mma_tf32_pair(d_cross, wl + 4, x + 4, idesc, 1u);
+            tc_mma_tf32_pair(d_main, wh + 6, x + 6, idesc, 1u);
+            tc_mma_tf32_pair(d_cross, wl + 6, x + 6, idesc, 1u);
+            tc_commit_pair(&raw_done[hs.stage]);   // the converters may overwrite the tile with its lo part
+          }
+          __syncwarp();
+          hs.advance(S);
+          if (++h_kc == kchunks) {
+            h_kc = 0;
+            ++h_it;
+          }
         }
       }
     }
-  } else if (warp >= 4 && warp < 8) {
-    // ===================== converter: Xl = x - trunc_tf32(x) for this CTA's half of the rows =====================
+  } else if (warp >= 4) {
+    // ===================== converter: tile <- x - trunc_tf32(x), in place, for this CTA's half of the rows =========
     if (t_limit > 0) {
       PipeState ps;
       const int ct = threadIdx.x - 128;  // 0..127
       const int nvec = p.Hp * 8;         // float4 per chunk
-      mbar_wait(wfull, 0);               // this CTA's weights are in place before its first `ready` arrival
-      for (long long t = t_first; t < t_limit; t += p.pairs_per_block) {
-        for (int kc = 0; kc < kchunks; ++kc) {
-          mbar_wait(&full[ps.stage], ps.phase);
-          const uint32_t raw = smem_u32(xring + ps.stage * p.stage_bytes);
-          convert_lo(raw, raw + (uint32_t)(p.Hp * 128), nvec, ct);
-          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-          __syncwarp();
-          if (lane == 0) mbar_arrive_cluster(&ready[ps.stage], 0);
-          ps.advance(p.stages);
-        }
+      const int n_items = (t_limit - t_first + t_stride - 1) / t_stride;
+      const int total = n_items * kchunks;
+      for (int c = 0; c < total; ++c) {
+        mbar_wait(&raw_done[ps.stage], ps.phase);
+        const uint32_t raw = smem_u32(xring + ps.stage * p.stage_bytes);
+        convert_lo(raw, raw, nvec, ct);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(&ready[ps.stage], 0);
+        ps.advance(S);
       }
     }
   }
@@ -1071,17 +1129,17 @@ static bool pair_plan(const JqDenseArgs& a, int sm_count, TcParams* p, int* smem
   if ((long long)2 * G_h > n_sub) G_h = (int)((n_sub + 1) / 2);
   const int Hp = (G_h * a.C + 7) / 8 * 8;
   const int w_bytes = (kt / TC_BK) * 2 * TCP_W_CHUNK;
-  const int stage_bytes = 2 * Hp * 128;
-  int stages = (TC_SMEM_LIMIT - 256 - w_bytes) / stage_bytes;
-  if (stages < 2) return false;
-  if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
+  const int stage_bytes = Hp * 128;   // one raw tile, converted to its lo part in place
+  int stages = (TC_SMEM_LIMIT - TCP_BAR_BYTES - w_bytes) / stage_bytes;
+  if (stages < TCP_LAG + 2) return false;
+  if (stages > TCP_MAX_STAGES) stages = TCP_MAX_STAGES;
   p->G_h = G_h;
   p->G_t = 2 * G_h;
   p->Hp = Hp;
   p->stages = stages;
   p->stage_bytes = stage_bytes;
   p->pairs_per_block = n_pairs / mblocks;
-  *smem_bytes = w_bytes + stages * stage_bytes + 256;
+  *smem_bytes = w_bytes + stages * stage_bytes + TCP_BAR_BYTES;
   // the dynamic shared-memory window starts 1024-byte aligned on sm_100 (the kernel traps otherwise); keep the pad
   // whenever it is free
   if (*smem_bytes + 1024 <= TC_SMEM_LIMIT) *smem_bytes += 1024;
