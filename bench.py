@@ -319,6 +319,27 @@ def run_ours(args):
     e2e_value = W * args.steps / (ms_e2e * 1e-3)
     finite = bool(torch.isfinite(e_host).all())
 
+    # second half of the BASELINE metric: sampling + energy part of one VMC iteration (workflow/stage/vmc.py:227-265):
+    # 10 MH sub-steps (11 value-only forward passes) followed by one local-energy evaluation; gradients and the
+    # optimizer stay in the reference's JAX code and are not part of this number
+    def vmc_iteration():
+        nonlocal data, st
+        data, _, st = plan.step(params, data, st, gen)
+        sums.zero_()
+        wf.local_energy(params, data, sums=sums)
+        if dist:
+            torch.distributed.all_reduce(sums)
+
+    vmc = None
+    if not args.no_vmc:
+        for _ in range(2):
+            vmc_iteration()
+        k_vmc = min(args.steps, 5)
+        ms_vmc = timed(vmc_iteration, k_vmc)
+        vmc = {"iters_per_sec": round(k_vmc / (ms_vmc * 1e-3), 2), "ms_per_iter": round(ms_vmc / k_vmc, 3),
+               "what": "10 MH sub-steps + 1 forward-Laplacian local-energy evaluation of all walkers "
+                       "(no parameter gradients / optimizer: those stay in JAX)"}
+
     # roofline leg: per-kernel CUDA events on the launch stream over the same steps (rank 0 only)
     roof, kernels = None, None
     if rank == 0:
@@ -341,11 +362,12 @@ def run_ours(args):
         peaks, src = load_peaks()
         kname = name.split("@")[0]
         per_launch_ms = v["ms"] / v["launches"]
+        # DRAM bytes of the same launch from an `ncu --set full` capture (profiles/ncu_traffic.json, per launch)
         traffic = None
-        tpath = os.path.join(ROOT, "profiles", "r1_dense_tc_ncu.json")
-        if kname == "k_dense_tc" and args.workload == "n2" and W // world == 4096 and os.path.exists(tpath):
+        tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+        if os.path.exists(tpath):
             with open(tpath) as f:
-                traffic = json.load(f).get("k_dense_tc_main_layer_traffic_bytes")
+                traffic = json.load(f).get(f"{kname}@{args.workload}@{W // world}", {}).get("dram_bytes")
         if v["flops"] > 0:
             # 3xTF32: three tensor-core products per multiply-add; TF32 runs at half the bf16 rate
             peak = peaks["bf16_tflops_sustained"] / 2.0 / 3.0
@@ -387,6 +409,8 @@ def run_ours(args):
                     "d2h_bytes_per_step": int(Wl * 4) * world, "finite": finite},
             "gpu_launches": int(launches), "clocks": clk, "roofline": roof, "kernels": kernels,
         }
+        if vmc is not None:
+            line["vmc_iteration"] = vmc
         if cpu is not None:
             line["cpu_baseline"] = cpu
         print(json.dumps(line), flush=True)
@@ -405,6 +429,7 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch the kernels one by one instead of replaying a CUDA graph")
+    ap.add_argument("--no-vmc", action="store_true", help="skip the MH + energy iteration timing")
     ap.add_argument("--no-equilibrate", action="store_true", help="skip the MH sweeps before timing (profiling runs)")
     args = ap.parse_args()
     if args.impl == "reference":

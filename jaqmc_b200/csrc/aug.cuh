@@ -69,6 +69,7 @@ struct JqDenseArgs {
   // scratch for the tensor-core path's transposed hi/lo weight split: jq_dense_tc_scratch_floats(k0+k1, N) floats,
   // or null to force the CUDA-core kernel
   float* wscratch;
+  int small_gt; // set by the launcher: groups per block of k_dense_small
   int tc_mode;  // 0: CTA-pair kernel (weights resident) when the shape allows, else the streaming one; 1: streaming only
 };
 int jq_launch_dense(const JqDenseArgs& a, cudaStream_t st);

@@ -192,9 +192,10 @@ __global__ void k_dense_small(JqDenseArgs a) {
   const int C = TC ? TC : a.C, K = TK ? TK : a.k0, N = TN ? TN : a.N;
   const int ldw = a.ldw ? a.ldw : N;
   float* Ws = sm;                 // [K][N]
-  float* Xs = Ws + K * N;         // [SM_GT][C][K]
-  const long long g0 = (long long)blockIdx.x * SM_GT;
-  const int ng = (int)((a.G - g0 < SM_GT) ? a.G - g0 : SM_GT);
+  float* Xs = Ws + K * N;         // [GT][C][K]
+  const int GT = a.small_gt;       // groups per block: SM_GT for 8-component groups, more for value-only launches
+  const long long g0 = (long long)blockIdx.x * GT;
+  const int ng = (int)((a.G - g0 < GT) ? a.G - g0 : GT);
   const int tid = threadIdx.x, nt = blockDim.x;
   for (int q = tid; q < K * N; q += nt) Ws[q] = a.w0[(long long)(q / N) * ldw + (q % N)];
   const float* xg = a.src0 + g0 * C * K;
@@ -268,6 +269,57 @@ size_t jq_dense_tc_scratch_floats(int k_total, int n_out) { return (size_t)2 * k
 bool jq_dense_tc_eligible(const JqDenseArgs&) { return false; }
 #endif
 
+#ifndef JAQMC_HOST_EMU
+// ------------------------------------------------------------------------------------------------
+// Value-only narrow layer with 32 output features (the FermiNet two-electron stream on the sampling path: 11 of the
+// 12 forward passes of a VMC iteration).  k_dense_small re-reads the weights from shared memory for every
+// multiply-add when a group has a single component; here a lane IS an output feature and keeps its weight column in
+// registers, a warp stages 32 groups with coalesced 16-byte loads and every lane reads a group's inputs as float4
+// broadcasts: 8 shared-memory reads per 32 multiply-adds, one coalesced 128-byte store per group.
+// ------------------------------------------------------------------------------------------------
+template <int K>
+__global__ void __launch_bounds__(256) k_dense_small_value(JqDenseArgs a) {
+  __shared__ float4 tile_all[8][32 * K / 4];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float4* tile = tile_all[warp];
+  const float* tile_f = reinterpret_cast<const float*>(tile);
+  const int ldw = a.ldw ? a.ldw : 32;
+  float wreg[K];
+#pragma unroll
+  for (int k = 0; k < K; ++k) wreg[k] = a.w0[(long long)k * ldw + lane];
+  const float bias = a.bias ? a.bias[lane] : 0.f;
+  const bool res_from_tile = (a.res == a.src0) && (K == 32);
+  const float inv_sqrt2 = 0.70710678118654752440f;
+  const float4* src4 = reinterpret_cast<const float4*>(a.src0);
+  for (long long g0 = ((long long)blockIdx.x * 8 + warp) * 32; g0 < a.G; g0 += (long long)gridDim.x * 8 * 32) {
+    const int ng = (int)((a.G - g0 < 32) ? a.G - g0 : 32);
+    for (int q = lane; q < ng * (K / 4); q += 32) tile[q] = src4[g0 * (K / 4) + q];
+    __syncwarp();
+    for (int gl = 0; gl < ng; ++gl) {
+      float acc = bias;
+#pragma unroll
+      for (int k = 0; k < K; k += 4) {
+        const float4 x = tile[gl * (K / 4) + k / 4];
+        acc = fmaf(x.x, wreg[k], acc);
+        acc = fmaf(x.y, wreg[k + 1], acc);
+        acc = fmaf(x.z, wreg[k + 2], acc);
+        acc = fmaf(x.w, wreg[k + 3], acc);
+      }
+      if (a.act == 1) acc = tanhf(acc);
+      if (a.res_mode) {
+        const float r = res_from_tile ? tile_f[gl * K + lane] : a.res[(g0 + gl) * 32 + lane];
+        acc = (a.res_mode == 1) ? (r + acc) * inv_sqrt2 : r + acc;
+      }
+      a.out[(g0 + gl) * 32 + lane] = acc;
+    }
+    __syncwarp();
+  }
+}
+#endif
+
+static int dense_small_launch(const JqDenseArgs& a, cudaStream_t st);
+static int dense_generic_launch(const JqDenseArgs& a, cudaStream_t st);
+
 int jq_launch_dense(const JqDenseArgs& a, cudaStream_t st) {
   if (a.G <= 0 || a.N <= 0) return JQ_OK;
 #ifdef JAQMC_HOST_EMU
@@ -286,7 +338,31 @@ int jq_launch_dense(const JqDenseArgs& a, cudaStream_t st) {
   if (handled) return JQ_OK;
 #endif
   if (dense_small_eligible(a)) {
-    size_t smem = sizeof(float) * ((size_t)a.k0 * a.N + (size_t)SM_GT * a.C * a.k0);
+    // ~256 rows per block: with one component per group (sampling path) a 32-group tile would be smaller than the
+    // weights every block stages
+    JqDenseArgs b = a;
+    b.small_gt = (SM_GT * SM_CMAX) / a.C;
+    if (b.small_gt < SM_GT) b.small_gt = SM_GT;
+    return dense_small_launch(b, st);
+  }
+  return dense_generic_launch(a, st);
+}
+
+static int dense_small_launch(const JqDenseArgs& a, cudaStream_t st) {
+#ifndef JAQMC_HOST_EMU
+  if (a.C == 1 && a.N == 32 && (a.k0 == 4 || a.k0 == 32) && (reinterpret_cast<uintptr_t>(a.src0) & 15) == 0 &&
+      a.out != a.src0) {
+    jq_prof_work(2.0 * (double)a.G * a.k0 * a.N, 4.0 * (double)a.G * (a.k0 + a.N));
+    long long blocks = jq_cdiv(a.G, 8 * 32);
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    if (a.k0 == 4) JQ_LAUNCH(k_dense_small_value<4>, dim3((unsigned)blocks), dim3(256), 0, st, a);
+    else JQ_LAUNCH(k_dense_small_value<32>, dim3((unsigned)blocks), dim3(256), 0, st, a);
+    JQ_CHECK_LAUNCH();
+    return JQ_OK;
+  }
+#endif
+  {
+    size_t smem = sizeof(float) * ((size_t)a.k0 * a.N + (size_t)a.small_gt * a.C * a.k0);
     jq_prof_work(2.0 * (double)a.G * a.C * a.k0 * a.N, 4.0 * (double)a.G * a.C * (a.k0 + a.N));
 #ifndef JAQMC_HOST_EMU
     static bool attr_set = false;
@@ -295,7 +371,7 @@ int jq_launch_dense(const JqDenseArgs& a, cudaStream_t st) {
       attr_set = true;
     }
 #endif
-    const dim3 grid((unsigned)jq_cdiv(a.G, SM_GT));
+    const dim3 grid((unsigned)jq_cdiv(a.G, a.small_gt));
     // the FermiNet two-electron stream (Local2: 8 components; value path: 1) and Local1 layers at the default widths
     if (a.C == 8 && a.k0 == 32 && a.N == 32) JQ_LAUNCH((k_dense_small<8, 32, 32>), grid, dim3(256), smem, st, a);
     else if (a.C == 8 && a.k0 == 4 && a.N == 32) JQ_LAUNCH((k_dense_small<8, 4, 32>), grid, dim3(256), smem, st, a);
@@ -306,6 +382,9 @@ int jq_launch_dense(const JqDenseArgs& a, cudaStream_t st) {
     JQ_CHECK_LAUNCH();
     return JQ_OK;
   }
+}
+
+static int dense_generic_launch(const JqDenseArgs& a, cudaStream_t st) {
   long long R = a.G * a.C;
   dim3 grid(jq_cdiv(R, GM_BM), jq_cdiv(a.N, GM_BN));
   jq_prof_work(2.0 * (double)R * (a.k0 + a.k1) * a.N, 4.0 * (double)R * (a.k0 + a.k1 + a.N));

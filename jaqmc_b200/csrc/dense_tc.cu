@@ -72,6 +72,9 @@ struct TcParams {
   // CTA-pair kernel (k_dense_tc_pair): G_t = 2 * G_h groups per tile, each CTA stages the Hp = roundup8(G_h * C)
   // rows of its half; pairs_per_block pairs walk the tiles of one 128-feature block
   int G_h, Hp, pairs_per_block, smem_request;
+  // walker-batched tiles (pair kernel, launches over a sub-range of a walker's groups, e.g. one spin channel): when a
+  // half-tile holds wb >= 2 whole walkers' sub-groups the TMA box spans wb walkers and G_h = wb * n_sub
+  int wb, Wn, stage_tx;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -336,12 +339,23 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& p, uint32_t tlane0
     EpiUnit u;
     while (item < limit) {
       const uint32_t t = PAIR ? (uint32_t)item : (uint32_t)item / mblocks;
-      const uint32_t w = t / tiles_per_w;
-      const int gsub = (int)(t - w * tiles_per_w) * p.G_t + g_first + gi;
+      uint32_t w;
+      int gsub;
+      bool ok;
+      if (PAIR && p.wb > 1) {   // tile = 2 * wb whole walkers; this lane quarter's half starts at walker w_half
+        const uint32_t wl = (uint32_t)gi / (uint32_t)p.n_sub;
+        gsub = gi - (int)wl * p.n_sub;
+        w = t * 2u * (uint32_t)p.wb + (uint32_t)((q >> 1) * p.wb) + wl;
+        ok = gi < g_count && (int)w < p.Wn;
+      } else {
+        w = t / tiles_per_w;
+        gsub = (int)(t - w * tiles_per_w) * p.G_t + g_first + gi;
+        ok = gi < g_count && gsub < p.n_sub;
+      }
       const int hf = PAIR ? pair_hf : (int)((uint32_t)item - t * mblocks);
       const int f = hf * TC_MBLK + f_lane;
       // N_out is a multiple of 32 (launcher): a warp's 32 features are all inside or all outside the layer
-      if (gi < g_count && gsub < p.n_sub && f - lane < p.N_out) {
+      if (ok && f - lane < p.N_out) {
         u.item = item;
         u.gi = gi;
         u.f_ok = true;
@@ -368,6 +382,89 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& p, uint32_t tlane0
     u.out_b = nullptr;
     return u;
   };
+
+  if (C == 1) {
+    // Value-only launches (the sampling path: one row per group; never with the envelope epilogue, see
+    // jq_dense_tc_eligible).  Consecutive groups are consecutive TMEM columns: a thread takes TC_CH groups per chunk.
+    uint32_t it = 0;
+    int f_cached = -1;
+    float bias_f = 0.f;
+    for (int item = first; item < limit; item += stride, ++it) {
+      const uint32_t buf = it & 1, acc_phase = (it >> 1) & 1;
+      const uint32_t tbuf = tlane0 + buf * 2 * TC_NMAX;
+      const uint32_t t = PAIR ? (uint32_t)item : (uint32_t)item / mblocks;
+      const int hf = PAIR ? pair_hf : (int)((uint32_t)item - t * mblocks);
+      const int f = hf * TC_MBLK + f_lane;
+      const bool batched = PAIR && p.wb > 1;
+      const uint32_t w = batched ? t * 2u * (uint32_t)p.wb + (uint32_t)((q >> 1) * p.wb) : t / tiles_per_w;
+      const int gsub_first = batched ? 0 : (int)(t - w * tiles_per_w) * p.G_t + g_first;
+      int nvalid = batched ? (p.Wn - (int)w) * p.n_sub : p.n_sub - gsub_first;   // groups gi < nvalid exist
+      if (nvalid > g_count) nvalid = g_count;
+      if (f - lane >= p.N_out) nvalid = 0;     // this warp's 32 features lie beyond the layer
+      const int g_base = (int)w * p.n_tot + p.j0 + gsub_first;   // group of gi = 0
+      // group index of gi: consecutive inside a walker's sub-range; a batched tile steps to the next walker every n_sub
+      auto group_at = [&](int gi) -> int {
+        if (!batched) return g_base + gi;
+        const uint32_t wl = (uint32_t)gi / (uint32_t)p.n_sub;
+        return g_base + (int)wl * p.n_tot + (gi - (int)wl * p.n_sub);
+      };
+      if (nvalid > 0 && f != f_cached) {       // per-feature constants (the feature block changes with the item)
+        f_cached = f;
+        bias_f = p.bias ? p.bias[f] : 0.f;
+      }
+      mbar_wait(&acc_full[buf], acc_phase);
+      tc_fence_after();
+      // super-steps of VS chunks of TC_CH groups (the two warps of a lane quarter alternate super-steps): all global
+      // operands of a super-step are requested before its first chunk is read from TMEM
+      constexpr int VS = 4;
+      for (int gs = sub * VS * TC_CH; gs < nvalid; gs += 2 * VS * TC_CH) {
+        int gidx[VS][TC_CH];
+        float cav[VS][TC_CH], rrv[VS][TC_CH];
+#pragma unroll
+        for (int s = 0; s < VS; ++s) {
+          const int gc = gs + s * TC_CH;
+          if (gc < nvalid) {
+#pragma unroll
+            for (int i = 0; i < TC_CH; ++i) {
+              const bool ok = gc + i < nvalid;
+              gidx[s][i] = group_at(ok ? gc + i : 0);
+              if (CADD) cav[s][i] = ok ? p.cadd[(size_t)((uint32_t)gidx[s][i] / (uint32_t)p.n_tot_true) * N + f] : 0.f;
+              if (RES) rrv[s][i] = ok ? p.res[(size_t)gidx[s][i] * N + f] : 0.f;
+            }
+          }
+        }
+#pragma unroll
+        for (int s = 0; s < VS; ++s) {
+          const int gc = gs + s * TC_CH;
+          if (gc < nvalid) {
+            float v[TC_CH], v2[TC_CH];
+            tmem_ld8_nowait(tbuf + gc, v);
+            tmem_ld8_nowait(tbuf + TC_NMAX + gc, v2);
+            tmem_wait_ld();
+#pragma unroll
+            for (int i = 0; i < TC_CH; ++i) {
+              if (gc + i < nvalid) {
+                float y = v[i] + v2[i];
+                if (CADD) y += cav[s][i];
+                y += bias_f;
+                if (ACT == 1) y = tanhf(y);
+                if (RES == 1) y = (rrv[s][i] + y) * inv_sqrt2;
+                if (RES == 2) y = rrv[s][i] + y;
+                p.out[(size_t)gidx[s][i] * N + f] = y;
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (PAIR) mbar_arrive_cluster(&acc_empty[buf], 0);
+        else mbar_arrive(&acc_empty[buf]);
+      }
+    }
+    return;
+  }
 
   // Rows [r0, r1) are walked in chunks: all rows without activation, the Jacobian rows otherwise (the value row
   // comes first -- tanh needs d1 = 1 - tanh(x)^2 before the Jacobian rows -- and the Laplacian row last, after
@@ -895,7 +992,7 @@ k_dense_tc_pair(const __grid_constant__ CUtensorMap mapX0, const __grid_constant
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0 && t_limit > 0) {
-      const uint32_t stage_tx = (uint32_t)(p.Hp * 128);
+      const uint32_t stage_tx = (uint32_t)p.stage_tx;
       if (rank == 0) mbar_expect_tx(wfull, 2u * (uint32_t)w_bytes);
       const uint32_t wfull_l = mapa_u32(wfull, 0);
       const int frow = hf * TC_MBLK + (int)rank * 64;
@@ -906,9 +1003,14 @@ k_dense_tc_pair(const __grid_constant__ CUtensorMap mapX0, const __grid_constant
       PipeState ps;
       const uint32_t full_l0 = mapa_u32(&full[0], 0);
       for (int t = t_first; t < t_limit; t += t_stride) {
-        const int w = (int)((uint32_t)t / (uint32_t)p.tiles_per_w);
-        const int gsub0 = (t - w * (int)p.tiles_per_w) * p.G_t + (int)rank * p.G_h;
-        const int row0 = (p.j0 + gsub0) * p.C;
+        int w, row0;
+        if (p.wb > 1) {   // box = (K chunk, the sub-range's rows, wb walkers)
+          w = t * 2 * p.wb + (int)rank * p.wb;
+          row0 = p.j0 * p.C;
+        } else {
+          w = (int)((uint32_t)t / (uint32_t)p.tiles_per_w);
+          row0 = (p.j0 + (t - w * (int)p.tiles_per_w) * p.G_t + (int)rank * p.G_h) * p.C;
+        }
         for (int kc = 0; kc < kchunks; ++kc) {
           mbar_wait(&empty[ps.stage], ps.phase ^ 1);
           unsigned char* st = xring + ps.stage * p.stage_bytes;
@@ -1109,6 +1211,7 @@ bool jq_dense_tc_eligible(const JqDenseArgs& a) {
   if (a.k0 % TC_BK || a.k1 % TC_BK) return false;
   if (a.k0 + a.k1 < 32) return false;
   if (a.N < 64 || a.N > 2 * TC_MBLK || a.N % 32) return false;   // a warp's 32 features are all valid or all not
+  if (a.act == 2 && a.C == 1) return false;   // value-only launches take the separate envelope pass
   if (!a.wscratch) return false;
   if ((reinterpret_cast<uintptr_t>(a.src0) & 15) || (a.src1 && (reinterpret_cast<uintptr_t>(a.src1) & 15))) return false;
   return true;
@@ -1126,7 +1229,14 @@ static bool pair_plan(const JqDenseArgs& a, int sm_count, TcParams* p, int* smem
   int G_h = TC_NMAX / a.C;
   if (G_h < 1) return false;
   const long long n_sub = (a.n_sub == a.n_tot) ? a.G : a.n_sub;
-  if ((long long)2 * G_h > n_sub) G_h = (int)((n_sub + 1) / 2);
+  int wb = 1;
+  if (a.n_sub != a.n_tot && G_h >= 2 * a.n_sub) {
+    wb = G_h / a.n_sub;   // whole walkers per half-tile
+    if (wb > 128) wb = 128;
+    G_h = wb * a.n_sub;
+  } else if ((long long)2 * G_h > n_sub) {
+    G_h = (int)((n_sub + 1) / 2);
+  }
   const int Hp = (G_h * a.C + 7) / 8 * 8;
   const int w_bytes = (kt / TC_BK) * 2 * TCP_W_CHUNK;
   const int stage_bytes = Hp * 128;   // one raw tile, converted to its lo part in place
@@ -1136,6 +1246,8 @@ static bool pair_plan(const JqDenseArgs& a, int sm_count, TcParams* p, int* smem
   p->G_h = G_h;
   p->G_t = 2 * G_h;
   p->Hp = Hp;
+  p->wb = wb;
+  p->stage_tx = (wb > 1 ? wb * a.n_sub * a.C : Hp) * 128;
   p->stages = stages;
   p->stage_bytes = stage_bytes;
   p->pairs_per_block = n_pairs / mblocks;
@@ -1207,8 +1319,14 @@ int jq_launch_dense_tc(const JqDenseArgs& a, cudaStream_t st, bool* handled) {
     if (p.stages > TC_MAX_STAGES) p.stages = TC_MAX_STAGES;
     smem_bytes = p.stages * p.stage_bytes + TC_SMEM_EXTRA;
   }
-  p.tiles_per_w = jq_cdiv(p.n_sub, p.G_t);
-  p.tiles = p.tiles_per_w * Wn;
+  p.Wn = (int)Wn;
+  if (pair && p.wb > 1) {
+    p.tiles_per_w = 1;
+    p.tiles = jq_cdiv(Wn, 2 * p.wb);
+  } else {
+    p.tiles_per_w = jq_cdiv(p.n_sub, p.G_t);
+    p.tiles = p.tiles_per_w * Wn;
+  }
   p.items = p.tiles * p.mblocks;
   JQ_REQUIRE(p.items < 0x7fffffffLL && a.G < 0x7fffffffLL, JQ_ERR_UNSUPPORTED, "dense_tc: too many tiles");
   p.G_sub_total = a.G;
@@ -1229,6 +1347,10 @@ int jq_launch_dense_tc(const JqDenseArgs& a, cudaStream_t st, bool* handled) {
     cuuint64_t dims[3] = {(cuuint64_t)a.k0, (cuuint64_t)p.n_tot * a.C, (cuuint64_t)Wn};
     cuuint64_t str[2] = {(cuuint64_t)a.k0 * 4, (cuuint64_t)p.n_tot * a.C * a.k0 * 4};
     cuuint32_t box[3] = {TC_BK, (cuuint32_t)(pair ? p.Hp : p.n_mma), 1};
+    if (pair && p.wb > 1) {
+      box[1] = (cuuint32_t)(p.n_sub * a.C);
+      box[2] = (cuuint32_t)p.wb;
+    }
     int rc = make_map(&mX0, a.src0, 3, dims, str, box);
     if (rc) return rc;
     if (a.k1 > 0) {

@@ -131,7 +131,9 @@ int jq_head_forward(const JqHeadDims& d, const jaqmc_head_params* p, const float
       a.n_sub = n;
     }
     a.G = W * a.n_sub;
-    if (d.envelope_type != JAQMC_ENVELOPE_NULL && env_fused && jq_dense_tc_eligible(a)) {
+    // the envelope is fused into the orbital GEMM's epilogue under the forward Laplacian; on the value-only
+    // sampling path (one row per electron) the separate elementwise pass is cheaper than a fused epilogue variant
+    if (track && d.envelope_type != JAQMC_ENVELOPE_NULL && env_fused && jq_dense_tc_eligible(a)) {
       ef[s].electrons = electrons;
       ef[s].atoms = atoms;
       ef[s].pi = p->env_pi[s];

@@ -399,9 +399,90 @@ __global__ void __launch_bounds__(256, 3) k_logdet(const float* __restrict__ orb
   for (int d = tid; d < db; d += nt) det_lap[w * D + d0 + d] = trL[d] - t2[d];
 }
 
+#ifndef JAQMC_HOST_EMU
+// ------------------------------------------------------------------------------------------------
+// Value-only slogdet (the MH sampling path: 11 of the 12 forward passes of a VMC iteration): one WARP per matrix.
+// Lane r keeps row r in registers; LU with partial pivoting without moving rows: at step p the pivot is the largest
+// |a[r][p]| among the rows not used yet (warp max + ballot), its row is broadcast by shuffles and eliminated from the
+// remaining rows -- the same pivots and the same fmaf sequence as the row-swapping elimination of k_logdet (and of
+// LAPACK getrf behind jnp.linalg.slogdet, wavefunction/output/logdet.py:65), so the two kernels agree on sign and
+// log|det|.  sign = parity(step -> row permutation) * prod sign(pivot); log|det| = sum log|pivot| in double.
+// ------------------------------------------------------------------------------------------------
+template <int NMAX>
+__global__ void __launch_bounds__(256) k_logdet_value_warp(const float* __restrict__ orb, int n, int D, long long M,
+                                                          float* __restrict__ det_sign, float* __restrict__ det_logabs) {
+  const unsigned full = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  const long long m = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);   // matrix = (walker, determinant)
+  if (m >= M) return;
+  const long long w = m / D;
+  const int d = (int)(m - w * D);
+  const int DN = D * n;
+  float a[NMAX];
+  bool used = lane >= n;
+  {
+    const float* row = orb + (w * n + (used ? 0 : lane)) * (long long)DN + d * n;
+#pragma unroll
+    for (int c = 0; c < NMAX; ++c) a[c] = (c < n) ? row[c] : 0.f;
+  }
+  int step_of = 0;
+  float sgn = 1.0f;
+  double logabs = 0.0;
+#pragma unroll
+  for (int p = 0; p < NMAX; ++p) {
+    if (p < n) {
+      const unsigned key = used ? 0u : __float_as_uint(fabsf(a[p]));
+      const unsigned mx = __reduce_max_sync(full, key);
+      const unsigned cand = __ballot_sync(full, !used && key == mx);
+      const int pl = __ffs(cand) - 1;               // first row holding the largest magnitude
+      const float pv = __shfl_sync(full, a[p], pl);
+      if (pv < 0.f) sgn = -sgn;
+      if (pv == 0.f) sgn = 0.f;
+      logabs += log((double)fabsf(pv));
+      const float pinv = 1.0f / pv;
+      if (lane == pl) {
+        used = true;
+        step_of = p;
+      }
+      const float f = used ? 0.f : a[p] * pinv;
+#pragma unroll
+      for (int c = p + 1; c < NMAX; ++c)
+        if (c < n) {
+          const float pc = __shfl_sync(full, a[c], pl);
+          a[c] = fmaf(-f, pc, a[c]);
+        }
+    }
+  }
+  // parity of the permutation row -> step: inversions counted per lane, summed over the warp
+  int inv_count = 0;
+  for (int i = 0; i < n; ++i) {
+    const int si = __shfl_sync(full, step_of, i);
+    if (i < lane && lane < n && si > step_of) ++inv_count;
+  }
+  const int total = __reduce_add_sync(full, inv_count);
+  if (lane == 0) {
+    det_sign[m] = (total & 1) ? -sgn : sgn;
+    det_logabs[m] = (float)logabs;
+  }
+}
+#endif
+
 int jq_launch_logdet(const float* orb, int W, int n, int D, int track, float* det_sign, float* det_logabs,
                      float* det_grad, float* det_lap, cudaStream_t st) {
   if ((long long)W * D <= 0) return JQ_OK;
+#ifndef JAQMC_HOST_EMU
+  if (!track && n <= 32) {
+    const long long M = (long long)W * D;
+    const dim3 grid((unsigned)jq_cdiv(M, 8)), block(256);
+    jq_prof_work((double)M * 0.67 * n * n * n, 4.0 * (double)M * n * n);
+    if (n <= 4) JQ_LAUNCH(k_logdet_value_warp<4>, grid, block, 0, st, orb, n, D, M, det_sign, det_logabs);
+    else if (n <= 8) JQ_LAUNCH(k_logdet_value_warp<8>, grid, block, 0, st, orb, n, D, M, det_sign, det_logabs);
+    else if (n <= 16) JQ_LAUNCH(k_logdet_value_warp<16>, grid, block, 0, st, orb, n, D, M, det_sign, det_logabs);
+    else JQ_LAUNCH(k_logdet_value_warp<32>, grid, block, 0, st, orb, n, D, M, det_sign, det_logabs);
+    JQ_CHECK_LAUNCH();
+    return JQ_OK;
+  }
+#endif
   const int C = track ? 3 * n + 2 : 1;
   const int KT = C > 1 ? C - 1 : 0;
   const size_t nn = (size_t)n * n;

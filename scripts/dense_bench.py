@@ -25,6 +25,9 @@ CASES = {
     "layer1": (W * 14, 44, 32, 0, 256, 14, 1, 0, True, False),
     "mean": (W, 44, 512, 0, 256, 1, 0, 0, False, False),
     "psi_dense": (W * 14, 44, 256, 0, 256, 14, 1, 2, True, False),
+    "value_main": (W * 14, 1, 256, 64, 256, 14, 1, 1, True, True),
+    "value_plain": (W * 14, 1, 256, 0, 256, 14, 0, 0, False, False),
+    "value_big": (W * 14 * 16, 1, 256, 64, 256, 14, 1, 1, True, True),
 }
 
 

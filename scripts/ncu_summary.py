@@ -64,6 +64,15 @@ def main():
             dom = ", ".join(f"{k} {v}" for v, k in st if v)
             n = int(r[jx["# Samples"]])
             out.append(f"| {n} | {100.0 * n / max(total, 1):.1f} | {r[jx['Address']][-5:]} | `{r[jx['Source']].strip()[:70]}` | {dom} |")
+    if "--json" in sys.argv:
+        import json
+        def num(r, m):
+            v = float(r[ix[m]].replace(",", ""))
+            u = units[ix[m]].lower()
+            return v * (1e9 if u.startswith("g") else 1e6 if u.startswith("m") else 1e3 if u.startswith("k") else 1)
+        js = [{"kernel": r[ix["Kernel Name"]][:60], "duration_ms": float(r[ix["gpu__time_duration.sum"]]) * (1e-3 if units[ix["gpu__time_duration.sum"]].startswith("u") else 1),
+               "dram_bytes": num(r, "dram__bytes_read.sum") + num(r, "dram__bytes_write.sum")} for r in body]
+        open(sys.argv[sys.argv.index("--json") + 1], "w").write(json.dumps(js, indent=1) + "\n")
     text = "\n".join(out)
     if "--md" in sys.argv:
         open(sys.argv[sys.argv.index("--md") + 1], "w").write(text + "\n")
