@@ -41,6 +41,10 @@ WORKLOADS = {
     "lih": ("LiH", 16, (256,) * 4, (32,) * 4, "FermiNet-LiH (4 electrons, 16 dets, 256x4/32x4)"),
     "n2-lapnet": ("N2", 16, None, None, "LapNet-N2 (14 electrons, 16 dets, 4 layers x 4 heads x 64)", "lapnet"),
     "n2-psiformer": ("N2", 16, None, None, "Psiformer-N2 (14 electrons, 16 dets, 4 x 4 x 64, MLP 256)", "psiformer"),
+    # configs[3] / configs[4]: 4096 walkers are sharded over 8 GPUs there, i.e. 512 per GPU -- pass --walkers 512
+    "benzene-psiformer": ("C6H6", 16, None, None, "Psiformer-C6H6 (42 electrons, 16 dets, 4 x 4 x 64, MLP 256)", "psiformer"),
+    "lih-solid": ("fcc_lih_222", 16, (256,) * 4, (32,) * 4,
+                  "periodic FermiNet, LiH rock salt 2x2x2 (32 electrons, 16 atoms, complex orbitals, Ewald)", "solid"),
 }
 
 
@@ -58,6 +62,8 @@ def make_wavefunction(name, nspins):
         return LapNetWavefunction(nspins=nspins, ndets=ndets)
     if kind == "psiformer":
         return PsiformerWavefunction(nspins=nspins, ndets=ndets)
+    if kind == "solid":
+        raise ValueError("the periodic workload is built by run_ours_solid")
     return FermiNetWavefunction(nspins=nspins, ndets=ndets, hidden_dims_single=list(hs), hidden_dims_double=list(hd))
 METRIC = "local_energy_evals_per_sec"
 UNIT = "evals/s"
@@ -121,6 +127,9 @@ def cpu_rate(workload: str, budget_s: float, chunk: int = 64):
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
+        return
+    if workload_kind(args.workload) == "solid":
+        print(json.dumps({"impl": "reference", "unavailable": "no vmapped CPU port of the periodic network (float64 oracle only)"}))
         return
     # K steps, each a bounded sample sized so the whole run ends within a few minutes
     per_step = max(2.0, min(20.0, 120.0 / max(1, args.steps + args.warmup)))
@@ -209,8 +218,110 @@ def parse_profile(rt):
     return out
 
 
+def run_ours_solid(args, dev, world, rank, dist):
+    """configs[4]: periodic FermiNet + Ewald local energy (complex log psi); resident and end-to-end timings."""
+    import numpy as np
+    from jaqmc_b200 import systems as H
+    from jaqmc_b200.data import SolidData
+    from jaqmc_b200.ewald import EwaldSum
+    from jaqmc_b200.wavefunction import SolidWavefunction
+    from jaqmc_b200._runtime import runtime
+
+    mol, ndets, hs, hd, desc = WORKLOADS[args.workload][:5]
+    prim, sim, patoms, cell_atoms, cell_charges, nspins, klist = H.solid_system(mol)
+    n = sum(nspins)
+    W = args.walkers
+    if W % world:
+        raise SystemExit(f"--walkers {W} not divisible by {world} ranks")
+    Wl = W // world
+    f32 = lambda a: torch.as_tensor(np.asarray(a), dtype=torch.float32).to(dev)  # noqa: E731
+    wf = SolidWavefunction(nspins=nspins, simulation_lattice=sim, primitive_lattice=prim, klist=klist, ndets=ndets,
+                           hidden_dims_single=list(hs), hidden_dims_double=list(hd))
+    el_host = torch.from_numpy(H.solid_walkers(cell_atoms, n, W, seed=0)[rank * Wl:(rank + 1) * Wl]).contiguous().pin_memory()
+    data = SolidData(electrons=el_host.to(dev), atoms=f32(cell_atoms), charges=f32(cell_charges), primitive_atoms=f32(patoms))
+    params = wf.init_params(data, 42)
+    ew = EwaldSum(sim, device=dev)
+    rt = runtime(dev)
+    sums = torch.zeros(3, device=dev)
+    e_host = torch.empty(Wl, dtype=torch.float32).pin_memory()
+
+    def step_resident():
+        sums.zero_()
+        out = wf.local_energy(params, data, ewald=ew, sums=sums)
+        if dist:
+            torch.distributed.all_reduce(sums)
+        return out
+
+    def step_e2e():
+        data.electrons.copy_(el_host, non_blocking=True)
+        out = step_resident()
+        e_host.copy_(out["e_loc"].real, non_blocking=True)
+
+    def timed(fn, k):
+        if dist:
+            torch.distributed.barrier()
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(k):
+            fn()
+        e1.record()
+        if dist:
+            torch.distributed.barrier()
+        torch.cuda.synchronize(dev)
+        ms = e0.elapsed_time(e1)
+        if dist:
+            t = torch.tensor([ms], device=dev)
+            torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+            ms = float(t)
+        return ms
+
+    for _ in range(max(3, args.warmup)):
+        step_resident()
+    clocks = ClockSampler(int(os.environ.get("LOCAL_RANK", "0")))
+    if rank == 0:
+        clocks.start()
+    rt.reset_launch_count()
+    ms = timed(step_resident, args.steps)
+    launches = rt.launch_count()
+    clk = clocks.stop() if rank == 0 else None
+    step_e2e()
+    ms_e2e = timed(step_e2e, args.steps)
+    finite = bool(torch.isfinite(e_host).all())
+    kernels = None
+    if rank == 0:
+        rt.lib.jaqmc_b200_profile_enable(1)
+        step_resident()
+        torch.cuda.synchronize(dev)
+        rt.lib.jaqmc_b200_profile_enable(0)
+        prof = parse_profile(rt)
+        tot_ms = sum(v["ms"] for v in prof.values()) or 1.0
+        kernels = {}
+        for k, v in prof.items():
+            e = kernels.setdefault(k.split("@")[0], {"launches": 0, "ms": 0.0})
+            e["launches"] += v["launches"]
+            e["ms"] += v["ms"]
+        kernels = {k: {"launches": v["launches"], "share": round(v["ms"] / tot_ms, 4),
+                       "ms_per_launch": round(v["ms"] / v["launches"], 4)} for k, v in kernels.items()}
+        line = {
+            "metric": METRIC, "value": round(W * args.steps / (ms * 1e-3), 1), "unit": UNIT, "n_gpus": world,
+            "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": round(ms / args.steps, 4),
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32 / complex64", "data": "synthetic",
+            "config": {"workload": f"{desc}, {W} walkers global ({Wl}/GPU), forward-Laplacian kinetic + Ewald potential",
+                       "parallelism": f"walkers sharded over {world} GPU(s); all-reduce of 3 floats per step",
+                       "launch": "kernel by kernel"},
+            "e2e": {"value": round(W * args.steps / (ms_e2e * 1e-3), 1), "unit": UNIT,
+                    "h2d_bytes_per_step": int(Wl * n * 3 * 4) * world, "d2h_bytes_per_step": int(Wl * 4) * world,
+                    "finite": finite},
+            "gpu_launches": int(launches), "clocks": clk, "roofline": None, "kernels": kernels,
+        }
+        print(json.dumps(line), flush=True)
+    if dist:
+        torch.distributed.destroy_process_group()
+
+
 def run_ours(args):
-    import helpers as H
+    from jaqmc_b200 import systems as H
     from jaqmc_b200.data import MoleculeData
     from jaqmc_b200.sampler import MCMCSampler, SamplePlan
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -225,6 +336,8 @@ def run_ours(args):
         print(f"warning: --gpus {args.gpus} but WORLD_SIZE={world}", file=sys.stderr)
 
     mol, ndets, hs, hd, desc = WORKLOADS[args.workload][:5]
+    if workload_kind(args.workload) == "solid":
+        return run_ours_solid(args, dev, world, rank, dist)
     atoms64, charges64, nspins = H.molecule(mol)
     n = sum(nspins)
     W = args.walkers

@@ -476,7 +476,11 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& p, uint32_t tlane0
   const int tail = (r1 - r0) - nfull * TC_CH;
   const bool chunked = nfull >= 1;
   const uint32_t o_last = (uint32_t)(C - 1) * N;
-  const uint32_t o_tail = (uint32_t)(r0 + nfull * TC_CH) * N;
+  // the tail slot covers the LAST TC_CH rows [r1 - TC_CH, r1) so that its TMEM read stays inside the group's columns;
+  // its first tail_skip rows belong to the last full chunk and are masked
+  const int tail_skip = TC_CH - tail;
+  const int tail_cs = r1 - TC_CH;
+  const uint32_t o_tail = (uint32_t)(chunked ? tail_cs : 0) * N;
   float ca[TC_RING][TC_CH], rr[TC_RING][TC_CH], caT[TC_CH], rrT[TC_CH];
   float ca0 = 0.f, rr0 = 0.f, caL = 0.f, rrL = 0.f;   // value / Laplacian row operands of the current unit
 #define TC_CHUNK_LOAD(u, j, slot)                                    \
@@ -490,8 +494,8 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& p, uint32_t tlane0
 #define TC_TAIL_LOAD(u)                                              \
   {                                                                  \
     uint32_t o_ = o_tail + (u).fo;                                   \
-    _Pragma("unroll") for (int i_ = 0; i_ < TC_CH - 1; ++i_, o_ += N) { \
-      if (i_ < tail) {                                               \
+    _Pragma("unroll") for (int i_ = 0; i_ < TC_CH; ++i_, o_ += N) { \
+      if (i_ >= tail_skip) {                                         \
         if (CADD) caT[i_] = (u).cadd_b[o_];                          \
         if (RES) rrT[i_] = (u).res_b[o_];                            \
       }                                                              \
@@ -625,15 +629,14 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& p, uint32_t tlane0
           }
         }
         if (tail) {
-          const int cs = r0 + nfull * TC_CH;
           float v[TC_CH], v2[TC_CH];
-          tmem_ld8_nowait(tcol + cs, v);   // columns past the group belong to the next group or are unused: ignored
-          tmem_ld8_nowait(tcol + TC_NMAX + cs, v2);
+          tmem_ld8_nowait(tcol + tail_cs, v);
+          tmem_ld8_nowait(tcol + TC_NMAX + tail_cs, v2);
           tmem_wait_ld();
           uint32_t o = o_tail + fo;
 #pragma unroll
-          for (int i = 0; i < TC_CH - 1; ++i, o += N)
-            if (i < tail) TC_ROW(cs + i, v[i] + v2[i], caT[i], rrT[i], o)
+          for (int i = 0; i < TC_CH; ++i, o += N)
+            if (i >= tail_skip) TC_ROW(tail_cs + i, v[i] + v2[i], caT[i], rrT[i], o)
           if (LD && have_nxt) TC_TAIL_LOAD(nxt)
         }
         if (ACT != 0 && C > 1) {   // Laplacian row
@@ -1203,6 +1206,18 @@ int pick_groups_per_tile(int C) {
 
 size_t jq_dense_tc_scratch_floats(int k_total, int n_out) { return (size_t)2 * k_total * n_out; }
 
+static bool pair_plan(const JqDenseArgs& a, int sm_count, TcParams* p, int* smem_bytes);
+
+static int tc_sm_count() {
+  static int sm_count = 0;
+  if (!sm_count) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
+  }
+  return sm_count;
+}
+
 bool jq_dense_tc_eligible(const JqDenseArgs& a) {
   // debugging switch (bisecting a numerical difference between the two dense kernels); both are sm_100a CUDA
   static const bool disabled = getenv("JAQMC_B200_DISABLE_TC") != nullptr;
@@ -1210,10 +1225,17 @@ bool jq_dense_tc_eligible(const JqDenseArgs& a) {
   if (a.C > TC_NMAX) return false;
   if (a.k0 % TC_BK || a.k1 % TC_BK) return false;
   if (a.k0 + a.k1 < 32) return false;
-  if (a.N < 64 || a.N > 2 * TC_MBLK || a.N % 32) return false;   // a warp's 32 features are all valid or all not
+  if (a.N < 64 || a.N % 32) return false;   // a warp's 32 features are all valid or all not
   if (a.act == 2 && a.C == 1) return false;   // value-only launches take the separate envelope pass
   if (!a.wscratch) return false;
   if ((reinterpret_cast<uintptr_t>(a.src0) & 15) || (a.src1 && (reinterpret_cast<uintptr_t>(a.src1) & 15))) return false;
+  if (a.N > 2 * TC_MBLK) {
+    // more than two 128-feature blocks (orbital layers of larger systems: D * n columns): the CTA-pair kernel only
+    TcParams tmp;
+    int smem = 0;
+    memset(&tmp, 0, sizeof(tmp));
+    return pair_plan(a, tc_sm_count(), &tmp, &smem);
+  }
   return true;
 }
 

@@ -28,6 +28,8 @@ CASES = [
     ("local1", 14 * 7, 5, 256, 0, 512 // 2, 14, 1, 2, True, False),
     ("minimal", 37, 8, 64, 0, 64, 1, 1, 0, True, False),
     ("wide_c", 6, 128, 64, 32, 128, 2, 1, 1, True, True),
+    ("wide_c_many", 42 * 8, 128, 64, 0, 128, 42, 1, 0, True, False),   # both accumulator buffers, 128-row groups
+    ("wide_n", 32 * 6, 98, 256, 0, 512, 32, 0, 0, False, False),        # four feature blocks (CTA-pair kernel only)
     ("n2_big", 14 * 300, 44, 256, 64, 256, 14, 1, 1, True, True),
 ]
 

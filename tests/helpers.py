@@ -16,6 +16,7 @@ if ROOT not in sys.path:
 
 from jaqmc_b200 import _abi  # noqa: E402
 from jaqmc_b200._runtime import Runtime  # noqa: E402
+from jaqmc_b200.systems import molecule, solid_system, solid_walkers, synthetic_walkers  # noqa: E402,F401
 from oracle import estimators as OE  # noqa: E402
 from oracle import networks as ON  # noqa: E402
 
@@ -42,39 +43,6 @@ def to_f32(tree, device="cpu"):
 def round_f32(tree):
     """float64 tree holding exactly the float32-representable values (so oracle and kernels see identical numbers)."""
     return ON.tree_map(lambda t: t.to(torch.float32).to(F64), tree)
-
-
-def molecule(name):
-    """(atoms (A,3) float64, charges (A,), nspins)."""
-    if name == "Li":
-        return torch.zeros(1, 3, dtype=F64), torch.tensor([3.0], dtype=F64), (2, 1)
-    if name == "H":
-        return torch.zeros(1, 3, dtype=F64), torch.tensor([1.0], dtype=F64), (1, 0)
-    if name == "He":
-        return torch.zeros(1, 3, dtype=F64), torch.tensor([2.0], dtype=F64), (1, 1)
-    if name == "LiH":
-        return (torch.tensor([[0.0, 0.0, 0.0], [0.0, 0.0, 3.015]], dtype=F64), torch.tensor([3.0, 1.0], dtype=F64), (2, 2))
-    if name == "Ar":  # 18 electrons: exercises the n > 16 code paths (generic LogDet kernel)
-        return torch.zeros(1, 3, dtype=F64), torch.tensor([18.0], dtype=F64), (9, 9)
-    if name == "N2":
-        return (torch.tensor([[0.0, 0.0, -1.034], [0.0, 0.0, 1.034]], dtype=F64), torch.tensor([7.0, 7.0], dtype=F64), (7, 7))
-    raise KeyError(name)
-
-
-def synthetic_walkers(atoms, charges, nspins, W, seed=0):
-    """Electrons ~ N(atom, 1) assigned to atoms in proportion to nuclear charge (app/molecule/data.py:36-44 style)."""
-    g = torch.Generator().manual_seed(seed)
-    n = sum(nspins)
-    A = atoms.shape[0]
-    owners = []
-    z = charges.clone()
-    for _ in range(n):
-        i = int(torch.argmax(z))
-        owners.append(i)
-        z[i] -= 1.0
-    centers = atoms[torch.tensor(owners)]
-    el = centers[None] + torch.randn(W, n, 3, generator=g, dtype=F64)
-    return el.to(torch.float32).to(F64)  # exactly float32-representable
 
 
 def oracle_batch(logpsi_fn, electrons, atoms=None, charges=None, track=True):

@@ -12,32 +12,7 @@ from oracle import networks as ON
 F64 = torch.float64
 
 
-def solid_system(kind):
-    """(prim_lattice, sim_lattice, prim_atoms, cell_atoms, cell_charges, nspins, klist) -- small synthetic crystals."""
-    if kind == "cubic_h2":       # simple cubic cell, 2 atoms, supercell = primitive cell, Gamma point
-        prim = 3.2 * np.eye(3)
-        sim = prim.copy()
-        patoms = np.array([[0.0, 0.0, 0.0], [1.4, 0.3, 0.2]])
-        nspins = (1, 1)
-        klist = np.zeros((2, 3))
-    elif kind == "fcc_lih_221":  # FCC rock-salt-like cell, 2x2x1 supercell, folding k-points
-        a = 4.4
-        prim = a / 2 * np.array([[0.0, 1.0, 1.0], [1.0, 0.0, 1.0], [1.0, 1.0, 0.0]])
-        S = np.diag([2, 2, 1])
-        sim = S @ prim
-        patoms = np.array([[0.0, 0.0, 0.0], [a / 2, a / 2, a / 2]])
-        nspins = (2, 2)
-        b = 2 * np.pi * np.linalg.inv(prim).T
-        ks = np.array([[0, 0, 0], [0.5, 0, 0], [0, 0.5, 0], [0.5, 0.5, 0]]) @ b
-        klist = np.concatenate([ks[:2], ks[2:]])  # one k-point per orbital: up orbitals, then down
-    else:
-        raise KeyError(kind)
-    S = np.round(sim @ np.linalg.inv(prim)).astype(int)
-    shifts = np.array([[i, j, k] for i in range(S[0, 0]) for j in range(S[1, 1]) for k in range(S[2, 2])]) @ prim
-    cell_atoms = (patoms[None] + shifts[:, None]).reshape(-1, 3)
-    z = np.array([3.0, 1.0]) if kind != "cubic_h2" else np.array([1.0, 1.0])
-    cell_charges = np.tile(z, len(shifts))
-    return prim, sim, patoms, cell_atoms, cell_charges, nspins, klist
+solid_system = H.solid_system
 
 
 def _setup(kind, W, ndets=2, hs=(16, 16), hd=(8, 8), seed=0, device="cpu"):
