@@ -9,6 +9,8 @@
 //     its hand rule :113-196 (q, k Local1, v dense); flax MultiHeadDotProductAttention for Psiformer
 //     (backbone/psiformer.py:76-82), traced through dot_general (laplacian/primitives/dot_general.py:410-449) and softmax
 // Both are evaluated here in closed form (Appendix A of SURVEY.md): same function, same derivatives.
+#include <cstdlib>
+
 #include "aug.cuh"
 
 // ------------------------------------------------------------------------------------------------
@@ -379,6 +381,281 @@ __global__ void k_attention_fl(JqAttnOperand q, JqAttnOperand k, JqAttnOperand v
   }
 }
 
+#ifndef JAQMC_HOST_EMU
+// ------------------------------------------------------------------------------------------------
+// Same rule for small molecules (n <= 16 electrons, head dimension 64): the Jacobian components are independent
+// given (q, k, v, w), so instead of walking them one by one with five block-wide barriers each (k_attention_fl: 2 % of
+// the FP32 peak), every WARP of the block takes components c = warp, warp + 8, ... and runs the three phases on its own
+// staging area with warp-level synchronisation only:
+//   A  aJ = (qJ.k + q.kJ)/sqrt(d), aL += 2 qJ.kJ/sqrt(d)   lane = 2 x 4 tile of (i, j) pairs, float4 operand reads
+//   B  abar, wJ, t1 += wJ (aJ - abar), t2 += sum wJ aJ       lane = row i
+//   C  oJ = wJ v + w vJ (stored), oL += 2 wJ vJ             lane = features (lane, lane + 32), 8 rows per pass
+// The Laplacian accumulators (aL, t1, t2, oL) are per-warp partial sums, reduced in a fixed order at the end, so the
+// result is deterministic.  Shared memory (floats): q0 k0 v0 [n][68] | w [n][n] | per warp: qJ kJ vJ [n][68],
+// aJ aL t1 [n][n], t2 abar [16], oL [n][64].
+// ------------------------------------------------------------------------------------------------
+constexpr int AW_LD = 68;      // row stride of the [n][64] operand tiles (16-byte aligned, rows 4 banks apart)
+constexpr int AW_WARPS = 8;
+
+__device__ __forceinline__ float4 attn_fetch4(const JqAttnOperand& t, long long w, int n, int i, int comp_dense, int col,
+                                              int Cd) {
+  const float* base = t.p + ((w * n + i) * (long long)t.C) * t.ld + col;
+  const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (t.C == Cd) return *reinterpret_cast<const float4*>(base + (long long)comp_dense * t.ld);
+  if (comp_dense == 0) return *reinterpret_cast<const float4*>(base);
+  if (comp_dense == Cd - 1) return *reinterpret_cast<const float4*>(base + (long long)4 * t.ld);
+  const int k = comp_dense - 1;
+  if (k / 3 != i) return z;
+  return *reinterpret_cast<const float4*>(base + (long long)(1 + k % 3) * t.ld);
+}
+
+__global__ void __launch_bounds__(AW_WARPS * 32, 1)
+k_attention_fl_warp(JqAttnOperand q, JqAttnOperand k, JqAttnOperand v, float* __restrict__ out, int ldo, int n, int H) {
+  constexpr int dh = 64;
+  JQ_DYN_SMEM(float, sm);
+  const int nn = n * n, nt = n * AW_LD;
+  float* q0 = sm;
+  float* k0 = q0 + nt;
+  float* v0 = k0 + nt;
+  float* wgt = v0 + nt;
+  const int per_warp = (3 * nt + 3 * nn + 32 + n * dh + 3) & ~3;   // keeps every warp's float4 tiles 16-byte aligned
+  float* wbase = wgt + ((nn + 3) & ~3);
+  const long long w = blockIdx.x / H;
+  const int h = blockIdx.x % H;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int Cd = 3 * n + 2, K = 3 * n;
+  const float scale = 0.125f;   // 1 / sqrt(64)
+  float* qJ = wbase + (size_t)warp * per_warp;
+  float* kJ = qJ + nt;
+  float* vJ = kJ + nt;
+  float* aJ = vJ + nt;
+  float* aLp = aJ + nn;
+  float* t1p = aLp + nn;
+  float* t2p = t1p + nn;
+  float* abar = t2p + 16;
+  float* oLp = abar + 16;
+
+  // ---- value row: operands, logits, softmax, o = w v ----
+  for (int x = tid; x < n * 16; x += blockDim.x) {
+    const int i = x >> 4, d4 = (x & 15) * 4;
+    *reinterpret_cast<float4*>(q0 + i * AW_LD + d4) = attn_fetch4(q, w, n, i, 0, q.off + h * dh + d4, Cd);
+    *reinterpret_cast<float4*>(k0 + i * AW_LD + d4) = attn_fetch4(k, w, n, i, 0, k.off + h * dh + d4, Cd);
+    *reinterpret_cast<float4*>(v0 + i * AW_LD + d4) = attn_fetch4(v, w, n, i, 0, v.off + h * dh + d4, Cd);
+  }
+  for (int x = lane; x < 2 * nn + 32; x += 32) aLp[x] = 0.f;   // aL, t1 partials, t2, abar
+  for (int x = lane; x < n * dh; x += 32) oLp[x] = 0.f;
+  __syncthreads();
+  for (int x = tid; x < nn; x += blockDim.x) {
+    const int i = x / n, j = x - i * n;
+    float acc = 0.f;
+    for (int d = 0; d < dh; ++d) acc = fmaf(q0[i * AW_LD + d], k0[j * AW_LD + d], acc);
+    wgt[x] = acc * scale;
+  }
+  __syncthreads();
+  for (int i = tid; i < n; i += blockDim.x) {
+    float m = wgt[i * n];
+    for (int j = 1; j < n; ++j) m = fmaxf(m, wgt[i * n + j]);
+    float z = 0.f;
+    for (int j = 0; j < n; ++j) {
+      const float e = expf(wgt[i * n + j] - m);
+      wgt[i * n + j] = e;
+      z += e;
+    }
+    const float zi = 1.0f / z;
+    for (int j = 0; j < n; ++j) wgt[i * n + j] *= zi;
+  }
+  __syncthreads();
+  for (int x = tid; x < n * dh; x += blockDim.x) {
+    const int i = x >> 6, d = x & 63;
+    float acc = 0.f;
+    for (int j = 0; j < n; ++j) acc = fmaf(wgt[i * n + j], v0[j * AW_LD + d], acc);
+    out[((w * n + i) * (long long)Cd) * ldo + h * dh + d] = acc;
+  }
+
+  // ---- Jacobian components: one per warp at a time ----
+  const int ti = (lane >> 2) * 2, tj = (lane & 3) * 4;          // phase A tile: rows ti, ti+1; columns tj .. tj+3
+  const bool tile_on = ti < n && tj < n;
+  const int i0 = min(ti, n - 1), i1 = min(ti + 1, n - 1);
+  int jr[4];
+#pragma unroll
+  for (int u = 0; u < 4; ++u) jr[u] = min(tj + u, n - 1);
+  for (int kk = warp; kk < K; kk += AW_WARPS) {
+    const int comp = 1 + kk;
+    for (int x = lane; x < n * 16; x += 32) {
+      const int i = x >> 4, d4 = (x & 15) * 4;
+      *reinterpret_cast<float4*>(qJ + i * AW_LD + d4) = attn_fetch4(q, w, n, i, comp, q.off + h * dh + d4, Cd);
+      *reinterpret_cast<float4*>(kJ + i * AW_LD + d4) = attn_fetch4(k, w, n, i, comp, k.off + h * dh + d4, Cd);
+      *reinterpret_cast<float4*>(vJ + i * AW_LD + d4) = attn_fetch4(v, w, n, i, comp, v.off + h * dh + d4, Cd);
+    }
+    __syncwarp();
+    // phase A
+    if (tile_on) {
+      float a1[2][4], a2[2][4];
+#pragma unroll
+      for (int r = 0; r < 2; ++r)
+#pragma unroll
+        for (int u = 0; u < 4; ++u) a1[r][u] = a2[r][u] = 0.f;
+#pragma unroll 4
+      for (int d4 = 0; d4 < dh; d4 += 4) {
+        float4 qa[2], qb[2], ka[4], kb[4];
+        qa[0] = *reinterpret_cast<const float4*>(q0 + i0 * AW_LD + d4);
+        qa[1] = *reinterpret_cast<const float4*>(q0 + i1 * AW_LD + d4);
+        qb[0] = *reinterpret_cast<const float4*>(qJ + i0 * AW_LD + d4);
+        qb[1] = *reinterpret_cast<const float4*>(qJ + i1 * AW_LD + d4);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          ka[u] = *reinterpret_cast<const float4*>(k0 + jr[u] * AW_LD + d4);
+          kb[u] = *reinterpret_cast<const float4*>(kJ + jr[u] * AW_LD + d4);
+        }
+#pragma unroll
+        for (int r = 0; r < 2; ++r)
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            float s1 = a1[r][u], s2 = a2[r][u];
+            s1 = fmaf(qb[r].x, ka[u].x, s1); s1 = fmaf(qa[r].x, kb[u].x, s1); s2 = fmaf(qb[r].x, kb[u].x, s2);
+            s1 = fmaf(qb[r].y, ka[u].y, s1); s1 = fmaf(qa[r].y, kb[u].y, s1); s2 = fmaf(qb[r].y, kb[u].y, s2);
+            s1 = fmaf(qb[r].z, ka[u].z, s1); s1 = fmaf(qa[r].z, kb[u].z, s1); s2 = fmaf(qb[r].z, kb[u].z, s2);
+            s1 = fmaf(qb[r].w, ka[u].w, s1); s1 = fmaf(qa[r].w, kb[u].w, s1); s2 = fmaf(qb[r].w, kb[u].w, s2);
+            a1[r][u] = s1;
+            a2[r][u] = s2;
+          }
+      }
+#pragma unroll
+      for (int r = 0; r < 2; ++r)
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          if (ti + r < n && tj + u < n) {
+            const int x = (ti + r) * n + tj + u;
+            aJ[x] = a1[r][u] * scale;
+            aLp[x] = fmaf(2.0f * scale, a2[r][u], aLp[x]);
+          }
+    }
+    __syncwarp();
+    // phase B
+    if (lane < n) {
+      const int i = lane;
+      float ab = 0.f;
+      for (int m = 0; m < n; ++m) ab = fmaf(wgt[i * n + m], aJ[i * n + m], ab);
+      float t2 = 0.f;
+      for (int j = 0; j < n; ++j) {
+        const float a = aJ[i * n + j];
+        const float c = a - ab;
+        const float wj = wgt[i * n + j] * c;
+        t1p[i * n + j] = fmaf(wj, c, t1p[i * n + j]);
+        t2 = fmaf(wj, a, t2);
+        aJ[i * n + j] = wj;   // aJ now holds wJ
+      }
+      t2p[i] += t2;
+    }
+    __syncwarp();
+    // phase C
+    for (int ib = 0; ib < n; ib += 8) {
+      float acc[8][2], acc2[8][2];
+#pragma unroll
+      for (int r = 0; r < 8; ++r) acc[r][0] = acc[r][1] = acc2[r][0] = acc2[r][1] = 0.f;
+      for (int j = 0; j < n; ++j) {
+        const float va = v0[j * AW_LD + lane], vb = v0[j * AW_LD + lane + 32];
+        const float ja = vJ[j * AW_LD + lane], jb = vJ[j * AW_LD + lane + 32];
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+          const int i = min(ib + r, n - 1);
+          const float wj = aJ[i * n + j], ww = wgt[i * n + j];
+          acc[r][0] = fmaf(wj, va, acc[r][0]);
+          acc[r][0] = fmaf(ww, ja, acc[r][0]);
+          acc[r][1] = fmaf(wj, vb, acc[r][1]);
+          acc[r][1] = fmaf(ww, jb, acc[r][1]);
+          acc2[r][0] = fmaf(wj, ja, acc2[r][0]);
+          acc2[r][1] = fmaf(wj, jb, acc2[r][1]);
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < 8; ++r)
+        if (ib + r < n) {
+          const int i = ib + r;
+          float* o = out + ((w * n + i) * (long long)Cd + comp) * ldo + h * dh;
+          o[lane] = acc[r][0];
+          o[lane + 32] = acc[r][1];
+          oLp[i * dh + lane] = fmaf(2.0f, acc2[r][0], oLp[i * dh + lane]);
+          oLp[i * dh + lane + 32] = fmaf(2.0f, acc2[r][1], oLp[i * dh + lane + 32]);
+        }
+    }
+    __syncwarp();
+  }
+  __syncthreads();
+
+  // ---- reduce the per-warp partial sums (fixed order) into warp 0's area ----
+  float* aL = wbase + nt * 3 + nn;          // warp 0: aLp
+  float* t1 = aL + nn;
+  float* t2 = t1 + nn;
+  float* oL = t2 + 32;
+  for (int x = tid; x < nn; x += blockDim.x) {
+    float s1 = 0.f, s2 = 0.f;
+    for (int ww = 0; ww < AW_WARPS; ++ww) {
+      const float* b = wbase + (size_t)ww * per_warp + 3 * nt + nn;
+      s1 += b[x];
+      s2 += b[nn + x];
+    }
+    aL[x] = s1;
+    t1[x] = s2;
+  }
+  for (int x = tid; x < n * dh; x += blockDim.x) {
+    float s = 0.f;
+    for (int ww = 0; ww < AW_WARPS; ++ww) s += (wbase + (size_t)ww * per_warp + 3 * nt + 3 * nn + 32)[x];
+    oL[x] = s;
+  }
+  if (tid < n) {
+    float s = 0.f;
+    for (int ww = 0; ww < AW_WARPS; ++ww) s += (wbase + (size_t)ww * per_warp + 3 * nt + 3 * nn)[tid];
+    t2[tid] = s;
+  }
+  __syncthreads();
+  // ---- Laplacian row ----
+  float* qL = wbase + (size_t)1 * per_warp;   // warp 1's staging area is free now
+  float* kL = qL + nt;
+  float* vL = kL + nt;
+  float* wL = vL + nt;                         // warp 1's aJ
+  float* abL = wL + 3 * nn + 16;               // warp 1's abar
+  const int cl = Cd - 1;
+  for (int x = tid; x < n * 16; x += blockDim.x) {
+    const int i = x >> 4, d4 = (x & 15) * 4;
+    *reinterpret_cast<float4*>(qL + i * AW_LD + d4) = attn_fetch4(q, w, n, i, cl, q.off + h * dh + d4, Cd);
+    *reinterpret_cast<float4*>(kL + i * AW_LD + d4) = attn_fetch4(k, w, n, i, cl, k.off + h * dh + d4, Cd);
+    *reinterpret_cast<float4*>(vL + i * AW_LD + d4) = attn_fetch4(v, w, n, i, cl, v.off + h * dh + d4, Cd);
+  }
+  __syncthreads();
+  for (int x = tid; x < nn; x += blockDim.x) {
+    const int i = x / n, j = x - i * n;
+    float a1 = 0.f;
+    for (int d = 0; d < dh; ++d) {
+      a1 = fmaf(qL[i * AW_LD + d], k0[j * AW_LD + d], a1);
+      a1 = fmaf(q0[i * AW_LD + d], kL[j * AW_LD + d], a1);
+    }
+    aL[x] = fmaf(a1, scale, aL[x]);
+  }
+  __syncthreads();
+  for (int i = tid; i < n; i += blockDim.x) {
+    float ab = 0.f;
+    for (int m = 0; m < n; ++m) ab = fmaf(wgt[i * n + m], aL[i * n + m], ab);
+    abL[i] = ab;
+  }
+  __syncthreads();
+  for (int x = tid; x < nn; x += blockDim.x) {
+    const int i = x / n;
+    wL[x] = t1[x] + wgt[x] * (aL[x] - abL[i] - t2[i]);
+  }
+  __syncthreads();
+  for (int x = tid; x < n * dh; x += blockDim.x) {
+    const int i = x >> 6, d = x & 63;
+    float acc = oL[x];
+    for (int j = 0; j < n; ++j) {
+      acc = fmaf(wL[i * n + j], v0[j * AW_LD + d], acc);
+      acc = fmaf(wgt[i * n + j], vL[j * AW_LD + d], acc);
+    }
+    out[((w * n + i) * (long long)Cd + cl) * ldo + h * dh + d] = acc;
+  }
+}
+#endif
+
 int jq_launch_attention_fl(const JqAttnOperand& q, const JqAttnOperand& k, const JqAttnOperand& v, float* out, int ldo,
                            long long W, int n, int H, int dh, int track, cudaStream_t st) {
   if (W <= 0) return JQ_OK;
@@ -396,6 +673,23 @@ int jq_launch_attention_fl(const JqAttnOperand& q, const JqAttnOperand& k, const
 #endif
   double K = track ? 3.0 * n + 1.0 : 0.0;
   jq_prof_work((double)W * H * (4.0 * n * n * dh * (1.0 + 2.0 * K)), 4.0 * (double)W * n * Cd * H * dh * 4);
+#ifndef JAQMC_HOST_EMU
+  {
+    static const bool old_kernel = getenv("JAQMC_B200_ATTENTION_BLOCK") != nullptr;   // A/B switch
+    const bool aligned = (q.ld % 4 == 0) && (k.ld % 4 == 0) && (v.ld % 4 == 0) && (q.off % 4 == 0) && (k.off % 4 == 0) &&
+                         (v.off % 4 == 0) && ((reinterpret_cast<uintptr_t>(q.p) | reinterpret_cast<uintptr_t>(k.p) |
+                                               reinterpret_cast<uintptr_t>(v.p)) % 16 == 0);
+    if (track && dh == 64 && n >= 2 && n <= 16 && aligned && !old_kernel) {
+      const int nt = n * AW_LD, nn = n * n;
+      const size_t sw = sizeof(float) * ((size_t)3 * nt + ((nn + 3) & ~3) + (size_t)AW_WARPS * ((3 * nt + 3 * nn + 32 + n * 64 + 3) & ~3));
+      cudaError_t e = cudaFuncSetAttribute(k_attention_fl_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sw);
+      JQ_REQUIRE(e == cudaSuccess, JQ_ERR_CUDA, "attention: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+      JQ_LAUNCH(k_attention_fl_warp, dim3((unsigned)(W * H)), dim3(AW_WARPS * 32), sw, st, q, k, v, out, ldo, n, H);
+      JQ_CHECK_LAUNCH();
+      return JQ_OK;
+    }
+  }
+#endif
   JQ_LAUNCH(k_attention_fl, dim3((unsigned)(W * H)), dim3(256), smem, st, q, k, v, out, ldo, n, H, dh, track);
   JQ_CHECK_LAUNCH();
   return JQ_OK;
