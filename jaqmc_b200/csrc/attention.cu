@@ -395,99 +395,129 @@ __global__ void k_attention_fl(JqAttnOperand q, JqAttnOperand k, JqAttnOperand v
 // aJ aL t1 [n][n], t2 abar [16], oL [n][64].
 // ------------------------------------------------------------------------------------------------
 constexpr int AW_LD = 68;      // row stride of the [n][64] operand tiles (16-byte aligned, rows 4 banks apart)
+constexpr int AW_NS = 16;      // row stride of the [n][n] matrices (n <= 16): float4 reads along j
 constexpr int AW_WARPS = 8;
 
-__device__ __forceinline__ float4 attn_fetch4(const JqAttnOperand& t, long long w, int n, int i, int comp_dense, int col,
-                                              int Cd) {
+// 16-byte asynchronous copy global -> shared (LDGSTS), or a zero fill when the source element does not exist
+__device__ __forceinline__ void attn_stage4(float* dst, const JqAttnOperand& t, long long w, int n, int i, int comp_dense,
+                                            int col, int Cd) {
   const float* base = t.p + ((w * n + i) * (long long)t.C) * t.ld + col;
-  const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (t.C == Cd) return *reinterpret_cast<const float4*>(base + (long long)comp_dense * t.ld);
-  if (comp_dense == 0) return *reinterpret_cast<const float4*>(base);
-  if (comp_dense == Cd - 1) return *reinterpret_cast<const float4*>(base + (long long)4 * t.ld);
-  const int k = comp_dense - 1;
-  if (k / 3 != i) return z;
-  return *reinterpret_cast<const float4*>(base + (long long)(1 + k % 3) * t.ld);
+  const float* src;
+  if (t.C == Cd) src = base + (long long)comp_dense * t.ld;
+  else if (comp_dense == 0) src = base;
+  else if (comp_dense == Cd - 1) src = base + (long long)4 * t.ld;
+  else {
+    const int k = comp_dense - 1;
+    src = (k / 3 == i) ? base + (long long)(1 + k % 3) * t.ld : nullptr;
+  }
+  if (src) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src) : "memory");
+  } else {
+    *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
 }
+__device__ __forceinline__ void attn_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void attn_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 __global__ void __launch_bounds__(AW_WARPS * 32, 1)
 k_attention_fl_warp(JqAttnOperand q, JqAttnOperand k, JqAttnOperand v, float* __restrict__ out, int ldo, int n, int H) {
   constexpr int dh = 64;
   JQ_DYN_SMEM(float, sm);
-  const int nn = n * n, nt = n * AW_LD;
+  const int nn = n * AW_NS, nt = n * AW_LD;
   float* q0 = sm;
   float* k0 = q0 + nt;
   float* v0 = k0 + nt;
-  float* wgt = v0 + nt;
-  const int per_warp = (3 * nt + 3 * nn + 32 + n * dh + 3) & ~3;   // keeps every warp's float4 tiles 16-byte aligned
-  float* wbase = wgt + ((nn + 3) & ~3);
+  float* wgt = v0 + nt;            // [n][16]
+  float* red = wgt + nn;           // block-level reduction targets: aL t1 [n][16] | t2 abL [16] | oL [n][64]
+  const int red_floats = 2 * nn + 32 + n * dh;
+  const int per_warp = 6 * nt + 3 * nn + 32;   // two staging sets {qJ kJ vJ} | aJ aL t1 | t2 pad
+  float* wbase = red + red_floats;
   const long long w = blockIdx.x / H;
   const int h = blockIdx.x % H;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int Cd = 3 * n + 2, K = 3 * n;
   const float scale = 0.125f;   // 1 / sqrt(64)
-  float* qJ = wbase + (size_t)warp * per_warp;
-  float* kJ = qJ + nt;
-  float* vJ = kJ + nt;
-  float* aJ = vJ + nt;
+  float* stage = wbase + (size_t)warp * per_warp;
+  float* aJ = stage + 6 * nt;
   float* aLp = aJ + nn;
   float* t1p = aLp + nn;
   float* t2p = t1p + nn;
-  float* abar = t2p + 16;
-  float* oLp = abar + 16;
 
   // ---- value row: operands, logits, softmax, o = w v ----
   for (int x = tid; x < n * 16; x += blockDim.x) {
     const int i = x >> 4, d4 = (x & 15) * 4;
-    *reinterpret_cast<float4*>(q0 + i * AW_LD + d4) = attn_fetch4(q, w, n, i, 0, q.off + h * dh + d4, Cd);
-    *reinterpret_cast<float4*>(k0 + i * AW_LD + d4) = attn_fetch4(k, w, n, i, 0, k.off + h * dh + d4, Cd);
-    *reinterpret_cast<float4*>(v0 + i * AW_LD + d4) = attn_fetch4(v, w, n, i, 0, v.off + h * dh + d4, Cd);
+    attn_stage4(q0 + i * AW_LD + d4, q, w, n, i, 0, q.off + h * dh + d4, Cd);
+    attn_stage4(k0 + i * AW_LD + d4, k, w, n, i, 0, k.off + h * dh + d4, Cd);
+    attn_stage4(v0 + i * AW_LD + d4, v, w, n, i, 0, v.off + h * dh + d4, Cd);
   }
-  for (int x = lane; x < 2 * nn + 32; x += 32) aLp[x] = 0.f;   // aL, t1 partials, t2, abar
-  for (int x = lane; x < n * dh; x += 32) oLp[x] = 0.f;
+  attn_async_commit();
+  // first component of this warp: staged while the block computes the softmax
+  auto stage_comp = [&](int kk, int buf) {
+    float* qJ = stage + buf * 3 * nt;
+    for (int x = lane; x < n * 16; x += 32) {
+      const int i = x >> 4, d4 = (x & 15) * 4;
+      attn_stage4(qJ + i * AW_LD + d4, q, w, n, i, 1 + kk, q.off + h * dh + d4, Cd);
+      attn_stage4(qJ + nt + i * AW_LD + d4, k, w, n, i, 1 + kk, k.off + h * dh + d4, Cd);
+      attn_stage4(qJ + 2 * nt + i * AW_LD + d4, v, w, n, i, 1 + kk, v.off + h * dh + d4, Cd);
+    }
+    attn_async_commit();
+  };
+  if (warp < K) stage_comp(warp, 0);
+  for (int x = lane; x < 2 * nn + 32; x += 32) aLp[x] = 0.f;   // aL, t1 partials, t2
+  attn_async_wait<1>();   // the value operands (first group) have landed
   __syncthreads();
-  for (int x = tid; x < nn; x += blockDim.x) {
+  for (int x = tid; x < n * n; x += blockDim.x) {
     const int i = x / n, j = x - i * n;
     float acc = 0.f;
     for (int d = 0; d < dh; ++d) acc = fmaf(q0[i * AW_LD + d], k0[j * AW_LD + d], acc);
-    wgt[x] = acc * scale;
+    wgt[i * AW_NS + j] = acc * scale;
   }
   __syncthreads();
   for (int i = tid; i < n; i += blockDim.x) {
-    float m = wgt[i * n];
-    for (int j = 1; j < n; ++j) m = fmaxf(m, wgt[i * n + j]);
+    float m = wgt[i * AW_NS];
+    for (int j = 1; j < n; ++j) m = fmaxf(m, wgt[i * AW_NS + j]);
     float z = 0.f;
     for (int j = 0; j < n; ++j) {
-      const float e = expf(wgt[i * n + j] - m);
-      wgt[i * n + j] = e;
+      const float e = expf(wgt[i * AW_NS + j] - m);
+      wgt[i * AW_NS + j] = e;
       z += e;
     }
     const float zi = 1.0f / z;
-    for (int j = 0; j < n; ++j) wgt[i * n + j] *= zi;
+    for (int j = 0; j < AW_NS; ++j) wgt[i * AW_NS + j] = (j < n) ? wgt[i * AW_NS + j] * zi : 0.f;
   }
   __syncthreads();
   for (int x = tid; x < n * dh; x += blockDim.x) {
     const int i = x >> 6, d = x & 63;
     float acc = 0.f;
-    for (int j = 0; j < n; ++j) acc = fmaf(wgt[i * n + j], v0[j * AW_LD + d], acc);
+    for (int j = 0; j < n; ++j) acc = fmaf(wgt[i * AW_NS + j], v0[j * AW_LD + d], acc);
     out[((w * n + i) * (long long)Cd) * ldo + h * dh + d] = acc;
   }
 
-  // ---- Jacobian components: one per warp at a time ----
+  // ---- Jacobian components: one per warp at a time, operands of the next one in flight (cp.async) ----
   const int ti = (lane >> 2) * 2, tj = (lane & 3) * 4;          // phase A tile: rows ti, ti+1; columns tj .. tj+3
   const bool tile_on = ti < n && tj < n;
   const int i0 = min(ti, n - 1), i1 = min(ti + 1, n - 1);
   int jr[4];
 #pragma unroll
   for (int u = 0; u < 4; ++u) jr[u] = min(tj + u, n - 1);
-  for (int kk = warp; kk < K; kk += AW_WARPS) {
+  float oL[AW_NS][2];   // this lane's features (lane, lane + 32) of the 2 sum_k wJ vJ term, all rows
+#pragma unroll
+  for (int r = 0; r < AW_NS; ++r) oL[r][0] = oL[r][1] = 0.f;
+  int buf = 0;
+  for (int kk = warp; kk < K; kk += AW_WARPS, buf ^= 1) {
     const int comp = 1 + kk;
-    for (int x = lane; x < n * 16; x += 32) {
-      const int i = x >> 4, d4 = (x & 15) * 4;
-      *reinterpret_cast<float4*>(qJ + i * AW_LD + d4) = attn_fetch4(q, w, n, i, comp, q.off + h * dh + d4, Cd);
-      *reinterpret_cast<float4*>(kJ + i * AW_LD + d4) = attn_fetch4(k, w, n, i, comp, k.off + h * dh + d4, Cd);
-      *reinterpret_cast<float4*>(vJ + i * AW_LD + d4) = attn_fetch4(v, w, n, i, comp, v.off + h * dh + d4, Cd);
+    if (kk + AW_WARPS < K) {
+      stage_comp(kk + AW_WARPS, buf ^ 1);
+      attn_async_wait<1>();
+    } else {
+      attn_async_wait<0>();
     }
     __syncwarp();
+    const float* qJ = stage + buf * 3 * nt;
+    const float* kJ = qJ + nt;
+    const float* vJ = kJ + nt;
     // phase A
     if (tile_on) {
       float a1[2][4], a2[2][4];
@@ -525,7 +555,7 @@ k_attention_fl_warp(JqAttnOperand q, JqAttnOperand k, JqAttnOperand v, float* __
 #pragma unroll
         for (int u = 0; u < 4; ++u)
           if (ti + r < n && tj + u < n) {
-            const int x = (ti + r) * n + tj + u;
+            const int x = (ti + r) * AW_NS + tj + u;
             aJ[x] = a1[r][u] * scale;
             aLp[x] = fmaf(2.0f * scale, a2[r][u], aLp[x]);
           }
@@ -535,63 +565,87 @@ k_attention_fl_warp(JqAttnOperand q, JqAttnOperand k, JqAttnOperand v, float* __
     if (lane < n) {
       const int i = lane;
       float ab = 0.f;
-      for (int m = 0; m < n; ++m) ab = fmaf(wgt[i * n + m], aJ[i * n + m], ab);
+      for (int m = 0; m < n; ++m) ab = fmaf(wgt[i * AW_NS + m], aJ[i * AW_NS + m], ab);
       float t2 = 0.f;
-      for (int j = 0; j < n; ++j) {
-        const float a = aJ[i * n + j];
+      for (int j = 0; j < AW_NS; ++j) {
+        const float a = (j < n) ? aJ[i * AW_NS + j] : 0.f;
         const float c = a - ab;
-        const float wj = wgt[i * n + j] * c;
-        t1p[i * n + j] = fmaf(wj, c, t1p[i * n + j]);
+        const float wj = wgt[i * AW_NS + j] * c;   // w = 0 in the padding columns
+        t1p[i * AW_NS + j] = fmaf(wj, c, t1p[i * AW_NS + j]);
         t2 = fmaf(wj, a, t2);
-        aJ[i * n + j] = wj;   // aJ now holds wJ
+        aJ[i * AW_NS + j] = wj;   // aJ now holds wJ
       }
       t2p[i] += t2;
     }
     __syncwarp();
-    // phase C
-    for (int ib = 0; ib < n; ib += 8) {
-      float acc[8][2], acc2[8][2];
+    // phase C: rows in two passes of 8, j in steps of 4 (float4 broadcasts of wJ and w)
 #pragma unroll
-      for (int r = 0; r < 8; ++r) acc[r][0] = acc[r][1] = acc2[r][0] = acc2[r][1] = 0.f;
-      for (int j = 0; j < n; ++j) {
-        const float va = v0[j * AW_LD + lane], vb = v0[j * AW_LD + lane + 32];
-        const float ja = vJ[j * AW_LD + lane], jb = vJ[j * AW_LD + lane + 32];
+    for (int ib = 0; ib < AW_NS; ib += 8) {
+      if (ib < n) {
+        float acc[8][2], acc2[8][2];
 #pragma unroll
-        for (int r = 0; r < 8; ++r) {
-          const int i = min(ib + r, n - 1);
-          const float wj = aJ[i * n + j], ww = wgt[i * n + j];
-          acc[r][0] = fmaf(wj, va, acc[r][0]);
-          acc[r][0] = fmaf(ww, ja, acc[r][0]);
-          acc[r][1] = fmaf(wj, vb, acc[r][1]);
-          acc[r][1] = fmaf(ww, jb, acc[r][1]);
-          acc2[r][0] = fmaf(wj, ja, acc2[r][0]);
-          acc2[r][1] = fmaf(wj, jb, acc2[r][1]);
+        for (int r = 0; r < 8; ++r) acc[r][0] = acc[r][1] = acc2[r][0] = acc2[r][1] = 0.f;
+        for (int j4 = 0; j4 < n; j4 += 4) {
+          float va[4], vb[4], ja[4], jb[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int j = min(j4 + u, n - 1);   // w = wJ = 0 beyond n: the clamped operand does not contribute
+            va[u] = v0[j * AW_LD + lane];
+            vb[u] = v0[j * AW_LD + lane + 32];
+            ja[u] = vJ[j * AW_LD + lane];
+            jb[u] = vJ[j * AW_LD + lane + 32];
+          }
+#pragma unroll
+          for (int r = 0; r < 8; ++r) {
+            const int i = min(ib + r, n - 1);
+            const float4 wj4 = *reinterpret_cast<const float4*>(aJ + i * AW_NS + j4);
+            const float4 ww4 = *reinterpret_cast<const float4*>(wgt + i * AW_NS + j4);
+            const float wj[4] = {wj4.x, wj4.y, wj4.z, wj4.w}, ww[4] = {ww4.x, ww4.y, ww4.z, ww4.w};
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              acc[r][0] = fmaf(wj[u], va[u], acc[r][0]);
+              acc[r][0] = fmaf(ww[u], ja[u], acc[r][0]);
+              acc[r][1] = fmaf(wj[u], vb[u], acc[r][1]);
+              acc[r][1] = fmaf(ww[u], jb[u], acc[r][1]);
+              acc2[r][0] = fmaf(wj[u], ja[u], acc2[r][0]);
+              acc2[r][1] = fmaf(wj[u], jb[u], acc2[r][1]);
+            }
+          }
         }
+#pragma unroll
+        for (int r = 0; r < 8; ++r)
+          if (ib + r < n) {
+            const int i = ib + r;
+            float* o = out + ((w * n + i) * (long long)Cd + comp) * ldo + h * dh;
+            o[lane] = acc[r][0];
+            o[lane + 32] = acc[r][1];
+            oL[ib + r][0] = fmaf(2.0f, acc2[r][0], oL[ib + r][0]);
+            oL[ib + r][1] = fmaf(2.0f, acc2[r][1], oL[ib + r][1]);
+          }
       }
-#pragma unroll
-      for (int r = 0; r < 8; ++r)
-        if (ib + r < n) {
-          const int i = ib + r;
-          float* o = out + ((w * n + i) * (long long)Cd + comp) * ldo + h * dh;
-          o[lane] = acc[r][0];
-          o[lane + 32] = acc[r][1];
-          oLp[i * dh + lane] = fmaf(2.0f, acc2[r][0], oLp[i * dh + lane]);
-          oLp[i * dh + lane + 32] = fmaf(2.0f, acc2[r][1], oLp[i * dh + lane + 32]);
-        }
     }
     __syncwarp();
   }
   __syncthreads();
 
-  // ---- reduce the per-warp partial sums (fixed order) into warp 0's area ----
-  float* aL = wbase + nt * 3 + nn;          // warp 0: aLp
+  // ---- reduce the per-warp partial sums in a fixed order ----
+  float* aL = red;
   float* t1 = aL + nn;
   float* t2 = t1 + nn;
-  float* oL = t2 + 32;
+  float* abL = t2 + 16;
+  float* oLs = abL + 16;
+  // oL lives in registers: each warp parks its partial in its own (now free) staging area first
+#pragma unroll
+  for (int r = 0; r < AW_NS; ++r)
+    if (r < n) {
+      stage[r * dh + lane] = oL[r][0];
+      stage[r * dh + lane + 32] = oL[r][1];
+    }
+  __syncthreads();
   for (int x = tid; x < nn; x += blockDim.x) {
     float s1 = 0.f, s2 = 0.f;
     for (int ww = 0; ww < AW_WARPS; ++ww) {
-      const float* b = wbase + (size_t)ww * per_warp + 3 * nt + nn;
+      const float* b = wbase + (size_t)ww * per_warp + 6 * nt + nn;
       s1 += b[x];
       s2 += b[nn + x];
     }
@@ -600,56 +654,57 @@ k_attention_fl_warp(JqAttnOperand q, JqAttnOperand k, JqAttnOperand v, float* __
   }
   for (int x = tid; x < n * dh; x += blockDim.x) {
     float s = 0.f;
-    for (int ww = 0; ww < AW_WARPS; ++ww) s += (wbase + (size_t)ww * per_warp + 3 * nt + 3 * nn + 32)[x];
-    oL[x] = s;
+    for (int ww = 0; ww < AW_WARPS; ++ww) s += (wbase + (size_t)ww * per_warp)[x];
+    oLs[x] = s;
   }
   if (tid < n) {
     float s = 0.f;
-    for (int ww = 0; ww < AW_WARPS; ++ww) s += (wbase + (size_t)ww * per_warp + 3 * nt + 3 * nn)[tid];
+    for (int ww = 0; ww < AW_WARPS; ++ww) s += (wbase + (size_t)ww * per_warp + 6 * nt + 3 * nn)[tid];
     t2[tid] = s;
   }
   __syncthreads();
   // ---- Laplacian row ----
-  float* qL = wbase + (size_t)1 * per_warp;   // warp 1's staging area is free now
+  float* qL = wbase + 3 * nt;   // warp 0's second staging set (not read by the reductions above)
   float* kL = qL + nt;
   float* vL = kL + nt;
-  float* wL = vL + nt;                         // warp 1's aJ
-  float* abL = wL + 3 * nn + 16;               // warp 1's abar
+  float* wL = wbase + 6 * nt;   // warp 0's aJ
   const int cl = Cd - 1;
   for (int x = tid; x < n * 16; x += blockDim.x) {
     const int i = x >> 4, d4 = (x & 15) * 4;
-    *reinterpret_cast<float4*>(qL + i * AW_LD + d4) = attn_fetch4(q, w, n, i, cl, q.off + h * dh + d4, Cd);
-    *reinterpret_cast<float4*>(kL + i * AW_LD + d4) = attn_fetch4(k, w, n, i, cl, k.off + h * dh + d4, Cd);
-    *reinterpret_cast<float4*>(vL + i * AW_LD + d4) = attn_fetch4(v, w, n, i, cl, v.off + h * dh + d4, Cd);
+    attn_stage4(qL + i * AW_LD + d4, q, w, n, i, cl, q.off + h * dh + d4, Cd);
+    attn_stage4(kL + i * AW_LD + d4, k, w, n, i, cl, k.off + h * dh + d4, Cd);
+    attn_stage4(vL + i * AW_LD + d4, v, w, n, i, cl, v.off + h * dh + d4, Cd);
   }
+  attn_async_commit();
+  attn_async_wait<0>();
   __syncthreads();
-  for (int x = tid; x < nn; x += blockDim.x) {
+  for (int x = tid; x < n * n; x += blockDim.x) {
     const int i = x / n, j = x - i * n;
     float a1 = 0.f;
     for (int d = 0; d < dh; ++d) {
       a1 = fmaf(qL[i * AW_LD + d], k0[j * AW_LD + d], a1);
       a1 = fmaf(q0[i * AW_LD + d], kL[j * AW_LD + d], a1);
     }
-    aL[x] = fmaf(a1, scale, aL[x]);
+    aL[i * AW_NS + j] = fmaf(a1, scale, aL[i * AW_NS + j]);
   }
   __syncthreads();
   for (int i = tid; i < n; i += blockDim.x) {
     float ab = 0.f;
-    for (int m = 0; m < n; ++m) ab = fmaf(wgt[i * n + m], aL[i * n + m], ab);
+    for (int m = 0; m < n; ++m) ab = fmaf(wgt[i * AW_NS + m], aL[i * AW_NS + m], ab);
     abL[i] = ab;
   }
   __syncthreads();
-  for (int x = tid; x < nn; x += blockDim.x) {
-    const int i = x / n;
-    wL[x] = t1[x] + wgt[x] * (aL[x] - abL[i] - t2[i]);
+  for (int x = tid; x < n * n; x += blockDim.x) {
+    const int i = x / n, j = x - i * n;
+    wL[i * AW_NS + j] = t1[i * AW_NS + j] + wgt[i * AW_NS + j] * (aL[i * AW_NS + j] - abL[i] - t2[i]);
   }
   __syncthreads();
   for (int x = tid; x < n * dh; x += blockDim.x) {
     const int i = x >> 6, d = x & 63;
-    float acc = oL[x];
+    float acc = oLs[x];
     for (int j = 0; j < n; ++j) {
-      acc = fmaf(wL[i * n + j], v0[j * AW_LD + d], acc);
-      acc = fmaf(wgt[i * n + j], vL[j * AW_LD + d], acc);
+      acc = fmaf(wL[i * AW_NS + j], v0[j * AW_LD + d], acc);
+      acc = fmaf(wgt[i * AW_NS + j], vL[j * AW_LD + d], acc);
     }
     out[((w * n + i) * (long long)Cd + cl) * ldo + h * dh + d] = acc;
   }
@@ -679,9 +734,9 @@ int jq_launch_attention_fl(const JqAttnOperand& q, const JqAttnOperand& k, const
     const bool aligned = (q.ld % 4 == 0) && (k.ld % 4 == 0) && (v.ld % 4 == 0) && (q.off % 4 == 0) && (k.off % 4 == 0) &&
                          (v.off % 4 == 0) && ((reinterpret_cast<uintptr_t>(q.p) | reinterpret_cast<uintptr_t>(k.p) |
                                                reinterpret_cast<uintptr_t>(v.p)) % 16 == 0);
-    if (track && dh == 64 && n >= 2 && n <= 16 && aligned && !old_kernel) {
-      const int nt = n * AW_LD, nn = n * n;
-      const size_t sw = sizeof(float) * ((size_t)3 * nt + ((nn + 3) & ~3) + (size_t)AW_WARPS * ((3 * nt + 3 * nn + 32 + n * 64 + 3) & ~3));
+    const int nt = n * AW_LD, nn = n * AW_NS;
+    const size_t sw = sizeof(float) * ((size_t)3 * nt + nn + (2 * nn + 32 + n * 64) + (size_t)AW_WARPS * (6 * nt + 3 * nn + 32));
+    if (track && dh == 64 && n >= 2 && n <= AW_NS && sw <= 227 * 1024 && aligned && !old_kernel) {
       cudaError_t e = cudaFuncSetAttribute(k_attention_fl_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sw);
       JQ_REQUIRE(e == cudaSuccess, JQ_ERR_CUDA, "attention: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
       JQ_LAUNCH(k_attention_fl_warp, dim3((unsigned)(W * H)), dim3(AW_WARPS * 32), sw, st, q, k, v, out, ldo, n, H);
