@@ -174,10 +174,139 @@ __global__ void k_layernorm_fl(const float* __restrict__ x, const float* __restr
   }
 }
 
+#ifndef JAQMC_HOST_EMU
+// Same rule with the group [C][F] cached in shared memory: global memory is read once and written once (k_layernorm_fl
+// walks it three times).  Row statistics: one warp per row, float4 reads, shuffle reduction.
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__global__ void __launch_bounds__(256) k_layernorm_fl_smem(const float* __restrict__ x, const float* __restrict__ scale,
+                                                          const float* __restrict__ bias, float* __restrict__ out, int C,
+                                                          int F, float eps) {
+  JQ_DYN_SMEM(float, sm);
+  float* xs = sm;                    // [C][F]
+  float* mu = xs + (size_t)C * F;    // [C]
+  float* dot = mu + C;
+  float* sq = dot + C;
+  float* sj = sq + C;
+  float* scal = sj + C;              // [8]
+  const long long g = blockIdx.x;
+  const float4* xg4 = reinterpret_cast<const float4*>(x + g * (long long)C * F);
+  float* og = out + g * (long long)C * F;
+  const int tid = threadIdx.x, nt = blockDim.x, warp = tid >> 5, lane = tid & 31, nw = nt >> 5;
+  const float invF = 1.0f / (float)F;
+  const int K = C - 2;
+  const int F4 = F >> 2;
+  float4* xs4 = reinterpret_cast<float4*>(xs);
+  for (int q = tid; q < C * F4; q += nt) xs4[q] = xg4[q];
+  __syncthreads();
+  // row means (+ mean square of the value row)
+  for (int c = warp; c < C; c += nw) {
+    float s = 0.f, s2 = 0.f;
+    for (int f4 = lane; f4 < F4; f4 += 32) {
+      const float4 v = xs4[c * F4 + f4];
+      s += (v.x + v.y) + (v.z + v.w);
+      if (c == 0) s2 = fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, fmaf(v.w, v.w, s2))));
+    }
+    s = warp_sum(s);
+    if (c == 0) s2 = warp_sum(s2);
+    if (lane == 0) {
+      mu[c] = s * invF;
+      if (c == 0) scal[7] = s2 * invF;
+    }
+  }
+  __syncthreads();
+  if (tid == 0) {
+    float var = scal[7] - mu[0] * mu[0];
+    if (var < 0.f) var = 0.f;
+    scal[0] = rsqrtf(var + eps);
+  }
+  __syncthreads();
+  const float s = scal[0];
+  const float mu0 = mu[0];
+  if (C > 1) {
+    for (int c = 1 + warp; c < C; c += nw) {
+      const float m = mu[c];
+      float d = 0.f, s2 = 0.f;
+      for (int f4 = lane; f4 < F4; f4 += 32) {
+        const float4 a = xs4[f4], v = xs4[c * F4 + f4];
+        const float v0 = v.x - m, v1 = v.y - m, v2 = v.z - m, v3 = v.w - m;
+        d = fmaf(a.x - mu0, v0, d);
+        d = fmaf(a.y - mu0, v1, d);
+        d = fmaf(a.z - mu0, v2, d);
+        d = fmaf(a.w - mu0, v3, d);
+        s2 = fmaf(v0, v0, fmaf(v1, v1, fmaf(v2, v2, fmaf(v3, v3, s2))));
+      }
+      d = warp_sum(d);
+      s2 = warp_sum(s2);
+      if (lane == 0) {
+        dot[c] = d;
+        sq[c] = s2;
+        sj[c] = -0.5f * s * s * s * (2.0f * d * invF);
+      }
+    }
+    __syncthreads();
+    if (tid == 0) {
+      float sumq = 0.f, sumv2 = 0.f;
+      for (int k = 1; k <= K; ++k) {
+        sumq += sq[k];
+        const float vj = 2.0f * dot[k] * invF;
+        sumv2 = fmaf(vj, vj, sumv2);
+      }
+      const float s3 = s * s * s;
+      const float varL = 2.0f * dot[C - 1] * invF + 2.0f * sumq * invF;
+      scal[1] = -0.5f * s3 * varL + 0.75f * s3 * s * s * sumv2;  // sL
+    }
+    __syncthreads();
+  }
+  // outputs
+  for (int q = tid; q < (C > 1 ? C - 1 : 1) * F; q += nt) {
+    const int c = q / F, f = q - c * F;
+    const float xc = xs[f] - mu0;
+    const float sc = scale ? scale[f] : 1.0f;
+    if (c == 0) {
+      float y = xc * s * sc;
+      if (bias) y += bias[f];
+      og[f] = y;
+    } else {
+      const float v = xs[c * F + f] - mu[c];
+      og[(long long)c * F + f] = (v * s + xc * sj[c]) * sc;
+    }
+  }
+  if (C > 1) {
+    const float sL = scal[1];
+    for (int f = tid; f < F; f += nt) {
+      const float xc = xs[f] - mu0;
+      float acc = 0.f;
+      for (int k = 1; k <= K; ++k) acc = fmaf(xs[k * F + f] - mu[k], sj[k], acc);
+      const float v = xs[(C - 1) * F + f] - mu[C - 1];
+      const float sc = scale ? scale[f] : 1.0f;
+      og[(long long)(C - 1) * F + f] = (v * s + xc * sL + 2.0f * acc) * sc;
+    }
+  }
+}
+#endif
+
 int jq_launch_layernorm_fl(const float* x, const float* scale, const float* bias, float* out, long long G, int C, int F,
                            float eps, cudaStream_t st) {
   if (G <= 0) return JQ_OK;
   JQ_REQUIRE(x != out, JQ_ERR_INVALID_ARGUMENT, "layernorm: in-place is not supported");
+#ifndef JAQMC_HOST_EMU
+  {
+    const size_t sc = sizeof(float) * ((size_t)C * F + 4 * (size_t)C + 8);
+    if (F % 4 == 0 && sc <= 200 * 1024 && (reinterpret_cast<uintptr_t>(x) & 15) == 0) {
+      cudaError_t e = cudaFuncSetAttribute(k_layernorm_fl_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sc);
+      JQ_REQUIRE(e == cudaSuccess, JQ_ERR_CUDA, "layernorm: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+      jq_prof_work(0.0, 8.0 * (double)G * C * F);
+      JQ_LAUNCH(k_layernorm_fl_smem, dim3((unsigned)G), dim3(256), sc, st, x, scale, bias, out, C, F, eps);
+      JQ_CHECK_LAUNCH();
+      return JQ_OK;
+    }
+  }
+#endif
   size_t smem = sizeof(float) * ((size_t)4 * C + (size_t)2 * C * LN_T + 8);
   JQ_REQUIRE(smem <= 200 * 1024, JQ_ERR_UNSUPPORTED, "layernorm: %d components need %zu bytes of shared memory", C, smem);
 #ifndef JAQMC_HOST_EMU
