@@ -88,6 +88,17 @@ def test_psiformer_parity_n2_full_network():
     _check(_psiformer("N2", 16, 4, 4, 64, (256,), 4), l_tol=TC_L_TOL)
 
 
+def test_psiformer_parity_benzene_full_network():
+    """BASELINE config 4 at its full per-walker size: C6H6 (42 electrons, 12 atoms, 128 components per group), default
+    Psiformer.  Exercises the 128-row groups of the tcgen05 kernel, the 672-column orbital layers (six feature blocks)
+    and the generic attention / LogDet kernels (n > 16)."""
+    _check(_psiformer("C6H6", 16, 4, 4, 64, (256,), 5), l_tol=TC_L_TOL)
+
+
+def test_lapnet_parity_benzene_full_network():
+    _check(_lapnet("C6H6", 16, 4, 4, 64, 5), l_tol=TC_L_TOL)
+
+
 def test_attention_nets_full_batch_properties():
     """Size-independent properties at 4096 walkers: finite energies, antisymmetry, walker-permutation equivariance."""
     rt = _rt()

@@ -25,6 +25,13 @@ def test_solid_local_energy_matches_oracle(kind, kw):
     assert np.isfinite(out["e_loc"].real).all()
 
 
+def test_solid_parity_lih_222_full_network():
+    """BASELINE config 5 at its full per-walker size: LiH rock salt 2x2x2 (32 electrons, 16 atoms, 98 components per
+    group, 512-column complex orbital layers), default network widths."""
+    out = S.check_solid(_rt(), "fcc_lih_222", 3, device="cuda", ndets=16, hs=(256,) * 4, hd=(32,) * 4)
+    assert np.isfinite(out["e_loc"].real).all()
+
+
 def test_solid_full_batch_properties():
     """4096 walkers: finite energies, invariance of psi under a simulation-lattice translation of one electron
     (reference tests/wavefunction/solid_test.py:112-137), determinism."""
