@@ -79,6 +79,12 @@ size_t jq_dense_tc_scratch_floats(int k_total, int n_out);
 int jq_launch_tanh_fl(const float* y, const float* res, float* out, long long G, int C, int F, int residual_mode,
                       cudaStream_t st);
 int jq_launch_pair_mean(const float* h2, float* g2, int W, JqSpins sp, int d2, int track, cudaStream_t st);
+#ifndef JAQMC_HOST_EMU
+// one two-electron layer fused with the spin-channel means of its output (32 output features); returns
+// false when the shape is not covered (the caller then takes jq_launch_dense + jq_launch_pair_mean)
+bool jq_launch_pair_layer_fused(const float* h2, int K, const float* w0, const float* bias, float* h2n, float* g2, int W,
+                                JqSpins sp, int N, int residual, int track, cudaStream_t st, int* rc);
+#endif
 int jq_launch_concat_layer1(const float* ae, const float* g2, float* out, int W, JqSpins sp, int f1, int fg,
                             int track, cudaStream_t st);
 int jq_launch_spin_mean(const float* h, float* m, int W, JqSpins sp, int C, int F, cudaStream_t st);

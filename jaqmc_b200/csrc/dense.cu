@@ -10,6 +10,8 @@
 // The CUDA-core GEMM below serves the narrow layers (contraction width < 64: input layers, the
 // two-electron stream) and is the numerical cross-check of the tcgen05 kernel in dense_tc.cu, which takes
 // the wide (>= 64-deep) layers on device builds.
+#include <cstdlib>
+
 #include "aug.cuh"
 
 // ------------------------------------------------------------------------------------------------
@@ -505,6 +507,173 @@ __global__ void k_pair_mean(const float* __restrict__ h2, float* __restrict__ g2
     }
   }
 }
+
+#ifndef JAQMC_HOST_EMU
+// ------------------------------------------------------------------------------------------------
+// FermiNet two-electron stream, one layer fused with the spin-channel means that feed the next one-electron layer
+// (wavefunction/backbone/ferminet.py:57-63 followed by aggregate_features :82-90 of the next layer):
+//     h2'[i,j] = res( tanh-FL( h2[i,j] . K + b ) ),      g2'[j] = mean_{i in channel} h2'[i,j]   (Local2 -> dense)
+// k_dense_small + k_pair_mean read / write the pair tensor three times; here one WARP owns a column j of a walker
+// (the n pairs (i, j)), a lane is an output feature (32 of them) with its weight column in registers, and the means
+// are accumulated in registers while the pairs stream through, so the pair tensor is read once and written once --
+// or not written at all for the last two-electron layer, whose output is only ever used through its means.
+// Local2 components: 0 value, 1-3 d/dr_i, 4-6 d/dr_j, 7 Laplacian.  g2' component of electron e, axis a:
+//     ([e in channel] h2'[e,j][1+a] + [e == j] sum_{i in channel} h2'[i,j][4+a]) / |channel|     (k_pair_mean).
+// ------------------------------------------------------------------------------------------------
+template <int K, int C2>   // C2 = 8: Local2 components (forward Laplacian); C2 = 1: value only (sampling path)
+__global__ void __launch_bounds__(256) k_pair_layer_fused(const float* __restrict__ h2, const float* __restrict__ w0,
+                                                         const float* __restrict__ bias, float* __restrict__ h2n,
+                                                         float* __restrict__ g2, long long WJ, JqSpins sp, int residual) {
+  __shared__ float4 tile_all[8][C2 * K / 4];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float4* tile = tile_all[warp];
+  const float* tile_f = reinterpret_cast<const float*>(tile);
+  const int n = sp.n(), nch = sp.nch();
+  const int C = (C2 == 8) ? 3 * n + 2 : 1, FO = nch * 32;
+  float wreg[K];
+#pragma unroll
+  for (int k = 0; k < K; ++k) wreg[k] = w0[k * 32 + lane];
+  const float b = bias ? bias[lane] : 0.f;
+  const float inv_sqrt2 = 0.70710678118654752440f;
+  const float4* src4 = reinterpret_cast<const float4*>(h2);
+  constexpr int NV = (C2 * K / 4 + 31) / 32;   // float4 per lane of one pair tile
+  for (long long wj = (long long)blockIdx.x * 8 + warp; wj < WJ; wj += (long long)gridDim.x * 8) {
+    const long long w = wj / n;
+    const int j = (int)(wj - w * n);
+    // per-channel sums kept in scalar registers (no dynamically indexed arrays): channel 0 / channel 1
+    float sx0 = 0.f, sx1 = 0.f, sl0 = 0.f, sl1 = 0.f, sj0[3] = {0.f, 0.f, 0.f}, sj1[3] = {0.f, 0.f, 0.f};
+    float own[3] = {0.f, 0.f, 0.f};
+    float* o = g2 + (wj * C) * FO + lane;   // component c, channel s at o[c * FO + s * 32]
+    // the next pair's tile travels in registers while the current one is processed
+    float4 nxt[NV];
+    {
+      const long long pair = (w * n) * n + j;
+#pragma unroll
+      for (int v = 0; v < NV; ++v)
+        if (lane + 32 * v < C2 * K / 4) nxt[v] = src4[pair * (C2 * K / 4) + lane + 32 * v];
+    }
+    for (int i = 0; i < n; ++i) {
+      const long long pair = (w * n + i) * n + j;
+#pragma unroll
+      for (int v = 0; v < NV; ++v)
+        if (lane + 32 * v < C2 * K / 4) tile[lane + 32 * v] = nxt[v];
+      if (i + 1 < n) {
+        const long long pn = pair + n;
+#pragma unroll
+        for (int v = 0; v < NV; ++v)
+          if (lane + 32 * v < C2 * K / 4) nxt[v] = src4[pn * (C2 * K / 4) + lane + 32 * v];
+      }
+      __syncwarp();
+      float y[8];
+#pragma unroll
+      for (int c = 0; c < C2; ++c) {
+        float acc = 0.f;
+#pragma unroll
+        for (int k = 0; k < K; k += 4) {
+          const float4 x = tile[(c * K + k) / 4];
+          acc = fmaf(x.x, wreg[k], acc);
+          acc = fmaf(x.y, wreg[k + 1], acc);
+          acc = fmaf(x.z, wreg[k + 2], acc);
+          acc = fmaf(x.w, wreg[k + 3], acc);
+        }
+        y[c] = acc;
+      }
+      // tanh with the forward-Laplacian rule (elementwise.py:42-72)
+      const float t = tanhf(y[0] + b);
+      if (C2 == 8) {
+        const float d1 = 1.0f - t * t;
+        float s2 = 0.f;
+#pragma unroll
+        for (int c = 1; c < 7; ++c) {
+          s2 = fmaf(y[c], y[c], s2);
+          y[c] *= d1;
+        }
+        y[7] = d1 * y[7] - 2.0f * t * d1 * s2;
+      }
+      y[0] = t;
+      if (residual) {
+#pragma unroll
+        for (int c = 0; c < C2; ++c) y[c] = (tile_f[c * K + lane] + y[c]) * inv_sqrt2;   // K == 32 here
+      }
+      if (h2n) {
+        float* out = h2n + pair * (C2 * 32) + lane;
+#pragma unroll
+        for (int c = 0; c < C2; ++c) out[c * 32] = y[c];
+      }
+      const int s = sp.chan_of(i);
+      const bool c1 = (s == 1);
+      const float inv_s = 1.0f / (float)(sp.hi(s) - sp.lo(s));
+      sx0 += c1 ? 0.f : y[0];
+      sx1 += c1 ? y[0] : 0.f;
+      if (C2 == 8) {
+        sl0 += c1 ? 0.f : y[7];
+        sl1 += c1 ? y[7] : 0.f;
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+          sj0[a] += c1 ? 0.f : y[4 + a];
+          sj1[a] += c1 ? y[4 + a] : 0.f;
+          if (i == j) {
+            own[a] = y[1 + a];
+          } else {
+            o[(long long)(1 + 3 * i + a) * FO + s * 32] = y[1 + a] * inv_s;
+            if (nch == 2) o[(long long)(1 + 3 * i + a) * FO + (1 - s) * 32] = 0.f;
+          }
+        }
+      }
+      __syncwarp();
+    }
+    const int sjn = sp.chan_of(j);
+    {
+      const float inv0 = 1.0f / (float)(sp.hi(0) - sp.lo(0));
+      o[0] = sx0 * inv0;
+      if (C2 == 8) {
+        o[(long long)(C - 1) * FO] = sl0 * inv0;
+#pragma unroll
+        for (int a = 0; a < 3; ++a) o[(long long)(1 + 3 * j + a) * FO] = ((sjn == 0 ? own[a] : 0.f) + sj0[a]) * inv0;
+      }
+    }
+    if (nch == 2) {
+      const float inv1 = 1.0f / (float)(sp.hi(1) - sp.lo(1));
+      o[32] = sx1 * inv1;
+      if (C2 == 8) {
+        o[(long long)(C - 1) * FO + 32] = sl1 * inv1;
+#pragma unroll
+        for (int a = 0; a < 3; ++a) o[(long long)(1 + 3 * j + a) * FO + 32] = ((sjn == 1 ? own[a] : 0.f) + sj1[a]) * inv1;
+      }
+    }
+  }
+}
+
+// h2 [W][n*n][C2][K] -> h2n [W][n*n][C2][32] (or null) and g2 [W][n][C][nch*32] (C2 = 8, C = 3n+2 tracked; 1, 1 value
+// only); false when the shape is not covered
+bool jq_launch_pair_layer_fused(const float* h2, int K, const float* w0, const float* bias, float* h2n, float* g2, int W,
+                                JqSpins sp, int N, int residual, int track, cudaStream_t st, int* rc) {
+  *rc = JQ_OK;
+  static const bool disabled = getenv("JAQMC_B200_UNFUSED_PAIR_LAYER") != nullptr;   // A/B switch
+  if (disabled || N != 32 || (K != 4 && K != 32) || (residual && K != 32) || (reinterpret_cast<uintptr_t>(h2) & 15)) return false;
+  const long long WJ = (long long)W * sp.n();
+  if (WJ <= 0) return true;
+  long long blocks = jq_cdiv(WJ, 8);   // one (walker, j) column per warp
+  const double pairs = (double)W * sp.n() * sp.n();
+  const int C2 = track ? 8 : 1, C = track ? 3 * sp.n() + 2 : 1;
+  jq_prof_work(2.0 * pairs * C2 * K * 32, 4.0 * (pairs * C2 * (K + (h2n ? 32 : 0)) + (double)WJ * C * sp.nch() * 32));
+#define JQ_PLF(KK, CC) JQ_LAUNCH((k_pair_layer_fused<KK, CC>), dim3((unsigned)blocks), dim3(256), 0, st, h2, w0, bias, h2n, g2, WJ, sp, residual)
+  if (track) {
+    if (K == 4) JQ_PLF(4, 8);
+    else JQ_PLF(32, 8);
+  } else {
+    if (K == 4) JQ_PLF(4, 1);
+    else JQ_PLF(32, 1);
+  }
+#undef JQ_PLF
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    jq_set_error("CUDA launch failed at %s:%d: %s", __FILE__, __LINE__, cudaGetErrorString(e));
+    *rc = JQ_ERR_CUDA;
+  }
+  return true;
+}
+#endif
 
 int jq_launch_pair_mean(const float* h2, float* g2, int W, JqSpins sp, int d2, int track, cudaStream_t st) {
   long long items = (long long)W * sp.n() * sp.nch() * d2;

@@ -96,9 +96,11 @@ int jq_fermi_backbone(const FermiDims& d, const jaqmc_ferminet_params* p, long l
   float* h = b.ha;
   float* hn = b.hb;
   int d2prev = d.fee, d1prev = d.f1;
+  bool g2_ready = false;   // the previous two-electron layer already produced this layer's spin-channel means
   for (int l = 0; l < d.L; ++l) {
     const int fg = d.nch * d2prev;
-    if ((rc = jq_launch_pair_mean(h2, b.g2, (int)W, d.sp, d2prev, track, st))) return rc;
+    if (!g2_ready && (rc = jq_launch_pair_mean(h2, b.g2, (int)W, d.sp, d2prev, track, st))) return rc;
+    g2_ready = false;
     JqDenseArgs a;
     memset(&a, 0, sizeof(a));
     a.N = d.d1[l];
@@ -151,6 +153,24 @@ int jq_fermi_backbone(const FermiDims& d, const jaqmc_ferminet_params* p, long l
       hn = t;
     }
     d1prev = d.d1[l];
+#ifndef JAQMC_HOST_EMU
+    if (l < d.L - 1) {
+      // layer + means of its output in one pass over the pair tensor; the last two-electron layer's output is only
+      // used through its means and is not written
+      const bool last2 = (l == d.L - 2);
+      int frc = JQ_OK;
+      if (jq_launch_pair_layer_fused(h2, d2prev, p->double_kernel[l], p->double_bias[l], last2 ? nullptr : h2n, b.g2,
+                                     (int)W, d.sp, d.d2[l], d2prev == d.d2[l], track, st, &frc)) {
+        if (frc) return frc;
+        float* t = h2;
+        h2 = h2n;
+        h2n = t;
+        d2prev = d.d2[l];
+        g2_ready = true;
+        continue;
+      }
+    }
+#endif
     if (l < d.L - 1) {
       JqDenseArgs a2;
       memset(&a2, 0, sizeof(a2));
