@@ -31,15 +31,42 @@ __device__ __forceinline__ void jq_divmod(int q, int d, float inv, int* quo, int
 // orb[w][j][c][d*n+i] *= envelope(j, i, d)   (in place, product rule).  One item per (w, j, d, i).
 // ------------------------------------------------------------------------------------------------
 __global__ void k_orb_envelope(float* __restrict__ orb, const float* __restrict__ el, const float* __restrict__ atoms,
-                               JqEnvelopeArgs env, long long items, JqSpins sp, int A, int D, int track) {
+                               JqEnvelopeArgs env, long long items, JqSpins sp, int A, int D, int track, int use_smem) {
   const int n = sp.n();
   const int DN = D * n;
   const int C = track ? 3 * n + 2 : 1;
+  // Optional staging of the envelope parameters [n_orb][A][D] in shared memory, transposed to [channel][atom][col]
+  // (col = d * n + i is the fastest index of consecutive items: the direct reads are A * D floats apart per lane).
+  JQ_DYN_SMEM(float, sm);
+  const int nch_p = (env.pi[1] != nullptr) ? 2 : 1;
+  if (use_smem) {
+    for (int q = threadIdx.x; q < nch_p * A * DN; q += blockDim.x) {
+      const int ch = q / (A * DN), r = q - ch * (A * DN);
+      const int I = r / DN, col = r - I * DN;
+      const int d = col / n, i = col - d * n;
+      float sv = env.sigma[ch][(i * A + I) * D + d];
+      if (env.type == 1) sv = fabsf(sv);
+      sm[q] = sv;
+      sm[nch_p * A * DN + q] = env.pi[ch][(i * A + I) * D + d];
+    }
+    __syncthreads();
+  }
+  const bool small = items < 0x7fffffffLL;   // 32-bit index arithmetic (the 64-bit divisions dominate the value-only pass)
   for (long long it = (long long)blockIdx.x * blockDim.x + threadIdx.x; it < items;
        it += (long long)gridDim.x * blockDim.x) {
-    int col = (int)(it % DN);
-    long long g = it / DN;  // (w, j)
-    int j = (int)(g % n);
+    int col;
+    long long g;  // (w, j)
+    int j;
+    if (small) {
+      const unsigned u = (unsigned)it, gq = u / (unsigned)DN;
+      col = (int)(u - gq * (unsigned)DN);
+      g = gq;
+      j = (int)(gq % (unsigned)n);
+    } else {
+      col = (int)(it % DN);
+      g = it / DN;
+      j = (int)(g % n);
+    }
     int d = col / n, i = col % n;
     int ch = (env.pi[1] != nullptr) ? sp.chan_of(j) : 0;
     const float* pi = env.pi[ch];
@@ -49,9 +76,16 @@ __global__ void k_orb_envelope(float* __restrict__ orb, const float* __restrict_
     for (int I = 0; I < A; ++I) {
       float dx = e[0] - atoms[I * 3], dy = e[1] - atoms[I * 3 + 1], dz = e[2] - atoms[I * 3 + 2];
       float r = sqrtf(dx * dx + dy * dy + dz * dz);
-      float s = sg[(i * A + I) * D + d];
-      if (env.type == 1) s = fabsf(s);
-      float t = pi[(i * A + I) * D + d] * expf(-s * r);
+      float s, pv;
+      if (use_smem) {
+        s = sm[(ch * A + I) * DN + col];
+        pv = sm[(nch_p + ch) * A * DN + I * DN + col];
+      } else {
+        s = sg[(i * A + I) * D + d];
+        if (env.type == 1) s = fabsf(s);
+        pv = pi[(i * A + I) * D + d];
+      }
+      float t = pv * expf(-s * r);
       ex += t;
       if (track) {
         float rinv = 1.0f / r;
@@ -80,15 +114,80 @@ __global__ void k_orb_envelope(float* __restrict__ orb, const float* __restrict_
   }
 }
 
+#ifndef JAQMC_HOST_EMU
+// Value-only envelope product (sampling path): a thread owns one column (determinant d, orbital i) with its pi / sigma
+// in registers and walks groups (walker, electron); no per-item index arithmetic.  Up to ENVV_A atoms.
+constexpr int ENVV_A = 8;
+constexpr int ENVV_GP = 32;   // groups per block
+__global__ void __launch_bounds__(256) k_orb_envelope_value(float* __restrict__ orb, const float* __restrict__ el,
+                                                           const float* __restrict__ atoms, JqEnvelopeArgs env,
+                                                           long long G, JqSpins sp, int A, int D) {
+  const int n = sp.n(), DN = D * n;
+  const long long g0 = (long long)blockIdx.x * ENVV_GP;
+  const long long g1 = (g0 + ENVV_GP < G) ? g0 + ENVV_GP : G;
+  const bool two = env.pi[1] != nullptr;
+  float ax[ENVV_A], ay[ENVV_A], az[ENVV_A];
+#pragma unroll
+  for (int I = 0; I < ENVV_A; ++I) {
+    ax[I] = (I < A) ? atoms[3 * I] : 0.f;
+    ay[I] = (I < A) ? atoms[3 * I + 1] : 0.f;
+    az[I] = (I < A) ? atoms[3 * I + 2] : 0.f;
+  }
+  for (int col = threadIdx.x; col < DN; col += blockDim.x) {
+    const int d = col / n, i = col - d * n;
+    float pv[2][ENVV_A], sv[2][ENVV_A];
+#pragma unroll
+    for (int ch = 0; ch < 2; ++ch)
+#pragma unroll
+      for (int I = 0; I < ENVV_A; ++I) {
+        const bool on = I < A && (ch == 0 || two);
+        float s = on ? env.sigma[ch][(i * A + I) * D + d] : 0.f;
+        if (env.type == 1) s = fabsf(s);
+        sv[ch][I] = s;
+        pv[ch][I] = on ? env.pi[ch][(i * A + I) * D + d] : 0.f;
+      }
+    int j = (int)(g0 % n);
+    for (long long g = g0; g < g1; ++g) {
+      const float ex = el[g * 3], ey = el[g * 3 + 1], ez = el[g * 3 + 2];
+      const bool c1 = two && sp.chan_of(j) == 1;
+      float e = 0.f;
+#pragma unroll
+      for (int I = 0; I < ENVV_A; ++I)
+        if (I < A) {
+          const float dx = ex - ax[I], dy = ey - ay[I], dz = ez - az[I];
+          const float r = sqrtf(dx * dx + dy * dy + dz * dz);
+          e += (c1 ? pv[1][I] : pv[0][I]) * expf(-(c1 ? sv[1][I] : sv[0][I]) * r);
+        }
+      orb[g * DN + col] *= e;
+      if (++j == n) j = 0;
+    }
+  }
+}
+#endif
+
 int jq_launch_orb_envelope(float* orb, const float* electrons, const float* atoms, const JqEnvelopeArgs& env,
                            int W, JqSpins sp, int A, int D, int track, cudaStream_t st) {
   if (env.type == 2) return JQ_OK;  // null envelope: ones
   long long items = (long long)W * sp.n() * D * sp.n();
   if (items <= 0) return JQ_OK;
+#ifndef JAQMC_HOST_EMU
+  if (!track && A <= ENVV_A) {
+    const long long G = (long long)W * sp.n();
+    jq_prof_work(0.0, 8.0 * (double)items);
+    JQ_LAUNCH(k_orb_envelope_value, dim3((unsigned)jq_cdiv(G, ENVV_GP)), dim3(256), 0, st, orb, electrons, atoms, env, G, sp,
+              A, D);
+    JQ_CHECK_LAUNCH();
+    return JQ_OK;
+  }
+#endif
   int grid = jq_cdiv(items, 256);
   if (grid > 148 * 32) grid = 148 * 32;
   jq_prof_work(0.0, 8.0 * (double)items * (track ? 3 * sp.n() + 2 : 1));
-  JQ_LAUNCH(k_orb_envelope, dim3(grid), dim3(256), 0, st, orb, electrons, atoms, env, items, sp, A, D, track);
+  const int nch_p = env.pi[1] ? 2 : 1;
+  const size_t smem = sizeof(float) * 2 * (size_t)nch_p * A * D * sp.n();
+  const int use_smem = smem <= 40 * 1024;
+  JQ_LAUNCH(k_orb_envelope, dim3(grid), dim3(256), use_smem ? smem : 0, st, orb, electrons, atoms, env, items, sp, A, D,
+            track, use_smem);
   JQ_CHECK_LAUNCH();
   return JQ_OK;
 }
@@ -406,7 +505,7 @@ __global__ void __launch_bounds__(256, 3) k_logdet(const float* __restrict__ orb
 // |a[r][p]| among the rows not used yet (warp max + ballot), its row is broadcast by shuffles and eliminated from the
 // remaining rows -- the same pivots and the same fmaf sequence as the row-swapping elimination of k_logdet (and of
 // LAPACK getrf behind jnp.linalg.slogdet, wavefunction/output/logdet.py:65), so the two kernels agree on sign and
-// log|det|.  sign = parity(step -> row permutation) * prod sign(pivot); log|det| = sum log|pivot| in double.
+// log|det|.  sign = parity(step -> row permutation) * prod sign(pivot); log|det| = log prod |pivot| in double.
 // ------------------------------------------------------------------------------------------------
 template <int NMAX>
 __global__ void __launch_bounds__(256) k_logdet_value_warp(const float* __restrict__ orb, int n, int D, long long M,
@@ -427,7 +526,9 @@ __global__ void __launch_bounds__(256) k_logdet_value_warp(const float* __restri
   }
   int step_of = 0;
   float sgn = 1.0f;
-  double logabs = 0.0;
+  // |det| = prod |pivot| kept as (mantissa product in double, binary exponent sum): one double log per matrix
+  double mant = 1.0;
+  int expo = 0;
 #pragma unroll
   for (int p = 0; p < NMAX; ++p) {
     if (p < n) {
@@ -438,7 +539,11 @@ __global__ void __launch_bounds__(256) k_logdet_value_warp(const float* __restri
       const float pv = __shfl_sync(full, a[p], pl);
       if (pv < 0.f) sgn = -sgn;
       if (pv == 0.f) sgn = 0.f;
-      logabs += log((double)fabsf(pv));
+      {
+        int e;
+        mant *= (double)frexpf(fabsf(pv), &e);   // zero pivot: mantissa 0 -> log 0 = -inf, like slogdet
+        expo += e;
+      }
       const float pinv = 1.0f / pv;
       if (lane == pl) {
         used = true;
@@ -462,7 +567,7 @@ __global__ void __launch_bounds__(256) k_logdet_value_warp(const float* __restri
   const int total = __reduce_add_sync(full, inv_count);
   if (lane == 0) {
     det_sign[m] = (total & 1) ? -sgn : sgn;
-    det_logabs[m] = (float)logabs;
+    det_logabs[m] = (float)(log(mant) + (double)expo * 0.69314718055994530942);
   }
 }
 #endif
