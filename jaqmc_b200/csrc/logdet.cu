@@ -146,20 +146,32 @@ __global__ void __launch_bounds__(256) k_orb_envelope_value(float* __restrict__ 
         sv[ch][I] = s;
         pv[ch][I] = on ? env.pi[ch][(i * A + I) * D + d] : 0.f;
       }
-    int j = (int)(g0 % n);
-    for (long long g = g0; g < g1; ++g) {
-      const float ex = el[g * 3], ey = el[g * 3 + 1], ez = el[g * 3 + 2];
-      const bool c1 = two && sp.chan_of(j) == 1;
-      float e = 0.f;
+    // groups in batches of 8: their orbital values and electron positions are requested together
+    for (long long gb = g0; gb < g1; gb += 8) {
+      float ov[8], px[8], py[8], pz[8];
 #pragma unroll
-      for (int I = 0; I < ENVV_A; ++I)
-        if (I < A) {
-          const float dx = ex - ax[I], dy = ey - ay[I], dz = ez - az[I];
-          const float r = sqrtf(dx * dx + dy * dy + dz * dz);
-          e += (c1 ? pv[1][I] : pv[0][I]) * expf(-(c1 ? sv[1][I] : sv[0][I]) * r);
-        }
-      orb[g * DN + col] *= e;
-      if (++j == n) j = 0;
+      for (int u = 0; u < 8; ++u) {
+        const long long g = (gb + u < g1) ? gb + u : g1 - 1;
+        ov[u] = orb[g * DN + col];
+        px[u] = el[g * 3];
+        py[u] = el[g * 3 + 1];
+        pz[u] = el[g * 3 + 2];
+      }
+      int j = (int)(gb % n);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const bool c1 = two && sp.chan_of(j) == 1;
+        float e = 0.f;
+#pragma unroll
+        for (int I = 0; I < ENVV_A; ++I)
+          if (I < A) {
+            const float dx = px[u] - ax[I], dy = py[u] - ay[I], dz = pz[u] - az[I];
+            const float r = sqrtf(dx * dx + dy * dy + dz * dz);
+            e += (c1 ? pv[1][I] : pv[0][I]) * expf(-(c1 ? sv[1][I] : sv[0][I]) * r);
+          }
+        if (gb + u < g1) orb[(gb + u) * DN + col] = ov[u] * e;
+        if (++j == n) j = 0;
+      }
     }
   }
 }
