@@ -260,6 +260,95 @@ __global__ void __launch_bounds__(256, 3) k_logdet(const float* __restrict__ orb
     trL[d] = 0.f;
   }
   __syncthreads();
+  bool fast_inv = false;
+#ifndef JAQMC_HOST_EMU
+  if (need_inv && n <= LD_NP && nt == 256) {
+    // ---- n <= 16: Gauss-Jordan inversion in registers, one matrix per HALF-warp (lane r = row r of [A | I]); rows are
+    // never moved: at step p the pivot is the largest |a[r][p]| among the rows not used yet, its row is scaled and
+    // eliminated from all others (same pivots and fmaf sequence as the shared-memory elimination below).  Afterwards
+    // row p of A^-1 is the right half of the row that served as pivot p; it goes straight into the row-padded layout
+    // of the trace phase.  sign = parity(row -> step) * prod sign(pivot), log|det| = log prod |pivot| in double.
+    fast_inv = true;
+    const unsigned full = 0xffffffffu;
+    const int hl = tid & 15, half = (tid >> 4) & 1, warp = tid >> 5;
+    const int IS = n * LD_NP + 4;
+    float* invp_w = Jc;
+    for (int dbase = 2 * warp; dbase < db; dbase += 16) {
+      const int d = dbase + half;
+      const bool on = d < db;
+      bool used = !on || hl >= n;
+      float a[LD_NP], bi[LD_NP];
+#pragma unroll
+      for (int c = 0; c < LD_NP; ++c) {
+        a[c] = (!used && c < n) ? inv[d * nn + hl * n + c] : 0.f;
+        bi[c] = (c == hl) ? 1.0f : 0.f;
+      }
+      int step_of = 0;
+      float sg = 1.0f;
+      double mant = 1.0;
+      int expo = 0;
+#pragma unroll
+      for (int p = 0; p < LD_NP; ++p) {
+        if (p < n) {
+          unsigned key = used ? 0u : __float_as_uint(fabsf(a[p]));
+          unsigned mx = key;
+#pragma unroll
+          for (int o = 8; o > 0; o >>= 1) mx = max(mx, __shfl_xor_sync(full, mx, o));
+          const unsigned cand = (__ballot_sync(full, !used && key == mx) >> (16 * half)) & 0xffffu;
+          const int pl = cand ? __ffs(cand) - 1 : 0;   // first unused row holding the largest magnitude
+          const float pv = __shfl_sync(full, a[p], pl, 16);
+          if (pv < 0.f) sg = -sg;
+          if (pv == 0.f) sg = 0.f;
+          {
+            int e;
+            mant *= (double)frexpf(fabsf(pv), &e);
+            expo += e;
+          }
+          const float pinv = 1.0f / pv;
+          const bool is_p = (hl == pl);
+          if (is_p && !used) {
+            used = true;
+            step_of = p;
+          }
+          const float f = is_p ? 0.f : a[p];   // column p before it is overwritten
+#pragma unroll
+          for (int c = 0; c < LD_NP; ++c)
+            if (c < n) {
+              // pivot row, scaled (its entry in column p becomes 1)
+              const float ap = __shfl_sync(full, a[c], pl, 16) * pinv;
+              const float bp = __shfl_sync(full, bi[c], pl, 16) * pinv;
+              if (is_p) {
+                a[c] = ap;
+                bi[c] = bp;
+              } else {
+                a[c] = fmaf(-f, ap, a[c]);
+                bi[c] = fmaf(-f, bp, bi[c]);
+              }
+            }
+        }
+      }
+      // permutation parity: inversions of row -> step, counted per lane and summed over the half-warp
+      int invc = 0;
+      for (int i = 0; i < n; ++i) {
+        const int si = __shfl_sync(full, step_of, i, 16);
+        if (i < hl && hl < n && si > step_of) ++invc;
+      }
+#pragma unroll
+      for (int o = 8; o > 0; o >>= 1) invc += __shfl_xor_sync(full, invc, o);
+      if (on && hl < n) {
+        float* dst = invp_w + (size_t)d * IS + step_of * LD_NP;
+#pragma unroll
+        for (int c = 0; c < LD_NP; ++c) dst[c] = (c < n) ? bi[c] : 0.f;
+      }
+      if (on && hl == 0) {
+        det_sign[w * D + d0 + d] = (invc & 1) ? -sg : sg;
+        det_logabs[w * D + d0 + d] = (float)(log(mant) + (double)expo * 0.69314718055994530942);
+      }
+    }
+    __syncthreads();
+  }
+#endif
+  if (!fast_inv) {
   for (int p = 0; p < n; ++p) {
     for (int d = tid; d < db; d += nt) {
       const float* a = inv + d * nn;
@@ -350,6 +439,7 @@ __global__ void __launch_bounds__(256, 3) k_logdet(const float* __restrict__ orb
     }
     __syncthreads();
   }
+  }  // !fast_inv
   if (n <= LD_NP) {
     // ---- small matrices (n <= 16): one item per (determinant, column i2) and derivative slab.  The item holds
     // column i2 of dA_c in registers and forms column i2 of M = A^-1 dA_c with the inverse read as float4 broadcasts
@@ -362,12 +452,14 @@ __global__ void __launch_bounds__(256, 3) k_logdet(const float* __restrict__ orb
     float* Ms = invp + (size_t)DB * IS;     // [DB][MS]
     p1 = Ms + (size_t)DB * MS;
     p2 = p1 + DB * n;
-    for (int q = tid; q < db * n * LD_NP; q += nt) {
-      int d = q / (n * LD_NP), r = q % (n * LD_NP);
-      int i = r / LD_NP, j = r % LD_NP;
-      invp[d * IS + r] = (j < n) ? inv[d * nn + i * n + j] : 0.f;
+    if (!fast_inv) {
+      for (int q = tid; q < db * n * LD_NP; q += nt) {
+        int d = q / (n * LD_NP), r = q % (n * LD_NP);
+        int i = r / LD_NP, j = r % LD_NP;
+        invp[d * IS + r] = (j < n) ? inv[d * nn + i * n + j] : 0.f;
+      }
+      __syncthreads();
     }
-    __syncthreads();
     // When every item has its own thread (db * n <= blockDim, the common case) the next slab's column is fetched
     // into registers before the current one is consumed, so the global-load latency overlaps the products.
     const bool one_item = (db * n <= nt);
