@@ -783,10 +783,100 @@ __global__ void k_logdet_combine(const float* __restrict__ det_sign, const float
   }
 }
 
+#ifndef JAQMC_HOST_EMU
+// Same combination with one WARP per walker (k_logdet_combine gives a walker to one thread: 16 x 42 serial loads, which
+// is the whole cost of the kernel once a GPU holds only a few hundred walkers).  Lane d holds determinant d's weight;
+// the gradient components are spread over the lanes.  D <= 32.
+__global__ void __launch_bounds__(256) k_logdet_combine_warp(const float* __restrict__ det_sign,
+                                                            const float* __restrict__ det_logabs,
+                                                            const float* __restrict__ det_grad,
+                                                            const float* __restrict__ det_lap, int W, int n, int D, int track,
+                                                            const float* __restrict__ extra, float* __restrict__ logpsi,
+                                                            float* __restrict__ sign, float* __restrict__ grad,
+                                                            float* __restrict__ lap, float* __restrict__ e_kin) {
+  const unsigned full = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  const int K = 3 * n, C = K + 2;
+  for (long long w = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); w < W;
+       w += (long long)gridDim.x * (blockDim.x >> 5)) {
+    const bool on = lane < D;
+    const float sd = on ? det_sign[w * D + lane] : 0.f;
+    const float ld = on ? det_logabs[w * D + lane] : -INFINITY;
+    float lmax = ld;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) lmax = fmaxf(lmax, __shfl_xor_sync(full, lmax, o));
+    // the sums over determinants run in determinant order on every lane (same order as the scalar kernel)
+    const float term = on ? sd * expf(ld - lmax) : 0.f;
+    float S = 0.f;
+    for (int d = 0; d < D; ++d) S += __shfl_sync(full, term, d);
+    const float sg = (S > 0.f) ? 1.f : ((S < 0.f) ? -1.f : 0.f);
+    float lp = logf(fabsf(S)) + lmax;
+    const float* ex = extra ? extra + w * (track ? C : 1) : nullptr;
+    if (ex) lp += ex[0];
+    if (lane == 0) {
+      logpsi[w] = lp;
+      sign[w] = sg;
+    }
+    if (!track) continue;
+    const float* g = det_grad + w * D * K;
+    const float wd = term * (1.0f / S);   // lane d: weight of determinant d
+    // per-determinant |grad|^2, lane d keeps determinant d's
+    float g2_mine = 0.f;
+    for (int d = 0; d < D; ++d) {
+      float part = 0.f;
+      for (int k = lane; k < K; k += 32) {
+        const float v = g[d * K + k];
+        part = fmaf(v, v, part);
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(full, part, o);
+      if (lane == d) g2_mine = part;
+    }
+    float acc_term = on ? wd * (det_lap[w * D + lane] + g2_mine) : 0.f;
+    float acc_l = 0.f;
+    for (int d = 0; d < D; ++d) acc_l += __shfl_sync(full, acc_term, d);
+    float gg_det = 0.f, gg = 0.f;
+    for (int k0 = 0; k0 < K; k0 += 32) {
+      const int k = k0 + lane;
+      float gk = 0.f;
+      for (int d = 0; d < D; ++d) {
+        const float wdd = __shfl_sync(full, wd, d);
+        if (k < K) gk = fmaf(wdd, g[d * K + k], gk);
+      }
+      if (k < K) {
+        gg_det = fmaf(gk, gk, gg_det);
+        if (ex) gk += ex[1 + k];
+        grad[w * K + k] = gk;
+        gg = fmaf(gk, gk, gg);
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      gg_det += __shfl_xor_sync(full, gg_det, o);
+      gg += __shfl_xor_sync(full, gg, o);
+    }
+    if (lane == 0) {
+      float lp_l = acc_l - gg_det;
+      if (ex) lp_l += ex[C - 1];
+      lap[w] = lp_l;
+      e_kin[w] = -0.5f * (lp_l + gg);
+    }
+  }
+}
+#endif
+
 int jq_launch_logdet_combine(const float* det_sign, const float* det_logabs, const float* det_grad,
                              const float* det_lap, int W, int n, int D, int track, const float* extra_logpsi,
                              float* logpsi, float* sign, float* grad, float* lap, float* e_kin, cudaStream_t st) {
   if (W <= 0) return JQ_OK;
+#ifndef JAQMC_HOST_EMU
+  if (D <= 32) {
+    JQ_LAUNCH(k_logdet_combine_warp, dim3(jq_cdiv(W, 8)), dim3(256), 0, st, det_sign, det_logabs, det_grad, det_lap, W, n,
+              D, track, extra_logpsi, logpsi, sign, grad, lap, e_kin);
+    JQ_CHECK_LAUNCH();
+    return JQ_OK;
+  }
+#endif
   JQ_LAUNCH(k_logdet_combine, dim3(jq_cdiv(W, 64)), dim3(64), 0, st, det_sign, det_logabs, det_grad, det_lap, W, n, D,
             track, extra_logpsi, logpsi, sign, grad, lap, e_kin);
   JQ_CHECK_LAUNCH();
