@@ -75,6 +75,7 @@ struct TcParams {
   // walker-batched tiles (pair kernel, launches over a sub-range of a walker's groups, e.g. one spin channel): when a
   // half-tile holds wb >= 2 whole walkers' sub-groups the TMA box spans wb walkers and G_h = wb * n_sub
   int wb, Wn, stage_tx;
+  int lag;   // chunks between the raw products and the lo product in the MMA issue order
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -1037,15 +1038,17 @@ k_dense_tc_pair(const __grid_constant__ CUtensorMap mapX0, const __grid_constant
       const uint64_t stage_step = (uint64_t)(p.stage_bytes >> 4);
       const int n_items = (t_limit - t_first + t_stride - 1) / t_stride;
       const int total = n_items * kchunks;
-      // head: raw products of chunk c; tail: lo product of chunk c - TCP_LAG
+      // head: raw products of chunk c; tail: lo product of chunk c - lag.  The head of item i+1 waits for the accumulator
+      // that the tail of item i-1's last chunk completes, so the lag must not exceed kchunks + 1 (single-chunk layers).
+      const int lag = (p.lag < kchunks + 1) ? p.lag : kchunks + 1;
       PipeState hs, ts;
       int h_kc = 0, t_kc = 0;
       uint32_t h_it = 0, t_it = 0;
       mbar_wait(wfull, 0);
       tc_fence_after();
-      for (int c = 0; c < total + TCP_LAG; ++c) {
+      for (int c = 0; c < total + lag; ++c) {
         // the lo product first: the raw products of a new item may wait for an accumulator that this one completes
-        if (c >= TCP_LAG) {
+        if (c >= lag) {
           const uint32_t buf = t_it & 1;
           const uint32_t d_cross = tmem_base + buf * 2 * TC_NMAX + TC_NMAX;
           const uint64_t wh = dw0 + w_chunk * (uint64_t)t_kc;
@@ -1269,6 +1272,10 @@ static bool pair_plan(const JqDenseArgs& a, int sm_count, TcParams* p, int* smem
   p->G_t = 2 * G_h;
   p->Hp = Hp;
   p->wb = wb;
+  {
+    static const int lag_env = getenv("JAQMC_B200_TC_LAG") ? atoi(getenv("JAQMC_B200_TC_LAG")) : 0;   // tuning switch
+    p->lag = (lag_env >= 1 && lag_env + 2 <= stages) ? lag_env : TCP_LAG;   // measured r1s: 2 and 3 within noise, 1 slower
+  }
   p->stage_tx = (wb > 1 ? wb * a.n_sub * a.C : Hp) * 128;
   p->stages = stages;
   p->stage_bytes = stage_bytes;
