@@ -357,7 +357,7 @@ def run_ours(args):
     data = MoleculeData(electrons=el_host.to(dev), atoms=atoms, charges=charges)
     params = wf.init_params(data, 42)
     # equilibrate a little so that no walker sits at a pathological random position
-    plan = SamplePlan(wf, MCMCSampler(steps=10))
+    plan = SamplePlan(wf, MCMCSampler(steps=10), graph=not args.no_graph)
     st = plan.init(data)
     gen = torch.Generator(device=dev).manual_seed(1234 + rank)
     for _ in range(0 if args.no_equilibrate else 2):
@@ -441,11 +441,17 @@ def run_ours(args):
     # second half of the BASELINE metric: sampling + energy part of one VMC iteration (workflow/stage/vmc.py:227-265):
     # 10 MH sub-steps (11 value-only forward passes) followed by one local-energy evaluation; gradients and the
     # optimizer stay in the reference's JAX code and are not part of this number
+    vmc_data = data   # the walkers of the sampling chain; `data.electrons` stays the captured graph input
+
     def vmc_iteration():
-        nonlocal data, st
-        data, _, st = plan.step(params, data, st, gen)
+        nonlocal vmc_data, st
+        vmc_data, _, st = plan.step(params, vmc_data, st, gen)
         sums.zero_()
-        wf.local_energy(params, data, sums=sums)
+        if use_graph:
+            data.electrons.copy_(vmc_data.electrons)
+            replay()
+        else:
+            wf.local_energy(params, vmc_data, sums=sums)
         if dist:
             torch.distributed.all_reduce(sums)
 

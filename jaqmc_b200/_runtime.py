@@ -171,6 +171,36 @@ class Runtime:
         _abi.check(self.lib, rc)
         return n_accept, accepted
 
+    def capture_mh_step(self, wf, system, electrons, normals, uniforms, stddev):
+        """CUDA-graph version of :meth:`mh_step` for fixed shapes (the ~350 launches of ten sub-steps replayed with one
+        launch: at a few hundred walkers per GPU the sampling pass is launch-bound).  ``replay()`` runs the sub-steps on
+        the CURRENT contents of ``electrons`` / ``normals`` / ``uniforms`` / ``stddev`` (same tensors) in place and
+        returns ``n_accept`` (1,)."""
+        W = electrons.shape[0]
+        logpsi = torch.empty(W, dtype=torch.float32, device=self.device)
+        keep0 = electrons.clone()
+        self.mh_step(wf, system, electrons, logpsi, normals, uniforms, stddev, logpsi_valid=False)  # warm-up
+        electrons.copy_(keep0)
+        torch.cuda.synchronize(self.device)
+        n_accept = torch.zeros(1, dtype=torch.float32, device=self.device)
+        ws = self._ws_for(wf, W, False)
+        S = normals.shape[0]
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            n_accept.zero_()
+            rc = self.lib.jaqmc_b200_mh_step(
+                C.byref(wf.struct), C.byref(system.struct), _ptr(electrons), _ptr(logpsi), 0, _ptr(normals),
+                _ptr(uniforms), _ptr(stddev), S, W, _ptr(n_accept), None, _ptr(ws), ws.numel(), self._stream())
+            _abi.check(self.lib, rc)
+        keep = (wf, system, electrons, normals, uniforms, stddev, logpsi, ws)
+
+        def replay():
+            graph.replay()
+            return n_accept
+
+        replay._keep = keep
+        return replay
+
     def launch_count(self) -> int:
         return int(self.lib.jaqmc_b200_launch_count())
 

@@ -65,8 +65,11 @@ class MCMCSampler:
             counter=0,
         )
 
-    def step(self, batch_log_prob, data: MoleculeData, state: MCMCState, rngs, record_accepts: bool = False):
-        """``(data, {"pmove": ...}, new_state)`` after ``steps`` all-electron MH updates (sampler/mcmc.py:139-197)."""
+    def step(self, batch_log_prob, data: MoleculeData, state: MCMCState, rngs, record_accepts: bool = False,
+             graph_cache: dict | None = None):
+        """``(data, {"pmove": ...}, new_state)`` after ``steps`` all-electron MH updates (sampler/mcmc.py:139-197).
+        ``graph_cache`` (a dict owned by the caller, see ``SamplePlan(graph=True)``) replays the sub-steps as one CUDA
+        graph on static buffers; results are identical to the launch-by-launch path."""
         if self.steps == 0:
             return data, {"pmove": torch.zeros((), device=data.electrons.device)}, state
         x = data.electrons.contiguous().clone()
@@ -74,7 +77,25 @@ class MCMCSampler:
         dev = x.device
         normals, uniforms = _noise(rngs, self.steps, tuple(x.shape), dev)
         rt = runtime(dev)
-        if isinstance(batch_log_prob, BatchLogProb):
+        if graph_cache is not None and isinstance(batch_log_prob, BatchLogProb) and not record_accepts and dev.type == "cuda":
+            blp = batch_log_prob
+            key = (id(blp.wf), tuple(x.shape), self.steps)
+            ent = graph_cache.get(key)
+            if ent is None:
+                wf = blp.wf._handle(blp.params, blp.data.atoms.shape[0])
+                sysh = _marshal.system_handle(blp.data.atoms, None)
+                bufs = dict(x=x.clone(), normals=normals.clone(), uniforms=uniforms.clone(), stddev=state.stddev.clone())
+                replay = rt.capture_mh_step(wf, sysh, bufs["x"], bufs["normals"], bufs["uniforms"], bufs["stddev"])
+                ent = graph_cache[key] = (replay, bufs, blp.params)
+            replay, bufs, _ = ent
+            bufs["x"].copy_(x)
+            bufs["normals"].copy_(normals)
+            bufs["uniforms"].copy_(uniforms)
+            bufs["stddev"].copy_(state.stddev)
+            n_acc = replay().clone()
+            x = bufs["x"].clone()
+            accepted = None
+        elif isinstance(batch_log_prob, BatchLogProb):
             blp = batch_log_prob
             wf = blp.wf._handle(blp.params, blp.data.atoms.shape[0])
             sysh = _marshal.system_handle(blp.data.atoms, None)
@@ -123,11 +144,12 @@ class MCMCSampler:
 class SamplePlan:
     """``SamplePlan`` for the single batched field ``electrons`` (sampler/base.py:123-181)."""
 
-    def __init__(self, wf, sampler: MCMCSampler):
+    def __init__(self, wf, sampler: MCMCSampler, graph: bool = False):
         self.wf, self.sampler = wf, sampler
+        self._graphs = {} if graph else None   # CUDA-graph replay of the MH sub-steps (parameters must stay in place)
 
     def init(self, data: MoleculeData, rngs=None) -> MCMCState:
         return self.sampler.init(data, rngs)
 
     def step(self, params, data: MoleculeData, state: MCMCState, rngs):
-        return self.sampler.step(BatchLogProb(self.wf, params, data), data, state, rngs)
+        return self.sampler.step(BatchLogProb(self.wf, params, data), data, state, rngs, graph_cache=self._graphs)

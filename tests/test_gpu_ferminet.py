@@ -231,3 +231,32 @@ def test_cuda_graph_replay_matches_direct_launches():
         ref = wf.local_energy(params, data)
         for k in ref:
             assert torch.equal(got[k], ref[k]), k
+
+
+def test_mh_graph_replay_matches_direct_launches():
+    """The MH sub-steps replayed as one CUDA graph (SamplePlan(graph=True)) move the walkers exactly as the
+    launch-by-launch path does, including after the proposal width has been adapted."""
+    from jaqmc_b200.data import MoleculeData
+    from jaqmc_b200.sampler import MCMCSampler, SamplePlan
+    from jaqmc_b200.wavefunction import FermiNetWavefunction
+
+    dev = torch.device("cuda", 0)
+    atoms, charges, nspins = H.molecule("N2")
+    wf = FermiNetWavefunction(nspins=nspins, ndets=4, hidden_dims_single=[64, 64], hidden_dims_double=[32, 32])
+    el = H.synthetic_walkers(atoms, charges, nspins, 128, seed=3).float().to(dev)
+    params = wf.init_params(MoleculeData(el, atoms.float().to(dev), charges.float().to(dev)), 7)
+    sampler = MCMCSampler(steps=4, adapt_frequency=2)
+    plans = [SamplePlan(wf, sampler), SamplePlan(wf, sampler, graph=True)]
+    datas = [MoleculeData(el.clone(), atoms.float().to(dev), charges.float().to(dev)) for _ in plans]
+    states = [p.init(d) for p, d in zip(plans, datas)]
+    g = torch.Generator(device=dev).manual_seed(11)
+    for it in range(5):
+        normals = torch.randn(4, *el.shape, generator=g, device=dev)
+        uniforms = torch.rand(4, el.shape[0], generator=g, device=dev).clamp_min_(1e-30)
+        outs = []
+        for k, plan in enumerate(plans):
+            datas[k], stats, states[k] = plan.step(params, datas[k], states[k], (normals, uniforms))
+            outs.append(stats["pmove"])
+        assert torch.equal(datas[0].electrons, datas[1].electrons), it
+        assert torch.equal(outs[0], outs[1]) and torch.equal(states[0].stddev, states[1].stddev), it
+    assert 0.0 < float(outs[0]) < 1.0
