@@ -75,6 +75,7 @@ struct TcParams {
   // walker-batched tiles (pair kernel, launches over a sub-range of a walker's groups, e.g. one spin channel): when a
   // half-tile holds wb >= 2 whole walkers' sub-groups the TMA box spans wb walkers and G_h = wb * n_sub
   int wb, Wn, stage_tx;
+  int burst; // activation chunks requested back to back by the TMA producer (tuning switch)
   int lag;   // chunks between the raw products and the lo product in the MMA issue order
 };
 
@@ -1015,16 +1016,24 @@ k_dense_tc_pair(const __grid_constant__ CUtensorMap mapX0, const __grid_constant
           w = (int)((uint32_t)t / (uint32_t)p.tiles_per_w);
           row0 = (p.j0 + (t - w * (int)p.tiles_per_w) * p.G_t + (int)rank * p.G_h) * p.C;
         }
-        for (int kc = 0; kc < kchunks; ++kc) {
-          mbar_wait(&empty[ps.stage], ps.phase ^ 1);
-          unsigned char* st = xring + ps.stage * p.stage_bytes;
-          if (rank == 0) mbar_expect_tx(&full[ps.stage], 2u * stage_tx);
-          const uint32_t fb = full_l0 + 8u * (uint32_t)ps.stage;
-          if (kc < p.kchunks0)
-            tma_load_3d_pair(st, &mapX0, fb, kc * TC_BK, row0, w);
-          else
-            tma_load_3d_pair(st, &mapX1, fb, (kc - p.kchunks0) * TC_BK, row0, w);
-          ps.advance(S);
+        // chunks are requested two at a time: the two 128-byte pieces of a row are adjacent in memory
+        for (int kc = 0; kc < kchunks; kc += p.burst) {
+          PipeState pw = ps;
+          for (int u = 0; u < p.burst && kc + u < kchunks; ++u) {
+            mbar_wait(&empty[pw.stage], pw.phase ^ 1);
+            pw.advance(S);
+          }
+          for (int u = 0; u < p.burst && kc + u < kchunks; ++u) {
+            const int kk = kc + u;
+            unsigned char* st = xring + ps.stage * p.stage_bytes;
+            if (rank == 0) mbar_expect_tx(&full[ps.stage], 2u * stage_tx);
+            const uint32_t fb = full_l0 + 8u * (uint32_t)ps.stage;
+            if (kk < p.kchunks0)
+              tma_load_3d_pair(st, &mapX0, fb, kk * TC_BK, row0, w);
+            else
+              tma_load_3d_pair(st, &mapX1, fb, (kk - p.kchunks0) * TC_BK, row0, w);
+            ps.advance(S);
+          }
         }
       }
     }
@@ -1274,6 +1283,8 @@ static bool pair_plan(const JqDenseArgs& a, int sm_count, TcParams* p, int* smem
   p->wb = wb;
   {
     static const int lag_env = getenv("JAQMC_B200_TC_LAG") ? atoi(getenv("JAQMC_B200_TC_LAG")) : 0;   // tuning switch
+    static const int burst_env = getenv("JAQMC_B200_TC_BURST") ? atoi(getenv("JAQMC_B200_TC_BURST")) : 0;
+    p->burst = (burst_env >= 1 && burst_env <= 4) ? burst_env : 1;
     p->lag = (lag_env >= 1 && lag_env + 2 <= stages) ? lag_env : TCP_LAG;   // measured r1s: 2 and 3 within noise, 1 slower
   }
   p->stage_tx = (wb > 1 ? wb * a.n_sub * a.C : Hp) * 128;
