@@ -550,6 +550,12 @@ __device__ __forceinline__ void attn_async_commit() { asm volatile("cp.async.com
 template <int N>
 __device__ __forceinline__ void attn_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
+// QKL: q and k are Local1 operands (LapNet: queries / keys come from the one-electron stream, so component (e, a) of
+// their Jacobian is non-zero for electron e only).  Then aJ has one non-zero row and one non-zero column, and
+//   sum_j wJ_ij v_j = -abar_i o_i + w_ie aJ_ie v_e   for i != e   (o = w v, the value output),
+// likewise with vJ for the Laplacian term: of the three n^2 d products per component only  w vJ  remains
+// (the reference's hand rule exploits the same structure, backbone/lapnet/_attention.py:113-196).
+template <bool QKL>
 __global__ void __launch_bounds__(AW_WARPS * 32, 1)
 k_attention_fl_warp(JqAttnOperand q, JqAttnOperand k, JqAttnOperand v, float* __restrict__ out, int ldo, int n, int H) {
   constexpr int dh = 64;
@@ -559,9 +565,9 @@ k_attention_fl_warp(JqAttnOperand q, JqAttnOperand k, JqAttnOperand v, float* __
   float* k0 = q0 + nt;
   float* v0 = k0 + nt;
   float* wgt = v0 + nt;            // [n][16]
-  float* red = wgt + nn;           // block-level reduction targets: aL t1 [n][16] | t2 abL [16] | oL [n][64]
-  const int red_floats = 2 * nn + 32 + n * dh;
-  const int per_warp = 6 * nt + 3 * nn + 32;   // two staging sets {qJ kJ vJ} | aJ aL t1 | t2 pad
+  float* red = wgt + nn;           // block-level: aL t1 [n][16] | t2 abL [16] | oL [n][64] | o0 [n][64] (value output)
+  const int red_floats = 2 * nn + 32 + 2 * n * dh;
+  const int per_warp = 6 * nt + 3 * nn + 48;   // two staging sets {qJ kJ vJ} | aJ aL t1 | t2 [16] abar [16] col [16]
   float* wbase = red + red_floats;
   const long long w = blockIdx.x / H;
   const int h = blockIdx.x % H;
@@ -572,7 +578,9 @@ k_attention_fl_warp(JqAttnOperand q, JqAttnOperand k, JqAttnOperand v, float* __
   float* aJ = stage + 6 * nt;
   float* aLp = aJ + nn;
   float* t1p = aLp + nn;
-  float* t2p = t1p + nn;
+  float* t2p = t1p + nn;           // [16]
+  float* abar_w = t2p + 16;        // QKL: abar [16] | column el of aJ [16] of the current component
+  float* o0s = red + 2 * nn + 32 + n * dh;
 
   // ---- value row: operands, logits, softmax, o = w v ----
   for (int x = tid; x < n * 16; x += blockDim.x) {
@@ -585,10 +593,17 @@ k_attention_fl_warp(JqAttnOperand q, JqAttnOperand k, JqAttnOperand v, float* __
   // first component of this warp: staged while the block computes the softmax
   auto stage_comp = [&](int kk, int buf) {
     float* qJ = stage + buf * 3 * nt;
+    if (QKL) {   // only row kk / 3 of qJ and kJ is non-zero, and phase A reads nothing else
+      const int e = kk / 3;
+      if (lane < 16) attn_stage4(qJ + e * AW_LD + lane * 4, q, w, n, e, 1 + kk, q.off + h * dh + lane * 4, Cd);
+      else attn_stage4(qJ + nt + e * AW_LD + (lane - 16) * 4, k, w, n, e, 1 + kk, k.off + h * dh + (lane - 16) * 4, Cd);
+    }
     for (int x = lane; x < n * 16; x += 32) {
       const int i = x >> 4, d4 = (x & 15) * 4;
-      attn_stage4(qJ + i * AW_LD + d4, q, w, n, i, 1 + kk, q.off + h * dh + d4, Cd);
-      attn_stage4(qJ + nt + i * AW_LD + d4, k, w, n, i, 1 + kk, k.off + h * dh + d4, Cd);
+      if (!QKL) {
+        attn_stage4(qJ + i * AW_LD + d4, q, w, n, i, 1 + kk, q.off + h * dh + d4, Cd);
+        attn_stage4(qJ + nt + i * AW_LD + d4, k, w, n, i, 1 + kk, k.off + h * dh + d4, Cd);
+      }
       attn_stage4(qJ + 2 * nt + i * AW_LD + d4, v, w, n, i, 1 + kk, v.off + h * dh + d4, Cd);
     }
     attn_async_commit();
@@ -622,7 +637,9 @@ k_attention_fl_warp(JqAttnOperand q, JqAttnOperand k, JqAttnOperand v, float* __
     float acc = 0.f;
     for (int j = 0; j < n; ++j) acc = fmaf(wgt[i * AW_NS + j], v0[j * AW_LD + d], acc);
     out[((w * n + i) * (long long)Cd) * ldo + h * dh + d] = acc;
+    o0s[x] = acc;
   }
+  if (QKL) __syncthreads();   // o0 is read by every warp below
 
   // ---- Jacobian components: one per warp at a time, operands of the next one in flight (cp.async) ----
   const int ti = (lane >> 2) * 2, tj = (lane & 3) * 4;          // phase A tile: rows ti, ti+1; columns tj .. tj+3
@@ -647,8 +664,36 @@ k_attention_fl_warp(JqAttnOperand q, JqAttnOperand k, JqAttnOperand v, float* __
     const float* qJ = stage + buf * 3 * nt;
     const float* kJ = qJ + nt;
     const float* vJ = kJ + nt;
+    const int el = kk / 3;   // electron of this component (QKL: the only non-zero row of qJ / kJ)
+    float col_e = 0.f;       // QKL: aJ[lane][el] before phase B overwrites aJ with wJ
     // phase A
-    if (tile_on) {
+    if (QKL) {
+      // row el: aJ[el][j] = qJ_el . k_j / sqrt(d);  column el: aJ[i][el] = q_i . kJ_el / sqrt(d);  both at [el][el]
+      for (int x = lane; x < nn; x += 32) aJ[x] = 0.f;
+      __syncwarp();
+      if (lane < n) {
+        float r = 0.f, c = 0.f, rc = 0.f;
+#pragma unroll 4
+        for (int d4 = 0; d4 < dh; d4 += 4) {
+          const float4 qe = *reinterpret_cast<const float4*>(qJ + el * AW_LD + d4);
+          const float4 ke = *reinterpret_cast<const float4*>(kJ + el * AW_LD + d4);
+          const float4 kj = *reinterpret_cast<const float4*>(k0 + lane * AW_LD + d4);
+          const float4 qi = *reinterpret_cast<const float4*>(q0 + lane * AW_LD + d4);
+          r = fmaf(qe.x, kj.x, r); r = fmaf(qe.y, kj.y, r); r = fmaf(qe.z, kj.z, r); r = fmaf(qe.w, kj.w, r);
+          c = fmaf(qi.x, ke.x, c); c = fmaf(qi.y, ke.y, c); c = fmaf(qi.z, ke.z, c); c = fmaf(qi.w, ke.w, c);
+          rc = fmaf(qe.x, ke.x, rc); rc = fmaf(qe.y, ke.y, rc); rc = fmaf(qe.z, ke.z, rc); rc = fmaf(qe.w, ke.w, rc);
+        }
+        if (lane == el) {
+          aJ[el * AW_NS + el] = (r + c) * scale;
+          aLp[el * AW_NS + el] = fmaf(2.0f * scale, rc, aLp[el * AW_NS + el]);
+          col_e = (r + c) * scale;
+        } else {
+          aJ[el * AW_NS + lane] = r * scale;
+          aJ[lane * AW_NS + el] = c * scale;
+          col_e = c * scale;
+        }
+      }
+    } else if (tile_on) {
       float a1[2][4], a2[2][4];
 #pragma unroll
       for (int r = 0; r < 2; ++r)
@@ -705,6 +750,10 @@ k_attention_fl_warp(JqAttnOperand q, JqAttnOperand k, JqAttnOperand v, float* __
         aJ[i * AW_NS + j] = wj;   // aJ now holds wJ
       }
       t2p[i] += t2;
+      if (QKL) {
+        abar_w[i] = ab;
+        abar_w[16 + i] = col_e;   // aJ[i][el]
+      }
     }
     __syncwarp();
     // phase C: rows in two passes of 8, j in steps of 4 (float4 broadcasts of wJ and w)
@@ -714,30 +763,81 @@ k_attention_fl_warp(JqAttnOperand q, JqAttnOperand k, JqAttnOperand v, float* __
         float acc[8][2], acc2[8][2];
 #pragma unroll
         for (int r = 0; r < 8; ++r) acc[r][0] = acc[r][1] = acc2[r][0] = acc2[r][1] = 0.f;
-        for (int j4 = 0; j4 < n; j4 += 4) {
-          float va[4], vb[4], ja[4], jb[4];
+        if (QKL) {
+          // only  w vJ  is an n^2 d product; the wJ terms follow from abar, column el of aJ and row el of wJ
+          for (int j4 = 0; j4 < n; j4 += 4) {
+            float ja[4], jb[4];
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const int j = min(j4 + u, n - 1);   // w = wJ = 0 beyond n: the clamped operand does not contribute
-            va[u] = v0[j * AW_LD + lane];
-            vb[u] = v0[j * AW_LD + lane + 32];
-            ja[u] = vJ[j * AW_LD + lane];
-            jb[u] = vJ[j * AW_LD + lane + 32];
+            for (int u = 0; u < 4; ++u) {
+              const int j = min(j4 + u, n - 1);
+              ja[u] = vJ[j * AW_LD + lane];
+              jb[u] = vJ[j * AW_LD + lane + 32];
+            }
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+              const int i = min(ib + r, n - 1);
+              const float4 ww4 = *reinterpret_cast<const float4*>(wgt + i * AW_NS + j4);
+              const float ww[4] = {ww4.x, ww4.y, ww4.z, ww4.w};
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                acc[r][0] = fmaf(ww[u], ja[u], acc[r][0]);
+                acc[r][1] = fmaf(ww[u], jb[u], acc[r][1]);
+              }
+            }
           }
+          const float ve_a = v0[el * AW_LD + lane], ve_b = v0[el * AW_LD + lane + 32];
+          const float je_a = vJ[el * AW_LD + lane], je_b = vJ[el * AW_LD + lane + 32];
 #pragma unroll
           for (int r = 0; r < 8; ++r) {
             const int i = min(ib + r, n - 1);
-            const float4 wj4 = *reinterpret_cast<const float4*>(aJ + i * AW_NS + j4);
-            const float4 ww4 = *reinterpret_cast<const float4*>(wgt + i * AW_NS + j4);
-            const float wj[4] = {wj4.x, wj4.y, wj4.z, wj4.w}, ww[4] = {ww4.x, ww4.y, ww4.z, ww4.w};
-#pragma unroll
+            if (i != el) {
+              const float ab = abar_w[i], g = wgt[i * AW_NS + el] * abar_w[16 + i];   // w_ie aJ_ie
+              const float wv_a = acc[r][0], wv_b = acc[r][1];
+              acc[r][0] = wv_a - ab * o0s[i * dh + lane] + g * ve_a;
+              acc[r][1] = wv_b - ab * o0s[i * dh + lane + 32] + g * ve_b;
+              acc2[r][0] = g * je_a - ab * wv_a;
+              acc2[r][1] = g * je_b - ab * wv_b;
+            } else {
+              float t_a = 0.f, t_b = 0.f, u_a = 0.f, u_b = 0.f;   // row el of wJ is dense
+              for (int j = 0; j < n; ++j) {
+                const float wj = aJ[el * AW_NS + j];
+                t_a = fmaf(wj, v0[j * AW_LD + lane], t_a);
+                t_b = fmaf(wj, v0[j * AW_LD + lane + 32], t_b);
+                u_a = fmaf(wj, vJ[j * AW_LD + lane], u_a);
+                u_b = fmaf(wj, vJ[j * AW_LD + lane + 32], u_b);
+              }
+              acc[r][0] += t_a;
+              acc[r][1] += t_b;
+              acc2[r][0] = u_a;
+              acc2[r][1] = u_b;
+            }
+          }
+        } else {
+        for (int j4 = 0; j4 < n; j4 += 4) {
+            float va[4], vb[4], ja[4], jb[4];
+  #pragma unroll
             for (int u = 0; u < 4; ++u) {
-              acc[r][0] = fmaf(wj[u], va[u], acc[r][0]);
-              acc[r][0] = fmaf(ww[u], ja[u], acc[r][0]);
-              acc[r][1] = fmaf(wj[u], vb[u], acc[r][1]);
-              acc[r][1] = fmaf(ww[u], jb[u], acc[r][1]);
-              acc2[r][0] = fmaf(wj[u], ja[u], acc2[r][0]);
-              acc2[r][1] = fmaf(wj[u], jb[u], acc2[r][1]);
+              const int j = min(j4 + u, n - 1);   // w = wJ = 0 beyond n: the clamped operand does not contribute
+              va[u] = v0[j * AW_LD + lane];
+              vb[u] = v0[j * AW_LD + lane + 32];
+              ja[u] = vJ[j * AW_LD + lane];
+              jb[u] = vJ[j * AW_LD + lane + 32];
+            }
+  #pragma unroll
+            for (int r = 0; r < 8; ++r) {
+              const int i = min(ib + r, n - 1);
+              const float4 wj4 = *reinterpret_cast<const float4*>(aJ + i * AW_NS + j4);
+              const float4 ww4 = *reinterpret_cast<const float4*>(wgt + i * AW_NS + j4);
+              const float wj[4] = {wj4.x, wj4.y, wj4.z, wj4.w}, ww[4] = {ww4.x, ww4.y, ww4.z, ww4.w};
+  #pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                acc[r][0] = fmaf(wj[u], va[u], acc[r][0]);
+                acc[r][0] = fmaf(ww[u], ja[u], acc[r][0]);
+                acc[r][1] = fmaf(wj[u], vb[u], acc[r][1]);
+                acc[r][1] = fmaf(ww[u], jb[u], acc[r][1]);
+                acc2[r][0] = fmaf(wj[u], ja[u], acc2[r][0]);
+                acc2[r][1] = fmaf(wj[u], jb[u], acc2[r][1]);
+              }
             }
           }
         }
@@ -864,11 +964,14 @@ int jq_launch_attention_fl(const JqAttnOperand& q, const JqAttnOperand& k, const
                          (v.off % 4 == 0) && ((reinterpret_cast<uintptr_t>(q.p) | reinterpret_cast<uintptr_t>(k.p) |
                                                reinterpret_cast<uintptr_t>(v.p)) % 16 == 0);
     const int nt = n * AW_LD, nn = n * AW_NS;
-    const size_t sw = sizeof(float) * ((size_t)3 * nt + nn + (2 * nn + 32 + n * 64) + (size_t)AW_WARPS * (6 * nt + 3 * nn + 32));
+    const size_t sw = sizeof(float) * ((size_t)3 * nt + nn + (2 * nn + 32 + 2 * n * 64) + (size_t)AW_WARPS * (6 * nt + 3 * nn + 48));
     if (track && dh == 64 && n >= 2 && n <= AW_NS && sw <= 227 * 1024 && aligned && !old_kernel) {
-      cudaError_t e = cudaFuncSetAttribute(k_attention_fl_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sw);
+      const bool qkl = (q.C == 5 && k.C == 5 && Cd != 5);
+      cudaError_t e = qkl ? cudaFuncSetAttribute(k_attention_fl_warp<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sw)
+                          : cudaFuncSetAttribute(k_attention_fl_warp<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sw);
       JQ_REQUIRE(e == cudaSuccess, JQ_ERR_CUDA, "attention: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-      JQ_LAUNCH(k_attention_fl_warp, dim3((unsigned)(W * H)), dim3(AW_WARPS * 32), sw, st, q, k, v, out, ldo, n, H);
+      if (qkl) JQ_LAUNCH(k_attention_fl_warp<true>, dim3((unsigned)(W * H)), dim3(AW_WARPS * 32), sw, st, q, k, v, out, ldo, n, H);
+      else JQ_LAUNCH(k_attention_fl_warp<false>, dim3((unsigned)(W * H)), dim3(AW_WARPS * 32), sw, st, q, k, v, out, ldo, n, H);
       JQ_CHECK_LAUNCH();
       return JQ_OK;
     }
