@@ -17,31 +17,35 @@
 // Local1 [W][n][5][F] -> dense [W][n][3n+2][F]: electron i owns Jacobian columns 3i..3i+2
 // (laplacian/sparse.py Local1Jacobian.to_dense).  One item per output element.
 // ------------------------------------------------------------------------------------------------
-__global__ void k_densify_local1(const float* __restrict__ in, float* __restrict__ out, long long items, int n, int F) {
+__global__ void k_densify_local1(const float* __restrict__ in, float* __restrict__ out, long long G, int n, int F) {
+  // one block per group g = (walker, electron i); a thread owns features f = tid, tid + blockDim, ... and writes the
+  // 3n + 2 rows from its five inputs (no per-element index arithmetic: the pass is a pure 2.6 GB write)
   const int C = 3 * n + 2;
-  for (long long it = (long long)blockIdx.x * blockDim.x + threadIdx.x; it < items;
-       it += (long long)gridDim.x * blockDim.x) {
-    int f = (int)(it % F);
-    long long t = it / F;
-    int c = (int)(t % C);
-    long long g = t / C;
-    int i = (int)(g % n);
-    float v = 0.f;
-    const float* p = in + g * 5 * F + f;
-    if (c == 0) v = p[0];
-    else if (c == C - 1) v = p[4 * F];
-    else if ((c - 1) / 3 == i) v = p[(1 + (c - 1) % 3) * F];
-    out[it] = v;
+  for (long long g = blockIdx.x; g < G; g += gridDim.x) {
+    const int i = (int)(g % n);
+    const float* p = in + g * 5 * F;
+    float* o = out + g * (long long)C * F;
+    for (int f = threadIdx.x; f < F; f += blockDim.x) {
+      const float v0 = p[f], j0 = p[F + f], j1 = p[2 * F + f], j2 = p[3 * F + f], l = p[4 * F + f];
+      o[f] = v0;
+      for (int e = 0; e < n; ++e) {
+        const bool own = (e == i);
+        o[(long long)(1 + 3 * e) * F + f] = own ? j0 : 0.f;
+        o[(long long)(2 + 3 * e) * F + f] = own ? j1 : 0.f;
+        o[(long long)(3 + 3 * e) * F + f] = own ? j2 : 0.f;
+      }
+      o[(long long)(C - 1) * F + f] = l;
+    }
   }
 }
 
 int jq_launch_densify_local1(const float* in, float* out, long long W, int n, int F, cudaStream_t st) {
-  long long items = W * n * (3 * n + 2) * F;
-  if (items <= 0) return JQ_OK;
-  int grid = jq_cdiv(items, 256);
-  if (grid > 148 * 32) grid = 148 * 32;
-  jq_prof_work(0.0, 4.0 * (double)items);
-  JQ_LAUNCH(k_densify_local1, dim3(grid), dim3(256), 0, st, in, out, items, n, F);
+  const long long G = W * n;
+  if (G <= 0 || F <= 0) return JQ_OK;
+  long long grid = G;
+  if (grid > 148LL * 64) grid = 148LL * 64;
+  jq_prof_work(0.0, 4.0 * (double)G * (3 * n + 2) * F);
+  JQ_LAUNCH(k_densify_local1, dim3((unsigned)grid), dim3(256), 0, st, in, out, G, n, F);
   JQ_CHECK_LAUNCH();
   return JQ_OK;
 }
@@ -262,29 +266,24 @@ __global__ void __launch_bounds__(256) k_layernorm_fl_smem(const float* __restri
     }
     __syncthreads();
   }
-  // outputs
-  for (int q = tid; q < (C > 1 ? C - 1 : 1) * F; q += nt) {
-    const int c = q / F, f = q - c * F;
+  // outputs: a thread owns feature columns f = tid, tid + blockDim, ... and walks the rows (no index division; the
+  // Laplacian row's sum over the Jacobian rows is accumulated on the way)
+  for (int f = tid; f < F; f += nt) {
     const float xc = xs[f] - mu0;
     const float sc = scale ? scale[f] : 1.0f;
-    if (c == 0) {
-      float y = xc * s * sc;
-      if (bias) y += bias[f];
-      og[f] = y;
-    } else {
-      const float v = xs[c * F + f] - mu[c];
-      og[(long long)c * F + f] = (v * s + xc * sj[c]) * sc;
-    }
-  }
-  if (C > 1) {
-    const float sL = scal[1];
-    for (int f = tid; f < F; f += nt) {
-      const float xc = xs[f] - mu0;
+    float y = xc * s * sc;
+    if (bias) y += bias[f];
+    og[f] = y;
+    if (C > 1) {
       float acc = 0.f;
-      for (int k = 1; k <= K; ++k) acc = fmaf(xs[k * F + f] - mu[k], sj[k], acc);
+      for (int k = 1; k <= K; ++k) {
+        const float v = xs[k * F + f] - mu[k];
+        const float sjk = sj[k];
+        og[(long long)k * F + f] = (v * s + xc * sjk) * sc;
+        acc = fmaf(v, sjk, acc);
+      }
       const float v = xs[(C - 1) * F + f] - mu[C - 1];
-      const float sc = scale ? scale[f] : 1.0f;
-      og[(long long)(C - 1) * F + f] = (v * s + xc * sL + 2.0f * acc) * sc;
+      og[(long long)(C - 1) * F + f] = (v * s + xc * scal[1] + 2.0f * acc) * sc;
     }
   }
 }
