@@ -22,6 +22,8 @@ def molecule(name):
     """(atoms (A,3) float64 [bohr], charges (A,), nspins)."""
     if name == "Li":
         return torch.zeros(1, 3, dtype=F64), torch.tensor([3.0], dtype=F64), (2, 1)
+    if name == "Li3up":  # spin-polarised lithium: a single spin channel with several electrons (test geometry)
+        return torch.zeros(1, 3, dtype=F64), torch.tensor([3.0], dtype=F64), (3, 0)
     if name == "H":
         return torch.zeros(1, 3, dtype=F64), torch.tensor([1.0], dtype=F64), (1, 0)
     if name == "He":

@@ -52,6 +52,7 @@ def _fp32_twin(p64, el, atoms, charges, nspins):
     ("H", 2, (8, 8), (4, 4)),
     ("LiH", 4, (64, 64, 64), (16, 16, 16)),
     ("Li", 16, (256,) * 4, (32,) * 4),   # BASELINE config 2 network
+    ("Li3up", 4, (64, 64, 64), (32, 32, 32)),   # one spin channel: fused pair layer / spin means with nch == 1
 ])
 def test_local_energy_parity_small(mol, ndets, hs, hd):
     rt = _rt()
