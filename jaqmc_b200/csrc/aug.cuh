@@ -69,6 +69,8 @@ struct JqDenseArgs {
   // scratch for the tensor-core path's transposed hi/lo weight split: jq_dense_tc_scratch_floats(k0+k1, N) floats,
   // or null to force the CUDA-core kernel
   float* wscratch;
+  int k0_valid; // 0 (= k0), or the number of kernel rows that exist: src0 columns [k0_valid, k0) are zero padding
+                // (lets a 20- or 56-wide first layer take the tensor-core path, which needs multiples of 32)
   int small_gt; // set by the launcher: groups per block of k_dense_small
   int tc_mode;  // 0: CTA-pair kernel (weights resident) when the shape allows, else the streaming one; 1: streaming only
 };
@@ -86,7 +88,7 @@ bool jq_launch_pair_layer_fused(const float* h2, int K, const float* w0, const f
                                 JqSpins sp, int N, int residual, int track, cudaStream_t st, int* rc);
 #endif
 int jq_launch_concat_layer1(const float* ae, const float* g2, float* out, int W, JqSpins sp, int f1, int fg,
-                            int track, cudaStream_t st);
+                            int track, int ld_out, cudaStream_t st);   // ld_out >= f1 (1 + nch) + fg: zero padded
 int jq_launch_spin_mean(const float* h, float* m, int W, JqSpins sp, int C, int F, cudaStream_t st);
 
 // ---- kernels implemented in logdet.cu -----------------------------------------------------------

@@ -72,7 +72,9 @@ __global__ void __launch_bounds__(256) k_dense_simt(JqDenseArgs a) {
       int kl = idx / GM_BN, cl = idx % GM_BN;
       int kk = kb + kl, col = col0 + cl;
       float v = 0.f;
-      if (kk < kt && col < a.N) v = (kk < a.k0) ? a.w0[(long long)kk * ldw + col] : a.w1[(long long)(kk - a.k0) * ldw + col];
+      if (kk < kt && col < a.N)
+        v = (kk < a.k0) ? ((a.k0_valid == 0 || kk < a.k0_valid) ? a.w0[(long long)kk * ldw + col] : 0.f)
+                        : a.w1[(long long)(kk - a.k0) * ldw + col];
       Bs[kl][cl] = v;
     }
     __syncthreads();
@@ -126,7 +128,8 @@ __global__ void k_dense_simt(JqDenseArgs a) {
     long long w = g / a.n_tot;
     for (int col = blockIdx.y * GM_BN; col < a.N && col < (int)(blockIdx.y + 1) * GM_BN; ++col) {
       float v = 0.f;
-      for (int k = 0; k < a.k0; ++k) v = fmaf(a.src0[row * a.k0 + k], a.w0[(long long)k * ldw + col], v);
+      const int kv = a.k0_valid ? a.k0_valid : a.k0;   // src0 columns [kv, k0) are zero padding without kernel rows
+      for (int k = 0; k < kv; ++k) v = fmaf(a.src0[row * a.k0 + k], a.w0[(long long)k * ldw + col], v);
       for (int k = 0; k < a.k1; ++k) v = fmaf(a.src1[row * a.k1 + k], a.w1[(long long)k * ldw + col], v);
       if (a.cadd) v += a.cadd[(w * a.C + c) * a.N + col];
       if (a.bias && c == 0) v += a.bias[col];
@@ -257,7 +260,7 @@ __global__ void k_dense_small(JqDenseArgs a) {
 }
 
 static bool dense_small_eligible(const JqDenseArgs& a) {
-  return a.C <= SM_CMAX && a.k1 == 0 && a.cadd == nullptr && a.n_sub == a.n_tot && a.k0 <= 64 && a.N <= 64 &&
+  return a.C <= SM_CMAX && a.k1 == 0 && a.k0_valid == 0 && a.cadd == nullptr && a.n_sub == a.n_tot && a.k0 <= 64 && a.N <= 64 &&
          a.out != a.src0;
 }
 
@@ -691,10 +694,10 @@ int jq_launch_pair_mean(const float* h2, float* g2, int W, JqSpins sp, int d2, i
 // One item per (walker, j, output column).
 // ------------------------------------------------------------------------------------------------
 __global__ void k_concat_layer1(const float* __restrict__ ae, const float* __restrict__ g2, float* __restrict__ out,
-                                long long items, JqSpins sp, int f1, int fg, int track) {
+                                long long items, JqSpins sp, int f1, int fg, int track, int FO) {
   const int n = sp.n(), nch = sp.nch();
   const int C1 = track ? 5 : 1, C = track ? 3 * n + 2 : 1;
-  const int FO = f1 * (1 + nch) + fg;
+  const int FV = f1 * (1 + nch) + fg;   // columns that exist; [FV, FO) is zero padding
   for (long long it = (long long)blockIdx.x * blockDim.x + threadIdx.x; it < items;
        it += (long long)gridDim.x * blockDim.x) {
     int col = (int)(it % FO);
@@ -702,7 +705,9 @@ __global__ void k_concat_layer1(const float* __restrict__ ae, const float* __res
     int j = (int)(t % n);
     long long w = t / n;
     float* o = out + ((w * n + j) * (long long)C) * FO + col;
-    if (col < f1) {
+    if (col >= FV) {
+      for (int c = 0; c < C; ++c) o[(long long)c * FO] = 0.f;
+    } else if (col < f1) {
       const float* p = ae + ((w * n + j) * (long long)C1) * f1 + col;
       o[0] = p[0];
       if (track) {
@@ -736,13 +741,13 @@ __global__ void k_concat_layer1(const float* __restrict__ ae, const float* __res
 }
 
 int jq_launch_concat_layer1(const float* ae, const float* g2, float* out, int W, JqSpins sp, int f1, int fg,
-                            int track, cudaStream_t st) {
-  int FO = f1 * (1 + sp.nch()) + fg;
+                            int track, int ld_out, cudaStream_t st) {
+  int FO = ld_out;
   long long items = (long long)W * sp.n() * FO;
   if (items <= 0) return JQ_OK;
   int grid = jq_cdiv(items, 256);
   if (grid > 148 * 32) grid = 148 * 32;
-  JQ_LAUNCH(k_concat_layer1, dim3(grid), dim3(256), 0, st, ae, g2, out, items, sp, f1, fg, track);
+  JQ_LAUNCH(k_concat_layer1, dim3(grid), dim3(256), 0, st, ae, g2, out, items, sp, f1, fg, track, FO);
   JQ_CHECK_LAUNCH();
   return JQ_OK;
 }

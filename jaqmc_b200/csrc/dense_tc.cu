@@ -1167,13 +1167,13 @@ k_dense_tc_pair(const __grid_constant__ CUtensorMap mapX0, const __grid_constant
 
 // Wt_hi / Wt_lo [N_out][Kt] (K-major) from the flax kernel rows w0 [k0][N], w1 [k1][N].
 __global__ void k_weight_split_t(const float* __restrict__ w0, int k0, const float* __restrict__ w1, int k1, int N,
-                                 int ldw, float* __restrict__ wh, float* __restrict__ wl) {
+                                 int ldw, float* __restrict__ wh, float* __restrict__ wl, int k0_valid) {
   const int kt = k0 + k1;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < (long long)N * kt;
        i += (long long)gridDim.x * blockDim.x) {
     int k = (int)(i % kt);
     int f = (int)(i / kt);
-    float v = (k < k0) ? w0[(long long)k * ldw + f] : w1[(long long)(k - k0) * ldw + f];
+    float v = (k < k0) ? (k < k0_valid ? w0[(long long)k * ldw + f] : 0.f) : w1[(long long)(k - k0) * ldw + f];
     float h = tf32_rna(v);
     wh[i] = h;
     wl[i] = tf32_rna(v - h);
@@ -1321,7 +1321,8 @@ int jq_launch_dense_tc(const JqDenseArgs& a, cudaStream_t st, bool* handled) {
     long long items = (long long)kt * a.N;
     int grid = jq_cdiv(items, 256);
     if (grid > 148 * 4) grid = 148 * 4;
-    JQ_LAUNCH(k_weight_split_t, dim3(grid), dim3(256), 0, st, a.w0, a.k0, a.w1, a.k1, a.N, a.ldw ? a.ldw : a.N, wh, wl);
+    JQ_LAUNCH(k_weight_split_t, dim3(grid), dim3(256), 0, st, a.w0, a.k0, a.w1, a.k1, a.N, a.ldw ? a.ldw : a.N, wh, wl,
+              a.k0_valid ? a.k0_valid : a.k0);
     JQ_CHECK_LAUNCH();
   }
   TcParams p;

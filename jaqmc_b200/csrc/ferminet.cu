@@ -39,6 +39,7 @@ int jq_fermi_dims(const jaqmc_ferminet_config* c, int track, int fat, int fee, F
     if (l < o->L - 1 && o->d2[l] > o->d2max) o->d2max = o->d2[l];
   }
   o->in1 = o->f1 * (1 + o->nch) + fee * o->nch;
+  o->in1p = (o->in1 + 31) / 32 * 32;   // layer-1 input row length: zero padded to the tensor-core path's K granularity
   JQ_REQUIRE(o->f1 != o->d1[0], JQ_ERR_UNSUPPORTED,
              "ferminet: input feature width == hidden_dims_single[0] (input-layer residual) is not supported");
   return JQ_OK;
@@ -64,14 +65,14 @@ void jq_fermi_carve_backbone(const FermiDims& d, long long W, JqArena& ar, Fermi
   b->h2a = ar.take<float>(W * nn * d.C2 * d.d2max);
   b->h2b = pairs ? ar.take<float>(W * nn * d.C2 * d.d2max) : nullptr;
   b->g2 = ar.take<float>(W * n * d.C * d.nch * d.d2max);
-  b->x1 = ar.take<float>(W * n * d.C * d.in1);
+  b->x1 = ar.take<float>(W * n * d.C * d.in1p);
   b->ha = ar.take<float>(W * n * d.C * d.d1max);
   b->hb = ar.take<float>(W * n * d.C * d.d1max);
   b->m = ar.take<float>(W * d.C * d.nch * d.d1max);
   b->cadd = ar.take<float>(W * d.C * d.d1max);
   {
     int kmax = d.d1max * (1 + d.nch) + d.nch * d.d2max;
-    if (d.in1 > kmax) kmax = d.in1;
+    if (d.in1p > kmax) kmax = d.in1p;
     int nmax = d.d1max > d.D * d.n ? d.d1max : d.D * d.n;
     b->wscr = ar.take<float>(jq_dense_tc_scratch_floats(kmax, nmax));
   }
@@ -113,9 +114,10 @@ int jq_fermi_backbone(const FermiDims& d, const jaqmc_ferminet_params* p, long l
     a.act = 1;
     a.wscratch = b.wscr;
     if (l == 0) {
-      if ((rc = jq_launch_concat_layer1(b.ae, b.g2, b.x1, (int)W, d.sp, d.f1, fg, track, st))) return rc;
+      if ((rc = jq_launch_concat_layer1(b.ae, b.g2, b.x1, (int)W, d.sp, d.f1, fg, track, d.in1p, st))) return rc;
       a.src0 = b.x1;
-      a.k0 = d.in1;
+      a.k0 = d.in1p;
+      a.k0_valid = d.in1;
       a.w0 = p->single_kernel[0];
       a.out = h;
       if ((rc = jq_launch_dense(a, st))) return rc;

@@ -52,7 +52,7 @@ struct FermiDims {
   JqSpins sp;
   int n, A, D, L, nch, C, C1, C2, f1, fee;  // f1 = input features per electron, fee = per pair
   int d1[JQ_MAX_LAYERS], d2[JQ_MAX_LAYERS];  // widths after layer l
-  int d1max, d2max, in1;
+  int d1max, d2max, in1, in1p;
 };
 
 struct FermiBufs {
