@@ -474,6 +474,7 @@ extern "C" int jaqmc_b200_dense_fl(const float* x, const float* x2, const float*
                workspace_bytes, need);
     a.wscratch = (float*)workspace;
     a.tc_mode = (use_tensor_cores == 2) ? 1 : 0;
+    a.tc_force = 1;   // the caller asked for the tensor-core kernel: no size heuristic
   }
   return jq_launch_dense(a, (cudaStream_t)stream);
 }

@@ -72,6 +72,7 @@ struct JqDenseArgs {
   int k0_valid; // 0 (= k0), or the number of kernel rows that exist: src0 columns [k0_valid, k0) are zero padding
                 // (lets a 20- or 56-wide first layer take the tensor-core path, which needs multiples of 32)
   int small_gt; // set by the launcher: groups per block of k_dense_small
+  int tc_force; // 1: take the tensor-core path whenever the shape allows, however small the launch (tests, dense_fl)
   int tc_mode;  // 0: CTA-pair kernel (weights resident) when the shape allows, else the streaming one; 1: streaming only
 };
 int jq_launch_dense(const JqDenseArgs& a, cudaStream_t st);

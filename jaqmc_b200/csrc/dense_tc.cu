@@ -330,13 +330,13 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& p, uint32_t tlane0
       }
       const int hf = PAIR ? pair_hf : (int)((uint32_t)item - t * mblocks);
       const int f = hf * TC_MBLK + f_lane;
-      // N_out is a multiple of 32 (launcher): a warp's 32 features are all inside or all outside the layer
+      // a warp whose 32 features all lie beyond the layer has no units
       if (ok && f - lane < p.N_out) {
         u.item = item;
         u.gi = gi;
-        u.f_ok = true;
-        u.fo = (uint32_t)f;
-        u.bias_f = p.bias ? p.bias[f] : 0.f;
+        u.f_ok = f < p.N_out;                                  // N_out not a multiple of 32: ragged last warp
+        u.fo = u.f_ok ? (uint32_t)f : (uint32_t)(p.N_out - 1);   // lanes beyond N_out read a valid column, never store
+        u.bias_f = p.bias ? p.bias[u.fo] : 0.f;
         u.g = (int)w * p.n_tot + p.j0 + gsub;
         const size_t go = (size_t)u.g * (size_t)C * N;
         u.cadd_b = CADD ? p.cadd + (size_t)((uint32_t)u.g / (uint32_t)p.n_tot_true) * (size_t)C * N : nullptr;
@@ -370,13 +370,15 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& p, uint32_t tlane0
       const uint32_t tbuf = tlane0 + buf * 2 * TC_NMAX;
       const uint32_t t = PAIR ? (uint32_t)item : (uint32_t)item / mblocks;
       const int hf = PAIR ? pair_hf : (int)((uint32_t)item - t * mblocks);
-      const int f = hf * TC_MBLK + f_lane;
+      const int f_raw = hf * TC_MBLK + f_lane;
+      const bool lane_ok = f_raw < p.N_out;
+      const int f = lane_ok ? f_raw : p.N_out - 1;   // ragged last warp: read a valid column, never store
       const bool batched = PAIR && p.wb > 1;
       const uint32_t w = batched ? t * 2u * (uint32_t)p.wb + (uint32_t)((q >> 1) * p.wb) : t / tiles_per_w;
       const int gsub_first = batched ? 0 : (int)(t - w * tiles_per_w) * p.G_t + g_first;
       int nvalid = batched ? (p.Wn - (int)w) * p.n_sub : p.n_sub - gsub_first;   // groups gi < nvalid exist
       if (nvalid > g_count) nvalid = g_count;
-      if (f - lane >= p.N_out) nvalid = 0;     // this warp's 32 features lie beyond the layer
+      if (f_raw - lane >= p.N_out) nvalid = 0;     // this warp's 32 features lie beyond the layer
       const int g_base = (int)w * p.n_tot + p.j0 + gsub_first;   // group of gi = 0
       // group index of gi: consecutive inside a walker's sub-range; a batched tile steps to the next walker every n_sub
       auto group_at = [&](int gi) -> int {
@@ -426,7 +428,7 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& p, uint32_t tlane0
                 if (ACT == 1) y = tanhf(y);
                 if (RES == 1) y = (rrv[s][i] + y) * inv_sqrt2;
                 if (RES == 2) y = rrv[s][i] + y;
-                p.out[(size_t)gidx[s][i] * N + f] = y;
+                if (lane_ok) p.out[(size_t)gidx[s][i] * N + f] = y;
               }
             }
           }
@@ -508,7 +510,7 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& p, uint32_t tlane0
     if (ACT == 0 && (c) == 0) y_ += bias_f;                            \
     if (RES == 1) y_ = ((rrv) + y_) * inv_sqrt2;                       \
     if (RES == 2) y_ = (rrv) + y_;                                     \
-    out_b[o] = y_;                                                     \
+    if (f_ok) out_b[o] = y_;                                           \
   }
 
   EpiUnit cur = find_unit(first, sub);
@@ -529,6 +531,7 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& p, uint32_t tlane0
       const EpiUnit nxt = find_unit(cur.item, cur.gi + 2);
       const bool have_nxt = nxt.item < limit;
       const uint32_t fo = cur.fo;
+      const bool f_ok = cur.f_ok;
       const float bias_f = cur.bias_f;
       const int g = cur.g;
       float* __restrict__ out_b = cur.out_b;
@@ -581,7 +584,7 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& p, uint32_t tlane0
           }
           if (RES == 1) o0 = (rr0 + o0) * inv_sqrt2;
           if (RES == 2) o0 = rr0 + o0;
-          out_b[fo] = o0;
+          if (f_ok) out_b[fo] = o0;
         }
         for (int j0 = 0; j0 < nfull; j0 += TC_RING) {
 #pragma unroll
@@ -621,7 +624,7 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& p, uint32_t tlane0
           float l = (ACT == 1) ? d1 * yl - 2.0f * th * d1 * s2 : yl * ev + y0 * e_l + 2.0f * s2;
           if (RES == 1) l = (rrL + l) * inv_sqrt2;
           if (RES == 2) l = rrL + l;
-          out_b[o_last + fo] = l;
+          if (f_ok) out_b[o_last + fo] = l;
         }
         ca0 = n_ca0;
         rr0 = n_rr0;
@@ -665,7 +668,7 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& p, uint32_t tlane0
           }
           if (RES == 1) y = (cur.res_b[o] + y) * inv_sqrt2;
           if (RES == 2) y = cur.res_b[o] + y;
-          out_b[o] = y;
+          if (f_ok) out_b[o] = y;
         }
       }
       cur = nxt;
@@ -1211,7 +1214,11 @@ bool jq_dense_tc_eligible(const JqDenseArgs& a) {
   if (a.C > TC_NMAX) return false;
   if (a.k0 % TC_BK || a.k1 % TC_BK) return false;
   if (a.k0 + a.k1 < 32) return false;
-  if (a.N < 64 || a.N % 32) return false;   // a warp's 32 features are all valid or all not
+  if (a.N < 32) return false;
+  // tiny launches (value-only layers of 3-electron systems): the persistent tcgen05 kernels cost ~50-100 us of fill,
+  // weight load and drain, the CUDA-core kernel a launch
+  static const double min_work = getenv("JAQMC_B200_TC_MIN_WORK") ? atof(getenv("JAQMC_B200_TC_MIN_WORK")) : 4e8;
+  if (!a.tc_force && (double)a.G * a.C * (a.k0 + a.k1) * a.N < min_work) return false;
   if (a.act == 2 && a.C == 1) return false;   // value-only launches take the separate envelope pass
   if (!a.wscratch) return false;
   if ((reinterpret_cast<uintptr_t>(a.src0) & 15) || (a.src1 && (reinterpret_cast<uintptr_t>(a.src1) & 15))) return false;

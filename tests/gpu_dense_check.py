@@ -31,6 +31,10 @@ CASES = [
     ("wide_c_many", 42 * 8, 128, 64, 0, 128, 42, 1, 0, True, False),   # both accumulator buffers, 128-row groups
     ("wide_n", 32 * 6, 98, 256, 0, 512, 32, 0, 0, False, False),        # four feature blocks (CTA-pair kernel only)
     ("n2_big", 14 * 300, 44, 256, 64, 256, 14, 1, 1, True, True),
+    ("ragged_n48", 3 * 200, 11, 256, 0, 48, 3, 0, 0, False, False),     # N not a multiple of 32 (Li orbitals: 16 x 3)
+    ("ragged_n80", 5 * 120, 17, 64, 32, 80, 5, 1, 0, True, True),
+    ("ragged_n208", 14 * 60, 44, 256, 0, 208, 14, 1, 2, True, False),
+    ("ragged_value", 3000, 1, 256, 0, 48, 3, 1, 0, True, True),
     ("k32_many", 14 * 400, 44, 32, 0, 256, 14, 1, 0, True, False),     # one K chunk per item, many items per CTA pair
     ("k64_many", 14 * 400, 11, 64, 0, 128, 14, 1, 2, True, False),
 ]
