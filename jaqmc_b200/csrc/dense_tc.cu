@@ -1215,10 +1215,12 @@ bool jq_dense_tc_eligible(const JqDenseArgs& a) {
   if (a.k0 % TC_BK || a.k1 % TC_BK) return false;
   if (a.k0 + a.k1 < 32) return false;
   if (a.N < 32) return false;
-  // tiny launches (value-only layers of 3-electron systems): the persistent tcgen05 kernels cost ~50-100 us of fill,
-  // weight load and drain, the CUDA-core kernel a launch
-  static const double min_work = getenv("JAQMC_B200_TC_MIN_WORK") ? atof(getenv("JAQMC_B200_TC_MIN_WORK")) : 4e8;
+  // Optional floor on the launch size (multiply-adds) below which the CUDA-core kernel is taken; off by default:
+  // measured r1w, the persistent tcgen05 kernels win down to the value-only layers of a 512-walker N2 shard, and lose
+  // only on the ragged value-only orbital layers of 3-electron systems, excluded below.
+  static const double min_work = getenv("JAQMC_B200_TC_MIN_WORK") ? atof(getenv("JAQMC_B200_TC_MIN_WORK")) : 0.0;
   if (!a.tc_force && (double)a.G * a.C * (a.k0 + a.k1) * a.N < min_work) return false;
+  if (!a.tc_force && a.C == 1 && a.N % 32) return false;
   if (a.act == 2 && a.C == 1) return false;   // value-only launches take the separate envelope pass
   if (!a.wscratch) return false;
   if ((reinterpret_cast<uintptr_t>(a.src0) & 15) || (a.src1 && (reinterpret_cast<uintptr_t>(a.src1) & 15))) return false;

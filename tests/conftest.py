@@ -9,9 +9,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-# The library routes launches below ~4e8 multiply-adds to the CUDA-core dense kernel (fixed cost of the persistent
-# tcgen05 kernels).  The parity tests run a handful of walkers: keep them on the tensor-core kernels they are there to
-# check (read once, when the library handles its first dense launch).
+# JAQMC_B200_TC_MIN_WORK is a tuning switch (launch size below which the CUDA-core dense kernel is taken; default 0).
+# The parity tests run a handful of walkers and are there to check the tensor-core kernels: pin it.
 os.environ.setdefault("JAQMC_B200_TC_MIN_WORK", "0")
 
 
