@@ -7,7 +7,9 @@ same marshalling code; the product singleton ``runtime()`` binds the CUDA librar
 
 from __future__ import annotations
 
+import contextlib
 import ctypes as C
+import functools
 
 import torch
 
@@ -16,6 +18,18 @@ from . import _abi
 
 def _ptr(t):
     return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def _on_device(fn):
+    """Run ``fn`` with the runtime's device current: the library queries the current device for its per-device
+    one-off setup (shared-memory opt-ins, SM count) and launches on the stream it is handed."""
+
+    @functools.wraps(fn)
+    def wrapped(self, *args, **kwargs):
+        with self._device_ctx():
+            return fn(self, *args, **kwargs)
+
+    return wrapped
 
 
 class Runtime:
@@ -31,6 +45,11 @@ class Runtime:
         self._ws = None
 
     # ---- plumbing -------------------------------------------------------------------------------
+    def _device_ctx(self):
+        if self.device.type == "cuda":
+            return torch.cuda.device(self.device)
+        return contextlib.nullcontext()
+
     def _stream(self):
         if self.device.type == "cuda":
             return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
@@ -67,6 +86,7 @@ class Runtime:
         return self.workspace(max(need, 1 << 16))
 
     # ---- entry points ---------------------------------------------------------------------------
+    @_on_device
     def logpsi(self, wf, system, electrons):
         """``electrons`` (W, n, 3) -> (logpsi (W,), sign (W,))."""
         self._check_tensor(electrons, "electrons")
@@ -79,6 +99,7 @@ class Runtime:
         _abi.check(self.lib, rc)
         return logpsi, sign
 
+    @_on_device
     def local_energy(self, wf, system, electrons, sums=None):
         """Returns a dict with logpsi, sign, grad (W,3n), lap, e_kin, e_pot, e_loc."""
         self._check_tensor(electrons, "electrons")
@@ -93,6 +114,7 @@ class Runtime:
         _abi.check(self.lib, rc)
         return out
 
+    @_on_device
     def local_energy_complex(self, wf, system, electrons, ewald=None, cell_atoms=None, cell_charges=None, sums=None):
         """Periodic (complex log psi) local energy: dict with complex64 logpsi / grad (W,3n) / lap / e_kin / e_loc and
         float32 e_pot (present when ``ewald`` -- a ``jaqmc_b200.ewald.EwaldSum`` -- is given)."""
@@ -116,6 +138,7 @@ class Runtime:
             out["e_pot"] = e_pot
         return out
 
+    @_on_device
     def capture_local_energy(self, wf, system, electrons, sums=None):
         """CUDA-graph version of :meth:`local_energy` for a fixed walker-batch shape: the ~60 kernel launches of one
         evaluation are captured once and replayed with a single launch.  Returns ``(replay, out)``: ``replay()``
@@ -135,6 +158,7 @@ class Runtime:
         replay._keep = keep
         return replay, out
 
+    @_on_device
     def coulomb(self, system, electrons):
         self._check_tensor(electrons, "electrons")
         W, n = electrons.shape[0], electrons.shape[1]
@@ -143,6 +167,7 @@ class Runtime:
         _abi.check(self.lib, rc)
         return e_pot
 
+    @_on_device
     def mh_step(self, wf, system, electrons, logpsi, normals, uniforms, stddev, logpsi_valid=True,
                 record_accepts=False, wrap_lattice=None):
         """In-place MH sub-steps on ``electrons`` / ``logpsi``; returns (n_accept (1,), accepted u8 (S,W) or None)."""
@@ -171,7 +196,8 @@ class Runtime:
         _abi.check(self.lib, rc)
         return n_accept, accepted
 
-    def capture_mh_step(self, wf, system, electrons, normals, uniforms, stddev):
+    @_on_device
+    def capture_mh_step(self, wf, system, electrons, normals, uniforms, stddev, wrap_lattice=None):
         """CUDA-graph version of :meth:`mh_step` for fixed shapes (the ~350 launches of ten sub-steps replayed with one
         launch: at a few hundred walkers per GPU the sampling pass is launch-bound).  ``replay()`` runs the sub-steps on
         the CURRENT contents of ``electrons`` / ``normals`` / ``uniforms`` / ``stddev`` (same tensors) in place and
@@ -179,18 +205,28 @@ class Runtime:
         W = electrons.shape[0]
         logpsi = torch.empty(W, dtype=torch.float32, device=self.device)
         keep0 = electrons.clone()
-        self.mh_step(wf, system, electrons, logpsi, normals, uniforms, stddev, logpsi_valid=False)  # warm-up
+        self.mh_step(wf, system, electrons, logpsi, normals, uniforms, stddev, logpsi_valid=False,
+                     wrap_lattice=wrap_lattice)  # warm-up
         electrons.copy_(keep0)
         torch.cuda.synchronize(self.device)
         n_accept = torch.zeros(1, dtype=torch.float32, device=self.device)
         ws = self._ws_for(wf, W, False)
         S = normals.shape[0]
         graph = torch.cuda.CUDAGraph()
+        lat = None
+        if wrap_lattice is not None:
+            lat = (C.c_float * 9)(*[float(v) for v in torch.as_tensor(wrap_lattice).reshape(-1).tolist()])
         with torch.cuda.graph(graph):
             n_accept.zero_()
-            rc = self.lib.jaqmc_b200_mh_step(
-                C.byref(wf.struct), C.byref(system.struct), _ptr(electrons), _ptr(logpsi), 0, _ptr(normals),
-                _ptr(uniforms), _ptr(stddev), S, W, _ptr(n_accept), None, _ptr(ws), ws.numel(), self._stream())
+            if lat is None:
+                rc = self.lib.jaqmc_b200_mh_step(
+                    C.byref(wf.struct), C.byref(system.struct), _ptr(electrons), _ptr(logpsi), 0, _ptr(normals),
+                    _ptr(uniforms), _ptr(stddev), S, W, _ptr(n_accept), None, _ptr(ws), ws.numel(), self._stream())
+            else:
+                rc = self.lib.jaqmc_b200_mh_step_pbc(
+                    C.byref(wf.struct), C.byref(system.struct), _ptr(electrons), _ptr(logpsi), 0, _ptr(normals),
+                    _ptr(uniforms), _ptr(stddev), S, W, _ptr(n_accept), None, lat, _ptr(ws), ws.numel(),
+                    self._stream())
             _abi.check(self.lib, rc)
         keep = (wf, system, electrons, normals, uniforms, stddev, logpsi, ws)
 
@@ -200,6 +236,28 @@ class Runtime:
 
         replay._keep = keep
         return replay
+
+    @_on_device
+    def mh_propose(self, x1, normals, stddev):
+        """``x1 + normals * stddev`` (sampler/mcmc.py:53-54) for samplers that drive their own loop."""
+        for t, nm in ((x1, "x1"), (normals, "normals"), (stddev, "stddev")):
+            self._check_tensor(t, nm)
+        x2 = torch.empty_like(x1)
+        rc = self.lib.jaqmc_b200_mh_propose(_ptr(x1), _ptr(normals), _ptr(stddev), _ptr(x2), x1.numel(), self._stream())
+        _abi.check(self.lib, rc)
+        return x2
+
+    @_on_device
+    def mh_accept(self, x1, x2, logprob1, logprob2, uniforms, n_accept, accepted=None):
+        """In-place accept / select on ``x1`` / ``logprob1`` (sampler/mcmc.py:128-137): accept iff
+        ``logprob2 - logprob1 > log(u)``."""
+        for t, nm in ((x1, "x1"), (x2, "x2"), (logprob1, "logprob1"), (logprob2, "logprob2"), (uniforms, "uniforms"),
+                      (n_accept, "n_accept")):
+            self._check_tensor(t, nm)
+        W = x1.shape[0]
+        rc = self.lib.jaqmc_b200_mh_accept(_ptr(x1), _ptr(x2), _ptr(logprob1), _ptr(logprob2), _ptr(uniforms), W,
+                                           x1.numel() // max(W, 1), _ptr(n_accept), _ptr(accepted), self._stream())
+        _abi.check(self.lib, rc)
 
     def launch_count(self) -> int:
         return int(self.lib.jaqmc_b200_launch_count())

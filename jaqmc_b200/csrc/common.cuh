@@ -81,6 +81,29 @@ static __device__ __forceinline__ void sincosf_(float x, float* s, float* c) { s
 static inline cudaError_t cudaMemcpyAsyncD2D(void* d, const void* s, size_t n, cudaStream_t st) {
   return cudaMemcpyAsync(d, s, n, cudaMemcpyDeviceToDevice, st);
 }
+// One-off per-DEVICE setup (cudaFuncSetAttribute opt-ins, SM count): function attributes belong to the device that is
+// current when they are set, so a process that drives several GPUs must repeat them per device.  Flags are written
+// after the setup they guard and only ever go false -> true, so a race between two threads repeats the (idempotent)
+// setup at worst.
+#define JQ_MAX_DEVICES 64
+static inline int jq_current_device() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return (dev >= 0 && dev < JQ_MAX_DEVICES) ? dev : 0;
+}
+struct JqPerDeviceFlag {
+  volatile bool done[JQ_MAX_DEVICES];
+};
+static inline int jq_sm_count() {
+  static volatile int count[JQ_MAX_DEVICES];
+  const int dev = jq_current_device();
+  if (!count[dev]) {
+    int c = 0;
+    cudaDeviceGetAttribute(&c, cudaDevAttrMultiProcessorCount, dev);
+    count[dev] = c;
+  }
+  return count[dev];
+}
 // Optional per-kernel device timing (bench.py's roofline leg): when enabled, every launch is bracketed by
 // two cudaEvents on the launching stream and tagged with the work the launcher declared via jq_prof_work().
 void jq_prof_before(const char* name, cudaStream_t st);

@@ -370,10 +370,11 @@ static int dense_small_launch(const JqDenseArgs& a, cudaStream_t st) {
     size_t smem = sizeof(float) * ((size_t)a.k0 * a.N + (size_t)a.small_gt * a.C * a.k0);
     jq_prof_work(2.0 * (double)a.G * a.C * a.k0 * a.N, 4.0 * (double)a.G * a.C * (a.k0 + a.N));
 #ifndef JAQMC_HOST_EMU
-    static bool attr_set = false;
-    if (!attr_set) {
+    static JqPerDeviceFlag attr_set;
+    const int dev = jq_current_device();
+    if (!attr_set.done[dev]) {
       cudaFuncSetAttribute(k_dense_small<0, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
-      attr_set = true;
+      attr_set.done[dev] = true;
     }
 #endif
     const dim3 grid((unsigned)jq_cdiv(a.G, a.small_gt));

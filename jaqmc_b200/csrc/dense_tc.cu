@@ -1197,15 +1197,7 @@ size_t jq_dense_tc_scratch_floats(int k_total, int n_out) { return (size_t)2 * k
 
 static bool pair_plan(const JqDenseArgs& a, int sm_count, TcParams* p, int* smem_bytes);
 
-static int tc_sm_count() {
-  static int sm_count = 0;
-  if (!sm_count) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
-  }
-  return sm_count;
-}
+static int tc_sm_count() { return jq_sm_count(); }
 
 bool jq_dense_tc_eligible(const JqDenseArgs& a) {
   // debugging switch (bisecting a numerical difference between the two dense kernels); both are sm_100a CUDA
@@ -1285,17 +1277,15 @@ static bool pair_plan(const JqDenseArgs& a, int sm_count, TcParams* p, int* smem
 int jq_launch_dense_tc(const JqDenseArgs& a, cudaStream_t st, bool* handled) {
   *handled = false;
   if (!jq_dense_tc_eligible(a)) return JQ_OK;
-  static int sm_count = 0;
-  static bool attr_set = false;
-  if (!attr_set) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
+  const int sm_count = jq_sm_count();
+  static JqPerDeviceFlag attr_set;
+  const int dev = jq_current_device();
+  if (!attr_set.done[dev]) {
     cudaError_t e = cudaFuncSetAttribute(k_dense_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT);
     JQ_REQUIRE(e == cudaSuccess, JQ_ERR_CUDA, "dense_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     e = cudaFuncSetAttribute(k_dense_tc_pair, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT);
     JQ_REQUIRE(e == cudaSuccess, JQ_ERR_CUDA, "dense_tc: cudaFuncSetAttribute (pair): %s", cudaGetErrorString(e));
-    attr_set = true;
+    attr_set.done[dev] = true;
   }
   const int kt = a.k0 + a.k1;
   float* wh = a.wscratch;

@@ -109,10 +109,15 @@ int jq_head_forward(const JqHeadDims& d, const jaqmc_head_params* p, const float
              "head: null jastrow parameter");
   int rc;
   const int nchan = split ? 2 : 1;
-  bool env_fused = true;  // the tcgen05 kernel applies the envelope in its epilogue; otherwise a separate pass does
+  // The envelope is fused into the orbital GEMM's epilogue under the forward Laplacian (tcgen05 kernel); on the
+  // value-only sampling path (one row per electron) the separate elementwise pass is cheaper than a fused epilogue
+  // variant.  Eligibility depends on the channel (its electron count enters the launch size), and the separate pass
+  // runs over the whole orbital buffer: fuse only when EVERY channel is eligible, decided before anything is launched.
+  JqDenseArgs args[2];
   JqEnvFuse ef[2];
+  bool env_fused = track && d.envelope_type != JAQMC_ENVELOPE_NULL;
   for (int s = 0; s < nchan; ++s) {
-    JqDenseArgs a;
+    JqDenseArgs& a = args[s];
     memset(&a, 0, sizeof(a));
     a.src0 = h;
     a.k0 = d.hidden;
@@ -131,9 +136,11 @@ int jq_head_forward(const JqHeadDims& d, const jaqmc_head_params* p, const float
       a.n_sub = n;
     }
     a.G = W * a.n_sub;
-    // the envelope is fused into the orbital GEMM's epilogue under the forward Laplacian; on the value-only
-    // sampling path (one row per electron) the separate elementwise pass is cheaper than a fused epilogue variant
-    if (track && d.envelope_type != JAQMC_ENVELOPE_NULL && env_fused && jq_dense_tc_eligible(a)) {
+    if (env_fused && !jq_dense_tc_eligible(a)) env_fused = false;
+  }
+  for (int s = 0; s < nchan; ++s) {
+    JqDenseArgs& a = args[s];
+    if (env_fused) {
       ef[s].electrons = electrons;
       ef[s].atoms = atoms;
       ef[s].pi = p->env_pi[s];
@@ -144,8 +151,6 @@ int jq_head_forward(const JqHeadDims& d, const jaqmc_head_params* p, const float
       ef[s].type = d.envelope_type;
       a.env = &ef[s];
       a.act = 2;
-    } else {
-      env_fused = false;
     }
     if ((rc = jq_launch_dense(a, st))) return rc;
   }

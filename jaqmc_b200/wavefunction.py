@@ -40,6 +40,10 @@ class Wavefunction:
     def init_params(self, data: MoleculeData, rngs):
         raise NotImplementedError
 
+    def _sampling_handles(self, params, data):
+        """Descriptors of the in-library MH step (``sampler.BatchLogProb.handles``)."""
+        return self._handle(params, data.atoms.shape[0]), _marshal.system_handle(data.atoms, None)
+
     # -- protocol --------------------------------------------------------------------------------
     def _check(self, data: MoleculeData):
         n = sum(self.nspins)
@@ -385,6 +389,10 @@ class SolidWavefunction:
         return _marshal.solid_handle(params, self.nspins, n_prim_atoms, self.simulation_lattice, self.primitive_lattice,
                                      kl, self.ndets, self.hidden_dims_single, self.hidden_dims_double,
                                      self.envelope_type, self.orbitals_spin_split)
+
+    def _sampling_handles(self, params, data):
+        return (self._handle(params, data.primitive_atoms.shape[0], data.electrons.device),
+                _marshal.system_handle(data.primitive_atoms, None))
 
     def evaluate(self, params, data) -> dict:
         """``{"logpsi"}``: complex log psi per walker (reference LogDet complex output)."""

@@ -140,7 +140,8 @@ def orbital_projection(p, h_one, nspins):
 
 
 def _isotropic_envelope(p, r_ae, is_abs=True):
-    """``output/envelope.py:123-140``: ``sum_I pi * exp(-|sigma * r|)`` -> ``(ndets, n_elec, n_orb)``."""
+    """``output/envelope.py:123-140``: ``sum_I pi * exp(-|sigma * r|)`` -> ``(ndets, n_elec, n_orb)``
+    (``is_abs=False``: exponent ``sigma * -r``)."""
     pi, sigma = p["pi"], p["sigma"]  # (n_orb, n_atoms, ndets)
     r = L.linear_map(lambda t: t[:, None, :, None], r_ae)  # (n_elec,1,n_atoms,1)
     sr = r * sigma
@@ -149,14 +150,35 @@ def _isotropic_envelope(p, r_ae, is_abs=True):
     return L.transpose(env, 2, 0, 1)
 
 
-def envelope(p, r_ae, nspins):
-    """``output/envelope.py:98-120`` (abs_isotropic)."""
-    n_up = nspins[0]
+def _diagonal_envelope(p, ae_vec):
+    """``output/envelope.py:143-163``: ``sum_I pi * exp(-||sigma (.) r_vec||)`` with ``sigma (n_orb, n_atoms, ndim, ndets)``."""
+    pi, sigma = p["pi"], p["sigma"]
+    v = L.linear_map(lambda t: t[:, None, :, :, None], ae_vec)  # (n_elec,1,n_atoms,ndim,1)
+    scaled = v * sigma
+    r_scaled = L.sqrt(L.sum_(L.square(scaled), dim=3))  # (n_elec, n_orb, n_atoms, ndets)
+    env = L.sum_(L.exp(-r_scaled) * pi, dim=2)
+    return L.transpose(env, 2, 0, 1)
+
+
+def envelope(p, r_ae, nspins, envelope_type="abs_isotropic", ae_vec=None):
+    """``output/envelope.py:98-120``; returns ``None`` for the ``null`` envelope (a factor of ones)."""
+    if envelope_type == "null":
+        return None
+    if envelope_type == "diagonal":
+        one = lambda q, lo, hi: _diagonal_envelope(q, ae_vec[lo:hi])  # noqa: E731
+    elif envelope_type in ("isotropic", "abs_isotropic"):
+        one = lambda q, lo, hi: _isotropic_envelope(q, r_ae[lo:hi], envelope_type == "abs_isotropic")  # noqa: E731
+    else:
+        raise ValueError(f"Unknown envelope: {envelope_type!r}")
+    n_up, n = nspins[0], nspins[0] + nspins[1]
     if "_env_up" in p:
-        up = _isotropic_envelope(p["_env_up"], r_ae[:n_up])
-        dn = _isotropic_envelope(p["_env_down"], r_ae[n_up:])
-        return L.cat([up, dn], dim=1)
-    return _isotropic_envelope(p["_env"], r_ae)
+        return L.cat([one(p["_env_up"], 0, n_up), one(p["_env_down"], n_up, n)], dim=1)
+    return one(p["_env"], 0, n)
+
+
+def _apply_envelope(orb, p, emb, nspins, envelope_type):
+    env = envelope(p.get("envelope_layer", {}), emb["r_ae"], nspins, envelope_type, emb.get("ae_vec"))
+    return orb if env is None else orb * env
 
 
 def logdet_sum(orbitals):
@@ -197,18 +219,19 @@ def simple_ee_jastrow(p, r_ee, nspins):
 # ---------------------------------------------------------------------------------------
 # FermiNet
 # ---------------------------------------------------------------------------------------
-def ferminet_orbitals(params, electrons, atoms, nspins):
+def ferminet_orbitals(params, electrons, atoms, nspins, envelope_type="abs_isotropic"):
+    """``(ndets, n, n)`` orbital matrices (``app/molecule/wavefunction/ferminet.py:110-138`` ``orbitals``)."""
     p = params["params"]
     n_layers = (len(p["backbone_layer"]) + 1) // 2
     emb = molecule_features(electrons, atoms, rescale=False)
     h_one, _ = fermi_layers(p["backbone_layer"], emb["ae_features"], emb["ee_features"], nspins, n_layers)
     orb = orbital_projection(p["orbital_layer"], h_one, nspins)
-    return orb * envelope(p["envelope_layer"], emb["r_ae"], nspins)
+    return _apply_envelope(orb, p, emb, nspins, envelope_type)
 
 
-def ferminet_logpsi(params, electrons, atoms, nspins):
+def ferminet_logpsi(params, electrons, atoms, nspins, envelope_type="abs_isotropic"):
     """``app/molecule/wavefunction/ferminet.py:76-108`` -> ``(sign, logpsi)``."""
-    return logdet_sum(ferminet_orbitals(params, electrons, atoms, nspins))
+    return logdet_sum(ferminet_orbitals(params, electrons, atoms, nspins, envelope_type))
 
 
 # ---------------------------------------------------------------------------------------
@@ -276,12 +299,17 @@ def lapnet_backbone(p, ae_features, nspins, heads):
     return hd
 
 
-def lapnet_logpsi(params, electrons, atoms, nspins, heads=4):
-    """``app/molecule/wavefunction/lapnet.py:117-135``."""
+def lapnet_orbitals(params, electrons, atoms, nspins, heads=4, envelope_type="abs_isotropic"):
     p = params["params"]
     emb = molecule_features(electrons, atoms, rescale=True)
     h = lapnet_backbone(p["backbone_layer"], emb["ae_features"], nspins, heads)
-    orb = orbital_projection(p["orbital_layer"], h, nspins) * envelope(p["envelope_layer"], emb["r_ae"], nspins)
+    return _apply_envelope(orbital_projection(p["orbital_layer"], h, nspins), p, emb, nspins, envelope_type), emb
+
+
+def lapnet_logpsi(params, electrons, atoms, nspins, heads=4, envelope_type="abs_isotropic"):
+    """``app/molecule/wavefunction/lapnet.py:117-135``."""
+    p = params["params"]
+    orb, emb = lapnet_orbitals(params, electrons, atoms, nspins, heads, envelope_type)
     sign, lp = logdet_sum(orb)
     if "jastrow_layer" in p:
         lp = lp + simple_ee_jastrow(p["jastrow_layer"], emb["r_ee"], nspins)
@@ -330,12 +358,17 @@ def psiformer_backbone(p, ae_features, nspins, layer_norm_mode="pre"):
     return x
 
 
-def psiformer_logpsi(params, electrons, atoms, nspins, layer_norm_mode="pre"):
-    """``app/molecule/wavefunction/psiformer.py:137-167``."""
+def psiformer_orbitals(params, electrons, atoms, nspins, layer_norm_mode="pre", envelope_type="abs_isotropic"):
     p = params["params"]
     emb = molecule_features(electrons, atoms, rescale=True)
     h = psiformer_backbone(p["backbone_layer"], emb["ae_features"], nspins, layer_norm_mode)
-    orb = orbital_projection(p["orbital_layer"], h, nspins) * envelope(p["envelope_layer"], emb["r_ae"], nspins)
+    return _apply_envelope(orbital_projection(p["orbital_layer"], h, nspins), p, emb, nspins, envelope_type), emb
+
+
+def psiformer_logpsi(params, electrons, atoms, nspins, layer_norm_mode="pre", envelope_type="abs_isotropic"):
+    """``app/molecule/wavefunction/psiformer.py:137-167``."""
+    p = params["params"]
+    orb, emb = psiformer_orbitals(params, electrons, atoms, nspins, layer_norm_mode, envelope_type)
     sign, lp = logdet_sum(orb)
     if "jastrow_layer" in p:
         lp = lp + simple_ee_jastrow(p["jastrow_layer"], emb["r_ee"], nspins)

@@ -113,3 +113,71 @@ def assert_fp32_parity(out, ref, electrons, e_tol=1e-5, l_tol=1e-6, outlier=10.0
         assert np.median(gerr) < 1e-5, np.median(gerr)
         assert np.median(gerr.max(axis=1)) < 1e-4 and gerr.max() < 1e-2, gerr.max(axis=1)
     return e_err, l_err
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Unscaled north-star errors (BASELINE.json: E_L 1e-5 relative, log|psi| 1e-6, float32).  Every GPU parity test that
+# evaluates a named configuration records them here; the table in DESIGN.md is generated from the JSON the GPU run
+# writes (gpurun_out/parity_table.json), next to the same numbers of the float32 twin of the oracle where computed.
+# ---------------------------------------------------------------------------------------------------------------
+def _quantiles(x):
+    x = np.asarray(x, dtype=np.float64)
+    return {"median": float(np.median(x)), "p99": float(np.quantile(x, 0.99)), "max": float(x.max())}
+
+
+def unscaled_errors(out, ref):
+    """``|dE_L| / |E_L|``, ``|dlog psi|`` (absolute, as the north star states it) and ``|dlog psi|`` in float32 ulps
+    of ``log psi`` (an error of 1e-6 is below one ulp once ``|log psi| >= 16``)."""
+    e_ref = ref["e_kin"] + ref["e_pot"]
+    e_out = out["e_loc"] if "e_loc" in out else out["e_kin"] + out["e_pot"]
+    e_rel = np.abs(e_out - e_ref) / np.abs(e_ref)
+    l_abs = np.abs(out["logpsi"] - ref["logpsi"])
+    l_ulp = l_abs / np.spacing(np.abs(ref["logpsi"]).astype(np.float32)).astype(np.float64)
+    return e_rel, l_abs, l_ulp
+
+
+def parity_report(name, out, ref, electrons, twin=None, assert_literal=True):
+    """Records the unscaled errors of configuration ``name`` and asserts the LITERAL north-star tolerances on the
+    well-conditioned walkers: those whose cancellation ratios ``(1/2|lap| + 1/2|grad|^2 + |V|) / |E_L|`` and
+    ``(|log psi| + |grad||r|) / |log psi|`` are below 10 -- for them the median error must meet 1e-5 (E_L, relative) and
+    1e-6 or one float32 ulp of log psi, whichever is larger (log|psi|)."""
+    e_rel, l_abs, l_ulp = unscaled_errors(out, ref)
+    e_scale, l_scale = fp32_scales(ref, electrons)
+    e_ref = np.abs(ref["e_kin"] + ref["e_pot"])
+    well_e = e_scale / e_ref < 10.0
+    well_l = l_scale / np.maximum(np.abs(ref["logpsi"]), 1e-30) < 10.0
+    rec = {"walkers": int(len(e_rel)), "E_L_rel": _quantiles(e_rel), "logpsi_abs": _quantiles(l_abs),
+           "logpsi_ulp": _quantiles(l_ulp), "well_conditioned_E": int(well_e.sum()), "well_conditioned_l": int(well_l.sum())}
+    if well_e.any():
+        rec["E_L_rel_well"] = _quantiles(e_rel[well_e])
+    if well_l.any():
+        rec["logpsi_abs_well"] = _quantiles(l_abs[well_l])
+    if twin is not None:
+        te, tl, tu = unscaled_errors(twin, ref)
+        rec["twin_E_L_rel"] = _quantiles(te)
+        rec["twin_logpsi_abs"] = _quantiles(tl)
+        rec["twin_logpsi_ulp"] = _quantiles(tu)
+    path = os.path.join(ROOT, "gpurun_out", "parity_table.json")
+    try:
+        import json
+
+        os.makedirs(os.path.dirname(path), exist_ok=True)
+        table = {}
+        if os.path.exists(path):
+            with open(path) as f:
+                table = json.load(f)
+        table[name] = rec
+        with open(path, "w") as f:
+            json.dump(table, f, indent=1, sort_keys=True)
+    except OSError:
+        pass
+    print(f"[parity] {name}: E_L rel median {rec['E_L_rel']['median']:.2e} p99 {rec['E_L_rel']['p99']:.2e} max "
+          f"{rec['E_L_rel']['max']:.2e} | logpsi abs median {rec['logpsi_abs']['median']:.2e} max "
+          f"{rec['logpsi_abs']['max']:.2e} ({rec['logpsi_ulp']['median']:.2f} / {rec['logpsi_ulp']['max']:.2f} ulp)")
+    if assert_literal:
+        if well_e.any():
+            assert np.median(e_rel[well_e]) < 1e-5, ("literal E_L tolerance", e_rel[well_e])
+        if well_l.any():
+            tol = np.maximum(1e-6, np.spacing(np.abs(ref["logpsi"][well_l]).astype(np.float32)).astype(np.float64))
+            assert np.median(l_abs[well_l] / tol) < 1.0, ("literal logpsi tolerance", l_abs[well_l])
+    return rec

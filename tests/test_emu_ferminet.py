@@ -19,6 +19,7 @@ CASES = {
     "h_single_channel": ("H", 2, (8, 8), (4, 4), True, "abs_isotropic"),
     "he_iso": ("He", 4, (12, 12, 12, 12), (6, 6, 6, 6), True, "isotropic"),
     "li_one_layer": ("Li", 2, (16,), (8,), True, "abs_isotropic"),
+    "lih_null_envelope": ("LiH", 3, (16, 16), (8, 8), True, "null"),
     "ar_18_electrons": ("Ar", 2, (8, 8), (4, 4), True, "abs_isotropic"),
 }
 
@@ -34,27 +35,14 @@ def _setup(case, W, seed=0):
             p["orbital_layer"] = {"DenseGeneral_0": p["orbital_layer"]["SplitChannelDense_0"]["DenseGeneral_0"]}
         if "_env_up" in p["envelope_layer"]:
             p["envelope_layer"] = {"_env": p["envelope_layer"]["_env_up"]}
+    if env == "null":
+        p64["params"]["envelope_layer"] = {}
     el = H.synthetic_walkers(atoms, charges, nspins, W, seed=seed)
     wf = M.ferminet_handle(H.to_f32(p64), nspins, atoms.shape[0], ndets, hs, hd, env, split)
     sysh = M.system_handle(atoms.float(), charges.float())
 
     def oracle_fn(e):
-        orb = ON.ferminet_orbitals(p64, e, atoms, nspins) if env == "abs_isotropic" else None
-        if orb is None:  # plain isotropic envelope: sigma may be negative
-            pp = p64["params"]
-            emb = ON.molecule_features(e, atoms, rescale=False)
-            h1, _ = ON.fermi_layers(pp["backbone_layer"], emb["ae_features"], emb["ee_features"], nspins, len(hs))
-            o = ON.orbital_projection(pp["orbital_layer"], h1, nspins)
-            n_up = nspins[0]
-            envp = pp["envelope_layer"]
-            if "_env_up" in envp:
-                from oracle import lap as L
-                ev = L.cat([ON._isotropic_envelope(envp["_env_up"], emb["r_ae"][:n_up], is_abs=False),
-                            ON._isotropic_envelope(envp["_env_down"], emb["r_ae"][n_up:], is_abs=False)], dim=1)
-            else:
-                ev = ON._isotropic_envelope(envp["_env"], emb["r_ae"], is_abs=False)
-            orb = o * ev
-        return ON.logdet_sum(orb)
+        return ON.ferminet_logpsi(p64, e, atoms, nspins, env)
 
     return wf, sysh, el, atoms, charges, nspins, oracle_fn
 

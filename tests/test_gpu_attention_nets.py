@@ -43,7 +43,7 @@ def _psiformer(mol, ndets, layers, heads, dh, mlp, W, seed=0, lnm="pre"):
     return wf, sysh, el, atoms, charges, nspins, (lambda e: ON.psiformer_logpsi(p64, e, atoms, nspins, lnm))
 
 
-def _check(setup, e_tol=1e-5, l_tol=1e-6):
+def _check(setup, e_tol=1e-5, l_tol=1e-6, report=None):
     rt = _rt()
     wf, sysh, el, atoms, charges, nspins, fn = setup
     e32 = el.float().contiguous().cuda()
@@ -52,6 +52,10 @@ def _check(setup, e_tol=1e-5, l_tol=1e-6):
     assert np.array_equal(out["sign"], ref["sign"])
     e_err, l_err = H.assert_fp32_parity(out, ref, el, e_tol=e_tol, l_tol=l_tol)
     print("scaled errors: E_L max %.2e, logpsi max %.2e" % (e_err.max(), l_err.max()))
+    if report:
+        # the literal log|psi| tolerance is asserted on the CUDA-core configurations; the tcgen05 layers carry the
+        # TC_L_TOL bias documented above and their unscaled numbers are recorded
+        H.parity_report(report, out, ref, el, assert_literal=False)
     lp, sg = rt.logpsi(wf, sysh, e32)
     assert torch.equal(sg.cpu(), torch.from_numpy(out["sign"]))
     _, l_scale = H.fp32_scales(ref, el)  # value-only (sampling) path against the oracle, same scaled tolerance
@@ -70,7 +74,7 @@ def test_lapnet_parity_small(mol, ndets, layers, heads, dh):
 
 def test_lapnet_parity_n2_full_network():
     """BASELINE config 3: N2, LapNet 4 layers x 4 heads x 64, 16 determinants."""
-    _check(_lapnet("N2", 16, 4, 4, 64, 6), l_tol=TC_L_TOL)
+    _check(_lapnet("N2", 16, 4, 4, 64, 6), l_tol=TC_L_TOL, report="C3 LapNet-N2")
 
 
 @pytest.mark.parametrize("mol,ndets,layers,heads,dh,mlp,lnm", [
@@ -85,18 +89,18 @@ def test_psiformer_parity_small(mol, ndets, layers, heads, dh, mlp, lnm):
 
 def test_psiformer_parity_n2_full_network():
     """Default Psiformer network (4 x 4 x 64, MLP 256) on N2 (14 electrons)."""
-    _check(_psiformer("N2", 16, 4, 4, 64, (256,), 4), l_tol=TC_L_TOL)
+    _check(_psiformer("N2", 16, 4, 4, 64, (256,), 4), l_tol=TC_L_TOL, report="Psiformer-N2")
 
 
 def test_psiformer_parity_benzene_full_network():
     """BASELINE config 4 at its full per-walker size: C6H6 (42 electrons, 12 atoms, 128 components per group), default
     Psiformer.  Exercises the 128-row groups of the tcgen05 kernel, the 672-column orbital layers (six feature blocks)
     and the generic attention / LogDet kernels (n > 16)."""
-    _check(_psiformer("C6H6", 16, 4, 4, 64, (256,), 5), l_tol=TC_L_TOL)
+    _check(_psiformer("C6H6", 16, 4, 4, 64, (256,), 5), l_tol=TC_L_TOL, report="C4 Psiformer-benzene")
 
 
 def test_lapnet_parity_benzene_full_network():
-    _check(_lapnet("C6H6", 16, 4, 4, 64, 5), l_tol=TC_L_TOL)
+    _check(_lapnet("C6H6", 16, 4, 4, 64, 5), l_tol=TC_L_TOL, report="LapNet-benzene")
 
 
 def test_attention_nets_full_batch_properties():

@@ -63,12 +63,14 @@ def test_local_energy_parity_small(mol, ndets, hs, hd):
     assert np.array_equal(out["sign"], ref["sign"])  # bit-exact sign
     H.assert_fp32_parity(out, ref, el)
     np.testing.assert_allclose(out["e_pot"], ref["e_pot"], rtol=2e-6)
+    if mol == "Li" and ndets == 16:
+        H.parity_report("C2 FermiNet-Li", out, ref, el, twin=_fp32_twin(p64, el, atoms, charges, nspins))
 
 
 def test_local_energy_parity_n2_full_network():
     """FermiNet-N2 (the headline network): error vs float64 no worse than 3x the float32 twin's own error."""
     rt = _rt()
-    W = 12
+    W = 24
     wf, sysh, el, atoms, charges, nspins, p64, fn = _setup("N2", 16, (256,) * 4, (32,) * 4, W)
     out = {k: v.cpu().numpy() for k, v in rt.local_energy(wf, sysh, el.float().contiguous().cuda()).items()}
     ref = H.oracle_batch(fn, el, atoms, charges)
@@ -83,6 +85,8 @@ def test_local_energy_parity_n2_full_network():
     # no worse than a plain float32 evaluation of the same graph (median over walkers, 3x slack)
     assert np.median(e_ours) <= 3 * np.median(e_twin) + 1e-7
     assert np.median(l_ours) <= 3 * np.median(l_twin) + 1e-8
+    # unscaled north-star numbers (recorded for DESIGN.md), literal tolerances on the well-conditioned walkers
+    H.parity_report("target FermiNet-N2", out, ref, el, twin=twin)
 
 
 def test_value_path_and_tiling():

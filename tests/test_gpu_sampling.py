@@ -1,0 +1,223 @@
+"""GPU tests of the sampling path: Metropolis-Hastings accept decisions against the float64 oracle replaying the same
+proposals and uniforms (reference sampler/mcmc.py:96-137; north star: decisions identical except where
+``|dlog p - log u| < 1e-6``), on the tcgen05 value-only path (FermiNet-N2, full network), with the periodic proposal
+(geometry/pbc.py:187-201) and through the host classes (``SamplePlan``, graph replay with replaced parameters)."""
+
+import numpy as np
+import pytest
+import torch
+
+import helpers as H
+import test_emu_solid as S
+from jaqmc_b200 import _marshal as M
+from oracle import estimators as OE
+from oracle import networks as ON
+
+pytestmark = pytest.mark.gpu
+MARGIN = 1e-6   # north star
+
+
+def _rt():
+    from jaqmc_b200._runtime import runtime
+
+    return runtime(torch.device("cuda", 0))
+
+
+def _replay_oracle(blp, el64, normals, uniforms, stddev, wrap=None):
+    """The oracle's MH update on the float32 proposals the kernel forms: x2 = fma(normal, sd, x1) in float32
+    (wrapped in float64 from there: the wrap itself is compared separately)."""
+    sd32 = torch.tensor(stddev, dtype=torch.float32)
+    x = el64.clone()
+    lp = blp(x)
+    acc, margin = [], []
+    for s in range(normals.shape[0]):
+        x2 = (x.float() + normals[s] * sd32).double()
+        if wrap is not None:
+            x2 = wrap(x2)
+        lp2 = blp(x2)
+        ratio = lp2 - lp
+        lu = torch.log(uniforms[s].double())
+        c = ratio > lu
+        acc.append(c)
+        margin.append((ratio - lu).abs())
+        x = torch.where(c[:, None, None], x2, x)
+        lp = torch.where(c, lp2, lp)
+    return torch.stack(acc), torch.stack(margin), x, lp
+
+
+def _compare(accepted, acc_ref, margin, allowed):
+    """Every differing decision must sit within ``allowed`` of the threshold; a walker whose chain diverged is dropped
+    from later steps.  Returns (still-identical mask, number of differing decisions)."""
+    W = accepted.shape[1]
+    ok = torch.ones(W, dtype=torch.bool)
+    n_diff = 0
+    for s in range(accepted.shape[0]):
+        diff = (accepted[s] != acc_ref[s]) & ok
+        assert (margin[s][diff] < allowed).all(), (s, margin[s][diff])
+        n_diff += int(diff.sum())
+        ok &= ~diff
+    return ok, n_diff
+
+
+def test_mh_accept_decisions_n2_full_network_tensor_core_path():
+    """FermiNet-N2 with the default 256/32 widths: every layer of the value-only forward runs on the tcgen05 kernels.
+    Margin 1e-6 as the north star states it, no unexplained mismatch."""
+    rt = _rt()
+    dev = torch.device("cuda", 0)
+    W, Sn = 192, 3
+    atoms, charges, nspins = H.molecule("N2")
+    hs, hd, ndets = (256,) * 4, (32,) * 4, 16
+    p64 = H.round_f32(ON.init_ferminet_params(nspins, atoms.shape[0], ndets, hs, hd, seed=31))
+    el = H.synthetic_walkers(atoms, charges, nspins, W, seed=17)
+    wf = M.ferminet_handle(H.to_f32(p64, dev), nspins, atoms.shape[0], ndets, hs, hd)
+    sysh = M.system_handle(atoms.float().to(dev), charges.float().to(dev))
+    g = torch.Generator().manual_seed(9)
+    normals = torch.randn(Sn, W, sum(nspins), 3, generator=g, dtype=torch.float64).float()
+    uniforms = torch.rand(Sn, W, generator=g, dtype=torch.float64).float().clamp_min(1e-7)
+    stddev = 0.05
+
+    def blp(x):
+        return torch.stack([2.0 * ON.ferminet_logpsi(p64, x[w], atoms, nspins)[1] for w in range(x.shape[0])])
+
+    acc_ref, margin, x_ref, lp_ref = _replay_oracle(blp, el, normals, uniforms, stddev)
+    e32 = el.float().contiguous().cuda()
+    logpsi = torch.empty(W, device="cuda")
+    n_acc, accepted = rt.mh_step(wf, sysh, e32, logpsi, normals.cuda().contiguous(), uniforms.cuda().contiguous(),
+                                 torch.tensor([stddev], device="cuda"), logpsi_valid=False, record_accepts=True)
+    accepted = accepted.cpu().bool()
+    same, n_diff = _compare(accepted, acc_ref, margin, MARGIN)
+    print(f"N2 MH: {int(acc_ref.sum())}/{acc_ref.numel()} accepted, {n_diff} decisions differ (all within {MARGIN})")
+    assert 0.1 < acc_ref.float().mean() < 0.95   # the test exercises both outcomes
+    assert int(n_acc) == int(accepted.sum())
+    np.testing.assert_allclose(e32.cpu()[same].numpy(), x_ref.float()[same].numpy(), atol=1e-6)
+    np.testing.assert_allclose(logpsi.cpu()[same].numpy(), (0.5 * lp_ref)[same].numpy(), atol=3e-5)
+
+
+def test_mh_step_pbc_matches_oracle():
+    """Periodic proposal (``jaqmc_b200_mh_step_pbc``) on the FCC LiH 2x2x1 cell against ``oracle.mh_update(wrap=...)``:
+    accept decisions, wrapped positions (inside the cell, equal to the oracle's) and Re log psi."""
+    rt = _rt()
+    W, Sn = 128, 4
+    wf, sysh, el, logpsi_fn, (sim, cell_atoms, cell_charges), f32 = S._setup("fcc_lih_221", W, device="cuda", seed=3)
+    lat = torch.as_tensor(sim, dtype=torch.float64)
+    inv = torch.linalg.inv(lat)
+
+    def wrap(x):
+        fr = x @ inv
+        return (fr - torch.floor(fr)) @ lat   # geometry/pbc.py:97-111
+
+    def blp(x):
+        return torch.stack([2.0 * logpsi_fn(x[w]).real for w in range(x.shape[0])])   # sampler/mcmc.py:122 (.real)
+
+    g = torch.Generator().manual_seed(2)
+    n = el.shape[1]
+    normals = torch.randn(Sn, W, n, 3, generator=g, dtype=torch.float64).float()
+    uniforms = torch.rand(Sn, W, generator=g, dtype=torch.float64).float().clamp_min(1e-7)
+    stddev = 0.25
+    el64 = torch.from_numpy(el).double()
+    acc_ref, margin, x_ref, lp_ref = _replay_oracle(blp, el64, normals, uniforms, stddev, wrap=wrap)
+    e32 = torch.from_numpy(el).cuda().contiguous()
+    logpsi = torch.empty(W, device="cuda")
+    n_acc, accepted = rt.mh_step(wf, sysh, e32, logpsi, normals.cuda().contiguous(), uniforms.cuda().contiguous(),
+                                 torch.tensor([stddev], device="cuda"), logpsi_valid=False, record_accepts=True,
+                                 wrap_lattice=sim)
+    accepted = accepted.cpu().bool()
+    # the float32 wrap can land an electron on the other side of a cell face than the float64 wrap does (a lattice
+    # translation: the wavefunction is periodic, so log psi is unaffected) -- compare positions modulo the lattice
+    same, n_diff = _compare(accepted, acc_ref, margin, 2e-5)
+    assert n_diff <= 1
+    assert int(n_acc) == int(accepted.sum())
+    assert accepted.any() and not accepted.all()
+    got = e32.cpu().double()
+    d = (got - x_ref) @ inv
+    d = d - torch.round(d)
+    assert (d[same] @ lat).abs().max() < 2e-5
+    moved = accepted.any(dim=0)
+    fr = got[moved] @ inv
+    assert (fr > -1e-5).all() and (fr < 1 + 1e-5).all()      # accepted proposals were wrapped into the cell
+    np.testing.assert_allclose(logpsi.cpu()[same].numpy(), (0.5 * lp_ref)[same].numpy(), atol=5e-5)
+
+
+def test_sample_plan_on_solid_wavefunction_uses_pbc_proposal():
+    """``SamplePlan(SolidWavefunction, MCMCSampler(sampling_proposal=make_pbc_gaussian_proposal(lattice)))`` as wired by
+    the reference's solid workflow (app/solid/workflow.py:87,185): runs in the library, equals the direct call."""
+    from jaqmc_b200.data import SolidData
+    from jaqmc_b200.sampler import MCMCSampler, SamplePlan, make_pbc_gaussian_proposal
+    from jaqmc_b200.wavefunction import SolidWavefunction
+
+    dev = torch.device("cuda", 0)
+    prim, sim, patoms, cell_atoms, cell_charges, nspins, klist = H.solid_system("fcc_lih_221")
+    f32 = lambda a: torch.as_tensor(np.asarray(a), dtype=torch.float32, device=dev)  # noqa: E731
+    wf = SolidWavefunction(nspins=nspins, simulation_lattice=sim, primitive_lattice=prim, klist=klist, ndets=2,
+                           hidden_dims_single=[32, 32], hidden_dims_double=[8, 8])
+    W = 64
+    el = torch.from_numpy(H.solid_walkers(cell_atoms, sum(nspins), W, seed=1)).to(dev)
+    data = SolidData(el, f32(cell_atoms), f32(cell_charges), f32(patoms))
+    params = wf.init_params(data, 5)
+    sampler = MCMCSampler(steps=3, sampling_proposal=make_pbc_gaussian_proposal(sim))
+    g = torch.Generator(device=dev).manual_seed(0)
+    normals = torch.randn(3, *el.shape, generator=g, device=dev)
+    uniforms = torch.rand(3, W, generator=g, device=dev).clamp_min_(1e-30)
+    outs = []
+    for graph in (False, True):
+        plan = SamplePlan(wf, sampler, graph=graph)
+        state = plan.init(data)
+        state = state._replace(stddev=torch.full((1,), 0.3, device=dev))
+        d2, stats, _ = plan.step(params, data, state, (normals, uniforms))
+        outs.append((d2.electrons.clone(), stats["pmove"].clone()))
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+    assert 0.0 < float(outs[0][1]) < 1.0
+    frac = outs[0][0].double() @ torch.linalg.inv(torch.as_tensor(sim, dtype=torch.float64, device=dev))
+    moved = (outs[0][0] != el).any(dim=-1).any(dim=-1)
+    assert moved.any()
+    assert (frac[moved] > -1e-5).all() and (frac[moved] < 1 + 1e-5).all()
+    # generic path: the same proposal object driven from the host (propose in torch, accept kernel) agrees on pmove
+    # up to decisions at float32 resolution of the wrap
+    class Opaque:   # not a BatchLogProb: forces the host-driven loop
+        def __init__(self, blp):
+            self.blp = blp
+
+        def __call__(self, x):
+            return self.blp(x)
+
+    from jaqmc_b200.sampler import BatchLogProb
+
+    state = plan.init(data)._replace(stddev=torch.full((1,), 0.3, device=dev))
+    d3, stats3, _ = sampler.step(Opaque(BatchLogProb(wf, params, data)), data, state, (normals, uniforms))
+    assert abs(float(stats3["pmove"]) - float(outs[0][1])) <= 2.0 / (3 * W)
+
+
+def test_graph_replay_recaptures_when_parameters_are_replaced():
+    """the captured MH graph bakes in parameter addresses.  Replacing the leaves (as an optimizer step that
+    returns new tensors does) must be seen: the second step samples from the NEW wavefunction."""
+    from jaqmc_b200.data import MoleculeData
+    from jaqmc_b200.sampler import MCMCSampler, SamplePlan
+    from jaqmc_b200.wavefunction import FermiNetWavefunction
+
+    dev = torch.device("cuda", 0)
+    atoms, charges, nspins = H.molecule("LiH")
+    wf = FermiNetWavefunction(nspins=nspins, ndets=4, hidden_dims_single=[64, 64], hidden_dims_double=[16, 16])
+    el = H.synthetic_walkers(atoms, charges, nspins, 128, seed=3).float().to(dev)
+    data = MoleculeData(el, atoms.float().to(dev), charges.float().to(dev))
+    p_a = wf.init_params(data, 1)
+    p_b = wf.init_params(data, 2)     # new tensors at new addresses
+    sampler = MCMCSampler(steps=4)
+    g = torch.Generator(device=dev).manual_seed(4)
+    normals = torch.randn(4, *el.shape, generator=g, device=dev)
+    uniforms = torch.rand(4, el.shape[0], generator=g, device=dev).clamp_min_(1e-30)
+    plain, graphed = SamplePlan(wf, sampler), SamplePlan(wf, sampler, graph=True)
+    st = plain.init(data)._replace(stddev=torch.full((1,), 0.4, device=dev))
+    for params in (p_a, p_b, p_a):
+        ref, _, _ = plain.step(params, data, st, (normals, uniforms))
+        got, _, _ = graphed.step(params, data, st, (normals, uniforms))
+        assert torch.equal(ref.electrons, got.electrons)
+    ra, _, _ = plain.step(p_a, data, st, (normals, uniforms))
+    rb, _, _ = plain.step(p_b, data, st, (normals, uniforms))
+    assert not torch.equal(ra.electrons, rb.electrons)   # the two parameter sets do sample differently
+    # in-place parameter updates keep the captured graph (same addresses) and are seen through it
+    with torch.no_grad():
+        for leaf in ON.tree_leaves(p_a):
+            leaf.mul_(1.01)
+    ref, _, _ = plain.step(p_a, data, st, (normals, uniforms))
+    got, _, _ = graphed.step(p_a, data, st, (normals, uniforms))
+    assert torch.equal(ref.electrons, got.electrons)
