@@ -36,10 +36,12 @@ extern "C" {
 
 #define JAQMC_MAX_LAYERS 8
 
-/* Envelope types: wavefunction/output/envelope.py:18-40 (EnvelopeType). */
+/* Envelope types: wavefunction/output/envelope.py:18-40 (EnvelopeType).  pi (n_orb, n_atoms, ndets); sigma the same
+ * shape, except (n_orb, n_atoms, 3, ndets) for the diagonal envelope. */
 #define JAQMC_ENVELOPE_ISOTROPIC 0
 #define JAQMC_ENVELOPE_ABS_ISOTROPIC 1
 #define JAQMC_ENVELOPE_NULL 2
+#define JAQMC_ENVELOPE_DIAGONAL 3 /* output/envelope.py:143-163; sigma has shape (n_orb, n_atoms, 3, ndets) */
 
 /* Wavefunction kinds (one descriptor type per reference class). */
 #define JAQMC_WF_FERMINET 1 /* app/molecule/wavefunction/ferminet.py:21-96  FermiNetWavefunction */
@@ -61,10 +63,14 @@ typedef struct {
   int32_t hidden_double[JAQMC_MAX_LAYERS];
   int32_t envelope_type;  /* JAQMC_ENVELOPE_* */
   int32_t orbitals_spin_split;
+  int32_t use_last_layer; /* backbone/ferminet.py:45-47: also update the double stream in the last layer and feed the
+                             orbitals the aggregated features (width d1 (1 + nch) + nch d2); the tree then holds one more
+                             double layer, Dense_{2 n_layers - 1} */
 } jaqmc_ferminet_config;
 
 /* Leaves of the Flax tree `params/…`.  backbone_layer/Dense_{2l} is single layer l,
- * Dense_{2l+1} double layer l (backbone/ferminet.py:37-43); only n_layers-1 double layers exist. */
+ * Dense_{2l+1} double layer l (backbone/ferminet.py:37-43); only n_layers-1 double layers exist unless
+ * use_last_layer is set. */
 typedef struct {
   const float* single_kernel[JAQMC_MAX_LAYERS]; /* (fan_in_l, hidden_single[l]) */
   const float* single_bias[JAQMC_MAX_LAYERS];   /* (hidden_single[l],) */
@@ -98,10 +104,12 @@ typedef struct {
   int32_t num_local_updates; /* per layer except the last (backbone/lapnet/_backbone.py:184-186) */
   int32_t envelope_type;
   int32_t rescale;           /* log-scaled input features (wavefunction/input/atomic.py:59-67) */
+  int32_t use_layernorm;     /* LayerNorm (epsilon 1e-6) before the Q/K projection, before the value projection and
+                                before value_update (_backbone.py:62-64,81-111,121) */
 } jaqmc_lapnet_config;
 
 /* backbone_layer/input_projection and backbone_layer/layers_{l}/... (_backbone.py:40-64,169-189).
- * Every bias may be NULL (use_input_bias / use_backbone_bias = False). use_layernorm=True is not supported. */
+ * Every bias may be NULL (use_input_bias / use_backbone_bias = False). */
 typedef struct {
   const float* input_kernel; /* (4*n_atoms+1, hidden) */
   const float* input_bias;
@@ -115,6 +123,13 @@ typedef struct {
   const float* update_bias[JAQMC_MAX_LAYERS];
   const float* qk_update_kernel[JAQMC_MAX_LAYERS][4]; /* qk_update_layers_{j}, j < num_local_updates <= 4 */
   const float* qk_update_bias[JAQMC_MAX_LAYERS][4];
+  /* layers_{l}/{qk_layernorm, value_layernorm, post_attention_layernorm}/{scale,bias} (hidden,): use_layernorm only */
+  const float* qk_ln_scale[JAQMC_MAX_LAYERS];
+  const float* qk_ln_bias[JAQMC_MAX_LAYERS];
+  const float* value_ln_scale[JAQMC_MAX_LAYERS];
+  const float* value_ln_bias[JAQMC_MAX_LAYERS];
+  const float* post_ln_scale[JAQMC_MAX_LAYERS];
+  const float* post_ln_bias[JAQMC_MAX_LAYERS];
   jaqmc_head_params head;
 } jaqmc_lapnet_params;
 
@@ -234,6 +249,15 @@ size_t jaqmc_b200_workspace_bytes(const jaqmc_wavefunction* wf, int64_t n_walker
 int jaqmc_b200_logpsi(const jaqmc_wavefunction* wf, const jaqmc_system* sys, const float* electrons,
                       int64_t n_walkers, float* logpsi, float* sign, void* workspace, size_t workspace_bytes,
                       jaqmc_stream_t stream);
+
+/* Replaces vmap(wf.orbitals) -- the pretraining head (app/molecule/wavefunction/base.py:60-72, ferminet.py:126-138,
+ * app/solid/wavefunction.py `orbitals`; consumer utils/atomic/pretrain.py:92-143): the orbital matrices after the
+ * envelope (and Bloch phase), before the determinant.
+ *   electrons (n_walkers, n, 3) -> orbitals (n_walkers, ndets, n, n) [electron, orbital]; JAQMC_WF_SOLID_FERMINET:
+ *   complex, interleaved (n_walkers, ndets, n, n, 2).  Workspace as for jaqmc_b200_logpsi (track = 0) + 2 floats per walker. */
+int jaqmc_b200_orbitals(const jaqmc_wavefunction* wf, const jaqmc_system* sys, const float* electrons,
+                        int64_t n_walkers, float* orbitals, void* workspace, size_t workspace_bytes,
+                        jaqmc_stream_t stream);
 
 /* Replaces the estimator half of EvaluationWorkStage.compute_step for the energy keys
  * (workflow/stage/evaluation.py:190-192): EuclideanKinetic in forward_laplacian mode

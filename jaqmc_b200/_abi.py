@@ -17,7 +17,7 @@ ERR_WORKSPACE_TOO_SMALL = 2
 ERR_CUDA = 3
 ERR_UNSUPPORTED = 4
 
-ENVELOPE = {"isotropic": 0, "abs_isotropic": 1, "null": 2}
+ENVELOPE = {"isotropic": 0, "abs_isotropic": 1, "null": 2, "diagonal": 3}
 
 WF_FERMINET = 1
 WF_LAPNET = 2
@@ -39,6 +39,7 @@ class FerminetConfig(C.Structure):
         ("hidden_double", C.c_int32 * MAX_LAYERS),
         ("envelope_type", C.c_int32),
         ("orbitals_spin_split", C.c_int32),
+        ("use_last_layer", C.c_int32),
     ]
 
 
@@ -77,6 +78,7 @@ class LapnetConfig(C.Structure):
         ("num_local_updates", C.c_int32),
         ("envelope_type", C.c_int32),
         ("rescale", C.c_int32),
+        ("use_layernorm", C.c_int32),
     ]
 
 
@@ -94,6 +96,12 @@ class LapnetParams(C.Structure):
         ("update_bias", FloatP * MAX_LAYERS),
         ("qk_update_kernel", (FloatP * 4) * MAX_LAYERS),
         ("qk_update_bias", (FloatP * 4) * MAX_LAYERS),
+        ("qk_ln_scale", FloatP * MAX_LAYERS),
+        ("qk_ln_bias", FloatP * MAX_LAYERS),
+        ("value_ln_scale", FloatP * MAX_LAYERS),
+        ("value_ln_bias", FloatP * MAX_LAYERS),
+        ("post_ln_scale", FloatP * MAX_LAYERS),
+        ("post_ln_bias", FloatP * MAX_LAYERS),
         ("head", HeadParams),
     ]
 
@@ -220,6 +228,10 @@ PROTOTYPES = {
         C.c_int,
         [C.POINTER(Wavefunction), C.POINTER(System), FloatP, FloatP, C.c_int32, FloatP, FloatP, FloatP, C.c_int32,
          C.c_int64, FloatP, C.c_void_p, C.POINTER(C.c_float), C.c_void_p, C.c_size_t, C.c_void_p],
+    ),
+    "jaqmc_b200_orbitals": (
+        C.c_int,
+        [C.POINTER(Wavefunction), C.POINTER(System), FloatP, C.c_int64, FloatP, C.c_void_p, C.c_size_t, C.c_void_p],
     ),
     "jaqmc_b200_dense_fl": (
         C.c_int,

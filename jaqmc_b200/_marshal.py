@@ -32,6 +32,11 @@ def _leaf(t, name, shape=None):
     return t if t.is_contiguous() else t.contiguous()
 
 
+def _sigma_shape(envelope, n, n_atoms, ndets):
+    """``sigma`` of the envelope: (n_orb, A, D), or (n_orb, A, 3, D) for the diagonal one (output/envelope.py:150-156)."""
+    return (n, n_atoms, 3, ndets) if envelope == "diagonal" else (n, n_atoms, ndets)
+
+
 def system_handle(atoms: torch.Tensor, charges: torch.Tensor | None) -> Handle:
     atoms = _leaf(atoms, "atoms")
     if atoms.dim() != 2 or atoms.shape[1] != 3:
@@ -50,7 +55,7 @@ def system_handle(atoms: torch.Tensor, charges: torch.Tensor | None) -> Handle:
 
 
 def ferminet_handle(params, nspins, n_atoms, ndets, hidden_dims_single, hidden_dims_double, envelope="abs_isotropic",
-                    orbitals_spin_split=True) -> Handle:
+                    orbitals_spin_split=True, use_last_layer=False) -> Handle:
     """Descriptor for ``FermiNetWavefunction`` (reference app/molecule/wavefunction/ferminet.py:43-74)."""
     n_up, n_dn = int(nspins[0]), int(nspins[1])
     n = n_up + n_dn
@@ -69,6 +74,7 @@ def ferminet_handle(params, nspins, n_atoms, ndets, hidden_dims_single, hidden_d
         cfg.hidden_double[i] = int(hidden_dims_double[i])
     cfg.envelope_type = _abi.ENVELOPE[envelope]
     cfg.orbitals_spin_split = int(split)
+    cfg.use_last_layer = int(bool(use_last_layer))
     ps = _abi.FerminetParams()
     keep = [cfg, ps]
     bb = p["backbone_layer"]
@@ -82,7 +88,7 @@ def ferminet_handle(params, nspins, n_atoms, ndets, hidden_dims_single, hidden_d
         keep += [k, b]
         ps.single_kernel[layer], ps.single_bias[layer] = k.data_ptr(), b.data_ptr()
         idx += 1
-        if layer < L - 1:
+        if layer < L - 1 or use_last_layer:
             h2 = int(hidden_dims_double[layer])
             k = _leaf(bb[f"Dense_{idx}"]["kernel"], f"backbone_layer/Dense_{idx}/kernel", (d2, h2))
             b = _leaf(bb[f"Dense_{idx}"]["bias"], f"backbone_layer/Dense_{idx}/bias", (h2,))
@@ -91,6 +97,8 @@ def ferminet_handle(params, nspins, n_atoms, ndets, hidden_dims_single, hidden_d
             idx += 1
             d2 = h2
         d1 = h1
+    if use_last_layer:   # the orbitals see the aggregated features (backbone/ferminet.py:45-47)
+        d1 = d1 * (1 + nch) + d2 * nch
     ol = p["orbital_layer"]
     if split:
         for s in range(2):
@@ -107,7 +115,7 @@ def ferminet_handle(params, nspins, n_atoms, ndets, hidden_dims_single, hidden_d
         names = ["_env_up", "_env_down"] if split else ["_env"]
         for s, nm in enumerate(names):
             pi = _leaf(el[nm]["pi"], f"envelope_layer/{nm}/pi", (n, n_atoms, ndets))
-            sg = _leaf(el[nm]["sigma"], f"envelope_layer/{nm}/sigma", (n, n_atoms, ndets))
+            sg = _leaf(el[nm]["sigma"], f"envelope_layer/{nm}/sigma", _sigma_shape(envelope, n, n_atoms, ndets))
             keep += [pi, sg]
             ps.env_pi[s], ps.env_sigma[s] = pi.data_ptr(), sg.data_ptr()
     wf = _abi.Wavefunction()
@@ -150,7 +158,7 @@ def _fill_head(b: _Binder, head: "_abi.HeadParams", p, n, n_atoms, ndets, hidden
         el = p["envelope_layer"]
         for s, nm in enumerate(["_env_up", "_env_down"] if split else ["_env"]):
             head.env_pi[s] = b.leaf(el, f"{nm}/pi", (n, n_atoms, ndets))
-            head.env_sigma[s] = b.leaf(el, f"{nm}/sigma", (n, n_atoms, ndets))
+            head.env_sigma[s] = b.leaf(el, f"{nm}/sigma", _sigma_shape(envelope, n, n_atoms, ndets))
     if jastrow:
         head.jastrow_alpha_par = b.leaf(p["jastrow_layer"], "alpha_par", (1,))
         head.jastrow_alpha_anti = b.leaf(p["jastrow_layer"], "alpha_anti", (1,))
@@ -165,7 +173,7 @@ def _wf_handle(kind, cfg, ps, keep):
 
 
 def lapnet_handle(params, nspins, n_atoms, ndets=16, num_layers=4, num_heads=4, heads_dim=64, num_local_updates=2,
-                  envelope="abs_isotropic", rescale=True, jastrow=True) -> Handle:
+                  envelope="abs_isotropic", rescale=True, jastrow=True, use_layernorm=False) -> Handle:
     """Descriptor for ``LapNetWavefunction`` (reference app/molecule/wavefunction/lapnet.py:63-115)."""
     n_up, n_dn = int(nspins[0]), int(nspins[1])
     n = n_up + n_dn
@@ -178,7 +186,7 @@ def lapnet_handle(params, nspins, n_atoms, ndets=16, num_layers=4, num_heads=4, 
     p = params["params"] if "params" in params else params
     hid = num_heads * heads_dim
     cfg = _abi.LapnetConfig(n_up, n_dn, int(n_atoms), int(ndets), int(num_layers), int(num_heads), int(heads_dim),
-                            int(num_local_updates), _abi.ENVELOPE[envelope], int(bool(rescale)))
+                            int(num_local_updates), _abi.ENVELOPE[envelope], int(bool(rescale)), int(bool(use_layernorm)))
     ps = _abi.LapnetParams()
     b = _Binder()
     bb = p["backbone_layer"]
@@ -186,8 +194,13 @@ def lapnet_handle(params, nspins, n_atoms, ndets=16, num_layers=4, num_heads=4, 
     ps.input_bias = b.leaf(bb, "input_projection/bias", (hid,), optional=True)
     for l in range(num_layers):
         lp = bb[f"layers_{l}"]
-        if "qk_layernorm" in lp or "value_layernorm" in lp:
-            raise NotImplementedError("LapNet use_layernorm=True is not supported by the CUDA pipeline")
+        if use_layernorm:
+            for nm, fld in (("qk_layernorm", "qk_ln"), ("value_layernorm", "value_ln"),
+                            ("post_attention_layernorm", "post_ln")):
+                getattr(ps, fld + "_scale")[l] = b.leaf(lp, f"{nm}/scale", (hid,))
+                getattr(ps, fld + "_bias")[l] = b.leaf(lp, f"{nm}/bias", (hid,))
+        elif "qk_layernorm" in lp or "value_layernorm" in lp:
+            raise ValueError("the parameter tree holds LayerNorm leaves but use_layernorm=False")
         ps.qk_kernel[l] = b.leaf(lp, "qk_projection/kernel", (hid, 2 * hid))
         ps.qk_bias[l] = b.leaf(lp, "qk_projection/bias", (2 * hid,), optional=True)
         for nm, fld in (("value_projection", "value"), ("output_projection", "output"), ("value_update", "update")):

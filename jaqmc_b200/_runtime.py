@@ -100,6 +100,19 @@ class Runtime:
         return logpsi, sign
 
     @_on_device
+    def orbitals(self, wf, system, electrons, n_dets, complex_valued=False):
+        """``electrons`` (W, n, 3) -> orbital matrices (W, ndets, n, n) (complex64 for the periodic network)."""
+        self._check_tensor(electrons, "electrons")
+        W, n = electrons.shape[0], electrons.shape[1]
+        shape = (W, n_dets, n, n, 2) if complex_valued else (W, n_dets, n, n)
+        orb = torch.empty(shape, dtype=torch.float32, device=self.device)
+        ws = self._ws_for(wf, W, False)
+        rc = self.lib.jaqmc_b200_orbitals(C.byref(wf.struct), C.byref(system.struct), _ptr(electrons), W, _ptr(orb),
+                                          _ptr(ws), ws.numel(), self._stream())
+        _abi.check(self.lib, rc)
+        return torch.view_as_complex(orb) if complex_valued else orb
+
+    @_on_device
     def local_energy(self, wf, system, electrons, sums=None):
         """Returns a dict with logpsi, sign, grad (W,3n), lap, e_kin, e_pot, e_loc."""
         self._check_tensor(electrons, "electrons")

@@ -182,7 +182,7 @@ static int wf_forward(const jaqmc_wavefunction* wf, const jaqmc_system* sys, con
     case JAQMC_WF_SOLID_FERMINET: {
       // value path only (sampling): real part -> logpsi, phase angle -> sign
       JQ_REQUIRE(track == 0, JQ_ERR_UNSUPPORTED, "solid: use jaqmc_b200_local_energy_complex for the tracked path");
-      JqWfOutC oc = {out.logpsi, out.sign, nullptr, nullptr, nullptr};
+      JqWfOutC oc = {out.logpsi, out.sign, nullptr, nullptr, nullptr, out.orbitals};
       return jq_solid_forward((const jaqmc_solid_config*)wf->config, (const jaqmc_solid_params*)wf->params, sys,
                               electrons, W, 0, ws, ws_bytes, oc, st);
     }
@@ -254,6 +254,44 @@ extern "C" int jaqmc_b200_logpsi(const jaqmc_wavefunction* wf, const jaqmc_syste
   for (long long w0 = 0; w0 < n_walkers; w0 += tile) {
     long long wc = (n_walkers - w0 < tile) ? n_walkers - w0 : tile;
     JqWfOut out = {logpsi + w0, sign_tmp + w0, nullptr, nullptr, nullptr};
+    rc = wf_forward(wf, sys, electrons + w0 * 3 * n, wc, 0, ar.base + ar.off, avail, out, st);
+    if (rc) return rc;
+  }
+  return JQ_OK;
+}
+
+static int wf_ndets(const jaqmc_wavefunction* wf) {
+  switch (wf->kind) {
+    case JAQMC_WF_FERMINET: return ((const jaqmc_ferminet_config*)wf->config)->ndets;
+    case JAQMC_WF_LAPNET: return ((const jaqmc_lapnet_config*)wf->config)->ndets;
+    case JAQMC_WF_PSIFORMER: return ((const jaqmc_psiformer_config*)wf->config)->ndets;
+    case JAQMC_WF_SOLID_FERMINET: return ((const jaqmc_solid_config*)wf->config)->net.ndets;
+    default: return 0;
+  }
+}
+
+extern "C" int jaqmc_b200_orbitals(const jaqmc_wavefunction* wf, const jaqmc_system* sys, const float* electrons,
+                                   int64_t n_walkers, float* orbitals, void* workspace, size_t workspace_bytes,
+                                   jaqmc_stream_t stream) {
+  int rc = check_wf(wf);
+  if (rc) return rc;
+  const int D = wf_ndets(wf);
+  JQ_REQUIRE(D > 0, JQ_ERR_UNSUPPORTED, "orbitals: wavefunction kind %d has no orbital matrices", wf->kind);
+  JQ_REQUIRE(n_walkers >= 0 && (n_walkers == 0 || (electrons && orbitals)), JQ_ERR_INVALID_ARGUMENT, "orbitals: null buffer");
+  if (n_walkers == 0) return JQ_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int n = wf_n_electrons(wf);
+  const size_t per_walker = (size_t)D * n * n * (wf->kind == JAQMC_WF_SOLID_FERMINET ? 2 : 1);
+  JqArena ar(workspace, workspace_bytes);
+  float* lp = ar.take<float>(n_walkers);
+  float* sg = ar.take<float>(n_walkers);
+  JQ_REQUIRE(workspace && ar.off <= workspace_bytes, JQ_ERR_WORKSPACE_TOO_SMALL, "orbitals: workspace too small");
+  size_t avail = workspace_bytes - ar.off;
+  long long tile = fit_tile(wf, n_walkers, 0, avail);
+  JQ_REQUIRE(tile >= 1, JQ_ERR_WORKSPACE_TOO_SMALL, "orbitals: workspace of %zu bytes cannot hold one walker", workspace_bytes);
+  for (long long w0 = 0; w0 < n_walkers; w0 += tile) {
+    long long wc = (n_walkers - w0 < tile) ? n_walkers - w0 : tile;
+    JqWfOut out = {lp + w0, sg + w0, nullptr, nullptr, nullptr, orbitals + (size_t)w0 * per_walker};
     rc = wf_forward(wf, sys, electrons + w0 * 3 * n, wc, 0, ar.base + ar.off, avail, out, st);
     if (rc) return rc;
   }
@@ -423,7 +461,7 @@ extern "C" int jaqmc_b200_local_energy_complex(const jaqmc_wavefunction* wf, con
              "local_energy_complex: workspace of %zu bytes cannot hold one walker", workspace_bytes);
   for (long long w0 = 0; w0 < W; w0 += tile) {
     long long wc = (W - w0 < tile) ? W - w0 : tile;
-    JqWfOutC out = {lp_re + w0, lp_im + w0, g + w0 * 3 * n * 2, lpc + w0 * 2, ek + w0 * 2};
+    JqWfOutC out = {lp_re + w0, lp_im + w0, g + w0 * 3 * n * 2, lpc + w0 * 2, ek + w0 * 2, nullptr};
     int rc = jq_solid_forward((const jaqmc_solid_config*)wf->config, (const jaqmc_solid_params*)wf->params, sys,
                               electrons + w0 * 3 * n, wc, 1, ar.base + ar.off, avail, out, st);
     if (rc) return rc;

@@ -44,6 +44,7 @@ JqHeadDims head_dims(const AttnDims& d, int envelope_type, int split, int jastro
   hd.D = d.D;
   hd.C = d.C;
   hd.hidden = d.hid;
+  hd.hidden_valid = 0;
   hd.envelope_type = envelope_type;
   hd.split = split;
   hd.jastrow = jastrow;
@@ -75,7 +76,7 @@ int common_dims(int n_up, int n_dn, int n_atoms, int ndets, int L, int H, int dh
 // LapNet
 // ------------------------------------------------------------------------------------------------
 struct LapBufs {
-  float *feat, *hs_a, *hs_b, *q[JQ_MAX_LAYERS], *k[JQ_MAX_LAYERS], *hd_a, *hd_b, *v, *att, *wscr;
+  float *feat, *hs_a, *hs_b, *q[JQ_MAX_LAYERS], *k[JQ_MAX_LAYERS], *hd_a, *hd_b, *v, *att, *wscr, *ln_s, *ln_d;
   JqHeadBufs head;
 };
 
@@ -92,6 +93,8 @@ void lap_carve(const AttnDims& d, const jaqmc_lapnet_config* c, long long W, JqA
   b->hd_b = ar.take<float>(W * n * d.C * d.hid);
   b->v = ar.take<float>(W * n * d.C * d.hid);
   b->att = ar.take<float>(W * n * d.C * d.hid);
+  b->ln_s = c->use_layernorm ? ar.take<float>(W * n * d.C1 * d.hid) : nullptr;
+  b->ln_d = c->use_layernorm ? ar.take<float>(W * n * d.C * d.hid) : nullptr;
   int nmax = d.hid > d.D * d.n ? d.hid : d.D * d.n;
   b->wscr = ar.take<float>(jq_dense_tc_scratch_floats(d.hid, nmax));
   jq_head_carve(head_dims(d, c->envelope_type, 1, 1), W, ar, &b->head);
@@ -127,7 +130,11 @@ int jq_lapnet_forward(const jaqmc_lapnet_config* c, const jaqmc_lapnet_params* p
     if (l < d.L - 1)
       for (int j = 0; j < c->num_local_updates; ++j)
         JQ_REQUIRE(p->qk_update_kernel[l][j], JQ_ERR_INVALID_ARGUMENT, "lapnet: null qk_update kernel %d/%d", l, j);
+    JQ_REQUIRE(!c->use_layernorm || (p->qk_ln_scale[l] && p->qk_ln_bias[l] && p->value_ln_scale[l] && p->value_ln_bias[l] &&
+                                     p->post_ln_scale[l] && p->post_ln_bias[l]),
+               JQ_ERR_INVALID_ARGUMENT, "lapnet: null LayerNorm parameter in layer %d", l);
   }
+  const float ln_eps = 1e-6f;   // _backbone.py:62-64
   JqArena ar(ws, ws_bytes);
   LapBufs b;
   lap_carve(d, c, W, ar, &b);
@@ -152,9 +159,14 @@ int jq_lapnet_forward(const jaqmc_lapnet_config* c, const jaqmc_lapnet_params* p
     cudaMemcpyAsyncD2D(hd, hs, sizeof(float) * G * hid, st);
   }
   for (int l = 0; l < d.L; ++l) {
-    if ((rc = dense(hs, d.C1, G, n, p->qk_kernel[l], hid, hid, 2 * hid, p->qk_bias[l], 0, nullptr, 0, b.q[l], b.wscr, st)))
+    const float* hs_in = hs;
+    if (c->use_layernorm) {   // project_qk_stream: qk_layernorm first (_backbone.py:121)
+      if ((rc = jq_launch_layernorm_fl(hs, p->qk_ln_scale[l], p->qk_ln_bias[l], b.ln_s, G, d.C1, hid, ln_eps, st))) return rc;
+      hs_in = b.ln_s;
+    }
+    if ((rc = dense(hs_in, d.C1, G, n, p->qk_kernel[l], hid, hid, 2 * hid, p->qk_bias[l], 0, nullptr, 0, b.q[l], b.wscr, st)))
       return rc;
-    if ((rc = dense(hs, d.C1, G, n, p->qk_kernel[l] + hid, hid, hid, 2 * hid, p->qk_bias[l] ? p->qk_bias[l] + hid : nullptr,
+    if ((rc = dense(hs_in, d.C1, G, n, p->qk_kernel[l] + hid, hid, hid, 2 * hid, p->qk_bias[l] ? p->qk_bias[l] + hid : nullptr,
                     0, nullptr, 0, b.k[l], b.wscr, st)))
       return rc;
     if (l < d.L - 1)
@@ -168,15 +180,27 @@ int jq_lapnet_forward(const jaqmc_lapnet_config* c, const jaqmc_lapnet_params* p
       }
   }
   for (int l = 0; l < d.L; ++l) {
-    if ((rc = dense(hd, d.C, G, n, p->value_kernel[l], hid, hid, 0, p->value_bias[l], 0, nullptr, 0, b.v, b.wscr, st)))
+    const float* v_in = hd;
+    if (c->use_layernorm) {   // value_layernorm (_backbone.py:92-95)
+      if ((rc = jq_launch_layernorm_fl(hd, p->value_ln_scale[l], p->value_ln_bias[l], b.ln_d, G, d.C, hid, ln_eps, st)))
+        return rc;
+      v_in = b.ln_d;
+    }
+    if ((rc = dense(v_in, d.C, G, n, p->value_kernel[l], hid, hid, 0, p->value_bias[l], 0, nullptr, 0, b.v, b.wscr, st)))
       return rc;
     JqAttnOperand q = {b.q[l], d.C1, hid, 0}, k = {b.k[l], d.C1, hid, 0}, v = {b.v, d.C, hid, 0};
     if ((rc = jq_launch_attention_fl(q, k, v, b.att, hid, W, n, d.H, d.dh, track, st))) return rc;
     // residual_value = hd + output_projection(att)
     if ((rc = dense(b.att, d.C, G, n, p->output_kernel[l], hid, hid, 0, p->output_bias[l], 0, hd, 2, hd_n, b.wscr, st)))
       return rc;
-    // hd = residual_value + tanh(value_update(residual_value))
-    if ((rc = dense(hd_n, d.C, G, n, p->update_kernel[l], hid, hid, 0, p->update_bias[l], 1, hd_n, 2, hd, b.wscr, st)))
+    // hd = residual_value + tanh(value_update(post_attention_layernorm(residual_value)))   (_backbone.py:105-111)
+    const float* u_in = hd_n;
+    if (c->use_layernorm) {
+      if ((rc = jq_launch_layernorm_fl(hd_n, p->post_ln_scale[l], p->post_ln_bias[l], b.ln_d, G, d.C, hid, ln_eps, st)))
+        return rc;
+      u_in = b.ln_d;
+    }
+    if ((rc = dense(u_in, d.C, G, n, p->update_kernel[l], hid, hid, 0, p->update_bias[l], 1, hd_n, 2, hd, b.wscr, st)))
       return rc;
   }
   return jq_head_forward(head_dims(d, c->envelope_type, 1, p->head.jastrow_alpha_par != nullptr), &p->head, hd,

@@ -10,6 +10,39 @@
 //   only [h_j | g2_j]  (256+64 wide instead of 832 wide for the default network).
 #include "wf.cuh"
 
+// out[w][j][c][:] = [h[w][j][c][0:f1] | m[w][c][0:fm] | g2[w][j][c][0:fg] | 0 ...]   (row length ld)
+__global__ void k_concat_agg(const float* __restrict__ h, const float* __restrict__ m, const float* __restrict__ g2,
+                             float* __restrict__ out, long long rows, int n, int C, int f1, int fm, int fg, int ld) {
+  const long long total = rows * ld;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int col = (int)(i % ld);
+    const long long row = i / ld;          // (w, j, c)
+    float v = 0.f;
+    if (col < f1) {
+      v = h[row * f1 + col];
+    } else if (col < f1 + fm) {
+      const int c = (int)(row % C);
+      const long long w = row / ((long long)C * n);
+      v = m[(w * C + c) * fm + (col - f1)];
+    } else if (col < f1 + fm + fg) {
+      v = g2[row * fg + (col - f1 - fm)];
+    }
+    out[i] = v;
+  }
+}
+
+static int jq_launch_concat_agg(const float* h, const float* m, const float* g2, float* out, long long W, int n, int C,
+                                int f1, int fm, int fg, int ld, cudaStream_t st) {
+  const long long rows = W * n * C;
+  if (rows <= 0) return JQ_OK;
+  int grid = jq_cdiv(rows * ld, 256);
+  if (grid > 148 * 32) grid = 148 * 32;
+  JQ_LAUNCH(k_concat_agg, dim3(grid), dim3(256), 0, st, h, m, g2, out, rows, n, C, f1, fm, fg, ld);
+  JQ_CHECK_LAUNCH();
+  return JQ_OK;
+}
+
 int jq_fermi_dims(const jaqmc_ferminet_config* c, int track, int fat, int fee, FermiDims* o) {
   JQ_REQUIRE(c->n_layers >= 1 && c->n_layers <= JQ_MAX_LAYERS, JQ_ERR_INVALID_ARGUMENT, "ferminet: n_layers=%d",
              c->n_layers);
@@ -34,10 +67,14 @@ int jq_fermi_dims(const jaqmc_ferminet_config* c, int track, int fat, int fee, F
   for (int l = 0; l < o->L; ++l) {
     o->d1[l] = c->hidden_single[l];
     o->d2[l] = c->hidden_double[l];
-    JQ_REQUIRE(o->d1[l] >= 1 && (l == o->L - 1 || o->d2[l] >= 1), JQ_ERR_INVALID_ARGUMENT, "ferminet: hidden dims");
+    JQ_REQUIRE(o->d1[l] >= 1 && ((l == o->L - 1 && !c->use_last_layer) || o->d2[l] >= 1), JQ_ERR_INVALID_ARGUMENT,
+               "ferminet: hidden dims");
     if (o->d1[l] > o->d1max) o->d1max = o->d1[l];
-    if (l < o->L - 1 && o->d2[l] > o->d2max) o->d2max = o->d2[l];
+    if ((l < o->L - 1 || c->use_last_layer) && o->d2[l] > o->d2max) o->d2max = o->d2[l];
   }
+  o->use_last = c->use_last_layer ? 1 : 0;
+  o->agg_w = o->d1[o->L - 1] * (1 + o->nch) + o->nch * o->d2[o->L - 1];
+  o->agg_wp = (o->agg_w + 31) / 32 * 32;
   o->in1 = o->f1 * (1 + o->nch) + fee * o->nch;
   o->in1p = (o->in1 + 31) / 32 * 32;   // layer-1 input row length: zero padded to the tensor-core path's K granularity
   JQ_REQUIRE(o->f1 != o->d1[0], JQ_ERR_UNSUPPORTED,
@@ -51,7 +88,8 @@ static JqHeadDims fermi_head_dims(const FermiDims& d, const jaqmc_ferminet_confi
   hd.A = d.A;
   hd.D = d.D;
   hd.C = d.C;
-  hd.hidden = d.d1[d.L - 1];
+  hd.hidden = d.use_last ? d.agg_wp : d.d1[d.L - 1];
+  hd.hidden_valid = d.use_last ? d.agg_w : 0;
   hd.envelope_type = c->envelope_type;
   hd.split = c->orbitals_spin_split;
   hd.jastrow = 0;
@@ -60,7 +98,7 @@ static JqHeadDims fermi_head_dims(const FermiDims& d, const jaqmc_ferminet_confi
 
 void jq_fermi_carve_backbone(const FermiDims& d, long long W, JqArena& ar, FermiBufs* b) {
   long long n = d.n, nn = (long long)d.n * d.n;
-  bool pairs = d.L > 1;
+  bool pairs = d.L > 1 || d.use_last;
   b->ae = ar.take<float>(W * n * d.C1 * d.f1);
   b->h2a = ar.take<float>(W * nn * d.C2 * d.d2max);
   b->h2b = pairs ? ar.take<float>(W * nn * d.C2 * d.d2max) : nullptr;
@@ -70,8 +108,10 @@ void jq_fermi_carve_backbone(const FermiDims& d, long long W, JqArena& ar, Fermi
   b->hb = ar.take<float>(W * n * d.C * d.d1max);
   b->m = ar.take<float>(W * d.C * d.nch * d.d1max);
   b->cadd = ar.take<float>(W * d.C * d.d1max);
+  b->agg = d.use_last ? ar.take<float>(W * n * d.C * d.agg_wp) : nullptr;
   {
     int kmax = d.d1max * (1 + d.nch) + d.nch * d.d2max;
+    if (d.use_last && d.agg_wp > kmax) kmax = d.agg_wp;
     if (d.in1p > kmax) kmax = d.in1p;
     int nmax = d.d1max > d.D * d.n ? d.d1max : d.D * d.n;
     b->wscr = ar.take<float>(jq_dense_tc_scratch_floats(kmax, nmax));
@@ -90,8 +130,10 @@ int jq_fermi_backbone(const FermiDims& d, const jaqmc_ferminet_params* p, long l
   int rc;
   const int n = d.n, C = d.C;
   for (int l = 0; l < d.L; ++l)
-    JQ_REQUIRE(p->single_kernel[l] && p->single_bias[l] && (l == d.L - 1 || (p->double_kernel[l] && p->double_bias[l])),
+    JQ_REQUIRE(p->single_kernel[l] && p->single_bias[l] &&
+                   ((l == d.L - 1 && !d.use_last) || (p->double_kernel[l] && p->double_bias[l])),
                JQ_ERR_INVALID_ARGUMENT, "ferminet: null parameter in layer %d", l);
+  const int n_double = d.use_last ? d.L : d.L - 1;   // two-electron layers that exist
   float* h2 = b.h2a;
   float* h2n = b.h2b;
   float* h = b.ha;
@@ -156,10 +198,10 @@ int jq_fermi_backbone(const FermiDims& d, const jaqmc_ferminet_params* p, long l
     }
     d1prev = d.d1[l];
 #ifndef JAQMC_HOST_EMU
-    if (l < d.L - 1) {
+    if (l < n_double) {
       // layer + means of its output in one pass over the pair tensor; the last two-electron layer's output is only
       // used through its means and is not written
-      const bool last2 = (l == d.L - 2);
+      const bool last2 = (l == n_double - 1);
       int frc = JQ_OK;
       if (jq_launch_pair_layer_fused(h2, d2prev, p->double_kernel[l], p->double_bias[l], last2 ? nullptr : h2n, b.g2,
                                      (int)W, d.sp, d.d2[l], d2prev == d.d2[l], track, st, &frc)) {
@@ -173,7 +215,7 @@ int jq_fermi_backbone(const FermiDims& d, const jaqmc_ferminet_params* p, long l
       }
     }
 #endif
-    if (l < d.L - 1) {
+    if (l < n_double) {
       JqDenseArgs a2;
       memset(&a2, 0, sizeof(a2));
       a2.src0 = h2;
@@ -200,6 +242,16 @@ int jq_fermi_backbone(const FermiDims& d, const jaqmc_ferminet_params* p, long l
     }
   }
 
+  if (d.use_last) {
+    // use_last_layer: the orbitals see aggregate_features(h_one, h_two) = [h_j | spin means of h | pair means of h_two]
+    // (backbone/ferminet.py:45-47,65-90), materialised once with zero padding to the tensor-core K granularity
+    if (!g2_ready && (rc = jq_launch_pair_mean(h2, b.g2, (int)W, d.sp, d2prev, track, st))) return rc;
+    if ((rc = jq_launch_spin_mean(h, b.m, (int)W, d.sp, C, d1prev, st))) return rc;
+    if ((rc = jq_launch_concat_agg(h, b.m, b.g2, b.agg, W, n, C, d1prev, d.nch * d1prev, d.nch * d2prev, d.agg_wp, st)))
+      return rc;
+    *h_out = b.agg;
+    return JQ_OK;
+  }
   *h_out = h;
   return JQ_OK;
 }

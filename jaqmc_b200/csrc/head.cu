@@ -82,6 +82,41 @@ int jq_launch_jastrow(const float* electrons, const float* alpha_par, const floa
 }
 
 // ------------------------------------------------------------------------------------------------
+// wf.orbitals output: (ndets, n_electrons, n_orbitals) per walker (output/orbital.py:78 transposes the electron-major
+// DenseGeneral output the same way); complex orbitals are written interleaved.
+// ------------------------------------------------------------------------------------------------
+__global__ void k_orbitals_out(const float* __restrict__ in_re, const float* __restrict__ in_im, float* __restrict__ out,
+                               long long total, int n, int D) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int o = (int)(i % n);
+    long long t = i / n;
+    const int e = (int)(t % n);
+    t /= n;
+    const int dd = (int)(t % D);
+    const long long w = t / D;
+    const long long src = ((w * n + e) * D + dd) * n + o;
+    if (in_im) {
+      out[2 * i] = in_re[src];
+      out[2 * i + 1] = in_im[src];
+    } else {
+      out[i] = in_re[src];
+    }
+  }
+}
+
+int jq_launch_orbitals_out(const float* in_re, const float* in_im, float* out, long long W, int n, int D,
+                           cudaStream_t st) {
+  const long long total = W * D * n * n;
+  if (total <= 0) return JQ_OK;
+  int grid = jq_cdiv(total, 256);
+  if (grid > 148 * 16) grid = 148 * 16;
+  JQ_LAUNCH(k_orbitals_out, dim3(grid), dim3(256), 0, st, in_re, in_im, out, total, n, D);
+  JQ_CHECK_LAUNCH();
+  return JQ_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
 // head pipeline
 // ------------------------------------------------------------------------------------------------
 void jq_head_carve(const JqHeadDims& d, long long W, JqArena& ar, JqHeadBufs* b) {
@@ -115,12 +150,13 @@ int jq_head_forward(const JqHeadDims& d, const jaqmc_head_params* p, const float
   // runs over the whole orbital buffer: fuse only when EVERY channel is eligible, decided before anything is launched.
   JqDenseArgs args[2];
   JqEnvFuse ef[2];
-  bool env_fused = track && d.envelope_type != JAQMC_ENVELOPE_NULL;
+  bool env_fused = track && (d.envelope_type == JAQMC_ENVELOPE_ISOTROPIC || d.envelope_type == JAQMC_ENVELOPE_ABS_ISOTROPIC);
   for (int s = 0; s < nchan; ++s) {
     JqDenseArgs& a = args[s];
     memset(&a, 0, sizeof(a));
     a.src0 = h;
     a.k0 = d.hidden;
+    a.k0_valid = d.hidden_valid;
     a.w0 = p->orbital_kernel[s];
     a.bias = p->orbital_bias[s];
     a.out = b.orb;
@@ -162,6 +198,10 @@ int jq_head_forward(const JqHeadDims& d, const jaqmc_head_params* p, const float
   env.sigma[1] = split ? p->env_sigma[1] : nullptr;
   if (!env_fused && (rc = jq_launch_orb_envelope(b.orb, electrons, atoms, env, (int)W, d.sp, d.A, d.D, track, st)))
     return rc;
+  if (out.orbitals) {   // wf.orbitals (pretraining head): the matrices themselves, no determinant
+    JQ_REQUIRE(!track, JQ_ERR_INVALID_ARGUMENT, "head: orbitals are emitted on the value path only");
+    return jq_launch_orbitals_out(b.orb, nullptr, out.orbitals, W, n, d.D, st);
+  }
   if ((rc = jq_launch_logdet(b.orb, (int)W, n, d.D, track, b.det_sign, b.det_logabs, b.det_grad, b.det_lap, st)))
     return rc;
   if (d.jastrow &&

@@ -3,6 +3,7 @@
 //
 // Reference semantics:
 //   * envelope  E_ik = sum_I pi_kI exp(-|sigma_kI| r_iI)          wavefunction/output/envelope.py:98-140
+//     (isotropic: exponent sigma * -r; diagonal: exp(-||sigma_kI (.) r_iI||), sigma (n_orb, A, 3, D), :143-163)
 //   * orbitals * envelope (product rule, Local1 x dense)           app/molecule/wavefunction/ferminet.py:90-93,
 //                                                                  laplacian/primitives/core.py:450-501
 //   * slogdet rule ld_J[k] = tr(A^-1 dA_k), ld_L = tr(A^-1 A_L) - sum_k tr((A^-1 dA_k)^2)
@@ -75,6 +76,26 @@ __global__ void k_orb_envelope(float* __restrict__ orb, const float* __restrict_
     float ex = 0.f, ej[3] = {0.f, 0.f, 0.f}, elap = 0.f;
     for (int I = 0; I < A; ++I) {
       float dx = e[0] - atoms[I * 3], dy = e[1] - atoms[I * 3 + 1], dz = e[2] - atoms[I * 3 + 2];
+      if (env.type == 3) {
+        // diagonal envelope: rho = ||sigma (.) r_vec||, t = pi exp(-rho);
+        //   dt/dx_a = -t sigma_a^2 x_a / rho,   lap t = t (sum_a sigma_a^4 x_a^2 (1/rho^2 + 1/rho^3) - sum_a sigma_a^2 / rho)
+        const float* s3 = sg + ((long long)(i * A + I) * 3) * D + d;
+        const float s0 = s3[0] * s3[0], s1 = s3[D] * s3[D], s2 = s3[2 * D] * s3[2 * D];
+        const float q0 = s0 * dx, q1 = s1 * dy, q2 = s2 * dz;          // sigma_a^2 x_a
+        const float rho = sqrtf(q0 * dx + q1 * dy + q2 * dz);
+        const float t = pi[(i * A + I) * D + d] * expf(-rho);
+        ex += t;
+        if (track) {
+          const float rinv = 1.0f / rho;
+          const float c1 = -t * rinv;
+          ej[0] += c1 * q0;
+          ej[1] += c1 * q1;
+          ej[2] += c1 * q2;
+          const float qq = q0 * q0 + q1 * q1 + q2 * q2;
+          elap += t * (qq * rinv * rinv * (1.0f + rinv) - (s0 + s1 + s2) * rinv);
+        }
+        continue;
+      }
       float r = sqrtf(dx * dx + dy * dy + dz * dz);
       float s, pv;
       if (use_smem) {
@@ -183,7 +204,7 @@ int jq_launch_orb_envelope(float* orb, const float* electrons, const float* atom
   long long items = (long long)W * sp.n() * D * sp.n();
   if (items <= 0) return JQ_OK;
 #ifndef JAQMC_HOST_EMU
-  if (!track && A <= ENVV_A) {
+  if (!track && A <= ENVV_A && env.type != 3) {
     const long long G = (long long)W * sp.n();
     jq_prof_work(0.0, 8.0 * (double)items);
     JQ_LAUNCH(k_orb_envelope_value, dim3((unsigned)jq_cdiv(G, ENVV_GP)), dim3(256), 0, st, orb, electrons, atoms, env, G, sp,
@@ -197,7 +218,7 @@ int jq_launch_orb_envelope(float* orb, const float* electrons, const float* atom
   jq_prof_work(0.0, 8.0 * (double)items * (track ? 3 * sp.n() + 2 : 1));
   const int nch_p = env.pi[1] ? 2 : 1;
   const size_t smem = sizeof(float) * 2 * (size_t)nch_p * A * D * sp.n();
-  const int use_smem = smem <= 40 * 1024;
+  const int use_smem = smem <= 40 * 1024 && env.type != 3;
   JQ_LAUNCH(k_orb_envelope, dim3(grid), dim3(256), use_smem ? smem : 0, st, orb, electrons, atoms, env, items, sp, A, D,
             track, use_smem);
   JQ_CHECK_LAUNCH();

@@ -445,6 +445,9 @@ int jq_solid_forward(const jaqmc_solid_config* c, const jaqmc_solid_params* p, c
   JQ_REQUIRE(sys && sys->atoms && sys->n_atoms == d.A, JQ_ERR_INVALID_ARGUMENT,
              "solid: system must hold the %d primitive-cell atoms", d.A);
   JQ_REQUIRE(p->klist, JQ_ERR_INVALID_ARGUMENT, "solid: null klist");
+  JQ_REQUIRE(!c->net.use_last_layer, JQ_ERR_UNSUPPORTED, "solid: use_last_layer is not implemented");
+  JQ_REQUIRE(c->net.envelope_type != JAQMC_ENVELOPE_DIAGONAL, JQ_ERR_UNSUPPORTED,
+             "solid: the diagonal envelope (6-component tri displacement) is not implemented");
   const bool split = c->net.orbitals_spin_split && d.nch == 2;
   JQ_REQUIRE(p->real_orbital_kernel[0] && p->imag_orbital_kernel[0] &&
                  (!split || (p->real_orbital_kernel[1] && p->imag_orbital_kernel[1])),
@@ -495,6 +498,10 @@ int jq_solid_forward(const jaqmc_solid_config* c, const jaqmc_solid_params* p, c
     JQ_LAUNCH(k_solid_orb_factor, dim3(grid), dim3(256), 0, st, b.orb_r, b.orb_i, electrons, b.r_ae, p->klist, env, items,
               d.sp, d.A, d.D, track);
     JQ_CHECK_LAUNCH();
+  }
+  if (out.orbitals) {   // wf.orbitals: complex matrices, no determinant
+    JQ_REQUIRE(!track, JQ_ERR_INVALID_ARGUMENT, "solid: orbitals are emitted on the value path only");
+    return jq_launch_orbitals_out(b.orb_r, b.orb_i, out.orbitals, W, n, d.D, st);
   }
   {
     int DB = d.D;

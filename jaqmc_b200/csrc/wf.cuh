@@ -9,7 +9,10 @@ struct JqWfOut {
   float* grad;    // [W][3n]   (track only)
   float* lap;     // [W]       (track only)
   float* e_kin;   // [W]       (track only)
+  float* orbitals;  // [W][D][n][n] or null: value path only -- stop after orbitals x envelope and emit the matrices
 };
+// out[w][d][e][o] = in[w][e][d*n + o]  (+ imaginary plane interleaved when in_im != null): the layout of wf.orbitals
+int jq_launch_orbitals_out(const float* in_re, const float* in_im, float* out, long long W, int n, int D, cudaStream_t st);
 
 size_t jq_ferminet_ws_bytes(const jaqmc_ferminet_config* c, long long W, int track);
 int jq_ferminet_forward(const jaqmc_ferminet_config* c, const jaqmc_ferminet_params* p, const jaqmc_system* sys,
@@ -20,6 +23,7 @@ int jq_ferminet_forward(const jaqmc_ferminet_config* c, const jaqmc_ferminet_par
 struct JqHeadDims {
   JqSpins sp;
   int A, D, C, hidden;
+  int hidden_valid;   // 0 (= hidden) or the number of orbital-kernel rows: input columns [hidden_valid, hidden) are zero padding
   int envelope_type, split, jastrow;
 };
 struct JqHeadBufs {
@@ -53,10 +57,11 @@ struct FermiDims {
   int n, A, D, L, nch, C, C1, C2, f1, fee;  // f1 = input features per electron, fee = per pair
   int d1[JQ_MAX_LAYERS], d2[JQ_MAX_LAYERS];  // widths after layer l
   int d1max, d2max, in1, in1p;
+  int use_last, agg_w, agg_wp;   // use_last_layer: aggregated feature width fed to the orbitals (and its padding to 32)
 };
 
 struct FermiBufs {
-  float *ae, *h2a, *h2b, *g2, *x1, *ha, *hb, *m, *cadd, *wscr;
+  float *ae, *h2a, *h2b, *g2, *x1, *ha, *hb, *m, *cadd, *wscr, *agg;
   JqHeadBufs head;
 };
 
@@ -75,6 +80,7 @@ struct JqWfOutC {
   float* grad;       // [W][3n][2]  (track only)
   float* lap;        // [W][2]
   float* e_kin;      // [W][2]
+  float* orbitals;   // [W][D][n][n][2] or null (value path only)
 };
 size_t jq_solid_ws_bytes(const jaqmc_solid_config* c, long long W, int track);
 int jq_solid_forward(const jaqmc_solid_config* c, const jaqmc_solid_params* p, const jaqmc_system* sys,

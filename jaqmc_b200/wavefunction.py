@@ -72,6 +72,16 @@ class Wavefunction:
     def __call__(self, params, data: MoleculeData):
         return self.evaluate(params, data)
 
+    def orbitals(self, params, data: MoleculeData) -> torch.Tensor:
+        """Orbital matrices ``(W, ndets, n, n)`` [or ``(ndets, n, n)`` for one walker] after the envelope -- the
+        pretraining head (reference app/molecule/wavefunction/base.py:60-72, ferminet.py:126-138)."""
+        self._check(data)
+        el, squeeze = _batched(data.electrons)
+        rt = runtime(el.device)
+        wf, sysh = self._sampling_handles(params, data)
+        orb = rt.orbitals(wf, sysh, el, self.ndets)
+        return orb[0] if squeeze else orb
+
     def local_energy(self, params, data: MoleculeData, sums: torch.Tensor | None = None) -> dict:
         """Value, gradient, Laplacian, kinetic / potential / local energy per walker in one pass."""
         self._check(data)
@@ -111,8 +121,6 @@ class FermiNetWavefunction(Wavefunction):
     def __post_init__(self):
         if not self.full_det:
             raise ValueError("FermiNet requires full_det=True.")
-        if self.use_last_layer:
-            raise NotImplementedError("use_last_layer=True is not supported by the CUDA pipeline")
         if len(self.hidden_dims_single) != len(self.hidden_dims_double):
             raise ValueError("hidden_dims_single and hidden_dims_double must have the same length")
 
@@ -139,26 +147,37 @@ class FermiNetWavefunction(Wavefunction):
             h1 = self.hidden_dims_single[layer]
             bb[f"Dense_{idx}"] = {"kernel": lecun(d1 * (1 + nch) + d2 * nch, h1), "bias": torch.zeros(h1, device=dev)}
             idx += 1
-            if layer < L - 1:
+            if layer < L - 1 or self.use_last_layer:
                 h2 = self.hidden_dims_double[layer]
                 bb[f"Dense_{idx}"] = {"kernel": lecun(d2, h2), "bias": torch.zeros(h2, device=dev)}
                 idx += 1
                 d2 = h2
             d1 = h1
+        if self.use_last_layer:
+            d1 = d1 * (1 + nch) + d2 * nch
         split = self.orbitals_spin_split and nch == 2
         if split:
             orb = {"SplitChannelDense_0": {f"DenseGeneral_{s}": {"kernel": lecun(d1, self.ndets, n)} for s in range(2)}}
         else:
             orb = {"DenseGeneral_0": {"kernel": lecun(d1, self.ndets, n)}}
-        ones = lambda: torch.ones(n, A, self.ndets, device=dev)  # noqa: E731
         names = ["_env_up", "_env_down"] if split else ["_env"]
-        env = {nm: {"pi": ones(), "sigma": ones()} for nm in names} if self.envelope != "null" else {}
+        env = _envelope_params(dev, names, n, A, self.ndets, self.envelope)
         return {"params": {"backbone_layer": bb, "orbital_layer": orb, "envelope_layer": env}}
 
     def _handle(self, params, n_atoms: int):
         # rebuilt per call (a few dozen pointer reads): parameter leaves may have been replaced by the optimizer
         return _marshal.ferminet_handle(params, self.nspins, n_atoms, self.ndets, self.hidden_dims_single,
-                                        self.hidden_dims_double, self.envelope, self.orbitals_spin_split)
+                                        self.hidden_dims_double, self.envelope, self.orbitals_spin_split,
+                                        self.use_last_layer)
+
+
+def _envelope_params(dev, names, n, n_atoms, ndets, envelope):
+    """``pi = sigma = 1`` (output/envelope.py:131-135; diagonal: sigma (n_orb, A, 3, D), :150-156)."""
+    if envelope == "null":
+        return {}
+    sshape = (n, n_atoms, 3, ndets) if envelope == "diagonal" else (n, n_atoms, ndets)
+    return {nm: {"pi": torch.ones(n, n_atoms, ndets, device=dev), "sigma": torch.ones(*sshape, device=dev)}
+            for nm in names}
 
 
 def _lecun(g, dev, *shape, fan_in=None):
@@ -178,9 +197,8 @@ def _head_params(g, dev, nspins, n_atoms, ndets, hidden, split, envelope, bias_o
         return d
 
     orb = {"SplitChannelDense_0": {"DenseGeneral_0": dg(), "DenseGeneral_1": dg()}} if split else {"DenseGeneral_0": dg()}
-    ones = lambda: torch.ones(n, n_atoms, ndets, device=dev)  # noqa: E731
     names = ["_env_up", "_env_down"] if split else ["_env"]
-    env = {nm: {"pi": ones(), "sigma": ones()} for nm in names} if envelope != "null" else {}
+    env = _envelope_params(dev, names, n, n_atoms, ndets, envelope)
     out = {"orbital_layer": orb, "envelope_layer": env}
     if jastrow:
         out["jastrow_layer"] = {"alpha_par": torch.full((1,), float(alpha_init), device=dev),
@@ -215,8 +233,6 @@ class LapNetWavefunction(Wavefunction):
             raise ValueError("LapNet requires at least one layer.")
         if self.jastrow not in ("none", "simple_ee"):
             raise ValueError(f"Invalid jastrow: {self.jastrow!r}. Must be one of: ['none', 'simple_ee']")
-        if self.use_layernorm:
-            raise NotImplementedError("use_layernorm=True is not supported by the CUDA pipeline")
 
     def init_params(self, data: MoleculeData, rngs) -> dict:
         """Flax-layout tree (backbone/lapnet/_backbone.py:40-64,169-189): LeCun-normal kernels, N(0,1) biases."""
@@ -240,6 +256,9 @@ class LapNetWavefunction(Wavefunction):
             if l < self.num_layers - 1:
                 for j in range(self.num_local_updates):
                     lp[f"qk_update_layers_{j}"] = dense(hid, hid, self.use_backbone_bias)
+            if self.use_layernorm:
+                for nm in ("qk_layernorm", "value_layernorm", "post_attention_layernorm"):
+                    lp[nm] = {"scale": torch.ones(hid, device=dev), "bias": torch.zeros(hid, device=dev)}
             bb[f"layers_{l}"] = lp
         split = self.nspins[0] > 0 and self.nspins[1] > 0
         tree = {"backbone_layer": bb}
@@ -250,7 +269,7 @@ class LapNetWavefunction(Wavefunction):
     def _handle(self, params, n_atoms: int):
         return _marshal.lapnet_handle(params, self.nspins, n_atoms, self.ndets, self.num_layers, self.num_heads,
                                       self.heads_dim, self.num_local_updates, self.envelope, self.rescale,
-                                      self.jastrow == "simple_ee")
+                                      self.jastrow == "simple_ee", self.use_layernorm)
 
 
 @dataclass
@@ -406,6 +425,14 @@ class SolidWavefunction:
 
     def logpsi(self, params, data):
         return self.evaluate(params, data)["logpsi"]
+
+    def orbitals(self, params, data) -> torch.Tensor:
+        """Complex orbital matrices ``(W, ndets, n, n)`` including envelope and Bloch phase
+        (reference app/solid/wavefunction.py ``get_orbitals`` / ``orbitals``)."""
+        el, squeeze = _batched(data.electrons)
+        wf, sysh = self._sampling_handles(params, data)
+        orb = runtime(el.device).orbitals(wf, sysh, el, self.ndets, complex_valued=True)
+        return orb[0] if squeeze else orb
 
     def phase_logpsi(self, params, data):
         lp = self.logpsi(params, data)

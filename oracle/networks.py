@@ -105,18 +105,21 @@ def ferminet_aggregate(h_one, h_two, nspins):
     return L.cat([h_one, *g_one, *g_two], dim=-1)
 
 
-def fermi_layers(p, h_one, h_two, nspins, n_layers):
-    """``backbone/ferminet.py:29-63`` with ``use_last_layer=False``; Dense_{2l} single, Dense_{2l+1} double."""
+def fermi_layers(p, h_one, h_two, nspins, n_layers, use_last_layer=False):
+    """``backbone/ferminet.py:29-63``; Dense_{2l} single, Dense_{2l+1} double.  ``use_last_layer=True`` also updates
+    the double stream in the last layer and returns the aggregated features (``:45-47``)."""
     idx = 0
     for layer in range(n_layers):
         d = p[f"Dense_{idx}"]
         idx += 1
         h_in = ferminet_aggregate(h_one, h_two, nspins)
         h_one = _residual(h_one, L.tanh(L.dense(h_in, d["kernel"], d["bias"])))
-        if layer < n_layers - 1:
+        if layer < n_layers - 1 or use_last_layer:
             d = p[f"Dense_{idx}"]
             idx += 1
             h_two = _residual(h_two, L.tanh(L.dense(h_two, d["kernel"], d["bias"])))
+    if use_last_layer:
+        return ferminet_aggregate(h_one, h_two, nspins), h_two
     return h_one, h_two
 
 
@@ -219,19 +222,20 @@ def simple_ee_jastrow(p, r_ee, nspins):
 # ---------------------------------------------------------------------------------------
 # FermiNet
 # ---------------------------------------------------------------------------------------
-def ferminet_orbitals(params, electrons, atoms, nspins, envelope_type="abs_isotropic"):
+def ferminet_orbitals(params, electrons, atoms, nspins, envelope_type="abs_isotropic", use_last_layer=False):
     """``(ndets, n, n)`` orbital matrices (``app/molecule/wavefunction/ferminet.py:110-138`` ``orbitals``)."""
     p = params["params"]
     n_layers = (len(p["backbone_layer"]) + 1) // 2
     emb = molecule_features(electrons, atoms, rescale=False)
-    h_one, _ = fermi_layers(p["backbone_layer"], emb["ae_features"], emb["ee_features"], nspins, n_layers)
+    h_one, _ = fermi_layers(p["backbone_layer"], emb["ae_features"], emb["ee_features"], nspins, n_layers,
+                            use_last_layer)
     orb = orbital_projection(p["orbital_layer"], h_one, nspins)
     return _apply_envelope(orb, p, emb, nspins, envelope_type)
 
 
-def ferminet_logpsi(params, electrons, atoms, nspins, envelope_type="abs_isotropic"):
+def ferminet_logpsi(params, electrons, atoms, nspins, envelope_type="abs_isotropic", use_last_layer=False):
     """``app/molecule/wavefunction/ferminet.py:76-108`` -> ``(sign, logpsi)``."""
-    return logdet_sum(ferminet_orbitals(params, electrons, atoms, nspins, envelope_type))
+    return logdet_sum(ferminet_orbitals(params, electrons, atoms, nspins, envelope_type, use_last_layer))
 
 
 # ---------------------------------------------------------------------------------------
@@ -266,7 +270,8 @@ def attention_core(q, k, v):
 # LapNet
 # ---------------------------------------------------------------------------------------
 def lapnet_backbone(p, ae_features, nspins, heads):
-    """``backbone/lapnet/_backbone.py:191-263`` (``use_layernorm=False`` default)."""
+    """``backbone/lapnet/_backbone.py:191-263``.  ``use_layernorm=True`` shows up as three extra sub-trees per layer
+    (``qk_layernorm``, ``value_layernorm``, ``post_attention_layernorm``, epsilon 1e-6, ``:62-64,81-111,121``)."""
     n_up, n_dn = nspins
     n = n_up + n_dn
     num_layers = sum(1 for k in p if k.startswith("layers_"))
@@ -278,7 +283,8 @@ def lapnet_backbone(p, ae_features, nspins, heads):
     qks = []
     for li in range(num_layers):
         lp = p[f"layers_{li}"]
-        qk = L.dense(hs, lp["qk_projection"]["kernel"], lp["qk_projection"].get("bias"))
+        hs_in = layer_norm(lp["qk_layernorm"], hs, 1e-6) if "qk_layernorm" in lp else hs
+        qk = L.dense(hs_in, lp["qk_projection"]["kernel"], lp["qk_projection"].get("bias"))
         half = qk.shape[-1] // 2
         qks.append((qk[:, :half], qk[:, half:]))
         j = 0
@@ -289,13 +295,15 @@ def lapnet_backbone(p, ae_features, nspins, heads):
     for li in range(num_layers):
         lp = p[f"layers_{li}"]
         q, k = qks[li]
-        v = L.dense(hd, lp["value_projection"]["kernel"], lp["value_projection"].get("bias"))
+        v_in = layer_norm(lp["value_layernorm"], hd, 1e-6) if "value_layernorm" in lp else hd
+        v = L.dense(v_in, lp["value_projection"]["kernel"], lp["value_projection"].get("bias"))
         dh = q.shape[-1] // heads
         rs = lambda t: L.reshape(t, n, heads, dh)  # noqa: E731
         att = L.reshape(attention_core(rs(q), rs(k), rs(v)), n, heads * dh)
         att = L.dense(att, lp["output_projection"]["kernel"], lp["output_projection"].get("bias"))
         res = hd + att
-        hd = res + L.tanh(L.dense(res, lp["value_update"]["kernel"], lp["value_update"].get("bias")))
+        res_n = layer_norm(lp["post_attention_layernorm"], res, 1e-6) if "post_attention_layernorm" in lp else res
+        hd = res + L.tanh(L.dense(res_n, lp["value_update"]["kernel"], lp["value_update"].get("bias")))
     return hd
 
 

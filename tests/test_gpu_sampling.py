@@ -90,7 +90,7 @@ def test_mh_accept_decisions_n2_full_network_tensor_core_path():
     assert 0.1 < acc_ref.float().mean() < 0.95   # the test exercises both outcomes
     assert int(n_acc) == int(accepted.sum())
     np.testing.assert_allclose(e32.cpu()[same].numpy(), x_ref.float()[same].numpy(), atol=1e-6)
-    np.testing.assert_allclose(logpsi.cpu()[same].numpy(), (0.5 * lp_ref)[same].numpy(), atol=3e-5)
+    np.testing.assert_allclose(logpsi.cpu()[same].numpy(), (0.5 * lp_ref)[same].numpy(), rtol=5e-6, atol=0)
 
 
 def test_mh_step_pbc_matches_oracle():
