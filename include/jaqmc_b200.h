@@ -332,6 +332,25 @@ int jaqmc_b200_mh_propose(const float* x1, const float* normals, const float* st
 int jaqmc_b200_mh_accept(float* x1, const float* x2, float* logprob1, const float* logprob2, const float* uniforms,
                          int64_t n_walkers, int32_t row, float* n_accept, uint8_t* accepted, jaqmc_stream_t stream);
 
+/* ---- parameter leaves -> descriptor structs -----------------------------------------------------------------------
+ * An XLA-FFI handler receives the parameters as a flat operand list in `jax.tree.leaves(params)` order (dictionary
+ * keys sorted at every level; reference trees: SURVEY.md Appendix B / tests/golden/ref_*.npz).  These three functions
+ * are the single definition of that order for every wavefunction kind (host-only code, no CUDA calls):
+ *   param_leaf_count  -> number of leaves of (kind, config), or -1;
+ *   param_leaf_info   -> path ("params/backbone_layer/Dense_0/bias"), element count and shape of leaf `index`;
+ *   bind_param_leaves -> writes leaves[i] into the field of `params` that leaf i belongs to, after checking count and
+ *                        element counts (leaf_elements may be NULL to skip the size check).
+ * Optional leaves (biases, Jastrow) exist or not depending on the reference class's flags; the caller states which
+ * exist by pre-setting these fields of `params` to any non-NULL value before the call: input_bias, qk_bias[l] (all
+ * backbone biases of LapNet layer l), q_bias[l] (with_bias, Psiformer layer l), head.orbital_bias[0],
+ * head.jastrow_alpha_par.  All other fields are outputs.  `params` is the kind's params struct; for the periodic
+ * network `klist` is not a parameter (module attribute) and stays the caller's to set. */
+int jaqmc_b200_param_leaf_count(int32_t kind, const void* config, void* params);
+int jaqmc_b200_param_leaf_info(int32_t kind, const void* config, void* params, int32_t index, char* path,
+                               size_t path_cap, int64_t* n_elements, int32_t* rank, int64_t* dims);
+int jaqmc_b200_bind_param_leaves(int32_t kind, const void* config, void* params, const float* const* leaves,
+                                 const int64_t* leaf_elements, int32_t n_leaves);
+
 /* Number of kernels the library has launched on this thread since the last reset (bench.py's gpu_launches). */
 int64_t jaqmc_b200_launch_count(void);
 void jaqmc_b200_reset_launch_count(void);

@@ -243,6 +243,16 @@ PROTOTYPES = {
         C.c_int,
         [FloatP, FloatP, FloatP, FloatP, FloatP, C.c_int64, C.c_int32, FloatP, C.c_void_p, C.c_void_p],
     ),
+    "jaqmc_b200_param_leaf_count": (C.c_int, [C.c_int32, C.c_void_p, C.c_void_p]),
+    "jaqmc_b200_param_leaf_info": (
+        C.c_int,
+        [C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_char_p, C.c_size_t, C.POINTER(C.c_int64),
+         C.POINTER(C.c_int32), C.POINTER(C.c_int64)],
+    ),
+    "jaqmc_b200_bind_param_leaves": (
+        C.c_int,
+        [C.c_int32, C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.c_int32],
+    ),
     "jaqmc_b200_launch_count": (C.c_int64, []),
     "jaqmc_b200_reset_launch_count": (None, []),
     "jaqmc_b200_profile_enable": (None, [C.c_int]),
