@@ -3,17 +3,24 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload n2|li|...]
 
-A *step* is one local-energy evaluation (forward-Laplacian kinetic + Coulomb potential + total) of the whole walker
-batch of the named system -- the estimator half of the reference's ``EvaluationWorkStage.compute_step``
-(workflow/stage/evaluation.py:190-192).  The walker batch is global (4096, the reference's ``workflow.batch_size``)
-and sharded over the ranks: strong scaling, as ``docs/guide/multi-device.md:25-29`` defines it.
+A *step* is ``evals_per_step`` (default 32 for the FermiNet workloads, 4 for the heavier ones; recorded in ``config``)
+consecutive local-energy evaluations (forward-Laplacian kinetic + Coulomb potential + total) of the whole walker batch
+of the named system -- the estimator half of the reference's ``EvaluationWorkStage.compute_step``
+(workflow/stage/evaluation.py:190-192) -- so that the timed region stays above a second at 8 GPUs too (one evaluation
+of the 512-walker shard takes 2 ms).  The walker batch is global (4096, the reference's ``workflow.batch_size``) and
+sharded over the ranks: strong scaling, as ``docs/guide/multi-device.md:25-29`` defines it.
 
-``value``   walkers * K / device time, inputs resident in HBM (max over ranks, CUDA events on the launch stream).
+``value``   walkers * evals_per_step * K / device time, inputs resident in HBM (max over ranks, CUDA events on the
+            launch stream); ``ms_per_eval`` is the time of one evaluation of the batch.
 ``e2e``     the same metric through the public API (``FermiNetWavefunction.local_energy``) with the step's electrons
             copied from pinned host memory and the per-walker local energies read back, inside the timed region.
 ``roofline``the dominant kernel's achieved algorithmic throughput against the measured peak (MEASURED_PEAKS.json).
 ``cpu_baseline`` / ``--impl reference``: the float32 ``torch.func.vmap`` port of the reference's CPU path
-            (oracle/, vmapped forward-Laplacian + potential) on the host cores, on a bounded sample of the workload.
+            (oracle/, vmapped forward-Laplacian + potential) on the host cores; a step of that arm is a bounded SAMPLE of
+            the workload (the walkers it actually evaluated are in ``cpu_baseline.sample`` and ``ms_per_step`` is the time
+            of that sample, not an extrapolation).  The port carries dense 3n-wide Jacobians through the pair stream where
+            the reference's interpreter keeps them 6 wide (Local2): it does several times the reference's FLOPs there and
+            is a lower bound on the reference's JAX-CPU throughput.
 """
 
 from __future__ import annotations
@@ -67,6 +74,17 @@ def make_wavefunction(name, nspins):
     return FermiNetWavefunction(nspins=nspins, ndets=ndets, hidden_dims_single=list(hs), hidden_dims_double=list(hd))
 METRIC = "local_energy_evals_per_sec"
 UNIT = "evals/s"
+
+
+def workload_string(name, walkers):
+    """``config.workload``: identical in both arms."""
+    kind = workload_kind(name)
+    what = "forward-Laplacian kinetic + Ewald potential" if kind == "solid" else "forward-Laplacian local energy"
+    return f"{WORKLOADS[name][4]}, {walkers} walkers, {what}"
+
+
+def default_evals_per_step(name):
+    return 32 if workload_kind(name) == "ferminet" else 4
 
 
 def load_peaks():
@@ -131,24 +149,27 @@ def run_reference(args):
     if workload_kind(args.workload) == "solid":
         print(json.dumps({"impl": "reference", "unavailable": "no vmapped CPU port of the periodic network (float64 oracle only)"}))
         return
-    # K steps, each a bounded sample sized so the whole run ends within a few minutes
+    # K steps, each a bounded sample of the workload sized so that the whole run ends within a few minutes; the line
+    # reports what actually ran: ms_per_step is the time of one sample, value = walkers evaluated / time
     per_step = max(2.0, min(20.0, 120.0 / max(1, args.steps + args.warmup)))
-    rates, total = [], 0
+    rates, total, secs = [], 0, 0.0
     for i in range(args.warmup + args.steps):
         r, done, threads = cpu_rate(args.workload, per_step)
         if i >= args.warmup:
             rates.append(r)
             total += done
-    value = float(np.mean(rates))
-    mol, ndets, hs, hd, desc = WORKLOADS[args.workload][:5]
+            secs += done / r
+    value = total / secs
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 * args.walkers / value, "higher_is_better": True, "scaling": "strong",
+        "warmup": args.warmup, "ms_per_step": 1e3 * secs / max(1, args.steps), "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{desc}, {args.walkers} walkers, forward-Laplacian local energy"},
+        "config": {"workload": workload_string(args.workload, args.walkers),
+                   "step": f"bounded sample: {total // max(1, args.steps)} walkers of the workload per step"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
-                         "sample": f"{total} walkers in chunks of 64 (torch.func.vmap float32 port of the reference "
-                                   f"graph; jax/jaxlib are not installable offline), scaled per walker"},
+                         "sample": f"{total} walkers in chunks of 64 over {args.steps} steps (torch.func.vmap float32 "
+                                   f"port of the reference graph with dense Jacobians -- jax/jaxlib are not installable "
+                                   f"offline; a lower bound on the reference's sparse-Jacobian JAX-CPU path)"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -282,17 +303,25 @@ def run_ours_solid(args, dev, world, rank, dist):
             ms = float(t)
         return ms
 
+    R = args.evals_per_step or default_evals_per_step(args.workload)
+
+    def repeat(fn):
+        def many():
+            for _ in range(R):
+                fn()
+        return many
+
     for _ in range(max(3, args.warmup)):
         step_resident()
     clocks = ClockSampler(int(os.environ.get("LOCAL_RANK", "0")))
     if rank == 0:
         clocks.start()
     rt.reset_launch_count()
-    ms = timed(step_resident, args.steps)
+    ms = timed(repeat(step_resident), args.steps)
     launches = rt.launch_count()
     clk = clocks.stop() if rank == 0 else None
     step_e2e()
-    ms_e2e = timed(step_e2e, args.steps)
+    ms_e2e = timed(repeat(step_e2e), args.steps)
     finite = bool(torch.isfinite(e_host).all())
     kernels = None
     if rank == 0:
@@ -310,14 +339,16 @@ def run_ours_solid(args, dev, world, rank, dist):
         kernels = {k: {"launches": v["launches"], "share": round(v["ms"] / tot_ms, 4),
                        "ms_per_launch": round(v["ms"] / v["launches"], 4)} for k, v in kernels.items()}
         line = {
-            "metric": METRIC, "value": round(W * args.steps / (ms * 1e-3), 1), "unit": UNIT, "n_gpus": world,
+            "metric": METRIC, "value": round(W * R * args.steps / (ms * 1e-3), 1), "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": round(ms / args.steps, 4),
+            "ms_per_eval": round(ms / args.steps / R, 4),
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32 / complex64", "data": "synthetic",
-            "config": {"workload": f"{desc}, {W} walkers global ({Wl}/GPU), forward-Laplacian kinetic + Ewald potential",
-                       "parallelism": f"walkers sharded over {world} GPU(s); all-reduce of 3 floats per step",
+            "config": {"workload": workload_string(args.workload, W), "walkers_per_gpu": Wl, "evals_per_step": R,
+                       "step": f"{R} consecutive evaluations of the {W}-walker batch",
+                       "parallelism": f"walkers sharded over {world} GPU(s); all-reduce of 3 floats per evaluation",
                        "launch": "kernel by kernel"},
-            "e2e": {"value": round(W * args.steps / (ms_e2e * 1e-3), 1), "unit": UNIT,
-                    "h2d_bytes_per_step": int(Wl * n * 3 * 4) * world, "d2h_bytes_per_step": int(Wl * 4) * world,
+            "e2e": {"value": round(W * R * args.steps / (ms_e2e * 1e-3), 1), "unit": UNIT,
+                    "h2d_bytes_per_step": int(Wl * n * 3 * 4) * world * R, "d2h_bytes_per_step": int(Wl * 4) * world * R,
                     "finite": finite},
             "gpu_launches": int(launches), "clocks": clk, "roofline": None, "kernels": kernels,
         }
@@ -417,25 +448,33 @@ def run_ours(args):
             ms = float(t)
         return ms
 
+    R = args.evals_per_step or default_evals_per_step(args.workload)   # evaluations of the batch per step
+
+    def repeat(fn):
+        def many():
+            for _ in range(R):
+                fn()
+        return many
+
     for _ in range(max(3, args.warmup)):
-        step_resident()
+        repeat(step_resident)()
     clocks = ClockSampler(local_rank)
     if rank == 0:
         clocks.start()
     rt.reset_launch_count()
-    ms = timed(step_resident, args.steps)
+    ms = timed(repeat(step_resident), args.steps)
     launches = rt.launch_count()
     if use_graph:  # replays do not pass through the launcher: count the kernels of one captured evaluation
         rt.reset_launch_count()
         wf.local_energy(params, data, sums=sums)
-        launches = rt.launch_count() * args.steps
+        launches = rt.launch_count() * args.steps * R
     clk = clocks.stop() if rank == 0 else None
-    value = W * args.steps / (ms * 1e-3)
+    value = W * R * args.steps / (ms * 1e-3)
 
     for _ in range(2):
         step_e2e()
-    ms_e2e = timed(step_e2e, args.steps)
-    e2e_value = W * args.steps / (ms_e2e * 1e-3)
+    ms_e2e = timed(repeat(step_e2e), args.steps)
+    e2e_value = W * R * args.steps / (ms_e2e * 1e-3)
     finite = bool(torch.isfinite(e_host).all())
 
     # second half of the BASELINE metric: sampling + energy part of one VMC iteration (workflow/stage/vmc.py:227-265):
@@ -493,19 +532,36 @@ def run_ours(args):
         if os.path.exists(tpath):
             with open(tpath) as f:
                 traffic = json.load(f).get(f"{kname}@{args.workload}@{W // world}", {}).get("dram_bytes")
-        if v["flops"] > 0:
-            # 3xTF32: three tensor-core products per multiply-add; TF32 runs at half the bf16 rate
-            peak = peaks["bf16_tflops_sustained"] / 2.0 / 3.0
+        tensor_kernel = kname.startswith("k_dense_tc")
+        if v["flops"] > 0 and tensor_kernel:
+            # 3xTF32: three tensor-core products per multiply-add; TF32 runs at half the bf16 rate.  The kernel is timed
+            # launch by launch with CUDA events (a burst, not a long saturated run): the burst figure is the denominator;
+            # the fraction of the sustained figure is given next to it
+            peak = peaks["bf16_tflops"] / 2.0 / 3.0
+            peak_sus = peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"]) / 2.0 / 3.0
             ach = v["flops"] / (v["ms"] * 1e-3) / 1e12
+            note = ("executed FLOPs of the restructured FermiNet layer (320-wide contraction + per-walker addend), not "
+                    "the reference's 832-wide formulation" if workload_kind(args.workload) == "ferminet" else
+                    "executed FLOPs of one Dense layer over all (value, Jacobian, Laplacian) rows")
             roof = {"kernel": kname, "bound": "tensor", "achieved": round(ach, 3), "peak": round(peak, 1),
-                    "unit": "TFLOP/s", "frac": round(ach / peak, 4), "traffic": traffic,
-                    "peak_source": f"{src}: bf16_tflops_sustained / 2 (tf32) / 3 (split products)",
+                    "unit": "TFLOP/s", "frac": round(ach / peak, 4), "frac_burst": round(ach / peak, 4),
+                    "frac_sustained": round(ach / peak_sus, 4), "traffic": traffic,
+                    "peak_source": f"{src}: bf16_tflops (burst) / 2 (tf32) / 3 (split products); frac_sustained uses "
+                                   f"bf16_tflops_sustained",
                     "launches_per_step": v["launches"] // min(args.steps, 3), "ms_per_launch": round(per_launch_ms, 4),
                     "flops_per_launch": v["flops"] / v["launches"], "bytes_per_launch": v["bytes"] / v["launches"],
                     "hbm_gbs": round(v["bytes"] / (v["ms"] * 1e-3) / 1e9, 1),
-                    "share_of_step": round(v["ms"] / tot_ms, 4),
-                    "note": "executed FLOPs of the restructured layer (320-wide contraction + per-walker addend), "
-                            "not the reference's 832-wide formulation"}
+                    "share_of_step": round(v["ms"] / tot_ms, 4), "note": note}
+        elif v["flops"] > 0:
+            # CUDA-core FP32 contraction (attention / LogDet kernels): against the split-precision tensor peak, which
+            # is where the north star wants these contractions
+            peak = peaks["bf16_tflops"] / 2.0 / 3.0
+            ach = v["flops"] / (v["ms"] * 1e-3) / 1e12
+            roof = {"kernel": kname, "bound": "tensor", "achieved": round(ach, 3), "peak": round(peak, 1),
+                    "unit": "TFLOP/s", "frac": round(ach / peak, 4), "traffic": traffic,
+                    "peak_source": f"{src}: bf16_tflops / 2 / 3", "ms_per_launch": round(per_launch_ms, 4),
+                    "flops_per_launch": v["flops"] / v["launches"], "share_of_step": round(v["ms"] / tot_ms, 4),
+                    "note": "FP32 CUDA-core kernel measured against the split-precision tensor-core peak"}
         else:
             ach = v["bytes"] / (v["ms"] * 1e-3) / 1e9
             roof = {"kernel": kname, "bound": "hbm", "achieved": round(ach, 1), "peak": peaks["hbm_gbs"], "unit": "GB/s",
@@ -524,14 +580,16 @@ def run_ours(args):
         ws_gb = rt.workspace_bytes(wf._handle(params, atoms.shape[0]), Wl, True) / 1e9
         line = {
             "metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": max(3, args.warmup), "ms_per_step": round(ms / args.steps, 4), "higher_is_better": True,
+            "warmup": max(3, args.warmup), "ms_per_step": round(ms / args.steps, 4),
+            "ms_per_eval": round(ms / args.steps / R, 4), "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"{desc}, {W} walkers global ({Wl}/GPU), forward-Laplacian local energy",
-                       "l2": f"no flush: each step streams a {ws_gb:.1f} GB working set (>> 126 MB L2) per GPU",
-                       "parallelism": f"walkers sharded over {world} GPU(s); all-reduce of 3 floats per step",
-                       "launch": "one CUDA-graph replay per step" if use_graph else "kernel by kernel"},
-            "e2e": {"value": round(e2e_value, 1), "unit": UNIT, "h2d_bytes_per_step": int(Wl * n * 3 * 4) * world,
-                    "d2h_bytes_per_step": int(Wl * 4) * world, "finite": finite},
+            "config": {"workload": workload_string(args.workload, W), "walkers_per_gpu": Wl, "evals_per_step": R,
+                       "step": f"{R} consecutive evaluations of the {W}-walker batch",
+                       "l2": f"no flush: each evaluation streams a {ws_gb:.1f} GB working set (>> 126 MB L2) per GPU",
+                       "parallelism": f"walkers sharded over {world} GPU(s); all-reduce of 3 floats per evaluation",
+                       "launch": "one CUDA-graph replay per evaluation" if use_graph else "kernel by kernel"},
+            "e2e": {"value": round(e2e_value, 1), "unit": UNIT, "h2d_bytes_per_step": int(Wl * n * 3 * 4) * world * R,
+                    "d2h_bytes_per_step": int(Wl * 4) * world * R, "finite": finite},
             "gpu_launches": int(launches), "clocks": clk, "roofline": roof, "kernels": kernels,
         }
         if vmc is not None:
@@ -551,6 +609,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="n2", choices=sorted(WORKLOADS))
     ap.add_argument("--walkers", type=int, default=4096, help="global walker batch (reference workflow.batch_size)")
+    ap.add_argument("--evals-per-step", type=int, default=0,
+                    help="evaluations of the walker batch per timed step (0: 32 for FermiNet workloads, 4 otherwise)")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch the kernels one by one instead of replaying a CUDA graph")

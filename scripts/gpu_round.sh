@@ -21,8 +21,8 @@ echo "== bench" ; timeout 900 python bench.py --steps ${STEPS:-5} --warmup 3 > $
 for WL in $EXTRA_WORKLOADS; do
   echo "== bench $WL" ; timeout 900 python bench.py --steps 3 --warmup 3 --workload $WL --cpu-seconds 8 > $OUT/bench_$WL.json 2> $OUT/bench_$WL.err ; echo "bench exit $?" ; tail -3 $OUT/bench_$WL.err ; cat $OUT/bench_$WL.json
 done
-echo "== ncu launch list" ; timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file $OUT/launches.csv python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-equilibrate --no-graph --no-vmc > $OUT/ncu_bench.log 2>&1 ; echo "ncu exit $?"
+echo "== ncu launch list" ; timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file $OUT/launches.csv python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-equilibrate --no-graph --no-vmc --evals-per-step 1 > $OUT/ncu_bench.log 2>&1 ; echo "ncu exit $?"
 if [ -n "$KREGEX" ]; then
-  echo "== ncu full $KREGEX" ; timeout 900 ncu --set full --clock-control none --import-source on -k regex:$KREGEX -s $KSKIP -c 2 -o $OUT/prof python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-equilibrate --no-graph --no-vmc --walkers ${NCU_WALKERS:-4096} > $OUT/ncu_full.log 2>&1 ; echo "ncu full exit $?"; tail -3 $OUT/ncu_full.log
+  echo "== ncu full $KREGEX" ; timeout 900 ncu --set full --clock-control none --import-source on -k regex:$KREGEX -s $KSKIP -c 2 -o $OUT/prof python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-equilibrate --no-graph --no-vmc --evals-per-step 1 --walkers ${NCU_WALKERS:-4096} > $OUT/ncu_full.log 2>&1 ; echo "ncu full exit $?"; tail -3 $OUT/ncu_full.log
 fi
 ls -la $OUT

@@ -41,6 +41,10 @@ def main():
     raw = list(csv.reader(io.StringIO(ncu(["-i", rep, "--page", "raw", "--csv"]))))
     hdr, units, body = raw[0], raw[1], raw[2:]
     ix = {h: i for i, h in enumerate(hdr)}
+    # every tensor-pipe counter the report holds (names differ between ncu versions / metric sets)
+    for h in hdr:
+        if ("pipe_tensor" in h or "pipe_tc" in h or "tcgen" in h.lower()) and h not in METRICS:
+            METRICS.append(h)
     out.append("| launch | " + " | ".join(m for m in METRICS if m in ix) + " |")
     out.append("|---|" + "---|" * sum(m in ix for m in METRICS))
     for r in body:
