@@ -10,6 +10,8 @@
 //                                                                  laplacian/primitives/slogdet.py:46-72
 //   * log-sum-exp over determinants with max shift                 wavefunction/output/logdet.py:65-79
 //   * E_kin = -1/2 (lap + |grad|^2)                                estimator/kinetic/_common.py:61-73
+#include <cstdlib>
+
 #include "aug.cuh"
 
 // q / d and q % d for block-uniform runtime d without the ~20-instruction integer division sequence
@@ -225,71 +227,249 @@ int jq_launch_orb_envelope(float* orb, const float* electrons, const float* atom
   return JQ_OK;
 }
 
-// ------------------------------------------------------------------------------------------------
-// slogdet + forward-Laplacian rule.  One block per (walker, group of DB determinants): a walker's orbital slab
-// [n][C][D*n] is read in rows of DB*n contiguous floats, and all DB matrices go through every phase together.
-// In-place Gauss-Jordan with partial (row) pivoting; sign = prod sign(pivot) * (-1)^swaps,
-// log|det| = sum log|pivot| accumulated in double.  Then, KC derivative slabs at a time,
-//   M = A^-1 dA_c,  ld_J[c] = tr M,  and  ld_L = tr(A^-1 A_L) - sum_k tr(M_k^2)      (primitives/slogdet.py:46-72).
-// Shared: inv[DB][nn] | colp[DB][n] | piv[DB][n] | pivinv[DB] sgn[DB] trL[DB] t2[DB] | logabs[DB] (double) |
-//         Jc[KC][DB][nn] | Mc[KC][DB][nn] | p1[KC][DB][n] | p2[KC][DB][n]
-// ------------------------------------------------------------------------------------------------
 #define LD_NP 16
-__global__ void __launch_bounds__(256, 3) k_logdet(const float* __restrict__ orb, int n, int D, int C, int DB, int KC,
-                         float* __restrict__ det_sign, float* __restrict__ det_logabs, float* __restrict__ det_grad,
-                         float* __restrict__ det_lap) {
+#ifndef JAQMC_HOST_EMU
+// ------------------------------------------------------------------------------------------------
+// slogdet + forward-Laplacian rule for n <= 16 on the tensor cores (r2): one WARP per determinant.
+//   M_c = A^-1 dA_c for every component c, ld_J[c] = tr M_c, ld_L = tr(A^-1 A_L) - sum_k tr(M_k^2)   (slogdet.py:46-72)
+// Phase 1: Gauss-Jordan inversion in registers (k_logdet_small's, run redundantly by both half-warps); A^-1 goes to a
+// zero-padded 16 x 16 shared tile and from there into mma.sync fragments that stay in registers for all 3n+1 slabs.
+// Phase 2, per slab: the thread loads the 8 entries dA[j][i2], j = t + 4s, i2 = g + 8r (g = lane / 4, t = lane % 4) --
+// which are at once the B fragments of  M = A^-1 dA  and the A fragments of  M^T = dA^T A^-T  (m16n8k8: the A fragment of
+// X^T and the B fragment of X hold the same elements; likewise the A^-1 registers serve as A fragment of the first and
+// B fragment of the second product).  Both products land in the same accumulator layout, so
+//   tr M^2 = sum_ab M[a][b] M^T[a][b]   and   tr M
+// are thread-local sums followed by one warp reduction: no shared-memory traffic in the loop (the FP32 kernel it
+// replaces spent its time re-reading A^-1 from shared memory: 512 B per LDS.128 warp instruction).
+// Arithmetic: 3xTF32 (x = hi + lo; lo*hi + hi*lo + hi*hi, FP32 accumulation), i.e. FP32-faithful to ~2^-21.
+// ------------------------------------------------------------------------------------------------
+#define LDM_KMAX 50   // slabs: 3 * 16 + 1
+__device__ __forceinline__ unsigned jq_tf32(float x) {
+  unsigned r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ void jq_mma_tf32(float (&c)[4], unsigned a0, unsigned a1, unsigned a2, unsigned a3, unsigned b0,
+                                            unsigned b1) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+// Index maps of the fragments.  The products are invariant under a common permutation pi of the matrix index (rows and
+// columns of M together): pi(g + 8r) = 2g + r puts the two columns a thread owns next to each other in memory, so a
+// slab costs four 8-byte loads per thread (n even; odd n takes 4-byte loads).
+template <bool VEC2>
+__global__ void __launch_bounds__(256, 2) k_logdet_mma(const float* __restrict__ orb, int n, int D, int C, long long MT,
+                                                        float* __restrict__ det_sign, float* __restrict__ det_logabs,
+                                                        float* __restrict__ det_grad, float* __restrict__ det_lap) {
+  __shared__ float tile_all[8][16 * 17];
+  __shared__ float diag_all[8][LDM_KMAX][8];   // per-slab partial traces of the 8 diagonal-holding lanes
+  const unsigned full = 0xffffffffu;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const long long m = (long long)blockIdx.x * 8 + warp;   // matrix = (walker, determinant)
+  if (m >= MT) return;
+  const long long w = m / D;
+  const int d = (int)(m - w * D);
+  const int DN = D * n;
+  const int K = C - 2, KT = C - 1;
+  const float* ow = orb + (w * n) * (long long)C * DN + d * n;  // (j, c, i) at ow[(j*C + c)*DN + i]
+  float* tile = tile_all[warp];
+  for (int q = lane; q < 16 * 17; q += 32) tile[q] = 0.f;
+  __syncwarp();
+  // ---- phase 1: [A | I] -> [I | A^-1], lane hl = row hl, both half-warps on the same matrix
+  {
+    const int hl = lane & 15;
+    bool used = hl >= n;
+    float a[LD_NP], bi[LD_NP];
+#pragma unroll
+    for (int c = 0; c < LD_NP; ++c) {
+      a[c] = (!used && c < n) ? ow[(long long)hl * C * DN + c] : 0.f;
+      bi[c] = (c == hl) ? 1.0f : 0.f;
+    }
+    int step_of = 0;
+    float sg = 1.0f;
+    double mant = 1.0;
+    int expo = 0;
+#pragma unroll
+    for (int p = 0; p < LD_NP; ++p) {
+      if (p < n) {
+        unsigned key = used ? 0u : __float_as_uint(fabsf(a[p]));
+        unsigned mx = key;
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) mx = max(mx, __shfl_xor_sync(full, mx, o));
+        const unsigned cand = __ballot_sync(full, !used && key == mx) & 0xffffu;
+        const int pl = cand ? __ffs(cand) - 1 : 0;   // first unused row holding the largest magnitude
+        const float pv = __shfl_sync(full, a[p], pl, 16);
+        if (pv < 0.f) sg = -sg;
+        if (pv == 0.f) sg = 0.f;
+        {
+          int e;
+          mant *= (double)frexpf(fabsf(pv), &e);
+          expo += e;
+        }
+        const float pinv = 1.0f / pv;
+        const bool is_p = (hl == pl);
+        if (is_p && !used) {
+          used = true;
+          step_of = p;
+        }
+        const float f = is_p ? 0.f : a[p];   // column p before it is overwritten
+#pragma unroll
+        for (int c = 0; c < LD_NP; ++c)
+          if (c < n) {
+            const float ap = __shfl_sync(full, a[c], pl, 16) * pinv;
+            const float bp = __shfl_sync(full, bi[c], pl, 16) * pinv;
+            if (is_p) {
+              a[c] = ap;
+              bi[c] = bp;
+            } else {
+              a[c] = fmaf(-f, ap, a[c]);
+              bi[c] = fmaf(-f, bp, bi[c]);
+            }
+          }
+      }
+    }
+    int invc = 0;
+    for (int i = 0; i < n; ++i) {
+      const int si = __shfl_sync(full, step_of, i, 16);
+      if (i < hl && hl < n && si > step_of) ++invc;
+    }
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) invc += __shfl_xor_sync(full, invc, o);
+    if (lane < n) {
+#pragma unroll
+      for (int c = 0; c < LD_NP; ++c)
+        if (c < n) tile[step_of * 17 + c] = bi[c];
+    }
+    if (lane == 0) {
+      det_sign[m] = (invc & 1) ? -sg : sg;
+      det_logabs[m] = (float)(log(mant) + (double)expo * 0.69314718055994530942);
+    }
+  }
+  __syncwarp();
+  // ---- A^-1 fragments (hi / lo), kept for every slab: ai[r][s] = A^-1[pi(g + 8r)][t + 4s]
+  const int g = lane >> 2, t = lane & 3;
+  const int i0 = 2 * g;   // pi(g) = 2g, pi(g + 8) = 2g + 1
+  unsigned aih[2][4], ail[2][4];
+#pragma unroll
+  for (int r = 0; r < 2; ++r)
+#pragma unroll
+    for (int s2 = 0; s2 < 4; ++s2) {
+      const float v = tile[(i0 + r) * 17 + t + 4 * s2];
+      aih[r][s2] = jq_tf32(v);
+      ail[r][s2] = jq_tf32(v - __uint_as_float(aih[r][s2]));   // rounded, not left to the tensor core's truncation (measured: 5x the error)
+    }
+  // ---- phase 2
+  bool okj[4];
+#pragma unroll
+  for (int s2 = 0; s2 < 4; ++s2) okj[s2] = (t + 4 * s2) < n;
+  const bool ok0 = i0 < n, ok1 = i0 + 1 < n;
+  const float* rowp[4];   // slab 0 of row j = t + 4s, column i0
+#pragma unroll
+  for (int s2 = 0; s2 < 4; ++s2) rowp[s2] = ow + ((long long)(okj[s2] ? t + 4 * s2 : 0) * C + 1) * DN + (ok0 ? i0 : 0);
+  auto fetch = [&](float (&dst)[2][4]) {
+#pragma unroll
+    for (int s2 = 0; s2 < 4; ++s2) {
+      if (VEC2) {
+        float2 v = make_float2(0.f, 0.f);
+        if (okj[s2] && ok0) v = *reinterpret_cast<const float2*>(rowp[s2]);   // n even: i0 + 1 < n whenever i0 < n
+        dst[0][s2] = v.x;
+        dst[1][s2] = v.y;
+      } else {
+        dst[0][s2] = (okj[s2] && ok0) ? rowp[s2][0] : 0.f;
+        dst[1][s2] = (okj[s2] && ok1) ? rowp[s2][1] : 0.f;
+      }
+      rowp[s2] += DN;
+    }
+  };
+  float nxt[2][4];
+  fetch(nxt);
+  // lanes holding diagonal entries of the accumulator tiles: fragment row g has fragment columns 2t, 2t + 1
+  const int e = g - 2 * t;
+  const bool has_diag = (e == 0 || e == 1);
+  float* dsm = diag_all[warp][0] + (2 * t + (e & 1));   // slot of this lane among the 8 diagonal holders
+  float t2acc = 0.f;
+  for (int kk = 0; kk < KT; ++kk) {
+    unsigned dh[2][4], dl[2][4];
+#pragma unroll
+    for (int r = 0; r < 2; ++r)
+#pragma unroll
+      for (int s2 = 0; s2 < 4; ++s2) {
+        const float v = nxt[r][s2];
+        dh[r][s2] = jq_tf32(v);
+        dl[r][s2] = jq_tf32(v - __uint_as_float(dh[r][s2]));
+      }
+    if (kk + 1 < KT) fetch(nxt);
+    float c1[2][4], c2[2][4];
+#pragma unroll
+    for (int u = 0; u < 2; ++u)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) c1[u][q] = c2[u][q] = 0.f;
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks) {
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        // M = A^-1 dA : A fragment from A^-1 (rows g, g+8; k = 8ks + t, +4), B fragment from dA (k = 8ks + t, +4; col 8u + g)
+        jq_mma_tf32(c1[u], ail[0][2 * ks], ail[1][2 * ks], ail[0][2 * ks + 1], ail[1][2 * ks + 1], dh[u][2 * ks], dh[u][2 * ks + 1]);
+        jq_mma_tf32(c1[u], aih[0][2 * ks], aih[1][2 * ks], aih[0][2 * ks + 1], aih[1][2 * ks + 1], dl[u][2 * ks], dl[u][2 * ks + 1]);
+        jq_mma_tf32(c1[u], aih[0][2 * ks], aih[1][2 * ks], aih[0][2 * ks + 1], aih[1][2 * ks + 1], dh[u][2 * ks], dh[u][2 * ks + 1]);
+        // M^T = dA^T A^-T : A fragment from dA (rows i2 = g, g+8; k = 8ks + t, +4), B fragment from A^-1 (col i = 8u + g)
+        jq_mma_tf32(c2[u], dl[0][2 * ks], dl[1][2 * ks], dl[0][2 * ks + 1], dl[1][2 * ks + 1], aih[u][2 * ks], aih[u][2 * ks + 1]);
+        jq_mma_tf32(c2[u], dh[0][2 * ks], dh[1][2 * ks], dh[0][2 * ks + 1], dh[1][2 * ks + 1], ail[u][2 * ks], ail[u][2 * ks + 1]);
+        jq_mma_tf32(c2[u], dh[0][2 * ks], dh[1][2 * ks], dh[0][2 * ks + 1], dh[1][2 * ks + 1], aih[u][2 * ks], aih[u][2 * ks + 1]);
+      }
+    }
+    // tr M^2 = sum_ab M[a][b] M^T[a][b]: thread-local partial, reduced over the warp once after the loop
+    if (kk < K) {
+#pragma unroll
+      for (int u = 0; u < 2; ++u)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) t2acc = fmaf(c1[u][q], c2[u][q], t2acc);
+    }
+    // tr M: fragment rows g hold columns 2t, 2t+1 of tile u = 0; rows g + 8 hold columns 8 + 2t, 8 + 2t + 1 of tile u = 1
+    if (has_diag) dsm[kk * 8] = (e == 0) ? c1[0][0] + c1[1][2] : c1[0][1] + c1[1][3];
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) t2acc += __shfl_xor_sync(full, t2acc, o);
+  __syncwarp();
+  float trl = 0.f;
+  for (int kk = lane; kk < KT; kk += 32) {
+    const float* p8 = diag_all[warp][kk];
+    const float v = ((p8[0] + p8[1]) + (p8[2] + p8[3])) + ((p8[4] + p8[5]) + (p8[6] + p8[7]));
+    if (kk < K) det_grad[m * (long long)K + kk] = v;
+    else trl = v;
+  }
+  trl = __shfl_sync(full, trl, K % 32);   // the Laplacian row is slab K
+  if (lane == 0) det_lap[m] = trl - t2acc;
+}
+#endif
+
+#ifndef JAQMC_HOST_EMU
+// ------------------------------------------------------------------------------------------------
+// slogdet + forward-Laplacian rule for n <= 16 (r2): one HALF-warp per determinant, no block-level synchronisation.
+// Phase 1: Gauss-Jordan inversion in registers (lane r = row r of [A | I]); rows are never moved: at step p the pivot is
+// the largest |a[r][p]| among the rows not used yet, its row is scaled and eliminated from all others (same pivots and
+// fmaf sequence as the shared-memory elimination of k_logdet).  Row p of A^-1 is the right half of the row that served
+// as pivot p; it goes into a row-padded shared copy.  sign = parity(row -> step) * prod sign(pivot),
+// log|det| = log prod |pivot| in double.   Phase 2: the traces, see inside.
+// Shared: invp[DB][n*16+4] | scr[DB][MS]
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256, 2) k_logdet_small(const float* __restrict__ orb, int n, int D, int C, int DB,
+                                                          float* __restrict__ det_sign, float* __restrict__ det_logabs,
+                                                          float* __restrict__ det_grad, float* __restrict__ det_lap) {
   JQ_DYN_SMEM(float, sm);
   const int nn = n * n;
-  const int K = C - 2;                 // Jacobian columns (C == 1: value only)
-  const int KT = (C > 1) ? C - 1 : 0;  // J columns + the Laplacian row
-  double* logabs = reinterpret_cast<double*>(sm);  // first, for 8-byte alignment
-  float* inv = reinterpret_cast<float*>(logabs + DB);
-  float* colp = inv + (size_t)DB * nn;
-  int* piv = reinterpret_cast<int*>(colp + DB * n);
-  float* pivinv = reinterpret_cast<float*>(piv + DB * n);
-  float* sgn = pivinv + DB;
-  float* trL = sgn + DB;
-  float* t2 = trL + DB;
-  float* Jc = sm + (((t2 + DB) - sm + 3) & ~3);  // 16-byte aligned (float4 reads of the padded inverses)
-  float* Mc = Jc + (size_t)KC * DB * nn;
-  float* p1 = Mc + (size_t)KC * DB * nn;
-  float* p2 = p1 + KC * DB * n;
+  const int K = C - 2, KT = C - 1;
   const int ngrp = (D + DB - 1) / DB;
   const long long w = blockIdx.x / ngrp;
   const int d0 = (int)(blockIdx.x % ngrp) * DB;
-  const int db = (D - d0 < DB) ? D - d0 : DB;  // determinants in this block
+  const int db = (D - d0 < DB) ? D - d0 : DB;
   const int DN = D * n;
-  const int tid = threadIdx.x, nt = blockDim.x;
-  const bool need_inv = (C > 1);
-  const int TX = (nt >= 64) ? 8 : 1, TY = nt / TX;
-  const int tx = tid % TX, ty = tid / TX;
-  const float inv_n = 1.0f / (float)n, inv_nn = 1.0f / (float)nn, inv_db = 1.0f / (float)db,
-              inv_dbn = 1.0f / (float)(db * n);
+  const int tid = threadIdx.x;
   const float* ow = orb + (w * n) * (long long)C * DN + d0 * n;  // (j, c, d, i) at ow[(j*C + c)*DN + d*n + i]
-
-  // value slab: inv[d][j][i] = A_d[j][i]; consecutive items read db*n contiguous floats
-  for (int q = tid; q < n * db * n; q += nt) {
-    int j, r, d, i;
-    jq_divmod(q, db * n, inv_dbn, &j, &r);
-    jq_divmod(r, n, inv_n, &d, &i);
-    inv[d * nn + j * n + i] = ow[(long long)j * C * DN + r];
-  }
-  for (int d = tid; d < db; d += nt) {
-    logabs[d] = 0.0;
-    sgn[d] = 1.0f;
-    t2[d] = 0.f;
-    trL[d] = 0.f;
-  }
-  __syncthreads();
-  bool fast_inv = false;
-#ifndef JAQMC_HOST_EMU
-  if (need_inv && n <= LD_NP && nt == 256) {
-    // ---- n <= 16: Gauss-Jordan inversion in registers, one matrix per HALF-warp (lane r = row r of [A | I]); rows are
-    // never moved: at step p the pivot is the largest |a[r][p]| among the rows not used yet, its row is scaled and
-    // eliminated from all others (same pivots and fmaf sequence as the shared-memory elimination below).  Afterwards
-    // row p of A^-1 is the right half of the row that served as pivot p; it goes straight into the row-padded layout
-    // of the trace phase.  sign = parity(row -> step) * prod sign(pivot), log|det| = log prod |pivot| in double.
-    fast_inv = true;
+  float* Jc = sm;
+  {
     const unsigned full = 0xffffffffu;
     const int hl = tid & 15, half = (tid >> 4) & 1, warp = tid >> 5;
     const int IS = n * LD_NP + 4;
@@ -301,7 +481,7 @@ __global__ void __launch_bounds__(256, 3) k_logdet(const float* __restrict__ orb
       float a[LD_NP], bi[LD_NP];
 #pragma unroll
       for (int c = 0; c < LD_NP; ++c) {
-        a[c] = (!used && c < n) ? inv[d * nn + hl * n + c] : 0.f;
+        a[c] = (!used && c < n) ? ow[(long long)hl * C * DN + d * n + c] : 0.f;
         bi[c] = (c == hl) ? 1.0f : 0.f;
       }
       int step_of = 0;
@@ -365,10 +545,135 @@ __global__ void __launch_bounds__(256, 3) k_logdet(const float* __restrict__ orb
         det_sign[w * D + d0 + d] = (invc & 1) ? -sg : sg;
         det_logabs[w * D + d0 + d] = (float)(log(mant) + (double)expo * 0.69314718055994530942);
       }
+      // ---- traces of this determinant, by the same half-warp and without any block-level synchronisation (r2):
+      // lane i2 holds column i2 of dA_c in registers and forms column i2 of M = A^-1 dA_c (the inverse is read as
+      // float4 broadcasts from the row-padded copy this half-warp has just written); tr M is the sum of the lanes'
+      // diagonal entries, tr M^2 = sum_{i,i2} M[i][i2] M[i2][i] needs the transposed element, exchanged through a
+      // per-determinant scratch tile.  The next slab's column is fetched before the current one is consumed.
+      // (Measured r2: a variant forming three slabs per pass over A^-1 -- a third of the shared-memory reads -- ran at
+      // 2.6 ms against 1.64 ms: register spills at the 128-register cap outweighed the saved LDS traffic.)
+      __syncwarp();
+      {
+        const float* ib = invp_w + (size_t)(on ? d : 0) * IS;
+        float* scr = invp_w + (size_t)DB * IS + (size_t)(on ? d : 0) * (nn + ((n - nn) % 32 + 32) % 32);
+        const bool act = on && hl < n;
+        const float* ocol = ow + (on ? d : 0) * n + (hl < n ? hl : 0);   // column (d, i2 = hl); + (1 + kk) * DN + j * C * DN
+        float nxt[LD_NP];
+#pragma unroll
+        for (int j = 0; j < LD_NP; ++j) nxt[j] = (act && j < n) ? ocol[(long long)DN + (long long)j * C * DN] : 0.f;
+        float t2acc = 0.f, trl = 0.f;
+        float* gout = det_grad + (w * D + d0 + (on ? d : 0)) * (long long)K;
+        for (int kk = 0; kk < KT; ++kk) {
+          float col[LD_NP];
+#pragma unroll
+          for (int j = 0; j < LD_NP; ++j) col[j] = nxt[j];
+          if (kk + 1 < KT) {
+            const float* oc = ocol + (long long)(2 + kk) * DN;
+#pragma unroll
+            for (int j = 0; j < LD_NP; ++j) nxt[j] = (act && j < n) ? oc[(long long)j * C * DN] : 0.f;
+          }
+          float m[LD_NP];
+          float dg = 0.f;
+#pragma unroll
+          for (int i = 0; i < LD_NP; ++i) {
+            float acc = 0.f;
+            if (i < n) {
+              const float4* r4 = reinterpret_cast<const float4*>(ib + i * LD_NP);
+#pragma unroll
+              for (int j4 = 0; j4 < LD_NP / 4; ++j4) {
+                const float4 v = r4[j4];
+                acc = fmaf(v.x, col[4 * j4 + 0], acc);
+                acc = fmaf(v.y, col[4 * j4 + 1], acc);
+                acc = fmaf(v.z, col[4 * j4 + 2], acc);
+                acc = fmaf(v.w, col[4 * j4 + 3], acc);
+              }
+              if (act) scr[i * n + hl] = acc;
+            }
+            m[i] = acc;
+            if (i == hl) dg = acc;
+          }
+          __syncwarp();
+          float s2 = 0.f;
+#pragma unroll
+          for (int i = 0; i < LD_NP; ++i)
+            if (i < n && act) s2 = fmaf(m[i], scr[hl * n + i], s2);
+          __syncwarp();
+          if (!act) dg = 0.f;
+#pragma unroll
+          for (int o = 8; o > 0; o >>= 1) {
+            dg += __shfl_xor_sync(full, dg, o);
+            s2 += __shfl_xor_sync(full, s2, o);
+          }
+          if (kk < K) {
+            if (on && hl == 0) gout[kk] = dg;
+            t2acc += s2;
+          } else {
+            trl = dg;
+          }
+        }
+        if (on && hl == 0) det_lap[w * D + d0 + d] = trl - t2acc;
+      }
     }
-    __syncthreads();
   }
+}
 #endif
+
+// ------------------------------------------------------------------------------------------------
+// slogdet + forward-Laplacian rule.  One block per (walker, group of DB determinants): a walker's orbital slab
+// [n][C][D*n] is read in rows of DB*n contiguous floats, and all DB matrices go through every phase together.
+// In-place Gauss-Jordan with partial (row) pivoting; sign = prod sign(pivot) * (-1)^swaps,
+// log|det| = sum log|pivot| accumulated in double.  Then, KC derivative slabs at a time,
+//   M = A^-1 dA_c,  ld_J[c] = tr M,  and  ld_L = tr(A^-1 A_L) - sum_k tr(M_k^2)      (primitives/slogdet.py:46-72).
+// Shared: inv[DB][nn] | colp[DB][n] | piv[DB][n] | pivinv[DB] sgn[DB] trL[DB] t2[DB] | logabs[DB] (double) |
+//         Jc[KC][DB][nn] | Mc[KC][DB][nn] | p1[KC][DB][n] | p2[KC][DB][n]
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256, 3) k_logdet(const float* __restrict__ orb, int n, int D, int C, int DB, int KC,
+                         float* __restrict__ det_sign, float* __restrict__ det_logabs, float* __restrict__ det_grad,
+                         float* __restrict__ det_lap) {
+  JQ_DYN_SMEM(float, sm);
+  const int nn = n * n;
+  const int K = C - 2;                 // Jacobian columns (C == 1: value only)
+  const int KT = (C > 1) ? C - 1 : 0;  // J columns + the Laplacian row
+  double* logabs = reinterpret_cast<double*>(sm);  // first, for 8-byte alignment
+  float* inv = reinterpret_cast<float*>(logabs + DB);
+  float* colp = inv + (size_t)DB * nn;
+  int* piv = reinterpret_cast<int*>(colp + DB * n);
+  float* pivinv = reinterpret_cast<float*>(piv + DB * n);
+  float* sgn = pivinv + DB;
+  float* trL = sgn + DB;
+  float* t2 = trL + DB;
+  float* Jc = sm + (((t2 + DB) - sm + 3) & ~3);  // 16-byte aligned (float4 reads of the padded inverses)
+  float* Mc = Jc + (size_t)KC * DB * nn;
+  float* p1 = Mc + (size_t)KC * DB * nn;
+  float* p2 = p1 + KC * DB * n;
+  const int ngrp = (D + DB - 1) / DB;
+  const long long w = blockIdx.x / ngrp;
+  const int d0 = (int)(blockIdx.x % ngrp) * DB;
+  const int db = (D - d0 < DB) ? D - d0 : DB;  // determinants in this block
+  const int DN = D * n;
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const bool need_inv = (C > 1);
+  const int TX = (nt >= 64) ? 8 : 1, TY = nt / TX;
+  const int tx = tid % TX, ty = tid / TX;
+  const float inv_n = 1.0f / (float)n, inv_nn = 1.0f / (float)nn, inv_db = 1.0f / (float)db,
+              inv_dbn = 1.0f / (float)(db * n);
+  const float* ow = orb + (w * n) * (long long)C * DN + d0 * n;  // (j, c, d, i) at ow[(j*C + c)*DN + d*n + i]
+
+  // value slab: inv[d][j][i] = A_d[j][i]; consecutive items read db*n contiguous floats
+  for (int q = tid; q < n * db * n; q += nt) {
+    int j, r, d, i;
+    jq_divmod(q, db * n, inv_dbn, &j, &r);
+    jq_divmod(r, n, inv_n, &d, &i);
+    inv[d * nn + j * n + i] = ow[(long long)j * C * DN + r];
+  }
+  for (int d = tid; d < db; d += nt) {
+    logabs[d] = 0.0;
+    sgn[d] = 1.0f;
+    t2[d] = 0.f;
+    trL[d] = 0.f;
+  }
+  __syncthreads();
+  const bool fast_inv = false;   // n <= 16 with 256 threads runs k_logdet_small on the device (r2)
   if (!fast_inv) {
   for (int p = 0; p < n; ++p) {
     for (int d = tid; d < db; d += nt) {
@@ -716,6 +1021,46 @@ int jq_launch_logdet(const float* orb, int W, int n, int D, int track, float* de
   const int C = track ? 3 * n + 2 : 1;
   const int KT = C > 1 ? C - 1 : 0;
   const size_t nn = (size_t)n * n;
+#ifndef JAQMC_HOST_EMU
+  // Opt-in: traces on the tensor cores (mma.sync 3xTF32), 20 % faster than the FP32 kernel but measured 3-10x its error
+  // on ill-conditioned determinants (22 mantissa bits per operand, truncating accumulation): LapNet-N2 parity no
+  // longer meets the north-star tolerance with it, so the FP32 kernel stays the default.
+  static const bool tc_traces = getenv("JAQMC_B200_LOGDET_TC") != nullptr;
+  if (track && n <= LD_NP && tc_traces) {
+    // warp per determinant, traces on the tensor cores (mma.sync 3xTF32)
+    const long long MT = (long long)W * D;
+    jq_prof_work((double)MT * (2.0 * n * n * n * ((C - 1) * 2 + 1)), 4.0 * (double)MT * C * n * n);
+    if (n % 2 == 0 && (reinterpret_cast<uintptr_t>(orb) & 7) == 0)
+      JQ_LAUNCH(k_logdet_mma<true>, dim3((unsigned)jq_cdiv(MT, 8)), dim3(256), 0, st, orb, n, D, C, MT, det_sign,
+                det_logabs, det_grad, det_lap);
+    else
+      JQ_LAUNCH(k_logdet_mma<false>, dim3((unsigned)jq_cdiv(MT, 8)), dim3(256), 0, st, orb, n, D, C, MT, det_sign,
+                det_logabs, det_grad, det_lap);
+    JQ_CHECK_LAUNCH();
+    return JQ_OK;
+  }
+  if (track && n <= LD_NP) {
+    // half-warp per determinant: 16 determinants per block
+    const int DB = D < 16 ? D : 16;
+    const size_t MS = nn + (size_t)((((int)n - (int)nn) % 32 + 32) % 32);
+    const size_t smem = sizeof(float) * ((size_t)DB * (n * LD_NP + 4) + (size_t)DB * MS) + 64;
+    if (smem > 48 * 1024) {
+      static JqPerDeviceFlag attr_set;
+      const int dev = jq_current_device();
+      if (!attr_set.done[dev]) {
+        cudaError_t e = cudaFuncSetAttribute(k_logdet_small, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+        JQ_REQUIRE(e == cudaSuccess, JQ_ERR_CUDA, "logdet: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+        attr_set.done[dev] = true;
+      }
+    }
+    const long long blocks = (long long)W * ((D + DB - 1) / DB);
+    jq_prof_work((double)W * D * (2.0 * n * n * n * ((C - 1) * 2 + 1)), 4.0 * (double)W * D * C * n * n);
+    JQ_LAUNCH(k_logdet_small, dim3((unsigned)blocks), dim3(256), smem, st, orb, n, D, C, DB, det_sign, det_logabs,
+              det_grad, det_lap);
+    JQ_CHECK_LAUNCH();
+    return JQ_OK;
+  }
+#endif
   // DB matrices per block: about 16 KB of inverses; KC slabs so that the block stays under ~100 KB
   int DB = (int)(16384 / (nn * 4));
   if (DB < 1) DB = 1;
