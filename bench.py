@@ -502,7 +502,26 @@ def run_ours(args):
         ms_vmc = timed(vmc_iteration, k_vmc)
         vmc = {"iters_per_sec": round(k_vmc / (ms_vmc * 1e-3), 2), "ms_per_iter": round(ms_vmc / k_vmc, 3),
                "what": "10 MH sub-steps + 1 forward-Laplacian local-energy evaluation of all walkers "
-                       "(no parameter gradients / optimizer: those stay in JAX)"}
+                       "(no parameter gradients / optimizer)"}
+        if workload_kind(args.workload) == "ferminet" and n <= 16:
+            # + LossAndGrad (estimator/loss_grad.py:70-128): MAD clipping, one reverse pass, all-reduce of the gradient --
+            # everything of VMCWorkStage.compute_step (workflow/stage/vmc.py:227-265) except the optimizer update
+            from jaqmc_b200.estimator import LossAndGrad
+
+            lag = LossAndGrad(f_log_psi=wf)
+
+            def vmc_iteration_grad():
+                vmc_iteration()
+                e = graph_out["e_loc"] if use_graph else wf.local_energy(params, vmc_data)["e_loc"]
+                return lag.evaluate(params, vmc_data, {"total_energy": e})
+
+            for _ in range(2):
+                vmc_iteration_grad()
+            ms_g = timed(vmc_iteration_grad, k_vmc)
+            vmc["with_loss_and_grad"] = {
+                "iters_per_sec": round(k_vmc / (ms_g * 1e-3), 2), "ms_per_iter": round(ms_g / k_vmc, 3),
+                "what": "the above + LossAndGrad (clipped-energy-weighted parameter gradient by one reverse pass, "
+                        "all-reduced over the GPUs): VMCWorkStage.compute_step without the optimizer update"}
 
     # roofline leg: per-kernel CUDA events on the launch stream over the same steps (rank 0 only)
     roof, kernels = None, None

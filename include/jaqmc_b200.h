@@ -82,6 +82,18 @@ typedef struct {
   const float* env_sigma[2];
 } jaqmc_ferminet_params;
 
+/* Gradient buffers of the FermiNet parameters: same leaves and shapes as jaqmc_ferminet_params, DEVICE pointers the
+ * library writes (jaqmc_b200_ferminet_logpsi_vjp). */
+typedef struct {
+  float* single_kernel[JAQMC_MAX_LAYERS];
+  float* single_bias[JAQMC_MAX_LAYERS];
+  float* double_kernel[JAQMC_MAX_LAYERS];
+  float* double_bias[JAQMC_MAX_LAYERS];
+  float* orbital_kernel[2];
+  float* env_pi[2];
+  float* env_sigma[2];
+} jaqmc_ferminet_grads;
+
 /* ---- shared output head: orbitals x envelope -> LogDet (+ Jastrow) ----------------------------
  * OrbitalProjection (wavefunction/output/orbital.py:59-78), Envelope (output/envelope.py:98-140),
  * SimpleEEJastrow (wavefunction/jastrow.py:47-122). */
@@ -285,6 +297,21 @@ int jaqmc_b200_local_energy_complex(const jaqmc_wavefunction* wf, const jaqmc_sy
                                     const float* electrons, int64_t n_walkers, float* logpsi, float* grad, float* lap,
                                     float* e_kin, float* e_pot, float* e_loc, float* sums, void* workspace,
                                     size_t workspace_bytes, jaqmc_stream_t stream);
+
+/* Parameter-gradient path.  Replaces the per-walker `jax.value_and_grad(wf.logpsi)` of
+ * LossAndGrad.evaluate_single_walker and the contraction with the clipped local energies of LossAndGrad.reduce /
+ * finalize_stats (estimator/loss_grad.py:70-128) by ONE reverse pass: the VJP of theta -> vmap(log|psi|)(theta, walkers),
+ *   grads[leaf] = sum_w cotangent[w] * d log|psi|(x_w) / d leaf        (every leaf of `grads` is OVERWRITTEN),
+ * so that LossAndGrad's `grads` is the call with cotangent[w] = 2 (E_clip[w] - mean E_clip) / W and the mean score the
+ * call with 1 / W; the W x P per-walker score tensor of the reference is never formed.  Also returns log|psi| / sign of
+ * the walkers (either may be NULL).  FermiNet kind, n <= 16 electrons, isotropic / abs_isotropic / null envelope.
+ * Needs the whole workspace of jaqmc_b200_ferminet_vjp_workspace_bytes (activations are kept; no walker tiling).
+ * Results are bit-reproducible (row reductions are split and summed in a fixed order). */
+size_t jaqmc_b200_ferminet_vjp_workspace_bytes(const jaqmc_ferminet_config* config, int64_t n_walkers);
+int jaqmc_b200_ferminet_logpsi_vjp(const jaqmc_ferminet_config* config, const jaqmc_ferminet_params* params,
+                                   const jaqmc_system* sys, const float* electrons, int64_t n_walkers,
+                                   const float* cotangent, const jaqmc_ferminet_grads* grads, float* logpsi, float* sign,
+                                   void* workspace, size_t workspace_bytes, jaqmc_stream_t stream);
 
 /* Replaces potential_energy (app/molecule/hamiltonian.py:9-22) vmapped over walkers. */
 int jaqmc_b200_coulomb(const jaqmc_system* sys, const float* electrons, int64_t n_walkers, int32_t n_electrons,

@@ -233,6 +233,12 @@ PROTOTYPES = {
         C.c_int,
         [C.POINTER(Wavefunction), C.POINTER(System), FloatP, C.c_int64, FloatP, C.c_void_p, C.c_size_t, C.c_void_p],
     ),
+    "jaqmc_b200_ferminet_vjp_workspace_bytes": (C.c_size_t, [C.POINTER(FerminetConfig), C.c_int64]),
+    "jaqmc_b200_ferminet_logpsi_vjp": (
+        C.c_int,
+        [C.POINTER(FerminetConfig), C.POINTER(FerminetParams), C.POINTER(System), FloatP, C.c_int64, FloatP,
+         C.POINTER(FerminetParams), FloatP, FloatP, C.c_void_p, C.c_size_t, C.c_void_p],
+    ),
     "jaqmc_b200_dense_fl": (
         C.c_int,
         [FloatP, FloatP, FloatP, FloatP, FloatP, FloatP, FloatP, FloatP, C.c_int64, C.c_int32, C.c_int32, C.c_int32,

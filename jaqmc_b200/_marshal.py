@@ -122,7 +122,9 @@ def ferminet_handle(params, nspins, n_atoms, ndets, hidden_dims_single, hidden_d
     wf.kind = _abi.WF_FERMINET
     wf.config = C.cast(C.pointer(cfg), C.c_void_p)
     wf.params = C.cast(C.pointer(ps), C.c_void_p)
-    return Handle(wf, keep)
+    h = Handle(wf, keep)
+    h.config_struct, h.params_struct = cfg, ps   # typed views (parameter-gradient entry point)
+    return h
 
 
 class _Binder:

@@ -251,6 +251,28 @@ class Runtime:
         return replay
 
     @_on_device
+    def ferminet_logpsi_vjp(self, wf, grads_handle, system, electrons, cotangent):
+        """``sum_w cotangent[w] d log|psi|(x_w) / d theta`` into the leaves behind ``grads_handle`` (a ``ferminet_handle``
+        built on a tree of gradient buffers); returns ``(logpsi (W,), sign (W,))``."""
+        self._check_tensor(electrons, "electrons")
+        self._check_tensor(cotangent, "cotangent")
+        W = electrons.shape[0]
+        if tuple(cotangent.shape) != (W,):
+            raise ValueError(f"cotangent: expected shape ({W},), got {tuple(cotangent.shape)}")
+        logpsi = torch.empty(W, dtype=torch.float32, device=self.device)
+        sign = torch.empty(W, dtype=torch.float32, device=self.device)
+        need = int(self.lib.jaqmc_b200_ferminet_vjp_workspace_bytes(C.byref(wf.config_struct), W))
+        if need == 0 and W > 0:
+            raise _abi.JaqmcB200Error(_abi.ERR_INVALID_ARGUMENT, self.lib.jaqmc_b200_last_error().decode())
+        ws = self.workspace(max(need, 1 << 16))
+        rc = self.lib.jaqmc_b200_ferminet_logpsi_vjp(
+            C.byref(wf.config_struct), C.byref(wf.params_struct), C.byref(system.struct), _ptr(electrons), W,
+            _ptr(cotangent), C.byref(grads_handle.params_struct), _ptr(logpsi), _ptr(sign), _ptr(ws), ws.numel(),
+            self._stream())
+        _abi.check(self.lib, rc)
+        return logpsi, sign
+
+    @_on_device
     def mh_propose(self, x1, normals, stddev):
         """``x1 + normals * stddev`` (sampler/mcmc.py:53-54) for samplers that drive their own loop."""
         for t, nm in ((x1, "x1"), (normals, "normals"), (stddev, "stddev")):

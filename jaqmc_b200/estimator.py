@@ -1,6 +1,7 @@
 """Energy estimators: host-side mirror of ``estimator/base.py`` (``PerWalkerEstimator``, ``mean_reduce``,
 ``EstimatorPipeline``), ``estimator/kinetic/euclidean.py`` (``EuclideanKinetic``, forward-Laplacian mode),
-``app/molecule/hamiltonian.py`` (``potential_energy``) and ``estimator/total_energy.py`` (``TotalEnergy``).
+``app/molecule/hamiltonian.py`` (``potential_energy``), ``estimator/total_energy.py`` (``TotalEnergy``) and
+``estimator/loss_grad.py`` (``LossAndGrad``).
 
 Batched like the wavefunction classes: ``evaluate_batch_walkers`` is the unit of work (the reference reaches it by
 ``chunked_vmap`` of ``evaluate_single_walker``, estimator/base.py:251-270).
@@ -82,6 +83,69 @@ class TotalEnergy:
                 raise ValueError(f"Energy term {k!r} must be a scalar per walker, got shape {tuple(v.shape[1:])}")
             total = v if total is None else total + v
         return {"total_energy": total}, state
+
+
+def clip_observable(x: torch.Tensor, method: str, scale: float = 100.0) -> torch.Tensor:
+    """Outlier clipping of the local energies (reference utils/clip.py): the window statistics are taken over ALL walkers
+    -- the reference all-gathers them across devices first."""
+    if method == "none":
+        return x
+    allx = x
+    if torch.distributed.is_available() and torch.distributed.is_initialized():
+        parts = [torch.empty_like(x) for _ in range(torch.distributed.get_world_size())]
+        torch.distributed.all_gather(parts, x.contiguous())
+        allx = torch.cat(parts)
+    if method == "iqr":
+        q1, q3 = torch.nanquantile(allx, 0.25), torch.nanquantile(allx, 0.75)
+        return torch.minimum(torch.maximum(x, q1 - scale * (q3 - q1)), q3 + scale * (q3 - q1))
+    if method == "mad":
+        med = torch.nanquantile(allx, 0.5)
+        dev = torch.nanquantile((allx - med).abs(), 0.5)
+        return torch.minimum(torch.maximum(x, med - scale * dev), med + scale * dev)
+    raise ValueError(f"Unknown clip method {method!r}.")
+
+
+@dataclass
+class LossAndGrad:
+    """VMC loss and parameter gradients (reference estimator/loss_grad.py:25-128; same fields and defaults):
+    ``grads = 2 (<d log psi * E_clip> - <E_clip> <d log psi>)``.
+
+    The reference vmaps ``jax.value_and_grad(f_log_psi)`` (a W x P score tensor), multiplies by the clipped local energies
+    and averages.  Both averages are one reverse pass here: ``wf.logpsi_vjp`` with the per-walker cotangent
+    ``2 (E_clip,w - <E_clip>) / W`` (W = global walker count), followed by the all-reduce of the gradient over devices
+    that ``mean_reduce`` performs in the reference.  ``f_log_psi`` is the wavefunction object."""
+
+    f_log_psi: object = None
+    loss_key: str = "total_energy"
+    clip_method: str = "mad"
+    clip_scale: float = 5.0
+
+    def evaluate(self, params, data: MoleculeData, walker_stats: dict) -> dict:
+        loss = walker_stats[self.loss_key]
+        if loss.dim() != 1:
+            raise ValueError(f"Expected scalar loss value (i.e. ndim=0), got shape {tuple(loss.shape[1:])}.")
+        dist = torch.distributed.is_available() and torch.distributed.is_initialized()
+        clipped = clip_observable(loss, self.clip_method, self.clip_scale)
+        ok = torch.isfinite(clipped)
+        stats = torch.stack([torch.where(ok, clipped, torch.zeros_like(clipped)).sum(), ok.sum().to(clipped.dtype),
+                             torch.nansum(loss), torch.isfinite(loss).sum().to(loss.dtype)])
+        if dist:
+            torch.distributed.all_reduce(stats)
+        mean_c, count = stats[0] / stats[1], stats[1]
+        cot = torch.where(ok, 2.0 * (clipped - mean_c) / count, torch.zeros_like(clipped))
+        grads, logpsi = self.f_log_psi.logpsi_vjp(params, data, cot)
+        if dist:
+            for leaf in _leaves(grads):
+                torch.distributed.all_reduce(leaf)
+        return {"loss": stats[2] / stats[3], "grads": grads, "clipped_loss": mean_c, "logpsi": logpsi}
+
+
+def _leaves(tree):
+    if isinstance(tree, dict):
+        for k in sorted(tree):
+            yield from _leaves(tree[k])
+    else:
+        yield tree
 
 
 class EstimatorPipeline:

@@ -19,6 +19,12 @@ from ._runtime import runtime
 from .data import MoleculeData
 
 
+def _tree_zeros_like(tree):
+    if isinstance(tree, dict):
+        return {k: _tree_zeros_like(v) for k, v in tree.items()}
+    return torch.zeros_like(tree, memory_format=torch.contiguous_format)
+
+
 def _batched(electrons: torch.Tensor):
     if electrons.dim() == 2:
         return electrons.unsqueeze(0).contiguous(), True
@@ -163,6 +169,22 @@ class FermiNetWavefunction(Wavefunction):
         names = ["_env_up", "_env_down"] if split else ["_env"]
         env = _envelope_params(dev, names, n, A, self.ndets, self.envelope)
         return {"params": {"backbone_layer": bb, "orbital_layer": orb, "envelope_layer": env}}
+
+    def logpsi_vjp(self, params, data: MoleculeData, cotangent: torch.Tensor):
+        """``(grads, logpsi)``: ``grads`` has the tree structure of ``params`` and holds
+        ``sum_w cotangent[w] * d log|psi|(x_w) / d theta`` -- the VJP of the batched ``logpsi`` with respect to the
+        parameters (what ``LossAndGrad`` needs, reference estimator/loss_grad.py:70-128, without the per-walker score
+        tensor)."""
+        self._check(data)
+        el, _ = _batched(data.electrons)
+        rt = runtime(el.device)
+        A = data.atoms.shape[0]
+        wf = self._handle(params, A)
+        grads = _tree_zeros_like(params)
+        gh = self._handle(grads, A)
+        sysh = _marshal.system_handle(data.atoms, None)
+        logpsi, _ = rt.ferminet_logpsi_vjp(wf, gh, sysh, el, cotangent.contiguous())
+        return grads, logpsi
 
     def _handle(self, params, n_atoms: int):
         # rebuilt per call (a few dozen pointer reads): parameter leaves may have been replaced by the optimizer

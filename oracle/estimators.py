@@ -252,3 +252,38 @@ def hydrogen_local_energy(alpha: float, r: torch.Tensor):
     """Closed form for ``log psi = alpha |r|``: ``E_L = -alpha^2/2 - (alpha + 1)/|r|``."""
     d = r.norm(dim=-1).squeeze(-1)
     return -0.5 * alpha * alpha - (alpha + 1.0) / d
+
+
+# ---------------------------------------------------------------------------------------
+# loss and parameter gradients
+# ---------------------------------------------------------------------------------------
+def clip_observable(x: torch.Tensor, method: str, scale: float = 100.0) -> torch.Tensor:
+    """``utils/clip.py``: ``iqr`` clips to [Q1 - s IQR, Q3 + s IQR], ``mad`` to median +- s median(|x - median|)
+    (nan-aware quantiles over all walkers), ``none`` leaves ``x`` alone."""
+    if method == "none":
+        return x
+    if method == "iqr":
+        q1, q3 = torch.nanquantile(x, 0.25), torch.nanquantile(x, 0.75)
+        return torch.clamp(x, q1 - scale * (q3 - q1), q3 + scale * (q3 - q1))
+    if method == "mad":
+        med = torch.nanquantile(x, 0.5)
+        dev = torch.nanquantile((x - med).abs(), 0.5)
+        return torch.clamp(x, med - scale * dev, med + scale * dev)
+    raise ValueError(f"Unknown clip method {method!r}.")
+
+
+def loss_and_grad(scores, loss: torch.Tensor, clip_method: str = "mad", clip_scale: float = 5.0):
+    """``LossAndGrad.reduce`` + ``finalize_stats`` (``estimator/loss_grad.py:96-128``) from per-walker scores.
+
+    ``scores`` is a list of per-leaf tensors ``(W, *leaf.shape)`` holding ``d log psi_w / d leaf`` (what
+    ``evaluate_single_walker`` returns under ``vmap``).  Returns ``(loss, grads)`` with
+    ``grads = 2 (<score * E_clip> - <E_clip> <score>)``."""
+    clipped = clip_observable(loss, clip_method, clip_scale)
+    mean_c = torch.nanmean(clipped)
+    grads = []
+    for s in scores:
+        e = clipped.reshape(-1, *([1] * (s.dim() - 1)))
+        g_and_l = torch.nanmean(s * e, dim=0)
+        g = torch.nanmean(s, dim=0)
+        grads.append(2.0 * (g_and_l - mean_c * g))
+    return torch.nanmean(loss), grads
