@@ -363,19 +363,22 @@ int grid_for(long long items) {
   return g < 1 ? 1 : g;
 }
 
-int gemm_splits(long long R, int Kd, int Nd) {
+// Row chunks of the reduction GEMM: about four blocks per SM, at least 64 rows per chunk, and the partial results
+// [S][Kd][Nd] must fit the scratch area (GEMM_PART_FLOATS, carved in bwd_carve)
+#define GEMM_PART_TILES 96
+int gemm_splits(long long R, int Kd, int Nd, long long part_floats) {
   const long long tiles = (long long)jq_cdiv(Kd, 64) * jq_cdiv(Nd, 64);
-  long long S = (148 * 3 + tiles - 1) / tiles;
-  if (S > 96) S = 96;
+  long long S = (148 * 4 + tiles - 1) / tiles;
   if (S > (R + 63) / 64) S = (R + 63) / 64;
+  if (S * Kd * Nd > part_floats) S = part_floats / ((long long)Kd * Nd);
   return S < 1 ? 1 : (int)S;
 }
 
 // out[Kd][Nd] = X^T Z (row stride of out: ldo)
 int launch_gemm_tn(const float* X, int ldx, const float* Z, int ldz, long long R, int Kd, int Nd, float* part,
-                   float* out, int ldo, cudaStream_t st) {
+                   long long part_floats, float* out, int ldo, cudaStream_t st) {
   if (R <= 0 || Kd <= 0 || Nd <= 0) return JQ_OK;
-  const int S = gemm_splits(R, Kd, Nd);
+  const int S = gemm_splits(R, Kd, Nd, part_floats);
   jq_prof_work(2.0 * (double)R * Kd * Nd, 4.0 * (double)R * (Kd + Nd));
 #ifdef JAQMC_HOST_EMU
   JQ_LAUNCH(k_gemm_tn, dim3(grid_for((long long)S * Kd * Nd)), dim3(256), 0, st, X, ldx, Z, ldz, R, Kd, Nd, S, part);
@@ -405,13 +408,15 @@ __global__ void k_colsum_partial(const float* __restrict__ Z, long long R, int F
   }
 }
 
-int launch_colsum(const float* Z, long long R, int F, float* part, float* out, cudaStream_t st) {
-  int S = (int)((R + 255) / 256);
-  if (S > 256) S = 256;
+int launch_colsum(const float* Z, long long R, int F, float* part, long long part_floats, float* out, cudaStream_t st) {
+  long long S = (R + 63) / 64;                       // 64 rows per item: enough items to fill the machine
+  const long long smax = (148LL * 2048) / F;         // ... but no more than ~8 items per resident thread
+  if (S > smax) S = smax;
+  if (S * F > part_floats) S = part_floats / F;
   if (S < 1) S = 1;
-  JQ_LAUNCH(k_colsum_partial, dim3(grid_for((long long)S * F)), dim3(256), 0, st, Z, R, F, S, part);
+  JQ_LAUNCH(k_colsum_partial, dim3(grid_for(S * F)), dim3(256), 0, st, Z, R, F, (int)S, part);
   JQ_CHECK_LAUNCH();
-  JQ_LAUNCH(k_reduce_partials, dim3(grid_for(F)), dim3(256), 0, st, part, S, (long long)F, (long long)F, out);
+  JQ_LAUNCH(k_reduce_partials, dim3(grid_for(F)), dim3(64), 0, st, part, (int)S, (long long)F, (long long)F, out);
   JQ_CHECK_LAUNCH();
   return JQ_OK;
 }
@@ -449,6 +454,7 @@ struct BwdBufs {
   float *orb, *env, *M, *minv, *dsign, *dlogabs, *wdet, *dorb, *denv;
   float *dh_a, *dh_b, *dz, *dres, *dzw, *dm, *dg2, *dh2_a, *dh2_b, *dz2, *dres2;
   float *wt, *part, *wscr;
+  long long part_floats;
 };
 
 void bwd_carve(const FermiDims& d, long long W, JqArena& ar, BwdBufs* b) {
@@ -485,7 +491,9 @@ void bwd_carve(const FermiDims& d, long long W, JqArena& ar, BwdBufs* b) {
                              : d.in1p;
   const long long nmax = d.d1max > DN ? d.d1max : DN;
   b->wt = ar.take<float>(kmax * nmax);
-  b->part = ar.take<float>(96 * kmax * nmax > 256 * 2 * n * d.A * d.D * 2 ? 96 * kmax * nmax : 256 * 2 * n * d.A * d.D * 2);
+  b->part_floats = GEMM_PART_TILES * kmax * nmax > 256 * 2 * n * d.A * d.D * 2 ? GEMM_PART_TILES * kmax * nmax
+                                                                                 : 256 * 2 * n * d.A * d.D * 2;
+  b->part = ar.take<float>(b->part_floats);
   b->wscr = ar.take<float>(jq_dense_tc_scratch_floats((int)kmax, (int)nmax));
 }
 
@@ -642,7 +650,7 @@ extern "C" int jaqmc_b200_ferminet_logpsi_vjp(const jaqmc_ferminet_config* c, co
   for (int s = 0; s < nchan; ++s) {
     const int lo = split ? d.sp.lo(s) : 0, ns = split ? d.sp.hi(s) - d.sp.lo(s) : n;
     if (ns == n) {
-      if ((rc = launch_gemm_tn(b.h[L], hid, b.dorb, DN, G, hid, DN, b.part, grads->orbital_kernel[s], DN, st))) return rc;
+      if ((rc = launch_gemm_tn(b.h[L], hid, b.dorb, DN, G, hid, DN, b.part, b.part_floats, grads->orbital_kernel[s], DN, st))) return rc;
     } else {
       // rows of one spin channel (electrons [lo, lo + ns) of every walker), compacted; dz and M are free here
       float* hc = b.dz;
@@ -651,7 +659,7 @@ extern "C" int jaqmc_b200_ferminet_logpsi_vjp(const jaqmc_ferminet_config* c, co
       JQ_CHECK_LAUNCH();
       JQ_LAUNCH(k_gather_channel, dim3(grid_for(W * ns * DN)), dim3(256), 0, st, b.dorb, W, n, lo, ns, DN, dc);
       JQ_CHECK_LAUNCH();
-      if ((rc = launch_gemm_tn(hc, hid, dc, DN, W * ns, hid, DN, b.part, grads->orbital_kernel[s], DN, st))) return rc;
+      if ((rc = launch_gemm_tn(hc, hid, dc, DN, W * ns, hid, DN, b.part, b.part_floats, grads->orbital_kernel[s], DN, st))) return rc;
     }
     // dh_L rows of this channel = dorb K_s^T : K_s (hid, DN) -> K_s^T (DN, hid)
     JQ_LAUNCH(k_transpose, dim3(grid_for((long long)hid * DN)), dim3(256), 0, st, p->orbital_kernel[s], hid, DN, DN, b.wt);
@@ -681,10 +689,10 @@ extern "C" int jaqmc_b200_ferminet_logpsi_vjp(const jaqmc_ferminet_config* c, co
     JQ_LAUNCH(k_tanh_bwd, dim3(grid_for(cnt)), dim3(256), 0, st, dh, b.h[l + 1], res1[l] ? b.h[l] : nullptr, res1[l] ? 1 : 0, cnt,
               b.dz, res1[l] ? b.dres : nullptr);
     JQ_CHECK_LAUNCH();
-    if ((rc = launch_colsum(b.dz, G, N1, b.part, grads->single_bias[l], st))) return rc;
+    if ((rc = launch_colsum(b.dz, G, N1, b.part, b.part_floats, grads->single_bias[l], st))) return rc;
     if (l == 0) {
       // dW_0 = x1^T dz over the in1 rows that exist (x1 rows are in1p wide, zero padded)
-      if ((rc = launch_gemm_tn(b.x1, d.in1p, b.dz, N1, G, d.in1, N1, b.part, grads->single_kernel[0], N1, st))) return rc;
+      if ((rc = launch_gemm_tn(b.x1, d.in1p, b.dz, N1, G, d.in1, N1, b.part, b.part_floats, grads->single_kernel[0], N1, st))) return rc;
       break;   // the input features carry no parameters
     }
     float* gW = grads->single_kernel[l];
@@ -692,9 +700,9 @@ extern "C" int jaqmc_b200_ferminet_logpsi_vjp(const jaqmc_ferminet_config* c, co
     if ((rc = jq_launch_spin_mean(b.h[l], b.m, (int)W, d.sp, 1, K1, st))) return rc;
     JQ_LAUNCH(k_walker_sum, dim3(grid_for(W * N1)), dim3(256), 0, st, b.dz, W, n, N1, b.dzw);
     JQ_CHECK_LAUNCH();
-    if ((rc = launch_gemm_tn(b.h[l], K1, b.dz, N1, G, K1, N1, b.part, gW, N1, st))) return rc;
-    if ((rc = launch_gemm_tn(b.m, nch * K1, b.dzw, N1, W, nch * K1, N1, b.part, gW + (size_t)K1 * N1, N1, st))) return rc;
-    if ((rc = launch_gemm_tn(b.g2[l], fg, b.dz, N1, G, fg, N1, b.part, gW + (size_t)K1 * (1 + nch) * N1, N1, st))) return rc;
+    if ((rc = launch_gemm_tn(b.h[l], K1, b.dz, N1, G, K1, N1, b.part, b.part_floats, gW, N1, st))) return rc;
+    if ((rc = launch_gemm_tn(b.m, nch * K1, b.dzw, N1, W, nch * K1, N1, b.part, b.part_floats, gW + (size_t)K1 * N1, N1, st))) return rc;
+    if ((rc = launch_gemm_tn(b.g2[l], fg, b.dz, N1, G, fg, N1, b.part, b.part_floats, gW + (size_t)K1 * (1 + nch) * N1, N1, st))) return rc;
     // dX = dz W^T, block by block of the transposed kernel WT [N1][fan_in]
     const int fan_in = K1 * (1 + nch) + fg;
     JQ_LAUNCH(k_transpose, dim3(grid_for((long long)fan_in * N1)), dim3(256), 0, st, p->single_kernel[l], fan_in, N1, N1, b.wt);
@@ -728,8 +736,8 @@ extern "C" int jaqmc_b200_ferminet_logpsi_vjp(const jaqmc_ferminet_config* c, co
     JQ_LAUNCH(k_tanh_bwd, dim3(grid_for(cnt2)), dim3(256), 0, st, dh2, b.h2[lp + 1], res2[lp] ? b.h2[lp] : nullptr,
               res2[lp] ? 1 : 0, cnt2, b.dz2, res2[lp] ? b.dres2 : nullptr);
     JQ_CHECK_LAUNCH();
-    if ((rc = launch_colsum(b.dz2, G2, N2, b.part, grads->double_bias[lp], st))) return rc;
-    if ((rc = launch_gemm_tn(b.h2[lp], K2, b.dz2, N2, G2, K2, N2, b.part, grads->double_kernel[lp], N2, st))) return rc;
+    if ((rc = launch_colsum(b.dz2, G2, N2, b.part, b.part_floats, grads->double_bias[lp], st))) return rc;
+    if ((rc = launch_gemm_tn(b.h2[lp], K2, b.dz2, N2, G2, K2, N2, b.part, b.part_floats, grads->double_kernel[lp], N2, st))) return rc;
     if (lp > 0) {   // h2[0] are the input features: nothing further below
       JQ_LAUNCH(k_transpose, dim3(grid_for((long long)K2 * N2)), dim3(256), 0, st, p->double_kernel[lp], K2, N2, N2, b.wt);
       JQ_CHECK_LAUNCH();
