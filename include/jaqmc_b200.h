@@ -271,6 +271,21 @@ int jaqmc_b200_orbitals(const jaqmc_wavefunction* wf, const jaqmc_system* sys, c
                         int64_t n_walkers, float* orbitals, void* workspace, size_t workspace_bytes,
                         jaqmc_stream_t stream);
 
+/* psi-ratio consumers.  Replaces the vmapped `phase_logpsi` evaluations of the ECP non-local
+ * integral (estimator/ecp/nonlocal_integral.py:43-110: one electron displaced to quadrature points around an atom) and
+ * of SpinSquared (estimator/spin.py:87-146: a minority-spin electron exchanged with each majority-spin electron): for
+ * every walker, `n_moves` configurations that differ from the walker's in at most two electrons.
+ *   move_index (n_moves, 2) int32 DEVICE: the electrons replaced in move q (second entry -1: only one);
+ *   move_pos   (n_walkers, n_moves, 2, 3): their new positions (entries of unused slots are ignored);
+ *   log_ratio  (n_walkers, n_moves) = log|psi(moved)| - log|psi(walker)|;
+ *   sign_ratio (n_walkers, n_moves) = sign(psi(moved)) * sign(psi(walker))  (periodic network: the phase difference
+ *              Im log psi(moved) - Im log psi(walker), wrapped into (-pi, pi]).
+ * A workspace smaller than the single-pass size tiles the configurations; it must hold one configuration. */
+int jaqmc_b200_psi_ratios(const jaqmc_wavefunction* wf, const jaqmc_system* sys, const float* electrons,
+                          int64_t n_walkers, int32_t n_moves, const int32_t* move_index, const float* move_pos,
+                          float* log_ratio, float* sign_ratio, void* workspace, size_t workspace_bytes,
+                          jaqmc_stream_t stream);
+
 /* Replaces the estimator half of EvaluationWorkStage.compute_step for the energy keys
  * (workflow/stage/evaluation.py:190-192): EuclideanKinetic in forward_laplacian mode
  * (estimator/kinetic/euclidean.py:114-135, laplacian/interpreter.py:392-438), the potential

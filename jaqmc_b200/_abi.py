@@ -233,6 +233,11 @@ PROTOTYPES = {
         C.c_int,
         [C.POINTER(Wavefunction), C.POINTER(System), FloatP, C.c_int64, FloatP, C.c_void_p, C.c_size_t, C.c_void_p],
     ),
+    "jaqmc_b200_psi_ratios": (
+        C.c_int,
+        [C.POINTER(Wavefunction), C.POINTER(System), FloatP, C.c_int64, C.c_int32, C.c_void_p, FloatP, FloatP, FloatP,
+         C.c_void_p, C.c_size_t, C.c_void_p],
+    ),
     "jaqmc_b200_ferminet_vjp_workspace_bytes": (C.c_size_t, [C.POINTER(FerminetConfig), C.c_int64]),
     "jaqmc_b200_ferminet_logpsi_vjp": (
         C.c_int,

@@ -251,6 +251,36 @@ class Runtime:
         return replay
 
     @_on_device
+    def psi_ratios(self, wf, system, electrons, move_index, move_pos):
+        """``(log|psi'/psi|, sign ratio)`` (W, Q) for Q moved configurations per walker: ``move_index`` (Q, 2) int32
+        (second entry -1: one electron), ``move_pos`` (W, Q, 2, 3)."""
+        self._check_tensor(electrons, "electrons")
+        self._check_tensor(move_pos, "move_pos")
+        self._check_tensor(move_index, "move_index", dtype=torch.int32)
+        W, n = electrons.shape[0], electrons.shape[1]
+        Q = move_index.shape[0]
+        if tuple(move_index.shape) != (Q, 2) or tuple(move_pos.shape) != (W, Q, 2, 3):
+            raise ValueError(f"psi_ratios: move_index {tuple(move_index.shape)} / move_pos {tuple(move_pos.shape)} do not "
+                             f"match ({Q}, 2) / ({W}, {Q}, 2, 3)")
+        lr = torch.empty(W, Q, dtype=torch.float32, device=self.device)
+        sr = torch.empty(W, Q, dtype=torch.float32, device=self.device)
+        if W * Q == 0:
+            return lr, sr
+        need = self.workspace_bytes(wf, W * Q, False) + 4 * (3 * n * W * Q + 2 * W) + 4096
+        if self.workspace_limit_bytes is not None:
+            need = min(need, self.workspace_limit_bytes)
+        elif self.device.type == "cuda":
+            free, _ = torch.cuda.mem_get_info(self.device)
+            held = self._ws.numel() if self._ws is not None else 0
+            need = min(need, int(0.8 * (free + held)))
+        ws = self.workspace(max(need, 1 << 16))
+        rc = self.lib.jaqmc_b200_psi_ratios(C.byref(wf.struct), C.byref(system.struct), _ptr(electrons), W, Q,
+                                            _ptr(move_index), _ptr(move_pos), _ptr(lr), _ptr(sr), _ptr(ws), ws.numel(),
+                                            self._stream())
+        _abi.check(self.lib, rc)
+        return lr, sr
+
+    @_on_device
     def ferminet_logpsi_vjp(self, wf, grads_handle, system, electrons, cotangent):
         """``sum_w cotangent[w] d log|psi|(x_w) / d theta`` into the leaves behind ``grads_handle`` (a ``ferminet_handle``
         built on a tree of gradient buffers); returns ``(logpsi (W,), sign (W,))``."""

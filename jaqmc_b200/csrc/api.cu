@@ -600,6 +600,111 @@ static int mh_step_impl(const jaqmc_wavefunction* wf, const jaqmc_system* sys, f
   return JQ_OK;
 }
 
+// ------------------------------------------------------------------------------------------------
+// psi-ratio consumers: the ECP non-local integral (estimator/ecp/nonlocal_integral.py:23-165) and
+// SpinSquared (estimator/spin.py:75-146) evaluate phase_logpsi at many configurations per walker that differ from the
+// walker's in one or two electrons.  One call: build the moved configurations tile by tile, run the value-only forward
+// pass (the sampling path's kernels), return log|psi'/psi| and the sign (phase) of the ratio.
+// ------------------------------------------------------------------------------------------------
+// cfg[t][e][:] = electrons[w][e][:] with electron idx[q][s] replaced by pos[w][q][s][:]  (t = local index of (w, q))
+__global__ void k_build_moved(const float* __restrict__ el, const int* __restrict__ idx, const float* __restrict__ pos,
+                              long long t0, long long count, int Q, int n, float* __restrict__ cfg) {
+  const long long items = count * n;
+  for (long long it = (long long)blockIdx.x * blockDim.x + threadIdx.x; it < items;
+       it += (long long)gridDim.x * blockDim.x) {
+    const int e = (int)(it % n);
+    const long long t = it / n;
+    const long long wq = t0 + t;
+    const long long w = wq / Q;
+    const int q = (int)(wq - w * Q);
+    const float* src = el + (w * n + e) * 3;
+    for (int s = 0; s < 2; ++s)
+      if (idx[2 * q + s] == e) src = pos + ((w * Q + q) * 2 + s) * 3;   // the later entry wins if both name e
+    float* o = cfg + it * 3;
+    o[0] = src[0];
+    o[1] = src[1];
+    o[2] = src[2];
+  }
+}
+
+// complex_phase: sign arrays hold phase angles (periodic network): difference wrapped into (-pi, pi]; else signs: product
+__global__ void k_ratio_finish(const float* __restrict__ lp0, const float* __restrict__ sg0, float* __restrict__ lp,
+                               float* __restrict__ sg, long long t0, long long count, int Q, int complex_phase) {
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < count; t += (long long)gridDim.x * blockDim.x) {
+    const long long w = (t0 + t) / Q;
+    lp[t] = lp[t] - lp0[w];
+    if (complex_phase) {
+      float dph = sg[t] - sg0[w];
+      const float two_pi = 6.28318530717958647692f;
+      dph -= two_pi * rintf(dph / two_pi);
+      sg[t] = dph;
+    } else {
+      sg[t] = sg[t] * sg0[w];
+    }
+  }
+}
+
+extern "C" int jaqmc_b200_psi_ratios(const jaqmc_wavefunction* wf, const jaqmc_system* sys, const float* electrons,
+                                     int64_t n_walkers, int32_t n_moves, const int32_t* move_index, const float* move_pos,
+                                     float* log_ratio, float* sign_ratio, void* workspace, size_t workspace_bytes,
+                                     jaqmc_stream_t stream) {
+  int rc = check_wf(wf);
+  if (rc) return rc;
+  JQ_REQUIRE(n_walkers >= 0 && n_moves >= 0, JQ_ERR_INVALID_ARGUMENT, "psi_ratios: negative size");
+  if (n_walkers == 0 || n_moves == 0) return JQ_OK;
+  JQ_REQUIRE(electrons && move_index && move_pos && log_ratio && sign_ratio, JQ_ERR_INVALID_ARGUMENT, "psi_ratios: null buffer");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int n = wf_n_electrons(wf);
+  const long long W = n_walkers, Q = n_moves, T = W * Q;
+  JqArena ar(workspace, workspace_bytes);
+  float* lp0 = ar.take<float>(W);
+  float* sg0 = ar.take<float>(W);
+  JQ_REQUIRE(workspace && ar.off <= workspace_bytes, JQ_ERR_WORKSPACE_TOO_SMALL, "psi_ratios: workspace too small");
+  // largest tile of configurations: per configuration 3n floats of positions + the pipeline's value-path workspace
+  const size_t fixed = ar.off;
+  auto fits = [&](long long tile) {
+    JqArena probe(nullptr, 0);
+    probe.take<float>(tile * 3 * n);
+    return fixed + probe.off + wf_ws_bytes(wf, tile, 0) + 256 <= workspace_bytes;
+  };
+  long long tile = T;
+  if (!fits(tile)) {
+    long long lo = 0, hi = T;
+    while (hi - lo > 1) {
+      const long long mid = (lo + hi) / 2;
+      if (fits(mid)) lo = mid; else hi = mid;
+    }
+    tile = lo;
+  }
+  JQ_REQUIRE(tile >= 1, JQ_ERR_WORKSPACE_TOO_SMALL, "psi_ratios: workspace of %zu bytes cannot hold one configuration", workspace_bytes);
+  float* cfg = ar.take<float>(tile * 3 * n);
+  void* wsn = ar.base ? ar.base + ar.off : nullptr;
+  const size_t avail = workspace_bytes - ar.off;
+  // reference values
+  {
+    const long long wt = (tile < W) ? tile : W;
+    for (long long w0 = 0; w0 < W; w0 += wt) {
+      const long long wc = (W - w0 < wt) ? W - w0 : wt;
+      JqWfOut out = {lp0 + w0, sg0 + w0, nullptr, nullptr, nullptr, nullptr};
+      if ((rc = wf_forward(wf, sys, electrons + w0 * 3 * n, wc, 0, wsn, avail, out, st))) return rc;
+    }
+  }
+  const int complex_phase = wf->kind == JAQMC_WF_SOLID_FERMINET;
+  for (long long t0 = 0; t0 < T; t0 += tile) {
+    const long long tc = (T - t0 < tile) ? T - t0 : tile;
+    int grid = jq_cdiv(tc * n, 256);
+    if (grid > 148 * 16) grid = 148 * 16;
+    JQ_LAUNCH(k_build_moved, dim3(grid), dim3(256), 0, st, electrons, move_index, move_pos, t0, tc, (int)Q, n, cfg);
+    JQ_CHECK_LAUNCH();
+    JqWfOut out = {log_ratio + t0, sign_ratio + t0, nullptr, nullptr, nullptr, nullptr};
+    if ((rc = wf_forward(wf, sys, cfg, tc, 0, wsn, avail, out, st))) return rc;
+    JQ_LAUNCH(k_ratio_finish, dim3(jq_cdiv(tc, 256)), dim3(256), 0, st, lp0, sg0, log_ratio + t0, sign_ratio + t0, t0, tc,
+              (int)Q, complex_phase);
+    JQ_CHECK_LAUNCH();
+  }
+  return JQ_OK;
+}
+
 extern "C" int64_t jaqmc_b200_launch_count(void) { return jq_launch_counter; }
 extern "C" void jaqmc_b200_reset_launch_count(void) { jq_launch_counter = 0; }
 extern "C" const char* jaqmc_b200_last_error(void) { return jq_err; }

@@ -364,6 +364,47 @@ def mcmc_case(name="mcmc_lih", pbc=False):
 
 
 # ---------------------------------------------------------------------------------------------------------------
+def observables_case(name, mol, kw, W):
+    """psi-ratio consumers on a FermiNet: ``SpinSquared`` (estimator/spin.py) and the non-local ECP integral
+    (estimator/ecp/nonlocal_integral.py, icosahedron_12 quadrature, 2 non-local channels) with queued rotation draws."""
+    if args.backend != "shim":
+        raise SystemExit("observables fixtures replay queued uniforms through the stand-in jax.random (shim backend)")
+    from jax import random as R
+
+    atoms, charges, nspins = systems.molecule(mol)
+    el = systems.synthetic_walkers(atoms, charges, nspins, W, seed=23).numpy()
+    wf = ref("jaqmc.app.molecule.wavefunction.ferminet").FermiNetWavefunction(nspins=tuple(nspins), **kw)
+    MoleculeData = ref("jaqmc.app.molecule.data").MoleculeData
+    A, Z = to_backend(atoms.numpy()), to_backend(charges.numpy())
+    mk = lambda e: MoleculeData(electrons=e, atoms=A, charges=Z)  # noqa: E731
+    flat = jittered_params(wf, mk(to_backend(el[0])), 17)
+    params = tree_to_backend(flat)
+    SpinSquared = ref("jaqmc.estimator.spin").SpinSquared
+    spin = SpinSquared(n_up=nspins[0], n_down=nspins[1], phase_logpsi=wf.phase_logpsi, data_field="electrons")
+    spin.init(mk(to_backend(el[0])), None)
+    quad = ref("jaqmc.estimator.ecp.quadrature").get_quadrature("icosahedron_12")
+    evaluate = ref("jaqmc.estimator.ecp.nonlocal_integral").make_nonlocal_integral(3, quad)
+    n = el.shape[1]
+    g = np.random.default_rng(31)
+    u1 = g.uniform(size=(W, n)).astype(np.float32).astype(np.float64)
+    u2 = g.uniform(size=(W, n)).astype(np.float32).astype(np.float64)
+    s2, integrals = [], []
+    for w in range(W):
+        x = to_backend(el[w])
+        s2.append(to_numpy(spin.evaluate_single_walker(params, mk(x), None, None, None)[0]["spin:s2"]))
+        R.queue_uniform(to_backend(u1[w]))
+        R.queue_uniform(to_backend(u2[w]))
+        atom_pos = to_backend(np.broadcast_to(atoms.numpy(), (n, atoms.shape[0], 3)).copy())
+        integrals.append(to_numpy(evaluate(lambda e: wf.phase_logpsi(params, mk(e)), x, atom_pos, None)))
+    meta = dict(kind="observables", wf="ferminet", molecule=mol, nspins=list(nspins), kwargs=kw, backend=args.backend,
+                quadrature="icosahedron_12", num_channels=3,
+                reference="bytedance/jaqmc 0.1.0 estimator/spin.py, estimator/ecp/nonlocal_integral.py, estimator/ecp/quadrature.py")
+    save(name, meta, flat, dict(electrons=el, atoms=atoms.numpy(), charges=charges.numpy(), s2=np.stack(s2),
+                                nonlocal_integrals=np.stack(integrals), u1=u1, u2=u2, quad_pts=to_numpy(quad.pts),
+                                quad_coefs=to_numpy(quad.coefs)))
+
+
+# ---------------------------------------------------------------------------------------------------------------
 def main():
     want = lambda nm: args.only is None or nm in args.only  # noqa: E731
     for name, (kind, mol, kw, W) in MOLECULE_CASES.items():
@@ -379,6 +420,10 @@ def main():
         mcmc_case("mcmc_lih", pbc=False)
     if want("mcmc_pbc"):
         mcmc_case("mcmc_pbc", pbc=True)
+    if want("observables_lih"):
+        observables_case("observables_lih", "LiH", dict(ndets=3, hidden_dims_single=[16, 16], hidden_dims_double=[8, 8]), 3)
+    if want("observables_li"):
+        observables_case("observables_li", "Li", dict(ndets=2, hidden_dims_single=[16, 16], hidden_dims_double=[8, 8]), 3)
 
 
 if __name__ == "__main__":

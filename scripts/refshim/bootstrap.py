@@ -47,7 +47,7 @@ def install():
     root = _pkg_stub("jaqmc", J)
     root._refshim = True
     # packages entered without running their __init__ (they import workflow / optimizers / pyscf)
-    for sub in ("app", "app/molecule", "app/solid", "estimator", "estimator/kinetic", "sampler", "utils",
+    for sub in ("app", "app/molecule", "app/solid", "estimator", "estimator/kinetic", "estimator/ecp", "sampler", "utils",
                 "utils/atomic", "geometry", "optimizer", "workflow"):
         _pkg_stub("jaqmc." + sub.replace("/", "."), os.path.join(J, sub))
 
@@ -55,6 +55,9 @@ def install():
     class Data:   # jaqmc/data.py: a dataclass pytree; the path only reads fields and calls merge
         def merge(self, updates):
             return dataclasses.replace(self, **updates)
+
+        def __getitem__(self, key):
+            return getattr(self, key)
 
     class BatchedData:
         pass

@@ -1,7 +1,7 @@
 """Eager torch-float64 stand-in for the parts of ``jax`` the reference's hot path touches (see ../README.md)."""
 import torch
 
-from . import lax, nn, numpy, random, tree, typing  # noqa: F401
+from . import lax, nn, numpy, random, scipy, tree, typing  # noqa: F401
 from . import core  # noqa: F401
 
 Array = torch.Tensor

@@ -21,10 +21,12 @@ def fori_loop(lower, upper, body, init):
 
 
 def scan(f, init, xs, length=None):
+    from . import tree
+
     carry = init
     ys = []
-    n = length if xs is None else len(xs)
+    n = length if xs is None else tree.leaves(xs)[0].shape[0]
     for i in range(n):
-        carry, y = f(carry, None if xs is None else xs[i])
+        carry, y = f(carry, None if xs is None else tree.map(lambda t: t[i], xs))
         ys.append(y)
-    return carry, (torch.stack(ys) if ys and isinstance(ys[0], torch.Tensor) else ys)
+    return carry, (tree.map(lambda *t: torch.stack(t), *ys) if ys else ys)

@@ -184,6 +184,13 @@ floor = _un(torch.floor)
 ceil = _un(torch.ceil)
 sign = _un(torch.sign)
 square = _un(torch.square)
+arctan = _un(torch.arctan)
+arccos = _un(torch.arccos)
+arcsin = _un(torch.arcsin)
+
+
+def tile(x, reps):
+    return asarray(x).repeat(*reps) if not isinstance(reps, int) else asarray(x).repeat(reps)
 
 
 def abs(x):  # noqa: A001

@@ -186,3 +186,29 @@ def test_oracle_mcmc_matches_reference(name):
         assert state[2] == int(z["counter_after"][it])
         np.testing.assert_allclose(x.numpy(), z[f"electrons_after_step{it + 1}"], rtol=0, atol=1e-12)
     assert float(z["stddev_after"][1]) != float(z["stddev_after"][0])   # the adaptation branch was exercised
+
+
+@pytest.mark.parametrize("name", ["observables_lih", "observables_li"])
+def test_oracle_observables_match_reference(name):
+    """psi-ratio consumers: ``SpinSquared`` (estimator/spin.py) and the non-local ECP integral
+    (estimator/ecp/nonlocal_integral.py) of the reference against the oracle's restatement."""
+    from jaqmc_b200.ecp import Quadrature, get_quadrature
+    from oracle import observables as OO
+
+    meta, params, z = load(name)
+    nspins = tuple(meta["nspins"])
+    atoms = torch.from_numpy(z["atoms"].astype(np.float64))
+    phase = lambda e: ON.ferminet_logpsi(params, e, atoms, nspins)  # noqa: E731
+    quad = get_quadrature(meta["quadrature"])
+    np.testing.assert_allclose(quad.pts.numpy(), z["quad_pts"], atol=1e-14)      # the host mirror's tables
+    np.testing.assert_allclose(quad.coefs.numpy(), z["quad_coefs"], atol=1e-15)
+    n = z["electrons"].shape[1]
+    for w in range(z["electrons"].shape[0]):
+        e = torch.from_numpy(z["electrons"][w].astype(np.float64))
+        s2 = OO.spin_squared(phase, e, *nspins)
+        assert abs(float(s2) - float(z["s2"][w])) < 1e-9 * (1 + abs(float(z["s2"][w])))
+        rot = Quadrature.rotation_matrices(2 * np.pi * torch.from_numpy(z["u1"][w]), 1.0 - 2.0 * torch.from_numpy(z["u2"][w]))
+        pts = torch.einsum("ijk,lk->ilj", rot, quad.pts)
+        atom_pos = atoms[None].expand(n, -1, -1)
+        got = OO.nonlocal_integral(phase, e, atom_pos, pts, quad.coefs, meta["num_channels"] - 1)
+        np.testing.assert_allclose(got.numpy(), z["nonlocal_integrals"][w], rtol=1e-8, atol=1e-10)
