@@ -857,6 +857,15 @@ __global__ void __launch_bounds__(256, 3) k_logdet(const float* __restrict__ orb
     return;
   }
   // traces, KC derivative slabs at a time.  slab kk <-> component c = 1 + k0 + kk (k0 + kk == K is the Laplacian row)
+  const int nb = (n + 3) / 4, tiles = nb * nb;
+  float* invT = p2 + KC * DB * n;   // [DB][nn]: invT[d][j][i] = inv[d][i][j]
+  for (int q = tid; q < db * nn; q += nt) {
+    int d, rem, i, j;
+    jq_divmod(q, nn, inv_nn, &d, &rem);
+    jq_divmod(rem, n, inv_n, &i, &j);
+    invT[d * nn + j * n + i] = inv[q];
+  }
+  __syncthreads();
   for (int k0 = 0; k0 < KT; k0 += KC) {
     const int kc = (KT - k0 < KC) ? KT - k0 : KC;
     for (int q = tid; q < kc * n * db * n; q += nt) {
@@ -867,27 +876,39 @@ __global__ void __launch_bounds__(256, 3) k_logdet(const float* __restrict__ orb
       Jc[(kk * DB + d) * nn + j * n + i] = ow[((long long)j * C + (1 + k0 + kk)) * DN + r];
     }
     __syncthreads();
-    // M = inv . J: thread (ty, tx) walks rows r = (kk, d, i) by TY and columns i2 by TX; a 1 x 2 register tile per step
-    for (int r = ty; r < kc * db * n; r += TY) {
-      int t, i, kk, d;
-      jq_divmod(r, n, inv_n, &t, &i);
-      jq_divmod(t, db, inv_db, &kk, &d);
-      const float* ip = inv + d * nn + i * n;
-      const float* jb = Jc + (kk * DB + d) * nn;
-      float* mrow = Mc + (kk * DB + d) * nn + i * n;
-      for (int i2 = tx; i2 < n; i2 += 2 * TX) {
-        const int i3 = i2 + TX;
-        const bool two = i3 < n;
-        const float* jp = jb + i2;
-        float a0 = 0.f, a1 = 0.f;
-        for (int j = 0; j < n; ++j) {
-          const float iv = ip[j];
-          a0 = fmaf(iv, jp[j * n], a0);
-          if (two) a1 = fmaf(iv, jp[j * n + TX], a1);
+    // M = inv . J in 4 x 4 register tiles (r2): per contraction index j a tile reads 4 entries of the j-major
+    // (transposed) inverse and 4 of the slab -- 8 shared-memory words per 16 multiply-adds, against 3 words per 2 for
+    // the 1 x 2 tiles this replaces (the kernel is bound by the shared-memory pipe)
+    for (int q = tid; q < kc * db * tiles; q += nt) {
+      const int t = q % tiles, dk = q / tiles;
+      const int d = dk % db, kk = dk / db;
+      const int i0 = 4 * (t / nb), c0 = 4 * (t % nb);
+      const float* tp = invT + d * nn + i0;
+      const float* jb = Jc + (kk * DB + d) * nn + c0;
+      float acc[4][4];
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
+      const bool full = (i0 + 4 <= n) && (c0 + 4 <= n);
+      for (int j = 0; j < n; ++j) {
+        float xv[4], yv[4];
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+          xv[a] = (full || i0 + a < n) ? tp[j * n + a] : 0.f;
+          yv[a] = (full || c0 + a < n) ? jb[j * n + a] : 0.f;
         }
-        mrow[i2] = a0;
-        if (two) mrow[i3] = a1;
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+          for (int b = 0; b < 4; ++b) acc[a][b] = fmaf(xv[a], yv[b], acc[a][b]);
       }
+      float* mo = Mc + (kk * DB + d) * nn;
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b)
+          if (i0 + a < n && c0 + b < n) mo[(i0 + a) * n + c0 + b] = acc[a][b];
     }
     __syncthreads();
     for (int q = tid; q < kc * db * n; q += nt) {
@@ -1071,7 +1092,7 @@ int jq_launch_logdet(const float* orb, int W, int n, int D, int track, float* de
       return (size_t)8 * db + sizeof(float) * ((size_t)db * nn + 2 * (size_t)db * n + 4 * (size_t)db +
                                               (size_t)db * (n * LD_NP + 4) + (size_t)db * (nn + 32) + 2 * (size_t)db * n) + 32;
     return (size_t)8 * db + sizeof(float) * ((size_t)db * nn + 2 * (size_t)db * n + 4 * (size_t)db +
-                                            (track ? (size_t)kc * db * nn * 2 + (size_t)kc * db * n * 2 : 0)) + 32;
+                                            (track ? (size_t)kc * db * nn * 2 + (size_t)kc * db * n * 2 + (size_t)db * nn : 0)) + 32;
   };
   if (track && n <= LD_NP) {
     // small-matrix path: all determinants of a walker in one block when they fit; the slab area [2*KC][DB][nn] must

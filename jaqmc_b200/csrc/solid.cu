@@ -102,7 +102,8 @@ __global__ void k_solid_orb_factor(float* __restrict__ orb_r, float* __restrict_
 // real kernel (logdet.cu) in complex arithmetic: Gauss-Jordan with partial pivoting on |z|,
 //   log det = sum log|p| + i (sum arg p + pi * swaps),  M = A^-1 dA_c,  ld_J[c] = tr M,  ld_L = tr(A^-1 A_L) - sum_k tr(M_k^2).
 // Shared (floats): logabs[DB] arg[DB] (double) | inv_r inv_i [DB][nn] | colp_r colp_i [DB][n] | piv[DB][n] |
-//                  pv_r pv_i [DB] | trL_r trL_i t2_r t2_i [DB] | J_r J_i M_r M_i [DB][nn] | p1r p1i p2r p2i [DB][n]
+//                  pv_r pv_i [DB] | trL_r trL_i t2_r t2_i [DB] | J_r J_i M_r M_i invT_r invT_i [DB][nn] |
+//                  p1r p1i p2r p2i [DB][max(n, tiles)]
 // ------------------------------------------------------------------------------------------------
 __global__ void k_logdet_c(const float* __restrict__ orb_r, const float* __restrict__ orb_i, int n, int D, int C, int DB,
                            float* __restrict__ det_ld, float* __restrict__ det_grad, float* __restrict__ det_lap) {
@@ -127,10 +128,13 @@ __global__ void k_logdet_c(const float* __restrict__ orb_r, const float* __restr
   float* J_i = J_r + (size_t)DB * nn;
   float* M_r = J_i + (size_t)DB * nn;
   float* M_i = M_r + (size_t)DB * nn;
-  float* p1r = M_i + (size_t)DB * nn;
-  float* p1i = p1r + DB * n;
-  float* p2r = p1i + DB * n;
-  float* p2i = p2r + DB * n;
+  float* invT_r = M_i + (size_t)DB * nn;
+  float* invT_i = invT_r + (size_t)DB * nn;
+  const int np_ = ((n + 3) / 4) * ((n + 3) / 4) > n ? ((n + 3) / 4) * ((n + 3) / 4) : n;   // per-tile partials
+  float* p1r = invT_i + (size_t)DB * nn;
+  float* p1i = p1r + DB * np_;
+  float* p2r = p1i + DB * np_;
+  float* p2i = p2r + DB * np_;
   const int ngrp = (D + DB - 1) / DB;
   const long long w = blockIdx.x / ngrp;
   const int d0 = (int)(blockIdx.x % ngrp) * DB;
@@ -262,6 +266,19 @@ __global__ void k_logdet_c(const float* __restrict__ orb_r, const float* __restr
     }
     __syncthreads();
   }
+  // ---- traces (r2).  M = A^-1 dA_c in 4 x 4 complex register tiles: per contraction index j a tile reads 4 entries of a
+  // j-major (transposed) copy of the inverse and 4 of the slab -- 16 shared-memory words for 16 complex multiply-adds
+  // (64 FMAs), against 4 words per complex multiply-add for one output per thread (the kernel was bound by the
+  // shared-memory pipe at 10 TFLOP/s).  tr M and tr M^2 = sum M[i][i2] M[i2][i] are per-tile partials summed in a
+  // fixed order.
+  const int nb = (n + 3) / 4, tiles = nb * nb;
+  for (int q = tid; q < db * nn; q += nt) {
+    const int d = q / nn, rem = q % nn;
+    const int i = rem / n, j = rem % n;
+    invT_r[d * nn + j * n + i] = inv_r[q];
+    invT_i[d * nn + j * n + i] = inv_i[q];
+  }
+  __syncthreads();
   for (int kk = 0; kk < KT; ++kk) {
     for (int q = tid; q < n * db * n; q += nt) {
       const int j = q / (db * n), r = q % (db * n);
@@ -271,46 +288,80 @@ __global__ void k_logdet_c(const float* __restrict__ orb_r, const float* __restr
       J_i[d * nn + j * n + i] = orb_i[src];
     }
     __syncthreads();
-    for (int q = tid; q < db * nn; q += nt) {
-      const int d = q / nn, rem = q % nn;
-      const int i = rem / n, i2 = rem % n;
-      const float* ir = inv_r + d * nn + i * n;
-      const float* ii = inv_i + d * nn + i * n;
-      const float* jr = J_r + d * nn + i2;
-      const float* ji = J_i + d * nn + i2;
-      float ar = 0.f, ai = 0.f;
+    for (int q = tid; q < db * tiles; q += nt) {
+      const int d = q / tiles, t = q % tiles;
+      const int i0 = 4 * (t / nb), c0 = 4 * (t % nb);
+      const float* tr = invT_r + d * nn + i0;
+      const float* ti = invT_i + d * nn + i0;
+      const float* jr = J_r + d * nn + c0;
+      const float* ji = J_i + d * nn + c0;
+      float ar[4][4], ai[4][4];
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) ar[a][b] = ai[a][b] = 0.f;
+      const bool full = (i0 + 4 <= n) && (c0 + 4 <= n);
       for (int j = 0; j < n; ++j) {
-        const float xr = ir[j], xi = ii[j], yr = jr[j * n], yi = ji[j * n];
-        ar += xr * yr - xi * yi;
-        ai += xr * yi + xi * yr;
+        float xr[4], xi[4], yr[4], yi[4];
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+          const bool oa = full || i0 + a < n, ob = full || c0 + a < n;
+          xr[a] = oa ? tr[j * n + a] : 0.f;
+          xi[a] = oa ? ti[j * n + a] : 0.f;
+          yr[a] = ob ? jr[j * n + a] : 0.f;
+          yi[a] = ob ? ji[j * n + a] : 0.f;
+        }
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+          for (int b = 0; b < 4; ++b) {
+            ar[a][b] = fmaf(xr[a], yr[b], ar[a][b]);
+            ar[a][b] = fmaf(-xi[a], yi[b], ar[a][b]);
+            ai[a][b] = fmaf(xr[a], yi[b], ai[a][b]);
+            ai[a][b] = fmaf(xi[a], yr[b], ai[a][b]);
+          }
       }
-      M_r[q] = ar;
-      M_i[q] = ai;
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b)
+          if (i0 + a < n && c0 + b < n) {
+            M_r[d * nn + (i0 + a) * n + c0 + b] = ar[a][b];
+            M_i[d * nn + (i0 + a) * n + c0 + b] = ai[a][b];
+          }
     }
     __syncthreads();
-    for (int q = tid; q < db * n; q += nt) {
-      const int d = q / n, i = q % n;
+    for (int q = tid; q < db * tiles; q += nt) {
+      const int d = q / tiles, t = q % tiles;
+      const int i0 = 4 * (t / nb), c0 = 4 * (t % nb);
       const float* mr = M_r + d * nn;
       const float* mi = M_i + d * nn;
-      float ar = 0.f, ai = 0.f;
-      for (int i2 = 0; i2 < n; ++i2) {
-        const float xr = mr[i * n + i2], xi = mi[i * n + i2], yr = mr[i2 * n + i], yi = mi[i2 * n + i];
-        ar += xr * yr - xi * yi;
-        ai += xr * yi + xi * yr;
-      }
-      p1r[q] = mr[i * n + i];
-      p1i[q] = mi[i * n + i];
-      p2r[q] = ar;
-      p2i[q] = ai;
+      float s1r = 0.f, s1i = 0.f, s2r = 0.f, s2i = 0.f;
+      for (int a = 0; a < 4; ++a)
+        for (int b = 0; b < 4; ++b) {
+          const int i = i0 + a, i2 = c0 + b;
+          if (i >= n || i2 >= n) continue;
+          const float xr = mr[i * n + i2], xi = mi[i * n + i2], yr = mr[i2 * n + i], yi = mi[i2 * n + i];
+          s2r += xr * yr - xi * yi;
+          s2i += xr * yi + xi * yr;
+          if (i == i2) {
+            s1r += xr;
+            s1i += xi;
+          }
+        }
+      p1r[q] = s1r;
+      p1i[q] = s1i;
+      p2r[q] = s2r;
+      p2i[q] = s2i;
     }
     __syncthreads();
     for (int d = tid; d < db; d += nt) {
       float s1r = 0.f, s1i = 0.f, s2r = 0.f, s2i = 0.f;
-      for (int i = 0; i < n; ++i) {
-        s1r += p1r[d * n + i];
-        s1i += p1i[d * n + i];
-        s2r += p2r[d * n + i];
-        s2i += p2i[d * n + i];
+      for (int t = 0; t < tiles; ++t) {
+        s1r += p1r[d * tiles + t];
+        s1i += p1i[d * tiles + t];
+        s2r += p2r[d * tiles + t];
+        s2i += p2i[d * tiles + t];
       }
       if (kk < K) {
         det_grad[((w * D + d0 + d) * K + kk) * 2] = s1r;
@@ -423,7 +474,9 @@ int solid_dims(const jaqmc_solid_config* c, int track, FermiDims* d) {
 
 size_t logdet_c_smem(int db, int n) {
   const size_t nn = (size_t)n * n;
-  return 16 * (size_t)db + sizeof(float) * (6 * db * nn + 7 * (size_t)db * n + 6 * (size_t)db) + 32;
+  const size_t nb = (size_t)(n + 3) / 4;
+  const size_t np = nb * nb > (size_t)n ? nb * nb : (size_t)n;
+  return 16 * (size_t)db + sizeof(float) * (8 * db * nn + 3 * (size_t)db * n + 4 * (size_t)db * np + 6 * (size_t)db) + 32;
 }
 }  // namespace
 
@@ -505,7 +558,9 @@ int jq_solid_forward(const jaqmc_solid_config* c, const jaqmc_solid_params* p, c
   }
   {
     int DB = d.D;
-    while (DB > 1 && logdet_c_smem(DB, n) > 96 * 1024) DB = (DB + 1) / 2;
+    // several resident blocks per SM hide each other's slab loads and barriers: at most ~72 KB per block
+    // (n = 32: two determinants, 128 register tiles, 128 threads)
+    while (DB > 1 && logdet_c_smem(DB, n) > 72 * 1024) DB = (DB + 1) / 2;
     size_t smem = logdet_c_smem(DB, n);
     JQ_REQUIRE(smem <= 200 * 1024, JQ_ERR_UNSUPPORTED, "solid: %d electrons need %zu bytes of shared memory", n, smem);
 #ifndef JAQMC_HOST_EMU
@@ -516,7 +571,9 @@ int jq_solid_forward(const jaqmc_solid_config* c, const jaqmc_solid_params* p, c
 #endif
     const long long blocks = W * ((d.D + DB - 1) / DB);
     jq_prof_work((double)W * d.D * 8.0 * n * n * n * (track ? 2 * (d.C - 1) + 1 : 0.34), 8.0 * (double)W * d.D * d.C * n * n);
-    JQ_LAUNCH(k_logdet_c, dim3((unsigned)blocks), dim3(256), smem, st, b.orb_r, b.orb_i, n, d.D, d.C, DB, b.det_ld,
+    const int tiles_blk = DB * ((n + 3) / 4) * ((n + 3) / 4);
+    const int nthr = (track && tiles_blk <= 128) ? 128 : 256;
+    JQ_LAUNCH(k_logdet_c, dim3((unsigned)blocks), dim3(nthr), smem, st, b.orb_r, b.orb_i, n, d.D, d.C, DB, b.det_ld,
               b.det_grad, b.det_lap);
     JQ_CHECK_LAUNCH();
   }
