@@ -344,6 +344,37 @@ __device__ __forceinline__ float attn_fetch(const JqAttnOperand& t, long long w,
   return base[(long long)(1 + k % 3) * t.ld];
 }
 
+// One component of one head of an operand -> shared tile dst[i][d] (row stride ldh).  Device build: dense operands go
+// through 4-byte cp.async, so that a thread's ~30 element loads are all in flight together (the plain
+// load -> store loop paid the global-memory latency once per element: 30 % of the kernel's stall samples, r2 profile);
+// the caller commits / waits.  Local1 operands (a single electron's columns) are mostly zeros: stored directly.
+__device__ __forceinline__ void attn_stage(float* dst, const JqAttnOperand& t, long long w, int n, int comp, int col0,
+                                           int Cd, int dh, int ldh, int tid, int nt) {
+  const int ndh = n * dh;
+#ifndef JAQMC_HOST_EMU
+  if (t.C == Cd) {
+    const float* base = t.p + ((w * n) * (long long)t.C + comp) * t.ld + col0;
+    const long long istride = (long long)t.C * t.ld;
+    const unsigned d0 = (unsigned)__cvta_generic_to_shared(dst);
+    for (int x = tid; x < ndh; x += nt) {
+      const int i = x / dh, d = x - i * dh;
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d0 + 4u * (unsigned)(i * ldh + d)), "l"(base + i * istride + d));
+    }
+    return;
+  }
+#endif
+  for (int x = tid; x < ndh; x += nt) {
+    const int i = x / dh, d = x % dh;
+    dst[i * ldh + d] = attn_fetch(t, w, n, i, comp, col0 + d, Cd);
+  }
+}
+__device__ __forceinline__ void attn_stage_wait() {
+#ifndef JAQMC_HOST_EMU
+  asm volatile("cp.async.commit_group;");
+  asm volatile("cp.async.wait_group 0;");
+#endif
+}
+
 __global__ void k_attention_fl(JqAttnOperand q, JqAttnOperand k, JqAttnOperand v, float* __restrict__ out, int ldo,
                                int n, int H, int dh, int track) {
   JQ_DYN_SMEM(float, sm);
@@ -370,6 +401,8 @@ __global__ void k_attention_fl(JqAttnOperand q, JqAttnOperand k, JqAttnOperand v
   const int K = track ? 3 * n : 0;
   const float scale = rsqrtf((float)dh);
   const int ndh = n * dh;
+  const int nbq = (n + 3) / 4, nbd = (dh + 3) / 4;
+  const int tiles_a = nbq * nbq, tiles_o = nbq * nbd;
 
   for (int x = tid; x < ndh; x += nt) {
     int i = x / dh, d = x % dh;
@@ -414,24 +447,53 @@ __global__ void k_attention_fl(JqAttnOperand q, JqAttnOperand k, JqAttnOperand v
   for (int kk = 0; kk < K; ++kk) {
     const int comp = 1 + kk;
     __syncthreads();
-    for (int x = tid; x < ndh; x += nt) {
-      int i = x / dh, d = x % dh;
-      qJ[i * ldh + d] = attn_fetch(q, w, n, i, comp, q.off + h * dh + d, Cd);
-      kJ[i * ldh + d] = attn_fetch(k, w, n, i, comp, k.off + h * dh + d, Cd);
-      vJ[i * ldh + d] = attn_fetch(v, w, n, i, comp, v.off + h * dh + d, Cd);
-    }
+    attn_stage(qJ, q, w, n, comp, q.off + h * dh, Cd, dh, ldh, tid, nt);
+    attn_stage(kJ, k, w, n, comp, k.off + h * dh, Cd, dh, ldh, tid, nt);
+    attn_stage(vJ, v, w, n, comp, v.off + h * dh, Cd, dh, ldh, tid, nt);
+    attn_stage_wait();
     __syncthreads();
-    for (int x = tid; x < nn; x += nt) {
-      int i = x / n, j = x % n;
-      float a1 = 0.f, a2 = 0.f;
-      for (int d = 0; d < dh; ++d) {
-        float qj = qJ[i * ldh + d], kj = kJ[j * ldh + d];
-        a1 = fmaf(qj, k0[j * ldh + d], a1);
-        a1 = fmaf(q0[i * ldh + d], kj, a1);
-        a2 = fmaf(qj, kj, a2);
+    // logit Jacobians in 4 x 4 register tiles (r2): 16 shared-memory words per 48 multiply-adds instead of 4 per 3 --
+    // the kernel is bound by the shared-memory pipe
+    for (int x = tid; x < tiles_a; x += nt) {
+      const int i0 = 4 * (x / nbq), j0 = 4 * (x % nbq);
+      int ir[4], jr[4];
+#pragma unroll
+      for (int a = 0; a < 4; ++a) {
+        ir[a] = ((i0 + a < n) ? i0 + a : n - 1) * ldh;
+        jr[a] = ((j0 + a < n) ? j0 + a : n - 1) * ldh;
       }
-      aJ[x] = a1 * scale;
-      aL[x] = fmaf(2.0f * scale, a2, aL[x]);
+      float a1[4][4], a2[4][4];
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) a1[a][b] = a2[a][b] = 0.f;
+      for (int d = 0; d < dh; ++d) {
+        float qj[4], qv[4], kj[4], kv[4];
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+          qj[a] = qJ[ir[a] + d];
+          qv[a] = q0[ir[a] + d];
+          kj[a] = kJ[jr[a] + d];
+          kv[a] = k0[jr[a] + d];
+        }
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+          for (int b = 0; b < 4; ++b) {
+            a1[a][b] = fmaf(qj[a], kv[b], a1[a][b]);
+            a1[a][b] = fmaf(qv[a], kj[b], a1[a][b]);
+            a2[a][b] = fmaf(qj[a], kj[b], a2[a][b]);
+          }
+      }
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b)
+          if (i0 + a < n && j0 + b < n) {
+            const int xx = (i0 + a) * n + j0 + b;
+            aJ[xx] = a1[a][b] * scale;
+            aL[xx] = fmaf(2.0f * scale, a2[a][b], aL[xx]);
+          }
     }
     __syncthreads();
     for (int i = tid; i < n; i += nt) {
@@ -453,29 +515,54 @@ __global__ void k_attention_fl(JqAttnOperand q, JqAttnOperand k, JqAttnOperand v
       for (int m = 0; m < n; ++m) acc = fmaf(wJ[i * n + m], aJ[i * n + m], acc);
       t2[i] += acc;
     }
-    for (int x = tid; x < ndh; x += nt) {
-      int i = x / dh, d = x % dh;
-      float acc = 0.f, acc2 = 0.f;
+    // oJ = wJ v + w vJ, oL += 2 wJ vJ in 4 (electrons) x 4 (features) register tiles
+    for (int x = tid; x < tiles_o; x += nt) {
+      const int i0 = 4 * (x / nbd), d0 = 4 * (x % nbd);
+      int ir[4];
+#pragma unroll
+      for (int a = 0; a < 4; ++a) ir[a] = ((i0 + a < n) ? i0 + a : n - 1) * n;
+      float acc[4][4], acc2[4][4];
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) acc[a][b] = acc2[a][b] = 0.f;
       for (int j = 0; j < n; ++j) {
-        float wj = wJ[i * n + j];
-        float vj = vJ[j * ldh + d];
-        acc = fmaf(wj, v0[j * ldh + d], acc);
-        acc = fmaf(wgt[i * n + j], vj, acc);
-        acc2 = fmaf(wj, vj, acc2);
+        float wj[4], wv[4], vv[4], vj[4];
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+          wj[a] = wJ[ir[a] + j];
+          wv[a] = wgt[ir[a] + j];
+          const int dd = (d0 + a < dh) ? d0 + a : dh - 1;
+          vv[a] = v0[j * ldh + dd];
+          vj[a] = vJ[j * ldh + dd];
+        }
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+          for (int b = 0; b < 4; ++b) {
+            acc[a][b] = fmaf(wj[a], vv[b], acc[a][b]);
+            acc[a][b] = fmaf(wv[a], vj[b], acc[a][b]);
+            acc2[a][b] = fmaf(wj[a], vj[b], acc2[a][b]);
+          }
       }
-      out[((w * n + i) * (long long)Cd + comp) * ldo + h * dh + d] = acc;
-      oL[i * ldh + d] = fmaf(2.0f, acc2, oL[i * ldh + d]);
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b)
+          if (i0 + a < n && d0 + b < dh) {
+            const int i = i0 + a, d = d0 + b;
+            out[((w * n + i) * (long long)Cd + comp) * ldo + h * dh + d] = acc[a][b];
+            oL[i * ldh + d] = fmaf(2.0f, acc2[a][b], oL[i * ldh + d]);
+          }
     }
   }
   // Laplacian row
   __syncthreads();
   const int cl = Cd - 1;
-  for (int x = tid; x < ndh; x += nt) {
-    int i = x / dh, d = x % dh;
-    qJ[i * ldh + d] = attn_fetch(q, w, n, i, cl, q.off + h * dh + d, Cd);
-    kJ[i * ldh + d] = attn_fetch(k, w, n, i, cl, k.off + h * dh + d, Cd);
-    vJ[i * ldh + d] = attn_fetch(v, w, n, i, cl, v.off + h * dh + d, Cd);
-  }
+  attn_stage(qJ, q, w, n, cl, q.off + h * dh, Cd, dh, ldh, tid, nt);
+  attn_stage(kJ, k, w, n, cl, k.off + h * dh, Cd, dh, ldh, tid, nt);
+  attn_stage(vJ, v, w, n, cl, v.off + h * dh, Cd, dh, ldh, tid, nt);
+  attn_stage_wait();
   __syncthreads();
   for (int x = tid; x < nn; x += nt) {
     int i = x / n, j = x % n;
