@@ -5,6 +5,7 @@
 #include "wf.cuh"
 
 thread_local long long jq_launch_counter = 0;
+thread_local JqPrepCache jq_prep = {};
 static thread_local char jq_err[512] = "";
 
 void jq_set_error(const char* fmt, ...) {
@@ -164,8 +165,31 @@ static size_t wf_ws_bytes(const jaqmc_wavefunction* wf, long long W, int track) 
   }
 }
 
+static int wf_forward_impl(const jaqmc_wavefunction* wf, const jaqmc_system* sys, const float* electrons, long long W,
+                           int track, void* ws, size_t ws_bytes, JqWfOut out, cudaStream_t st);
+
+// Weight-split cache scope (JqPrepCache): `begin` at the start of an API call that may run several forwards of the same
+// network with the same walker-tile shape, `end` before returning.  The first forward fills, later ones reuse.
+#define JQ_PREP_BYTES ((size_t)24 << 20)
+static void prep_begin(void* base, size_t bytes) {
+  jq_prep.base = (float*)base;
+  jq_prep.cap = (long long)(bytes / sizeof(float));
+  jq_prep.used = 0;
+  jq_prep.n = jq_prep.cur = 0;
+  jq_prep.mode = base ? 1 : 0;
+}
+static void prep_end() { jq_prep.mode = 0; }
+
 static int wf_forward(const jaqmc_wavefunction* wf, const jaqmc_system* sys, const float* electrons, long long W,
                       int track, void* ws, size_t ws_bytes, JqWfOut out, cudaStream_t st) {
+  jq_prep.cur = 0;
+  const int rc = wf_forward_impl(wf, sys, electrons, W, track, ws, ws_bytes, out, st);
+  if (jq_prep.mode == 1) jq_prep.mode = 2;   // the launch sequence is recorded: reuse from the next forward on
+  return rc;
+}
+
+static int wf_forward_impl(const jaqmc_wavefunction* wf, const jaqmc_system* sys, const float* electrons, long long W,
+                           int track, void* ws, size_t ws_bytes, JqWfOut out, cudaStream_t st) {
   switch (wf->kind) {
     case JAQMC_WF_FERMINET:
       return jq_ferminet_forward((const jaqmc_ferminet_config*)wf->config, (const jaqmc_ferminet_params*)wf->params,
@@ -233,7 +257,7 @@ extern "C" size_t jaqmc_b200_workspace_bytes(const jaqmc_wavefunction* wf, int64
   }
   size_t api = api_scratch_bytes(n, n_walkers);
   if (wf->kind == JAQMC_WF_SOLID_FERMINET) api = 2 * api + 4 * 256 + (size_t)n_walkers * 16;  // complex grad / lap / e_kin, logpsi planes
-  return wf_ws_bytes(wf, n_walkers, track) + (api > mh ? api : mh) + 256;
+  return wf_ws_bytes(wf, n_walkers, track) + (api > mh ? api : mh) + (track ? 0 : JQ_PREP_BYTES) + 1024;
 }
 
 extern "C" int jaqmc_b200_logpsi(const jaqmc_wavefunction* wf, const jaqmc_system* sys, const float* electrons,
@@ -574,6 +598,16 @@ static int mh_step_impl(const jaqmc_wavefunction* wf, const jaqmc_system* sys, f
   float* lp2 = ar.take<float>(W);
   float* sg = ar.take<float>(W);
   JQ_REQUIRE(workspace && ar.off <= workspace_bytes, JQ_ERR_WORKSPACE_TOO_SMALL, "mh_step: workspace too small");
+  // weight-split cache for the n_steps + 1 forwards, when the workspace has room for it next to a full-batch pass
+  struct PrepScope {
+    ~PrepScope() { prep_end(); }
+  } prep_scope;
+  if (workspace_bytes >= ar.off + wf_ws_bytes(wf, W, 0) + JQ_PREP_BYTES + 256) {
+    float* prep = ar.take<float>(JQ_PREP_BYTES / sizeof(float));
+    prep_begin(prep, JQ_PREP_BYTES);
+  } else {
+    prep_begin(nullptr, 0);
+  }
   size_t avail = workspace_bytes - ar.off;
   long long tile = fit_tile(wf, W, 0, avail);
   JQ_REQUIRE(tile >= 1, JQ_ERR_WORKSPACE_TOO_SMALL, "mh_step: workspace of %zu bytes cannot hold one walker", workspace_bytes);
@@ -660,6 +694,15 @@ extern "C" int jaqmc_b200_psi_ratios(const jaqmc_wavefunction* wf, const jaqmc_s
   float* lp0 = ar.take<float>(W);
   float* sg0 = ar.take<float>(W);
   JQ_REQUIRE(workspace && ar.off <= workspace_bytes, JQ_ERR_WORKSPACE_TOO_SMALL, "psi_ratios: workspace too small");
+  struct PrepScope {
+    ~PrepScope() { prep_end(); }
+  } prep_scope;
+  if (workspace_bytes >= ar.off + JQ_PREP_BYTES + 64 * wf_ws_bytes(wf, 1, 0) + (size_t)64 * 3 * n * 4 + 1024) {
+    float* prep = ar.take<float>(JQ_PREP_BYTES / sizeof(float));
+    prep_begin(prep, JQ_PREP_BYTES);
+  } else {
+    prep_begin(nullptr, 0);
+  }
   // largest tile of configurations: per configuration 3n floats of positions + the pipeline's value-path workspace
   const size_t fixed = ar.off;
   auto fits = [&](long long tile) {

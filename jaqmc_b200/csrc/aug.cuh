@@ -76,6 +76,26 @@ struct JqDenseArgs {
   int tc_mode;  // 0: CTA-pair kernel (weights resident) when the shape allows, else the streaming one; 1: streaming only
 };
 int jq_launch_dense(const JqDenseArgs& a, cudaStream_t st);
+
+// Per-API-call cache of the tensor-core path's hi/lo weight splits.  The weights are constant within one call, but a
+// call may run the same network many times (jaqmc_b200_mh_step: 11 value-only forwards, psi_ratios and tiled calls:
+// one per tile): the first forward fills the cache launch by launch (mode 1), later forwards walk the same launch
+// sequence and reuse the slots (mode 2) instead of re-running k_weight_split_t -- 9 of the ~32 launches of a
+// FermiNet forward on the launch-latency-bound sampling path.  Thread-local: set and cleared by api.cu around a call.
+struct JqPrepSlot {
+  const float* w0;
+  const float* w1;
+  int k0, k1, N, k0_valid, ldw;
+  long long off;   // float offset into base, or -1: no room, this launch splits into its own scratch
+};
+struct JqPrepCache {
+  float* base;
+  long long cap, used;   // floats
+  int mode;              // 0 off, 1 fill, 2 reuse
+  int n, cur;
+  JqPrepSlot slot[96];
+};
+extern thread_local JqPrepCache jq_prep;
 bool jq_dense_tc_eligible(const JqDenseArgs& a);  // device build: will this launch take the tcgen05 kernel?
 size_t jq_dense_tc_scratch_floats(int k_total, int n_out);
 // out = act(y) or (res + act(y))/sqrt(2); act = tanh with the forward-Laplacian rule.  In-place allowed.

@@ -1289,8 +1289,32 @@ int jq_launch_dense_tc(const JqDenseArgs& a, cudaStream_t st, bool* handled) {
   }
   const int kt = a.k0 + a.k1;
   float* wh = a.wscratch;
-  float* wl = a.wscratch + (size_t)kt * a.N;
+  bool need_split = true;
   {
+    JqPrepCache& pc = jq_prep;
+    const int ldw_ = a.ldw ? a.ldw : a.N, kv_ = a.k0_valid ? a.k0_valid : a.k0;
+    if (pc.mode == 1 && pc.n < (int)(sizeof(pc.slot) / sizeof(pc.slot[0]))) {
+      JqPrepSlot& sl = pc.slot[pc.n++];
+      sl.w0 = a.w0; sl.w1 = a.w1; sl.k0 = a.k0; sl.k1 = a.k1; sl.N = a.N; sl.k0_valid = kv_; sl.ldw = ldw_;
+      const long long need = ((long long)2 * kt * a.N + 63) / 64 * 64;
+      if (pc.base && pc.used + need <= pc.cap) {
+        sl.off = pc.used;
+        pc.used += need;
+        wh = pc.base + sl.off;
+      } else {
+        sl.off = -1;
+      }
+    } else if (pc.mode == 2 && pc.cur < pc.n) {
+      const JqPrepSlot& sl = pc.slot[pc.cur++];
+      if (sl.off >= 0 && sl.w0 == a.w0 && sl.w1 == a.w1 && sl.k0 == a.k0 && sl.k1 == a.k1 && sl.N == a.N &&
+          sl.k0_valid == kv_ && sl.ldw == ldw_) {
+        wh = pc.base + sl.off;
+        need_split = false;
+      }
+    }
+  }
+  float* wl = wh + (size_t)kt * a.N;
+  if (need_split) {
     long long items = (long long)kt * a.N;
     int grid = jq_cdiv(items, 256);
     if (grid > 148 * 4) grid = 148 * 4;
