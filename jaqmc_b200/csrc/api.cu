@@ -172,6 +172,7 @@ static int wf_forward_impl(const jaqmc_wavefunction* wf, const jaqmc_system* sys
 // network with the same walker-tile shape, `end` before returning.  The first forward fills, later ones reuse.
 #define JQ_PREP_BYTES ((size_t)24 << 20)
 static void prep_begin(void* base, size_t bytes) {
+  jq_prep.collect = 0;
   jq_prep.base = (float*)base;
   jq_prep.cap = (long long)(bytes / sizeof(float));
   jq_prep.used = 0;
@@ -257,7 +258,7 @@ extern "C" size_t jaqmc_b200_workspace_bytes(const jaqmc_wavefunction* wf, int64
   }
   size_t api = api_scratch_bytes(n, n_walkers);
   if (wf->kind == JAQMC_WF_SOLID_FERMINET) api = 2 * api + 4 * 256 + (size_t)n_walkers * 16;  // complex grad / lap / e_kin, logpsi planes
-  return wf_ws_bytes(wf, n_walkers, track) + (api > mh ? api : mh) + (track ? 0 : JQ_PREP_BYTES) + 1024;
+  return wf_ws_bytes(wf, n_walkers, track) + (api > mh ? api : mh) + JQ_PREP_BYTES + 1024;
 }
 
 extern "C" int jaqmc_b200_logpsi(const jaqmc_wavefunction* wf, const jaqmc_system* sys, const float* electrons,
@@ -395,6 +396,17 @@ extern "C" int jaqmc_b200_local_energy(const jaqmc_wavefunction* wf, const jaqmc
   float* ep = e_pot ? e_pot : ar.take<float>(W);
   float* sg = sign ? sign : ar.take<float>(W);
   JQ_REQUIRE(workspace && ar.off <= workspace_bytes, JQ_ERR_WORKSPACE_TOO_SMALL, "local_energy: workspace too small");
+  // weight-split cache (one split kernel per evaluation for the pipelines that can list their dense launches; shared by
+  // the walker tiles otherwise), when the workspace has room for it next to a full-batch pass
+  struct PrepScope {
+    ~PrepScope() { prep_end(); }
+  } prep_scope;
+  if (workspace_bytes >= ar.off + wf_ws_bytes(wf, W, 1) + JQ_PREP_BYTES + 256) {
+    float* prep = ar.take<float>(JQ_PREP_BYTES / sizeof(float));
+    prep_begin(prep, JQ_PREP_BYTES);
+  } else {
+    prep_begin(nullptr, 0);
+  }
   size_t avail = workspace_bytes - ar.off;
   long long tile = fit_tile(wf, W, 1, avail);
   JQ_REQUIRE(tile >= 1, JQ_ERR_WORKSPACE_TOO_SMALL, "local_energy: workspace of %zu bytes cannot hold one walker",

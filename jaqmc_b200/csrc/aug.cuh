@@ -82,20 +82,27 @@ int jq_launch_dense(const JqDenseArgs& a, cudaStream_t st);
 // one per tile): the first forward fills the cache launch by launch (mode 1), later forwards walk the same launch
 // sequence and reuse the slots (mode 2) instead of re-running k_weight_split_t -- 9 of the ~32 launches of a
 // FermiNet forward on the launch-latency-bound sampling path.  Thread-local: set and cleared by api.cu around a call.
+// A pipeline that knows its dense launches up front (FermiNet) can do better still: a COLLECT pass walks the launch
+// sequence without launching anything (jq_launch_dense only records the tensor-core launches' weights), one
+// multi-segment kernel splits them all (jq_prep_flush), and the real pass finds every split by key -- one launch
+// instead of nine per local-energy evaluation, which matters for the 512-walker shard of the 8-GPU run.
 struct JqPrepSlot {
   const float* w0;
   const float* w1;
   int k0, k1, N, k0_valid, ldw;
   long long off;   // float offset into base, or -1: no room, this launch splits into its own scratch
+  int pending;     // recorded by the collect pass, not split yet
 };
 struct JqPrepCache {
   float* base;
   long long cap, used;   // floats
-  int mode;              // 0 off, 1 fill, 2 reuse
+  int mode;              // 0 off, 1 fill (launch by launch), 2 reuse (lookup by key)
+  int collect;           // 1: dry pass -- launchers record / skip instead of launching
   int n, cur;
   JqPrepSlot slot[96];
 };
 extern thread_local JqPrepCache jq_prep;
+int jq_prep_flush(cudaStream_t st);   // splits every pending slot with one kernel (device build; no-op in the emulation)
 bool jq_dense_tc_eligible(const JqDenseArgs& a);  // device build: will this launch take the tcgen05 kernel?
 size_t jq_dense_tc_scratch_floats(int k_total, int n_out);
 // out = act(y) or (res + act(y))/sqrt(2); act = tanh with the forward-Laplacian rule.  In-place allowed.

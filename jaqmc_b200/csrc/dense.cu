@@ -341,6 +341,7 @@ int jq_launch_dense(const JqDenseArgs& a, cudaStream_t st) {
   int rc = jq_launch_dense_tc(a, st, &handled);
   if (rc != JQ_OK) return rc;
   if (handled) return JQ_OK;
+  if (jq_prep.collect) return JQ_OK;   // dry pass of the weight-split cache: CUDA-core launches have nothing to record
 #endif
   if (dense_small_eligible(a)) {
     // ~256 rows per block: with one component per group (sampling path) a 32-group tile would be smaller than the
@@ -655,6 +656,7 @@ bool jq_launch_pair_layer_fused(const float* h2, int K, const float* w0, const f
   *rc = JQ_OK;
   static const bool disabled = getenv("JAQMC_B200_UNFUSED_PAIR_LAYER") != nullptr;   // A/B switch
   if (disabled || N != 32 || (K != 4 && K != 32) || (residual && K != 32) || (reinterpret_cast<uintptr_t>(h2) & 15)) return false;
+  if (jq_prep.collect) return true;   // dry pass: same decision, nothing launched
   const long long WJ = (long long)W * sp.n();
   if (WJ <= 0) return true;
   long long blocks = jq_cdiv(WJ, 8);   // one (walker, j) column per warp

@@ -1157,6 +1157,35 @@ __global__ void k_weight_split_t(const float* __restrict__ w0, int k0, const flo
   }
 }
 
+// All pending splits of the cache in one launch: the segments' items are laid end to end.
+struct SplitSeg {
+  const float* w0;
+  const float* w1;
+  float* wh;
+  int k0, k1, N, ldw, kv;
+  long long start;   // first global item of the segment
+};
+struct SplitBatch {
+  SplitSeg seg[16];
+  int n;
+  long long total;
+};
+__global__ void k_weight_split_multi(const __grid_constant__ SplitBatch b) {
+  for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < b.total; g += (long long)gridDim.x * blockDim.x) {
+    int s = 0;
+    while (s + 1 < b.n && g >= b.seg[s + 1].start) ++s;
+    const SplitSeg& sg = b.seg[s];
+    const long long i = g - sg.start;
+    const int kt = sg.k0 + sg.k1;
+    const int k = (int)(i % kt);
+    const int f = (int)(i / kt);
+    const float v = (k < sg.k0) ? (k < sg.kv ? sg.w0[(long long)k * sg.ldw + f] : 0.f) : sg.w1[(long long)(k - sg.k0) * sg.ldw + f];
+    const float h = tf32_rna(v);
+    sg.wh[i] = h;
+    sg.wh[(long long)kt * sg.N + i] = tf32_rna(v - h);
+  }
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -1194,6 +1223,33 @@ int pick_groups_per_tile(int C) {
 }  // namespace
 
 size_t jq_dense_tc_scratch_floats(int k_total, int n_out) { return (size_t)2 * k_total * n_out; }
+
+int jq_prep_flush(cudaStream_t st) {
+  JqPrepCache& pc = jq_prep;
+  int i = 0;
+  while (i < pc.n) {
+    SplitBatch b;
+    memset(&b, 0, sizeof(b));
+    long long total = 0;
+    for (; i < pc.n && b.n < 16; ++i) {
+      JqPrepSlot& sl = pc.slot[i];
+      if (!sl.pending || sl.off < 0) continue;
+      SplitSeg& sg = b.seg[b.n++];
+      sg.w0 = sl.w0; sg.w1 = sl.w1; sg.wh = pc.base + sl.off;
+      sg.k0 = sl.k0; sg.k1 = sl.k1; sg.N = sl.N; sg.ldw = sl.ldw; sg.kv = sl.k0_valid;
+      sg.start = total;
+      total += (long long)(sl.k0 + sl.k1) * sl.N;
+      sl.pending = 0;
+    }
+    if (b.n == 0) break;
+    b.total = total;
+    int grid = jq_cdiv(total, 256);
+    if (grid > 148 * 8) grid = 148 * 8;
+    JQ_LAUNCH(k_weight_split_multi, dim3(grid), dim3(256), 0, st, b);
+    JQ_CHECK_LAUNCH();
+  }
+  return JQ_OK;
+}
 
 static bool pair_plan(const JqDenseArgs& a, int sm_count, TcParams* p, int* smem_bytes);
 
@@ -1293,24 +1349,41 @@ int jq_launch_dense_tc(const JqDenseArgs& a, cudaStream_t st, bool* handled) {
   {
     JqPrepCache& pc = jq_prep;
     const int ldw_ = a.ldw ? a.ldw : a.N, kv_ = a.k0_valid ? a.k0_valid : a.k0;
-    if (pc.mode == 1 && pc.n < (int)(sizeof(pc.slot) / sizeof(pc.slot[0]))) {
-      JqPrepSlot& sl = pc.slot[pc.n++];
-      sl.w0 = a.w0; sl.w1 = a.w1; sl.k0 = a.k0; sl.k1 = a.k1; sl.N = a.N; sl.k0_valid = kv_; sl.ldw = ldw_;
-      const long long need = ((long long)2 * kt * a.N + 63) / 64 * 64;
-      if (pc.base && pc.used + need <= pc.cap) {
-        sl.off = pc.used;
-        pc.used += need;
-        wh = pc.base + sl.off;
-      } else {
-        sl.off = -1;
+    auto same = [&](const JqPrepSlot& sl) {
+      return sl.w0 == a.w0 && sl.w1 == a.w1 && sl.k0 == a.k0 && sl.k1 == a.k1 && sl.N == a.N && sl.k0_valid == kv_ &&
+             sl.ldw == ldw_;
+    };
+    if (pc.collect || pc.mode == 1) {
+      int found = -1;
+      for (int i = 0; i < pc.n; ++i)
+        if (same(pc.slot[i])) found = i;
+      if (found < 0 && pc.n < (int)(sizeof(pc.slot) / sizeof(pc.slot[0]))) {
+        JqPrepSlot& sl = pc.slot[pc.n];
+        sl.w0 = a.w0; sl.w1 = a.w1; sl.k0 = a.k0; sl.k1 = a.k1; sl.N = a.N; sl.k0_valid = kv_; sl.ldw = ldw_;
+        const long long need = ((long long)2 * kt * a.N + 63) / 64 * 64;
+        sl.pending = 0;
+        if (pc.base && pc.used + need <= pc.cap) {
+          sl.off = pc.used;
+          pc.used += need;
+          sl.pending = pc.collect ? 1 : 0;
+          found = pc.n;
+        } else {
+          sl.off = -1;
+        }
+        ++pc.n;
       }
-    } else if (pc.mode == 2 && pc.cur < pc.n) {
-      const JqPrepSlot& sl = pc.slot[pc.cur++];
-      if (sl.off >= 0 && sl.w0 == a.w0 && sl.w1 == a.w1 && sl.k0 == a.k0 && sl.k1 == a.k1 && sl.N == a.N &&
-          sl.k0_valid == kv_ && sl.ldw == ldw_) {
-        wh = pc.base + sl.off;
-        need_split = false;
+      if (pc.collect) {   // dry pass: nothing is launched
+        *handled = true;
+        return JQ_OK;
       }
+      if (found >= 0 && pc.slot[found].off >= 0) wh = pc.base + pc.slot[found].off;   // split below, into the cache
+    } else if (pc.mode == 2) {
+      for (int i = 0; i < pc.n; ++i)
+        if (pc.slot[i].off >= 0 && !pc.slot[i].pending && same(pc.slot[i])) {
+          wh = pc.base + pc.slot[i].off;
+          need_split = false;
+          break;
+        }
     }
   }
   float* wl = wh + (size_t)kt * a.N;

@@ -142,7 +142,7 @@ int jq_fermi_backbone(const FermiDims& d, const jaqmc_ferminet_params* p, long l
   bool g2_ready = false;   // the previous two-electron layer already produced this layer's spin-channel means
   for (int l = 0; l < d.L; ++l) {
     const int fg = d.nch * d2prev;
-    if (!g2_ready && (rc = jq_launch_pair_mean(h2, b.g2, (int)W, d.sp, d2prev, track, st))) return rc;
+    if (!g2_ready && !jq_prep.collect && (rc = jq_launch_pair_mean(h2, b.g2, (int)W, d.sp, d2prev, track, st))) return rc;
     g2_ready = false;
     JqDenseArgs a;
     memset(&a, 0, sizeof(a));
@@ -156,7 +156,7 @@ int jq_fermi_backbone(const FermiDims& d, const jaqmc_ferminet_params* p, long l
     a.act = 1;
     a.wscratch = b.wscr;
     if (l == 0) {
-      if ((rc = jq_launch_concat_layer1(b.ae, b.g2, b.x1, (int)W, d.sp, d.f1, fg, track, d.in1p, st))) return rc;
+      if (!jq_prep.collect && (rc = jq_launch_concat_layer1(b.ae, b.g2, b.x1, (int)W, d.sp, d.f1, fg, track, d.in1p, st))) return rc;
       a.src0 = b.x1;
       a.k0 = d.in1p;
       a.k0_valid = d.in1;
@@ -165,7 +165,7 @@ int jq_fermi_backbone(const FermiDims& d, const jaqmc_ferminet_params* p, long l
       if ((rc = jq_launch_dense(a, st))) return rc;
     } else {
       // walker-wide part: cadd[w][c] = [mean_up h | mean_dn h] . K[d1prev : d1prev*(1+nch)]
-      if ((rc = jq_launch_spin_mean(h, b.m, (int)W, d.sp, C, d1prev, st))) return rc;
+      if (!jq_prep.collect && (rc = jq_launch_spin_mean(h, b.m, (int)W, d.sp, C, d1prev, st))) return rc;
       JqDenseArgs am;
       memset(&am, 0, sizeof(am));
       am.src0 = b.m;
@@ -245,6 +245,10 @@ int jq_fermi_backbone(const FermiDims& d, const jaqmc_ferminet_params* p, long l
   if (d.use_last) {
     // use_last_layer: the orbitals see aggregate_features(h_one, h_two) = [h_j | spin means of h | pair means of h_two]
     // (backbone/ferminet.py:45-47,65-90), materialised once with zero padding to the tensor-core K granularity
+    if (jq_prep.collect) {
+      *h_out = b.agg;
+      return JQ_OK;
+    }
     if (!g2_ready && (rc = jq_launch_pair_mean(h2, b.g2, (int)W, d.sp, d2prev, track, st))) return rc;
     if ((rc = jq_launch_spin_mean(h, b.m, (int)W, d.sp, C, d1prev, st))) return rc;
     if ((rc = jq_launch_concat_agg(h, b.m, b.g2, b.agg, W, n, C, d1prev, d.nch * d1prev, d.nch * d2prev, d.agg_wp, st)))
@@ -276,12 +280,6 @@ int jq_ferminet_forward(const jaqmc_ferminet_config* c, const jaqmc_ferminet_par
   FermiBufs b;
   fermi_carve(d, c, W, ar, &b);
   JQ_REQUIRE(ar.ok(), JQ_ERR_WORKSPACE_TOO_SMALL, "ferminet: workspace %zu < %zu bytes", ws_bytes, ar.off);
-  // features: ae Local1 [W][n][C1][4A], ee Local2 [W][n*n][C2][4] (into h2a)
-  if ((rc = jq_launch_mol_features(electrons, sys->atoms, (int)W, d.sp, d.A, /*rescale=*/0, track, /*spin_column=*/0, b.ae, b.h2a, st)))
-    return rc;
-
-  float* h = nullptr;
-  if ((rc = jq_fermi_backbone(d, p, W, track, b, st, &h))) return rc;
   jaqmc_head_params hp;
   memset(&hp, 0, sizeof(hp));
   for (int s = 0; s < 2; ++s) {
@@ -289,5 +287,27 @@ int jq_ferminet_forward(const jaqmc_ferminet_config* c, const jaqmc_ferminet_par
     hp.env_pi[s] = p->env_pi[s];
     hp.env_sigma[s] = p->env_sigma[s];
   }
-  return jq_head_forward(fermi_head_dims(d, c), &hp, h, electrons, sys->atoms, W, b.head, b.wscr, out, st);
+  auto run = [&]() -> int {
+    int r;
+    // features: ae Local1 [W][n][C1][4A], ee Local2 [W][n*n][C2][4] (into h2a)
+    if (!jq_prep.collect &&
+        (r = jq_launch_mol_features(electrons, sys->atoms, (int)W, d.sp, d.A, /*rescale=*/0, track, /*spin_column=*/0, b.ae, b.h2a, st)))
+      return r;
+    float* h = nullptr;
+    if ((r = jq_fermi_backbone(d, p, W, track, b, st, &h))) return r;
+    return jq_head_forward(fermi_head_dims(d, c), &hp, h, electrons, sys->atoms, W, b.head, b.wscr, out, st);
+  };
+#ifndef JAQMC_HOST_EMU
+  if (jq_prep.base && jq_prep.mode == 1 && jq_prep.n == 0) {
+    // the launch sequence is known: collect the tensor-core launches' weights in a dry pass, split them all with one
+    // kernel, and let the real pass find the splits by key
+    jq_prep.collect = 1;
+    rc = run();
+    jq_prep.collect = 0;
+    if (rc) return rc;
+    if ((rc = jq_prep_flush(st))) return rc;
+    jq_prep.mode = 2;
+  }
+#endif
+  return run();
 }

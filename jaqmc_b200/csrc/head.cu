@@ -190,6 +190,7 @@ int jq_head_forward(const JqHeadDims& d, const jaqmc_head_params* p, const float
     }
     if ((rc = jq_launch_dense(a, st))) return rc;
   }
+  if (jq_prep.collect) return JQ_OK;   // dry pass of the weight-split cache: only the dense launches above matter
   JqEnvelopeArgs env;
   env.type = d.envelope_type;
   env.pi[0] = p->env_pi[0];
