@@ -375,6 +375,7 @@ __device__ __forceinline__ void attn_stage_wait() {
 #endif
 }
 
+template <int TAI, int TAJ, int TOI, int TOD>
 __global__ void k_attention_fl(JqAttnOperand q, JqAttnOperand k, JqAttnOperand v, float* __restrict__ out, int ldo,
                                int n, int H, int dh, int track) {
   JQ_DYN_SMEM(float, sm);
@@ -401,8 +402,9 @@ __global__ void k_attention_fl(JqAttnOperand q, JqAttnOperand k, JqAttnOperand v
   const int K = track ? 3 * n : 0;
   const float scale = rsqrtf((float)dh);
   const int ndh = n * dh;
-  const int nbq = (n + 3) / 4, nbd = (dh + 3) / 4;
-  const int tiles_a = nbq * nbq, tiles_o = nbq * nbd;
+  // register tiles: TAI x TAJ logits per item in the Jacobian phase, TOI electrons x TOD features in the output phase
+  const int nbi = (n + TAI - 1) / TAI, nbj = (n + TAJ - 1) / TAJ, nbo = (n + TOI - 1) / TOI, nbd = (dh + TOD - 1) / TOD;
+  const int tiles_a = nbi * nbj, tiles_o = nbo * nbd;
 
   for (int x = tid; x < ndh; x += nt) {
     int i = x / dh, d = x % dh;
@@ -455,40 +457,42 @@ __global__ void k_attention_fl(JqAttnOperand q, JqAttnOperand k, JqAttnOperand v
     // logit Jacobians in 4 x 4 register tiles (r2): 16 shared-memory words per 48 multiply-adds instead of 4 per 3 --
     // the kernel is bound by the shared-memory pipe
     for (int x = tid; x < tiles_a; x += nt) {
-      const int i0 = 4 * (x / nbq), j0 = 4 * (x % nbq);
-      int ir[4], jr[4];
+      const int i0 = TAI * (x / nbj), j0 = TAJ * (x % nbj);
+      int ir[TAI], jr[TAJ];
 #pragma unroll
-      for (int a = 0; a < 4; ++a) {
-        ir[a] = ((i0 + a < n) ? i0 + a : n - 1) * ldh;
-        jr[a] = ((j0 + a < n) ? j0 + a : n - 1) * ldh;
-      }
-      float a1[4][4], a2[4][4];
+      for (int a = 0; a < TAI; ++a) ir[a] = ((i0 + a < n) ? i0 + a : n - 1) * ldh;
 #pragma unroll
-      for (int a = 0; a < 4; ++a)
+      for (int b = 0; b < TAJ; ++b) jr[b] = ((j0 + b < n) ? j0 + b : n - 1) * ldh;
+      float a1[TAI][TAJ], a2[TAI][TAJ];
 #pragma unroll
-        for (int b = 0; b < 4; ++b) a1[a][b] = a2[a][b] = 0.f;
+      for (int a = 0; a < TAI; ++a)
+#pragma unroll
+        for (int b = 0; b < TAJ; ++b) a1[a][b] = a2[a][b] = 0.f;
       for (int d = 0; d < dh; ++d) {
-        float qj[4], qv[4], kj[4], kv[4];
+        float qj[TAI], qv[TAI], kj[TAJ], kv[TAJ];
 #pragma unroll
-        for (int a = 0; a < 4; ++a) {
+        for (int a = 0; a < TAI; ++a) {
           qj[a] = qJ[ir[a] + d];
           qv[a] = q0[ir[a] + d];
-          kj[a] = kJ[jr[a] + d];
-          kv[a] = k0[jr[a] + d];
         }
 #pragma unroll
-        for (int a = 0; a < 4; ++a)
+        for (int b = 0; b < TAJ; ++b) {
+          kj[b] = kJ[jr[b] + d];
+          kv[b] = k0[jr[b] + d];
+        }
 #pragma unroll
-          for (int b = 0; b < 4; ++b) {
+        for (int a = 0; a < TAI; ++a)
+#pragma unroll
+          for (int b = 0; b < TAJ; ++b) {
             a1[a][b] = fmaf(qj[a], kv[b], a1[a][b]);
             a1[a][b] = fmaf(qv[a], kj[b], a1[a][b]);
             a2[a][b] = fmaf(qj[a], kj[b], a2[a][b]);
           }
       }
 #pragma unroll
-      for (int a = 0; a < 4; ++a)
+      for (int a = 0; a < TAI; ++a)
 #pragma unroll
-        for (int b = 0; b < 4; ++b)
+        for (int b = 0; b < TAJ; ++b)
           if (i0 + a < n && j0 + b < n) {
             const int xx = (i0 + a) * n + j0 + b;
             aJ[xx] = a1[a][b] * scale;
@@ -517,38 +521,42 @@ __global__ void k_attention_fl(JqAttnOperand q, JqAttnOperand k, JqAttnOperand v
     }
     // oJ = wJ v + w vJ, oL += 2 wJ vJ in 4 (electrons) x 4 (features) register tiles
     for (int x = tid; x < tiles_o; x += nt) {
-      const int i0 = 4 * (x / nbd), d0 = 4 * (x % nbd);
-      int ir[4];
+      const int i0 = TOI * (x / nbd), d0 = TOD * (x % nbd);
+      int ir[TOI], dc[TOD];
 #pragma unroll
-      for (int a = 0; a < 4; ++a) ir[a] = ((i0 + a < n) ? i0 + a : n - 1) * n;
-      float acc[4][4], acc2[4][4];
+      for (int a = 0; a < TOI; ++a) ir[a] = ((i0 + a < n) ? i0 + a : n - 1) * n;
 #pragma unroll
-      for (int a = 0; a < 4; ++a)
+      for (int b = 0; b < TOD; ++b) dc[b] = (d0 + b < dh) ? d0 + b : dh - 1;
+      float acc[TOI][TOD], acc2[TOI][TOD];
 #pragma unroll
-        for (int b = 0; b < 4; ++b) acc[a][b] = acc2[a][b] = 0.f;
+      for (int a = 0; a < TOI; ++a)
+#pragma unroll
+        for (int b = 0; b < TOD; ++b) acc[a][b] = acc2[a][b] = 0.f;
       for (int j = 0; j < n; ++j) {
-        float wj[4], wv[4], vv[4], vj[4];
+        float wj[TOI], wv[TOI], vv[TOD], vj[TOD];
 #pragma unroll
-        for (int a = 0; a < 4; ++a) {
+        for (int a = 0; a < TOI; ++a) {
           wj[a] = wJ[ir[a] + j];
           wv[a] = wgt[ir[a] + j];
-          const int dd = (d0 + a < dh) ? d0 + a : dh - 1;
-          vv[a] = v0[j * ldh + dd];
-          vj[a] = vJ[j * ldh + dd];
         }
 #pragma unroll
-        for (int a = 0; a < 4; ++a)
+        for (int b = 0; b < TOD; ++b) {
+          vv[b] = v0[j * ldh + dc[b]];
+          vj[b] = vJ[j * ldh + dc[b]];
+        }
 #pragma unroll
-          for (int b = 0; b < 4; ++b) {
+        for (int a = 0; a < TOI; ++a)
+#pragma unroll
+          for (int b = 0; b < TOD; ++b) {
             acc[a][b] = fmaf(wj[a], vv[b], acc[a][b]);
             acc[a][b] = fmaf(wv[a], vj[b], acc[a][b]);
             acc2[a][b] = fmaf(wj[a], vj[b], acc2[a][b]);
           }
       }
 #pragma unroll
-      for (int a = 0; a < 4; ++a)
+      for (int a = 0; a < TOI; ++a)
 #pragma unroll
-        for (int b = 0; b < 4; ++b)
+        for (int b = 0; b < TOD; ++b)
           if (i0 + a < n && d0 + b < dh) {
             const int i = i0 + a, d = d0 + b;
             out[((w * n + i) * (long long)Cd + comp) * ldo + h * dh + d] = acc[a][b];
@@ -1037,7 +1045,9 @@ int jq_launch_attention_fl(const JqAttnOperand& q, const JqAttnOperand& k, const
              smem);
 #ifndef JAQMC_HOST_EMU
   if (smem > 48 * 1024) {
-    cudaError_t e = cudaFuncSetAttribute(k_attention_fl, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(k_attention_fl<4, 4, 4, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_attention_fl<2, 4, 2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_attention_fl<2, 2, 2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     JQ_REQUIRE(e == cudaSuccess, JQ_ERR_CUDA, "attention: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
   }
 #endif
@@ -1063,7 +1073,13 @@ int jq_launch_attention_fl(const JqAttnOperand& q, const JqAttnOperand& k, const
     }
   }
 #endif
-  JQ_LAUNCH(k_attention_fl, dim3((unsigned)(W * H)), dim3(256), smem, st, q, k, v, out, ldo, n, H, dh, track);
+#ifndef JAQMC_HOST_EMU
+  static const int tile_sel = getenv("JAQMC_B200_ATTENTION_TILES") ? atoi(getenv("JAQMC_B200_ATTENTION_TILES")) : 0;   // tuning
+  if (tile_sel == 1) JQ_LAUNCH((k_attention_fl<2, 4, 2, 4>), dim3((unsigned)(W * H)), dim3(256), smem, st, q, k, v, out, ldo, n, H, dh, track);
+  else if (tile_sel == 2) JQ_LAUNCH((k_attention_fl<2, 2, 2, 2>), dim3((unsigned)(W * H)), dim3(256), smem, st, q, k, v, out, ldo, n, H, dh, track);
+  else
+#endif
+  JQ_LAUNCH((k_attention_fl<4, 4, 4, 4>), dim3((unsigned)(W * H)), dim3(256), smem, st, q, k, v, out, ldo, n, H, dh, track);
   JQ_CHECK_LAUNCH();
   return JQ_OK;
 }
