@@ -455,6 +455,7 @@ __global__ void __launch_bounds__(256, 2) k_logdet_mma(const float* __restrict__
 // log|det| = log prod |pivot| in double.   Phase 2: the traces, see inside.
 // Shared: invp[DB][n*16+4] | scr[DB][MS]
 // ------------------------------------------------------------------------------------------------
+template <int NS>
 __global__ void __launch_bounds__(256, 2) k_logdet_small(const float* __restrict__ orb, int n, int D, int C, int DB,
                                                           float* __restrict__ det_sign, float* __restrict__ det_logabs,
                                                           float* __restrict__ det_grad, float* __restrict__ det_lap) {
@@ -549,66 +550,86 @@ __global__ void __launch_bounds__(256, 2) k_logdet_small(const float* __restrict
       // lane i2 holds column i2 of dA_c in registers and forms column i2 of M = A^-1 dA_c (the inverse is read as
       // float4 broadcasts from the row-padded copy this half-warp has just written); tr M is the sum of the lanes'
       // diagonal entries, tr M^2 = sum_{i,i2} M[i][i2] M[i2][i] needs the transposed element, exchanged through a
-      // per-determinant scratch tile.  The next slab's column is fetched before the current one is consumed.
-      // (Measured r2: a variant forming three slabs per pass over A^-1 -- a third of the shared-memory reads -- ran at
-      // 2.6 ms against 1.64 ms: register spills at the 128-register cap outweighed the saved LDS traffic.)
+      // per-determinant scratch tile.  NS slabs share one pass over A^-1 (each float4 of the inverse feeds NS columns).
+      // Measured r2 (ncu, N2 4096 walkers x 16 determinants): NS = 1 with a register prefetch of the next column 1.88 ms,
+      // NS = 2 1.38 ms (default), NS = 3 1.41 ms, NS = 4 1.63 ms (spills at the 128-register cap); dropping the kept
+      // column of M in favour of re-reading the scratch tile, or prefetching with NS = 2, both lose (1.45 - 1.55 ms).
       __syncwarp();
       {
         const float* ib = invp_w + (size_t)(on ? d : 0) * IS;
-        float* scr = invp_w + (size_t)DB * IS + (size_t)(on ? d : 0) * (nn + ((n - nn) % 32 + 32) % 32);
+        float* scr = invp_w + (size_t)DB * IS + (size_t)(on ? d : 0) * NS * (nn + ((n - nn) % 32 + 32) % 32);
         const bool act = on && hl < n;
         const float* ocol = ow + (on ? d : 0) * n + (hl < n ? hl : 0);   // column (d, i2 = hl); + (1 + kk) * DN + j * C * DN
-        float nxt[LD_NP];
-#pragma unroll
-        for (int j = 0; j < LD_NP; ++j) nxt[j] = (act && j < n) ? ocol[(long long)DN + (long long)j * C * DN] : 0.f;
         float t2acc = 0.f, trl = 0.f;
         float* gout = det_grad + (w * D + d0 + (on ? d : 0)) * (long long)K;
-        for (int kk = 0; kk < KT; ++kk) {
-          float col[LD_NP];
+        const int MS = nn + ((n - nn) % 32 + 32) % 32;
+        // NS slabs per pass over A^-1: each float4 of the inverse read from shared memory feeds NS columns.
+        for (int kk = 0; kk < KT; kk += NS) {
+          float col[NS][LD_NP];
 #pragma unroll
-          for (int j = 0; j < LD_NP; ++j) col[j] = nxt[j];
-          if (kk + 1 < KT) {
-            const float* oc = ocol + (long long)(2 + kk) * DN;
+          for (int s = 0; s < NS; ++s) {
+            const bool sv = act && kk + s < KT;
+            const float* oc = ocol + (long long)(1 + kk + s) * DN;
 #pragma unroll
-            for (int j = 0; j < LD_NP; ++j) nxt[j] = (act && j < n) ? oc[(long long)j * C * DN] : 0.f;
+            for (int j = 0; j < LD_NP; ++j) col[s][j] = (sv && j < n) ? oc[(long long)j * C * DN] : 0.f;
           }
-          float m[LD_NP];
-          float dg = 0.f;
+          float m[NS][LD_NP];
+          float dg[NS];
+#pragma unroll
+          for (int s = 0; s < NS; ++s) dg[s] = 0.f;
 #pragma unroll
           for (int i = 0; i < LD_NP; ++i) {
-            float acc = 0.f;
+            float acc[NS];
+#pragma unroll
+            for (int s = 0; s < NS; ++s) acc[s] = 0.f;
             if (i < n) {
               const float4* r4 = reinterpret_cast<const float4*>(ib + i * LD_NP);
 #pragma unroll
               for (int j4 = 0; j4 < LD_NP / 4; ++j4) {
                 const float4 v = r4[j4];
-                acc = fmaf(v.x, col[4 * j4 + 0], acc);
-                acc = fmaf(v.y, col[4 * j4 + 1], acc);
-                acc = fmaf(v.z, col[4 * j4 + 2], acc);
-                acc = fmaf(v.w, col[4 * j4 + 3], acc);
+#pragma unroll
+                for (int s = 0; s < NS; ++s) {
+                  acc[s] = fmaf(v.x, col[s][4 * j4 + 0], acc[s]);
+                  acc[s] = fmaf(v.y, col[s][4 * j4 + 1], acc[s]);
+                  acc[s] = fmaf(v.z, col[s][4 * j4 + 2], acc[s]);
+                  acc[s] = fmaf(v.w, col[s][4 * j4 + 3], acc[s]);
+                }
               }
-              if (act) scr[i * n + hl] = acc;
+              if (act) {
+#pragma unroll
+                for (int s = 0; s < NS; ++s) scr[s * MS + i * n + hl] = acc[s];
+              }
             }
-            m[i] = acc;
-            if (i == hl) dg = acc;
+#pragma unroll
+            for (int s = 0; s < NS; ++s) {
+              m[s][i] = acc[s];
+              if (i == hl) dg[s] = acc[s];
+            }
           }
           __syncwarp();
-          float s2 = 0.f;
+          float s2[NS];
 #pragma unroll
-          for (int i = 0; i < LD_NP; ++i)
-            if (i < n && act) s2 = fmaf(m[i], scr[hl * n + i], s2);
-          __syncwarp();
-          if (!act) dg = 0.f;
+          for (int s = 0; s < NS; ++s) {
+            s2[s] = 0.f;
 #pragma unroll
-          for (int o = 8; o > 0; o >>= 1) {
-            dg += __shfl_xor_sync(full, dg, o);
-            s2 += __shfl_xor_sync(full, s2, o);
+            for (int i = 0; i < LD_NP; ++i)
+              if (i < n && act) s2[s] = fmaf(m[s][i], scr[s * MS + hl * n + i], s2[s]);
           }
-          if (kk < K) {
-            if (on && hl == 0) gout[kk] = dg;
-            t2acc += s2;
-          } else {
-            trl = dg;
+          __syncwarp();
+#pragma unroll
+          for (int s = 0; s < NS; ++s) {
+            float dgs = act ? dg[s] : 0.f, s2s = s2[s];
+#pragma unroll
+            for (int o = 8; o > 0; o >>= 1) {
+              dgs += __shfl_xor_sync(full, dgs, o);
+              s2s += __shfl_xor_sync(full, s2s, o);
+            }
+            if (kk + s < K) {
+              if (on && hl == 0) gout[kk + s] = dgs;
+              t2acc += s2s;
+            } else if (kk + s == K) {
+              trl = dgs;
+            }
           }
         }
         if (on && hl == 0) det_lap[w * D + d0 + d] = trl - t2acc;
@@ -1061,23 +1082,25 @@ int jq_launch_logdet(const float* orb, int W, int n, int D, int track, float* de
     return JQ_OK;
   }
   if (track && n <= LD_NP) {
-    // half-warp per determinant: 16 determinants per block
+    // half-warp per determinant: 16 determinants per block; NS derivative slabs per pass over A^-1
     const int DB = D < 16 ? D : 16;
     const size_t MS = nn + (size_t)((((int)n - (int)nn) % 32 + 32) % 32);
-    const size_t smem = sizeof(float) * ((size_t)DB * (n * LD_NP + 4) + (size_t)DB * MS) + 64;
+    static const int ns_env = getenv("JAQMC_B200_LOGDET_SLABS") ? atoi(getenv("JAQMC_B200_LOGDET_SLABS")) : 2;
+    const int NS = ns_env == 1 ? 1 : (ns_env == 3 ? 3 : 2);
+    const size_t smem = sizeof(float) * ((size_t)DB * (n * LD_NP + 4) + (size_t)DB * MS * NS) + 64;
+    auto kern = NS == 1 ? k_logdet_small<1> : NS == 3 ? k_logdet_small<3> : k_logdet_small<2>;
     if (smem > 48 * 1024) {
-      static JqPerDeviceFlag attr_set;
+      static JqPerDeviceFlag attr_set[4];
       const int dev = jq_current_device();
-      if (!attr_set.done[dev]) {
-        cudaError_t e = cudaFuncSetAttribute(k_logdet_small, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+      if (!attr_set[NS].done[dev]) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
         JQ_REQUIRE(e == cudaSuccess, JQ_ERR_CUDA, "logdet: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-        attr_set.done[dev] = true;
+        attr_set[NS].done[dev] = true;
       }
     }
     const long long blocks = (long long)W * ((D + DB - 1) / DB);
     jq_prof_work((double)W * D * (2.0 * n * n * n * ((C - 1) * 2 + 1)), 4.0 * (double)W * D * C * n * n);
-    JQ_LAUNCH(k_logdet_small, dim3((unsigned)blocks), dim3(256), smem, st, orb, n, D, C, DB, det_sign, det_logabs,
-              det_grad, det_lap);
+    JQ_LAUNCH(kern, dim3((unsigned)blocks), dim3(256), smem, st, orb, n, D, C, DB, det_sign, det_logabs, det_grad, det_lap);
     JQ_CHECK_LAUNCH();
     return JQ_OK;
   }
