@@ -1,6 +1,3 @@
-mkdir -p gpurun_out/r2x
-run() { ncu --metrics gpu__time_duration.sum --clock-control none -k regex:k_logdet_small -c 4 --csv --log-file gpurun_out/r2x/ldm_$1.csv python bench.py --steps 1 --warmup 1 --evals-per-step 1 --no-cpu-baseline --no-vmc --no-equilibrate --no-graph > gpurun_out/r2x/bm_$1.log 2>&1; }
-JAQMC_B200_LOGDET_PREFETCH=1 run 2
-JAQMC_B200_LOGDET_SLABS=3 run 3
-JAQMC_B200_LOGDET_SLABS=4 run 4
-JAQMC_B200_LOGDET_SLABS=3 python -m pytest tests -m gpu -x -q -k "logdet or parity" 2>&1 | tail -3 > gpurun_out/r2x/tests3.log
+mkdir -p gpurun_out/r2y
+python bench.py --steps 5 --warmup 3 > gpurun_out/r2y/bench_n2.json 2> gpurun_out/r2y/bench_n2.err
+JAQMC_B200_LOGDET_SLABS=1 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-vmc > gpurun_out/r2y/bench_n2_ns1.json 2> gpurun_out/r2y/bench_n2_ns1.err
