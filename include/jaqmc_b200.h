@@ -367,6 +367,18 @@ int jaqmc_b200_dense_fl(const float* x, const float* x2, const float* kernel, co
                         int32_t residual_mode, int32_t use_tensor_cores, void* workspace, size_t workspace_bytes,
                         jaqmc_stream_t stream);
 
+/* Softmax self-attention core under the forward Laplacian: replaces `attention_core` traced by forward_laplacian
+ * (wavefunction/backbone/psiformer.py attention block; backbone/lapnet/_attention.py:20-34, :113-196 for the
+ * one-electron query / key structure).  Operands are augmented tensors (n_walkers, n_electrons, C, n_heads * head_dim)
+ * with C = 3 n + 2 components {value, 3n Jacobian columns, Laplacian}; q and k may instead carry C = 5 ("local":
+ * electron i holds only its own three Jacobian columns, the rest are zero).  out is always dense.
+ *   kernel 0: the library's choice for the shape; 1: CUDA-core block kernel; 2: CUDA-core warp-per-component kernel
+ *   (n <= 14 at head_dim 64: shared-memory limit); 3: mma.sync 3xTF32 tensor-core kernel (n <= 48, head_dim 64).  A forced kernel that does not support the shape
+ *   returns JAQMC_ERR_UNSUPPORTED. */
+int jaqmc_b200_attention_fl(const float* q, const float* k, const float* v, float* out, int64_t n_walkers,
+                            int32_t n_electrons, int32_t n_heads, int32_t head_dim, int32_t q_components,
+                            int32_t k_components, int32_t kernel, jaqmc_stream_t stream);
+
 /* Building blocks of the MH step, exported for samplers that drive their own loop
  * (sampler/mcmc.py:53-54 gaussian_proposal; :128-137 accept/select). */
 int jaqmc_b200_mh_propose(const float* x1, const float* normals, const float* stddev, float* x2, int64_t count,

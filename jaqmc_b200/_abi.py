@@ -249,6 +249,11 @@ PROTOTYPES = {
         [FloatP, FloatP, FloatP, FloatP, FloatP, FloatP, FloatP, FloatP, C.c_int64, C.c_int32, C.c_int32, C.c_int32,
          C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_size_t, C.c_void_p],
     ),
+    "jaqmc_b200_attention_fl": (
+        C.c_int,
+        [FloatP, FloatP, FloatP, FloatP, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+         C.c_void_p],
+    ),
     "jaqmc_b200_mh_propose": (C.c_int, [FloatP, FloatP, FloatP, FloatP, C.c_int64, C.c_void_p]),
     "jaqmc_b200_mh_accept": (
         C.c_int,

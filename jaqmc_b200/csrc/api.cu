@@ -515,6 +515,19 @@ extern "C" int jaqmc_b200_local_energy_complex(const jaqmc_wavefunction* wf, con
   return JQ_OK;
 }
 
+extern "C" int jaqmc_b200_attention_fl(const float* q, const float* k, const float* v, float* out, int64_t n_walkers,
+                                       int32_t n_electrons, int32_t n_heads, int32_t head_dim, int32_t q_components,
+                                       int32_t k_components, int32_t kernel, jaqmc_stream_t stream) {
+  JQ_REQUIRE(n_walkers >= 0 && n_electrons >= 1 && n_heads >= 1 && head_dim >= 1, JQ_ERR_INVALID_ARGUMENT,
+             "attention_fl: bad sizes");
+  JQ_REQUIRE(kernel >= 0 && kernel <= 3, JQ_ERR_INVALID_ARGUMENT, "attention_fl: kernel selector %d", kernel);
+  JQ_REQUIRE(q && k && v && out, JQ_ERR_INVALID_ARGUMENT, "attention_fl: null operand");
+  const int F = n_heads * head_dim, Cd = 3 * n_electrons + 2;
+  JqAttnOperand qo{q, q_components, F, 0}, ko{k, k_components, F, 0}, vo{v, Cd, F, 0};
+  return jq_launch_attention_fl_sel(qo, ko, vo, out, F, n_walkers, n_electrons, n_heads, head_dim, 1, kernel,
+                                    (cudaStream_t)stream);
+}
+
 extern "C" int jaqmc_b200_dense_fl(const float* x, const float* x2, const float* kernel, const float* kernel2,
                                    const float* bias, const float* addend, const float* residual, float* out,
                                    int64_t n_groups, int32_t n_components, int32_t k0, int32_t k1, int32_t n_out,

@@ -1034,8 +1034,331 @@ k_attention_fl_warp(JqAttnOperand q, JqAttnOperand k, JqAttnOperand v, float* __
 }
 #endif
 
+
+#ifndef JAQMC_HOST_EMU
+// ------------------------------------------------------------------------------------------------
+// Same rule on the tensor cores for 16 < n <= 48, head dimension 64 (r2): mma.sync.m16n8k8 TF32 with the 3xTF32 split
+// (a = a_hi + a_lo, three products, FP32 accumulation), so the products keep FP32-level accuracy.
+// One block per (walker, head); a block holds SLOTS component slots of RT = ceil(n / 16) warps each.  Warp (slot, r)
+// owns rows 16r .. 16r+15 of every [n x n] / [n x d] matrix of the slot's current component and ALL their columns, so
+// the three phases run in its registers with no block-level barrier:
+//   A  aJ = (qJ k^T + q kJ^T)/sqrt(d), a2 = qJ kJ^T          A operands: qJ rows straight from global, q from shared;
+//                                                              B operands: k, kJ rows from shared
+//   B  abar (quad shuffles), wJ = w (aJ - abar), X += wJ (aJ - abar) + 2 w a2 / sqrt(d)
+//   C  oJ = wJ v + w vJ (stored), oL2 += wJ vJ                the accumulator fragment of wJ IS the A fragment of the
+//      next product once the contraction index is permuted (slot t <-> column 2t, slot t+4 <-> column 2t+1); the B
+//      fragments of v / vJ are read with the same permutation.
+// The Laplacian row needs only X and oL2:  with Y = X + w aL' (aL' = (qL k^T + q kL^T)/sqrt(d)),
+//   wL = Y - w rowsum(Y)   (the t2 term of the SIMT kernels cancels: sum_j wJ_ij = 0),   oL = 2 oL2 + wL v + w vL.
+// The RT warps of a slot share the staged kJ / vJ tiles (cp.async, named barrier per slot).
+// Shared (floats): q0 k0 v0 [48][68] | w [48][56] | per slot: kJ vJ [48][68]
+// ------------------------------------------------------------------------------------------------
+constexpr int AM_LD = 68;     // 68 mod 32 = 4: the (g, t) fragment loads touch 32 distinct banks
+constexpr int AM_LW = 56;     // 56 mod 32 = 24: the float2 accumulator-layout loads of w are conflict-free per half-warp
+constexpr int AM_SLOTS = 4;
+constexpr int AM_NP = 48;     // padded electron count
+
+__device__ __forceinline__ void am_split(float x, unsigned& hi, unsigned& lo) {
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(x));
+  const float r = x - __uint_as_float(hi);
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lo) : "f"(r));
+}
+__device__ __forceinline__ void am_mma(float (&c)[4], const unsigned (&a)[4], const unsigned (&b)[2]) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+// c += (ah + al)(bh + bl) without the al bl term; small products first
+__device__ __forceinline__ void am_mma3(float (&c)[4], const unsigned (&ah)[4], const unsigned (&al)[4],
+                                        const unsigned (&bh)[2], const unsigned (&bl)[2]) {
+  am_mma(c, al, bh);
+  am_mma(c, ah, bl);
+  am_mma(c, ah, bh);
+}
+// pointer to (walker w, electron i, dense component comp) of one head of an operand, or null where it is zero
+__device__ __forceinline__ const float* am_row(const JqAttnOperand& t, long long w, int n, int i, int comp, int col, int Cd) {
+  if (i >= n) return nullptr;
+  const float* base = t.p + ((w * n + i) * (long long)t.C) * t.ld + col;
+  if (t.C == Cd) return base + (long long)comp * t.ld;
+  if (comp == 0) return base;
+  if (comp == Cd - 1) return base + (long long)4 * t.ld;
+  const int k = comp - 1;
+  return (k / 3 == i) ? base + (long long)(1 + k % 3) * t.ld : nullptr;
+}
+
+template <int NJ>
+__global__ void __launch_bounds__(AM_SLOTS * 3 * 32, 1)
+k_attention_fl_mma(JqAttnOperand q, JqAttnOperand k, JqAttnOperand v, float* __restrict__ out, int ldo, int n, int H) {
+  constexpr int dh = 64;
+  JQ_DYN_SMEM(float, sm);
+  constexpr int NT = AM_NP * AM_LD;
+  float* q0 = sm;
+  float* k0 = q0 + NT;
+  float* v0 = k0 + NT;
+  float* wgt = v0 + NT;                   // [48][56]
+  float* slots = wgt + AM_NP * AM_LW;     // per slot: kJ | vJ
+  const long long w = blockIdx.x / H;
+  const int h = blockIdx.x % H;
+  const int tid = threadIdx.x, nthr = blockDim.x, warp = tid >> 5, lane = tid & 31;
+  const int RT = (n + 15) >> 4;
+  const int slot = warp / RT, r = warp - slot * RT;
+  const int g = lane >> 2, t = lane & 3;
+  const int Cd = 3 * n + 2, K = 3 * n;
+  const float scale = 0.125f;   // 1 / sqrt(64)
+  float* kJs = slots + (size_t)slot * 2 * NT;
+  float* vJs = kJs + NT;
+
+  // ---- value row: operands (zero padded), logits, softmax, o = w v ----
+  for (int x = tid; x < 3 * NT + AM_NP * AM_LW + AM_SLOTS * 2 * NT; x += nthr) sm[x] = 0.f;
+  __syncthreads();
+  for (int x = tid; x < n * 16; x += nthr) {
+    const int i = x >> 4, d4 = (x & 15) * 4;
+    attn_stage4(q0 + i * AM_LD + d4, q, w, n, i, 0, q.off + h * dh + d4, Cd);
+    attn_stage4(k0 + i * AM_LD + d4, k, w, n, i, 0, k.off + h * dh + d4, Cd);
+    attn_stage4(v0 + i * AM_LD + d4, v, w, n, i, 0, v.off + h * dh + d4, Cd);
+  }
+  attn_async_commit();
+  attn_async_wait<0>();
+  __syncthreads();
+  for (int x = tid; x < n * n; x += nthr) {
+    const int i = x / n, j = x - i * n;
+    float acc = 0.f;
+    for (int d = 0; d < dh; ++d) acc = fmaf(q0[i * AM_LD + d], k0[j * AM_LD + d], acc);
+    wgt[i * AM_LW + j] = acc * scale;
+  }
+  __syncthreads();
+  for (int i = tid; i < n; i += nthr) {
+    float m = wgt[i * AM_LW];
+    for (int j = 1; j < n; ++j) m = fmaxf(m, wgt[i * AM_LW + j]);
+    float z = 0.f;
+    for (int j = 0; j < n; ++j) {
+      const float e = expf(wgt[i * AM_LW + j] - m);
+      wgt[i * AM_LW + j] = e;
+      z += e;
+    }
+    const float zi = 1.0f / z;
+    for (int j = 0; j < n; ++j) wgt[i * AM_LW + j] *= zi;
+  }
+  __syncthreads();
+  for (int x = tid; x < n * dh; x += nthr) {
+    const int i = x >> 6, d = x & 63;
+    float acc = 0.f;
+    for (int j = 0; j < n; ++j) acc = fmaf(wgt[i * AM_LW + j], v0[j * AM_LD + d], acc);
+    out[((w * n + i) * (long long)Cd) * ldo + h * dh + d] = acc;
+  }
+
+  // ---- Jacobian components ----
+  const int i0 = 16 * r + g, i1 = i0 + 8;            // this lane's fragment rows
+  float X[NJ][4], oL2[8][4];
+#pragma unroll
+  for (int a = 0; a < NJ; ++a) X[a][0] = X[a][1] = X[a][2] = X[a][3] = 0.f;
+#pragma unroll
+  for (int a = 0; a < 8; ++a) oL2[a][0] = oL2[a][1] = oL2[a][2] = oL2[a][3] = 0.f;
+  const int sthreads = 32 * RT, sl = r * 32 + lane;
+  const bool slot_on = slot < AM_SLOTS;
+  if (slot_on) {
+    // softmax weights of this warp's rows, accumulator layout (kept for the whole loop)
+    float wf[NJ][4];
+#pragma unroll
+    for (int a = 0; a < NJ; ++a) {
+      const float2 u0 = *reinterpret_cast<const float2*>(wgt + i0 * AM_LW + 8 * a + 2 * t);
+      const float2 u1 = *reinterpret_cast<const float2*>(wgt + i1 * AM_LW + 8 * a + 2 * t);
+      wf[a][0] = u0.x; wf[a][1] = u0.y; wf[a][2] = u1.x; wf[a][3] = u1.y;
+    }
+    for (int kk = slot; kk < K; kk += AM_SLOTS) {
+      const int comp = 1 + kk;
+      asm volatile("bar.sync %0, %1;" ::"r"(1 + slot), "r"(sthreads) : "memory");   // previous tiles fully consumed
+      for (int x = sl; x < n * 16; x += sthreads) {
+        const int i = x >> 4, d4 = (x & 15) * 4;
+        attn_stage4(kJs + i * AM_LD + d4, k, w, n, i, comp, k.off + h * dh + d4, Cd);
+        attn_stage4(vJs + i * AM_LD + d4, v, w, n, i, comp, v.off + h * dh + d4, Cd);
+      }
+      attn_async_commit();
+      const float* pJ0 = am_row(q, w, n, i0, comp, q.off + h * dh, Cd);
+      const float* pJ1 = am_row(q, w, n, i1, comp, q.off + h * dh, Cd);
+      float xq[4];
+      xq[0] = pJ0 ? pJ0[t] : 0.f; xq[1] = pJ1 ? pJ1[t] : 0.f; xq[2] = pJ0 ? pJ0[t + 4] : 0.f; xq[3] = pJ1 ? pJ1[t + 4] : 0.f;
+      attn_async_wait<0>();
+      asm volatile("bar.sync %0, %1;" ::"r"(1 + slot), "r"(sthreads) : "memory");
+      // phase A
+      float aJ[NJ][4], a2[NJ][4];
+#pragma unroll
+      for (int a = 0; a < NJ; ++a) aJ[a][0] = aJ[a][1] = aJ[a][2] = aJ[a][3] = a2[a][0] = a2[a][1] = a2[a][2] = a2[a][3] = 0.f;
+#pragma unroll
+      for (int ks = 0; ks < dh / 8; ++ks) {
+        unsigned qJh[4], qJl[4], q0h[4], q0l[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) am_split(xq[e], qJh[e], qJl[e]);
+        if (ks + 1 < dh / 8) {
+          const int c = 8 * (ks + 1) + t;
+          xq[0] = pJ0 ? pJ0[c] : 0.f; xq[1] = pJ1 ? pJ1[c] : 0.f; xq[2] = pJ0 ? pJ0[c + 4] : 0.f; xq[3] = pJ1 ? pJ1[c + 4] : 0.f;
+        }
+        am_split(q0[i0 * AM_LD + 8 * ks + t], q0h[0], q0l[0]);
+        am_split(q0[i1 * AM_LD + 8 * ks + t], q0h[1], q0l[1]);
+        am_split(q0[i0 * AM_LD + 8 * ks + t + 4], q0h[2], q0l[2]);
+        am_split(q0[i1 * AM_LD + 8 * ks + t + 4], q0h[3], q0l[3]);
+#pragma unroll
+        for (int a = 0; a < NJ; ++a) {
+          unsigned k0h[2], k0l[2], kJh[2], kJl[2];
+          const int o = (8 * a + g) * AM_LD + 8 * ks + t;
+          am_split(k0[o], k0h[0], k0l[0]);
+          am_split(k0[o + 4], k0h[1], k0l[1]);
+          am_split(kJs[o], kJh[0], kJl[0]);
+          am_split(kJs[o + 4], kJh[1], kJl[1]);
+          am_mma3(aJ[a], qJh, qJl, k0h, k0l);
+          am_mma3(aJ[a], q0h, q0l, kJh, kJl);
+          am_mma3(a2[a], qJh, qJl, kJh, kJl);
+        }
+      }
+      // phase B (registers): rows i0 (elements 0, 1) and i1 (elements 2, 3)
+      float ab0 = 0.f, ab1 = 0.f;
+#pragma unroll
+      for (int a = 0; a < NJ; ++a) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) aJ[a][e] *= scale;
+        ab0 = fmaf(wf[a][0], aJ[a][0], ab0);
+        ab0 = fmaf(wf[a][1], aJ[a][1], ab0);
+        ab1 = fmaf(wf[a][2], aJ[a][2], ab1);
+        ab1 = fmaf(wf[a][3], aJ[a][3], ab1);
+      }
+      ab0 += __shfl_xor_sync(0xffffffffu, ab0, 1);
+      ab0 += __shfl_xor_sync(0xffffffffu, ab0, 2);
+      ab1 += __shfl_xor_sync(0xffffffffu, ab1, 1);
+      ab1 += __shfl_xor_sync(0xffffffffu, ab1, 2);
+#pragma unroll
+      for (int a = 0; a < NJ; ++a)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float c = aJ[a][e] - (e < 2 ? ab0 : ab1);
+          const float wj = wf[a][e] * c;
+          X[a][e] = fmaf(wj, c, X[a][e]);
+          X[a][e] = fmaf(2.0f * scale * wf[a][e], a2[a][e], X[a][e]);
+          aJ[a][e] = wj;   // aJ now holds wJ
+        }
+      // phase C: contraction over j in steps of 8 (slot t <-> j = 8 ks + 2t, slot t+4 <-> j = 8 ks + 2t + 1)
+      float oJ[8][4];
+#pragma unroll
+      for (int a = 0; a < 8; ++a) oJ[a][0] = oJ[a][1] = oJ[a][2] = oJ[a][3] = 0.f;
+#pragma unroll
+      for (int ks = 0; ks < NJ; ++ks) {
+        unsigned wJh[4], wJl[4], wh[4], wl[4];
+        am_split(aJ[ks][0], wJh[0], wJl[0]);
+        am_split(aJ[ks][2], wJh[1], wJl[1]);
+        am_split(aJ[ks][1], wJh[2], wJl[2]);
+        am_split(aJ[ks][3], wJh[3], wJl[3]);
+        am_split(wf[ks][0], wh[0], wl[0]);
+        am_split(wf[ks][2], wh[1], wl[1]);
+        am_split(wf[ks][1], wh[2], wl[2]);
+        am_split(wf[ks][3], wh[3], wl[3]);
+#pragma unroll
+        for (int a = 0; a < 8; ++a) {
+          unsigned v0h[2], v0l[2], vJh[2], vJl[2];
+          const int o = (8 * ks + 2 * t) * AM_LD + 8 * a + g;
+          am_split(v0[o], v0h[0], v0l[0]);
+          am_split(v0[o + AM_LD], v0h[1], v0l[1]);
+          am_split(vJs[o], vJh[0], vJl[0]);
+          am_split(vJs[o + AM_LD], vJh[1], vJl[1]);
+          am_mma3(oJ[a], wJh, wJl, v0h, v0l);
+          am_mma3(oJ[a], wh, wl, vJh, vJl);
+          am_mma3(oL2[a], wJh, wJl, vJh, vJl);
+        }
+      }
+      if (i0 < n) {
+        float* o = out + ((w * n + i0) * (long long)Cd + comp) * ldo + h * dh + 2 * t;
+#pragma unroll
+        for (int a = 0; a < 8; ++a) *reinterpret_cast<float2*>(o + 8 * a) = make_float2(oJ[a][0], oJ[a][1]);
+      }
+      if (i1 < n) {
+        float* o = out + ((w * n + i1) * (long long)Cd + comp) * ldo + h * dh + 2 * t;
+#pragma unroll
+        for (int a = 0; a < 8; ++a) *reinterpret_cast<float2*>(o + 8 * a) = make_float2(oJ[a][2], oJ[a][3]);
+      }
+    }
+  }
+  __syncthreads();
+
+  // ---- per-warp partial X and oL2 -> the slot's (now free) tiles, then a fixed-order sum over the slots ----
+  if (slot_on) {
+#pragma unroll
+    for (int a = 0; a < NJ; ++a) {
+      *reinterpret_cast<float2*>(kJs + i0 * AM_LW + 8 * a + 2 * t) = make_float2(X[a][0], X[a][1]);
+      *reinterpret_cast<float2*>(kJs + i1 * AM_LW + 8 * a + 2 * t) = make_float2(X[a][2], X[a][3]);
+    }
+#pragma unroll
+    for (int a = 0; a < 8; ++a) {
+      *reinterpret_cast<float2*>(vJs + i0 * AM_LD + 8 * a + 2 * t) = make_float2(oL2[a][0], oL2[a][1]);
+      *reinterpret_cast<float2*>(vJs + i1 * AM_LD + 8 * a + 2 * t) = make_float2(oL2[a][2], oL2[a][3]);
+    }
+  }
+  __syncthreads();
+  float* Xs = slots;            // slot 0: X [48][56] | oL2 [48][68]
+  float* oLs = slots + NT;
+  for (int x = tid; x < AM_NP * AM_LW; x += nthr) {
+    float s2 = 0.f;
+    for (int ss = 0; ss < AM_SLOTS; ++ss) s2 += slots[(size_t)ss * 2 * NT + x];
+    Xs[x] = s2;
+  }
+  for (int x = tid; x < NT; x += nthr) {
+    float s2 = 0.f;
+    for (int ss = 0; ss < AM_SLOTS; ++ss) s2 += slots[(size_t)ss * 2 * NT + NT + x];
+    oLs[x] = s2;
+  }
+  __syncthreads();
+  // ---- Laplacian row ----
+  float* qL = slots + 2 * NT;   // slot 1
+  float* kL = qL + NT;
+  float* vL = kL + NT;          // slot 2
+  float* rs = vL + NT;          // row sums of Y [48]
+  const int cl = Cd - 1;
+  for (int x = tid; x < n * 16; x += nthr) {
+    const int i = x >> 4, d4 = (x & 15) * 4;
+    attn_stage4(qL + i * AM_LD + d4, q, w, n, i, cl, q.off + h * dh + d4, Cd);
+    attn_stage4(kL + i * AM_LD + d4, k, w, n, i, cl, k.off + h * dh + d4, Cd);
+    attn_stage4(vL + i * AM_LD + d4, v, w, n, i, cl, v.off + h * dh + d4, Cd);
+  }
+  attn_async_commit();
+  attn_async_wait<0>();
+  __syncthreads();
+  for (int x = tid; x < n * n; x += nthr) {
+    const int i = x / n, j = x - i * n;
+    float a1 = 0.f;
+    for (int d = 0; d < dh; ++d) {
+      a1 = fmaf(qL[i * AM_LD + d], k0[j * AM_LD + d], a1);
+      a1 = fmaf(q0[i * AM_LD + d], kL[j * AM_LD + d], a1);
+    }
+    Xs[i * AM_LW + j] = fmaf(wgt[i * AM_LW + j] * scale, a1, Xs[i * AM_LW + j]);   // Y
+  }
+  __syncthreads();
+  for (int i = tid; i < n; i += nthr) {
+    float s2 = 0.f;
+    for (int j = 0; j < n; ++j) s2 += Xs[i * AM_LW + j];
+    rs[i] = s2;
+  }
+  __syncthreads();
+  for (int x = tid; x < n * n; x += nthr) {
+    const int i = x / n, j = x - i * n;
+    Xs[i * AM_LW + j] -= wgt[i * AM_LW + j] * rs[i];   // wL
+  }
+  __syncthreads();
+  for (int x = tid; x < n * dh; x += nthr) {
+    const int i = x >> 6, d = x & 63;
+    float acc = 2.0f * oLs[i * AM_LD + d];
+    for (int j = 0; j < n; ++j) {
+      acc = fmaf(Xs[i * AM_LW + j], v0[j * AM_LD + d], acc);
+      acc = fmaf(wgt[i * AM_LW + j], vL[j * AM_LD + d], acc);
+    }
+    out[((w * n + i) * (long long)Cd + cl) * ldo + h * dh + d] = acc;
+  }
+}
+#endif
+
 int jq_launch_attention_fl(const JqAttnOperand& q, const JqAttnOperand& k, const JqAttnOperand& v, float* out, int ldo,
                            long long W, int n, int H, int dh, int track, cudaStream_t st) {
+  return jq_launch_attention_fl_sel(q, k, v, out, ldo, W, n, H, dh, track, 0, st);
+}
+
+int jq_launch_attention_fl_sel(const JqAttnOperand& q, const JqAttnOperand& k, const JqAttnOperand& v, float* out, int ldo,
+                               long long W, int n, int H, int dh, int track, int force, cudaStream_t st) {
   if (W <= 0) return JQ_OK;
   const int Cd = track ? 3 * n + 2 : 1;
   JQ_REQUIRE(v.C == Cd && (q.C == Cd || (track && q.C == 5)) && (k.C == Cd || (track && k.C == 5)),
@@ -1055,13 +1378,14 @@ int jq_launch_attention_fl(const JqAttnOperand& q, const JqAttnOperand& k, const
   jq_prof_work((double)W * H * (4.0 * n * n * dh * (1.0 + 2.0 * K)), 4.0 * (double)W * n * Cd * H * dh * 4);
 #ifndef JAQMC_HOST_EMU
   {
-    static const bool old_kernel = getenv("JAQMC_B200_ATTENTION_BLOCK") != nullptr;   // A/B switch
+    static const bool env_block = getenv("JAQMC_B200_ATTENTION_BLOCK") != nullptr;   // A/B switch
+    const bool old_kernel = force ? force == 1 : env_block;
     const bool aligned = (q.ld % 4 == 0) && (k.ld % 4 == 0) && (v.ld % 4 == 0) && (q.off % 4 == 0) && (k.off % 4 == 0) &&
                          (v.off % 4 == 0) && ((reinterpret_cast<uintptr_t>(q.p) | reinterpret_cast<uintptr_t>(k.p) |
                                                reinterpret_cast<uintptr_t>(v.p)) % 16 == 0);
     const int nt = n * AW_LD, nn = n * AW_NS;
     const size_t sw = sizeof(float) * ((size_t)3 * nt + nn + (2 * nn + 32 + 2 * n * 64) + (size_t)AW_WARPS * (6 * nt + 3 * nn + 48));
-    if (track && dh == 64 && n >= 2 && n <= AW_NS && sw <= 227 * 1024 && aligned && !old_kernel) {
+    if (track && dh == 64 && n >= 2 && n <= AW_NS && sw <= 227 * 1024 && aligned && !old_kernel && (force == 0 || force == 2)) {
       const bool qkl = (q.C == 5 && k.C == 5 && Cd != 5);
       cudaError_t e = qkl ? cudaFuncSetAttribute(k_attention_fl_warp<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sw)
                           : cudaFuncSetAttribute(k_attention_fl_warp<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sw);
@@ -1071,8 +1395,30 @@ int jq_launch_attention_fl(const JqAttnOperand& q, const JqAttnOperand& k, const
       JQ_CHECK_LAUNCH();
       return JQ_OK;
     }
+    // n <= 48 and not taken by the warp kernel above: the tensor-core kernel (A/B switch: JAQMC_B200_ATTENTION_SIMT keeps the CUDA-core block kernel)
+    static const bool env_simt = getenv("JAQMC_B200_ATTENTION_SIMT") != nullptr;
+    const bool simt_kernel = force ? force != 3 : env_simt;
+    // (also n = 15, 16, where the warp kernel's per-warp staging no longer fits in shared memory)
+    if (track && dh == 64 && n >= 2 && n <= AM_NP && aligned && ldo % 2 == 0 &&
+        reinterpret_cast<uintptr_t>(out) % 8 == 0 && !old_kernel && !simt_kernel) {
+      const int RT = (n + 15) / 16;
+      const size_t sm_mma = sizeof(float) * ((size_t)3 * AM_NP * AM_LD + AM_NP * AM_LW + (size_t)AM_SLOTS * 2 * AM_NP * AM_LD);
+      static JqPerDeviceFlag attr_set;
+      const int dev = jq_current_device();
+      if (!attr_set.done[dev]) {
+        cudaError_t e = cudaFuncSetAttribute(k_attention_fl_mma<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_mma);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_attention_fl_mma<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_mma);
+        JQ_REQUIRE(e == cudaSuccess, JQ_ERR_CUDA, "attention: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+        attr_set.done[dev] = true;
+      }
+      if (n <= 32) JQ_LAUNCH(k_attention_fl_mma<4>, dim3((unsigned)(W * H)), dim3(32 * RT * AM_SLOTS), sm_mma, st, q, k, v, out, ldo, n, H);
+      else JQ_LAUNCH(k_attention_fl_mma<6>, dim3((unsigned)(W * H)), dim3(32 * RT * AM_SLOTS), sm_mma, st, q, k, v, out, ldo, n, H);
+      JQ_CHECK_LAUNCH();
+      return JQ_OK;
+    }
   }
 #endif
+  JQ_REQUIRE(force == 0 || force == 1, JQ_ERR_UNSUPPORTED, "attention: kernel %d does not support n=%d head_dim=%d", force, n, dh);
 #ifndef JAQMC_HOST_EMU
   static const int tile_sel = getenv("JAQMC_B200_ATTENTION_TILES") ? atoi(getenv("JAQMC_B200_ATTENTION_TILES")) : 0;   // tuning
   if (tile_sel == 1) JQ_LAUNCH((k_attention_fl<2, 4, 2, 4>), dim3((unsigned)(W * H)), dim3(256), smem, st, q, k, v, out, ldo, n, H, dh, track);

@@ -156,3 +156,6 @@ int jq_launch_layernorm_fl(const float* x, const float* scale, const float* bias
                            float eps, cudaStream_t st);
 int jq_launch_attention_fl(const JqAttnOperand& q, const JqAttnOperand& k, const JqAttnOperand& v, float* out, int ldo,
                            long long W, int n, int H, int dh, int track, cudaStream_t st);
+// force: 0 library's choice | 1 block kernel | 2 warp kernel | 3 mma.sync kernel (JQ_ERR_UNSUPPORTED when not eligible)
+int jq_launch_attention_fl_sel(const JqAttnOperand& q, const JqAttnOperand& k, const JqAttnOperand& v, float* out, int ldo,
+                               long long W, int n, int H, int dh, int track, int force, cudaStream_t st);

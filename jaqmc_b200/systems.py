@@ -32,6 +32,9 @@ def molecule(name):
         return (torch.tensor([[0.0, 0.0, 0.0], [0.0, 0.0, 3.015]], dtype=F64), torch.tensor([3.0, 1.0], dtype=F64), (2, 2))
     if name == "Ar":  # 18 electrons: exercises the n > 16 code paths (generic LogDet kernel)
         return torch.zeros(1, 3, dtype=F64), torch.tensor([18.0], dtype=F64), (9, 9)
+    if name in ("Zn", "As", "Cd"):  # 30 / 33 / 48 electrons on one nucleus: tile-shape edge cases of the attention kernels
+        z = {"Zn": 30, "As": 33, "Cd": 48}[name]
+        return torch.zeros(1, 3, dtype=F64), torch.tensor([float(z)], dtype=F64), ((z + 1) // 2, z // 2)
     if name == "N2":
         return (torch.tensor([[0.0, 0.0, -1.034], [0.0, 0.0, 1.034]], dtype=F64), torch.tensor([7.0, 7.0], dtype=F64), (7, 7))
     if name == "C6H6":  # 42 electrons, 12 atoms
