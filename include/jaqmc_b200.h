@@ -379,6 +379,15 @@ int jaqmc_b200_attention_fl(const float* q, const float* k, const float* v, floa
                             int32_t n_electrons, int32_t n_heads, int32_t head_dim, int32_t q_components,
                             int32_t k_components, int32_t kernel, jaqmc_stream_t stream);
 
+/* LayerNorm over the feature axis under the forward Laplacian (flax nn.LayerNorm traced by forward_laplacian in the
+ * Psiformer block, backbone/psiformer.py, and LapNet's optional layer norms, backbone/lapnet/_backbone.py:62-64):
+ *   x, out (n_groups, n_components, n_features), n_components = 1 or K+2; scale / bias (n_features,) or NULL.
+ *   kernel 0: the library's choice; 1: three-pass kernel (any shape); 2: group cached in shared memory; 3: streaming
+ *   row-per-warp kernel (n_features 128, 256 or 512, 16-byte aligned).  In-place is not supported. */
+int jaqmc_b200_layernorm_fl(const float* x, const float* scale, const float* bias, float* out, int64_t n_groups,
+                            int32_t n_components, int32_t n_features, float epsilon, int32_t kernel,
+                            jaqmc_stream_t stream);
+
 /* Building blocks of the MH step, exported for samplers that drive their own loop
  * (sampler/mcmc.py:53-54 gaussian_proposal; :128-137 accept/select). */
 int jaqmc_b200_mh_propose(const float* x1, const float* normals, const float* stddev, float* x2, int64_t count,

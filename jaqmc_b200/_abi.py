@@ -249,6 +249,10 @@ PROTOTYPES = {
         [FloatP, FloatP, FloatP, FloatP, FloatP, FloatP, FloatP, FloatP, C.c_int64, C.c_int32, C.c_int32, C.c_int32,
          C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_size_t, C.c_void_p],
     ),
+    "jaqmc_b200_layernorm_fl": (
+        C.c_int,
+        [FloatP, FloatP, FloatP, FloatP, C.c_int64, C.c_int32, C.c_int32, C.c_float, C.c_int32, C.c_void_p],
+    ),
     "jaqmc_b200_attention_fl": (
         C.c_int,
         [FloatP, FloatP, FloatP, FloatP, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,

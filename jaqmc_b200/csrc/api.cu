@@ -515,6 +515,16 @@ extern "C" int jaqmc_b200_local_energy_complex(const jaqmc_wavefunction* wf, con
   return JQ_OK;
 }
 
+extern "C" int jaqmc_b200_layernorm_fl(const float* x, const float* scale, const float* bias, float* out, int64_t n_groups,
+                                       int32_t n_components, int32_t n_features, float epsilon, int32_t kernel,
+                                       jaqmc_stream_t stream) {
+  JQ_REQUIRE(n_groups >= 0 && n_components >= 1 && n_features >= 1, JQ_ERR_INVALID_ARGUMENT, "layernorm_fl: bad sizes");
+  JQ_REQUIRE(kernel >= 0 && kernel <= 3, JQ_ERR_INVALID_ARGUMENT, "layernorm_fl: kernel selector %d", kernel);
+  JQ_REQUIRE(x && out, JQ_ERR_INVALID_ARGUMENT, "layernorm_fl: null operand");
+  return jq_launch_layernorm_fl_sel(x, scale, bias, out, n_groups, n_components, n_features, epsilon, kernel,
+                                    (cudaStream_t)stream);
+}
+
 extern "C" int jaqmc_b200_attention_fl(const float* q, const float* k, const float* v, float* out, int64_t n_walkers,
                                        int32_t n_electrons, int32_t n_heads, int32_t head_dim, int32_t q_components,
                                        int32_t k_components, int32_t kernel, jaqmc_stream_t stream) {

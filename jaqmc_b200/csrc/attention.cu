@@ -289,14 +289,180 @@ __global__ void __launch_bounds__(256) k_layernorm_fl_smem(const float* __restri
 }
 #endif
 
+#ifndef JAQMC_HOST_EMU
+// Same rule, streaming (r2): a derivative row's statistics depend only on the row itself and on the value row, so each
+// WARP takes rows c = 1 + warp, 1 + warp + nw, ...: loads the row into registers (F / 32 values per lane, float4), reduces
+// mu_c, dot_c, sq_c with shuffles and writes the normalised row at once -- the group never sits in shared memory, several
+// blocks are resident per SM and every warp keeps the next row in flight while it works on the current one.  The value
+// row's statistics are recomputed by every warp (1 KB from L1); the Laplacian row needs sum_k xcJ_k sJ_k per feature and
+// two scalars, accumulated per warp and reduced in a fixed order.   F = 128 NV.
+constexpr int LNR_WARPS = 8;
+__device__ __forceinline__ float ln_hsum(const float4& v) { return (v.x + v.y) + (v.z + v.w); }
+
+template <int NV>
+__global__ void __launch_bounds__(LNR_WARPS * 32) k_layernorm_fl_rows(const float* __restrict__ x, const float* __restrict__ scale,
+                                                                      const float* __restrict__ bias, float* __restrict__ out,
+                                                                      int C, float eps) {
+  constexpr int F = 128 * NV, F4 = 32 * NV;
+  __shared__ float4 acc_s[LNR_WARPS][F4];
+  __shared__ float red_s[LNR_WARPS][2];
+  const long long g = blockIdx.x;
+  const float4* xg4 = reinterpret_cast<const float4*>(x + g * (long long)C * F);
+  float4* og4 = reinterpret_cast<float4*>(out + g * (long long)C * F);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float invF = 1.0f / (float)F;
+  float4 xc[NV], sc[NV];
+  float s = 0.f, s2 = 0.f;
+#pragma unroll
+  for (int u = 0; u < NV; ++u) {
+    xc[u] = xg4[lane + 32 * u];
+    s += ln_hsum(xc[u]);
+    s2 = fmaf(xc[u].x, xc[u].x, fmaf(xc[u].y, xc[u].y, fmaf(xc[u].z, xc[u].z, fmaf(xc[u].w, xc[u].w, s2))));
+    sc[u] = scale ? reinterpret_cast<const float4*>(scale)[lane + 32 * u] : make_float4(1.f, 1.f, 1.f, 1.f);
+  }
+  s = warp_sum(s);
+  s2 = warp_sum(s2);
+  const float mu0 = s * invF;
+  float var = s2 * invF - mu0 * mu0;
+  if (var < 0.f) var = 0.f;
+  const float sinv = rsqrtf(var + eps);
+#pragma unroll
+  for (int u = 0; u < NV; ++u) {
+    xc[u].x -= mu0; xc[u].y -= mu0; xc[u].z -= mu0; xc[u].w -= mu0;
+  }
+  if (warp == 0) {
+#pragma unroll
+    for (int u = 0; u < NV; ++u) {
+      float4 y = make_float4(xc[u].x * sinv * sc[u].x, xc[u].y * sinv * sc[u].y, xc[u].z * sinv * sc[u].z, xc[u].w * sinv * sc[u].w);
+      if (bias) {
+        const float4 b = reinterpret_cast<const float4*>(bias)[lane + 32 * u];
+        y.x += b.x; y.y += b.y; y.z += b.z; y.w += b.w;
+      }
+      og4[lane + 32 * u] = y;
+    }
+  }
+  if (C == 1) return;
+  const int K = C - 2;
+  const float s3 = sinv * sinv * sinv;
+  float4 acc[NV];
+#pragma unroll
+  for (int u = 0; u < NV; ++u) acc[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+  float sumq = 0.f, sumv2 = 0.f;
+  float4 nxt[NV];
+  int c = 1 + warp;
+  if (c <= K) {
+#pragma unroll
+    for (int u = 0; u < NV; ++u) nxt[u] = xg4[(long long)c * F4 + lane + 32 * u];
+  }
+  for (; c <= K; c += LNR_WARPS) {
+    float4 v[NV];
+    float m = 0.f;
+#pragma unroll
+    for (int u = 0; u < NV; ++u) {
+      v[u] = nxt[u];
+      m += ln_hsum(v[u]);
+    }
+    if (c + LNR_WARPS <= K) {
+#pragma unroll
+      for (int u = 0; u < NV; ++u) nxt[u] = xg4[(long long)(c + LNR_WARPS) * F4 + lane + 32 * u];
+    }
+    m = warp_sum(m) * invF;
+    float d = 0.f, q = 0.f;
+#pragma unroll
+    for (int u = 0; u < NV; ++u) {
+      v[u].x -= m; v[u].y -= m; v[u].z -= m; v[u].w -= m;
+      d = fmaf(xc[u].x, v[u].x, fmaf(xc[u].y, v[u].y, fmaf(xc[u].z, v[u].z, fmaf(xc[u].w, v[u].w, d))));
+      q = fmaf(v[u].x, v[u].x, fmaf(v[u].y, v[u].y, fmaf(v[u].z, v[u].z, fmaf(v[u].w, v[u].w, q))));
+    }
+    d = warp_sum(d);
+    q = warp_sum(q);
+    const float vj = 2.0f * d * invF;
+    const float sj = -0.5f * s3 * vj;
+    sumq += q;
+    sumv2 = fmaf(vj, vj, sumv2);
+#pragma unroll
+    for (int u = 0; u < NV; ++u) {
+      og4[(long long)c * F4 + lane + 32 * u] =
+          make_float4((v[u].x * sinv + xc[u].x * sj) * sc[u].x, (v[u].y * sinv + xc[u].y * sj) * sc[u].y,
+                      (v[u].z * sinv + xc[u].z * sj) * sc[u].z, (v[u].w * sinv + xc[u].w * sj) * sc[u].w);
+      acc[u].x = fmaf(v[u].x, sj, acc[u].x);
+      acc[u].y = fmaf(v[u].y, sj, acc[u].y);
+      acc[u].z = fmaf(v[u].z, sj, acc[u].z);
+      acc[u].w = fmaf(v[u].w, sj, acc[u].w);
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < NV; ++u) acc_s[warp][lane + 32 * u] = acc[u];
+  if (lane == 0) {
+    red_s[warp][0] = sumq;
+    red_s[warp][1] = sumv2;
+  }
+  __syncthreads();
+  if (warp == 0) {
+    float tq = 0.f, tv = 0.f;
+    for (int ww = 0; ww < LNR_WARPS; ++ww) {
+      tq += red_s[ww][0];
+      tv += red_s[ww][1];
+    }
+    float4 v[NV];
+    float m = 0.f;
+#pragma unroll
+    for (int u = 0; u < NV; ++u) {
+      v[u] = xg4[(long long)(C - 1) * F4 + lane + 32 * u];
+      m += ln_hsum(v[u]);
+    }
+    m = warp_sum(m) * invF;
+    float d = 0.f;
+#pragma unroll
+    for (int u = 0; u < NV; ++u) {
+      v[u].x -= m; v[u].y -= m; v[u].z -= m; v[u].w -= m;
+      d = fmaf(xc[u].x, v[u].x, fmaf(xc[u].y, v[u].y, fmaf(xc[u].z, v[u].z, fmaf(xc[u].w, v[u].w, d))));
+    }
+    d = warp_sum(d);
+    const float varL = 2.0f * d * invF + 2.0f * tq * invF;
+    const float sL = -0.5f * s3 * varL + 0.75f * s3 * sinv * sinv * tv;
+#pragma unroll
+    for (int u = 0; u < NV; ++u) {
+      float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int ww = 0; ww < LNR_WARPS; ++ww) {
+        const float4 p = acc_s[ww][lane + 32 * u];
+        a.x += p.x; a.y += p.y; a.z += p.z; a.w += p.w;
+      }
+      og4[(long long)(C - 1) * F4 + lane + 32 * u] =
+          make_float4((v[u].x * sinv + xc[u].x * sL + 2.0f * a.x) * sc[u].x, (v[u].y * sinv + xc[u].y * sL + 2.0f * a.y) * sc[u].y,
+                      (v[u].z * sinv + xc[u].z * sL + 2.0f * a.z) * sc[u].z, (v[u].w * sinv + xc[u].w * sL + 2.0f * a.w) * sc[u].w);
+    }
+  }
+}
+#endif
+
 int jq_launch_layernorm_fl(const float* x, const float* scale, const float* bias, float* out, long long G, int C, int F,
                            float eps, cudaStream_t st) {
+  return jq_launch_layernorm_fl_sel(x, scale, bias, out, G, C, F, eps, 0, st);
+}
+
+int jq_launch_layernorm_fl_sel(const float* x, const float* scale, const float* bias, float* out, long long G, int C, int F,
+                               float eps, int force, cudaStream_t st) {
   if (G <= 0) return JQ_OK;
   JQ_REQUIRE(x != out, JQ_ERR_INVALID_ARGUMENT, "layernorm: in-place is not supported");
 #ifndef JAQMC_HOST_EMU
   {
+    static const bool env_no_rows = getenv("JAQMC_B200_LAYERNORM_SMEM") != nullptr;   // A/B switch: the shared-memory kernel
+    const bool no_rows = force ? force != 3 : env_no_rows;
+    const bool al16 = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(scale) |
+                        reinterpret_cast<uintptr_t>(bias)) & 15) == 0;
+    if (!no_rows && al16 && (F == 128 || F == 256 || F == 512)) {
+      jq_prof_work(0.0, 8.0 * (double)G * C * F);
+      if (F == 128) JQ_LAUNCH(k_layernorm_fl_rows<1>, dim3((unsigned)G), dim3(LNR_WARPS * 32), 0, st, x, scale, bias, out, C, eps);
+      else if (F == 256) JQ_LAUNCH(k_layernorm_fl_rows<2>, dim3((unsigned)G), dim3(LNR_WARPS * 32), 0, st, x, scale, bias, out, C, eps);
+      else JQ_LAUNCH(k_layernorm_fl_rows<4>, dim3((unsigned)G), dim3(LNR_WARPS * 32), 0, st, x, scale, bias, out, C, eps);
+      JQ_CHECK_LAUNCH();
+      return JQ_OK;
+    }
+  }
+  {
     const size_t sc = sizeof(float) * ((size_t)C * F + 4 * (size_t)C + 8);
-    if (F % 4 == 0 && sc <= 200 * 1024 && (reinterpret_cast<uintptr_t>(x) & 15) == 0) {
+    if (F % 4 == 0 && sc <= 200 * 1024 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (force == 0 || force == 2)) {
       cudaError_t e = cudaFuncSetAttribute(k_layernorm_fl_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sc);
       JQ_REQUIRE(e == cudaSuccess, JQ_ERR_CUDA, "layernorm: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
       jq_prof_work(0.0, 8.0 * (double)G * C * F);
@@ -306,6 +472,7 @@ int jq_launch_layernorm_fl(const float* x, const float* scale, const float* bias
     }
   }
 #endif
+  JQ_REQUIRE(force == 0 || force == 1, JQ_ERR_UNSUPPORTED, "layernorm: kernel %d does not support C=%d F=%d", force, C, F);
   size_t smem = sizeof(float) * ((size_t)4 * C + (size_t)2 * C * LN_T + 8);
   JQ_REQUIRE(smem <= 200 * 1024, JQ_ERR_UNSUPPORTED, "layernorm: %d components need %zu bytes of shared memory", C, smem);
 #ifndef JAQMC_HOST_EMU

@@ -154,6 +154,9 @@ struct JqAttnOperand {
 int jq_launch_densify_local1(const float* in, float* out, long long W, int n, int F, cudaStream_t st);
 int jq_launch_layernorm_fl(const float* x, const float* scale, const float* bias, float* out, long long G, int C, int F,
                            float eps, cudaStream_t st);
+// force: 0 library's choice | 1 three-pass kernel | 2 group in shared memory | 3 streaming row-per-warp kernel
+int jq_launch_layernorm_fl_sel(const float* x, const float* scale, const float* bias, float* out, long long G, int C, int F,
+                               float eps, int force, cudaStream_t st);
 int jq_launch_attention_fl(const JqAttnOperand& q, const JqAttnOperand& k, const JqAttnOperand& v, float* out, int ldo,
                            long long W, int n, int H, int dh, int track, cudaStream_t st);
 // force: 0 library's choice | 1 block kernel | 2 warp kernel | 3 mma.sync kernel (JQ_ERR_UNSUPPORTED when not eligible)

@@ -21,7 +21,7 @@ def declared_symbols():
 def test_header_declares_the_entry_points():
     names = declared_symbols()
     for must in ("jaqmc_b200_logpsi", "jaqmc_b200_local_energy", "jaqmc_b200_local_energy_complex", "jaqmc_b200_mh_step",
-                 "jaqmc_b200_mh_step_pbc", "jaqmc_b200_coulomb", "jaqmc_b200_ewald", "jaqmc_b200_dense_fl", "jaqmc_b200_attention_fl",
+                 "jaqmc_b200_mh_step_pbc", "jaqmc_b200_coulomb", "jaqmc_b200_ewald", "jaqmc_b200_dense_fl", "jaqmc_b200_attention_fl", "jaqmc_b200_layernorm_fl",
                  "jaqmc_b200_workspace_bytes"):
         assert must in names
 
