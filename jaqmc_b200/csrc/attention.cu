@@ -1225,10 +1225,21 @@ constexpr int AM_LW = 56;     // 56 mod 32 = 24: the float2 accumulator-layout l
 constexpr int AM_SLOTS = 4;
 constexpr int AM_NP = 48;     // padded electron count
 
+// x = hi + lo for the 3xTF32 products.  RNA: both parts rounded to nearest with cvt.rna.tf32.f32 -- which sm_100a has no
+// single instruction for: ncu shows ~11 integer / predicate instructions per split, 63 % of everything the first version
+// of this kernel issued, against 14.5 % HMMA.  !RNA: hi = x with the 13 low mantissa bits cleared (one LOP3),
+// lo = x - hi (exact, one FADD) handed to the tensor core as is, which ignores its low 13 bits: two instructions, at the
+// price of a one-sided 2^-22 relative truncation of each operand (measured error: DESIGN.md section 4).
+template <bool RNA>
 __device__ __forceinline__ void am_split(float x, unsigned& hi, unsigned& lo) {
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(x));
-  const float r = x - __uint_as_float(hi);
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lo) : "f"(r));
+  if (RNA) {
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(x));
+    const float r = x - __uint_as_float(hi);
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lo) : "f"(r));
+  } else {
+    hi = __float_as_uint(x) & 0xffffe000u;
+    lo = __float_as_uint(x - __uint_as_float(hi));
+  }
 }
 __device__ __forceinline__ void am_mma(float (&c)[4], const unsigned (&a)[4], const unsigned (&b)[2]) {
   asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
@@ -1253,7 +1264,7 @@ __device__ __forceinline__ const float* am_row(const JqAttnOperand& t, long long
   return (k / 3 == i) ? base + (long long)(1 + k % 3) * t.ld : nullptr;
 }
 
-template <int NJ>
+template <int NJ, bool RNA>
 __global__ void __launch_bounds__(AM_SLOTS * 3 * 32, 1)
 k_attention_fl_mma(JqAttnOperand q, JqAttnOperand k, JqAttnOperand v, float* __restrict__ out, int ldo, int n, int H) {
   constexpr int dh = 64;
@@ -1324,14 +1335,12 @@ k_attention_fl_mma(JqAttnOperand q, JqAttnOperand k, JqAttnOperand v, float* __r
   const int sthreads = 32 * RT, sl = r * 32 + lane;
   const bool slot_on = slot < AM_SLOTS;
   if (slot_on) {
-    // softmax weights of this warp's rows, accumulator layout (kept for the whole loop)
-    float wf[NJ][4];
-#pragma unroll
-    for (int a = 0; a < NJ; ++a) {
-      const float2 u0 = *reinterpret_cast<const float2*>(wgt + i0 * AM_LW + 8 * a + 2 * t);
-      const float2 u1 = *reinterpret_cast<const float2*>(wgt + i1 * AM_LW + 8 * a + 2 * t);
-      wf[a][0] = u0.x; wf[a][1] = u0.y; wf[a][2] = u1.x; wf[a][3] = u1.y;
-    }
+    // softmax weights of this warp's rows in accumulator layout: re-read from shared memory where they are used (24
+    // registers fewer than keeping them; the first version of this kernel spilled 300 bytes per thread)
+    const float* wrow0 = wgt + i0 * AM_LW + 2 * t;
+    const float* wrow1 = wgt + i1 * AM_LW + 2 * t;
+    // (Measured r2: fetching kJ of the next component during phases B / C and vJ during phase A -- one more named
+    // barrier per component -- changed the launch time by 1-2 %, inside the box-to-box spread; the simpler form is kept.)
     for (int kk = slot; kk < K; kk += AM_SLOTS) {
       const int comp = 1 + kk;
       asm volatile("bar.sync %0, %1;" ::"r"(1 + slot), "r"(sthreads) : "memory");   // previous tiles fully consumed
@@ -1351,27 +1360,27 @@ k_attention_fl_mma(JqAttnOperand q, JqAttnOperand k, JqAttnOperand v, float* __r
       float aJ[NJ][4], a2[NJ][4];
 #pragma unroll
       for (int a = 0; a < NJ; ++a) aJ[a][0] = aJ[a][1] = aJ[a][2] = aJ[a][3] = a2[a][0] = a2[a][1] = a2[a][2] = a2[a][3] = 0.f;
-#pragma unroll
+#pragma unroll 2
       for (int ks = 0; ks < dh / 8; ++ks) {
         unsigned qJh[4], qJl[4], q0h[4], q0l[4];
 #pragma unroll
-        for (int e = 0; e < 4; ++e) am_split(xq[e], qJh[e], qJl[e]);
+        for (int e = 0; e < 4; ++e) am_split<RNA>(xq[e], qJh[e], qJl[e]);
         if (ks + 1 < dh / 8) {
           const int c = 8 * (ks + 1) + t;
           xq[0] = pJ0 ? pJ0[c] : 0.f; xq[1] = pJ1 ? pJ1[c] : 0.f; xq[2] = pJ0 ? pJ0[c + 4] : 0.f; xq[3] = pJ1 ? pJ1[c + 4] : 0.f;
         }
-        am_split(q0[i0 * AM_LD + 8 * ks + t], q0h[0], q0l[0]);
-        am_split(q0[i1 * AM_LD + 8 * ks + t], q0h[1], q0l[1]);
-        am_split(q0[i0 * AM_LD + 8 * ks + t + 4], q0h[2], q0l[2]);
-        am_split(q0[i1 * AM_LD + 8 * ks + t + 4], q0h[3], q0l[3]);
+        am_split<RNA>(q0[i0 * AM_LD + 8 * ks + t], q0h[0], q0l[0]);
+        am_split<RNA>(q0[i1 * AM_LD + 8 * ks + t], q0h[1], q0l[1]);
+        am_split<RNA>(q0[i0 * AM_LD + 8 * ks + t + 4], q0h[2], q0l[2]);
+        am_split<RNA>(q0[i1 * AM_LD + 8 * ks + t + 4], q0h[3], q0l[3]);
 #pragma unroll
         for (int a = 0; a < NJ; ++a) {
           unsigned k0h[2], k0l[2], kJh[2], kJl[2];
           const int o = (8 * a + g) * AM_LD + 8 * ks + t;
-          am_split(k0[o], k0h[0], k0l[0]);
-          am_split(k0[o + 4], k0h[1], k0l[1]);
-          am_split(kJs[o], kJh[0], kJl[0]);
-          am_split(kJs[o + 4], kJh[1], kJl[1]);
+          am_split<RNA>(k0[o], k0h[0], k0l[0]);
+          am_split<RNA>(k0[o + 4], k0h[1], k0l[1]);
+          am_split<RNA>(kJs[o], kJh[0], kJl[0]);
+          am_split<RNA>(kJs[o + 4], kJh[1], kJl[1]);
           am_mma3(aJ[a], qJh, qJl, k0h, k0l);
           am_mma3(aJ[a], q0h, q0l, kJh, kJl);
           am_mma3(a2[a], qJh, qJl, kJh, kJl);
@@ -1383,25 +1392,31 @@ k_attention_fl_mma(JqAttnOperand q, JqAttnOperand k, JqAttnOperand v, float* __r
       for (int a = 0; a < NJ; ++a) {
 #pragma unroll
         for (int e = 0; e < 4; ++e) aJ[a][e] *= scale;
-        ab0 = fmaf(wf[a][0], aJ[a][0], ab0);
-        ab0 = fmaf(wf[a][1], aJ[a][1], ab0);
-        ab1 = fmaf(wf[a][2], aJ[a][2], ab1);
-        ab1 = fmaf(wf[a][3], aJ[a][3], ab1);
+        const float2 u0 = *reinterpret_cast<const float2*>(wrow0 + 8 * a);
+        const float2 u1 = *reinterpret_cast<const float2*>(wrow1 + 8 * a);
+        ab0 = fmaf(u0.x, aJ[a][0], ab0);
+        ab0 = fmaf(u0.y, aJ[a][1], ab0);
+        ab1 = fmaf(u1.x, aJ[a][2], ab1);
+        ab1 = fmaf(u1.y, aJ[a][3], ab1);
       }
       ab0 += __shfl_xor_sync(0xffffffffu, ab0, 1);
       ab0 += __shfl_xor_sync(0xffffffffu, ab0, 2);
       ab1 += __shfl_xor_sync(0xffffffffu, ab1, 1);
       ab1 += __shfl_xor_sync(0xffffffffu, ab1, 2);
 #pragma unroll
-      for (int a = 0; a < NJ; ++a)
+      for (int a = 0; a < NJ; ++a) {
+        const float2 u0 = *reinterpret_cast<const float2*>(wrow0 + 8 * a);
+        const float2 u1 = *reinterpret_cast<const float2*>(wrow1 + 8 * a);
+        const float wv[4] = {u0.x, u0.y, u1.x, u1.y};
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           const float c = aJ[a][e] - (e < 2 ? ab0 : ab1);
-          const float wj = wf[a][e] * c;
+          const float wj = wv[e] * c;
           X[a][e] = fmaf(wj, c, X[a][e]);
-          X[a][e] = fmaf(2.0f * scale * wf[a][e], a2[a][e], X[a][e]);
+          X[a][e] = fmaf(2.0f * scale * wv[e], a2[a][e], X[a][e]);
           aJ[a][e] = wj;   // aJ now holds wJ
         }
+      }
       // phase C: contraction over j in steps of 8 (slot t <-> j = 8 ks + 2t, slot t+4 <-> j = 8 ks + 2t + 1)
       float oJ[8][4];
 #pragma unroll
@@ -1409,22 +1424,26 @@ k_attention_fl_mma(JqAttnOperand q, JqAttnOperand k, JqAttnOperand v, float* __r
 #pragma unroll
       for (int ks = 0; ks < NJ; ++ks) {
         unsigned wJh[4], wJl[4], wh[4], wl[4];
-        am_split(aJ[ks][0], wJh[0], wJl[0]);
-        am_split(aJ[ks][2], wJh[1], wJl[1]);
-        am_split(aJ[ks][1], wJh[2], wJl[2]);
-        am_split(aJ[ks][3], wJh[3], wJl[3]);
-        am_split(wf[ks][0], wh[0], wl[0]);
-        am_split(wf[ks][2], wh[1], wl[1]);
-        am_split(wf[ks][1], wh[2], wl[2]);
-        am_split(wf[ks][3], wh[3], wl[3]);
+        am_split<RNA>(aJ[ks][0], wJh[0], wJl[0]);
+        am_split<RNA>(aJ[ks][2], wJh[1], wJl[1]);
+        am_split<RNA>(aJ[ks][1], wJh[2], wJl[2]);
+        am_split<RNA>(aJ[ks][3], wJh[3], wJl[3]);
+        {
+          const float2 u0 = *reinterpret_cast<const float2*>(wrow0 + 8 * ks);
+          const float2 u1 = *reinterpret_cast<const float2*>(wrow1 + 8 * ks);
+          am_split<RNA>(u0.x, wh[0], wl[0]);
+          am_split<RNA>(u1.x, wh[1], wl[1]);
+          am_split<RNA>(u0.y, wh[2], wl[2]);
+          am_split<RNA>(u1.y, wh[3], wl[3]);
+        }
 #pragma unroll
         for (int a = 0; a < 8; ++a) {
           unsigned v0h[2], v0l[2], vJh[2], vJl[2];
           const int o = (8 * ks + 2 * t) * AM_LD + 8 * a + g;
-          am_split(v0[o], v0h[0], v0l[0]);
-          am_split(v0[o + AM_LD], v0h[1], v0l[1]);
-          am_split(vJs[o], vJh[0], vJl[0]);
-          am_split(vJs[o + AM_LD], vJh[1], vJl[1]);
+          am_split<RNA>(v0[o], v0h[0], v0l[0]);
+          am_split<RNA>(v0[o + AM_LD], v0h[1], v0l[1]);
+          am_split<RNA>(vJs[o], vJh[0], vJl[0]);
+          am_split<RNA>(vJs[o + AM_LD], vJh[1], vJl[1]);
           am_mma3(oJ[a], wJh, wJl, v0h, v0l);
           am_mma3(oJ[a], wh, wl, vJh, vJl);
           am_mma3(oL2[a], wJh, wJl, vJh, vJl);
@@ -1564,22 +1583,29 @@ int jq_launch_attention_fl_sel(const JqAttnOperand& q, const JqAttnOperand& k, c
     }
     // n <= 48 and not taken by the warp kernel above: the tensor-core kernel (A/B switch: JAQMC_B200_ATTENTION_SIMT keeps the CUDA-core block kernel)
     static const bool env_simt = getenv("JAQMC_B200_ATTENTION_SIMT") != nullptr;
-    const bool simt_kernel = force ? force != 3 : env_simt;
+    const bool simt_kernel = force ? (force != 3 && force != 4) : env_simt;
     // (also n = 15, 16, where the warp kernel's per-warp staging no longer fits in shared memory)
     if (track && dh == 64 && n >= 2 && n <= AM_NP && aligned && ldo % 2 == 0 &&
         reinterpret_cast<uintptr_t>(out) % 8 == 0 && !old_kernel && !simt_kernel) {
       const int RT = (n + 15) / 16;
       const size_t sm_mma = sizeof(float) * ((size_t)3 * AM_NP * AM_LD + AM_NP * AM_LW + (size_t)AM_SLOTS * 2 * AM_NP * AM_LD);
+      static const bool env_rna = getenv("JAQMC_B200_ATTENTION_RNA") != nullptr;   // A/B switch: round-to-nearest operand split
+      const bool rna = force == 4 || (force != 3 && env_rna);
       static JqPerDeviceFlag attr_set;
       const int dev = jq_current_device();
       if (!attr_set.done[dev]) {
-        cudaError_t e = cudaFuncSetAttribute(k_attention_fl_mma<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_mma);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_attention_fl_mma<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_mma);
+        cudaError_t e = cudaFuncSetAttribute(k_attention_fl_mma<6, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_mma);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_attention_fl_mma<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_mma);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_attention_fl_mma<6, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_mma);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_attention_fl_mma<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_mma);
         JQ_REQUIRE(e == cudaSuccess, JQ_ERR_CUDA, "attention: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
         attr_set.done[dev] = true;
       }
-      if (n <= 32) JQ_LAUNCH(k_attention_fl_mma<4>, dim3((unsigned)(W * H)), dim3(32 * RT * AM_SLOTS), sm_mma, st, q, k, v, out, ldo, n, H);
-      else JQ_LAUNCH(k_attention_fl_mma<6>, dim3((unsigned)(W * H)), dim3(32 * RT * AM_SLOTS), sm_mma, st, q, k, v, out, ldo, n, H);
+      const dim3 grid((unsigned)(W * H)), block(32 * RT * AM_SLOTS);
+      if (n <= 32 && !rna) JQ_LAUNCH((k_attention_fl_mma<4, false>), grid, block, sm_mma, st, q, k, v, out, ldo, n, H);
+      else if (n <= 32) JQ_LAUNCH((k_attention_fl_mma<4, true>), grid, block, sm_mma, st, q, k, v, out, ldo, n, H);
+      else if (!rna) JQ_LAUNCH((k_attention_fl_mma<6, false>), grid, block, sm_mma, st, q, k, v, out, ldo, n, H);
+      else JQ_LAUNCH((k_attention_fl_mma<6, true>), grid, block, sm_mma, st, q, k, v, out, ldo, n, H);
       JQ_CHECK_LAUNCH();
       return JQ_OK;
     }

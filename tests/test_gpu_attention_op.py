@@ -1,5 +1,5 @@
 """``jaqmc_b200_attention_fl`` on the GPU: every attention kernel (CUDA-core block kernel, warp-per-component kernel,
-mma.sync 3xTF32 tensor-core kernel) on the SAME random augmented operands against a float64 statement of the
+mma.sync 3xTF32 tensor-core kernel with truncating (3) and round-to-nearest (4) operand splits) on the SAME random augmented operands against a float64 statement of the
 forward-Laplacian rule of ``softmax(q k^T / sqrt(d)) v``.  Operand-level, so that the tile-shape edge cases
 (n = 17, 32, 33, 48 ...) are tested without the conditioning of a wavefunction entering: the network-level parity tests
 in test_gpu_attention_nets.py cannot separate a kernel error from an ill-conditioned walker.
@@ -120,8 +120,8 @@ def _errors(out, ref):
 
 
 # (n, kernels that must support the shape)
-SHAPES = [(5, (1, 2, 3)), (14, (1, 2, 3)), (15, (1, 3)), (16, (1, 3)), (17, (1, 3)), (18, (1, 3)), (24, (1, 3)), (30, (1, 3)), (32, (1, 3)),
-          (33, (1, 3)), (40, (1, 3)), (42, (1, 3)), (47, (1, 3)), (48, (1, 3))]
+SHAPES = [(5, (1, 2, 3, 4)), (14, (1, 2, 3, 4)), (15, (1, 3, 4)), (16, (1, 3, 4)), (17, (1, 3, 4)), (18, (1, 3, 4)), (24, (1, 3, 4)), (30, (1, 3, 4)), (32, (1, 3, 4)),
+          (33, (1, 3, 4)), (40, (1, 3, 4)), (42, (1, 3, 4)), (47, (1, 3, 4)), (48, (1, 3, 4))]
 
 
 @pytest.mark.gpu
