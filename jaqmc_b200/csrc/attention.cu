@@ -1218,12 +1218,12 @@ k_attention_fl_warp(JqAttnOperand q, JqAttnOperand k, JqAttnOperand v, float* __
 // The Laplacian row needs only X and oL2:  with Y = X + w aL' (aL' = (qL k^T + q kL^T)/sqrt(d)),
 //   wL = Y - w rowsum(Y)   (the t2 term of the SIMT kernels cancels: sum_j wJ_ij = 0),   oL = 2 oL2 + wL v + w vL.
 // The RT warps of a slot share the staged kJ / vJ tiles (cp.async, named barrier per slot).
-// Shared (floats): q0 k0 v0 [48][68] | w [48][56] | per slot: kJ vJ [48][68]
+// Shared (floats): q0 k0 v0 [NP][68] | w [NP][56] | per slot: kJ vJ [NP][68], NP = 16 RT the padded electron count.
+// Instantiated as <NJ, NP, SLOTS> = <2, 16, 8> (n <= 16, two blocks per SM), <4, 32, 4>, <6, 48, 4>.
 // ------------------------------------------------------------------------------------------------
 constexpr int AM_LD = 68;     // 68 mod 32 = 4: the (g, t) fragment loads touch 32 distinct banks
 constexpr int AM_LW = 56;     // 56 mod 32 = 24: the float2 accumulator-layout loads of w are conflict-free per half-warp
-constexpr int AM_SLOTS = 4;
-constexpr int AM_NP = 48;     // padded electron count
+constexpr int AM_NP = 48;     // largest padded electron count
 
 // x = hi + lo for the 3xTF32 products.  RNA: both parts rounded to nearest with cvt.rna.tf32.f32 -- which sm_100a has no
 // single instruction for: ncu shows ~11 integer / predicate instructions per split, 63 % of everything the first version
@@ -1264,21 +1264,21 @@ __device__ __forceinline__ const float* am_row(const JqAttnOperand& t, long long
   return (k / 3 == i) ? base + (long long)(1 + k % 3) * t.ld : nullptr;
 }
 
-template <int NJ, bool RNA>
-__global__ void __launch_bounds__(AM_SLOTS * 3 * 32, 1)
+template <int NJ, int NP, int SLOTS, bool RNA>
+__global__ void __launch_bounds__(SLOTS * (NP / 16) * 32, NP == 16 ? 2 : 1)
 k_attention_fl_mma(JqAttnOperand q, JqAttnOperand k, JqAttnOperand v, float* __restrict__ out, int ldo, int n, int H) {
   constexpr int dh = 64;
   JQ_DYN_SMEM(float, sm);
-  constexpr int NT = AM_NP * AM_LD;
+  constexpr int NT = NP * AM_LD;
   float* q0 = sm;
   float* k0 = q0 + NT;
   float* v0 = k0 + NT;
   float* wgt = v0 + NT;                   // [48][56]
-  float* slots = wgt + AM_NP * AM_LW;     // per slot: kJ | vJ
+  float* slots = wgt + NP * AM_LW;     // per slot: kJ | vJ
   const long long w = blockIdx.x / H;
   const int h = blockIdx.x % H;
   const int tid = threadIdx.x, nthr = blockDim.x, warp = tid >> 5, lane = tid & 31;
-  const int RT = (n + 15) >> 4;
+  constexpr int RT = NP / 16;
   const int slot = warp / RT, r = warp - slot * RT;
   const int g = lane >> 2, t = lane & 3;
   const int Cd = 3 * n + 2, K = 3 * n;
@@ -1287,7 +1287,7 @@ k_attention_fl_mma(JqAttnOperand q, JqAttnOperand k, JqAttnOperand v, float* __r
   float* vJs = kJs + NT;
 
   // ---- value row: operands (zero padded), logits, softmax, o = w v ----
-  for (int x = tid; x < 3 * NT + AM_NP * AM_LW + AM_SLOTS * 2 * NT; x += nthr) sm[x] = 0.f;
+  for (int x = tid; x < 3 * NT + NP * AM_LW + SLOTS * 2 * NT; x += nthr) sm[x] = 0.f;
   __syncthreads();
   for (int x = tid; x < n * 16; x += nthr) {
     const int i = x >> 4, d4 = (x & 15) * 4;
@@ -1333,7 +1333,7 @@ k_attention_fl_mma(JqAttnOperand q, JqAttnOperand k, JqAttnOperand v, float* __r
 #pragma unroll
   for (int a = 0; a < 8; ++a) oL2[a][0] = oL2[a][1] = oL2[a][2] = oL2[a][3] = 0.f;
   const int sthreads = 32 * RT, sl = r * 32 + lane;
-  const bool slot_on = slot < AM_SLOTS;
+  const bool slot_on = slot < SLOTS;
   if (slot_on) {
     // softmax weights of this warp's rows in accumulator layout: re-read from shared memory where they are used (24
     // registers fewer than keeping them; the first version of this kernel spilled 300 bytes per thread)
@@ -1341,7 +1341,7 @@ k_attention_fl_mma(JqAttnOperand q, JqAttnOperand k, JqAttnOperand v, float* __r
     const float* wrow1 = wgt + i1 * AM_LW + 2 * t;
     // (Measured r2: fetching kJ of the next component during phases B / C and vJ during phase A -- one more named
     // barrier per component -- changed the launch time by 1-2 %, inside the box-to-box spread; the simpler form is kept.)
-    for (int kk = slot; kk < K; kk += AM_SLOTS) {
+    for (int kk = slot; kk < K; kk += SLOTS) {
       const int comp = 1 + kk;
       asm volatile("bar.sync %0, %1;" ::"r"(1 + slot), "r"(sthreads) : "memory");   // previous tiles fully consumed
       for (int x = sl; x < n * 16; x += sthreads) {
@@ -1479,14 +1479,14 @@ k_attention_fl_mma(JqAttnOperand q, JqAttnOperand k, JqAttnOperand v, float* __r
   __syncthreads();
   float* Xs = slots;            // slot 0: X [48][56] | oL2 [48][68]
   float* oLs = slots + NT;
-  for (int x = tid; x < AM_NP * AM_LW; x += nthr) {
+  for (int x = tid; x < NP * AM_LW; x += nthr) {
     float s2 = 0.f;
-    for (int ss = 0; ss < AM_SLOTS; ++ss) s2 += slots[(size_t)ss * 2 * NT + x];
+    for (int ss = 0; ss < SLOTS; ++ss) s2 += slots[(size_t)ss * 2 * NT + x];
     Xs[x] = s2;
   }
   for (int x = tid; x < NT; x += nthr) {
     float s2 = 0.f;
-    for (int ss = 0; ss < AM_SLOTS; ++ss) s2 += slots[(size_t)ss * 2 * NT + NT + x];
+    for (int ss = 0; ss < SLOTS; ++ss) s2 += slots[(size_t)ss * 2 * NT + NT + x];
     oLs[x] = s2;
   }
   __syncthreads();
@@ -1571,7 +1571,10 @@ int jq_launch_attention_fl_sel(const JqAttnOperand& q, const JqAttnOperand& k, c
                                                reinterpret_cast<uintptr_t>(v.p)) % 16 == 0);
     const int nt = n * AW_LD, nn = n * AW_NS;
     const size_t sw = sizeof(float) * ((size_t)3 * nt + nn + (2 * nn + 32 + 2 * n * 64) + (size_t)AW_WARPS * (6 * nt + 3 * nn + 48));
-    if (track && dh == 64 && n >= 2 && n <= AW_NS && sw <= 227 * 1024 && aligned && !old_kernel && (force == 0 || force == 2)) {
+    static const bool env_warp = getenv("JAQMC_B200_ATTENTION_WARP") != nullptr;   // A/B switch: warp kernel for n <= 14
+    const bool mma_ok = dh == 64 && n >= 2 && n <= AM_NP && ldo % 2 == 0 && reinterpret_cast<uintptr_t>(out) % 8 == 0;
+    const bool prefer_warp = force == 2 || env_warp || !mma_ok || getenv("JAQMC_B200_ATTENTION_SIMT") != nullptr;
+    if (track && dh == 64 && n >= 2 && n <= AW_NS && sw <= 227 * 1024 && aligned && !old_kernel && (force == 0 || force == 2) && prefer_warp) {
       const bool qkl = (q.C == 5 && k.C == 5 && Cd != 5);
       cudaError_t e = qkl ? cudaFuncSetAttribute(k_attention_fl_warp<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sw)
                           : cudaFuncSetAttribute(k_attention_fl_warp<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sw);
@@ -1587,25 +1590,30 @@ int jq_launch_attention_fl_sel(const JqAttnOperand& q, const JqAttnOperand& k, c
     // (also n = 15, 16, where the warp kernel's per-warp staging no longer fits in shared memory)
     if (track && dh == 64 && n >= 2 && n <= AM_NP && aligned && ldo % 2 == 0 &&
         reinterpret_cast<uintptr_t>(out) % 8 == 0 && !old_kernel && !simt_kernel) {
-      const int RT = (n + 15) / 16;
-      const size_t sm_mma = sizeof(float) * ((size_t)3 * AM_NP * AM_LD + AM_NP * AM_LW + (size_t)AM_SLOTS * 2 * AM_NP * AM_LD);
       static const bool env_rna = getenv("JAQMC_B200_ATTENTION_RNA") != nullptr;   // A/B switch: round-to-nearest operand split
       const bool rna = force == 4 || (force != 3 && env_rna);
-      static JqPerDeviceFlag attr_set;
-      const int dev = jq_current_device();
-      if (!attr_set.done[dev]) {
-        cudaError_t e = cudaFuncSetAttribute(k_attention_fl_mma<6, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_mma);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_attention_fl_mma<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_mma);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_attention_fl_mma<6, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_mma);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_attention_fl_mma<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_mma);
-        JQ_REQUIRE(e == cudaSuccess, JQ_ERR_CUDA, "attention: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-        attr_set.done[dev] = true;
-      }
-      const dim3 grid((unsigned)(W * H)), block(32 * RT * AM_SLOTS);
-      if (n <= 32 && !rna) JQ_LAUNCH((k_attention_fl_mma<4, false>), grid, block, sm_mma, st, q, k, v, out, ldo, n, H);
-      else if (n <= 32) JQ_LAUNCH((k_attention_fl_mma<4, true>), grid, block, sm_mma, st, q, k, v, out, ldo, n, H);
-      else if (!rna) JQ_LAUNCH((k_attention_fl_mma<6, false>), grid, block, sm_mma, st, q, k, v, out, ldo, n, H);
-      else JQ_LAUNCH((k_attention_fl_mma<6, true>), grid, block, sm_mma, st, q, k, v, out, ldo, n, H);
+      const int NP = 16 * ((n + 15) / 16), SL = NP == 16 ? 8 : 4;
+      const size_t sm_mma = sizeof(float) * ((size_t)3 * NP * AM_LD + NP * AM_LW + (size_t)SL * 2 * NP * AM_LD);
+      const dim3 grid((unsigned)(W * H)), block(32 * (NP / 16) * SL);
+#define JQ_AM_LAUNCH(NJ_, NP_, SL_, RNA_)                                                                                \
+  do {                                                                                                                   \
+    static JqPerDeviceFlag attr_set;                                                                                     \
+    const int dev = jq_current_device();                                                                                 \
+    if (!attr_set.done[dev]) {                                                                                           \
+      cudaError_t e = cudaFuncSetAttribute(k_attention_fl_mma<NJ_, NP_, SL_, RNA_>,                                      \
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_mma);                   \
+      JQ_REQUIRE(e == cudaSuccess, JQ_ERR_CUDA, "attention: cudaFuncSetAttribute: %s", cudaGetErrorString(e));           \
+      attr_set.done[dev] = true;                                                                                         \
+    }                                                                                                                    \
+    JQ_LAUNCH((k_attention_fl_mma<NJ_, NP_, SL_, RNA_>), grid, block, sm_mma, st, q, k, v, out, ldo, n, H);             \
+  } while (0)
+      if (NP == 16 && !rna) JQ_AM_LAUNCH(2, 16, 8, false);
+      else if (NP == 16) JQ_AM_LAUNCH(2, 16, 8, true);
+      else if (NP == 32 && !rna) JQ_AM_LAUNCH(4, 32, 4, false);
+      else if (NP == 32) JQ_AM_LAUNCH(4, 32, 4, true);
+      else if (!rna) JQ_AM_LAUNCH(6, 48, 4, false);
+      else JQ_AM_LAUNCH(6, 48, 4, true);
+#undef JQ_AM_LAUNCH
       JQ_CHECK_LAUNCH();
       return JQ_OK;
     }
