@@ -129,6 +129,11 @@ int jq_launch_orb_envelope(float* orb, const float* electrons, const float* atom
                            int W, JqSpins sp, int A, int D, int track, cudaStream_t st);
 int jq_launch_logdet(const float* orb, int W, int n, int D, int track, float* det_sign, float* det_logabs,
                      float* det_grad, float* det_lap, cudaStream_t st);
+// value path, n <= 32: envelope (isotropic / abs_isotropic) applied while the rows are loaded, then the LU
+bool jq_logdet_value_env_eligible(int n, int A, int env_type);
+int jq_launch_logdet_value_env(const float* orb, const float* electrons, const float* atoms, const JqEnvelopeArgs& env,
+                               int has_env, int W, JqSpins sp, int A, int D, float* det_sign, float* det_logabs,
+                               cudaStream_t st);
 int jq_launch_logdet_combine(const float* det_sign, const float* det_logabs, const float* det_grad,
                              const float* det_lap, int W, int n, int D, int track, const float* extra_logpsi,
                              float* logpsi, float* sign, float* grad, float* lap, float* e_kin, cudaStream_t st);

@@ -197,14 +197,20 @@ int jq_head_forward(const JqHeadDims& d, const jaqmc_head_params* p, const float
   env.sigma[0] = p->env_sigma[0];
   env.pi[1] = split ? p->env_pi[1] : nullptr;
   env.sigma[1] = split ? p->env_sigma[1] : nullptr;
-  if (!env_fused && (rc = jq_launch_orb_envelope(b.orb, electrons, atoms, env, (int)W, d.sp, d.A, d.D, track, st)))
+  // sampling path (value only, n <= 32): the envelope is applied inside the determinant kernel as it loads the rows
+  const bool env_in_logdet = !track && !out.orbitals && jq_logdet_value_env_eligible(n, d.A, d.envelope_type);
+  if (!env_fused && !env_in_logdet &&
+      (rc = jq_launch_orb_envelope(b.orb, electrons, atoms, env, (int)W, d.sp, d.A, d.D, track, st)))
     return rc;
   if (out.orbitals) {   // wf.orbitals (pretraining head): the matrices themselves, no determinant
     JQ_REQUIRE(!track, JQ_ERR_INVALID_ARGUMENT, "head: orbitals are emitted on the value path only");
     return jq_launch_orbitals_out(b.orb, nullptr, out.orbitals, W, n, d.D, st);
   }
-  if ((rc = jq_launch_logdet(b.orb, (int)W, n, d.D, track, b.det_sign, b.det_logabs, b.det_grad, b.det_lap, st)))
-    return rc;
+  if (env_in_logdet)
+    rc = jq_launch_logdet_value_env(b.orb, electrons, atoms, env, 1, (int)W, d.sp, d.A, d.D, b.det_sign, b.det_logabs, st);
+  else
+    rc = jq_launch_logdet(b.orb, (int)W, n, d.D, track, b.det_sign, b.det_logabs, b.det_grad, b.det_lap, st);
+  if (rc) return rc;
   if (d.jastrow &&
       (rc = jq_launch_jastrow(electrons, p->jastrow_alpha_par, p->jastrow_alpha_anti, (int)W, d.sp, track, b.extra, st)))
     return rc;

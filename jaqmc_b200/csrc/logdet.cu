@@ -980,21 +980,60 @@ __global__ void __launch_bounds__(256, 3) k_logdet(const float* __restrict__ orb
 // log|det|.  sign = parity(step -> row permutation) * prod sign(pivot); log|det| = log prod |pivot| in double.
 // ------------------------------------------------------------------------------------------------
 template <int NMAX>
-__global__ void __launch_bounds__(256) k_logdet_value_warp(const float* __restrict__ orb, int n, int D, long long M,
+__global__ void __launch_bounds__(256) k_logdet_value_warp(const float* __restrict__ orb, const float* __restrict__ el,
+                                                          const float* __restrict__ atoms, JqEnvelopeArgs env, int has_env,
+                                                          JqSpins sp, int A, int n, int D, long long M,
                                                           float* __restrict__ det_sign, float* __restrict__ det_logabs) {
-  const unsigned full = 0xffffffffu;
+  // r2: NMAX lanes per matrix (32 / NMAX matrices per warp, sub-group shuffles), and the isotropic envelope
+  // (output/envelope.py:131-135) applied to the row as it is loaded when has_env -- k_orb_envelope_value's arithmetic,
+  // without its pass over the orbital buffer (the two kernels were 20 % of a sampling forward pass).
+  constexpr int LPM = NMAX, MPW = 32 / NMAX;
   const int lane = threadIdx.x & 31;
-  const long long m = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);   // matrix = (walker, determinant)
-  if (m >= M) return;
+  const int sub = lane / LPM, hl = lane - sub * LPM;
+  // all collectives below use the FULL mask with a width: sub-group masks (tried first) compile to MATCH / branch /
+  // BSYNC sequences that made the LU 13 % slower than the one-matrix-per-warp kernel it replaced (ncu, r2)
+  const unsigned full = 0xffffffffu;
+  const unsigned smask = (LPM == 32) ? 0xffffffffu : ((1u << LPM) - 1u);
+  const long long m0 = ((long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * MPW + sub;   // (walker, determinant)
+  const bool on = m0 < M;
+  const long long m = on ? m0 : M - 1;
   const long long w = m / D;
   const int d = (int)(m - w * D);
   const int DN = D * n;
   float a[NMAX];
-  bool used = lane >= n;
+  bool used = hl >= n || !on;
+  const int j = hl < n ? hl : 0;   // electron = row
   {
-    const float* row = orb + (w * n + (used ? 0 : lane)) * (long long)DN + d * n;
+    const float* row = orb + (w * n + j) * (long long)DN + d * n;
 #pragma unroll
     for (int c = 0; c < NMAX; ++c) a[c] = (c < n) ? row[c] : 0.f;
+  }
+  if (has_env) {
+    const float* e3 = el + (w * n + j) * 3;
+    const float px = e3[0], py = e3[1], pz = e3[2];
+    const int ch = (env.pi[1] != nullptr && sp.chan_of(j) == 1) ? 1 : 0;
+    const float* pi = env.pi[ch];
+    const float* sg = env.sigma[ch];
+    float r[ENVV_A];
+#pragma unroll
+    for (int I = 0; I < ENVV_A; ++I) {
+      const float dx = px - ((I < A) ? atoms[3 * I] : 0.f), dy = py - ((I < A) ? atoms[3 * I + 1] : 0.f),
+                  dz = pz - ((I < A) ? atoms[3 * I + 2] : 0.f);
+      r[I] = sqrtf(dx * dx + dy * dy + dz * dz);
+    }
+#pragma unroll
+    for (int c = 0; c < NMAX; ++c)
+      if (c < n) {
+        float e = 0.f;
+#pragma unroll
+        for (int I = 0; I < ENVV_A; ++I)
+          if (I < A) {
+            float sv = sg[(c * A + I) * D + d];
+            if (env.type == 1) sv = fabsf(sv);
+            e += pi[(c * A + I) * D + d] * expf(-sv * r[I]);
+          }
+        a[c] *= e;
+      }
   }
   int step_of = 0;
   float sgn = 1.0f;
@@ -1005,10 +1044,12 @@ __global__ void __launch_bounds__(256) k_logdet_value_warp(const float* __restri
   for (int p = 0; p < NMAX; ++p) {
     if (p < n) {
       const unsigned key = used ? 0u : __float_as_uint(fabsf(a[p]));
-      const unsigned mx = __reduce_max_sync(full, key);
-      const unsigned cand = __ballot_sync(full, !used && key == mx);
-      const int pl = __ffs(cand) - 1;               // first row holding the largest magnitude
-      const float pv = __shfl_sync(full, a[p], pl);
+      unsigned mx = key;
+#pragma unroll
+      for (int o = LPM / 2; o > 0; o >>= 1) mx = max(mx, __shfl_xor_sync(full, mx, o, LPM));
+      const unsigned cand = (__ballot_sync(full, !used && key == mx) >> (sub * LPM)) & smask;
+      const int pl = cand ? __ffs(cand) - 1 : 0;    // first row holding the largest magnitude
+      const float pv = __shfl_sync(full, a[p], pl, LPM);
       if (pv < 0.f) sgn = -sgn;
       if (pv == 0.f) sgn = 0.f;
       {
@@ -1017,7 +1058,7 @@ __global__ void __launch_bounds__(256) k_logdet_value_warp(const float* __restri
         expo += e;
       }
       const float pinv = 1.0f / pv;
-      if (lane == pl) {
+      if (hl == pl && !used) {
         used = true;
         step_of = p;
       }
@@ -1025,39 +1066,67 @@ __global__ void __launch_bounds__(256) k_logdet_value_warp(const float* __restri
 #pragma unroll
       for (int c = p + 1; c < NMAX; ++c)
         if (c < n) {
-          const float pc = __shfl_sync(full, a[c], pl);
+          const float pc = __shfl_sync(full, a[c], pl, LPM);
           a[c] = fmaf(-f, pc, a[c]);
         }
     }
   }
-  // parity of the permutation row -> step: inversions counted per lane, summed over the warp
+  // parity of the permutation row -> step: inversions counted per lane, summed over the sub-group
   int inv_count = 0;
   for (int i = 0; i < n; ++i) {
-    const int si = __shfl_sync(full, step_of, i);
-    if (i < lane && lane < n && si > step_of) ++inv_count;
+    const int si = __shfl_sync(full, step_of, i, LPM);
+    if (i < hl && hl < n && si > step_of) ++inv_count;
   }
-  const int total = __reduce_add_sync(full, inv_count);
-  if (lane == 0) {
+  int total = inv_count;
+#pragma unroll
+  for (int o = LPM / 2; o > 0; o >>= 1) total += __shfl_xor_sync(full, total, o, LPM);
+  if (on && hl == 0) {
     det_sign[m] = (total & 1) ? -sgn : sgn;
     det_logabs[m] = (float)(log(mant) + (double)expo * 0.69314718055994530942);
   }
 }
 #endif
 
+// Value-only slogdet of orb [W][n][D*n] (n <= 32), optionally times the isotropic envelope of (electrons, atoms) first.
+bool jq_logdet_value_env_eligible(int n, int A, int env_type) {
+#ifdef JAQMC_HOST_EMU
+  return false;
+#else
+  static const bool off = getenv("JAQMC_B200_UNFUSED_ENV_LOGDET") != nullptr;   // A/B switch
+  return !off && n <= 32 && A <= ENVV_A && (env_type == 0 || env_type == 1);
+#endif
+}
+
+int jq_launch_logdet_value_env(const float* orb, const float* electrons, const float* atoms, const JqEnvelopeArgs& env,
+                               int has_env, int W, JqSpins sp, int A, int D, float* det_sign, float* det_logabs,
+                               cudaStream_t st) {
+#ifdef JAQMC_HOST_EMU
+  return JQ_ERR_UNSUPPORTED;
+#else
+  const int n = sp.n();
+  const long long M = (long long)W * D;
+  if (M <= 0) return JQ_OK;
+  JQ_REQUIRE(n <= 32, JQ_ERR_UNSUPPORTED, "logdet (value): n=%d", n);
+  const int lpm = n <= 4 ? 4 : n <= 8 ? 8 : n <= 16 ? 16 : 32;
+  const dim3 grid((unsigned)jq_cdiv(M, 8 * (32 / lpm))), block(256);
+  jq_prof_work((double)M * 0.67 * n * n * n, 4.0 * (double)M * n * n);
+  if (lpm == 4) JQ_LAUNCH(k_logdet_value_warp<4>, grid, block, 0, st, orb, electrons, atoms, env, has_env, sp, A, n, D, M, det_sign, det_logabs);
+  else if (lpm == 8) JQ_LAUNCH(k_logdet_value_warp<8>, grid, block, 0, st, orb, electrons, atoms, env, has_env, sp, A, n, D, M, det_sign, det_logabs);
+  else if (lpm == 16) JQ_LAUNCH(k_logdet_value_warp<16>, grid, block, 0, st, orb, electrons, atoms, env, has_env, sp, A, n, D, M, det_sign, det_logabs);
+  else JQ_LAUNCH(k_logdet_value_warp<32>, grid, block, 0, st, orb, electrons, atoms, env, has_env, sp, A, n, D, M, det_sign, det_logabs);
+  JQ_CHECK_LAUNCH();
+  return JQ_OK;
+#endif
+}
+
 int jq_launch_logdet(const float* orb, int W, int n, int D, int track, float* det_sign, float* det_logabs,
                      float* det_grad, float* det_lap, cudaStream_t st) {
   if ((long long)W * D <= 0) return JQ_OK;
 #ifndef JAQMC_HOST_EMU
   if (!track && n <= 32) {
-    const long long M = (long long)W * D;
-    const dim3 grid((unsigned)jq_cdiv(M, 8)), block(256);
-    jq_prof_work((double)M * 0.67 * n * n * n, 4.0 * (double)M * n * n);
-    if (n <= 4) JQ_LAUNCH(k_logdet_value_warp<4>, grid, block, 0, st, orb, n, D, M, det_sign, det_logabs);
-    else if (n <= 8) JQ_LAUNCH(k_logdet_value_warp<8>, grid, block, 0, st, orb, n, D, M, det_sign, det_logabs);
-    else if (n <= 16) JQ_LAUNCH(k_logdet_value_warp<16>, grid, block, 0, st, orb, n, D, M, det_sign, det_logabs);
-    else JQ_LAUNCH(k_logdet_value_warp<32>, grid, block, 0, st, orb, n, D, M, det_sign, det_logabs);
-    JQ_CHECK_LAUNCH();
-    return JQ_OK;
+    JqEnvelopeArgs no_env;
+    memset(&no_env, 0, sizeof(no_env));
+    return jq_launch_logdet_value_env(orb, nullptr, nullptr, no_env, 0, W, JqSpins{n, 0}, 0, D, det_sign, det_logabs, st);
   }
 #endif
   const int C = track ? 3 * n + 2 : 1;
