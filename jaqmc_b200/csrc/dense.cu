@@ -649,6 +649,65 @@ __global__ void __launch_bounds__(256) k_pair_layer_fused(const float* __restric
   }
 }
 
+// Value-only (sampling path) version of the same layer, r2: with one pair per iteration (k_pair_layer_fused<K, 1>) only
+// K / 4 lanes of the warp had a load in flight -- 128 bytes per warp, 1.5 TB/s (ncu).  Here a batch of PB = 128 / K pairs
+// is fetched with one float4 per lane (512 bytes per warp in flight, the next batch prefetched), then the pairs of the
+// batch are contracted one after the other from the shared tile.
+template <int K>
+__global__ void __launch_bounds__(256) k_pair_layer_value(const float* __restrict__ h2, const float* __restrict__ w0,
+                                                         const float* __restrict__ bias, float* __restrict__ h2n,
+                                                         float* __restrict__ g2, long long WJ, JqSpins sp, int residual) {
+  constexpr int V4 = K / 4, PB = 32 / V4;
+  __shared__ float4 tile_all[8][32];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float4* tile = tile_all[warp];
+  const float* tile_f = reinterpret_cast<const float*>(tile);
+  const int n = sp.n(), nch = sp.nch(), FO = nch * 32;
+  float wreg[K];
+#pragma unroll
+  for (int k = 0; k < K; ++k) wreg[k] = w0[k * 32 + lane];
+  const float b = bias ? bias[lane] : 0.f;
+  const float inv_sqrt2 = 0.70710678118654752440f;
+  const float4* src4 = reinterpret_cast<const float4*>(h2);
+  const int pp_l = lane / V4, v_l = lane - pp_l * V4;   // this lane's pair of the batch and float4 of that pair
+  const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (long long wj = (long long)blockIdx.x * 8 + warp; wj < WJ; wj += (long long)gridDim.x * 8) {
+    const long long w = wj / n;
+    const int j = (int)(wj - w * n);
+    float sx0 = 0.f, sx1 = 0.f;
+    float4 nxt = (pp_l < n) ? src4[((w * n + pp_l) * n + j) * V4 + v_l] : zero4;
+    for (int i0 = 0; i0 < n; i0 += PB) {
+      tile[lane] = nxt;
+      const int in = i0 + PB + pp_l;
+      nxt = (in < n) ? src4[((w * n + in) * n + j) * V4 + v_l] : zero4;
+      __syncwarp();
+      const int np = (n - i0 < PB) ? n - i0 : PB;
+      for (int pp = 0; pp < np; ++pp) {
+        const int i = i0 + pp;
+        float acc = 0.f;
+#pragma unroll
+        for (int k = 0; k < K; k += 4) {
+          const float4 x = tile[pp * V4 + k / 4];
+          acc = fmaf(x.x, wreg[k], acc);
+          acc = fmaf(x.y, wreg[k + 1], acc);
+          acc = fmaf(x.z, wreg[k + 2], acc);
+          acc = fmaf(x.w, wreg[k + 3], acc);
+        }
+        float y = tanhf(acc + b);
+        if (residual) y = (tile_f[pp * K + lane] + y) * inv_sqrt2;   // K == 32 here
+        if (h2n) h2n[((w * n + i) * n + j) * 32 + lane] = y;
+        const bool c1 = sp.chan_of(i) == 1;
+        sx0 += c1 ? 0.f : y;
+        sx1 += c1 ? y : 0.f;
+      }
+      __syncwarp();
+    }
+    float* o = g2 + wj * FO + lane;
+    o[0] = sx0 * (1.0f / (float)(sp.hi(0) - sp.lo(0)));
+    if (nch == 2) o[32] = sx1 * (1.0f / (float)(sp.hi(1) - sp.lo(1)));
+  }
+}
+
 // h2 [W][n*n][C2][K] -> h2n [W][n*n][C2][32] (or null) and g2 [W][n][C][nch*32] (C2 = 8, C = 3n+2 tracked; 1, 1 value
 // only); false when the shape is not covered
 bool jq_launch_pair_layer_fused(const float* h2, int K, const float* w0, const float* bias, float* h2n, float* g2, int W,
@@ -668,8 +727,15 @@ bool jq_launch_pair_layer_fused(const float* h2, int K, const float* w0, const f
     if (K == 4) JQ_PLF(4, 8);
     else JQ_PLF(32, 8);
   } else {
-    if (K == 4) JQ_PLF(4, 1);
-    else JQ_PLF(32, 1);
+    static const bool one_pair = getenv("JAQMC_B200_PAIR_LAYER_ONE_PAIR") != nullptr;   // A/B switch: one pair per iteration
+    if (one_pair) {
+      if (K == 4) JQ_PLF(4, 1);
+      else JQ_PLF(32, 1);
+    } else if (K == 4) {
+      JQ_LAUNCH(k_pair_layer_value<4>, dim3((unsigned)blocks), dim3(256), 0, st, h2, w0, bias, h2n, g2, WJ, sp, residual);
+    } else {
+      JQ_LAUNCH(k_pair_layer_value<32>, dim3((unsigned)blocks), dim3(256), 0, st, h2, w0, bias, h2n, g2, WJ, sp, residual);
+    }
   }
 #undef JQ_PLF
   cudaError_t e = cudaGetLastError();
