@@ -110,6 +110,120 @@ __global__ void k_minv(const float* __restrict__ M, long long MT, int n, int D, 
   }
 }
 
+#ifndef JAQMC_HOST_EMU
+// Device version (r2): one HALF-warp per matrix, lane r = row r of [A | I] in registers, Gauss-Jordan with shuffle
+// pivoting and no row movement (the scheme of k_logdet_small): at step p the pivot is the largest |a[r][p]| among the
+// rows not used yet -- the same choice as the row-swapping elimination above -- and row p of A^-1 is the right half of
+// the row that served as pivot p.  The thread-per-matrix kernel kept 2 KB of local arrays per thread and ran with 256
+// blocks of 64 threads: 1.50 ms of a 10.5 ms reverse pass (ncu, N2, 4096 walkers).
+__global__ void __launch_bounds__(256) k_minv_small(const float* __restrict__ M, long long MT, int n, int D,
+                                                    float* __restrict__ minv, float* __restrict__ sign,
+                                                    float* __restrict__ logabs) {
+  const unsigned full = 0xffffffffu;
+  const int lane = threadIdx.x & 31, half = lane >> 4, hl = lane & 15;
+  const long long m0 = ((long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 2 + half;
+  const bool on = m0 < MT;
+  const long long m = on ? m0 : MT - 1;
+  const long long w = m / D;
+  const int d = (int)(m - w * D);
+  bool used = !on || hl >= n;
+  float a[BW_NMAX], bi[BW_NMAX];
+  {
+    const float* row = M + (w * n + (hl < n ? hl : 0)) * (long long)D * n + d * n;
+#pragma unroll
+    for (int c = 0; c < BW_NMAX; ++c) {
+      a[c] = (!used && c < n) ? row[c] : 0.f;
+      bi[c] = (c == hl) ? 1.0f : 0.f;
+    }
+  }
+  int step_of = 0;
+  float sg = 1.0f;
+  double mant = 1.0;
+  int expo = 0;
+#pragma unroll
+  for (int p = 0; p < BW_NMAX; ++p) {
+    if (p < n) {
+      const unsigned key = used ? 0u : __float_as_uint(fabsf(a[p]));
+      unsigned mx = key;
+#pragma unroll
+      for (int o = 8; o > 0; o >>= 1) mx = max(mx, __shfl_xor_sync(full, mx, o));
+      const unsigned cand = (__ballot_sync(full, !used && key == mx) >> (16 * half)) & 0xffffu;
+      const int pl = cand ? __ffs(cand) - 1 : 0;
+      const float pv = __shfl_sync(full, a[p], pl, 16);
+      if (pv < 0.f) sg = -sg;
+      if (pv == 0.f) sg = 0.f;
+      {
+        int e;
+        mant *= (double)frexpf(fabsf(pv), &e);
+        expo += e;
+      }
+      const float pinv = 1.0f / pv;
+      const bool is_p = (hl == pl);
+      if (is_p && !used) {
+        used = true;
+        step_of = p;
+      }
+      const float f = is_p ? 0.f : a[p];
+#pragma unroll
+      for (int c = 0; c < BW_NMAX; ++c)
+        if (c < n) {
+          const float ap = __shfl_sync(full, a[c], pl, 16) * pinv;
+          const float bp = __shfl_sync(full, bi[c], pl, 16) * pinv;
+          if (is_p) {
+            a[c] = ap;
+            bi[c] = bp;
+          } else {
+            a[c] = fmaf(-f, ap, a[c]);
+            bi[c] = fmaf(-f, bp, bi[c]);
+          }
+        }
+    }
+  }
+  int invc = 0;
+  for (int i = 0; i < n; ++i) {
+    const int si = __shfl_sync(full, step_of, i, 16);
+    if (i < hl && hl < n && si > step_of) ++invc;
+  }
+#pragma unroll
+  for (int o = 8; o > 0; o >>= 1) invc += __shfl_xor_sync(full, invc, o);
+  if (on && hl < n) {
+    float* dst = minv + (m * n + step_of) * n;
+#pragma unroll
+    for (int c = 0; c < BW_NMAX; ++c)
+      if (c < n) dst[c] = bi[c];
+  }
+  if (on && hl == 0) {
+    sign[m] = (invc & 1) ? -sg : sg;
+    logabs[m] = (float)(log(mant) + (double)expo * 0.69314718055994530942);
+  }
+}
+
+// out[p] = sum_s part[s * stride + p] for few outputs and many partials: a block takes 32 outputs (lanes) x 8 slices of
+// the partial index (warps); slice sums and the final sum over the slices both run in a fixed order.  The simple kernel
+// below walks all S partials in one thread: with S ~ 1000 and one block (the column sums of the bias gradients) that was
+// 0.32 - 0.78 ms per call, 3.9 ms of the reverse pass.
+__global__ void __launch_bounds__(256) k_reduce_partials_wide(const float* __restrict__ part, int S, long long stride,
+                                                              long long P, float* __restrict__ out) {
+  __shared__ float sl[8][32];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (long long p0 = (long long)blockIdx.x * 32; p0 < P; p0 += (long long)gridDim.x * 32) {
+    const long long p = p0 + lane;
+    float acc = 0.f;
+    if (p < P)
+      for (int s2 = warp; s2 < S; s2 += 8) acc += part[(long long)s2 * stride + p];
+    sl[warp][lane] = acc;
+    __syncthreads();
+    if (warp == 0 && p < P) {
+      float t = 0.f;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) t += sl[q][lane];
+      out[p] = t;
+    }
+    __syncthreads();
+  }
+}
+#endif
+
 // log-sum-exp over determinants (output/logdet.py:65-79) and its adjoint weights:
 //   wdet[w][d] = cot[w] * s_d e^{ld_d - max} / sum_e s_e e^{ld_e - max}
 __global__ void k_det_weights(const float* __restrict__ sign, const float* __restrict__ logabs,
@@ -357,10 +471,127 @@ __global__ void __launch_bounds__(256) k_gemm_tn(const float* __restrict__ X, in
 }
 #endif
 
+#ifndef JAQMC_HOST_EMU
+// dW = X^T dZ on the tensor cores (r2): mma.sync.m16n8k8 TF32, operands split x = hi + lo by truncation (three MMAs per
+// product, FP32 accumulation), same grid and partial layout as k_gemm_tn.  A = X^T is read from the row-major shared tile
+// as A[m = feature][k = row]; the row stride 72 (= 8 mod 32) makes both fragment loads conflict-free.
+// Block tile 64 x 64, 8 warps = 4 feature tiles x 2 halves of the output columns, 32 rows per stage, the next stage's
+// global loads in flight in registers while the current one is multiplied.
+#define GTM_R 32
+#define GTM_LD 72
+__device__ __forceinline__ void gtm_split(float x, unsigned& hi, unsigned& lo) {
+  hi = __float_as_uint(x) & 0xffffe000u;
+  lo = __float_as_uint(x - __uint_as_float(hi));
+}
+__device__ __forceinline__ void gtm_mma(float (&c)[4], const unsigned (&a)[4], const unsigned (&b)[2]) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+__global__ void __launch_bounds__(256) k_gemm_tn_mma(const float* __restrict__ X, int ldx, const float* __restrict__ Z, int ldz,
+                                                     long long R, int Kd, int Nd, int S, float* __restrict__ part) {
+  __shared__ float Xs[GTM_R][GTM_LD], Zs[GTM_R][GTM_LD];
+  const int k0 = blockIdx.x * 64, n0 = blockIdx.y * 64, s = blockIdx.z;
+  const long long r0 = R * s / S, r1 = R * (s + 1) / S;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int mt = warp & 3, nh = warp >> 2;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
+  // staging: thread -> rows lr, lr + 16; columns lc .. lc + 3 of each operand
+  const int lr = threadIdx.x >> 4, lc = (threadIdx.x & 15) * 4;
+  const bool vx = (ldx % 4 == 0) && (k0 + lc + 3 < Kd) && ((reinterpret_cast<uintptr_t>(X) & 15) == 0);
+  const bool vz = (ldz % 4 == 0) && (n0 + lc + 3 < Nd) && ((reinterpret_cast<uintptr_t>(Z) & 15) == 0);
+  float4 px[2], pz[2];
+  auto fetch = [&](long long rb) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const long long r = rb + lr + 16 * h;
+      const bool okr = r < r1;
+      if (okr && vx) px[h] = *reinterpret_cast<const float4*>(X + r * ldx + k0 + lc);
+      else {
+        px[h].x = (okr && k0 + lc + 0 < Kd) ? X[r * ldx + k0 + lc + 0] : 0.f;
+        px[h].y = (okr && k0 + lc + 1 < Kd) ? X[r * ldx + k0 + lc + 1] : 0.f;
+        px[h].z = (okr && k0 + lc + 2 < Kd) ? X[r * ldx + k0 + lc + 2] : 0.f;
+        px[h].w = (okr && k0 + lc + 3 < Kd) ? X[r * ldx + k0 + lc + 3] : 0.f;
+      }
+      if (okr && vz) pz[h] = *reinterpret_cast<const float4*>(Z + r * ldz + n0 + lc);
+      else {
+        pz[h].x = (okr && n0 + lc + 0 < Nd) ? Z[r * ldz + n0 + lc + 0] : 0.f;
+        pz[h].y = (okr && n0 + lc + 1 < Nd) ? Z[r * ldz + n0 + lc + 1] : 0.f;
+        pz[h].z = (okr && n0 + lc + 2 < Nd) ? Z[r * ldz + n0 + lc + 2] : 0.f;
+        pz[h].w = (okr && n0 + lc + 3 < Nd) ? Z[r * ldz + n0 + lc + 3] : 0.f;
+      }
+    }
+  };
+  fetch(r0);
+  for (long long rb = r0; rb < r1; rb += GTM_R) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      *reinterpret_cast<float4*>(&Xs[lr + 16 * h][lc]) = px[h];
+      *reinterpret_cast<float4*>(&Zs[lr + 16 * h][lc]) = pz[h];
+    }
+    __syncthreads();
+    if (rb + GTM_R < r1) fetch(rb + GTM_R);
+#pragma unroll
+    for (int ks = 0; ks < GTM_R / 8; ++ks) {
+      unsigned ah[4], al[4];
+      gtm_split(Xs[8 * ks + t][16 * mt + g], ah[0], al[0]);
+      gtm_split(Xs[8 * ks + t][16 * mt + g + 8], ah[1], al[1]);
+      gtm_split(Xs[8 * ks + t + 4][16 * mt + g], ah[2], al[2]);
+      gtm_split(Xs[8 * ks + t + 4][16 * mt + g + 8], ah[3], al[3]);
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        unsigned bh[2], bl[2];
+        gtm_split(Zs[8 * ks + t][32 * nh + 8 * nt + g], bh[0], bl[0]);
+        gtm_split(Zs[8 * ks + t + 4][32 * nh + 8 * nt + g], bh[1], bl[1]);
+        gtm_mma(acc[nt], al, bh);
+        gtm_mma(acc[nt], ah, bl);
+        gtm_mma(acc[nt], ah, bh);
+      }
+    }
+    __syncthreads();
+  }
+  float* o = part + (long long)s * Kd * Nd;
+#pragma unroll
+  for (int nt = 0; nt < 4; ++nt) {
+    const int nn = n0 + 32 * nh + 8 * nt + 2 * t;
+    const int ka = k0 + 16 * mt + g, kb = ka + 8;
+    if (ka < Kd) {
+      if (nn < Nd) o[(long long)ka * Nd + nn] = acc[nt][0];
+      if (nn + 1 < Nd) o[(long long)ka * Nd + nn + 1] = acc[nt][1];
+    }
+    if (kb < Kd) {
+      if (nn < Nd) o[(long long)kb * Nd + nn] = acc[nt][2];
+      if (nn + 1 < Nd) o[(long long)kb * Nd + nn + 1] = acc[nt][3];
+    }
+  }
+}
+#endif
+
+int grid_for(long long items);
+// fixed-order sum over S partials; wide = parallel over the partial index (device only)
+int launch_reduce_partials(const float* part, int S, long long stride, long long P, float* out, cudaStream_t st);
+
 int grid_for(long long items) {
   int g = jq_cdiv(items, 256);
   if (g > 148 * 32) g = 148 * 32;
   return g < 1 ? 1 : g;
+}
+
+int launch_reduce_partials(const float* part, int S, long long stride, long long P, float* out, cudaStream_t st) {
+#ifndef JAQMC_HOST_EMU
+  if (S >= 16) {
+    long long g = jq_cdiv(P, 32);
+    if (g > 148 * 16) g = 148 * 16;
+    JQ_LAUNCH(k_reduce_partials_wide, dim3((unsigned)g), dim3(256), 0, st, part, S, stride, P, out);
+    JQ_CHECK_LAUNCH();
+    return JQ_OK;
+  }
+#endif
+  JQ_LAUNCH(k_reduce_partials, dim3(grid_for(P)), dim3(256), 0, st, part, S, stride, P, out);
+  JQ_CHECK_LAUNCH();
+  return JQ_OK;
 }
 
 // Row chunks of the reduction GEMM: about four blocks per SM, at least 64 rows per chunk, and the partial results
@@ -383,15 +614,14 @@ int launch_gemm_tn(const float* X, int ldx, const float* Z, int ldz, long long R
 #ifdef JAQMC_HOST_EMU
   JQ_LAUNCH(k_gemm_tn, dim3(grid_for((long long)S * Kd * Nd)), dim3(256), 0, st, X, ldx, Z, ldz, R, Kd, Nd, S, part);
 #else
-  JQ_LAUNCH(k_gemm_tn, dim3(jq_cdiv(Kd, 64), jq_cdiv(Nd, 64), S), dim3(256), 0, st, X, ldx, Z, ldz, R, Kd, Nd, S, part);
+  static const bool simt = getenv("JAQMC_B200_GEMM_TN_SIMT") != nullptr;   // A/B switch: the FP32 CUDA-core kernel
+  if (simt) JQ_LAUNCH(k_gemm_tn, dim3(jq_cdiv(Kd, 64), jq_cdiv(Nd, 64), S), dim3(256), 0, st, X, ldx, Z, ldz, R, Kd, Nd, S, part);
+  else JQ_LAUNCH(k_gemm_tn_mma, dim3(jq_cdiv(Kd, 64), jq_cdiv(Nd, 64), S), dim3(256), 0, st, X, ldx, Z, ldz, R, Kd, Nd, S, part);
 #endif
   JQ_CHECK_LAUNCH();
   // reduce into out (possibly strided rows): ldo == Nd for every caller but the layer-1 kernel, which is contiguous too
   JQ_REQUIRE(ldo == Nd, JQ_ERR_INVALID_ARGUMENT, "gemm_tn: strided output is not supported");
-  JQ_LAUNCH(k_reduce_partials, dim3(grid_for((long long)Kd * Nd)), dim3(256), 0, st, part, S, (long long)Kd * Nd,
-            (long long)Kd * Nd, out);
-  JQ_CHECK_LAUNCH();
-  return JQ_OK;
+  return launch_reduce_partials(part, S, (long long)Kd * Nd, (long long)Kd * Nd, out, st);
 }
 
 // column sums: out[f] = sum_r Z[r][f]  == gemm_tn with X = ones; done as a two-stage reduction
@@ -416,9 +646,7 @@ int launch_colsum(const float* Z, long long R, int F, float* part, long long par
   if (S < 1) S = 1;
   JQ_LAUNCH(k_colsum_partial, dim3(grid_for(S * F)), dim3(256), 0, st, Z, R, F, (int)S, part);
   JQ_CHECK_LAUNCH();
-  JQ_LAUNCH(k_reduce_partials, dim3(grid_for(F)), dim3(64), 0, st, part, (int)S, (long long)F, (long long)F, out);
-  JQ_CHECK_LAUNCH();
-  return JQ_OK;
+  return launch_reduce_partials(part, (int)S, (long long)F, (long long)F, out, st);
 }
 
 // value-only dense through the forward launcher: out[G][N] = act(x [G][k0] W[k0][N] (+ x2 W2) + bias + cadd) (+ residual)
@@ -618,7 +846,11 @@ extern "C" int jaqmc_b200_ferminet_logpsi_vjp(const jaqmc_ferminet_config* c, co
     JQ_CHECK_LAUNCH();
     Mv = b.M;
   }
+#ifndef JAQMC_HOST_EMU
+  JQ_LAUNCH(k_minv_small, dim3((unsigned)jq_cdiv(W * d.D, 16)), dim3(256), 0, st, Mv, W * d.D, n, d.D, b.minv, b.dsign, b.dlogabs);
+#else
   JQ_LAUNCH(k_minv, dim3(grid_for(W * d.D)), dim3(64), 0, st, Mv, W * d.D, n, d.D, b.minv, b.dsign, b.dlogabs);
+#endif
   JQ_CHECK_LAUNCH();
   JQ_LAUNCH(k_det_weights, dim3(grid_for(W)), dim3(128), 0, st, b.dsign, b.dlogabs, cotangent, W, d.D, b.wdet, logpsi, sign);
   JQ_CHECK_LAUNCH();
@@ -638,10 +870,8 @@ extern "C" int jaqmc_b200_ferminet_logpsi_vjp(const jaqmc_ferminet_config* c, co
     for (int s = 0; s < nchan; ++s) {
       const long long Ps = (long long)n * d.A * d.D;
       // partials are laid out [chunk][channel][o][I][d]: reduce one channel at a time with stride P
-      JQ_LAUNCH(k_reduce_partials, dim3(grid_for(Ps)), dim3(256), 0, st, part_pi + s * Ps, chunks, P, Ps, grads->env_pi[s]);
-      JQ_CHECK_LAUNCH();
-      JQ_LAUNCH(k_reduce_partials, dim3(grid_for(Ps)), dim3(256), 0, st, part_sg + s * Ps, chunks, P, Ps, grads->env_sigma[s]);
-      JQ_CHECK_LAUNCH();
+      if ((rc = launch_reduce_partials(part_pi + s * Ps, chunks, P, Ps, grads->env_pi[s], st))) return rc;
+      if ((rc = launch_reduce_partials(part_sg + s * Ps, chunks, P, Ps, grads->env_sigma[s], st))) return rc;
     }
   }
   // orbital kernels: dK_s = h_L(rows of channel s)^T dorb(rows of channel s); dh_L = dorb K_s^T

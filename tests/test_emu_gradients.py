@@ -51,10 +51,13 @@ def check_vjp(rt, mol, ndets, hs, hd, W, device="cpu", envelope="abs_isotropic",
     got = ON.tree_leaves(grads)
     names = [k for k, _ in sorted(_flat(p64["params"]).items())]
     assert len(got) == len(want) == len(names)
+    worst = (0.0, "")
     for nm, g_, w_ in zip(names, got, want):
         scale = float(w_.abs().max()) + 1e-12
         err = float((g_.cpu().double() - w_).abs().max()) / scale
+        worst = max(worst, (err, nm))
         assert err < tol, (nm, err, scale)
+    print("vjp %s %s: largest leaf error %.2e (%s), tolerance %.0e" % (mol, tuple(hs), worst[0], worst[1], tol))
     return grads
 
 
