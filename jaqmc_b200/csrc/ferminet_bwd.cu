@@ -860,7 +860,7 @@ extern "C" int jaqmc_b200_ferminet_logpsi_vjp(const jaqmc_ferminet_config* c, co
             d.D, b.dorb, has_env ? b.denv : nullptr);
   JQ_CHECK_LAUNCH();
   if (has_env) {
-    const int chunks = 64;
+    const int chunks = W >= 256 ? 256 : (W >= 64 ? 64 : (int)W);   // walker chunks: ~230 k items at N2 (r2: 64 chunks left the kernel at 224 blocks, 0.53 ms)
     const long long P = (long long)nchan * n * d.A * d.D;
     float* part_pi = b.part;
     float* part_sg = b.part + (long long)chunks * P;
