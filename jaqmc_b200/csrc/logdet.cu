@@ -664,7 +664,8 @@ __global__ void __launch_bounds__(256, 3) k_logdet(const float* __restrict__ orb
   float* trL = sgn + DB;
   float* t2 = trL + DB;
   float* Jc = sm + (((t2 + DB) - sm + 3) & ~3);  // 16-byte aligned (float4 reads of the padded inverses)
-  float* Mc = Jc + (size_t)KC * DB * nn;
+  const int NP4 = (n + 3) & ~3;        // row stride of the slab / transposed-inverse tiles: float4 reads (r2)
+  float* Mc = Jc + (size_t)KC * DB * n * NP4;
   float* p1 = Mc + (size_t)KC * DB * nn;
   float* p2 = p1 + KC * DB * n;
   const int ngrp = (D + DB - 1) / DB;
@@ -879,46 +880,66 @@ __global__ void __launch_bounds__(256, 3) k_logdet(const float* __restrict__ orb
   }
   // traces, KC derivative slabs at a time.  slab kk <-> component c = 1 + k0 + kk (k0 + kk == K is the Laplacian row)
   const int nb = (n + 3) / 4, tiles = nb * nb;
-  float* invT = p2 + KC * DB * n;   // [DB][nn]: invT[d][j][i] = inv[d][i][j]
+  float* invT = sm + (((p2 + KC * DB * n) - sm + 3) & ~3);   // [DB][n][NP4]: invT[d][j][i] = inv[d][i][j], 16-byte aligned
   for (int q = tid; q < db * nn; q += nt) {
     int d, rem, i, j;
     jq_divmod(q, nn, inv_nn, &d, &rem);
     jq_divmod(rem, n, inv_n, &i, &j);
-    invT[d * nn + j * n + i] = inv[q];
+    invT[(d * n + j) * NP4 + i] = inv[q];
   }
   __syncthreads();
   for (int k0 = 0; k0 < KT; k0 += KC) {
     const int kc = (KT - k0 < KC) ? KT - k0 : KC;
+    // Slab staging.  r2 profile (benzene): 40 % of the kernel's stall samples sat on the shared store of the plain
+    // load -> store loop, each element paying the global latency on its own (0.3 TB/s).  Device build: a warp takes
+    // (slab, row j) pairs -- db * n contiguous floats each -- and issues 4-byte cp.async copies, all of a thread's
+    // elements in flight together; one wait per batch.
+#ifndef JAQMC_HOST_EMU
+    {
+      const int warp_ = tid >> 5, lane_ = tid & 31, nw_ = nt >> 5;
+      const unsigned jc0 = (unsigned)__cvta_generic_to_shared(Jc);
+      for (int pr = warp_; pr < kc * n; pr += nw_) {
+        const int kk = pr / n, j = pr - kk * n;
+        const float* src = ow + ((long long)j * C + (1 + k0 + kk)) * DN;
+        for (int r = lane_; r < db * n; r += 32) {
+          const int d = r / n, i = r - d * n;
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(jc0 + 4u * (unsigned)(((kk * DB + d) * n + j) * NP4 + i)),
+                       "l"(src + r));
+        }
+      }
+      asm volatile("cp.async.commit_group;");
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+#else
     for (int q = tid; q < kc * n * db * n; q += nt) {
       int t, r, kk, j, d, i;
       jq_divmod(q, db * n, inv_dbn, &t, &r);
       jq_divmod(t, n, inv_n, &kk, &j);
       jq_divmod(r, n, inv_n, &d, &i);
-      Jc[(kk * DB + d) * nn + j * n + i] = ow[((long long)j * C + (1 + k0 + kk)) * DN + r];
+      Jc[((kk * DB + d) * n + j) * NP4 + i] = ow[((long long)j * C + (1 + k0 + kk)) * DN + r];
     }
+#endif
     __syncthreads();
-    // M = inv . J in 4 x 4 register tiles (r2): per contraction index j a tile reads 4 entries of the j-major
-    // (transposed) inverse and 4 of the slab -- 8 shared-memory words per 16 multiply-adds, against 3 words per 2 for
-    // the 1 x 2 tiles this replaces (the kernel is bound by the shared-memory pipe)
+    // M = inv . J in 4 x 4 register tiles: per contraction index j a tile reads one float4 of the j-major (transposed)
+    // inverse and one of the slab -- rows padded to a multiple of 4 so that both are single 16-byte shared loads (r2:
+    // eight scalar loads per 16 multiply-adds before; the kernel is bound by the shared-memory pipe).  The padding
+    // columns are never initialised: they only reach accumulators that are not stored.
     for (int q = tid; q < kc * db * tiles; q += nt) {
       const int t = q % tiles, dk = q / tiles;
       const int d = dk % db, kk = dk / db;
       const int i0 = 4 * (t / nb), c0 = 4 * (t % nb);
-      const float* tp = invT + d * nn + i0;
-      const float* jb = Jc + (kk * DB + d) * nn + c0;
+      const float* tp = invT + (size_t)d * n * NP4 + i0;
+      const float* jb = Jc + (size_t)(kk * DB + d) * n * NP4 + c0;
       float acc[4][4];
 #pragma unroll
       for (int a = 0; a < 4; ++a)
 #pragma unroll
         for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
-      const bool full = (i0 + 4 <= n) && (c0 + 4 <= n);
+#pragma unroll 2
       for (int j = 0; j < n; ++j) {
-        float xv[4], yv[4];
-#pragma unroll
-        for (int a = 0; a < 4; ++a) {
-          xv[a] = (full || i0 + a < n) ? tp[j * n + a] : 0.f;
-          yv[a] = (full || c0 + a < n) ? jb[j * n + a] : 0.f;
-        }
+        const float4 x4 = *reinterpret_cast<const float4*>(tp + j * NP4);
+        const float4 y4 = *reinterpret_cast<const float4*>(jb + j * NP4);
+        const float xv[4] = {x4.x, x4.y, x4.z, x4.w}, yv[4] = {y4.x, y4.y, y4.z, y4.w};
 #pragma unroll
         for (int a = 0; a < 4; ++a)
 #pragma unroll
@@ -1187,8 +1208,10 @@ int jq_launch_logdet(const float* orb, int W, int n, int D, int track, float* de
     if (track && kc == 0)  // small path: inv | colp piv scalars | padded inverses | one product slab | p1 p2
       return (size_t)8 * db + sizeof(float) * ((size_t)db * nn + 2 * (size_t)db * n + 4 * (size_t)db +
                                               (size_t)db * (n * LD_NP + 4) + (size_t)db * (nn + 32) + 2 * (size_t)db * n) + 32;
+    const size_t np4 = (size_t)((n + 3) & ~3);   // padded rows of the slab and transposed-inverse tiles
     return (size_t)8 * db + sizeof(float) * ((size_t)db * nn + 2 * (size_t)db * n + 4 * (size_t)db +
-                                            (track ? (size_t)kc * db * nn * 2 + (size_t)kc * db * n * 2 + (size_t)db * nn : 0)) + 32;
+                                            (track ? (size_t)kc * db * (n * np4 + nn) + (size_t)kc * db * n * 2 +
+                                                         (size_t)db * n * np4 + 8 : 0)) + 32;
   };
   if (track && n <= LD_NP) {
     // small-matrix path: all determinants of a walker in one block when they fit; the slab area [2*KC][DB][nn] must
