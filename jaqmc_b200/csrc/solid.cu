@@ -106,7 +106,8 @@ __global__ void k_solid_orb_factor(float* __restrict__ orb_r, float* __restrict_
 //                  p1r p1i p2r p2i [DB][max(n, tiles)]
 // ------------------------------------------------------------------------------------------------
 __global__ void k_logdet_c(const float* __restrict__ orb_r, const float* __restrict__ orb_i, int n, int D, int C, int DB,
-                           float* __restrict__ det_ld, float* __restrict__ det_grad, float* __restrict__ det_lap) {
+                           float* __restrict__ det_ld, float* __restrict__ det_grad, float* __restrict__ det_lap,
+                           int plain_staging) {
   JQ_DYN_SMEM(float, sm);
   const int nn = n * n;
   const int K = C - 2;
@@ -280,6 +281,23 @@ __global__ void k_logdet_c(const float* __restrict__ orb_r, const float* __restr
   }
   __syncthreads();
   for (int kk = 0; kk < KT; ++kk) {
+    // slab staging: 4-byte cp.async on the device (all of a thread's elements in flight together; the plain
+    // load -> store loop paid the global latency per element: 40 % of the real-valued kernel's stall samples, r2)
+#ifndef JAQMC_HOST_EMU
+    if (!plain_staging) {
+      const unsigned jr0 = (unsigned)__cvta_generic_to_shared(J_r), ji0 = (unsigned)__cvta_generic_to_shared(J_i);
+      for (int q = tid; q < n * db * n; q += nt) {
+        const int j = q / (db * n), r = q % (db * n);
+        const int d = r / n, i = r % n;
+        const long long src = base + ((long long)j * C + (1 + kk)) * DN + r;
+        const unsigned off = 4u * (unsigned)(d * nn + j * n + i);
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(jr0 + off), "l"(orb_r + src));
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(ji0 + off), "l"(orb_i + src));
+      }
+      asm volatile("cp.async.commit_group;");
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    } else
+#endif
     for (int q = tid; q < n * db * n; q += nt) {
       const int j = q / (db * n), r = q % (db * n);
       const int d = r / n, i = r % n;
@@ -573,8 +591,9 @@ int jq_solid_forward(const jaqmc_solid_config* c, const jaqmc_solid_params* p, c
     jq_prof_work((double)W * d.D * 8.0 * n * n * n * (track ? 2 * (d.C - 1) + 1 : 0.34), 8.0 * (double)W * d.D * d.C * n * n);
     const int tiles_blk = DB * ((n + 3) / 4) * ((n + 3) / 4);
     const int nthr = (track && tiles_blk <= 128) ? 128 : 256;
+    static const int plain_staging = getenv("JAQMC_B200_LOGDET_PLAIN_STAGING") != nullptr;   // A/B switch
     JQ_LAUNCH(k_logdet_c, dim3((unsigned)blocks), dim3(nthr), smem, st, b.orb_r, b.orb_i, n, d.D, d.C, DB, b.det_ld,
-              b.det_grad, b.det_lap);
+              b.det_grad, b.det_lap, plain_staging);
     JQ_CHECK_LAUNCH();
   }
   JQ_LAUNCH(k_logdet_combine_c, dim3(jq_cdiv(W, 64)), dim3(64), 0, st, b.det_ld, b.det_grad, b.det_lap, (int)W, n, d.D,
