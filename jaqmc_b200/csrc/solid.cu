@@ -102,7 +102,7 @@ __global__ void k_solid_orb_factor(float* __restrict__ orb_r, float* __restrict_
 // real kernel (logdet.cu) in complex arithmetic: Gauss-Jordan with partial pivoting on |z|,
 //   log det = sum log|p| + i (sum arg p + pi * swaps),  M = A^-1 dA_c,  ld_J[c] = tr M,  ld_L = tr(A^-1 A_L) - sum_k tr(M_k^2).
 // Shared (floats): logabs[DB] arg[DB] (double) | inv_r inv_i [DB][nn] | colp_r colp_i [DB][n] | piv[DB][n] |
-//                  pv_r pv_i [DB] | trL_r trL_i t2_r t2_i [DB] | J_r J_i M_r M_i invT_r invT_i [DB][nn] |
+//                  (J_r J_i invT_r invT_i [DB][n][NP4] first, r2) pv_r pv_i [DB] | trL_r trL_i t2_r t2_i [DB] | M_r M_i [DB][nn] |
 //                  p1r p1i p2r p2i [DB][max(n, tiles)]
 // ------------------------------------------------------------------------------------------------
 __global__ void k_logdet_c(const float* __restrict__ orb_r, const float* __restrict__ orb_i, int n, int D, int C, int DB,
@@ -114,7 +114,13 @@ __global__ void k_logdet_c(const float* __restrict__ orb_r, const float* __restr
   const int KT = (C > 1) ? C - 1 : 0;
   double* logabs = reinterpret_cast<double*>(sm);
   double* argsum = logabs + DB;
-  float* inv_r = reinterpret_cast<float*>(argsum + DB);
+  // the four arrays read as float4 come first (16-byte aligned: 16 DB bytes of doubles before them), rows padded to NP4
+  const int NP4 = (n + 3) & ~3;
+  float* J_r = reinterpret_cast<float*>(argsum + DB);
+  float* J_i = J_r + (size_t)DB * n * NP4;
+  float* invT_r = J_i + (size_t)DB * n * NP4;
+  float* invT_i = invT_r + (size_t)DB * n * NP4;
+  float* inv_r = invT_i + (size_t)DB * n * NP4;
   float* inv_i = inv_r + (size_t)DB * nn;
   float* colp_r = inv_i + (size_t)DB * nn;
   float* colp_i = colp_r + DB * n;
@@ -125,14 +131,10 @@ __global__ void k_logdet_c(const float* __restrict__ orb_r, const float* __restr
   float* trL_i = trL_r + DB;
   float* t2_r = trL_i + DB;
   float* t2_i = t2_r + DB;
-  float* J_r = t2_i + DB;
-  float* J_i = J_r + (size_t)DB * nn;
-  float* M_r = J_i + (size_t)DB * nn;
+  float* M_r = t2_i + DB;
   float* M_i = M_r + (size_t)DB * nn;
-  float* invT_r = M_i + (size_t)DB * nn;
-  float* invT_i = invT_r + (size_t)DB * nn;
   const int np_ = ((n + 3) / 4) * ((n + 3) / 4) > n ? ((n + 3) / 4) * ((n + 3) / 4) : n;   // per-tile partials
-  float* p1r = invT_i + (size_t)DB * nn;
+  float* p1r = M_i + (size_t)DB * nn;
   float* p1i = p1r + DB * np_;
   float* p2r = p1i + DB * np_;
   float* p2i = p2r + DB * np_;
@@ -276,8 +278,8 @@ __global__ void k_logdet_c(const float* __restrict__ orb_r, const float* __restr
   for (int q = tid; q < db * nn; q += nt) {
     const int d = q / nn, rem = q % nn;
     const int i = rem / n, j = rem % n;
-    invT_r[d * nn + j * n + i] = inv_r[q];
-    invT_i[d * nn + j * n + i] = inv_i[q];
+    invT_r[(d * n + j) * NP4 + i] = inv_r[q];
+    invT_i[(d * n + j) * NP4 + i] = inv_i[q];
   }
   __syncthreads();
   for (int kk = 0; kk < KT; ++kk) {
@@ -290,7 +292,7 @@ __global__ void k_logdet_c(const float* __restrict__ orb_r, const float* __restr
         const int j = q / (db * n), r = q % (db * n);
         const int d = r / n, i = r % n;
         const long long src = base + ((long long)j * C + (1 + kk)) * DN + r;
-        const unsigned off = 4u * (unsigned)(d * nn + j * n + i);
+        const unsigned off = 4u * (unsigned)((d * n + j) * NP4 + i);
         asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(jr0 + off), "l"(orb_r + src));
         asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(ji0 + off), "l"(orb_i + src));
       }
@@ -302,33 +304,30 @@ __global__ void k_logdet_c(const float* __restrict__ orb_r, const float* __restr
       const int j = q / (db * n), r = q % (db * n);
       const int d = r / n, i = r % n;
       const long long src = base + ((long long)j * C + (1 + kk)) * DN + r;
-      J_r[d * nn + j * n + i] = orb_r[src];
-      J_i[d * nn + j * n + i] = orb_i[src];
+      J_r[(d * n + j) * NP4 + i] = orb_r[src];
+      J_i[(d * n + j) * NP4 + i] = orb_i[src];
     }
     __syncthreads();
     for (int q = tid; q < db * tiles; q += nt) {
       const int d = q / tiles, t = q % tiles;
       const int i0 = 4 * (t / nb), c0 = 4 * (t % nb);
-      const float* tr = invT_r + d * nn + i0;
-      const float* ti = invT_i + d * nn + i0;
-      const float* jr = J_r + d * nn + c0;
-      const float* ji = J_i + d * nn + c0;
+      const float* tr = invT_r + (size_t)d * n * NP4 + i0;
+      const float* ti = invT_i + (size_t)d * n * NP4 + i0;
+      const float* jr = J_r + (size_t)d * n * NP4 + c0;
+      const float* ji = J_i + (size_t)d * n * NP4 + c0;
       float ar[4][4], ai[4][4];
 #pragma unroll
       for (int a = 0; a < 4; ++a)
 #pragma unroll
         for (int b = 0; b < 4; ++b) ar[a][b] = ai[a][b] = 0.f;
-      const bool full = (i0 + 4 <= n) && (c0 + 4 <= n);
+      // one float4 per operand and contraction index (rows padded to a multiple of 4; the padding columns only reach
+      // accumulators that are not stored): 4 shared loads per 64 FMAs instead of 16 predicated scalar ones
+#pragma unroll 2
       for (int j = 0; j < n; ++j) {
-        float xr[4], xi[4], yr[4], yi[4];
-#pragma unroll
-        for (int a = 0; a < 4; ++a) {
-          const bool oa = full || i0 + a < n, ob = full || c0 + a < n;
-          xr[a] = oa ? tr[j * n + a] : 0.f;
-          xi[a] = oa ? ti[j * n + a] : 0.f;
-          yr[a] = ob ? jr[j * n + a] : 0.f;
-          yi[a] = ob ? ji[j * n + a] : 0.f;
-        }
+        const float4 xr4 = *reinterpret_cast<const float4*>(tr + j * NP4), xi4 = *reinterpret_cast<const float4*>(ti + j * NP4);
+        const float4 yr4 = *reinterpret_cast<const float4*>(jr + j * NP4), yi4 = *reinterpret_cast<const float4*>(ji + j * NP4);
+        const float xr[4] = {xr4.x, xr4.y, xr4.z, xr4.w}, xi[4] = {xi4.x, xi4.y, xi4.z, xi4.w};
+        const float yr[4] = {yr4.x, yr4.y, yr4.z, yr4.w}, yi[4] = {yi4.x, yi4.y, yi4.z, yi4.w};
 #pragma unroll
         for (int a = 0; a < 4; ++a)
 #pragma unroll
@@ -494,7 +493,8 @@ size_t logdet_c_smem(int db, int n) {
   const size_t nn = (size_t)n * n;
   const size_t nb = (size_t)(n + 3) / 4;
   const size_t np = nb * nb > (size_t)n ? nb * nb : (size_t)n;
-  return 16 * (size_t)db + sizeof(float) * (8 * db * nn + 3 * (size_t)db * n + 4 * (size_t)db * np + 6 * (size_t)db) + 32;
+  const size_t np4 = (size_t)((n + 3) & ~3);
+  return 16 * (size_t)db + sizeof(float) * (4 * db * nn + 4 * (size_t)db * n * np4 + 3 * (size_t)db * n + 4 * (size_t)db * np + 6 * (size_t)db) + 32;
 }
 }  // namespace
 
