@@ -935,34 +935,12 @@ __global__ void __launch_bounds__(256, 3) k_logdet(const float* __restrict__ orb
       for (int a = 0; a < 4; ++a)
 #pragma unroll
         for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
-      // four contraction steps per trip with all eight loads issued first (r2 profile after the staging fix: the first
-      // FMA after the loads carried the largest share of the stall samples, 16 warps per SM do not hide the LDS latency)
-      const float4* tp4 = reinterpret_cast<const float4*>(tp);
-      const float4* jb4 = reinterpret_cast<const float4*>(jb);
-      const int st4 = NP4 >> 2;
-      int j = 0;
-      for (; j + 4 <= n; j += 4) {
-        float4 x4[4], y4[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          x4[u] = tp4[u * st4];
-          y4[u] = jb4[u * st4];
-        }
-        tp4 += 4 * st4;
-        jb4 += 4 * st4;
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const float xv[4] = {x4[u].x, x4[u].y, x4[u].z, x4[u].w}, yv[4] = {y4[u].x, y4[u].y, y4[u].z, y4[u].w};
-#pragma unroll
-          for (int a = 0; a < 4; ++a)
-#pragma unroll
-            for (int b = 0; b < 4; ++b) acc[a][b] = fmaf(xv[a], yv[b], acc[a][b]);
-        }
-      }
-      for (; j < n; ++j) {
-        const float4 x4 = *tp4, y4 = *jb4;
-        tp4 += st4;
-        jb4 += st4;
+      // (r2: four contraction steps per trip with all eight loads hoisted was tried after the profile showed the first
+      // FMA behind the loads as the top stall site: 15.3 -> 15.7 ms, i.e. slower; reverted)
+#pragma unroll 2
+      for (int j = 0; j < n; ++j) {
+        const float4 x4 = *reinterpret_cast<const float4*>(tp + j * NP4);
+        const float4 y4 = *reinterpret_cast<const float4*>(jb + j * NP4);
         const float xv[4] = {x4.x, x4.y, x4.z, x4.w}, yv[4] = {y4.x, y4.y, y4.z, y4.w};
 #pragma unroll
         for (int a = 0; a < 4; ++a)
