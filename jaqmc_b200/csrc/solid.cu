@@ -80,7 +80,29 @@ __global__ void k_solid_orb_factor(float* __restrict__ orb_r, float* __restrict_
       const float olr = pr[(long long)(C - 1) * DN], oli = pq[(long long)(C - 1) * DN];
       pr[(long long)(C - 1) * DN] = olr * fr - oli * fi + o0r * lr - o0i * li + 2.f * cr;
       pq[(long long)(C - 1) * DN] = olr * fi + oli * fr + o0r * li + o0i * lr + 2.f * ci;
-      for (int c = 1; c < C - 1; ++c) {
+      // Jacobian rows in batches of four: the eight loads of a batch are issued before any of its stores (r2 profile:
+      // 74 % of the stall samples waited on one load pair at a time; the kernel streamed at 3.8 TB/s)
+      int c = 1;
+      for (; c + 4 <= C - 1; c += 4) {
+        float ur[4], ui[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          ur[u] = pr[(long long)(c + u) * DN];
+          ui[u] = pq[(long long)(c + u) * DN];
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          float vr = ur[u] * fr - ui[u] * fi, vi = ur[u] * fi + ui[u] * fr;
+          const int k = c + u - 1;
+          if (k / 3 == j) {
+            vr += o0r * gr[k % 3] - o0i * gi[k % 3];
+            vi += o0r * gi[k % 3] + o0i * gr[k % 3];
+          }
+          pr[(long long)(c + u) * DN] = vr;
+          pq[(long long)(c + u) * DN] = vi;
+        }
+      }
+      for (; c < C - 1; ++c) {
         const float ur = pr[(long long)c * DN], ui = pq[(long long)c * DN];
         float vr = ur * fr - ui * fi, vi = ur * fi + ui * fr;
         const int k = c - 1;
