@@ -79,7 +79,7 @@ size_t ConfigWords(int kind) {
     case JAQMC_WF_FERMINET: return sizeof(jaqmc_ferminet_config) / 4;
     case JAQMC_WF_LAPNET: return sizeof(jaqmc_lapnet_config) / 4;
     case JAQMC_WF_PSIFORMER: return sizeof(jaqmc_psiformer_config) / 4;
-    case JAQMC_WF_SOLID_FERMINET: return sizeof(jaqmc_ferminet_config) / 4;   // + 18 floats in fconfig
+    case JAQMC_WF_SOLID_FERMINET: return sizeof(jaqmc_ferminet_config) / 4 + 2;   // + distance_type, sym_type; 18 floats in fconfig
     case JAQMC_WF_HYDROGEN: return sizeof(jaqmc_hydrogen_config) / 4;
     default: return 0;
   }
@@ -93,7 +93,7 @@ ffi::Error Assemble(int32_t kind, ffi::Span<const int32_t> config, ffi::Span<con
   if (config.size() != words)
     return Invalid("jaqmc_b200: attribute `config` has " + std::to_string(config.size()) + " words, the kind needs " +
                    std::to_string(words));
-  std::memcpy(&d->config, config.begin(), words * 4);
+  std::memcpy(&d->config, config.begin(), (kind == JAQMC_WF_SOLID_FERMINET ? words - 2 : words) * 4);
   const float* present = reinterpret_cast<const float*>(1);   // "this optional leaf exists" marker (see header)
   switch (kind) {
     case JAQMC_WF_FERMINET:
@@ -103,6 +103,8 @@ ffi::Error Assemble(int32_t kind, ffi::Span<const int32_t> config, ffi::Span<con
       if (fconfig.size() != 18) return Invalid("jaqmc_b200: attribute `fconfig` must hold the two 3x3 lattices");
       std::memcpy(d->config.solid.simulation_lattice, fconfig.begin(), 9 * 4);
       std::memcpy(d->config.solid.primitive_lattice, fconfig.begin() + 9, 9 * 4);
+      d->config.solid.distance_type = config.begin()[words - 2];
+      d->config.solid.sym_type = config.begin()[words - 1];
       d->n_electrons = d->config.solid.net.n_up + d->config.solid.net.n_dn;
       break;
     case JAQMC_WF_LAPNET:

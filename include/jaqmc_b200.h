@@ -195,6 +195,8 @@ typedef struct {
   jaqmc_ferminet_config net;      /* n_atoms = atoms of the PRIMITIVE cell (SolidData.primitive_atoms) */
   float simulation_lattice[9];    /* rows are lattice vectors (host values) */
   float primitive_lattice[9];
+  int32_t distance_type;          /* JAQMC_DISTANCE_* (geometry/pbc.py DistanceType): tri -> 7, nu -> 4 features per pair */
+  int32_t sym_type;               /* JAQMC_SYMMETRY_* (geometry/pbc.py:347-381 get_symmetry_lat) */
 } jaqmc_solid_config;
 
 typedef struct {
@@ -203,6 +205,13 @@ typedef struct {
   const float* imag_orbital_kernel[2];   /* imag_orbital_layer/.../kernel */
   const float* klist;                    /* (n, 3) k-point of every orbital (module attribute `klist`) */
 } jaqmc_solid_params;
+
+#define JAQMC_DISTANCE_TRI 0
+#define JAQMC_DISTANCE_NU 1
+#define JAQMC_SYMMETRY_MINIMAL 0
+#define JAQMC_SYMMETRY_FCC 1
+#define JAQMC_SYMMETRY_BCC 2
+#define JAQMC_SYMMETRY_HEXAGONAL 3
 
 /* ---- HydrogenAtom demo wavefunction (app/hydrogen_atom.py:28-35): log psi = alpha * |electrons| ------------------ */
 typedef struct {

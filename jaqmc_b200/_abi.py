@@ -150,8 +150,13 @@ class PsiformerParams(C.Structure):
     ]
 
 
+DISTANCE = {"tri": 0, "nu": 1}                                   # geometry/pbc.py DistanceType
+SYMMETRY = {"minimal": 0, "fcc": 1, "bcc": 2, "hexagonal": 3}     # geometry/pbc.py SymmetryType
+
+
 class SolidConfig(C.Structure):
-    _fields_ = [("net", FerminetConfig), ("simulation_lattice", C.c_float * 9), ("primitive_lattice", C.c_float * 9)]
+    _fields_ = [("net", FerminetConfig), ("simulation_lattice", C.c_float * 9), ("primitive_lattice", C.c_float * 9),
+                ("distance_type", C.c_int32), ("sym_type", C.c_int32)]
 
 
 class SolidParams(C.Structure):

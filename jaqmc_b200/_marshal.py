@@ -274,8 +274,9 @@ def psiformer_handle(params, nspins, n_atoms, ndets=16, num_layers=4, num_heads=
 
 def solid_handle(params, nspins, n_prim_atoms, simulation_lattice, primitive_lattice, klist, ndets=16,
                  hidden_dims_single=(256,) * 4, hidden_dims_double=(32,) * 4, envelope="abs_isotropic",
-                 orbitals_spin_split=True) -> Handle:
-    """Descriptor for ``SolidWavefunction`` (reference app/solid/wavefunction.py:40-147); ``klist`` (n, 3) on device."""
+                 orbitals_spin_split=True, distance_type="tri", sym_type="minimal") -> Handle:
+    """Descriptor for ``SolidWavefunction`` (reference app/solid/wavefunction.py:40-147); ``klist`` (n, 3) on device.
+    ``distance_type`` 'tri' | 'nu' and ``sym_type`` 'minimal' | 'fcc' | 'bcc' | 'hexagonal' as in geometry/pbc.py."""
     n_up, n_dn = int(nspins[0]), int(nspins[1])
     n = n_up + n_dn
     L = len(hidden_dims_single)
@@ -294,6 +295,10 @@ def solid_handle(params, nspins, n_prim_atoms, simulation_lattice, primitive_lat
         net.hidden_double[i] = int(hidden_dims_double[i])
     net.envelope_type = _abi.ENVELOPE[envelope]
     net.orbitals_spin_split = int(split)
+    if str(distance_type) not in _abi.DISTANCE or str(sym_type) not in _abi.SYMMETRY:
+        raise ValueError(f"Unknown distance_type / sym_type: {distance_type!r} / {sym_type!r}")
+    cfg.distance_type, cfg.sym_type = _abi.DISTANCE[str(distance_type)], _abi.SYMMETRY[str(sym_type)]
+    fw = 4 if str(distance_type) == "nu" else 7   # features per electron-atom / electron-electron pair
     for name, lat in (("simulation_lattice", simulation_lattice), ("primitive_lattice", primitive_lattice)):
         vals = [float(v) for v in torch.as_tensor(lat).reshape(-1).tolist()]
         if len(vals) != 9:
@@ -303,7 +308,7 @@ def solid_handle(params, nspins, n_prim_atoms, simulation_lattice, primitive_lat
     ps = _abi.SolidParams()
     b = _Binder()
     bb = p["backbone_layer"]
-    d1, d2 = 7 * n_prim_atoms, 7
+    d1, d2 = fw * n_prim_atoms, fw
     idx = 0
     for layer in range(L):
         h1 = int(hidden_dims_single[layer])

@@ -122,7 +122,8 @@ int build(int kind, const void* config, void* params, LeafList& L) {
       auto* c = (const jaqmc_solid_config*)config;
       auto* p = (jaqmc_solid_params*)params;
       JQ_REQUIRE(c->net.n_layers >= 1 && c->net.n_layers <= JQ_MAX_LAYERS, JQ_ERR_INVALID_ARGUMENT, "leaves: n_layers");
-      fermi_backbone_leaves(L, &c->net, &p->net, 7, 7);
+      fermi_backbone_leaves(L, &c->net, &p->net, c->distance_type == JAQMC_DISTANCE_NU ? 4 : 7,
+                            c->distance_type == JAQMC_DISTANCE_NU ? 4 : 7);
       const int hid = fermi_orbital_width(&c->net);
       head_leaves(L, "real_orbital_layer", p->real_orbital_kernel, nullptr, false, p->net.env_pi, p->net.env_sigma, nullptr,
                   nullptr, c->net.n_up, c->net.n_dn, c->net.n_atoms, c->net.ndets, hid, c->net.orbitals_spin_split,

@@ -508,7 +508,8 @@ void solid_carve(const FermiDims& d, long long W, JqArena& ar, SolidBufs* b) {
 }
 
 int solid_dims(const jaqmc_solid_config* c, int track, FermiDims* d) {
-  return jq_fermi_dims(&c->net, track, 7, 7, d);
+  const int fw = c->distance_type == JAQMC_DISTANCE_NU ? 4 : 7;   // features per electron-atom / electron-electron pair
+  return jq_fermi_dims(&c->net, track, fw, fw, d);
 }
 
 size_t logdet_c_smem(int db, int n) {
@@ -553,7 +554,8 @@ int jq_solid_forward(const jaqmc_solid_config* c, const jaqmc_solid_params* p, c
   solid_carve(d, W, ar, &b);
   JQ_REQUIRE(ar.ok(), JQ_ERR_WORKSPACE_TOO_SMALL, "solid: workspace %zu < %zu bytes", ws_bytes, ar.off);
   const int n = d.n;
-  if ((rc = jq_launch_solid_features(electrons, sys->atoms, c->simulation_lattice, c->primitive_lattice, (int)W, n, d.A,
+  if ((rc = jq_launch_solid_features(electrons, sys->atoms, c->simulation_lattice, c->primitive_lattice, c->distance_type,
+                                     c->sym_type, (int)W, n, d.A,
                                      track, b.f.ae, b.r_ae, b.f.h2a, st)))
     return rc;
   float* h = nullptr;

@@ -70,8 +70,8 @@ void jq_fermi_carve_backbone(const FermiDims& d, long long W, JqArena& ar, Fermi
 int jq_fermi_backbone(const FermiDims& d, const jaqmc_ferminet_params* p, long long W, int track, const FermiBufs& b,
                       cudaStream_t st, float** h_out);
 int jq_launch_solid_features(const float* electrons, const float* prim_atoms, const float* sim_lattice,
-                             const float* prim_lattice, int W, int n, int A, int track, float* ae, float* r_ae, float* ee,
-                             cudaStream_t st);
+                             const float* prim_lattice, int distance_type, int sym_type, int W, int n, int A, int track,
+                             float* ae, float* r_ae, float* ee, cudaStream_t st);
 
 // ---- periodic FermiNet (solid.cu) ------------------------------------------------------------------
 struct JqWfOutC {

@@ -390,8 +390,8 @@ class SolidWavefunction:
     full_det: bool = True
 
     def __post_init__(self):
-        if self.distance_type != "tri" or self.sym_type != "minimal":
-            raise NotImplementedError("only distance_type='tri' with sym_type='minimal' is implemented by the CUDA pipeline")
+        if self.distance_type not in ("tri", "nu") or self.sym_type not in ("minimal", "fcc", "bcc", "hexagonal"):
+            raise ValueError(f"unknown distance_type / sym_type: {self.distance_type!r} / {self.sym_type!r}")
         if len(self.hidden_dims_single) != len(self.hidden_dims_double):
             raise ValueError("hidden_dims_single and hidden_dims_double must have the same length")
         if self.simulation_lattice is None or self.primitive_lattice is None or self.klist is None:
@@ -406,7 +406,8 @@ class SolidWavefunction:
         A = data.primitive_atoms.shape[0]
         nch = 2 if (n_up > 0 and n_dn > 0) else 1
         bb = {}
-        d1, d2 = 7 * A, 7
+        fw = 4 if self.distance_type == "nu" else 7
+        d1, d2 = fw * A, fw
         idx = 0
         L = len(self.hidden_dims_single)
         for layer in range(L):
@@ -429,7 +430,7 @@ class SolidWavefunction:
         kl = torch.as_tensor(self.klist, dtype=torch.float32).to(device).contiguous()
         return _marshal.solid_handle(params, self.nspins, n_prim_atoms, self.simulation_lattice, self.primitive_lattice,
                                      kl, self.ndets, self.hidden_dims_single, self.hidden_dims_double,
-                                     self.envelope_type, self.orbitals_spin_split)
+                                     self.envelope_type, self.orbitals_spin_split, self.distance_type, self.sym_type)
 
     def _sampling_handles(self, params, data):
         return (self._handle(params, data.primitive_atoms.shape[0], data.electrons.device),

@@ -34,6 +34,9 @@ def pack_config(kind: str, **f):
             return WF_FERMINET, np.asarray(words, np.int32), np.zeros(0, np.float32), 0
         lat = np.concatenate([np.asarray(f["simulation_lattice"], np.float32).reshape(9),
                               np.asarray(f["primitive_lattice"], np.float32).reshape(9)])
+        # two trailing words: geometry/pbc.py DistanceType / SymmetryType (JAQMC_DISTANCE_*, JAQMC_SYMMETRY_*)
+        words += [{"tri": 0, "nu": 1}[str(f.get("distance_type", "tri"))],
+                  {"minimal": 0, "fcc": 1, "bcc": 2, "hexagonal": 3}[str(f.get("sym_type", "minimal"))]]
         return WF_SOLID_FERMINET, np.asarray(words, np.int32), lat, 0
     if kind == "lapnet":
         words = [n_up, n_dn, int(f["n_atoms"]), int(f["ndets"]), int(f["num_layers"]), int(f["num_heads"]), int(f["heads_dim"]),

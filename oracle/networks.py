@@ -386,9 +386,19 @@ def psiformer_logpsi(params, electrons, atoms, nspins, layer_norm_mode="pre", en
 # ---------------------------------------------------------------------------------------
 # periodic FermiNet (solid)
 # ---------------------------------------------------------------------------------------
-def get_symmetry_lat(lattice: torch.Tensor):
-    """``geometry/pbc.py:347-381`` (``SymmetryType.minimal``)."""
-    bv = 2 * math.pi * torch.linalg.inv(lattice).T
+_SYM_MATS = {
+    "minimal": [[1, 0, 0], [0, 1, 0], [0, 0, 1]],
+    "fcc": [[1, 0, 0], [0, 1, 0], [0, 0, 1], [1, 1, 1]],
+    "bcc": [[1, 0, 0], [0, 1, 0], [0, 0, 1], [1, -1, 0], [1, 0, -1], [0, 1, -1]],
+    "hexagonal": [[1, 0, 0], [0, 1, 0], [0, 0, 1], [-1, -1, 0]],
+}
+
+
+def get_symmetry_lat(lattice: torch.Tensor, sym_type: str = "minimal"):
+    """``geometry/pbc.py:347-381``: reciprocal vectors expanded by the integer direction table of the symmetry type
+    (unknown types fall back to the identity there; here they raise), ``av = pinv(bv)^T``."""
+    mat = torch.tensor(_SYM_MATS[sym_type], dtype=F64)
+    bv = mat @ (2 * math.pi * torch.linalg.inv(lattice).T)
     av = torch.linalg.pinv(bv).T
     return av, bv
 
@@ -416,18 +426,50 @@ def tri_distance(xea, a: torch.Tensor, b: torch.Tensor):
     return sd, rel
 
 
-def solid_features(electrons, prim_atoms, sim_lattice, prim_lattice):
-    """``wavefunction/input/atomic.py:108-147`` (``tri`` distance, minimal symmetry)."""
-    sim_av, sim_bv = get_symmetry_lat(sim_lattice)
-    prim_av, prim_bv = get_symmetry_lat(prim_lattice)
+def _scaled_f(w):
+    """``geometry/pbc.py:205-220``: ``f(w) = |w| (1 - |w / pi|^3 / 4)``."""
+    aw = L.abs_(w)
+    z = aw * (1.0 / math.pi)
+    return aw * (1.0 - z * z * z * 0.25)
+
+
+def _scaled_g(w):
+    """``geometry/pbc.py:223-240``: ``g(w) = w (1 - 3/2 |w / pi| + 1/2 |w / pi|^2)``."""
+    z = L.abs_(w) * (1.0 / math.pi)
+    return w * (1.0 - z * 1.5 + z * z * 0.5)
+
+
+def nu_distance(xea, a: torch.Tensor, b: torch.Tensor):
+    """``geometry/pbc.py:243-279``: polynomial periodic distance; ``(w + pi) // (2 pi)`` is a constant integer shift
+    under derivative tracking."""
+    w = L.matmul(xea, b.T)
+    shift = torch.floor((L.value(w) + math.pi) / (2 * math.pi)).detach()
+    w = w - shift * (2 * math.pi)
+    fw = _scaled_f(w) * torch.linalg.norm(a, dim=-1)
+    r1 = L.sum_(fw * fw, dim=-1)
+    sg = _scaled_g(w)
+    rel = L.matmul(sg, a)
+    metric = a @ a.T
+    off = metric * (1.0 - torch.eye(a.shape[0], dtype=F64))
+    un_r = lambda t: L.linear_map(lambda u: u[..., :, None], t)  # noqa: E731
+    un_c = lambda t: L.linear_map(lambda u: u[..., None, :], t)  # noqa: E731
+    r2 = L.sum_(L.sum_(un_r(sg) * un_c(sg) * off, dim=-1), dim=-1)
+    return L.sqrt(r1 + r2), rel
+
+
+def solid_features(electrons, prim_atoms, sim_lattice, prim_lattice, distance_type="tri", sym_type="minimal"):
+    """``wavefunction/input/atomic.py:108-147``; ``distance_type`` 'tri' | 'nu' (``geometry/pbc.py:327-344``)."""
+    dist = {"tri": tri_distance, "nu": nu_distance}[distance_type]
+    sim_av, sim_bv = get_symmetry_lat(sim_lattice, sym_type)
+    prim_av, prim_bv = get_symmetry_lat(prim_lattice, sym_type)
     n = electrons.shape[0]
     pe = wrap_positions(electrons, prim_lattice)
     ae_disp = L.linear_map(lambda t: t[:, None, :], pe) - prim_atoms
-    r_ae, ae_vec = tri_distance(ae_disp, prim_av, prim_bv)
+    r_ae, ae_vec = dist(ae_disp, prim_av, prim_bv)
     se = wrap_positions(electrons, sim_lattice)
     ee_disp = L.linear_map(lambda t: t[:, None, :], se) - L.linear_map(lambda t: t[None, :, :], se)
     eye = torch.eye(n, dtype=F64)
-    r_ee, ee_vec = tri_distance(ee_disp + eye[..., None], sim_av, sim_bv)
+    r_ee, ee_vec = dist(ee_disp + eye[..., None], sim_av, sim_bv)
     r_ee = r_ee * (1.0 - eye)
     ee_vec = ee_vec * (1.0 - eye)[..., None]
     un = lambda t: L.linear_map(lambda u: u[..., None], t)  # noqa: E731
@@ -436,11 +478,12 @@ def solid_features(electrons, prim_atoms, sim_lattice, prim_lattice):
     return dict(ae_features=ae_features, ee_features=ee_features, r_ae=r_ae, ae_vec=ae_vec)
 
 
-def solid_logpsi(params, electrons, prim_atoms, nspins, sim_lattice, prim_lattice, klist):
+def solid_logpsi(params, electrons, prim_atoms, nspins, sim_lattice, prim_lattice, klist, distance_type="tri",
+                 sym_type="minimal"):
     """``app/solid/wavefunction.py:91-147`` -> complex ``logpsi``."""
     p = params["params"]
     n_layers = (len(p["backbone_layer"]) + 1) // 2
-    emb = solid_features(electrons, prim_atoms, sim_lattice, prim_lattice)
+    emb = solid_features(electrons, prim_atoms, sim_lattice, prim_lattice, distance_type, sym_type)
     h_one, _ = fermi_layers(p["backbone_layer"], emb["ae_features"], emb["ee_features"], nspins, n_layers)
     orb_r = orbital_projection(p["real_orbital_layer"], h_one, nspins)
     orb_i = orbital_projection(p["imag_orbital_layer"], h_one, nspins)
@@ -537,10 +580,11 @@ def init_ferminet_params(nspins, n_atoms, ndets=16, hidden_single=(256,) * 4, hi
 
 
 def init_solid_params(nspins, n_prim_atoms, ndets=16, hidden_single=(256,) * 4, hidden_double=(32,) * 4,
-                      seed=0, jitter=0.2):
-    """Tree of ``app/solid/wavefunction.py:58-89`` (``tri`` features: 7 per atom / pair)."""
+                      seed=0, jitter=0.2, distance_type="tri"):
+    """Tree of ``app/solid/wavefunction.py:58-89`` (``tri`` features: 7 per atom / pair; ``nu``: 4)."""
+    fw = 4 if distance_type == "nu" else 7
     base = init_ferminet_params(nspins, n_prim_atoms, ndets, hidden_single, hidden_double, seed, jitter,
-                                feat_per_atom=7, ee_feat=7)["params"]
+                                feat_per_atom=fw, ee_feat=fw)["params"]
     g = torch.Generator().manual_seed(seed + 7919)
     h = hidden_single[-1]
     return {"params": {

@@ -414,6 +414,14 @@ def main():
         solid_case("solid_cubic_h2", "cubic_h2", dict(ndets=2, hidden_dims_single=[16, 16], hidden_dims_double=[8, 8]), 2)
     if want("solid_fcc_lih_221"):
         solid_case("solid_fcc_lih_221", "fcc_lih_221", dict(ndets=2, hidden_dims_single=[16, 16], hidden_dims_double=[8, 8]), 2)
+    # geometry/pbc.py options: polynomial `nu` distance (4 features per pair) and over-complete direction sets
+    small = dict(ndets=2, hidden_dims_single=[16, 16], hidden_dims_double=[8, 8])
+    for nm, kind, opts in (("solid_cubic_h2_nu", "cubic_h2", dict(distance_type="nu")),
+                           ("solid_fcc_lih_221_tri_fcc", "fcc_lih_221", dict(sym_type="fcc")),
+                           ("solid_fcc_lih_221_nu_bcc", "fcc_lih_221", dict(distance_type="nu", sym_type="bcc")),
+                           ("solid_cubic_h2_tri_hexagonal", "cubic_h2", dict(sym_type="hexagonal"))):
+        if want(nm):
+            solid_case(nm, kind, dict(small, **opts), 2)
     if want("ewald"):
         madelung_case()
     if want("mcmc_lih"):

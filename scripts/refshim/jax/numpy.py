@@ -340,3 +340,16 @@ if not getattr(torch.Tensor, "_refshim_matmul", False):
 
     torch.Tensor.__matmul__ = _promoting_matmul
     torch.Tensor._refshim_matmul = True
+
+# ``a // b`` under jax autodiff has a zero derivative; torch's floor_divide has no derivative formula at all.
+# floor(a / b) is the same value with a zero gradient.
+if not getattr(torch.Tensor, "_refshim_floordiv", False):
+    def _floordiv(self, other):
+        return torch.floor(torch.true_divide(self, other))
+
+    def _rfloordiv(self, other):
+        return torch.floor(torch.true_divide(other, self))
+
+    torch.Tensor.__floordiv__ = _floordiv
+    torch.Tensor.__rfloordiv__ = _rfloordiv
+    torch.Tensor._refshim_floordiv = True

@@ -15,19 +15,21 @@ F64 = torch.float64
 solid_system = H.solid_system
 
 
-def _setup(kind, W, ndets=2, hs=(16, 16), hd=(8, 8), seed=0, device="cpu"):
+def _setup(kind, W, ndets=2, hs=(16, 16), hd=(8, 8), seed=0, device="cpu", distance_type="tri", sym_type="minimal"):
     prim, sim, patoms, cell_atoms, cell_charges, nspins, klist = solid_system(kind)
     n = sum(nspins)
-    p64 = H.round_f32(ON.init_solid_params(nspins, patoms.shape[0], ndets, hs, hd, seed=seed + 21))
+    p64 = H.round_f32(ON.init_solid_params(nspins, patoms.shape[0], ndets, hs, hd, seed=seed + 21,
+                                           distance_type=distance_type))
     g = np.random.default_rng(seed)
     el = (cell_atoms[g.integers(0, len(cell_atoms), (W, n))] + 0.8 * g.normal(size=(W, n, 3))).astype(np.float32)
     f32 = lambda a: torch.as_tensor(np.asarray(a), dtype=torch.float32).to(device)  # noqa: E731
-    wf = M.solid_handle(H.to_f32(p64, device), nspins, patoms.shape[0], sim, prim, f32(klist), ndets, hs, hd)
+    wf = M.solid_handle(H.to_f32(p64, device), nspins, patoms.shape[0], sim, prim, f32(klist), ndets, hs, hd,
+                        distance_type=distance_type, sym_type=sym_type)
     sysh = M.system_handle(f32(patoms), None)
     t = lambda a: torch.as_tensor(np.asarray(a, dtype=np.float64))  # noqa: E731
 
     def logpsi(e):
-        return ON.solid_logpsi(p64, e, t(patoms), nspins, t(sim), t(prim), t(klist))
+        return ON.solid_logpsi(p64, e, t(patoms), nspins, t(sim), t(prim), t(klist), distance_type, sym_type)
 
     return wf, sysh, el, logpsi, (sim, cell_atoms, cell_charges), f32
 
@@ -78,3 +80,14 @@ def check_solid(rt, kind, W, device="cpu", **kw):
 @pytest.mark.parametrize("kind", ["cubic_h2", "fcc_lih_221"])
 def test_solid_local_energy_matches_oracle(kind):
     check_solid(H.emu_runtime(), kind, 4)
+
+
+# geometry/pbc.py options: the polynomial `nu` distance (4 features per pair) and the over-complete direction sets of
+# get_symmetry_lat (4 directions for fcc / hexagonal, 6 for bcc)
+PBC_OPTIONS = [("cubic_h2", "nu", "minimal"), ("fcc_lih_221", "tri", "fcc"), ("fcc_lih_221", "nu", "bcc"),
+               ("cubic_h2", "tri", "hexagonal"), ("fcc_lih_221", "nu", "fcc")]
+
+
+@pytest.mark.parametrize("kind,distance_type,sym_type", PBC_OPTIONS)
+def test_solid_distance_and_symmetry_options_match_oracle(kind, distance_type, sym_type):
+    check_solid(H.emu_runtime(), kind, 3, distance_type=distance_type, sym_type=sym_type)

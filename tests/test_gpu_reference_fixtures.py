@@ -45,7 +45,7 @@ def test_kernels_match_reference_molecule(name):
     assert (np.abs(orb - z["orbitals"]) / scale).max() < 2e-5
 
 
-@pytest.mark.parametrize("name", ["solid_cubic_h2", "solid_fcc_lih_221"])
+@pytest.mark.parametrize("name", R.SOLID)
 def test_kernels_match_reference_solid(name):
     from jaqmc_b200.ewald import EwaldSum
     from jaqmc_b200.wavefunction import SolidWavefunction

@@ -25,6 +25,20 @@ def test_solid_local_energy_matches_oracle(kind, kw):
     assert np.isfinite(out["e_loc"].real).all()
 
 
+@pytest.mark.parametrize("kind,distance_type,sym_type", S.PBC_OPTIONS)
+def test_solid_distance_and_symmetry_options_match_oracle(kind, distance_type, sym_type):
+    """geometry/pbc.py `nu` distance and fcc / bcc / hexagonal direction sets on the CUDA kernels."""
+    out = S.check_solid(_rt(), kind, 6, device="cuda", distance_type=distance_type, sym_type=sym_type)
+    assert np.isfinite(out["e_loc"].real).all()
+
+
+def test_solid_nu_bcc_default_widths():
+    """Default network widths with the 4-feature `nu` inputs (tcgen05 dense layers, K = 4 pair layer kernels)."""
+    out = S.check_solid(_rt(), "fcc_lih_221", 4, device="cuda", ndets=16, hs=(256,) * 4, hd=(32,) * 4,
+                        distance_type="nu", sym_type="bcc")
+    assert np.isfinite(out["e_loc"].real).all()
+
+
 def test_solid_parity_lih_222_full_network():
     """BASELINE config 5 at its full per-walker size: LiH rock salt 2x2x2 (32 electrons, 16 atoms, 98 components per
     group, 512-column complex orbital layers), default network widths."""

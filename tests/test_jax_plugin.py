@@ -59,10 +59,16 @@ def test_config_packing_matches_the_c_structs():
     assert kind == _abi.WF_PSIFORMER and np.array_equal(words, _words(cfg, C.sizeof(cfg)))
     prim, sim, patoms, cell_atoms, cell_charges, sn, klist = H.solid_system("fcc_lih_221")
     p = H.to_f32(ON.init_solid_params(sn, 2, 2, (16, 16), (8, 8), seed=2))
-    h = M.solid_handle(p, sn, 2, sim, prim, torch.as_tensor(klist, dtype=torch.float32), 2, (16, 16), (8, 8))
+    p = H.to_f32(ON.init_solid_params(sn, 2, 2, (16, 16), (8, 8), seed=2, distance_type="nu"))
+    h = M.solid_handle(p, sn, 2, sim, prim, torch.as_tensor(klist, dtype=torch.float32), 2, (16, 16), (8, 8),
+                       distance_type="nu", sym_type="bcc")
     cfg = C.cast(h.struct.config, C.POINTER(_abi.SolidConfig)).contents
     kind, words, fcfg, opt = pack_config("solid", nspins=sn, n_atoms=2, ndets=2, hidden_dims_single=(16, 16),
-                                         hidden_dims_double=(8, 8), simulation_lattice=sim, primitive_lattice=prim)
+                                         hidden_dims_double=(8, 8), simulation_lattice=sim, primitive_lattice=prim,
+                                         distance_type="nu", sym_type="bcc")
+    # the shim's `config` attribute: the embedded FermiNet config words, then distance_type and sym_type; the two
+    # lattices travel as 18 floats in `fconfig`
     n_int = C.sizeof(_abi.FerminetConfig)
-    assert kind == _abi.WF_SOLID_FERMINET and np.array_equal(words, _words(cfg, n_int))
-    assert np.array_equal(fcfg, np.frombuffer(bytes(cfg)[n_int:], dtype=np.float32))
+    assert kind == _abi.WF_SOLID_FERMINET and np.array_equal(words[:-2], _words(cfg, n_int))
+    assert list(words[-2:]) == [cfg.distance_type, cfg.sym_type] == [1, 2]
+    assert np.array_equal(fcfg, np.frombuffer(bytes(cfg)[n_int:n_int + 72], dtype=np.float32))

@@ -105,14 +105,19 @@ def test_oracle_matches_reference_molecule(name):
     np.testing.assert_allclose(L.value(orb).numpy(), z["orbitals"][0], rtol=1e-9, atol=1e-12)
 
 
-@pytest.mark.parametrize("name", ["solid_cubic_h2", "solid_fcc_lih_221"])
+SOLID = ["solid_cubic_h2", "solid_fcc_lih_221", "solid_cubic_h2_nu", "solid_fcc_lih_221_tri_fcc", "solid_fcc_lih_221_nu_bcc",
+         "solid_cubic_h2_tri_hexagonal"]
+
+
+@pytest.mark.parametrize("name", SOLID)
 def test_oracle_matches_reference_solid(name):
     meta, params, z = load(name)
     t = lambda k: torch.from_numpy(z[k].astype(np.float64))  # noqa: E731
     nspins = tuple(meta["nspins"])
+    opts = (meta["kwargs"].get("distance_type", "tri"), meta["kwargs"].get("sym_type", "minimal"))
 
     def logpsi(e):
-        return ON.solid_logpsi(params, e, t("prim_atoms"), nspins, t("sim_lattice"), t("prim_lattice"), t("klist"))
+        return ON.solid_logpsi(params, e, t("prim_atoms"), nspins, t("sim_lattice"), t("prim_lattice"), t("klist"), *opts)
 
     ew = OE.EwaldSum(z["sim_lattice"])
     assert abs(ew.alpha - float(z["ewald_alpha"])) < 1e-12 * ew.alpha
