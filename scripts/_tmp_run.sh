@@ -1,2 +1,2 @@
-mkdir -p gpurun_out/r2be
-timeout 1500 python -m pytest tests -m gpu -q -k "solid or reference_fixtures or leaf" 2>&1 | tail -6 > gpurun_out/r2be/tests.log
+mkdir -p gpurun_out/r2bg
+python bench.py --walkers 512 --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/r2bg/n2_512.json 2> gpurun_out/r2bg/n2_512.err
