@@ -556,12 +556,15 @@ __global__ void __launch_bounds__(256, 2) k_logdet_small(const float* __restrict
       // column of M in favour of re-reading the scratch tile, or prefetching with NS = 2, both lose (1.45 - 1.55 ms).
       __syncwarp();
       {
-        const float* ib = invp_w + (size_t)(on ? d : 0) * IS;
-        float* scr = invp_w + (size_t)DB * IS + (size_t)(on ? d : 0) * NS * (nn + ((n - nn) % 32 + 32) % 32);
+        // an idle half-warp (odd determinant count) addresses the slot of its own warp's other half: written before the
+        // __syncwarp above, so it never reads a tile another warp is still writing (compute-sanitizer racecheck, r2)
+        const int ds = on ? d : dbase;
+        const float* ib = invp_w + (size_t)ds * IS;
+        float* scr = invp_w + (size_t)DB * IS + (size_t)ds * NS * (nn + ((n - nn) % 32 + 32) % 32);
         const bool act = on && hl < n;
-        const float* ocol = ow + (on ? d : 0) * n + (hl < n ? hl : 0);   // column (d, i2 = hl); + (1 + kk) * DN + j * C * DN
+        const float* ocol = ow + ds * n + (hl < n ? hl : 0);   // column (d, i2 = hl); + (1 + kk) * DN + j * C * DN
         float t2acc = 0.f, trl = 0.f;
-        float* gout = det_grad + (w * D + d0 + (on ? d : 0)) * (long long)K;
+        float* gout = det_grad + (w * D + d0 + ds) * (long long)K;
         const int MS = nn + ((n - nn) % 32 + 32) % 32;
         // NS slabs per pass over A^-1: each float4 of the inverse read from shared memory feeds NS columns.
         for (int kk = 0; kk < KT; kk += NS) {
