@@ -48,6 +48,16 @@ constexpr int TC_SMEM_LIMIT = 227 * 1024;
 constexpr int TC_SMEM_EXTRA = 1024 /*align*/ + 256 /*barriers*/;
 constexpr int TC_THREADS = 512;
 constexpr int TC_TMEM_COLS = 512;  // 2 buffers x {main, cross} x 128 columns
+// A/B (r2): cache-streaming hints on the epilogue's global traffic (the residual is read once, the output written once).
+// Measured with -DJQ_TC_STREAM_HINTS, same box, FermiNet-N2: 16.887 (off) / 16.894 (on) / 16.869 (off) ms per
+// evaluation -- no effect; left off.
+#ifdef JQ_TC_STREAM_HINTS
+#define TC_LD_RES(ptr) __ldcs(ptr)
+#define TC_ST_OUT(ptr, v) __stcs((ptr), (v))
+#else
+#define TC_LD_RES(ptr) (*(ptr))
+#define TC_ST_OUT(ptr, v) (*(ptr) = (v))
+#endif
 constexpr int TC_CH = 8;           // epilogue column chunk
 
 struct TcParams {
@@ -466,7 +476,7 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& p, uint32_t tlane0
     uint32_t o_ = (uint32_t)(r0 + (j) * TC_CH) * N + (u).fo;         \
     _Pragma("unroll") for (int i_ = 0; i_ < TC_CH; ++i_, o_ += N) { \
       if (CADD) ca[slot][i_] = (u).cadd_b[o_];                       \
-      if (RES) rr[slot][i_] = (u).res_b[o_];                         \
+      if (RES) rr[slot][i_] = TC_LD_RES((u).res_b + o_);                         \
     }                                                                \
   }
 #define TC_TAIL_LOAD(u)                                              \
@@ -475,17 +485,17 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& p, uint32_t tlane0
     _Pragma("unroll") for (int i_ = 0; i_ < TC_CH; ++i_, o_ += N) { \
       if (i_ >= tail_skip) {                                         \
         if (CADD) caT[i_] = (u).cadd_b[o_];                          \
-        if (RES) rrT[i_] = (u).res_b[o_];                            \
+        if (RES) rrT[i_] = TC_LD_RES((u).res_b + o_);                            \
       }                                                              \
     }                                                                \
   }
 #define TC_EDGE_LOAD(u, c0_, r0_, cl_, rl_)                          \
   {                                                                  \
     if (CADD) c0_ = (u).cadd_b[(u).fo];                              \
-    if (RES) r0_ = (u).res_b[(u).fo];                                \
+    if (RES) r0_ = TC_LD_RES((u).res_b + (u).fo);                                \
     if (C > 1) {                                                     \
       if (CADD) cl_ = (u).cadd_b[o_last + (u).fo];                   \
-      if (RES) rl_ = (u).res_b[o_last + (u).fo];                     \
+      if (RES) rl_ = TC_LD_RES((u).res_b + o_last + (u).fo);                     \
     }                                                                \
   }
   // one chunk row: accumulator sum (+ addend) -> activation rule -> residual; `c` is the row's component index
@@ -510,7 +520,7 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& p, uint32_t tlane0
     if (ACT == 0 && (c) == 0) y_ += bias_f;                            \
     if (RES == 1) y_ = ((rrv) + y_) * inv_sqrt2;                       \
     if (RES == 2) y_ = (rrv) + y_;                                     \
-    if (f_ok) out_b[o] = y_;                                           \
+    if (f_ok) TC_ST_OUT(out_b + (o), y_);                                         \
   }
 
   EpiUnit cur = find_unit(first, sub);
@@ -584,7 +594,7 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& p, uint32_t tlane0
           }
           if (RES == 1) o0 = (rr0 + o0) * inv_sqrt2;
           if (RES == 2) o0 = rr0 + o0;
-          if (f_ok) out_b[fo] = o0;
+          if (f_ok) TC_ST_OUT(out_b + fo, o0);
         }
         for (int j0 = 0; j0 < nfull; j0 += TC_RING) {
 #pragma unroll
@@ -624,7 +634,7 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& p, uint32_t tlane0
           float l = (ACT == 1) ? d1 * yl - 2.0f * th * d1 * s2 : yl * ev + y0 * e_l + 2.0f * s2;
           if (RES == 1) l = (rrL + l) * inv_sqrt2;
           if (RES == 2) l = rrL + l;
-          if (f_ok) out_b[o_last + fo] = l;
+          if (f_ok) TC_ST_OUT(out_b + o_last + fo, l);
         }
         ca0 = n_ca0;
         rr0 = n_rr0;
@@ -668,7 +678,7 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& p, uint32_t tlane0
           }
           if (RES == 1) y = (cur.res_b[o] + y) * inv_sqrt2;
           if (RES == 2) y = cur.res_b[o] + y;
-          if (f_ok) out_b[o] = y;
+          if (f_ok) TC_ST_OUT(out_b + o, y);
         }
       }
       cur = nxt;
