@@ -1343,7 +1343,9 @@ k_attention_fl_mma(JqAttnOperand q, JqAttnOperand k, JqAttnOperand v, float* __r
     // barrier per component -- changed the launch time by 1-2 %, inside the box-to-box spread; the simpler form is kept.)
     for (int kk = slot; kk < K; kk += SLOTS) {
       const int comp = 1 + kk;
-      asm volatile("bar.sync %0, %1;" ::"r"(1 + slot), "r"(sthreads) : "memory");   // previous tiles fully consumed
+      // (a slot is a single warp when NP == 16: __syncwarp instead of a named barrier)
+      if (RT == 1) __syncwarp();
+      else asm volatile("bar.sync %0, %1;" ::"r"(1 + slot), "r"(sthreads) : "memory");   // previous tiles fully consumed
       for (int x = sl; x < n * 16; x += sthreads) {
         const int i = x >> 4, d4 = (x & 15) * 4;
         attn_stage4(kJs + i * AM_LD + d4, k, w, n, i, comp, k.off + h * dh + d4, Cd);
@@ -1352,22 +1354,33 @@ k_attention_fl_mma(JqAttnOperand q, JqAttnOperand k, JqAttnOperand v, float* __r
       attn_async_commit();
       const float* pJ0 = am_row(q, w, n, i0, comp, q.off + h * dh, Cd);
       const float* pJ1 = am_row(q, w, n, i1, comp, q.off + h * dh, Cd);
-      float xq[4];
-      xq[0] = pJ0 ? pJ0[t] : 0.f; xq[1] = pJ1 ? pJ1[t] : 0.f; xq[2] = pJ0 ? pJ0[t + 4] : 0.f; xq[3] = pJ1 ? pJ1[t + 4] : 0.f;
+      // qJ fragments straight from global.  NP == 16 (few accumulators): all eight k-steps are requested here, before
+      // the wait on the staged tiles (r2 profile of this variant: 17 % of the stall samples at the first use of a
+      // fragment fetched one step ahead); the larger variants are at their register cap and keep the one-step prefetch.
+      // Measured: 4.11-4.19 -> 4.09 ms (Psiformer-N2), 3.46 -> 3.42 ms (LapNet-N2) at equal dense-kernel times: ~1 %, the
+      // stalls moved elsewhere (tensor pipe 41 % active, 7.8 instructions per HMMA with only two column tiles per A fragment).
+      constexpr int XQ = (NP == 16) ? dh / 8 : 1;
+      float xq[XQ][4];
+#pragma unroll
+      for (int u = 0; u < XQ; ++u) {
+        const int c = 8 * u + t;
+        xq[u][0] = pJ0 ? pJ0[c] : 0.f; xq[u][1] = pJ1 ? pJ1[c] : 0.f; xq[u][2] = pJ0 ? pJ0[c + 4] : 0.f; xq[u][3] = pJ1 ? pJ1[c + 4] : 0.f;
+      }
       attn_async_wait<0>();
-      asm volatile("bar.sync %0, %1;" ::"r"(1 + slot), "r"(sthreads) : "memory");
+      if (RT == 1) __syncwarp();
+      else asm volatile("bar.sync %0, %1;" ::"r"(1 + slot), "r"(sthreads) : "memory");
       // phase A
       float aJ[NJ][4], a2[NJ][4];
 #pragma unroll
       for (int a = 0; a < NJ; ++a) aJ[a][0] = aJ[a][1] = aJ[a][2] = aJ[a][3] = a2[a][0] = a2[a][1] = a2[a][2] = a2[a][3] = 0.f;
-#pragma unroll 2
+#pragma unroll (NP == 16 ? 8 : 2)
       for (int ks = 0; ks < dh / 8; ++ks) {
         unsigned qJh[4], qJl[4], q0h[4], q0l[4];
 #pragma unroll
-        for (int e = 0; e < 4; ++e) am_split<RNA>(xq[e], qJh[e], qJl[e]);
-        if (ks + 1 < dh / 8) {
+        for (int e = 0; e < 4; ++e) am_split<RNA>(xq[XQ == 1 ? 0 : ks][e], qJh[e], qJl[e]);
+        if (XQ == 1 && ks + 1 < dh / 8) {
           const int c = 8 * (ks + 1) + t;
-          xq[0] = pJ0 ? pJ0[c] : 0.f; xq[1] = pJ1 ? pJ1[c] : 0.f; xq[2] = pJ0 ? pJ0[c + 4] : 0.f; xq[3] = pJ1 ? pJ1[c + 4] : 0.f;
+          xq[0][0] = pJ0 ? pJ0[c] : 0.f; xq[0][1] = pJ1 ? pJ1[c] : 0.f; xq[0][2] = pJ0 ? pJ0[c + 4] : 0.f; xq[0][3] = pJ1 ? pJ1[c + 4] : 0.f;
         }
         am_split<RNA>(q0[i0 * AM_LD + 8 * ks + t], q0h[0], q0l[0]);
         am_split<RNA>(q0[i1 * AM_LD + 8 * ks + t], q0h[1], q0l[1]);
