@@ -383,7 +383,8 @@ int jaqmc_b200_dense_fl(const float* x, const float* x2, const float* kernel, co
  * electron i holds only its own three Jacobian columns, the rest are zero).  out is always dense.
  *   kernel 0: the library's choice for the shape; 1: CUDA-core block kernel; 2: CUDA-core warp-per-component kernel
  *   (n <= 14 at head_dim 64: shared-memory limit); 3: mma.sync 3xTF32 tensor-core kernel (n <= 48, head_dim 64), operands split by truncation; 4: the same with
- *   round-to-nearest operand splits.  A forced kernel that does not support the shape
+ *   round-to-nearest operand splits; 5: kernel 3 with the sparse logit-Jacobian phase for one-electron q / k operands
+ *   (q_components = k_components = 5 only).  A forced kernel that does not support the shape
  *   returns JAQMC_ERR_UNSUPPORTED. */
 int jaqmc_b200_attention_fl(const float* q, const float* k, const float* v, float* out, int64_t n_walkers,
                             int32_t n_electrons, int32_t n_heads, int32_t head_dim, int32_t q_components,

@@ -530,7 +530,7 @@ extern "C" int jaqmc_b200_attention_fl(const float* q, const float* k, const flo
                                        int32_t k_components, int32_t kernel, jaqmc_stream_t stream) {
   JQ_REQUIRE(n_walkers >= 0 && n_electrons >= 1 && n_heads >= 1 && head_dim >= 1, JQ_ERR_INVALID_ARGUMENT,
              "attention_fl: bad sizes");
-  JQ_REQUIRE(kernel >= 0 && kernel <= 4, JQ_ERR_INVALID_ARGUMENT, "attention_fl: kernel selector %d", kernel);
+  JQ_REQUIRE(kernel >= 0 && kernel <= 5, JQ_ERR_INVALID_ARGUMENT, "attention_fl: kernel selector %d", kernel);
   JQ_REQUIRE(q && k && v && out, JQ_ERR_INVALID_ARGUMENT, "attention_fl: null operand");
   const int F = n_heads * head_dim, Cd = 3 * n_electrons + 2;
   JqAttnOperand qo{q, q_components, F, 0}, ko{k, k_components, F, 0}, vo{v, Cd, F, 0};

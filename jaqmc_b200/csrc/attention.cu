@@ -1264,7 +1264,7 @@ __device__ __forceinline__ const float* am_row(const JqAttnOperand& t, long long
   return (k / 3 == i) ? base + (long long)(1 + k % 3) * t.ld : nullptr;
 }
 
-template <int NJ, int NP, int SLOTS, bool RNA>
+template <int NJ, int NP, int SLOTS, bool RNA, bool QKL>
 __global__ void __launch_bounds__(SLOTS * (NP / 16) * 32, NP == 16 ? 2 : 1)
 k_attention_fl_mma(JqAttnOperand q, JqAttnOperand k, JqAttnOperand v, float* __restrict__ out, int ldo, int n, int H) {
   constexpr int dh = 64;
@@ -1346,57 +1346,119 @@ k_attention_fl_mma(JqAttnOperand q, JqAttnOperand k, JqAttnOperand v, float* __r
       // (a slot is a single warp when NP == 16: __syncwarp instead of a named barrier)
       if (RT == 1) __syncwarp();
       else asm volatile("bar.sync %0, %1;" ::"r"(1 + slot), "r"(sthreads) : "memory");   // previous tiles fully consumed
-      for (int x = sl; x < n * 16; x += sthreads) {
-        const int i = x >> 4, d4 = (x & 15) * 4;
-        attn_stage4(kJs + i * AM_LD + d4, k, w, n, i, comp, k.off + h * dh + d4, Cd);
-        attn_stage4(vJs + i * AM_LD + d4, v, w, n, i, comp, v.off + h * dh + d4, Cd);
-      }
-      attn_async_commit();
-      const float* pJ0 = am_row(q, w, n, i0, comp, q.off + h * dh, Cd);
-      const float* pJ1 = am_row(q, w, n, i1, comp, q.off + h * dh, Cd);
-      // qJ fragments straight from global.  NP == 16 (few accumulators): all eight k-steps are requested here, before
-      // the wait on the staged tiles (r2 profile of this variant: 17 % of the stall samples at the first use of a
-      // fragment fetched one step ahead); the larger variants are at their register cap and keep the one-step prefetch.
-      // Measured: 4.11-4.19 -> 4.09 ms (Psiformer-N2), 3.46 -> 3.42 ms (LapNet-N2) at equal dense-kernel times: ~1 %, the
-      // stalls moved elsewhere (tensor pipe 41 % active, 7.8 instructions per HMMA with only two column tiles per A fragment).
-      constexpr int XQ = (NP == 16) ? dh / 8 : 1;
-      float xq[XQ][4];
-#pragma unroll
-      for (int u = 0; u < XQ; ++u) {
-        const int c = 8 * u + t;
-        xq[u][0] = pJ0 ? pJ0[c] : 0.f; xq[u][1] = pJ1 ? pJ1[c] : 0.f; xq[u][2] = pJ0 ? pJ0[c + 4] : 0.f; xq[u][3] = pJ1 ? pJ1[c + 4] : 0.f;
-      }
-      attn_async_wait<0>();
-      if (RT == 1) __syncwarp();
-      else asm volatile("bar.sync %0, %1;" ::"r"(1 + slot), "r"(sthreads) : "memory");
-      // phase A
       float aJ[NJ][4], a2[NJ][4];
 #pragma unroll
       for (int a = 0; a < NJ; ++a) aJ[a][0] = aJ[a][1] = aJ[a][2] = aJ[a][3] = a2[a][0] = a2[a][1] = a2[a][2] = a2[a][3] = 0.f;
-#pragma unroll (NP == 16 ? 8 : 2)
-      for (int ks = 0; ks < dh / 8; ++ks) {
-        unsigned qJh[4], qJl[4], q0h[4], q0l[4];
-#pragma unroll
-        for (int e = 0; e < 4; ++e) am_split<RNA>(xq[XQ == 1 ? 0 : ks][e], qJh[e], qJl[e]);
-        if (XQ == 1 && ks + 1 < dh / 8) {
-          const int c = 8 * (ks + 1) + t;
-          xq[0][0] = pJ0 ? pJ0[c] : 0.f; xq[0][1] = pJ1 ? pJ1[c] : 0.f; xq[0][2] = pJ0 ? pJ0[c + 4] : 0.f; xq[0][3] = pJ1 ? pJ1[c + 4] : 0.f;
+      if constexpr (QKL) {
+        // One-electron queries / keys (LapNet, backbone/lapnet/_attention.py:113-196): component (el, axis) of qJ and kJ is
+        // non-zero for electron el only, so the logit Jacobian has one non-zero row and one non-zero column,
+        //   aJ[el][j] = qJ_el . k_j,   aJ[i][el] = q_i . kJ_el,   a2[el][el] = qJ_el . kJ_el      (before the 1/sqrt(d)),
+        // i.e. 16 RT + 16 dot products of length 64 on the CUDA cores instead of 144 HMMAs per row tile; only vJ is a
+        // full tile.  The two rows travel in the first two rows of the slot's kJ area.
+        const int el = kk / 3;
+        for (int x = sl; x < n * 16; x += sthreads) {
+          const int i = x >> 4, d4 = (x & 15) * 4;
+          attn_stage4(vJs + i * AM_LD + d4, v, w, n, i, comp, v.off + h * dh + d4, Cd);
         }
-        am_split<RNA>(q0[i0 * AM_LD + 8 * ks + t], q0h[0], q0l[0]);
-        am_split<RNA>(q0[i1 * AM_LD + 8 * ks + t], q0h[1], q0l[1]);
-        am_split<RNA>(q0[i0 * AM_LD + 8 * ks + t + 4], q0h[2], q0l[2]);
-        am_split<RNA>(q0[i1 * AM_LD + 8 * ks + t + 4], q0h[3], q0l[3]);
+        if (sl < 16) attn_stage4(kJs + sl * 4, q, w, n, el, comp, q.off + h * dh + sl * 4, Cd);
+        else if (sl < 32) attn_stage4(kJs + AM_LD + (sl - 16) * 4, k, w, n, el, comp, k.off + h * dh + (sl - 16) * 4, Cd);
+        attn_async_commit();
+        attn_async_wait<0>();
+        if (RT == 1) __syncwarp();
+        else asm volatile("bar.sync %0, %1;" ::"r"(1 + slot), "r"(sthreads) : "memory");
+        const float4* qe4 = reinterpret_cast<const float4*>(kJs);
+        const float4* ke4 = reinterpret_cast<const float4*>(kJs + AM_LD);
+        auto dot64 = [](const float4* x4, const float4* y4) {
+          float acc = 0.f;
+#pragma unroll
+          for (int d4 = 0; d4 < 16; ++d4) {
+            const float4 xv = x4[d4], yv = y4[d4];
+            acc = fmaf(xv.x, yv.x, acc); acc = fmaf(xv.y, yv.y, acc); acc = fmaf(xv.z, yv.z, acc); acc = fmaf(xv.w, yv.w, acc);
+          }
+          return acc;
+        };
+        float cval = 0.f, rv[RT];
+#pragma unroll
+        for (int m = 0; m < RT; ++m) rv[m] = 0.f;
+        if (lane < 16) {
+          cval = dot64(reinterpret_cast<const float4*>(q0 + (16 * r + lane) * AM_LD), ke4);     // column el, row 16 r + lane
+        } else {
+#pragma unroll
+          for (int m = 0; m < RT; ++m)
+            rv[m] = dot64(qe4, reinterpret_cast<const float4*>(k0 + (lane - 16 + 16 * m) * AM_LD));   // row el, column
+        }
+        float dee = 0.f;
+        if (lane < 16) {
+          const float4 xv = qe4[lane], yv = ke4[lane];
+          dee = xv.x * yv.x + xv.y * yv.y + xv.z * yv.z + xv.w * yv.w;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) dee += __shfl_xor_sync(0xffffffffu, dee, o);
+        const float c0 = __shfl_sync(0xffffffffu, cval, g), c1 = __shfl_sync(0xffffffffu, cval, g + 8);
 #pragma unroll
         for (int a = 0; a < NJ; ++a) {
-          unsigned k0h[2], k0l[2], kJh[2], kJl[2];
-          const int o = (8 * a + g) * AM_LD + 8 * ks + t;
-          am_split<RNA>(k0[o], k0h[0], k0l[0]);
-          am_split<RNA>(k0[o + 4], k0h[1], k0l[1]);
-          am_split<RNA>(kJs[o], kJh[0], kJl[0]);
-          am_split<RNA>(kJs[o + 4], kJh[1], kJl[1]);
-          am_mma3(aJ[a], qJh, qJl, k0h, k0l);
-          am_mma3(aJ[a], q0h, q0l, kJh, kJl);
-          am_mma3(a2[a], qJh, qJl, kJh, kJl);
+          const int colA = 8 * a + 2 * t, colB = colA + 1;
+          const float rA = __shfl_sync(0xffffffffu, rv[a / 2], 16 + (colA & 15));
+          const float rB = __shfl_sync(0xffffffffu, rv[a / 2], 16 + (colB & 15));
+          aJ[a][0] = (i0 == el ? rA : 0.f) + (colA == el ? c0 : 0.f);
+          aJ[a][1] = (i0 == el ? rB : 0.f) + (colB == el ? c0 : 0.f);
+          aJ[a][2] = (i1 == el ? rA : 0.f) + (colA == el ? c1 : 0.f);
+          aJ[a][3] = (i1 == el ? rB : 0.f) + (colB == el ? c1 : 0.f);
+          a2[a][0] = (i0 == el && colA == el) ? dee : 0.f;
+          a2[a][1] = (i0 == el && colB == el) ? dee : 0.f;
+          a2[a][2] = (i1 == el && colA == el) ? dee : 0.f;
+          a2[a][3] = (i1 == el && colB == el) ? dee : 0.f;
+        }
+      } else {
+        for (int x = sl; x < n * 16; x += sthreads) {
+          const int i = x >> 4, d4 = (x & 15) * 4;
+          attn_stage4(kJs + i * AM_LD + d4, k, w, n, i, comp, k.off + h * dh + d4, Cd);
+          attn_stage4(vJs + i * AM_LD + d4, v, w, n, i, comp, v.off + h * dh + d4, Cd);
+        }
+        attn_async_commit();
+        const float* pJ0 = am_row(q, w, n, i0, comp, q.off + h * dh, Cd);
+        const float* pJ1 = am_row(q, w, n, i1, comp, q.off + h * dh, Cd);
+        // qJ fragments straight from global.  NP == 16 (few accumulators): all eight k-steps are requested here, before
+        // the wait on the staged tiles (r2 profile of this variant: 17 % of the stall samples at the first use of a
+        // fragment fetched one step ahead); the larger variants are at their register cap and keep the one-step prefetch.
+        // Measured: 4.11-4.19 -> 4.09 ms (Psiformer-N2), 3.46 -> 3.42 ms (LapNet-N2) at equal dense-kernel times: ~1 %, the
+        // stalls moved elsewhere (tensor pipe 41 % active, 7.8 instructions per HMMA with only two column tiles per A fragment).
+        constexpr int XQ = (NP == 16) ? dh / 8 : 1;
+        float xq[XQ][4];
+  #pragma unroll
+        for (int u = 0; u < XQ; ++u) {
+          const int c = 8 * u + t;
+          xq[u][0] = pJ0 ? pJ0[c] : 0.f; xq[u][1] = pJ1 ? pJ1[c] : 0.f; xq[u][2] = pJ0 ? pJ0[c + 4] : 0.f; xq[u][3] = pJ1 ? pJ1[c + 4] : 0.f;
+        }
+        attn_async_wait<0>();
+        if (RT == 1) __syncwarp();
+        else asm volatile("bar.sync %0, %1;" ::"r"(1 + slot), "r"(sthreads) : "memory");
+        // phase A
+  #pragma unroll (NP == 16 ? 8 : 2)
+        for (int ks = 0; ks < dh / 8; ++ks) {
+          unsigned qJh[4], qJl[4], q0h[4], q0l[4];
+  #pragma unroll
+          for (int e = 0; e < 4; ++e) am_split<RNA>(xq[XQ == 1 ? 0 : ks][e], qJh[e], qJl[e]);
+          if (XQ == 1 && ks + 1 < dh / 8) {
+            const int c = 8 * (ks + 1) + t;
+            xq[0][0] = pJ0 ? pJ0[c] : 0.f; xq[0][1] = pJ1 ? pJ1[c] : 0.f; xq[0][2] = pJ0 ? pJ0[c + 4] : 0.f; xq[0][3] = pJ1 ? pJ1[c + 4] : 0.f;
+          }
+          am_split<RNA>(q0[i0 * AM_LD + 8 * ks + t], q0h[0], q0l[0]);
+          am_split<RNA>(q0[i1 * AM_LD + 8 * ks + t], q0h[1], q0l[1]);
+          am_split<RNA>(q0[i0 * AM_LD + 8 * ks + t + 4], q0h[2], q0l[2]);
+          am_split<RNA>(q0[i1 * AM_LD + 8 * ks + t + 4], q0h[3], q0l[3]);
+  #pragma unroll
+          for (int a = 0; a < NJ; ++a) {
+            unsigned k0h[2], k0l[2], kJh[2], kJl[2];
+            const int o = (8 * a + g) * AM_LD + 8 * ks + t;
+            am_split<RNA>(k0[o], k0h[0], k0l[0]);
+            am_split<RNA>(k0[o + 4], k0h[1], k0l[1]);
+            am_split<RNA>(kJs[o], kJh[0], kJl[0]);
+            am_split<RNA>(kJs[o + 4], kJh[1], kJl[1]);
+            am_mma3(aJ[a], qJh, qJl, k0h, k0l);
+            am_mma3(aJ[a], q0h, q0l, kJh, kJl);
+            am_mma3(a2[a], qJh, qJl, kJh, kJl);
+          }
         }
       }
       // phase B (registers): rows i0 (elements 0, 1) and i1 (elements 2, 3)
@@ -1599,33 +1661,40 @@ int jq_launch_attention_fl_sel(const JqAttnOperand& q, const JqAttnOperand& k, c
     }
     // n <= 48 and not taken by the warp kernel above: the tensor-core kernel (A/B switch: JAQMC_B200_ATTENTION_SIMT keeps the CUDA-core block kernel)
     static const bool env_simt = getenv("JAQMC_B200_ATTENTION_SIMT") != nullptr;
-    const bool simt_kernel = force ? (force != 3 && force != 4) : env_simt;
+    const bool simt_kernel = force ? (force != 3 && force != 4 && force != 5) : env_simt;
     // (also n = 15, 16, where the warp kernel's per-warp staging no longer fits in shared memory)
     if (track && dh == 64 && n >= 2 && n <= AM_NP && aligned && ldo % 2 == 0 &&
         reinterpret_cast<uintptr_t>(out) % 8 == 0 && !old_kernel && !simt_kernel) {
       static const bool env_rna = getenv("JAQMC_B200_ATTENTION_RNA") != nullptr;   // A/B switch: round-to-nearest operand split
-      const bool rna = force == 4 || (force != 3 && env_rna);
+      const bool rna = force == 4 || (force == 0 && env_rna);
       const int NP = 16 * ((n + 15) / 16), SL = NP == 16 ? 8 : 4;
       const size_t sm_mma = sizeof(float) * ((size_t)3 * NP * AM_LD + NP * AM_LW + (size_t)SL * 2 * NP * AM_LD);
       const dim3 grid((unsigned)(W * H)), block(32 * (NP / 16) * SL);
-#define JQ_AM_LAUNCH(NJ_, NP_, SL_, RNA_)                                                                                \
+#define JQ_AM_LAUNCH(NJ_, NP_, SL_, RNA_, QKL_)                                                                               \
   do {                                                                                                                   \
     static JqPerDeviceFlag attr_set;                                                                                     \
     const int dev = jq_current_device();                                                                                 \
     if (!attr_set.done[dev]) {                                                                                           \
-      cudaError_t e = cudaFuncSetAttribute(k_attention_fl_mma<NJ_, NP_, SL_, RNA_>,                                      \
+      cudaError_t e = cudaFuncSetAttribute(k_attention_fl_mma<NJ_, NP_, SL_, RNA_, QKL_>,                                \
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_mma);                   \
       JQ_REQUIRE(e == cudaSuccess, JQ_ERR_CUDA, "attention: cudaFuncSetAttribute: %s", cudaGetErrorString(e));           \
       attr_set.done[dev] = true;                                                                                         \
     }                                                                                                                    \
-    JQ_LAUNCH((k_attention_fl_mma<NJ_, NP_, SL_, RNA_>), grid, block, sm_mma, st, q, k, v, out, ldo, n, H);             \
+    JQ_LAUNCH((k_attention_fl_mma<NJ_, NP_, SL_, RNA_, QKL_>), grid, block, sm_mma, st, q, k, v, out, ldo, n, H);       \
   } while (0)
-      if (NP == 16 && !rna) JQ_AM_LAUNCH(2, 16, 8, false);
-      else if (NP == 16) JQ_AM_LAUNCH(2, 16, 8, true);
-      else if (NP == 32 && !rna) JQ_AM_LAUNCH(4, 32, 4, false);
-      else if (NP == 32) JQ_AM_LAUNCH(4, 32, 4, true);
-      else if (!rna) JQ_AM_LAUNCH(6, 48, 4, false);
-      else JQ_AM_LAUNCH(6, 48, 4, true);
+      // one-electron queries / keys (LapNet): sparse logit-Jacobian phase (A/B switch JAQMC_B200_ATTENTION_DENSE_QK)
+      static const bool env_dense_qk = getenv("JAQMC_B200_ATTENTION_DENSE_QK") != nullptr;
+      const bool qkl = q.C == 5 && k.C == 5 && Cd != 5 && !rna && ((force == 0 && !env_dense_qk) || force == 5);
+      JQ_REQUIRE(force != 5 || qkl, JQ_ERR_UNSUPPORTED, "attention: kernel 5 needs one-electron (5-component) q and k operands");
+      if (NP == 16 && qkl) JQ_AM_LAUNCH(2, 16, 8, false, true);
+      else if (NP == 32 && qkl) JQ_AM_LAUNCH(4, 32, 4, false, true);
+      else if (qkl) JQ_AM_LAUNCH(6, 48, 4, false, true);
+      else if (NP == 16 && !rna) JQ_AM_LAUNCH(2, 16, 8, false, false);
+      else if (NP == 16) JQ_AM_LAUNCH(2, 16, 8, true, false);
+      else if (NP == 32 && !rna) JQ_AM_LAUNCH(4, 32, 4, false, false);
+      else if (NP == 32) JQ_AM_LAUNCH(4, 32, 4, true, false);
+      else if (!rna) JQ_AM_LAUNCH(6, 48, 4, false, false);
+      else JQ_AM_LAUNCH(6, 48, 4, true, false);
 #undef JQ_AM_LAUNCH
       JQ_CHECK_LAUNCH();
       return JQ_OK;

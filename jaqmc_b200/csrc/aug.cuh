@@ -165,6 +165,6 @@ int jq_launch_layernorm_fl_sel(const float* x, const float* scale, const float* 
 int jq_launch_attention_fl(const JqAttnOperand& q, const JqAttnOperand& k, const JqAttnOperand& v, float* out, int ldo,
                            long long W, int n, int H, int dh, int track, cudaStream_t st);
 // force: 0 library's choice | 1 block kernel | 2 warp kernel | 3 mma.sync kernel, truncating split | 4 mma.sync kernel,
-// round-to-nearest split (JQ_ERR_UNSUPPORTED when not eligible)
+// round-to-nearest split | 5 mma.sync kernel, sparse phase for one-electron q / k (JQ_ERR_UNSUPPORTED when not eligible)
 int jq_launch_attention_fl_sel(const JqAttnOperand& q, const JqAttnOperand& k, const JqAttnOperand& v, float* out, int ldo,
                                long long W, int n, int H, int dh, int track, int force, cudaStream_t st);

@@ -1,5 +1,6 @@
 """``jaqmc_b200_attention_fl`` on the GPU: every attention kernel (CUDA-core block kernel, warp-per-component kernel,
-mma.sync 3xTF32 tensor-core kernel with truncating (3) and round-to-nearest (4) operand splits) on the SAME random augmented operands against a float64 statement of the
+mma.sync 3xTF32 tensor-core kernel with truncating (3) and round-to-nearest (4) operand splits, and its sparse
+logit-Jacobian phase for one-electron queries / keys (5)) on the SAME random augmented operands against a float64 statement of the
 forward-Laplacian rule of ``softmax(q k^T / sqrt(d)) v``.  Operand-level, so that the tile-shape edge cases
 (n = 17, 32, 33, 48 ...) are tested without the conditioning of a wavefunction entering: the network-level parity tests
 in test_gpu_attention_nets.py cannot separate a kernel error from an ill-conditioned walker.
@@ -131,6 +132,8 @@ def test_attention_kernels_match_float64_rule(n, kernels, local_qk):
     H, d, W = 2, 64, 3
     dense, stored = _operands(n, H, d, W, local_qk, seed=100 + n)
     ref = torch.stack([rule_f64(dense[0][w], dense[1][w], dense[2][w]) for w in range(W)])
+    if local_qk and 3 in kernels:
+        kernels = kernels + (5,)      # the tensor-core kernel's sparse phase for one-electron q / k
     outs = {}
     for kern in kernels + (0,):
         rc, out = _run(kern, stored, n, H, d, W, local_qk)
