@@ -300,7 +300,7 @@ struct EpiUnit {
   float* out_b;
 };
 
-template <int ACT, int RES, bool CADD, bool PAIR>
+template <int ACT, int RES, bool CADD, bool PAIR, bool SHORT = false>
 __device__ __forceinline__ void epilogue_loop(const TcParams& p, uint32_t tlane0, int q, int sub, uint64_t* acc_full,
                                               uint64_t* acc_empty, int lane) {
   const float inv_sqrt2 = 0.70710678118654752440f;
@@ -524,6 +524,22 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& p, uint32_t tlane0
   }
 
   EpiUnit cur = find_unit(first, sub);
+  // short groups (C <= TC_CH: Local1 inputs, 5 rows): the unit's addend / residual operands travel one unit ahead too
+  // (r2: they were loaded row by row on demand -- a LapNet one-electron update layer took 800 us against 252 us for the
+  // same GEMM without a residual)
+  const bool short_ld = SHORT && LD && !chunked && C <= TC_CH && C > 1;   // SHORT: a separate kernel instantiation, so that
+  float sca[SHORT ? TC_CH : 1], srr[SHORT ? TC_CH : 1];                  // the main kernels' register allocation is untouched
+#define TC_SHORT_LOAD(u, cav, rrv)                                   \
+  {                                                                  \
+    uint32_t o_ = (u).fo;                                            \
+    _Pragma("unroll") for (int i_ = 0; i_ < (SHORT ? TC_CH : 1); ++i_, o_ += N) { \
+      if (i_ < C) {                                                  \
+        if (CADD) cav[i_] = (u).cadd_b[o_];                          \
+        if (RES) rrv[i_] = TC_LD_RES((u).res_b + o_);                \
+      }                                                              \
+    }                                                                \
+  }
+  if (short_ld && cur.item < limit) TC_SHORT_LOAD(cur, sca, srr)
   if (LD && chunked && cur.item < limit) {
     if (ACT != 0) TC_EDGE_LOAD(cur, ca0, rr0, caL, rrL)
 #pragma unroll
@@ -641,11 +657,14 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& p, uint32_t tlane0
         caL = n_caL;
         rrL = n_rrL;
       } else {
-        // short groups (value-only sampling path, Local1 inputs): row by row, operands loaded on demand
+        // short groups (value-only sampling path, Local1 inputs): row by row
+        float nca[SHORT ? TC_CH : 1], nrr[SHORT ? TC_CH : 1];
+        if (short_ld && have_nxt) TC_SHORT_LOAD(nxt, nca, nrr)
+#pragma unroll(SHORT ? TC_CH : 1)
         for (int c = 0; c < C; ++c) {
           float y = tmem_sum1(tcol + c);
           const uint32_t o = (uint32_t)c * N + fo;
-          if (CADD) y += cur.cadd_b[o];
+          if (CADD) y += short_ld ? sca[SHORT ? c : 0] : cur.cadd_b[o];
           if (ACT == 1) {
             if (c == 0) {
               th = tanhf(y + bias_f);
@@ -676,9 +695,18 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& p, uint32_t tlane0
           } else if (c == 0) {
             y += bias_f;
           }
-          if (RES == 1) y = (cur.res_b[o] + y) * inv_sqrt2;
-          if (RES == 2) y = cur.res_b[o] + y;
+          if (RES != 0) {
+            const float rres = short_ld ? srr[SHORT ? c : 0] : cur.res_b[o];
+            y = (RES == 1) ? (rres + y) * inv_sqrt2 : rres + y;
+          }
           if (f_ok) TC_ST_OUT(out_b + o, y);
+        }
+        if (short_ld) {
+#pragma unroll
+          for (int i = 0; i < (SHORT ? TC_CH : 1); ++i) {
+            sca[i] = nca[i];
+            srr[i] = nrr[i];
+          }
         }
       }
       cur = nxt;
@@ -690,6 +718,7 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& p, uint32_t tlane0
       else mbar_arrive(&acc_empty[buf]);
     }
   }
+#undef TC_SHORT_LOAD
 #undef TC_ROW
 #undef TC_TAIL_LOAD
 #undef TC_EDGE_LOAD
@@ -922,6 +951,7 @@ __device__ __forceinline__ uint32_t mapa_u32(const void* p, uint32_t cta) {
   return r;
 }
 
+template <bool SHORT>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
 k_dense_tc_pair(const __grid_constant__ CUtensorMap mapX0, const __grid_constant__ CUtensorMap mapX1,
                 const __grid_constant__ CUtensorMap mapWh, const __grid_constant__ CUtensorMap mapWl, TcParams p) {
@@ -1124,7 +1154,7 @@ k_dense_tc_pair(const __grid_constant__ CUtensorMap mapX0, const __grid_constant
     const int q = warp & 3;
     const int sub = (warp - 8) >> 2;
     const uint32_t tlane0 = tmem_base + ((uint32_t)(q * 32) << 16);
-#define TC_EPI(ACT, RES, CADD) epilogue_loop<ACT, RES, CADD, true>(p, tlane0, q, sub, acc_full, acc_empty, lane)
+#define TC_EPI(ACT, RES, CADD) epilogue_loop<ACT, RES, CADD, true, SHORT>(p, tlane0, q, sub, acc_full, acc_empty, lane)
     const int key = (p.act == 2) ? 16 : ((p.act ? 8 : 0) | (p.res_mode << 1) | (p.cadd ? 1 : 0));
     switch (key) {
       case 16: TC_EPI(2, 0, false); break;
@@ -1349,7 +1379,8 @@ int jq_launch_dense_tc(const JqDenseArgs& a, cudaStream_t st, bool* handled) {
   if (!attr_set.done[dev]) {
     cudaError_t e = cudaFuncSetAttribute(k_dense_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT);
     JQ_REQUIRE(e == cudaSuccess, JQ_ERR_CUDA, "dense_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-    e = cudaFuncSetAttribute(k_dense_tc_pair, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT);
+    e = cudaFuncSetAttribute(k_dense_tc_pair<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_dense_tc_pair<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT);
     JQ_REQUIRE(e == cudaSuccess, JQ_ERR_CUDA, "dense_tc: cudaFuncSetAttribute (pair): %s", cudaGetErrorString(e));
     attr_set.done[dev] = true;
   }
@@ -1494,7 +1525,11 @@ int jq_launch_dense_tc(const JqDenseArgs& a, cudaStream_t st, bool* handled) {
   double R = (double)a.G * a.C;
   jq_prof_work(2.0 * R * kt * a.N, 4.0 * R * (kt + a.N * (a.res ? 2 : 1)));
   if (pair) {
-    JQ_LAUNCH(k_dense_tc_pair, dim3((unsigned)(sm_count / 2 * 2)), dim3(TC_THREADS), smem_bytes, st, mX0, mX1, mWh, mWl, p);
+    // short groups (Local1 inputs: 5 rows) with an addend or a residual: the instantiation that carries those operands
+    // one group ahead (profile label: the same kernel name)
+    const bool short_epi = p.C > 1 && p.C <= TC_CH && (a.res != nullptr || a.cadd != nullptr);
+    if (short_epi) JQ_LAUNCH(k_dense_tc_pair<true>, dim3((unsigned)(sm_count / 2 * 2)), dim3(TC_THREADS), smem_bytes, st, mX0, mX1, mWh, mWl, p);
+    else JQ_LAUNCH(k_dense_tc_pair<false>, dim3((unsigned)(sm_count / 2 * 2)), dim3(TC_THREADS), smem_bytes, st, mX0, mX1, mWh, mWl, p);
   } else {
     JQ_LAUNCH(k_dense_tc, dim3((unsigned)grid), dim3(TC_THREADS), smem_bytes, st, mX0, mX1, mWh, mWl, p);
   }
