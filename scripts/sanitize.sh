@@ -16,3 +16,6 @@ $S --tool racecheck --error-exitcode 7 python -m pytest tests/test_gpu_ferminet.
 $S --tool racecheck --error-exitcode 7 python -m pytest tests/test_gpu_attention_nets.py tests/test_gpu_sampling.py -m gpu -q -x \
    -k "small or sampling" > "$OUT/racecheck_nets2.log" 2>&1
 grep -H -E "ERROR SUMMARY|RACECHECK SUMMARY" "$OUT"/*.log
+$S --tool initcheck --error-exitcode 7 python -m pytest tests/test_gpu_ferminet.py tests/test_gpu_solid.py tests/test_gpu_attention_nets.py \
+   tests/test_gpu_gradients.py -m gpu -q -x -k "small or cubic_h2 or Ar or options" > "$OUT/initcheck.log" 2>&1
+grep -H -E "ERROR SUMMARY" "$OUT/initcheck.log"
