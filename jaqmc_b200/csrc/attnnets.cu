@@ -301,6 +301,24 @@ int jq_psiformer_forward(const jaqmc_psiformer_config* c, const jaqmc_psiformer_
   }
   for (int l = 0; l < d.L; ++l) {
     // attention block: x = x + out(MHA(LN0(x)))            (pre-LN; post / null: MHA(x))
+    static const bool dense_l0 = getenv("JAQMC_B200_PSIFORMER_DENSE_LAYER0") != nullptr;   // A/B switch
+    if (l == 0 && track && !dense_l0) {
+      // The first block sees the projected one-electron features: electron i's row depends on r_i only (Local1, 5 rows
+      // per group instead of 3n + 2).  LayerNorm and the q / k / v projections act row-wise, so they run on the 5-row
+      // groups (r2: 44 -> 5 rows at N2 for one LayerNorm and three dense launches); q and k enter the attention kernel
+      // in that form (its one-electron phase), v is expanded first.  The residual uses the expanded x as before.
+      const float* xin = b.x0;
+      if (c->layer_norm_mode == JAQMC_LAYERNORM_PRE) {
+        if ((rc = jq_launch_layernorm_fl(b.x0, p->ln0_scale[l], p->ln0_bias[l], b.ln, G, d.C1, hid, eps, st))) return rc;
+        xin = b.ln;
+      }
+      if ((rc = dense(xin, d.C1, G, n, p->q_kernel[l], hid, hid, 0, p->q_bias[l], 0, nullptr, 0, b.q, b.wscr, st))) return rc;
+      if ((rc = dense(xin, d.C1, G, n, p->k_kernel[l], hid, hid, 0, p->k_bias[l], 0, nullptr, 0, b.k, b.wscr, st))) return rc;
+      if ((rc = dense(xin, d.C1, G, n, p->v_kernel[l], hid, hid, 0, p->v_bias[l], 0, nullptr, 0, b.m1, b.wscr, st))) return rc;
+      if ((rc = jq_launch_densify_local1(b.m1, b.v, W, n, hid, st))) return rc;
+      JqAttnOperand q = {b.q, d.C1, hid, 0}, k = {b.k, d.C1, hid, 0}, v = {b.v, C, hid, 0};
+      if ((rc = jq_launch_attention_fl(q, k, v, b.att, hid, W, n, d.H, d.dh, track, st))) return rc;
+    } else {
     const float* xin = x;
     if (c->layer_norm_mode == JAQMC_LAYERNORM_PRE) {
       if ((rc = jq_launch_layernorm_fl(x, p->ln0_scale[l], p->ln0_bias[l], b.ln, G, C, hid, eps, st))) return rc;
@@ -311,6 +329,7 @@ int jq_psiformer_forward(const jaqmc_psiformer_config* c, const jaqmc_psiformer_
     if ((rc = dense(xin, C, G, n, p->v_kernel[l], hid, hid, 0, p->v_bias[l], 0, nullptr, 0, b.v, b.wscr, st))) return rc;
     JqAttnOperand q = {b.q, C, hid, 0}, k = {b.k, C, hid, 0}, v = {b.v, C, hid, 0};
     if ((rc = jq_launch_attention_fl(q, k, v, b.att, hid, W, n, d.H, d.dh, track, st))) return rc;
+    }
     if ((rc = dense(b.att, C, G, n, p->out_kernel[l], hid, hid, 0, p->out_bias[l], 0, x, 2, xn, b.wscr, st))) return rc;
     {
       float* t = x;
