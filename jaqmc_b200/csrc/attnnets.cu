@@ -158,6 +158,15 @@ int jq_lapnet_forward(const jaqmc_lapnet_config* c, const jaqmc_lapnet_params* p
   } else {
     cudaMemcpyAsyncD2D(hd, hs, sizeof(float) * G * hid, st);
   }
+  // The first value projection sees hd0 = hs0, still a one-electron (5-row) tensor: project in that form and expand the
+  // result (r2; 1.64 -> 0.27 + 0.5 ms at N2).  Not with use_layernorm (the value LayerNorm comes first).
+  static const bool dense_v0 = getenv("JAQMC_B200_LAPNET_DENSE_VALUE0") != nullptr;   // A/B switch
+  const bool local_v0 = track && !c->use_layernorm && !dense_v0;
+  if (local_v0) {
+    if ((rc = dense(hs, d.C1, G, n, p->value_kernel[0], hid, hid, 0, p->value_bias[0], 0, nullptr, 0, b.att, b.wscr, st)))
+      return rc;
+    if ((rc = jq_launch_densify_local1(b.att, b.v, W, n, hid, st))) return rc;
+  }
   for (int l = 0; l < d.L; ++l) {
     const float* hs_in = hs;
     if (c->use_layernorm) {   // project_qk_stream: qk_layernorm first (_backbone.py:121)
@@ -186,7 +195,8 @@ int jq_lapnet_forward(const jaqmc_lapnet_config* c, const jaqmc_lapnet_params* p
         return rc;
       v_in = b.ln_d;
     }
-    if ((rc = dense(v_in, d.C, G, n, p->value_kernel[l], hid, hid, 0, p->value_bias[l], 0, nullptr, 0, b.v, b.wscr, st)))
+    if (!(l == 0 && local_v0) &&
+        (rc = dense(v_in, d.C, G, n, p->value_kernel[l], hid, hid, 0, p->value_bias[l], 0, nullptr, 0, b.v, b.wscr, st)))
       return rc;
     JqAttnOperand q = {b.q[l], d.C1, hid, 0}, k = {b.k[l], d.C1, hid, 0}, v = {b.v, d.C, hid, 0};
     if ((rc = jq_launch_attention_fl(q, k, v, b.att, hid, W, n, d.H, d.dh, track, st))) return rc;
