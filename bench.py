@@ -557,7 +557,8 @@ def run_ours(args):
         tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
         if os.path.exists(tpath):
             with open(tpath) as f:
-                traffic = json.load(f).get(f"{kname}@{args.workload}@{W // world}", {}).get("dram_bytes")
+                # the capture is keyed by the kernel's base name (template arguments of the instantiation dropped)
+                traffic = json.load(f).get(f"{kname.split('<')[0]}@{args.workload}@{W // world}", {}).get("dram_bytes")
         tensor_kernel = kname.startswith("k_dense_tc")
         if v["flops"] > 0 and tensor_kernel:
             # 3xTF32: three tensor-core products per multiply-add; TF32 runs at half the bf16 rate.  The kernel is timed
