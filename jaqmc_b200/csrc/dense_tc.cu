@@ -1355,7 +1355,9 @@ static bool pair_plan(const JqDenseArgs& a, int sm_count, TcParams* p, int* smem
   {
     static const int lag_env = getenv("JAQMC_B200_TC_LAG") ? atoi(getenv("JAQMC_B200_TC_LAG")) : 0;   // tuning switch
     static const int burst_env = getenv("JAQMC_B200_TC_BURST") ? atoi(getenv("JAQMC_B200_TC_BURST")) : 0;
-    p->burst = (burst_env >= 1 && burst_env <= 4) ? burst_env : 1;
+    // the producer waits for `burst` free stages at once: more than stages - 1 can never be free together (r2: burst = 4
+    // with three stages hung the kernel until the harness killed it)
+    p->burst = (burst_env >= 1 && burst_env <= 4 && burst_env <= stages - 1) ? burst_env : 1;
     p->lag = (lag_env >= 1 && lag_env + 2 <= stages) ? lag_env : TCP_LAG;   // measured r1s: 2 and 3 within noise, 1 slower
   }
   p->stage_tx = (wb > 1 ? wb * a.n_sub * a.C : Hp) * 128;
