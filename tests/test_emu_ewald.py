@@ -56,3 +56,36 @@ def test_madelung_nacl():
     e = float(ew.energy(el, at, ch, _rt=rt)[0])
     madelung = e * (a / 2)  # nearest-neighbour distance a/2, one ion pair
     assert abs(madelung - (-1.74756)) < 1e-4, madelung
+
+
+def madelung_cases():
+    """The three known answers of the reference (tests/estimator/ewald_test.py:72-152): anions as unit-charge "electrons",
+    cations as atoms; energies per formula unit in units where the quoted constants apply directly."""
+    L = 2.0
+    fcc = (np.ones((3, 3)) - np.eye(3)) * L / 2
+    conv = (np.ones((3, 3)) - 2 * np.eye(3)) @ fcc                       # cubic conventional cell, 4 NaCl units
+    cat4 = np.array([[0.0, 0.0, 0.0], [0.0, L / 2, L / 2], [L / 2, 0.0, L / 2], [L / 2, L / 2, 0.0]])
+    an4 = np.array([[L / 2, L / 2, L / 2], [L / 2, 0.0, 0.0], [0.0, L / 2, 0.0], [0.0, 0.0, L / 2]])
+    Lc = 4 / np.sqrt(3)
+    fcc_c = (np.ones((3, 3)) - np.eye(3)) * Lc / 2
+    return {
+        "nacl_primitive": (fcc, np.array([[L / 2, L / 2, L / 2]]), np.zeros((1, 3)), np.array([1.0]), 1, -1.74756),
+        "nacl_conventional": (conv, an4, cat4, np.ones(4), 4, -1.74756),
+        "caf2": (fcc_c, np.array([[Lc / 4, Lc / 4, Lc / 4], [Lc / 4, -Lc / 4, Lc / 4]]), np.zeros((1, 3)), np.array([2.0]), 1,
+                 -5.03879),
+    }
+
+
+def check_madelung(rt, name, device="cpu"):
+    lat, el, at, ch, units, want = madelung_cases()[name]
+    ew = EwaldSum(lat, device=device)
+    f32 = lambda a: torch.as_tensor(np.asarray(a), dtype=torch.float32).to(device)  # noqa: E731
+    e = float(ew.energy(f32(el)[None], f32(at), f32(ch), _rt=rt)[0])
+    assert abs(e / units - want) < 1e-4, (name, e / units)
+    ref = OE.solid_potential_energy(OE.EwaldSum(lat), el, at, ch)       # the oracle on the same system
+    assert abs(e - ref) < 2e-5 * max(1.0, abs(ref))
+
+
+@pytest.mark.parametrize("name", ["nacl_primitive", "nacl_conventional", "caf2"])
+def test_madelung_constants(name):
+    check_madelung(H.emu_runtime(), name)
