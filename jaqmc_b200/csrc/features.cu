@@ -167,9 +167,56 @@ __global__ void k_coulomb(const float* __restrict__ el, const float* __restrict_
   }
 }
 
+#ifndef JAQMC_HOST_EMU
+// One warp per walker (r2): the thread-per-walker kernel above walks n (n - 1) / 2 + n A reciprocal square roots serially,
+// 25 us of pure latency at any batch size -- visible in the 512-walker shard of the 8-GPU run.  Lanes take the
+// electron-electron pairs (row-major upper triangle), the electron-nucleus pairs and the nucleus-nucleus pairs in
+// strides of 32; the lane sums are combined by a fixed-order shuffle tree.
+__global__ void __launch_bounds__(256) k_coulomb_warp(const float* __restrict__ el, const float* __restrict__ atoms,
+                                                      const float* __restrict__ charges, int W, int n, int A,
+                                                      float* __restrict__ e_pot) {
+  const int lane = threadIdx.x & 31;
+  const long long w = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (w >= W) return;
+  const float* e = el + w * n * 3;
+  float v = 0.f;
+  const int npair = n * (n - 1) / 2;
+  for (int q = lane; q < npair; q += 32) {
+    // q -> (i, j), i < j: row i starts at i (2n - i - 1) / 2
+    int i = (int)floorf(((float)(2 * n - 1) - sqrtf((float)((2 * n - 1) * (2 * n - 1) - 8 * q))) * 0.5f);
+    while (i * (2 * n - i - 1) / 2 > q) --i;
+    while ((i + 1) * (2 * n - i - 2) / 2 <= q) ++i;
+    const int j = i + 1 + (q - i * (2 * n - i - 1) / 2);
+    const float dx = e[i * 3] - e[j * 3], dy = e[i * 3 + 1] - e[j * 3 + 1], dz = e[i * 3 + 2] - e[j * 3 + 2];
+    v += 1.0f / sqrtf(dx * dx + dy * dy + dz * dz);
+  }
+  for (int q = lane; q < n * A; q += 32) {
+    const int i = q / A, I = q - i * A;
+    const float dx = e[i * 3] - atoms[I * 3], dy = e[i * 3 + 1] - atoms[I * 3 + 1], dz = e[i * 3 + 2] - atoms[I * 3 + 2];
+    v -= charges[I] / sqrtf(dx * dx + dy * dy + dz * dz);
+  }
+  for (int q = lane; q < A * A; q += 32) {
+    const int I = q / A, J = q - I * A;
+    if (J > I) {
+      const float dx = atoms[I * 3] - atoms[J * 3], dy = atoms[I * 3 + 1] - atoms[J * 3 + 1],
+                  dz = atoms[I * 3 + 2] - atoms[J * 3 + 2];
+      v += charges[I] * charges[J] / sqrtf(dx * dx + dy * dy + dz * dz);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  if (lane == 0) e_pot[w] = v;
+}
+#endif
+
 int jq_launch_coulomb(const float* electrons, const float* atoms, const float* charges, int W, int n, int A,
                       float* e_pot, cudaStream_t st) {
   if (W <= 0) return JQ_OK;
+#ifndef JAQMC_HOST_EMU
+  JQ_LAUNCH(k_coulomb_warp, dim3(jq_cdiv(W, 8)), dim3(256), 0, st, electrons, atoms, charges, W, n, A, e_pot);
+  JQ_CHECK_LAUNCH();
+  return JQ_OK;
+#endif
   JQ_LAUNCH(k_coulomb, dim3(jq_cdiv(W, 128)), dim3(128), 0, st, electrons, atoms, charges, W, n, A, e_pot);
   JQ_CHECK_LAUNCH();
   return JQ_OK;

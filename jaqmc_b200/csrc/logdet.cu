@@ -1333,7 +1333,8 @@ __global__ void __launch_bounds__(256) k_logdet_combine_warp(const float* __rest
     const float wd = term * (1.0f / S);   // lane d: weight of determinant d
     // per-determinant |grad|^2, lane d keeps determinant d's
     float g2_mine = 0.f;
-    for (int d = 0; d < D; ++d) {
+#pragma unroll 4
+    for (int d = 0; d < D; ++d) {   // (unrolled: the loads of four determinants in flight; the kernel is pure latency)
       float part = 0.f;
       for (int k = lane; k < K; k += 32) {
         const float v = g[d * K + k];
@@ -1350,6 +1351,7 @@ __global__ void __launch_bounds__(256) k_logdet_combine_warp(const float* __rest
     for (int k0 = 0; k0 < K; k0 += 32) {
       const int k = k0 + lane;
       float gk = 0.f;
+#pragma unroll 4
       for (int d = 0; d < D; ++d) {
         const float wdd = __shfl_sync(full, wd, d);
         if (k < K) gk = fmaf(wdd, g[d * K + k], gk);
