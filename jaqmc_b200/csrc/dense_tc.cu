@@ -48,6 +48,17 @@ constexpr int TC_SMEM_LIMIT = 227 * 1024;
 constexpr int TC_SMEM_EXTRA = 1024 /*align*/ + 256 /*barriers*/;
 constexpr int TC_THREADS = 512;
 constexpr int TC_TMEM_COLS = 512;  // 2 buffers x {main, cross} x 128 columns
+// Measurement switch (r2, never shipped): -DJQ_TC_FAST_TANH replaces tanhf by the 2^-11-accurate MUFU tanh to measure how
+// much of the value-only epilogue is tanhf (sampling path).
+#ifdef JQ_TC_FAST_TANH
+__device__ __forceinline__ float jq_tc_tanh(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+#else
+__device__ __forceinline__ float jq_tc_tanh(float x) { return tanhf(x); }
+#endif
 // A/B (r2): cache-streaming hints on the epilogue's global traffic (the residual is read once, the output written once).
 // Measured with -DJQ_TC_STREAM_HINTS, same box, FermiNet-N2: 16.887 (off) / 16.894 (on) / 16.869 (off) ms per
 // evaluation -- no effect; left off.
@@ -435,7 +446,7 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& p, uint32_t tlane0
                 float y = v[i] + v2[i];
                 if (CADD) y += cav[s][i];
                 y += bias_f;
-                if (ACT == 1) y = tanhf(y);
+                if (ACT == 1) y = jq_tc_tanh(y);
                 if (RES == 1) y = (rrv[s][i] + y) * inv_sqrt2;
                 if (RES == 2) y = rrv[s][i] + y;
                 if (lane_ok) p.out[(size_t)gidx[s][i] * N + f] = y;
@@ -601,7 +612,7 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& p, uint32_t tlane0
           x += bias_f;
           float o0;
           if (ACT == 1) {
-            th = tanhf(x);
+            th = jq_tc_tanh(x);
             d1 = 1.0f - th * th;
             o0 = th;
           } else {
@@ -667,7 +678,7 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& p, uint32_t tlane0
           if (CADD) y += short_ld ? sca[SHORT ? c : 0] : cur.cadd_b[o];
           if (ACT == 1) {
             if (c == 0) {
-              th = tanhf(y + bias_f);
+              th = jq_tc_tanh(y + bias_f);
               d1 = 1.0f - th * th;
               y = th;
             } else if (c == C - 1) {
