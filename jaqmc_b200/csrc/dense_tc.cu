@@ -401,12 +401,7 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& p, uint32_t tlane0
       if (nvalid > g_count) nvalid = g_count;
       if (f_raw - lane >= p.N_out) nvalid = 0;     // this warp's 32 features lie beyond the layer
       const int g_base = (int)w * p.n_tot + p.j0 + gsub_first;   // group of gi = 0
-      // group index of gi: consecutive inside a walker's sub-range; a batched tile steps to the next walker every n_sub
-      auto group_at = [&](int gi) -> int {
-        if (!batched) return g_base + gi;
-        const uint32_t wl = (uint32_t)gi / (uint32_t)p.n_sub;
-        return g_base + (int)wl * p.n_tot + (gi - (int)wl * p.n_sub);
-      };
+      // (group index of gi: consecutive inside a walker's sub-range; a batched tile steps to the next walker every n_sub)
       if (nvalid > 0 && f != f_cached) {       // per-feature constants (the feature block changes with the item)
         f_cached = f;
         bias_f = p.bias ? p.bias[f] : 0.f;
@@ -423,12 +418,33 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& p, uint32_t tlane0
         for (int s = 0; s < VS; ++s) {
           const int gc = gs + s * TC_CH;
           if (gc < nvalid) {
+            // walker-local position of the chunk's first group: one division per chunk (r2: two per group before --
+            // the one-row-per-group epilogue is instruction-bound), then counted up; the addend row is the walker's
+            int wl = batched ? (int)((uint32_t)gc / (uint32_t)p.n_sub) : 0;
+            int el = gc - wl * p.n_sub;
+            // addend row = true walker of the group.  Batched tiles: w + wl.  Otherwise (one walker per tile, or a flat
+            // launch whose single "walker" spans all groups) the groups are consecutive: counted up with period
+            // n_tot_true from the chunk's first group
+            int wk = 0, ek = 0;
+            if (CADD && !batched) {
+              wk = (int)((uint32_t)(g_base + gc) / (uint32_t)p.n_tot_true);
+              ek = g_base + gc - wk * p.n_tot_true;
+            }
 #pragma unroll
             for (int i = 0; i < TC_CH; ++i) {
               const bool ok = gc + i < nvalid;
-              gidx[s][i] = group_at(ok ? gc + i : 0);
-              if (CADD) cav[s][i] = ok ? p.cadd[(size_t)((uint32_t)gidx[s][i] / (uint32_t)p.n_tot_true) * N + f] : 0.f;
+              gidx[s][i] = ok ? g_base + wl * p.n_tot + el : g_base;
+              if (CADD) cav[s][i] = ok ? p.cadd[(size_t)(batched ? (int)w + wl : wk) * N + f] : 0.f;
               if (RES) rrv[s][i] = ok ? p.res[(size_t)gidx[s][i] * N + f] : 0.f;
+              ++el;
+              if (batched && el == p.n_sub) {
+                el = 0;
+                ++wl;
+              }
+              if (CADD && !batched && ++ek == p.n_tot_true) {
+                ek = 0;
+                ++wk;
+              }
             }
           }
         }
