@@ -1113,6 +1113,119 @@ __global__ void __launch_bounds__(256) k_logdet_value_warp(const float* __restri
 }
 #endif
 
+#ifndef JAQMC_HOST_EMU
+// ------------------------------------------------------------------------------------------------
+// slogdet + forward-Laplacian rule for TINY matrices (n <= 4: Li, LiH ...; r2): one THREAD per determinant, everything
+// in registers.  The half-warp kernel above keeps 16 lanes per determinant and ran at 252 us for the 65536 3 x 3
+// matrices of the Li configuration (3 of 16 lanes busy).  Gauss-Jordan with partial pivoting (row swaps), sign =
+// (-1)^swaps prod sign(pivot), log|det| = log prod |pivot| in double; then per derivative slab M = A^-1 dA_c,
+// tr M and tr M^2 = sum_ij M_ij M_ji.  The 16 determinants of a walker are adjacent threads: a row (j, c) of the slab
+// is D * n contiguous floats.
+// ------------------------------------------------------------------------------------------------
+template <int N>
+__global__ void __launch_bounds__(128) k_logdet_tiny(const float* __restrict__ orb, int D, int C, long long M,
+                                                     float* __restrict__ det_sign, float* __restrict__ det_logabs,
+                                                     float* __restrict__ det_grad, float* __restrict__ det_lap) {
+  const long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // (walker, determinant)
+  if (m >= M) return;
+  const long long w = m / D;
+  const int d = (int)(m - w * D);
+  const int DN = D * N, K = C - 2, KT = C - 1;
+  const float* ow = orb + (w * N) * (long long)C * DN + d * N;   // (j, c, i) at ow[(j * C + c) * DN + i]
+  float a[N][N], b[N][N];
+#pragma unroll
+  for (int j = 0; j < N; ++j)
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      a[j][i] = ow[(long long)j * C * DN + i];
+      b[j][i] = (i == j) ? 1.0f : 0.f;
+    }
+  float sg = 1.0f;
+  double mant = 1.0;
+  int expo = 0;
+#pragma unroll
+  for (int p = 0; p < N; ++p) {
+    // pivot: largest |a[r][p]|, r >= p (first one on ties); rows are swapped with predicated moves (N is tiny)
+    int r = p;
+    float best = fabsf(a[p][p]);
+#pragma unroll
+    for (int q = p + 1; q < N; ++q)
+      if (fabsf(a[q][p]) > best) {
+        best = fabsf(a[q][p]);
+        r = q;
+      }
+#pragma unroll
+    for (int q = p + 1; q < N; ++q)
+      if (q == r) {
+#pragma unroll
+        for (int c = 0; c < N; ++c) {
+          float t = a[p][c]; a[p][c] = a[q][c]; a[q][c] = t;
+          t = b[p][c]; b[p][c] = b[q][c]; b[q][c] = t;
+        }
+        sg = -sg;
+      }
+    const float pv = a[p][p];
+    if (pv < 0.f) sg = -sg;
+    if (pv == 0.f) sg = 0.f;
+    {
+      int e;
+      mant *= (double)frexpf(fabsf(pv), &e);
+      expo += e;
+    }
+    const float pinv = 1.0f / pv;
+#pragma unroll
+    for (int c = 0; c < N; ++c) {
+      a[p][c] *= pinv;
+      b[p][c] *= pinv;
+    }
+#pragma unroll
+    for (int q = 0; q < N; ++q)
+      if (q != p) {
+        const float f = a[q][p];
+#pragma unroll
+        for (int c = 0; c < N; ++c) {
+          a[q][c] = fmaf(-f, a[p][c], a[q][c]);
+          b[q][c] = fmaf(-f, b[p][c], b[q][c]);
+        }
+      }
+  }
+  det_sign[m] = sg;
+  det_logabs[m] = (float)(log(mant) + (double)expo * 0.69314718055994530942);
+  // b = A^-1 (A[j][i]: row = electron j, column = orbital i): b[i][j]
+  float t2 = 0.f, trl = 0.f;
+  float* gout = det_grad + m * (long long)K;
+  for (int kk = 0; kk < KT; ++kk) {
+    float da[N][N], mm[N][N];
+#pragma unroll
+    for (int j = 0; j < N; ++j)
+#pragma unroll
+      for (int i = 0; i < N; ++i) da[j][i] = ow[((long long)j * C + 1 + kk) * DN + i];
+    float tr = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int x = 0; x < N; ++x)
+#pragma unroll
+      for (int y = 0; y < N; ++y) {
+        float acc = 0.f;
+#pragma unroll
+        for (int j = 0; j < N; ++j) acc = fmaf(b[x][j], da[j][y], acc);
+        mm[x][y] = acc;
+        if (x == y) tr += acc;
+      }
+#pragma unroll
+    for (int x = 0; x < N; ++x)
+#pragma unroll
+      for (int y = 0; y < N; ++y) s2 = fmaf(mm[x][y], mm[y][x], s2);
+    if (kk < K) {
+      gout[kk] = tr;
+      t2 += s2;
+    } else {
+      trl = tr;
+    }
+  }
+  det_lap[m] = trl - t2;
+}
+#endif
+
 // Value-only slogdet of orb [W][n][D*n] (n <= 32), optionally times the isotropic envelope of (electrons, atoms) first.
 bool jq_logdet_value_env_eligible(int n, int A, int env_type) {
 #ifdef JAQMC_HOST_EMU
@@ -1173,6 +1286,19 @@ int jq_launch_logdet(const float* orb, int W, int n, int D, int track, float* de
     else
       JQ_LAUNCH(k_logdet_mma<false>, dim3((unsigned)jq_cdiv(MT, 8)), dim3(256), 0, st, orb, n, D, C, MT, det_sign,
                 det_logabs, det_grad, det_lap);
+    JQ_CHECK_LAUNCH();
+    return JQ_OK;
+  }
+  static const bool no_tiny = getenv("JAQMC_B200_LOGDET_NO_TINY") != nullptr;   // A/B switch
+  if (track && n <= 4 && !no_tiny) {
+    // thread per determinant (n <= 4)
+    const long long MT = (long long)W * D;
+    jq_prof_work((double)MT * (2.0 * n * n * n * ((C - 1) * 2 + 1)), 4.0 * (double)MT * C * n * n);
+    const dim3 grid((unsigned)jq_cdiv(MT, 128)), block(128);
+    if (n == 1) JQ_LAUNCH(k_logdet_tiny<1>, grid, block, 0, st, orb, D, C, MT, det_sign, det_logabs, det_grad, det_lap);
+    else if (n == 2) JQ_LAUNCH(k_logdet_tiny<2>, grid, block, 0, st, orb, D, C, MT, det_sign, det_logabs, det_grad, det_lap);
+    else if (n == 3) JQ_LAUNCH(k_logdet_tiny<3>, grid, block, 0, st, orb, D, C, MT, det_sign, det_logabs, det_grad, det_lap);
+    else JQ_LAUNCH(k_logdet_tiny<4>, grid, block, 0, st, orb, D, C, MT, det_sign, det_logabs, det_grad, det_lap);
     JQ_CHECK_LAUNCH();
     return JQ_OK;
   }
