@@ -455,7 +455,12 @@ __global__ void __launch_bounds__(256, 2) k_logdet_mma(const float* __restrict__
 // log|det| = log prod |pivot| in double.   Phase 2: the traces, see inside.
 // Shared: invp[DB][n*16+4] | scr[DB][MS]
 // ------------------------------------------------------------------------------------------------
-template <int NS>
+// ST (r2, late): the derivative slabs of the warp's two determinants (n rows of 2n contiguous floats per slab) are
+// staged by the warp itself with 16-byte cp.async copies into a private double buffer, NS slabs (one pass) ahead, instead
+// of 14 dependent 4-byte global loads per lane and slab: no global-load latency on the critical path at 4 warps per
+// scheduler.  Needs n and D even (16-byte source alignment); same FMA order, results bit-identical to ST = false.
+// Shared (ST): ... | ring[8 warps][2][NS][n][2n]
+template <int NS, bool ST>
 __global__ void __launch_bounds__(256, 2) k_logdet_small(const float* __restrict__ orb, int n, int D, int C, int DB,
                                                           float* __restrict__ det_sign, float* __restrict__ det_logabs,
                                                           float* __restrict__ det_grad, float* __restrict__ det_lap) {
@@ -479,6 +484,44 @@ __global__ void __launch_bounds__(256, 2) k_logdet_small(const float* __restrict
       const int d = dbase + half;
       const bool on = d < db;
       bool used = !on || hl >= n;
+      // ---- ST: per-warp staging of the derivative slabs of determinants (dbase, dbase + 1)
+      const int lane = tid & 31;
+      const int n2 = 2 * n;
+      const int nch = n * (n >> 1);   // 16-byte chunks per slab: n rows of 2n floats
+      int soff[4];                    // source offset (floats) of this lane's chunks q = lane + 32 i within a slab
+      uint32_t ring_w = 0;            // shared address of this warp's ring [2][NS][n][2n]
+      const float* ring_f = nullptr;
+      const float* owd = ow + dbase * n;
+      if (ST) {
+        const int MSr = nn + ((n - nn) % 32 + 32) % 32;
+        float* rf = Jc + (size_t)DB * IS + (size_t)DB * NS * MSr + (size_t)warp * (2 * NS * n * n2);
+        ring_f = rf;
+        ring_w = (uint32_t)__cvta_generic_to_shared(rf);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int q = lane + 32 * i;
+          const int j = q / (n >> 1), part = q - j * (n >> 1);
+          soff[i] = j * C * DN + part * 4;
+        }
+      }
+      auto stage_pass = [&](int it) {   // slabs it * NS ... of this warp's determinant pair -> buffer it & 1
+#pragma unroll
+        for (int s2i = 0; s2i < NS; ++s2i) {
+          const int kq = it * NS + s2i;
+          if (kq < KT) {
+            const float* src = owd + (long long)(1 + kq) * DN;
+            const uint32_t dst = ring_w + 4u * (unsigned)((((it & 1) * NS + s2i) * n) * n2);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int q = lane + 32 * i;
+              if (q < nch)
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 16u * (unsigned)q), "l"(src + soff[i]) : "memory");
+            }
+          }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+      };
+      if (ST) stage_pass(0);   // in flight during the inversion
       float a[LD_NP], bi[LD_NP];
 #pragma unroll
       for (int c = 0; c < LD_NP; ++c) {
@@ -569,12 +612,26 @@ __global__ void __launch_bounds__(256, 2) k_logdet_small(const float* __restrict
         // NS slabs per pass over A^-1: each float4 of the inverse read from shared memory feeds NS columns.
         for (int kk = 0; kk < KT; kk += NS) {
           float col[NS][LD_NP];
+          if (ST) {
+            const int it = kk / NS;
+            stage_pass(it + 1);   // the other buffer: its readers finished before the __syncwarp that ended pass it - 1
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+            __syncwarp();
+            const float* stg = ring_f + (size_t)((it & 1) * NS) * n * n2 + half * n + (hl < n ? hl : 0);
+#pragma unroll
+            for (int s = 0; s < NS; ++s) {
+              const bool sv = act && kk + s < KT;
+#pragma unroll
+              for (int j = 0; j < LD_NP; ++j) col[s][j] = (sv && j < n) ? stg[(s * n + j) * n2] : 0.f;
+            }
+          } else {
 #pragma unroll
           for (int s = 0; s < NS; ++s) {
             const bool sv = act && kk + s < KT;
             const float* oc = ocol + (long long)(1 + kk + s) * DN;
 #pragma unroll
             for (int j = 0; j < LD_NP; ++j) col[s][j] = (sv && j < n) ? oc[(long long)j * C * DN] : 0.f;
+          }
           }
           float m[NS][LD_NP];
           float dg[NS];
@@ -636,6 +693,10 @@ __global__ void __launch_bounds__(256, 2) k_logdet_small(const float* __restrict
           }
         }
         if (on && hl == 0) det_lap[w * D + d0 + d] = trl - t2acc;
+        if (ST) {
+          asm volatile("cp.async.wait_group 0;" ::: "memory");
+          __syncwarp();
+        }
       }
     }
   }
@@ -1308,24 +1369,36 @@ int jq_launch_logdet(const float* orb, int W, int n, int D, int track, float* de
     const size_t MS = nn + (size_t)((((int)n - (int)nn) % 32 + 32) % 32);
     static const int ns_env = getenv("JAQMC_B200_LOGDET_SLABS") ? atoi(getenv("JAQMC_B200_LOGDET_SLABS")) : 2;
     const int NS = ns_env == 1 ? 1 : (ns_env == 3 ? 3 : 2);
-    const size_t smem = sizeof(float) * ((size_t)DB * (n * LD_NP + 4) + (size_t)DB * MS * NS) + 64;
+    // staged slabs (cp.async, per-warp double buffer): n and D even, 16-byte aligned orbital buffer, default NS
+    static const bool sync_loads = getenv("JAQMC_B200_LOGDET_SYNC_LOADS") != nullptr;   // A/B switch
+    const bool staged = NS == 2 && !sync_loads && n >= 6 && (n % 2) == 0 && (D % 2) == 0 &&
+                        (reinterpret_cast<uintptr_t>(orb) & 15) == 0;
+    const size_t smem = sizeof(float) * ((size_t)DB * (n * LD_NP + 4) + (size_t)DB * MS * NS +
+                                         (staged ? (size_t)8 * 2 * NS * n * 2 * n : 0)) + 64;
     void (*kern)(const float*, int, int, int, int, float*, float*, float*, float*) =
-        NS == 1 ? k_logdet_small<1> : NS == 3 ? k_logdet_small<3> : k_logdet_small<2>;   // for the attribute call only
+        staged ? k_logdet_small<2, true>
+               : NS == 1 ? k_logdet_small<1, false> : NS == 3 ? k_logdet_small<3, false> : k_logdet_small<2, false>;   // for the attribute call only
     if (smem > 48 * 1024) {
-      static JqPerDeviceFlag attr_set[4];
+      static JqPerDeviceFlag attr_set[5];
       const int dev = jq_current_device();
-      if (!attr_set[NS].done[dev]) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+      const int slot = staged ? 4 : NS;
+      if (!attr_set[slot].done[dev]) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024);
         JQ_REQUIRE(e == cudaSuccess, JQ_ERR_CUDA, "logdet: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-        attr_set[NS].done[dev] = true;
+        attr_set[slot].done[dev] = true;
       }
     }
     const long long blocks = (long long)W * ((D + DB - 1) / DB);
     jq_prof_work((double)W * D * (2.0 * n * n * n * ((C - 1) * 2 + 1)), 4.0 * (double)W * D * C * n * n);
-    // launched by name: JQ_LAUNCH labels the profile entry with its first argument
-    if (NS == 1) JQ_LAUNCH(k_logdet_small<1>, dim3((unsigned)blocks), dim3(256), smem, st, orb, n, D, C, DB, det_sign, det_logabs, det_grad, det_lap);
-    else if (NS == 3) JQ_LAUNCH(k_logdet_small<3>, dim3((unsigned)blocks), dim3(256), smem, st, orb, n, D, C, DB, det_sign, det_logabs, det_grad, det_lap);
-    else JQ_LAUNCH(k_logdet_small<2>, dim3((unsigned)blocks), dim3(256), smem, st, orb, n, D, C, DB, det_sign, det_logabs, det_grad, det_lap);
+    // launched through named pointers: JQ_LAUNCH labels the profile entry with its first argument
+    auto k_logdet_small_staged = k_logdet_small<2, true>;
+    auto k_logdet_small_ns1 = k_logdet_small<1, false>;
+    auto k_logdet_small_ns2 = k_logdet_small<2, false>;
+    auto k_logdet_small_ns3 = k_logdet_small<3, false>;
+    if (staged) JQ_LAUNCH(k_logdet_small_staged, dim3((unsigned)blocks), dim3(256), smem, st, orb, n, D, C, DB, det_sign, det_logabs, det_grad, det_lap);
+    else if (NS == 1) JQ_LAUNCH(k_logdet_small_ns1, dim3((unsigned)blocks), dim3(256), smem, st, orb, n, D, C, DB, det_sign, det_logabs, det_grad, det_lap);
+    else if (NS == 3) JQ_LAUNCH(k_logdet_small_ns3, dim3((unsigned)blocks), dim3(256), smem, st, orb, n, D, C, DB, det_sign, det_logabs, det_grad, det_lap);
+    else JQ_LAUNCH(k_logdet_small_ns2, dim3((unsigned)blocks), dim3(256), smem, st, orb, n, D, C, DB, det_sign, det_logabs, det_grad, det_lap);
     JQ_CHECK_LAUNCH();
     return JQ_OK;
   }
