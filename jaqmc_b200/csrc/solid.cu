@@ -487,6 +487,95 @@ __global__ void k_logdet_combine_c(const float* __restrict__ det_ld, const float
   }
 }
 
+#ifndef JAQMC_HOST_EMU
+// The same reduction with one WARP per walker (D <= 32; r2): lane d holds determinant d's weight
+// w_d = exp(ld_d - lmax) / sum, the lanes stride over the 3n derivative components and make ONE pass over det_grad
+// (coalesced float2 reads), accumulating grad_k = sum_d w_d g_dk and sum_d w_d g_dk^2 together.  The thread-per-walker
+// kernel above took 0.80 ms for a 512-walker shard of LiH 2x2x2 (8 blocks of 64 threads, exp / sincos recomputed in the
+// inner loop); the sums over k are taken in a different order, so results agree to rounding, not bit for bit.
+__global__ void __launch_bounds__(256) k_logdet_combine_c_warp(const float* __restrict__ det_ld,
+                                                               const float* __restrict__ det_grad,
+                                                               const float* __restrict__ det_lap, int W, int n, int D,
+                                                               int track, float* __restrict__ logpsi_re,
+                                                               float* __restrict__ logpsi_im, float* __restrict__ grad,
+                                                               float* __restrict__ lap, float* __restrict__ e_kin) {
+  const unsigned full = 0xffffffffu;
+  const int K = 3 * n;
+  const int lane = threadIdx.x & 31;
+  const long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (w >= W) return;
+  const bool has = lane < D;
+  const float lr_d = has ? det_ld[(w * D + lane) * 2] : -INFINITY;
+  const float li_d = has ? det_ld[(w * D + lane) * 2 + 1] : 0.f;
+  float lmax = lr_d;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) lmax = fmaxf(lmax, __shfl_xor_sync(full, lmax, o));
+  float er = 0.f, ei = 0.f;
+  if (has) {
+    const float m = expf(lr_d - lmax);
+    float sn, cs;
+    sincosf_(li_d, &sn, &cs);
+    er = m * cs;
+    ei = m * sn;
+  }
+  float sr = er, si = ei;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    sr += __shfl_xor_sync(full, sr, o);
+    si += __shfl_xor_sync(full, si, o);
+  }
+  const float s2 = sr * sr + si * si;
+  if (lane == 0) {
+    logpsi_re[w] = 0.5f * logf(s2) + lmax;
+    logpsi_im[w] = atan2f(si, sr);
+  }
+  if (!track) return;
+  const float inv2 = 1.0f / s2;
+  const float wr_d = (er * sr + ei * si) * inv2, wi_d = (ei * sr - er * si) * inv2;   // exp(ld_d - lmax) / s
+  // sum_d w_d lap_d (lane d's term), then + sum_d w_d sum_k g_dk^2 below
+  float alr = 0.f, ali = 0.f;
+  if (has) {
+    const float qr = det_lap[(w * D + lane) * 2], qi = det_lap[(w * D + lane) * 2 + 1];
+    alr = wr_d * qr - wi_d * qi;
+    ali = wr_d * qi + wi_d * qr;
+  }
+  const float2* g = reinterpret_cast<const float2*>(det_grad) + w * D * K;
+  float2* gout = reinterpret_cast<float2*>(grad) + w * K;
+  float ggr = 0.f, ggi = 0.f;
+  for (int k0 = 0; k0 < K; k0 += 32) {
+    const int k = k0 + lane;
+    const bool kv = k < K;
+    float gr = 0.f, gi = 0.f;
+    for (int d = 0; d < D; ++d) {
+      const float wr = __shfl_sync(full, wr_d, d), wi = __shfl_sync(full, wi_d, d);
+      const float2 x = kv ? g[d * K + k] : make_float2(0.f, 0.f);
+      gr += wr * x.x - wi * x.y;
+      gi += wr * x.y + wi * x.x;
+      const float x2r = x.x * x.x - x.y * x.y, x2i = 2.f * x.x * x.y;
+      alr += wr * x2r - wi * x2i;
+      ali += wr * x2i + wi * x2r;
+    }
+    if (kv) gout[k] = make_float2(gr, gi);
+    ggr += gr * gr - gi * gi;
+    ggi += 2.f * gr * gi;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    alr += __shfl_xor_sync(full, alr, o);
+    ali += __shfl_xor_sync(full, ali, o);
+    ggr += __shfl_xor_sync(full, ggr, o);
+    ggi += __shfl_xor_sync(full, ggi, o);
+  }
+  if (lane == 0) {
+    const float lr = alr - ggr, li = ali - ggi;
+    lap[2 * w] = lr;
+    lap[2 * w + 1] = li;
+    e_kin[2 * w] = -0.5f * (lr + ggr);
+    e_kin[2 * w + 1] = -0.5f * (li + ggi);
+  }
+}
+#endif
+
 // ------------------------------------------------------------------------------------------------
 // pipeline
 // ------------------------------------------------------------------------------------------------
@@ -620,6 +709,13 @@ int jq_solid_forward(const jaqmc_solid_config* c, const jaqmc_solid_params* p, c
               b.det_grad, b.det_lap, plain_staging);
     JQ_CHECK_LAUNCH();
   }
+#ifndef JAQMC_HOST_EMU
+  static const bool combine_thread = getenv("JAQMC_B200_COMBINE_C_THREAD") != nullptr;   // A/B switch
+  if (d.D <= 32 && !combine_thread) {
+    JQ_LAUNCH(k_logdet_combine_c_warp, dim3((unsigned)jq_cdiv(W, 8)), dim3(256), 0, st, b.det_ld, b.det_grad, b.det_lap,
+              (int)W, n, d.D, track, out.logpsi_re, out.logpsi_im, out.grad, out.lap, out.e_kin);
+  } else
+#endif
   JQ_LAUNCH(k_logdet_combine_c, dim3(jq_cdiv(W, 64)), dim3(64), 0, st, b.det_ld, b.det_grad, b.det_lap, (int)W, n, d.D,
             track, out.logpsi_re, out.logpsi_im, out.grad, out.lap, out.e_kin);
   JQ_CHECK_LAUNCH();
