@@ -124,7 +124,7 @@ __global__ void k_solid_orb_factor(float* __restrict__ orb_r, float* __restrict_
 // real kernel (logdet.cu) in complex arithmetic: Gauss-Jordan with partial pivoting on |z|,
 //   log det = sum log|p| + i (sum arg p + pi * swaps),  M = A^-1 dA_c,  ld_J[c] = tr M,  ld_L = tr(A^-1 A_L) - sum_k tr(M_k^2).
 // Shared (floats): logabs[DB] arg[DB] (double) | inv_r inv_i [DB][nn] | colp_r colp_i [DB][n] | piv[DB][n] |
-//                  (J_r J_i invT_r invT_i [DB][n][NP4] first, r2) pv_r pv_i [DB] | trL_r trL_i t2_r t2_i [DB] | M_r M_i [DB][nn] |
+//                  (J_r J_i invT_r invT_i [DB][n][NP4], then M_r M_i [DB][MT] tile-major, first) pv_r pv_i [DB] | trL_r trL_i t2_r t2_i [DB] |
 //                  p1r p1i p2r p2i [DB][max(n, tiles)]
 // ------------------------------------------------------------------------------------------------
 __global__ void k_logdet_c(const float* __restrict__ orb_r, const float* __restrict__ orb_i, int n, int D, int C, int DB,
@@ -142,7 +142,16 @@ __global__ void k_logdet_c(const float* __restrict__ orb_r, const float* __restr
   float* J_i = J_r + (size_t)DB * n * NP4;
   float* invT_r = J_i + (size_t)DB * n * NP4;
   float* invT_i = invT_r + (size_t)DB * n * NP4;
-  float* inv_r = invT_i + (size_t)DB * n * NP4;
+  // M = A^-1 dA_c is kept TILE-major (r2, late): the 4 x 4 tile (ti, tj) of a determinant is 16 contiguous floats at
+  // ti * MS1 + tj * 20 -- a thread stores / re-reads its tile and reads the transposed tile (tj, ti) as float4s, and with
+  // strides 20 and MS1 = 20 nb + 4 both walks are bank-conflict free for nb = 8.  The row-major M cost 4-way conflicts
+  // on its 32 scalar stores and 4- / 8-way conflicts on the 64 scalar loads of the trace phase: half of the kernel's
+  // shared-memory wavefronts (ncu, LiH 2x2x2: 1000 wavefronts per warp and slab, 436 of them in the product loop).
+  const int nbt = (n + 3) >> 2;
+  const int MS1 = 20 * nbt + 4, MT = nbt * MS1;
+  float* M_r = invT_i + (size_t)DB * n * NP4;
+  float* M_i = M_r + (size_t)DB * MT;
+  float* inv_r = M_i + (size_t)DB * MT;
   float* inv_i = inv_r + (size_t)DB * nn;
   float* colp_r = inv_i + (size_t)DB * nn;
   float* colp_i = colp_r + DB * n;
@@ -153,10 +162,8 @@ __global__ void k_logdet_c(const float* __restrict__ orb_r, const float* __restr
   float* trL_i = trL_r + DB;
   float* t2_r = trL_i + DB;
   float* t2_i = t2_r + DB;
-  float* M_r = t2_i + DB;
-  float* M_i = M_r + (size_t)DB * nn;
   const int np_ = ((n + 3) / 4) * ((n + 3) / 4) > n ? ((n + 3) / 4) * ((n + 3) / 4) : n;   // per-tile partials
-  float* p1r = M_i + (size_t)DB * nn;
+  float* p1r = t2_i + DB;
   float* p1i = p1r + DB * np_;
   float* p2r = p1i + DB * np_;
   float* p2i = p2r + DB * np_;
@@ -304,11 +311,63 @@ __global__ void k_logdet_c(const float* __restrict__ orb_r, const float* __restr
     invT_i[(d * n + j) * NP4 + i] = inv_i[q];
   }
   __syncthreads();
-  for (int kk = 0; kk < KT; ++kk) {
-    // slab staging: 4-byte cp.async on the device (all of a thread's elements in flight together; the plain
-    // load -> store loop paid the global latency per element: 40 % of the real-valued kernel's stall samples, r2)
+  // ---- slab staging (r2, late).  mode 0: 16-byte cp.async chunks (4 consecutive orbitals of one (j, d) row) whose source /
+  // destination offsets are computed ONCE per thread, double-buffered one slab ahead -- the second buffer is the inv_r /
+  // inv_i region, dead after the transposed copy above (needs n % 4 == 0, i.e. NP4 == n, and 16-byte aligned rows).
+  // Before: 4-byte copies with three integer divisions per element (~2.2 k of the ~4.8 k instructions a thread issued per
+  // slab) and a wait for the slab's own global latency in every iteration.  mode 2 keeps that path, mode 1 plain loads.
 #ifndef JAQMC_HOST_EMU
-    if (!plain_staging) {
+  constexpr int LC_MAXCH = 8;
+  const int nq = n >> 2;
+  const int nch = n * db * nq;   // 16-byte chunks per slab and array
+  const bool vec = plain_staging == 0 && (n & 3) == 0 && (DN & 3) == 0 && nch <= LC_MAXCH * nt &&
+                   ((reinterpret_cast<uintptr_t>(orb_r) | reinterpret_cast<uintptr_t>(orb_i)) & 15) == 0;
+  int so[LC_MAXCH], dof[LC_MAXCH];
+  unsigned jb0r = 0, jb0i = 0, jb1r = 0, jb1i = 0;
+  if (vec) {
+#pragma unroll
+    for (int s = 0; s < LC_MAXCH; ++s) {
+      const int q = tid + s * nt;
+      const int j = q / (db * nq), r4 = q - j * (db * nq);
+      const int d = r4 / nq, i4 = r4 - d * nq;
+      so[s] = j * C * DN + d * n + 4 * i4;
+      dof[s] = 4 * ((d * n + j) * NP4 + 4 * i4);
+    }
+    jb0r = (unsigned)__cvta_generic_to_shared(J_r);
+    jb0i = (unsigned)__cvta_generic_to_shared(J_i);
+    jb1r = (unsigned)__cvta_generic_to_shared(inv_r);
+    jb1i = (unsigned)__cvta_generic_to_shared(inv_i);
+  }
+  auto stage_vec = [&](int slab) {
+    if (slab < KT) {
+      const float* sr_ = orb_r + base + (long long)(1 + slab) * DN;
+      const float* si_ = orb_i + base + (long long)(1 + slab) * DN;
+      const unsigned br = (slab & 1) ? jb1r : jb0r, bi = (slab & 1) ? jb1i : jb0i;
+#pragma unroll
+      for (int s = 0; s < LC_MAXCH; ++s)
+        if (tid + s * nt < nch) {
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(br + (unsigned)dof[s]), "l"(sr_ + so[s]) : "memory");
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(bi + (unsigned)dof[s]), "l"(si_ + so[s]) : "memory");
+        }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  if (vec) stage_vec(0);
+#else
+  const bool vec = false;
+#endif
+  for (int kk = 0; kk < KT; ++kk) {
+    const float* Jc_r = J_r;
+    const float* Jc_i = J_i;
+#ifndef JAQMC_HOST_EMU
+    if (vec) {
+      stage_vec(kk + 1);   // the other buffer: last read before the barriers that ended slab kk - 1
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+      if (kk & 1) {
+        Jc_r = inv_r;
+        Jc_i = inv_i;
+      }
+    } else if (plain_staging != 1) {
       const unsigned jr0 = (unsigned)__cvta_generic_to_shared(J_r), ji0 = (unsigned)__cvta_generic_to_shared(J_i);
       for (int q = tid; q < n * db * n; q += nt) {
         const int j = q / (db * n), r = q % (db * n);
@@ -335,8 +394,8 @@ __global__ void k_logdet_c(const float* __restrict__ orb_r, const float* __restr
       const int i0 = 4 * (t / nb), c0 = 4 * (t % nb);
       const float* tr = invT_r + (size_t)d * n * NP4 + i0;
       const float* ti = invT_i + (size_t)d * n * NP4 + i0;
-      const float* jr = J_r + (size_t)d * n * NP4 + c0;
-      const float* ji = J_i + (size_t)d * n * NP4 + c0;
+      const float* jr = Jc_r + (size_t)d * n * NP4 + c0;
+      const float* ji = Jc_i + (size_t)d * n * NP4 + c0;
       float ar[4][4], ai[4][4];
 #pragma unroll
       for (int a = 0; a < 4; ++a)
@@ -360,27 +419,44 @@ __global__ void k_logdet_c(const float* __restrict__ orb_r, const float* __restr
             ai[a][b] = fmaf(xi[a], yr[b], ai[a][b]);
           }
       }
+      float* mtr = M_r + (size_t)d * MT + (t / nb) * MS1 + (t % nb) * 20;
+      float* mti = M_i + (size_t)d * MT + (t / nb) * MS1 + (t % nb) * 20;
 #pragma unroll
-      for (int a = 0; a < 4; ++a)
-#pragma unroll
-        for (int b = 0; b < 4; ++b)
-          if (i0 + a < n && c0 + b < n) {
-            M_r[d * nn + (i0 + a) * n + c0 + b] = ar[a][b];
-            M_i[d * nn + (i0 + a) * n + c0 + b] = ai[a][b];
-          }
+      for (int a = 0; a < 4; ++a) {
+        float4 vr, vi;
+        vr.x = ar[a][0]; vr.y = ar[a][1]; vr.z = ar[a][2]; vr.w = ar[a][3];
+        vi.x = ai[a][0]; vi.y = ai[a][1]; vi.z = ai[a][2]; vi.w = ai[a][3];
+        *reinterpret_cast<float4*>(mtr + 4 * a) = vr;
+        *reinterpret_cast<float4*>(mti + 4 * a) = vi;
+      }
     }
     __syncthreads();
     for (int q = tid; q < db * tiles; q += nt) {
       const int d = q / tiles, t = q % tiles;
       const int i0 = 4 * (t / nb), c0 = 4 * (t % nb);
-      const float* mr = M_r + d * nn;
-      const float* mi = M_i + d * nn;
+      const int ti = t / nb, tj = t % nb;
+      const float* own_r = M_r + (size_t)d * MT + ti * MS1 + tj * 20;
+      const float* own_i = M_i + (size_t)d * MT + ti * MS1 + tj * 20;
+      const float* tp_r = M_r + (size_t)d * MT + tj * MS1 + ti * 20;   // the transposed tile (tj, ti)
+      const float* tp_i = M_i + (size_t)d * MT + tj * MS1 + ti * 20;
+      float xr_[4][4], xi_[4][4], yr_[4][4], yi_[4][4];
+#pragma unroll
+      for (int a = 0; a < 4; ++a) {
+        const float4 v0 = *reinterpret_cast<const float4*>(own_r + 4 * a), v1 = *reinterpret_cast<const float4*>(own_i + 4 * a);
+        const float4 v2 = *reinterpret_cast<const float4*>(tp_r + 4 * a), v3 = *reinterpret_cast<const float4*>(tp_i + 4 * a);
+        xr_[a][0] = v0.x; xr_[a][1] = v0.y; xr_[a][2] = v0.z; xr_[a][3] = v0.w;
+        xi_[a][0] = v1.x; xi_[a][1] = v1.y; xi_[a][2] = v1.z; xi_[a][3] = v1.w;
+        yr_[a][0] = v2.x; yr_[a][1] = v2.y; yr_[a][2] = v2.z; yr_[a][3] = v2.w;
+        yi_[a][0] = v3.x; yi_[a][1] = v3.y; yi_[a][2] = v3.z; yi_[a][3] = v3.w;
+      }
       float s1r = 0.f, s1i = 0.f, s2r = 0.f, s2i = 0.f;
+#pragma unroll
       for (int a = 0; a < 4; ++a)
+#pragma unroll
         for (int b = 0; b < 4; ++b) {
           const int i = i0 + a, i2 = c0 + b;
           if (i >= n || i2 >= n) continue;
-          const float xr = mr[i * n + i2], xi = mi[i * n + i2], yr = mr[i2 * n + i], yi = mi[i2 * n + i];
+          const float xr = xr_[a][b], xi = xi_[a][b], yr = yr_[b][a], yi = yi_[b][a];   // M[i][i2], M[i2][i]
           s2r += xr * yr - xi * yi;
           s2i += xr * yi + xi * yr;
           if (i == i2) {
@@ -394,6 +470,40 @@ __global__ void k_logdet_c(const float* __restrict__ orb_r, const float* __restr
       p2i[q] = s2i;
     }
     __syncthreads();
+#ifndef JAQMC_HOST_EMU
+    // one warp per determinant sums the tile partials (lanes stride over the tiles, then a shuffle tree: fixed order);
+    // only lane 0 of that warp ever touches t2 / trL of the determinant, and the partial arrays are rewritten two
+    // barriers into the next slab, so no barrier is needed after this phase.  (Before: db threads summed tiles x 4
+    // partials serially while the block waited.)
+    for (int d = tid >> 5; d < db; d += nt >> 5) {
+      const int lane = tid & 31;
+      float s1r = 0.f, s1i = 0.f, s2r = 0.f, s2i = 0.f;
+      for (int t = lane; t < tiles; t += 32) {
+        s1r += p1r[d * tiles + t];
+        s1i += p1i[d * tiles + t];
+        s2r += p2r[d * tiles + t];
+        s2i += p2i[d * tiles + t];
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        s1r += __shfl_xor_sync(0xffffffffu, s1r, o);
+        s1i += __shfl_xor_sync(0xffffffffu, s1i, o);
+        s2r += __shfl_xor_sync(0xffffffffu, s2r, o);
+        s2i += __shfl_xor_sync(0xffffffffu, s2i, o);
+      }
+      if (lane == 0) {
+        if (kk < K) {
+          det_grad[((w * D + d0 + d) * K + kk) * 2] = s1r;
+          det_grad[((w * D + d0 + d) * K + kk) * 2 + 1] = s1i;
+          t2_r[d] += s2r;
+          t2_i[d] += s2i;
+        } else {
+          trL_r[d] = s1r;
+          trL_i[d] = s1i;
+        }
+      }
+    }
+#else
     for (int d = tid; d < db; d += nt) {
       float s1r = 0.f, s1i = 0.f, s2r = 0.f, s2i = 0.f;
       for (int t = 0; t < tiles; ++t) {
@@ -413,7 +523,12 @@ __global__ void k_logdet_c(const float* __restrict__ orb_r, const float* __restr
       }
     }
     __syncthreads();
+#endif
   }
+#ifndef JAQMC_HOST_EMU
+  if (vec) asm volatile("cp.async.wait_group 0;" ::: "memory");
+#endif
+  __syncthreads();
   for (int d = tid; d < db; d += nt) {
     det_lap[(w * D + d0 + d) * 2] = trL_r[d] - t2_r[d];
     det_lap[(w * D + d0 + d) * 2 + 1] = trL_i[d] - t2_i[d];
@@ -606,7 +721,8 @@ size_t logdet_c_smem(int db, int n) {
   const size_t nb = (size_t)(n + 3) / 4;
   const size_t np = nb * nb > (size_t)n ? nb * nb : (size_t)n;
   const size_t np4 = (size_t)((n + 3) & ~3);
-  return 16 * (size_t)db + sizeof(float) * (4 * db * nn + 4 * (size_t)db * n * np4 + 3 * (size_t)db * n + 4 * (size_t)db * np + 6 * (size_t)db) + 32;
+  const size_t mt = nb * (20 * nb + 4);   // tile-major M (see k_logdet_c)
+  return 16 * (size_t)db + sizeof(float) * (2 * db * nn + 2 * db * mt + 4 * (size_t)db * n * np4 + 3 * (size_t)db * n + 4 * (size_t)db * np + 6 * (size_t)db) + 32;
 }
 }  // namespace
 
@@ -691,7 +807,7 @@ int jq_solid_forward(const jaqmc_solid_config* c, const jaqmc_solid_params* p, c
     int DB = d.D;
     // several resident blocks per SM hide each other's slab loads and barriers: at most ~72 KB per block
     // (n = 32: two determinants, 128 register tiles, 128 threads)
-    while (DB > 1 && logdet_c_smem(DB, n) > 72 * 1024) DB = (DB + 1) / 2;
+    while (DB > 1 && logdet_c_smem(DB, n) > 74 * 1024) DB = (DB + 1) / 2;   // three blocks per SM: 3 x (74 + 1) KB <= 228 KB
     size_t smem = logdet_c_smem(DB, n);
     JQ_REQUIRE(smem <= 200 * 1024, JQ_ERR_UNSUPPORTED, "solid: %d electrons need %zu bytes of shared memory", n, smem);
 #ifndef JAQMC_HOST_EMU
@@ -704,7 +820,8 @@ int jq_solid_forward(const jaqmc_solid_config* c, const jaqmc_solid_params* p, c
     jq_prof_work((double)W * d.D * 8.0 * n * n * n * (track ? 2 * (d.C - 1) + 1 : 0.34), 8.0 * (double)W * d.D * d.C * n * n);
     const int tiles_blk = DB * ((n + 3) / 4) * ((n + 3) / 4);
     const int nthr = (track && tiles_blk <= 128) ? 128 : 256;
-    static const int plain_staging = getenv("JAQMC_B200_LOGDET_PLAIN_STAGING") != nullptr;   // A/B switch
+    // A/B switches: 1 = plain load / store staging, 2 = 4-byte cp.async staging (r2's first version), 0 = default
+    static const int plain_staging = getenv("JAQMC_B200_LOGDET_PLAIN_STAGING") ? 1 : getenv("JAQMC_B200_LOGDET_C_SCALAR_STAGING") ? 2 : 0;
     JQ_LAUNCH(k_logdet_c, dim3((unsigned)blocks), dim3(nthr), smem, st, b.orb_r, b.orb_i, n, d.D, d.C, DB, b.det_ld,
               b.det_grad, b.det_lap, plain_staging);
     JQ_CHECK_LAUNCH();
