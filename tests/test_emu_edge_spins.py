@@ -14,14 +14,14 @@ F64 = torch.float64
 CASES = [((1, 0), 1.0), ((0, 2), 2.0), ((3, 0), 3.0), ((0, 1), 1.0)]
 
 
-def setup(nspins, charge, kind, device="cpu", W=4, seed=0):
+def setup(nspins, charge, kind, device="cpu", W=4, seed=0, ndets=3):
     atoms = torch.zeros(1, 3, dtype=F64)
     charges = torch.tensor([charge], dtype=F64)
     el = H.synthetic_walkers(atoms, charges, nspins, W, seed=seed)
     if kind == "ferminet":
         hs, hd = (16, 16), (8, 8)
-        p64 = H.round_f32(ON.init_ferminet_params(nspins, 1, 3, hs, hd, seed=seed + 1))
-        wf = M.ferminet_handle(H.to_f32(p64, device), nspins, 1, 3, hs, hd, "abs_isotropic", True)
+        p64 = H.round_f32(ON.init_ferminet_params(nspins, 1, ndets, hs, hd, seed=seed + 1))
+        wf = M.ferminet_handle(H.to_f32(p64, device), nspins, 1, ndets, hs, hd, "abs_isotropic", True)
         fn = lambda e: ON.ferminet_logpsi(p64, e, atoms, nspins)  # noqa: E731
     elif kind == "psiformer":
         p64 = H.round_f32(ON.init_psiformer_params(nspins, 1, 3, 2, 2, 8, (16,), seed=seed + 5))
@@ -35,8 +35,8 @@ def setup(nspins, charge, kind, device="cpu", W=4, seed=0):
     return wf, sysh, el, atoms, charges, fn
 
 
-def check(rt, nspins, charge, kind, device="cpu"):
-    wf, sysh, el, atoms, charges, fn = setup(nspins, charge, kind, device)
+def check(rt, nspins, charge, kind, device="cpu", ndets=3):
+    wf, sysh, el, atoms, charges, fn = setup(nspins, charge, kind, device, ndets=ndets)
     e32 = el.float().contiguous().to(device)
     out = {k: v.cpu().numpy() for k, v in rt.local_energy(wf, sysh, e32).items()}
     ref = H.oracle_batch(fn, el, atoms, charges)
