@@ -328,7 +328,7 @@ int jaqmc_b200_local_energy_complex(const jaqmc_wavefunction* wf, const jaqmc_sy
  *   grads[leaf] = sum_w cotangent[w] * d log|psi|(x_w) / d leaf        (every leaf of `grads` is OVERWRITTEN),
  * so that LossAndGrad's `grads` is the call with cotangent[w] = 2 (E_clip[w] - mean E_clip) / W and the mean score the
  * call with 1 / W; the W x P per-walker score tensor of the reference is never formed.  Also returns log|psi| / sign of
- * the walkers (either may be NULL).  FermiNet kind, n <= 16 electrons, isotropic / abs_isotropic / null envelope.
+ * the walkers (either may be NULL).  FermiNet kind, n <= 32 electrons, isotropic / abs_isotropic / null envelope.
  * Needs the whole workspace of jaqmc_b200_ferminet_vjp_workspace_bytes (activations are kept; no walker tiling).
  * Results are bit-reproducible (row reductions are split and summed in a fixed order). */
 size_t jaqmc_b200_ferminet_vjp_workspace_bytes(const jaqmc_ferminet_config* config, int64_t n_walkers);

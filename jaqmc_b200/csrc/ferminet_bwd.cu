@@ -12,7 +12,7 @@
 // with every activation kept.  Reverse: dense layers by  dX = dZ W^T  (the forward dense kernels on the transposed
 // weights, tcgen05 where the shape allows) and  dW = X^T dZ  (row-reduction GEMM, split over row chunks and reduced in a
 // fixed order: bit-reproducible); tanh / residual / spin-mean / pair-mean adjoints elementwise; the determinant head by
-// d log|det M| / dM = M^-T weighted with the log-sum-exp weights.  n <= 16 electrons (in-thread inversion).
+// d log|det M| / dM = M^-T weighted with the log-sum-exp weights.  n <= 32 electrons (half-warp / warp inversion in registers).
 #include "wf.cuh"
 
 namespace {
@@ -51,7 +51,7 @@ __global__ void k_mul(const float* __restrict__ a, const float* __restrict__ b, 
 
 // One item per matrix (walker, determinant): Gauss-Jordan with partial pivoting on a local copy.
 //   M[w][e][d*n + o]  ->  minv[w][d][o][e] = (M_d^-1)[o][e],  sign, log|det|
-#define BW_NMAX 16
+#define BW_NMAX 32   // r2, late: 16 before (a full warp per matrix for 17 ... 32 electrons)
 __global__ void k_minv(const float* __restrict__ M, long long MT, int n, int D, float* __restrict__ minv,
                        float* __restrict__ sign, float* __restrict__ logabs) {
   for (long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x; m < MT; m += (long long)gridDim.x * blockDim.x) {
@@ -116,22 +116,24 @@ __global__ void k_minv(const float* __restrict__ M, long long MT, int n, int D, 
 // rows not used yet -- the same choice as the row-swapping elimination above -- and row p of A^-1 is the right half of
 // the row that served as pivot p.  The thread-per-matrix kernel kept 2 KB of local arrays per thread and ran with 256
 // blocks of 64 threads: 1.50 ms of a 10.5 ms reverse pass (ncu, N2, 4096 walkers).
+// G lanes per matrix: 16 (two matrices per warp, n <= 16) or 32 (one per warp, n <= 32).
+template <int G>
 __global__ void __launch_bounds__(256) k_minv_small(const float* __restrict__ M, long long MT, int n, int D,
                                                     float* __restrict__ minv, float* __restrict__ sign,
                                                     float* __restrict__ logabs) {
   const unsigned full = 0xffffffffu;
-  const int lane = threadIdx.x & 31, half = lane >> 4, hl = lane & 15;
-  const long long m0 = ((long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 2 + half;
+  const int lane = threadIdx.x & 31, half = lane / G, hl = lane & (G - 1);
+  const long long m0 = ((long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * (32 / G) + half;
   const bool on = m0 < MT;
   const long long m = on ? m0 : MT - 1;
   const long long w = m / D;
   const int d = (int)(m - w * D);
   bool used = !on || hl >= n;
-  float a[BW_NMAX], bi[BW_NMAX];
+  float a[G], bi[G];
   {
     const float* row = M + (w * n + (hl < n ? hl : 0)) * (long long)D * n + d * n;
 #pragma unroll
-    for (int c = 0; c < BW_NMAX; ++c) {
+    for (int c = 0; c < G; ++c) {
       a[c] = (!used && c < n) ? row[c] : 0.f;
       bi[c] = (c == hl) ? 1.0f : 0.f;
     }
@@ -141,15 +143,15 @@ __global__ void __launch_bounds__(256) k_minv_small(const float* __restrict__ M,
   double mant = 1.0;
   int expo = 0;
 #pragma unroll
-  for (int p = 0; p < BW_NMAX; ++p) {
+  for (int p = 0; p < G; ++p) {
     if (p < n) {
       const unsigned key = used ? 0u : __float_as_uint(fabsf(a[p]));
       unsigned mx = key;
 #pragma unroll
-      for (int o = 8; o > 0; o >>= 1) mx = max(mx, __shfl_xor_sync(full, mx, o));
-      const unsigned cand = (__ballot_sync(full, !used && key == mx) >> (16 * half)) & 0xffffu;
+      for (int o = G / 2; o > 0; o >>= 1) mx = max(mx, __shfl_xor_sync(full, mx, o));
+      const unsigned cand = (__ballot_sync(full, !used && key == mx) >> (G * half)) & (G == 32 ? 0xffffffffu : 0xffffu);
       const int pl = cand ? __ffs(cand) - 1 : 0;
-      const float pv = __shfl_sync(full, a[p], pl, 16);
+      const float pv = __shfl_sync(full, a[p], pl, G);
       if (pv < 0.f) sg = -sg;
       if (pv == 0.f) sg = 0.f;
       {
@@ -165,10 +167,10 @@ __global__ void __launch_bounds__(256) k_minv_small(const float* __restrict__ M,
       }
       const float f = is_p ? 0.f : a[p];
 #pragma unroll
-      for (int c = 0; c < BW_NMAX; ++c)
+      for (int c = 0; c < G; ++c)
         if (c < n) {
-          const float ap = __shfl_sync(full, a[c], pl, 16) * pinv;
-          const float bp = __shfl_sync(full, bi[c], pl, 16) * pinv;
+          const float ap = __shfl_sync(full, a[c], pl, G) * pinv;
+          const float bp = __shfl_sync(full, bi[c], pl, G) * pinv;
           if (is_p) {
             a[c] = ap;
             bi[c] = bp;
@@ -181,15 +183,15 @@ __global__ void __launch_bounds__(256) k_minv_small(const float* __restrict__ M,
   }
   int invc = 0;
   for (int i = 0; i < n; ++i) {
-    const int si = __shfl_sync(full, step_of, i, 16);
+    const int si = __shfl_sync(full, step_of, i, G);
     if (i < hl && hl < n && si > step_of) ++invc;
   }
 #pragma unroll
-  for (int o = 8; o > 0; o >>= 1) invc += __shfl_xor_sync(full, invc, o);
+  for (int o = G / 2; o > 0; o >>= 1) invc += __shfl_xor_sync(full, invc, o);
   if (on && hl < n) {
     float* dst = minv + (m * n + step_of) * n;
 #pragma unroll
-    for (int c = 0; c < BW_NMAX; ++c)
+    for (int c = 0; c < G; ++c)
       if (c < n) dst[c] = bi[c];
   }
   if (on && hl == 0) {
@@ -847,7 +849,13 @@ extern "C" int jaqmc_b200_ferminet_logpsi_vjp(const jaqmc_ferminet_config* c, co
     Mv = b.M;
   }
 #ifndef JAQMC_HOST_EMU
-  JQ_LAUNCH(k_minv_small, dim3((unsigned)jq_cdiv(W * d.D, 16)), dim3(256), 0, st, Mv, W * d.D, n, d.D, b.minv, b.dsign, b.dlogabs);
+  if (n <= 16) {
+    auto k_minv_halfwarp = k_minv_small<16>;
+    JQ_LAUNCH(k_minv_halfwarp, dim3((unsigned)jq_cdiv(W * d.D, 16)), dim3(256), 0, st, Mv, W * d.D, n, d.D, b.minv, b.dsign, b.dlogabs);
+  } else {
+    auto k_minv_warp = k_minv_small<32>;
+    JQ_LAUNCH(k_minv_warp, dim3((unsigned)jq_cdiv(W * d.D, 8)), dim3(256), 0, st, Mv, W * d.D, n, d.D, b.minv, b.dsign, b.dlogabs);
+  }
 #else
   JQ_LAUNCH(k_minv, dim3(grid_for(W * d.D)), dim3(64), 0, st, Mv, W * d.D, n, d.D, b.minv, b.dsign, b.dlogabs);
 #endif

@@ -78,6 +78,7 @@ def _flat(tree, prefix=""):
     ("He", 4, (12, 12, 12), (6, 6, 6), dict(envelope="isotropic")),
     ("LiH", 3, (16, 16), (8, 8), dict(envelope="null")),
     ("Li", 2, (16,), (8,), {}),                                    # one layer: no two-electron layer at all
+    ("Ar", 2, (16, 16), (8, 8), {}),                               # 18 electrons: the warp-per-matrix inversion (17 ... 32)
 ])
 def test_ferminet_logpsi_vjp_matches_autograd(mol, ndets, hs, hd, kw):
     check_vjp(H.emu_runtime(), mol, ndets, hs, hd, 5, **kw)
