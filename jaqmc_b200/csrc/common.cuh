@@ -48,6 +48,11 @@ using std::isfinite;
 static inline float rsqrtf(float x) { return 1.0f / sqrtf(x); }
 static inline float __fdividef(float a, float b) { return a / b; }
 static inline void sincosf_(float x, float* s, float* c) { *s = sinf(x); *c = cosf(x); }
+// (a0, a1) += s * (y0, y1): two fmaf on the host; one packed FFMA2 on the device (below)
+static inline void jq_fma2(float& a0, float& a1, float s, float y0, float y1) {
+  a0 = fmaf(s, y0, a0);
+  a1 = fmaf(s, y1, a1);
+}
 static inline const char* cudaGetErrorString(int) { return "emu"; }
 static inline int cudaGetLastError() { return 0; }
 static inline int cudaMemsetAsync(void* p, int v, size_t n, cudaStream_t) { memset(p, v, n); return 0; }
@@ -78,6 +83,23 @@ static inline int cudaMemcpyAsyncD2D(void* d, const void* s, size_t n, cudaStrea
   extern __shared__ __align__(16) unsigned char jq_dyn_smem_[]; \
   type* name = reinterpret_cast<type*>(jq_dyn_smem_)
 static __device__ __forceinline__ void sincosf_(float x, float* s, float* c) { sincosf(x, s, c); }
+// (a0, a1) += s * (y0, y1) as ONE packed instruction (sm_100: fma.rn.f32x2 -> FFMA2 with a broadcast scalar operand; ptxas
+// folds the mov.b64 packing into register-pair allocation when y0 / y1 and a0 / a1 are adjacent, e.g. halves of a float4).
+// Two IEEE round-to-nearest FMAs: bit-identical to two fmaf, at half the issue slots -- for the issue-bound CUDA-core
+// contractions (r2, late).  -DJQ_NO_FFMA2 restores the scalar form (A/B).
+static __device__ __forceinline__ void jq_fma2(float& a0, float& a1, float s, float y0, float y1) {
+#ifdef JQ_NO_FFMA2
+  a0 = fmaf(s, y0, a0);
+  a1 = fmaf(s, y1, a1);
+#else
+  unsigned long long ss, yy, zz;
+  asm("mov.b64 %0, {%1, %1};" : "=l"(ss) : "f"(s));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(yy) : "f"(y0), "f"(y1));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(zz) : "f"(a0), "f"(a1));
+  asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(zz) : "l"(ss), "l"(yy));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(a0), "=f"(a1) : "l"(zz));
+#endif
+}
 static inline cudaError_t cudaMemcpyAsyncD2D(void* d, const void* s, size_t n, cudaStream_t st) {
   return cudaMemcpyAsync(d, s, n, cudaMemcpyDeviceToDevice, st);
 }

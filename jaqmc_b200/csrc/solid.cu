@@ -409,15 +409,18 @@ __global__ void k_logdet_c(const float* __restrict__ orb_r, const float* __restr
         const float4 yr4 = *reinterpret_cast<const float4*>(jr + j * NP4), yi4 = *reinterpret_cast<const float4*>(ji + j * NP4);
         const float xr[4] = {xr4.x, xr4.y, xr4.z, xr4.w}, xi[4] = {xi4.x, xi4.y, xi4.z, xi4.w};
         const float yr[4] = {yr4.x, yr4.y, yr4.z, yr4.w}, yi[4] = {yi4.x, yi4.y, yi4.z, yi4.w};
+        // packed FMAs over column pairs (b, b + 1): same operations and order per accumulator as the scalar form
 #pragma unroll
-        for (int a = 0; a < 4; ++a)
+        for (int a = 0; a < 4; ++a) {
+          const float nxi = -xi[a];
 #pragma unroll
-          for (int b = 0; b < 4; ++b) {
-            ar[a][b] = fmaf(xr[a], yr[b], ar[a][b]);
-            ar[a][b] = fmaf(-xi[a], yi[b], ar[a][b]);
-            ai[a][b] = fmaf(xr[a], yi[b], ai[a][b]);
-            ai[a][b] = fmaf(xi[a], yr[b], ai[a][b]);
+          for (int b = 0; b < 4; b += 2) {
+            jq_fma2(ar[a][b], ar[a][b + 1], xr[a], yr[b], yr[b + 1]);
+            jq_fma2(ar[a][b], ar[a][b + 1], nxi, yi[b], yi[b + 1]);
+            jq_fma2(ai[a][b], ai[a][b + 1], xr[a], yi[b], yi[b + 1]);
+            jq_fma2(ai[a][b], ai[a][b + 1], xi[a], yr[b], yr[b + 1]);
           }
+        }
       }
       float* mtr = M_r + (size_t)d * MT + (t / nb) * MS1 + (t % nb) * 20;
       float* mti = M_i + (size_t)d * MT + (t / nb) * MS1 + (t % nb) * 20;
