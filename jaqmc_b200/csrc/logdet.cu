@@ -1371,10 +1371,12 @@ int jq_launch_logdet(const float* orb, int W, int n, int D, int track, float* de
     const int NS = ns_env == 1 ? 1 : (ns_env == 3 ? 3 : 2);
     // staged slabs (cp.async, per-warp double buffer): n and D even, 16-byte aligned orbital buffer, default NS
     static const bool sync_loads = getenv("JAQMC_B200_LOGDET_SYNC_LOADS") != nullptr;   // A/B switch
+    const size_t smem_sync = sizeof(float) * ((size_t)DB * (n * LD_NP + 4) + (size_t)DB * MS * NS) + 64;
+    const size_t ring_bytes = sizeof(float) * (size_t)8 * 2 * NS * n * 2 * n;   // 8 warps x double buffer x NS slabs x [n][2n]
+    // (two blocks per SM need <= 112 KB each: 16 electrons x 16 determinants would take 117 KB and keeps the synchronous loads)
     const bool staged = NS == 2 && !sync_loads && n >= 6 && (n % 2) == 0 && (D % 2) == 0 &&
-                        (reinterpret_cast<uintptr_t>(orb) & 15) == 0;
-    const size_t smem = sizeof(float) * ((size_t)DB * (n * LD_NP + 4) + (size_t)DB * MS * NS +
-                                         (staged ? (size_t)8 * 2 * NS * n * 2 * n : 0)) + 64;
+                        (reinterpret_cast<uintptr_t>(orb) & 15) == 0 && smem_sync + ring_bytes <= 112 * 1024;
+    const size_t smem = smem_sync + (staged ? ring_bytes : 0);
     void (*kern)(const float*, int, int, int, int, float*, float*, float*, float*) =
         staged ? k_logdet_small<2, true>
                : NS == 1 ? k_logdet_small<1, false> : NS == 3 ? k_logdet_small<3, false> : k_logdet_small<2, false>;   // for the attribute call only

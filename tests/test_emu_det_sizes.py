@@ -17,6 +17,7 @@ CASES = [
     ((5, 5), 10.0, 3),   # n = 10 with an odd determinant count: synchronous loads
     ((6, 6), 12.0, 2),   # n = 12: staged, one warp busy
     ((8, 8), 16.0, 4),   # n = 16: staged, the largest half-warp size
+    ((8, 8), 16.0, 16),  # n = 16 with 16 determinants: the staging ring would not fit beside two blocks per SM -> synchronous loads
     ((9, 8), 17.0, 2),   # n = 17: block kernel
 ]
 IDS = ["n%d_d%d" % (c[0][0] + c[0][1], c[2]) for c in CASES]
